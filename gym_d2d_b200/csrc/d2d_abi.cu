@@ -1,0 +1,369 @@
+// d2d_abi.cu - the C ABI of libd2d_b200.so (include/d2d_b200.h): handle management, host-side folding of
+// the link-budget constants, and the kernel launches.  sm_100a only; there is no CPU path.
+#include "../../include/d2d_b200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "d2d_aux.cuh"
+#include "d2d_common.cuh"
+#include "d2d_step_block.cuh"
+#include "d2d_step_warp.cuh"
+
+static_assert(D2D_STATS_REPLICAS * 8 * sizeof(double) == 2048, "stats layout");
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define D2D_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t err__ = (call);                                                                 \
+        if (err__ != cudaSuccess)                                                                   \
+            return fail(D2D_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__));        \
+    } while (0)
+
+constexpr double kSpeedOfLight = 299792458.0;   // path_loss.py:9
+
+}  // namespace
+
+struct d2d_handle {
+    d2d_config_t cfg{};
+    int N = 0, V = 0;
+    int num_sms = 0;
+    bool ple2 = true;
+    bool use_warp = true;
+    int grid = 0, block = 0, smem = 0, envs_per_block = 0;
+    double K_dB = 0.0, ple = 2.0;
+    D2DLinkA *dA = nullptr;
+    D2DLinkB *dB = nullptr;
+    D2DLinkD *dD = nullptr;
+    float *dPwr = nullptr;
+    double *dPwrD = nullptr;
+    // bound state (caller-owned)
+    float *pos = nullptr;
+    uint8_t *step_count = nullptr;
+    double *stats = nullptr;
+    // staging for d2d_step_host / d2d_set_positions (handle-owned, allocated on first use)
+    void *stage[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double *stage_pos = nullptr;
+    int64_t stage_pos_envs = 0;
+    int64_t launches = 0;
+};
+
+namespace {
+
+int ensure_device(const d2d_handle *h) {
+    int cur = -1;
+    D2D_CUDA(cudaGetDevice(&cur));
+    if (cur != h->cfg.cuda_device) D2D_CUDA(cudaSetDevice(h->cfg.cuda_device));
+    return D2D_OK;
+}
+
+D2DParams make_params(const d2d_handle *h, const d2d_step_io_t *io) {
+    D2DParams P{};
+    P.num_envs = h->cfg.num_envs;
+    P.N = h->N; P.V = h->V; P.C = h->cfg.num_cues; P.R = h->cfg.num_rbs;
+    P.n_pwr_cue = h->cfg.n_pwr_cue; P.n_pwr_due = h->cfg.n_pwr_due;
+    P.episode_length = h->cfg.episode_length;
+    P.nbins = h->cfg.num_rbs;
+    P.ple = (float)h->ple;
+    P.neg_half_ple = (float)(-0.5 * h->ple);
+    P.snr_slope = (float)(5.0 * h->ple * std::log10(2.0));
+    P.min_cap = (float)h->cfg.min_capacity_mbps;
+    P.rescue_band_dB = h->ple2 ? 0.125f : 1.0f;
+    P.ple_d = h->ple;
+    P.linkA = h->dA; P.linkB = h->dB; P.linkD = h->dD; P.pwr_lin = h->dPwr; P.pwr_lin_d = h->dPwrD;
+    P.pos = h->pos; P.step_count = h->step_count; P.stats = h->stats;
+    P.actions = io->actions; P.obs = io->obs; P.cap = io->capacity_mbps; P.reward = io->reward;
+    P.done = io->done; P.rate = io->rate_bps; P.rb_out = io->rb; P.pwr_out = io->tx_pwr_dBm;
+    return P;
+}
+
+template <typename K>
+int plan_geometry(d2d_handle *h, K kernel, int block, size_t smem, int envs_per_block) {
+    if (smem > 48 * 1024)
+        D2D_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    D2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem));
+    if (occ < 1) return fail(D2D_ERR_UNSUPPORTED, "step kernel does not fit on an SM for this configuration");
+    const int64_t need = (h->cfg.num_envs + envs_per_block - 1) / envs_per_block;
+    const int64_t resident = (int64_t)h->num_sms * occ;
+    h->grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, resident));
+    h->block = block;
+    h->smem = (int)smem;
+    h->envs_per_block = envs_per_block;
+    return D2D_OK;
+}
+
+}  // namespace
+
+D2D_API int d2d_abi_version(void) { return D2D_ABI_VERSION; }
+
+D2D_API const char *d2d_last_error(void) { return g_last_error.c_str(); }
+
+D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_handle_t **out) {
+    if (!cfg || !links || !out) return fail(D2D_ERR_INVALID_ARG, "d2d_create: null argument");
+    *out = nullptr;
+    if (cfg->abi_version != D2D_ABI_VERSION) return fail(D2D_ERR_INVALID_ARG, "d2d_create: abi_version mismatch");
+    if (cfg->num_envs < 1) return fail(D2D_ERR_INVALID_ARG, "d2d_create: num_envs must be >= 1");
+    if (cfg->num_rbs < 1 || cfg->num_cues < 0 || cfg->num_due_pairs < 0 || cfg->num_cues + cfg->num_due_pairs < 1)
+        return fail(D2D_ERR_INVALID_ARG, "d2d_create: need num_rbs >= 1 and at least one link");
+    if (cfg->n_pwr_cue < 1 || cfg->n_pwr_due < 1 || cfg->n_pwr_cue > D2D_MAX_PWR_LEVELS || cfg->n_pwr_due > D2D_MAX_PWR_LEVELS)
+        return fail(D2D_ERR_UNSUPPORTED, "d2d_create: power levels per link must be in [1, 128]");
+    if (cfg->num_rbs > 32767) return fail(D2D_ERR_UNSUPPORTED, "d2d_create: num_rbs must be <= 32767");
+    if (cfg->path_loss_model != D2D_PL_LOG_DISTANCE && cfg->path_loss_model != D2D_PL_FREE_SPACE)
+        return fail(D2D_ERR_UNSUPPORTED, "d2d_create: unsupported path_loss_model (LogDistance / FreeSpace only)");
+    if (cfg->obs_fn != D2D_OBS_LINEAR) return fail(D2D_ERR_UNSUPPORTED, "d2d_create: unsupported obs_fn (LinearObsFunction only)");
+    if (cfg->reward_fn != D2D_REWARD_SYSTEM_CAPACITY)
+        return fail(D2D_ERR_UNSUPPORTED, "d2d_create: unsupported reward_fn (SystemCapacityRewardFunction only)");
+    if (!(cfg->carrier_freq_GHz > 0.0)) return fail(D2D_ERR_INVALID_ARG, "d2d_create: carrier_freq_GHz must be > 0");
+    const double ple = cfg->path_loss_model == D2D_PL_FREE_SPACE ? 2.0 : cfg->ple;
+    if (!(ple > 0.0) || ple > 8.0) return fail(D2D_ERR_INVALID_ARG, "d2d_create: ple must be in (0, 8]");
+    if (cfg->episode_length < 1 || cfg->episode_length > 255)
+        return fail(D2D_ERR_UNSUPPORTED, "d2d_create: episode_length must be in [1, 255]");
+
+    d2d_handle *h = new (std::nothrow) d2d_handle();
+    if (!h) return fail(D2D_ERR_INVALID_ARG, "d2d_create: out of host memory");
+    h->cfg = *cfg;
+    h->N = cfg->num_cues + cfg->num_due_pairs;
+    h->V = 1 + cfg->num_cues + 2 * cfg->num_due_pairs;
+    h->ple = ple;
+    h->ple2 = ple == 2.0;
+    if (h->N > 65535) { delete h; return fail(D2D_ERR_UNSUPPORTED, "d2d_create: at most 65535 links per env"); }
+    // path_loss.py:28-39
+    h->K_dB = 10.0 * ple * std::log10(cfg->carrier_freq_GHz * 1e9) + 10.0 * ple * std::log10((4.0 * M_PI) / kSpeedOfLight);
+
+    auto bail = [&](int code) { d2d_destroy(h); return code; };
+    cudaError_t e = cudaSetDevice(cfg->cuda_device);
+    if (e != cudaSuccess) return bail(fail(D2D_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e)));
+    cudaDeviceProp prop{};
+    e = cudaGetDeviceProperties(&prop, cfg->cuda_device);
+    if (e != cudaSuccess) return bail(fail(D2D_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e)));
+    if (prop.major != 10)
+        return bail(fail(D2D_ERR_UNSUPPORTED, "libd2d_b200 is built for sm_100a (Blackwell B200) only; device is sm_" +
+                                                  std::to_string(prop.major) + std::to_string(prop.minor)));
+    h->num_sms = prop.multiProcessorCount;
+
+    // fold the link-budget constants in fp64, store fp32 + fp64 copies
+    std::vector<D2DLinkA> A(h->N);
+    std::vector<D2DLinkB> B(h->N);
+    std::vector<D2DLinkD> Dv(h->N);
+    for (int j = 0; j < h->N; ++j) {
+        const d2d_link_t &L = links[j];
+        const bool cue = j < cfg->num_cues;
+        const int expect = cue ? D2D_LINK_UPLINK : D2D_LINK_SIDELINK;
+        if (L.link_type != expect)
+            return bail(fail(D2D_ERR_UNSUPPORTED, "d2d_create: link " + std::to_string(j) +
+                                                      " has an unsupported link_type (CUE uplinks then DUE sidelinks)"));
+        A[j].tx_lin0 = (float)std::pow(10.0, (L.tx_eirp_offset_dB - h->K_dB) / 10.0);
+        const double snr0 = L.tx_eirp_offset_dB + L.rx_offset_dB - h->K_dB - L.rx_noise_dBm;
+        A[j].a_lin = (float)std::pow(10.0, snr0 / 10.0);
+        A[j].inv_noise = (float)std::pow(10.0, -L.rx_noise_dBm / 10.0);
+        A[j].snr0_dB = (float)snr0;
+        B[j].sens_dBm = (float)L.rx_sensitivity_dBm;
+        B[j].bw_MHz = (float)(1e-6 * (L.tx_rb_bandwidth_kHz * 1000.0));
+        B[j].tx_dev = cue ? 1 + j : 1 + cfg->num_cues + 2 * (j - cfg->num_cues);
+        B[j].rx_dev = cue ? 0 : B[j].tx_dev + 1;
+        Dv[j].a_lin = std::pow(10.0, snr0 / 10.0);
+        Dv[j].t_lin = std::pow(10.0, (L.tx_eirp_offset_dB - h->K_dB) / 10.0);
+        Dv[j].inv_noise = std::pow(10.0, -L.rx_noise_dBm / 10.0);
+        Dv[j].bw_MHz = 1e-6 * (L.tx_rb_bandwidth_kHz * 1000.0);
+    }
+    float pwr[D2D_MAX_PWR_LEVELS];
+    double pwr_d[D2D_MAX_PWR_LEVELS];
+    for (int p = 0; p < D2D_MAX_PWR_LEVELS; ++p) {   // conversion.py:4-13
+        pwr_d[p] = std::pow(10.0, p / 10.0);
+        pwr[p] = (float)pwr_d[p];
+    }
+
+#define D2D_CUDA_BAIL(call)                                                                              \
+    do {                                                                                                 \
+        cudaError_t err__ = (call);                                                                      \
+        if (err__ != cudaSuccess)                                                                        \
+            return bail(fail(D2D_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__)));       \
+    } while (0)
+    D2D_CUDA_BAIL(cudaMalloc(&h->dA, sizeof(D2DLinkA) * h->N));
+    D2D_CUDA_BAIL(cudaMalloc(&h->dB, sizeof(D2DLinkB) * h->N));
+    D2D_CUDA_BAIL(cudaMalloc(&h->dD, sizeof(D2DLinkD) * h->N));
+    D2D_CUDA_BAIL(cudaMalloc(&h->dPwr, sizeof(pwr)));
+    D2D_CUDA_BAIL(cudaMalloc(&h->dPwrD, sizeof(pwr_d)));
+    D2D_CUDA_BAIL(cudaMemcpy(h->dPwrD, pwr_d, sizeof(pwr_d), cudaMemcpyHostToDevice));
+    D2D_CUDA_BAIL(cudaMemcpy(h->dA, A.data(), sizeof(D2DLinkA) * h->N, cudaMemcpyHostToDevice));
+    D2D_CUDA_BAIL(cudaMemcpy(h->dB, B.data(), sizeof(D2DLinkB) * h->N, cudaMemcpyHostToDevice));
+    D2D_CUDA_BAIL(cudaMemcpy(h->dD, Dv.data(), sizeof(D2DLinkD) * h->N, cudaMemcpyHostToDevice));
+    D2D_CUDA_BAIL(cudaMemcpy(h->dPwr, pwr, sizeof(pwr), cudaMemcpyHostToDevice));
+#undef D2D_CUDA_BAIL
+
+    h->use_warp = h->N <= D2D_WARP_MAX_LINKS;
+    int rc;
+    if (h->use_warp) {
+        rc = h->ple2 ? plan_geometry(h, d2d_step_warp_kernel<true>, D2D_WARP_WARPS_PER_BLOCK * 32, sizeof(D2DWarpSmem),
+                                     D2D_WARP_WARPS_PER_BLOCK)
+                     : plan_geometry(h, d2d_step_warp_kernel<false>, D2D_WARP_WARPS_PER_BLOCK * 32, sizeof(D2DWarpSmem),
+                                     D2D_WARP_WARPS_PER_BLOCK);
+    } else {
+        const size_t smem = d2d_block_smem_bytes(h->N, cfg->num_rbs);
+        if (smem > 227 * 1024) return bail(fail(D2D_ERR_UNSUPPORTED, "d2d_create: too many links / RBs for one SM's shared memory"));
+        rc = h->ple2 ? plan_geometry(h, d2d_step_block_kernel<true>, D2D_BLOCK_THREADS, smem, 1)
+                     : plan_geometry(h, d2d_step_block_kernel<false>, D2D_BLOCK_THREADS, smem, 1);
+    }
+    if (rc != D2D_OK) return bail(rc);
+    *out = h;
+    return D2D_OK;
+}
+
+D2D_API int d2d_destroy(d2d_handle_t *h) {
+    if (!h) return D2D_OK;
+    cudaFree(h->dA); cudaFree(h->dB); cudaFree(h->dD); cudaFree(h->dPwr); cudaFree(h->dPwrD); cudaFree(h->stage_pos);
+    for (void *p : h->stage) cudaFree(p);
+    delete h;
+    return D2D_OK;
+}
+
+D2D_API int d2d_state_bytes(const d2d_handle_t *h, size_t *pos_bytes, size_t *step_bytes, size_t *stats_bytes) {
+    if (!h) return fail(D2D_ERR_INVALID_ARG, "d2d_state_bytes: null handle");
+    if (pos_bytes) *pos_bytes = (size_t)h->cfg.num_envs * h->V * 2 * sizeof(float);
+    if (step_bytes) *step_bytes = (size_t)h->cfg.num_envs;
+    if (stats_bytes) *stats_bytes = (size_t)D2D_STATS_REPLICAS * 8 * sizeof(double);
+    return D2D_OK;
+}
+
+D2D_API int d2d_bind_state(d2d_handle_t *h, float *positions, uint8_t *step_count, double *stats) {
+    if (!h || !positions) return fail(D2D_ERR_INVALID_ARG, "d2d_bind_state: positions buffer is required");
+    if ((uintptr_t)positions % 16) return fail(D2D_ERR_INVALID_ARG, "d2d_bind_state: positions must be 16-byte aligned");
+    h->pos = positions;
+    h->step_count = step_count;
+    h->stats = stats;
+    return D2D_OK;
+}
+
+D2D_API int d2d_set_positions(d2d_handle_t *h, const double *src, int src_on_device, int64_t first_env, int64_t count,
+                              void *stream) {
+    if (!h || !src) return fail(D2D_ERR_INVALID_ARG, "d2d_set_positions: null argument");
+    if (!h->pos) return fail(D2D_ERR_STATE, "d2d_set_positions: call d2d_bind_state first");
+    if (first_env < 0 || count < 0 || first_env + count > h->cfg.num_envs)
+        return fail(D2D_ERR_INVALID_ARG, "d2d_set_positions: env range out of bounds");
+    if (count == 0) return D2D_OK;
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const double *dsrc = src;
+    if (!src_on_device) {
+        if (h->stage_pos_envs < count) {
+            cudaFree(h->stage_pos);
+            h->stage_pos = nullptr; h->stage_pos_envs = 0;
+            D2D_CUDA(cudaMalloc(&h->stage_pos, sizeof(double) * 2 * h->V * count));
+            h->stage_pos_envs = count;
+        }
+        D2D_CUDA(cudaMemcpyAsync(h->stage_pos, src, sizeof(double) * 2 * h->V * count, cudaMemcpyHostToDevice, st));
+        dsrc = h->stage_pos;
+    }
+    const int64_t total = count * h->V;
+    const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->num_sms * 8);
+    d2d_set_positions_kernel<<<grid, 256, 0, st>>>(dsrc, h->pos + first_env * h->V * 2, count, h->V);
+    D2D_CUDA(cudaGetLastError());
+    ++h->launches;
+    if (!src_on_device) D2D_CUDA(cudaStreamSynchronize(st));
+    return D2D_OK;
+}
+
+D2D_API int d2d_reset(d2d_handle_t *h, uint64_t seed, uint64_t first_global_env, const uint8_t *env_mask, void *stream) {
+    if (!h) return fail(D2D_ERR_INVALID_ARG, "d2d_reset: null handle");
+    if (!h->pos) return fail(D2D_ERR_STATE, "d2d_reset: call d2d_bind_state first");
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    const int64_t total = h->cfg.num_envs * h->N;
+    const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->num_sms * 16);
+    d2d_reset_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->pos, h->step_count, env_mask, h->cfg.num_envs, h->cfg.num_cues,
+                                                             h->cfg.num_due_pairs, (float)h->cfg.cell_radius_m,
+                                                             (float)h->cfg.d2d_radius_m, seed, first_global_env);
+    D2D_CUDA(cudaGetLastError());
+    ++h->launches;
+    return D2D_OK;
+}
+
+D2D_API int d2d_step(d2d_handle_t *h, const d2d_step_io_t *io, void *stream) {
+    if (!h || !io || !io->actions) return fail(D2D_ERR_INVALID_ARG, "d2d_step: handle, io and io->actions are required");
+    if (!h->pos) return fail(D2D_ERR_STATE, "d2d_step: call d2d_bind_state first");
+    if (io->obs && ((uintptr_t)io->obs % 8)) return fail(D2D_ERR_INVALID_ARG, "d2d_step: obs must be 8-byte aligned");
+    const D2DParams P = make_params(h, io);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->use_warp) {
+        if (h->ple2) d2d_step_warp_kernel<true><<<h->grid, h->block, h->smem, st>>>(P);
+        else d2d_step_warp_kernel<false><<<h->grid, h->block, h->smem, st>>>(P);
+    } else {
+        if (h->ple2) d2d_step_block_kernel<true><<<h->grid, h->block, h->smem, st>>>(P);
+        else d2d_step_block_kernel<false><<<h->grid, h->block, h->smem, st>>>(P);
+    }
+    D2D_CUDA(cudaGetLastError());
+    ++h->launches;
+    return D2D_OK;
+}
+
+D2D_API int d2d_step_host(d2d_handle_t *h, const d2d_step_io_t *hio, void *stream) {
+    if (!h || !hio || !hio->actions) return fail(D2D_ERR_INVALID_ARG, "d2d_step_host: handle, io and io->actions are required");
+    if (!h->pos) return fail(D2D_ERR_STATE, "d2d_step_host: call d2d_bind_state first");
+    int rc = ensure_device(h);
+    if (rc) return rc;
+    const size_t E = (size_t)h->cfg.num_envs, EN = E * h->N;
+    const size_t bytes[8] = {EN * 4, EN * 24, EN * 4, E * 4, E, EN * 4, EN * 2, EN * 2};
+    void *host[8] = {(void *)hio->actions, hio->obs, hio->capacity_mbps, hio->reward, hio->done, hio->rate_bps, hio->rb, hio->tx_pwr_dBm};
+    for (int i = 0; i < 8; ++i)
+        if (host[i] && !h->stage[i]) D2D_CUDA(cudaMalloc(&h->stage[i], bytes[i]));
+    cudaStream_t st = (cudaStream_t)stream;
+    D2D_CUDA(cudaMemcpyAsync(h->stage[0], host[0], bytes[0], cudaMemcpyHostToDevice, st));
+    d2d_step_io_t dio{};
+    dio.actions = (const int32_t *)h->stage[0];
+    dio.obs = hio->obs ? (float *)h->stage[1] : nullptr;
+    dio.capacity_mbps = hio->capacity_mbps ? (float *)h->stage[2] : nullptr;
+    dio.reward = hio->reward ? (float *)h->stage[3] : nullptr;
+    dio.done = hio->done ? (uint8_t *)h->stage[4] : nullptr;
+    dio.rate_bps = hio->rate_bps ? (float *)h->stage[5] : nullptr;
+    dio.rb = hio->rb ? (int16_t *)h->stage[6] : nullptr;
+    dio.tx_pwr_dBm = hio->tx_pwr_dBm ? (int16_t *)h->stage[7] : nullptr;
+    rc = d2d_step(h, &dio, stream);
+    if (rc) return rc;
+    for (int i = 1; i < 8; ++i)
+        if (host[i]) D2D_CUDA(cudaMemcpyAsync(host[i], h->stage[i], bytes[i], cudaMemcpyDeviceToHost, st));
+    D2D_CUDA(cudaStreamSynchronize(st));
+    return D2D_OK;
+}
+
+D2D_API int d2d_per_agent_obs(d2d_handle_t *h, const float *table, float *out, int64_t num_envs, void *stream) {
+    if (!h || !table || !out) return fail(D2D_ERR_INVALID_ARG, "d2d_per_agent_obs: null argument");
+    if (num_envs < 0 || num_envs > h->cfg.num_envs) return fail(D2D_ERR_INVALID_ARG, "d2d_per_agent_obs: bad num_envs");
+    if (num_envs == 0) return D2D_OK;
+    if (num_envs * h->N > 0x7fffffffLL) return fail(D2D_ERR_UNSUPPORTED, "d2d_per_agent_obs: num_envs * N exceeds the grid limit");
+    d2d_per_agent_obs_kernel<<<(unsigned)(num_envs * h->N), 128, 0, (cudaStream_t)stream>>>(table, out, h->N);
+    D2D_CUDA(cudaGetLastError());
+    ++h->launches;
+    return D2D_OK;
+}
+
+D2D_API int d2d_stats_reset(d2d_handle_t *h, void *stream) {
+    if (!h) return fail(D2D_ERR_INVALID_ARG, "d2d_stats_reset: null handle");
+    if (!h->stats) return fail(D2D_ERR_STATE, "d2d_stats_reset: no stats buffer bound");
+    D2D_CUDA(cudaMemsetAsync(h->stats, 0, (size_t)D2D_STATS_REPLICAS * 8 * sizeof(double), (cudaStream_t)stream));
+    return D2D_OK;
+}
+
+D2D_API int64_t d2d_launch_count(const d2d_handle_t *h) { return h ? h->launches : -1; }
+
+D2D_API int d2d_step_geometry(const d2d_handle_t *h, int32_t *grid, int32_t *block, int32_t *smem_bytes, int32_t *envs_per_block) {
+    if (!h) return fail(D2D_ERR_INVALID_ARG, "d2d_step_geometry: null handle");
+    if (grid) *grid = h->grid;
+    if (block) *block = h->block;
+    if (smem_bytes) *smem_bytes = h->smem;
+    if (envs_per_block) *envs_per_block = h->envs_per_block;
+    return D2D_OK;
+}

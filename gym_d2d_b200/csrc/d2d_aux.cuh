@@ -1,0 +1,88 @@
+// d2d_aux.cuh - the kernels either side of the step: position upload, device-side reset, and the
+// optional per-agent observation materialisation.
+#pragma once
+
+#include "d2d_common.cuh"
+
+// Device.set_position over a batch (device.py:82-83): float64 [count][V][2] -> float32 state.
+// Device 0 (the MBS) is pinned to the origin like simulator.py:63-64.
+__global__ void d2d_set_positions_kernel(const double *__restrict__ src, float *__restrict__ dst, int64_t count, int V) {
+    const int64_t total = count * V;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(i % V);
+        const double2 s = reinterpret_cast<const double2 *>(src)[i];
+        reinterpret_cast<float2 *>(dst)[i] = v == 0 ? make_float2(0.f, 0.f) : make_float2((float)s.x, (float)s.y);
+    }
+}
+
+// Philox4x32-10 (Salmon et al. 2011); same constants as the oracle's restatement.
+__device__ __forceinline__ uint4 d2d_philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// uniform-in-disc draw (position.py:24-28): theta = 2 pi u1, r = radius sqrt(u2)
+__device__ __forceinline__ float2 d2d_disc_draw(uint64_t seed, uint64_t genv, uint32_t dev, uint32_t attempt, float radius) {
+    const uint4 o = d2d_philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32), dev, attempt),
+                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const float u1 = (float)(o.x >> 8) * (1.0f / 16777216.0f), u2 = (float)(o.y >> 8) * (1.0f / 16777216.0f);
+    float s, c;
+    sincospif(2.0f * u1, &s, &c);
+    const float r = radius * sqrtf(u2);
+    return make_float2(r * c, r * s);
+}
+
+// Simulator.reset (simulator.py:61-75): one thread per (env, link slot); a DUE thread draws its tx in
+// the cell and re-draws its rx around the tx until it falls inside the cell (position.py:31-45).
+__global__ void d2d_reset_kernel(float *__restrict__ pos, uint8_t *__restrict__ step_count,
+                                 const uint8_t *__restrict__ env_mask, int64_t num_envs, int C, int D, float cell_radius,
+                                 float d2d_radius, uint64_t seed, uint64_t first_global_env) {
+    const int N = C + D, V = 1 + C + 2 * D;
+    const int64_t total = num_envs * N;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t e = i / N;
+        const int j = (int)(i - e * N);
+        if (env_mask && !env_mask[e]) continue;
+        float2 *pe = reinterpret_cast<float2 *>(pos) + e * V;
+        const uint64_t g = first_global_env + (uint64_t)e;
+        if (j == 0) {
+            pe[0] = make_float2(0.f, 0.f);                       // simulator.py:63-64
+            if (step_count) step_count[e] = 0;                   // envs/d2d_env.py:46
+        }
+        if (j < C) {
+            pe[1 + j] = d2d_disc_draw(seed, g, (uint32_t)(1 + j), 0, cell_radius);
+        } else {
+            const int t = 1 + C + 2 * (j - C);
+            const float2 tx = d2d_disc_draw(seed, g, (uint32_t)t, 0, cell_radius);
+            float2 rx = tx;
+            for (uint32_t a = 0; a < 64; ++a) {
+                const float2 o = d2d_disc_draw(seed, g, (uint32_t)(t + 1), a, d2d_radius);
+                rx = make_float2(tx.x + o.x, tx.y + o.y);
+                if (fmaf(rx.x, rx.x, rx.y * rx.y) <= cell_radius * cell_radius) break;
+            }
+            pe[t] = tx;
+            pe[t + 1] = rx;
+        }
+    }
+}
+
+// LinearObsFunction.get_state (envs/obs_fn.py:43-53): agent i's vector = its own row, then every other
+// row in link order.  One block per (env, agent); float2 granularity (3 per row).
+__global__ void d2d_per_agent_obs_kernel(const float *__restrict__ table, float *__restrict__ out, int N) {
+    const int64_t e = blockIdx.x / N;
+    const int i = (int)(blockIdx.x - e * N);
+    const float2 *src = reinterpret_cast<const float2 *>(table) + e * N * 3;
+    float2 *dst = reinterpret_cast<float2 *>(out) + (e * N + i) * (int64_t)N * 3;
+    for (int m = threadIdx.x; m < 3 * N; m += blockDim.x) {
+        const int row = m / 3, part = m - row * 3;
+        const int link = row == 0 ? i : (row - 1 < i ? row - 1 : row);
+        dst[m] = src[link * 3 + part];
+    }
+}

@@ -1,0 +1,206 @@
+// d2d_common.cuh - shared device types and math for the sm_100a step kernels.
+//
+// The arithmetic contract is SURVEY.md Appendix A (reference simulator.py:89-154).  The kernels work in
+// the LINEAR power domain in fp32 and only go to dB for the two quantities the reference reports in dB:
+//
+//   w_k     = 10^(p_k/10) * 10^((eo_k - K)/10)          interferer EIRP minus the path-loss constant [mW]
+//   g(d)    = d^-ple                                    (= 1/d^2 for ple = 2: no transcendental)
+//   I_j     = sum_{k != j, rb_k = rb_j} w_k * g(|tx_k - rx_j|)            simulator.py:95-101
+//   snr_lin = 10^(p_j/10) * a_j * g(d_j),  a_j = 10^((eo + ro - K - noise)/10)   simulator.py:93,115
+//   r       = snr_lin / (1 + I_j / noise_lin)           = 10^(SINR_dB/10)        simulator.py:106-107
+//   SINR_dB = 10 log10(r);  SNR_dB = p + snr0_dB - 5 ple log10(d^2)
+//   rate    = log2(1 + r);  cap = bw_MHz * rate  (both gated by SINR_dB > sensitivity) simulator.py:118-154
+//
+// fp32 keeps ~1e-6 dB absolute error; links whose SINR falls within `rescue_band_dB` of 0 dB (where a
+// pure relative tolerance on a dB value is ill-conditioned) are recomputed in fp64 from the same inputs
+// (d2d_rescue_fp64 below).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define D2D_MAX_PWR_LEVELS 128     // entries of the integer-dBm -> mW table
+#define D2D_WARP_MAX_LINKS 64      // warp-per-env kernel: 2 link slots per lane
+#define D2D_INACTIVE_KEY 0x80000000u
+#ifndef D2D_RESCUE_ENABLED
+#define D2D_RESCUE_ENABLED 1
+#endif
+
+// fp32 per-link constants (SoA of two float4 so a lane fetches each with one conflict-free LDS.128)
+struct __align__(16) D2DLinkA {
+    float tx_lin0;    // 10^((eo_t - K)/10)
+    float a_lin;      // 10^((eo_t + ro_v - K - noise_v)/10)
+    float inv_noise;  // 10^(-noise_v/10)
+    float snr0_dB;    // eo_t + ro_v - K - noise_v
+};
+struct __align__(16) D2DLinkB {
+    float sens_dBm;   // receiver sensitivity (compared with SINR_dB as the reference does)
+    float bw_MHz;     // 1e-6 * rb_bandwidth_kHz * 1000
+    int32_t tx_dev;   // device index of the transmitter
+    int32_t rx_dev;   // device index of the receiver
+};
+// fp64 per-link constants for the rescue path (same folding as D2DLinkA, kept in double)
+struct D2DLinkD {
+    double a_lin;     // 10^((eo_t + ro_v - K - noise_v)/10)
+    double t_lin;     // 10^((eo_t - K)/10)
+    double inv_noise; // 10^(-noise_v/10)
+    double bw_MHz;
+};
+
+struct D2DParams {
+    int64_t num_envs;
+    int32_t N, V, C, R;
+    int32_t n_pwr_cue, n_pwr_due;
+    int32_t episode_length;
+    int32_t nbins;               // block kernel: number of RB bins
+    float ple;                   // path-loss exponent
+    float neg_half_ple;          // -ple/2           : g = exp2(neg_half_ple * log2(d^2))
+    float snr_slope;             // 5*ple*log10(2)   : SNR_dB = p + snr0 - snr_slope*log2(d^2)
+    float min_cap;               // SystemCapacityRewardFunction.min_capacity_mbps
+    float rescue_band_dB;        // |SINR_dB| below this is recomputed in fp64
+    double ple_d;                // fp64 copy for the rescue path
+    const D2DLinkA *linkA;       // [N]
+    const D2DLinkB *linkB;       // [N]
+    const D2DLinkD *linkD;       // [N]
+    const float *pwr_lin;        // [D2D_MAX_PWR_LEVELS] 10^(p/10), correctly rounded from fp64
+    const double *pwr_lin_d;     // same table in fp64 (rescue path)
+    // state
+    const float *pos;            // [E][V][2]
+    uint8_t *step_count;         // [E]
+    double *stats;               // [D2D_NUM_STATS] or nullptr
+    // step io
+    const int32_t *actions;      // [E][N]
+    float *obs;                  // [E][N][6]
+    float *cap;                  // [E][N]
+    float *reward;               // [E]
+    uint8_t *done;               // [E]
+    float *rate;                 // [E][N]
+    int16_t *rb_out;             // [E][N]
+    int16_t *pwr_out;            // [E][N]
+};
+
+__device__ __forceinline__ float d2d_lg2(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float d2d_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float d2d_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Path gain g(d^2) = d^-ple.  PLE2: one MUFU.RCP; otherwise MUFU.LG2 + MUFU.EX2.
+template <bool PLE2>
+__device__ __forceinline__ float d2d_gain(float d2, float neg_half_ple) {
+    if (PLE2) return d2d_rcp(d2);
+    return d2d_ex2(neg_half_ple * d2d_lg2(d2));
+}
+
+// log2(1 + r) with full relative accuracy for small r (the reference's log2(1 + 10^(sinr/10)),
+// simulator.py:124,151).  For r < 0.25 the MUFU path would lose the low bits of r in 1 + r, so use
+// log1p(r) = 2 atanh(r / (2 + r)) with a 4-term odd series (|s| <= 1/9: truncation < 3e-9 relative).
+__device__ __forceinline__ float d2d_log2_1p(float r) {
+    if (r < 0.25f) {
+        float s = r * d2d_rcp(2.0f + r);
+        // one Newton step on the quotient keeps s at ~1 ulp (rcp.approx alone is 1-2 ulp: fine, but cheap)
+        float s2 = s * s;
+        float poly = fmaf(s2, fmaf(s2, fmaf(s2, (1.0f / 7.0f), 0.2f), (1.0f / 3.0f)), 1.0f);
+        return 2.8853900817779268f * s * poly;   // 2 / ln 2
+    }
+    return d2d_lg2(1.0f + r);
+}
+
+struct D2DLinkOut {
+    float sinr_dB, snr_dB, rate, cap;
+};
+
+// Per-link epilogue in fp32 (Appendix A).  p_lin = 10^(p/10), d2 = own-link distance^2, I = interference.
+template <bool PLE2>
+__device__ __forceinline__ D2DLinkOut d2d_link_epilogue(int p, float p_lin, float d2, float I, const D2DLinkA &A,
+                                                        const D2DLinkB &B, const D2DParams &P) {
+    D2DLinkOut o;
+    const float lg_d2 = d2d_lg2(d2);
+    const float g = PLE2 ? d2d_rcp(d2) : d2d_ex2(P.neg_half_ple * lg_d2);
+    const float snr_lin = p_lin * A.a_lin * g;
+    const float r = snr_lin * d2d_rcp(fmaf(I, A.inv_noise, 1.0f));
+    o.snr_dB = ((float)p + A.snr0_dB) - P.snr_slope * lg_d2;
+    o.sinr_dB = 3.0102999566398120f * d2d_lg2(r);
+    const bool ok = o.sinr_dB > B.sens_dBm;
+    const float rate = d2d_log2_1p(r);
+    o.rate = ok ? rate : 0.0f;
+    o.cap = ok ? B.bw_MHz * rate : 0.0f;
+    return o;
+}
+
+// ---- fp64 rescue ------------------------------------------------------------------------------------
+// A pure relative tolerance on SINR_dB is ill-conditioned where SINR_dB crosses 0: fp32 leaves ~1e-6 dB
+// of absolute error there.  (Rate, capacity and reward are well-conditioned at r ~ 1 and need nothing.)
+// Links whose fp32 SINR lands within rescue_band_dB of 0 dB therefore get SINR_dB recomputed in fp64
+// from the same fp32 inputs, in the linear domain with fp64-folded constants.  It is written without
+// libm calls on purpose: log10/pow would raise the whole kernel's register allocation for a path that
+// ~1e-4 of links take.  The kernels run it AFTER the env's outputs are stored, when nothing else is live.
+
+// ln(r) for r in [0.7, 1.45]: 2 atanh((r-1)/(r+1)), odd series to s^19 (truncation < 1e-16 relative)
+__device__ __forceinline__ double d2d_ln_near1(double r) {
+    const double s = (r - 1.0) / (r + 1.0), s2 = s * s;
+    double q = 1.0 / 19.0;
+    q = fma(q, s2, 1.0 / 17.0); q = fma(q, s2, 1.0 / 15.0); q = fma(q, s2, 1.0 / 13.0);
+    q = fma(q, s2, 1.0 / 11.0); q = fma(q, s2, 1.0 / 9.0);  q = fma(q, s2, 1.0 / 7.0);
+    q = fma(q, s2, 1.0 / 5.0);  q = fma(q, s2, 1.0 / 3.0);  q = fma(q, s2, 1.0);
+    return 2.0 * s * q;
+}
+// ln(x), x > 0 normal: exponent split so the mantissa lies in [0.75, 1.5)
+__device__ __forceinline__ double d2d_ln_f64(double x) {
+    int hi = __double2hiint(x), lo = __double2loint(x);
+    int ex = ((hi >> 20) & 0x7ff) - 1023;
+    hi = (hi & 0x000fffff) | 0x3ff00000;
+    double m = __hiloint2double(hi, lo);
+    if (m >= 1.5) { m *= 0.5; ++ex; }
+    return fma((double)ex, 0.6931471805599453094, d2d_ln_near1(m));
+}
+// exp(y) for |y| < 700: Cody-Waite reduction + degree-13 Taylor on |f| <= ln2/2
+__device__ __forceinline__ double d2d_exp_f64(double y) {
+    const double n = rint(y * 1.4426950408889634074);
+    const double f = fma(-n, 1.9082149292705877e-10, fma(-n, 0.693147180369123816490, y));
+    double q = 1.0 / 6227020800.0;
+    q = fma(q, f, 1.0 / 479001600.0); q = fma(q, f, 1.0 / 39916800.0); q = fma(q, f, 1.0 / 3628800.0);
+    q = fma(q, f, 1.0 / 362880.0);    q = fma(q, f, 1.0 / 40320.0);    q = fma(q, f, 1.0 / 5040.0);
+    q = fma(q, f, 1.0 / 720.0);       q = fma(q, f, 1.0 / 120.0);      q = fma(q, f, 1.0 / 24.0);
+    q = fma(q, f, 1.0 / 6.0);         q = fma(q, f, 0.5);              q = fma(q, f, 1.0);
+    q = fma(q, f, 1.0);
+    return q * __hiloint2double(((int)n + 1023) << 20, 0);
+}
+template <bool PLE2>
+__device__ __forceinline__ double d2d_gain_f64(double d2, double ple) {
+    if (PLE2) return 1.0 / d2;
+    return d2d_exp_f64(-0.5 * ple * d2d_ln_f64(d2));
+}
+// integer Tx power of link k re-derived from the env's raw action row (envs/d2d_env.py:96)
+__device__ __forceinline__ int d2d_pwr_of(const int32_t *act_env, int k, const D2DParams &P) {
+    const int a = act_env[k];
+    const int npw = k < P.C ? P.n_pwr_cue : P.n_pwr_due;
+    return (a - (a / npw) * npw) & (D2D_MAX_PWR_LEVELS - 1);
+}
+// interferer k's fp64 contribution at receiver (rxx, rxy): w_k * g(d)
+template <bool PLE2>
+__device__ __forceinline__ double d2d_ix_term_f64(int k, const float4 &rk, float rxx, float rxy, const int32_t *act_env,
+                                                  const D2DParams &P) {
+    const double ex = (double)rk.x - (double)rxx, ey = (double)rk.y - (double)rxy;
+    return P.pwr_lin_d[d2d_pwr_of(act_env, k, P)] * P.linkD[k].t_lin * d2d_gain_f64<PLE2>(ex * ex + ey * ey, P.ple_d);
+}
+// SINR_dB of link j from its fp64 interference sum (simulator.py:106-107 in the linear domain)
+template <bool PLE2>
+__device__ __forceinline__ float d2d_sinr_f64(int j, float txx, float txy, float rxx, float rxy, double I,
+                                              const int32_t *act_env, const D2DParams &P) {
+    const D2DLinkD Lj = P.linkD[j];
+    const double dx = (double)txx - (double)rxx, dy = (double)txy - (double)rxy;
+    const double S = P.pwr_lin_d[d2d_pwr_of(act_env, j, P)] * Lj.a_lin * d2d_gain_f64<PLE2>(dx * dx + dy * dy, P.ple_d);
+    const double r = S / fma(I, Lj.inv_noise, 1.0);            // a_lin already carries 1/noise
+    return (float)(4.3429448190325182765 * d2d_ln_near1(r));   // 10 log10(r), |r - 1| small by construction
+}

@@ -1,0 +1,184 @@
+"""D2DEnv: the reference's single-environment dict API (envs/d2d_env.py) as an E = 1 view over the CUDA path.
+
+Same surface as the reference class: `D2DEnv(env_config)`, `reset() -> {key: ndarray(6N,)}`,
+`step({'tx:rx': int}) -> (obs, rewards, {'__all__': done}, info)`, `render()`, `save_device_config(Path)`,
+attributes `observation_space`, `action_space`, `num_pwr_actions`, `actions`, `state`, `num_steps`.
+All arithmetic runs in the sm_100a step kernel through `d2d_step_host`; this file is key parsing and
+dict building only.
+
+Documented divergences from the reference:
+  * custom / unimplemented plugin classes are rejected at construction (north star);
+  * negative or out-of-range integer actions raise ValueError (the reference decodes them silently, B.9);
+  * 'mbs:cueXX' downlink keys raise NotImplementedError (B.8);
+  * device positions come from a Philox stream keyed by `seed`, not Python's global `random` (section 3.2).
+"""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .config import BASE_STATION_ID, EPISODE_LENGTH
+from .spaces import Box, Dict as DictSpace, Discrete
+from .vec_env import VecD2DEnv
+
+
+class D2DEnv:
+    metadata = {'render.modes': ['human']}
+
+    def __init__(self, env_config: Optional[dict] = None, device: Any = 'cuda', seed: int = 0) -> None:
+        env_config = env_config or {}
+        # VecD2DEnv pops 'obs_fn' / 'reward_fn' from the caller's dict exactly like envs/d2d_env.py:27-28
+        self.vec = VecD2DEnv(1, env_config, device=device, seed=seed, info=True)
+        cfg = self.vec.config
+        self.config = cfg
+        r = cfg.cell_radius_m
+        # envs/obs_fn.py:36-41
+        self.observation_space = Box(low=-r, high=r, shape=(6 * cfg.num_links,))
+        self.num_pwr_actions = cfg.num_pwr_actions                               # envs/d2d_env.py:31-35
+        self.action_space = DictSpace({k: Discrete(cfg.num_rbs * n) for k, n in
+                                       (('due', self.num_pwr_actions['due']), ('cue', self.num_pwr_actions['cue']),
+                                        ('mbs', self.num_pwr_actions['mbs']))})   # envs/d2d_env.py:36-40
+        self.device_ids = cfg.device_ids()
+        self.link_keys = cfg.link_keys()
+        self._link_index = {k: i for i, k in enumerate(self.link_keys)}
+        self._device_set = set(self.device_ids)
+        self._cues = set(self.device_ids[1:1 + cfg.num_cues])
+        self._due_tx = {t for (t, _r) in cfg.link_ids()[cfg.num_cues:]}
+        self._host = self.vec.alloc_host_outputs(pinned=False, info=True)
+        self.actions: Optional[Dict[str, Tuple[int, int]]] = None
+        self.state: Optional[dict] = None
+        self.num_steps = 0
+        self._present: List[int] = []
+
+    # ---- helpers ------------------------------------------------------------------------------
+    def _decode_action(self, key: str, action: Any) -> int:
+        """Type rule of envs/d2d_env.py:93-101; the integer itself is decoded on the GPU."""
+        if not isinstance(action, (int, np.integer)) or isinstance(action, bool):
+            raise ValueError(f'Unable to decode action type "{type(action)}"')
+        tx_id, _, rx_id = key.partition(':')
+        for id_ in (tx_id, rx_id):
+            if id_ not in self._device_set:
+                raise KeyError(id_)                                   # devices.py:28
+        if key not in self._link_index:
+            if tx_id == BASE_STATION_ID:
+                raise NotImplementedError(f'downlink action "{key}" is not implemented by the CUDA path')
+            raise KeyError(key)
+        j = self._link_index[key]
+        n = int(self.vec.action_nvec[j])
+        a = int(action)
+        if not 0 <= a < n:
+            raise ValueError(f'action {a} for "{key}" is outside Discrete({n})')
+        return a
+
+    def _step_arrays(self, raw_actions: Dict[str, Any]) -> List[str]:
+        acts = np.full((1, self.config.num_links), -1, np.int32)      # -1: agent absent (Appendix B.8)
+        keys = []
+        for key, action in raw_actions.items():                       # caller's insertion order (envs/d2d_env.py:75)
+            a = self._decode_action(key, action)
+            acts[0, self._link_index[key]] = a
+            keys.append(key)
+        self.vec.step_host(acts, self._host)
+        return keys
+
+    def _obs_dict(self, keys: List[str]) -> Dict[str, np.ndarray]:
+        """envs/obs_fn.py:43-53: own 6-tuple then every other present link's, in the action dict's order."""
+        table = self._host['obs'][0].astype(np.float64)
+        rows = [self._link_index[k] for k in keys]
+        out = {}
+        for i, k in enumerate(keys):
+            order = [rows[i]] + rows[:i] + rows[i + 1:]
+            out[k] = table[order].reshape(-1)
+        return out
+
+    def _state(self, keys: List[str]) -> dict:
+        h = self._host
+        ids = [tuple(k.split(':')) for k in keys]
+        rows = [self._link_index[k] for k in keys]
+        return {
+            'sinrs_db': {i: float(h['obs'][0, r, 4]) for i, r in zip(ids, rows)},
+            'snrs_db': {i: float(h['obs'][0, r, 5]) for i, r in zip(ids, rows)},
+            'rate_bps': {i: float(h['rate_bps'][0, r]) for i, r in zip(ids, rows)},
+            'capacity_mbps': {i: float(h['capacity_mbps'][0, r]) for i, r in zip(ids, rows)},
+        }
+
+    # ---- gym surface ----------------------------------------------------------------------------
+    def reset(self) -> Dict[str, np.ndarray]:
+        """envs/d2d_env.py:45-52: new positions, then one uncounted step with random actions."""
+        self.num_steps = 0
+        self.vec.reset(mask=np_mask_all(self.vec))                    # positions + counters only
+        file_devices = self.config.devices
+        if file_devices:                                               # simulator.py:65-66
+            pos = self.vec.positions[0].cpu().numpy().astype(np.float64)
+            for idx, id_ in enumerate(self.device_ids):
+                if idx and id_ in file_devices and 'position' in file_devices[id_]:
+                    pos[idx] = file_devices[id_]['position']
+            self.vec.set_positions(pos[None])
+        raw = {k: self.action_space['cue' if k.startswith('cue') else 'due'].sample() for k in self.link_keys}
+        self.vec._bind(False)                                          # the reset step is not counted
+        try:
+            keys = self._step_arrays(raw)
+        finally:
+            self.vec._bind(True)
+        self.actions = self._actions_view(keys)
+        self.state = self._state(keys)
+        return self._obs_dict(keys)
+
+    def step(self, raw_actions: Dict[str, Any]):
+        """envs/d2d_env.py:62-71."""
+        keys = self._step_arrays(raw_actions)
+        self.num_steps += 1
+        self.actions = self._actions_view(keys)
+        self.state = self._state(keys)
+        obs = self._obs_dict(keys)
+        reward = float(self._host['reward'][0])
+        rewards = {k: reward for k in keys}                            # envs/reward_fn.py:44
+        game_over = {'__all__': self.num_steps >= EPISODE_LENGTH}      # envs/d2d_env.py:68
+        info = {k: self._info(k) for k in keys}
+        return obs, rewards, game_over, info
+
+    def _actions_view(self, keys: List[str]) -> Dict[str, Tuple[int, int]]:
+        h = self._host
+        return {k: (int(h['rb'][0, self._link_index[k]]), int(h['tx_pwr_dbm'][0, self._link_index[k]])) for k in keys}
+
+    def _info(self, key: str) -> Dict[str, Any]:
+        """envs/d2d_env.py:106-116."""
+        j, h = self._link_index[key], self._host
+        return {'rb': int(h['rb'][0, j]), 'tx_pwr_dbm': int(h['tx_pwr_dbm'][0, j]),
+                'snr_db': float(h['obs'][0, j, 5]), 'sinr_db': float(h['obs'][0, j, 4]),
+                'rate_bps': float(h['rate_bps'][0, j]), 'capacity_mbps': float(h['capacity_mbps'][0, j])}
+
+    def render(self, mode: str = 'human') -> None:
+        assert self.state is not None and self.actions is not None, \
+            'Initialise environment with `reset()` before calling `render()`'
+        print(self._obs_dict(list(self.actions.keys())))
+
+    # ---- device config I/O (envs/d2d_env.py:124-134, envs/env_config.py:32-37) -----------------------
+    def device_positions(self) -> Dict[str, Tuple[float, float]]:
+        pos = self.vec.positions[0].cpu().numpy()
+        return {id_: (float(pos[i, 0]), float(pos[i, 1])) for i, id_ in enumerate(self.device_ids)}
+
+    def set_device_positions(self, positions: Dict[str, Tuple[float, float]]) -> None:
+        """Batch form of Device.set_position (device.py:82-83) for this env."""
+        pos = self.vec.positions[0].cpu().numpy().astype(np.float64)
+        index = {id_: i for i, id_ in enumerate(self.device_ids)}
+        for id_, xy in positions.items():
+            pos[index[id_]] = xy                                       # KeyError on unknown id, like devices.py:28
+        self.vec.set_positions(pos[None])
+
+    def save_device_config(self, config_file: Path) -> None:
+        positions = self.device_positions()
+        configs = self.config.device_configs()
+        doc = {id_: {'position': positions[id_], 'config': configs[id_]} for id_ in self.device_ids}
+        with config_file.open(mode='w') as fid:
+            json.dump(doc, fid)
+
+    def close(self) -> None:
+        self.vec.close()
+
+
+def np_mask_all(vec: VecD2DEnv):
+    import torch
+    return torch.ones((vec.num_envs,), dtype=torch.uint8, device=vec.device)

@@ -1,0 +1,254 @@
+"""VecD2DEnv: the batched tensor API over libd2d_b200.so.
+
+E independent default-topology D2D environments live on one GPU (positions, step counters and statistics
+resident in HBM as PyTorch tensors); `step(actions)` is ONE fused kernel launch that replaces, for every
+env, the reference's D2DEnv.step -> Simulator.step -> LinearObsFunction -> SystemCapacityRewardFunction
+chain (envs/d2d_env.py:62-71).  PyTorch is used for device memory, streams and torch.distributed only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import EPISODE_LENGTH, EnvConfig, link_table, to_c_config
+from .plugins import (LinearObsFunction, SystemCapacityRewardFunction, resolve_obs_fn, resolve_reward_fn)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class VecD2DEnv:
+    """Batched GymD2D step path on one B200.
+
+    Parameters
+    ----------
+    num_envs : number of environments resident on this device (this rank's slice for multi-GPU runs).
+    env_config : the reference's env_config dict (same keys/defaults as EnvConfig, plus 'obs_fn' and
+        'reward_fn' plugin classes).  Like the reference ctor (envs/d2d_env.py:27-28) the two plugin keys
+        are popped from the caller's dict.
+    device : CUDA device.
+    seed, global_env_offset : Philox key and the global index of local env 0; a sharded batch draws the
+        same scenario for a given global env whatever the number of GPUs.
+    """
+
+    def __init__(self, num_envs: int, env_config: Optional[dict] = None, device: Any = 'cuda', seed: int = 0,
+                 global_env_offset: int = 0, info: bool = False) -> None:
+        env_config = env_config if env_config is not None else {}
+        obs_enum = resolve_obs_fn(env_config.pop('obs_fn', LinearObsFunction))
+        reward_enum, min_cap = resolve_reward_fn(env_config.pop('reward_fn', SystemCapacityRewardFunction))
+        self.config = EnvConfig(**env_config)          # unknown key -> TypeError, like the reference dataclass
+        self.num_envs = int(num_envs)
+        if self.num_envs < 1:
+            raise ValueError('num_envs must be >= 1')
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise _lib.D2DError('gym_d2d_b200 runs on CUDA (sm_100a) only; there is no CPU path')
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        self.seed = int(seed)
+        self.global_env_offset = int(global_env_offset)
+        self.num_links = self.config.num_links
+        self.num_devices = self.config.num_devices
+        self.link_keys = self.config.link_keys()
+        self.num_pwr_actions = self.config.num_pwr_actions
+        npw = self.num_pwr_actions
+        # envs/d2d_env.py:36-40: Discrete(num_rbs * n_pwr) per transmitter type
+        self.action_nvec = np.array([self.config.num_rbs * npw['cue']] * self.config.num_cues
+                                    + [self.config.num_rbs * npw['due']] * self.config.num_due_pairs, np.int64)
+        self.episode_length = EPISODE_LENGTH
+        self.want_info = bool(info)
+        self._episode = 0
+
+        self._lib = _lib.load()
+        links = link_table(self.config)
+        c_links = (_lib.D2DLink * len(links))(*[_lib.D2DLink(**row) for row in links])
+        c_cfg = to_c_config(self.config, self.num_envs, self.device.index, obs_enum, reward_enum, min_cap)
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.d2d_create(C.byref(c_cfg), c_links, C.byref(handle)))
+        self._h = handle
+
+        E, N, V = self.num_envs, self.num_links, self.num_devices
+        dev = self.device
+        self.positions = torch.zeros((E, V, 2), dtype=torch.float32, device=dev)
+        self.step_count = torch.zeros((E,), dtype=torch.uint8, device=dev)
+        self._stats = torch.zeros((_lib.STATS_REPLICAS, _lib.NUM_STATS), dtype=torch.float64, device=dev)
+        self._bind(True)
+        # output buffers, reused by every step (clone what you keep)
+        self.obs = torch.zeros((E, N, 6), dtype=torch.float32, device=dev)
+        self.capacity_mbps = torch.zeros((E, N), dtype=torch.float32, device=dev)
+        self.reward = torch.zeros((E,), dtype=torch.float32, device=dev)
+        self.done = torch.zeros((E,), dtype=torch.uint8, device=dev)
+        self.rate_bps = torch.zeros((E, N), dtype=torch.float32, device=dev) if self.want_info else None
+        self.rb = torch.zeros((E, N), dtype=torch.int16, device=dev) if self.want_info else None
+        self.tx_pwr_dbm = torch.zeros((E, N), dtype=torch.int16, device=dev) if self.want_info else None
+        self._io = _lib.D2DStepIO()
+        self._nvec_dev = torch.as_tensor(self.action_nvec, device=dev)
+        self._nvec_f = self._nvec_dev.to(torch.float32)
+        self._nvec_m1 = (self._nvec_dev - 1).to(torch.int32)
+
+    # ---- plumbing -----------------------------------------------------------------------------
+    def _bind(self, counted: bool) -> None:
+        _lib.check(self._lib.d2d_bind_state(self._h, self.positions.data_ptr(),
+                                            self.step_count.data_ptr() if counted else None,
+                                            self._stats.data_ptr() if counted else None))
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def close(self) -> None:
+        if getattr(self, '_h', None):
+            self._lib.d2d_destroy(self._h)
+            self._h = None
+
+    def __del__(self) -> None:
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- state --------------------------------------------------------------------------------
+    def set_positions(self, positions, first_env: int = 0) -> None:
+        """Upload float64 positions [count][V][2] (device order mbs, cues, due tx/rx ...).  Replaces
+        Device.set_position (device.py:82-83); device 0 is pinned to the origin (simulator.py:63-64)."""
+        if isinstance(positions, torch.Tensor) and positions.is_cuda:
+            src = positions.to(torch.float64).contiguous()
+            on_dev = 1
+            ptr = src.data_ptr()
+        else:
+            src = np.ascontiguousarray(np.asarray(positions.cpu() if isinstance(positions, torch.Tensor) else positions,
+                                                  dtype=np.float64))
+            on_dev = 0
+            ptr = src.ctypes.data
+        if src.ndim != 3 or tuple(src.shape[1:]) != (self.num_devices, 2):
+            raise ValueError(f'positions must be [count][{self.num_devices}][2], got {tuple(src.shape)}')
+        _lib.check(self._lib.d2d_set_positions(self._h, ptr, on_dev, int(first_env), int(src.shape[0]), self._stream()))
+
+    def sample_actions(self, generator: Optional[torch.Generator] = None) -> torch.Tensor:
+        """Uniform draw from the reference's Discrete action spaces (envs/d2d_env.py:36-40, :54-60)."""
+        u = torch.rand((self.num_envs, self.num_links), device=self.device, generator=generator)
+        return torch.minimum((u * self._nvec_f).to(torch.int32), self._nvec_m1)
+
+    def reset(self, seed: Optional[int] = None, mask: Optional[torch.Tensor] = None,
+              initial_actions: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+        """Re-draw device positions on the GPU and zero the step counters (Simulator.reset, simulator.py:61-75;
+        `num_steps = 0`, envs/d2d_env.py:46).  With mask=None this follows D2DEnv.reset (envs/d2d_env.py:45-52):
+        one uncounted step with random actions produces the initial observation table, which is returned.
+        With a uint8/bool mask [E] only the flagged envs are re-drawn and nothing is returned."""
+        if seed is not None:
+            self.seed = int(seed)
+            self._episode = 0
+        # a fresh Philox key per reset call so successive episodes differ (the reference re-draws from `random`)
+        key = (self.seed + 0x9E3779B97F4A7C15 * self._episode) & 0xFFFFFFFFFFFFFFFF
+        self._episode += 1
+        m = None
+        if mask is not None:
+            m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            if m.shape != (self.num_envs,):
+                raise ValueError('mask must have shape [num_envs]')
+        _lib.check(self._lib.d2d_reset(self._h, key, self.global_env_offset, _ptr(m), self._stream()))
+        if mask is not None:
+            return None
+        actions = initial_actions if initial_actions is not None else self.sample_actions()
+        self._bind(False)            # the reset step is not counted (simulator.step is called directly, :50)
+        try:
+            self._launch(actions)
+        finally:
+            self._bind(True)
+        return self.obs
+
+    # ---- the hot path --------------------------------------------------------------------------
+    def _launch(self, actions: torch.Tensor) -> None:
+        if actions.dtype != torch.int32 or not actions.is_cuda or not actions.is_contiguous():
+            raise ValueError('actions must be a contiguous int32 CUDA tensor [num_envs][num_links]')
+        if tuple(actions.shape) != (self.num_envs, self.num_links):
+            raise ValueError(f'actions must have shape {(self.num_envs, self.num_links)}, got {tuple(actions.shape)}')
+        io = self._io
+        io.actions = actions.data_ptr()
+        io.obs = self.obs.data_ptr()
+        io.capacity_mbps = self.capacity_mbps.data_ptr()
+        io.reward = self.reward.data_ptr()
+        io.done = self.done.data_ptr()
+        io.rate_bps = _ptr(self.rate_bps)
+        io.rb = _ptr(self.rb)
+        io.tx_pwr_dBm = _ptr(self.tx_pwr_dbm)
+        _lib.check(self._lib.d2d_step(self._h, C.byref(io), self._stream()))
+
+    def step(self, actions: torch.Tensor, validate: bool = False
+             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, Dict[str, torch.Tensor]]:
+        """One env.step for all E envs: a single fused kernel launch on the current stream, no host sync.
+
+        actions: int32 [E][N]; < 0 marks an agent absent this step (Appendix B.8).  Returns the preallocated
+        (obs [E][N][6], reward [E], done [E] uint8, info) tensors, overwritten by the next call.
+        validate=True checks the action range on the device first (costs a host sync); out-of-range actions
+        are otherwise the caller's responsibility (the reference accepts them silently, Appendix B.9)."""
+        if validate and bool((actions >= self._nvec_dev.to(actions.dtype)).any()):
+            raise ValueError('action out of range for its Discrete space')
+        self._launch(actions)
+        info = {'capacity_mbps': self.capacity_mbps}
+        if self.want_info:
+            info.update(rate_bps=self.rate_bps, rb=self.rb, tx_pwr_dbm=self.tx_pwr_dbm,
+                        sinr_db=self.obs[..., 4], snr_db=self.obs[..., 5])
+        return self.obs, self.reward, self.done, info
+
+    def step_host(self, actions: np.ndarray, out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
+        """End-to-end host call (d2d_step_host): host int32 actions in, host arrays out, copies included.
+        This is the entry the reference's CPU-side loop would bind."""
+        a = np.ascontiguousarray(actions, dtype=np.int32)
+        E, N = self.num_envs, self.num_links
+        if a.shape != (E, N):
+            raise ValueError(f'actions must have shape {(E, N)}')
+        if out is None:
+            out = self.alloc_host_outputs()
+        io = _lib.D2DStepIO(actions=a.ctypes.data, obs=out['obs'].ctypes.data,
+                            capacity_mbps=out['capacity_mbps'].ctypes.data, reward=out['reward'].ctypes.data,
+                            done=out['done'].ctypes.data,
+                            rate_bps=out['rate_bps'].ctypes.data if 'rate_bps' in out else None,
+                            rb=out['rb'].ctypes.data if 'rb' in out else None,
+                            tx_pwr_dBm=out['tx_pwr_dbm'].ctypes.data if 'tx_pwr_dbm' in out else None)
+        _lib.check(self._lib.d2d_step_host(self._h, C.byref(io), self._stream()))
+        return out
+
+    def alloc_host_outputs(self, pinned: bool = False, info: bool = True) -> Dict[str, np.ndarray]:
+        E, N = self.num_envs, self.num_links
+        spec = {'obs': ((E, N, 6), torch.float32), 'capacity_mbps': ((E, N), torch.float32),
+                'reward': ((E,), torch.float32), 'done': ((E,), torch.uint8)}
+        if info:
+            spec.update({'rate_bps': ((E, N), torch.float32), 'rb': ((E, N), torch.int16),
+                         'tx_pwr_dbm': ((E, N), torch.int16)})
+        self._host_keepalive = {k: torch.zeros(s, dtype=d, pin_memory=pinned) for k, (s, d) in spec.items()}
+        return {k: t.numpy() for k, t in self._host_keepalive.items()}
+
+    def per_agent_obs(self, obs: Optional[torch.Tensor] = None, num_envs: Optional[int] = None) -> torch.Tensor:
+        """Materialise the reference's per-agent layout (envs/obs_fn.py:43-53): [E][N][6N].  O(N^2) bytes."""
+        obs = self.obs if obs is None else obs
+        n = self.num_envs if num_envs is None else int(num_envs)
+        out = torch.empty((n, self.num_links, 6 * self.num_links), dtype=torch.float32, device=self.device)
+        _lib.check(self._lib.d2d_per_agent_obs(self._h, obs.data_ptr(), out.data_ptr(), n, self._stream()))
+        return out
+
+    # ---- statistics ------------------------------------------------------------------------------
+    def stats_tensor(self) -> torch.Tensor:
+        """float64 [NUM_STATS] device tensor (summed over the atomics replicas) - what dist.all_reduce_stats sums."""
+        return self._stats.sum(dim=0)
+
+    def stats(self) -> Dict[str, float]:
+        v = self.stats_tensor().cpu().tolist()
+        return dict(zip(_lib.STAT_NAMES, v))
+
+    def reset_stats(self) -> None:
+        _lib.check(self._lib.d2d_stats_reset(self._h, self._stream()))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.d2d_launch_count(self._h))
+
+    def step_geometry(self) -> Dict[str, int]:
+        g, b, s, e = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        _lib.check(self._lib.d2d_step_geometry(self._h, C.byref(g), C.byref(b), C.byref(s), C.byref(e)))
+        return dict(grid=g.value, block=b.value, smem_bytes=s.value, envs_per_block=e.value)

@@ -1,0 +1,169 @@
+/*
+ * d2d_b200.h - C ABI of libd2d_b200.so: the B200 (sm_100a) batched replacement for GymD2D's per-step
+ * radio physics.  Plain C types only; no torch, no C++ in the signatures.
+ *
+ * The reference (davidcotton/gym-d2d) is pure Python and has no FFI of its own, so each entry point
+ * cites the reference *interface* it replaces (paths relative to /root/reference/src/gym_d2d/).  The
+ * ctypes stub a maintainer would add on the reference side is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative d2d_status; d2d_last_error() gives the message
+ *    of the calling thread's last failure.  Nothing here throws or aborts.
+ *  - all device buffers are CALLER-OWNED (PyTorch CUDA allocations in the Python shell) and passed as
+ *    raw device pointers; the handle owns only its small constant tables and host staging buffers.
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls are
+ *    stream-ordered and asynchronous unless stated; d2d_step performs no allocation and no host
+ *    synchronisation, so it can be captured into a CUDA graph.
+ *  - a handle is bound to one CUDA device and is not thread-safe.  Multi-GPU = one process (one
+ *    handle) per GPU, each owning a contiguous slice of the global environment batch.
+ *
+ * Index conventions (devices.py:20-25, simulator.py:34-48, envs/d2d_env.py:55-60):
+ *   C = num_cues, D = num_due_pairs, N = C + D links, V = 1 + C + 2D devices.
+ *   device 0 = 'mbs'; 1..C = 'cue00'..; pair d: tx = 1+C+2d ('due{2d}'), rx = tx+1 ('due{2d+1}').
+ *   link j < C : CUE j -> MBS (UPLINK);  link j >= C : DUE pair j-C (SIDELINK).
+ */
+#ifndef D2D_B200_H
+#define D2D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+#define D2D_API extern "C" __attribute__((visibility("default")))
+#else
+#define D2D_API __attribute__((visibility("default")))
+#endif
+
+#define D2D_ABI_VERSION 1
+
+typedef struct d2d_handle d2d_handle_t;
+
+typedef enum d2d_status {
+    D2D_OK = 0,
+    D2D_ERR_INVALID_ARG = -1,   /* bad pointer / size / enum: the shell maps this to ValueError / TypeError */
+    D2D_ERR_UNSUPPORTED = -2,   /* configuration outside what the kernels implement */
+    D2D_ERR_CUDA = -3,          /* a CUDA runtime call failed; message carries cudaGetErrorString */
+    D2D_ERR_STATE = -4          /* state buffers not bound / called out of order */
+} d2d_status;
+
+/* path_loss_model plugin (envs/env_config.py:21; classes in path_loss.py:42-66).  FREE_SPACE is
+ * LogDistancePathLoss with ple = 2 (path_loss.py:43,45): it is not a separate class in the reference. */
+typedef enum d2d_path_loss_model { D2D_PL_LOG_DISTANCE = 0, D2D_PL_FREE_SPACE = 1 } d2d_path_loss_model;
+/* obs_fn plugin (envs/d2d_env.py:27; envs/obs_fn.py:35-61) */
+typedef enum d2d_obs_fn { D2D_OBS_LINEAR = 0 } d2d_obs_fn;
+/* reward_fn plugin (envs/d2d_env.py:28; envs/reward_fn.py:22-44) */
+typedef enum d2d_reward_fn { D2D_REWARD_SYSTEM_CAPACITY = 0 } d2d_reward_fn;
+/* link_type.py:4-7 */
+typedef enum d2d_link_type { D2D_LINK_UPLINK = 1, D2D_LINK_DOWNLINK = 2, D2D_LINK_SIDELINK = 3 } d2d_link_type;
+
+/* The hot-path subset of EnvConfig (envs/env_config.py:12-27) plus the plugin enums. */
+typedef struct d2d_config {
+    int32_t abi_version;        /* must be D2D_ABI_VERSION */
+    int32_t cuda_device;        /* ordinal the handle is bound to */
+    int64_t num_envs;           /* E: environments resident on this device */
+    int32_t num_rbs;            /* envs/env_config.py:12 */
+    int32_t num_cues;           /* :13 */
+    int32_t num_due_pairs;      /* :14 */
+    int32_t n_pwr_cue;          /* envs/d2d_env.py:33  cue_max_tx_power_dBm + 1 */
+    int32_t n_pwr_due;          /* envs/d2d_env.py:32  due_max - due_min + 1 */
+    int32_t episode_length;     /* envs/d2d_env.py:16  EPISODE_LENGTH = 10 */
+    int32_t path_loss_model;    /* d2d_path_loss_model */
+    int32_t obs_fn;             /* d2d_obs_fn */
+    int32_t reward_fn;          /* d2d_reward_fn */
+    int32_t reserved0;
+    double carrier_freq_GHz;    /* envs/env_config.py:23 */
+    double ple;                 /* path_loss.py:43 path-loss exponent (ignored, = 2, for FREE_SPACE) */
+    double cell_radius_m;       /* envs/env_config.py:15 */
+    double d2d_radius_m;        /* :16 */
+    double min_capacity_mbps;   /* envs/reward_fn.py:23 */
+} d2d_config_t;
+
+/* Per-link link-budget constants, folded on the host from the per-device config dicts
+ * (device.py:12-41, 51-80, 93-95, 134-140, 158-162; per-device overrides come from the
+ * device_config_file, simulator.py:31). */
+typedef struct d2d_link {
+    double tx_eirp_offset_dB;   /* eirp_dBm(p) - p for the link's transmitter (device.py:60,135,159) */
+    double rx_offset_dB;        /* rx_signal_level_dBm(e, pl) - (e - pl) for its receiver (device.py:72,137-140,161-162) */
+    double rx_noise_dBm;        /* receiver thermal_noise_dBm (device.py:117-119; used at simulator.py:107,115) */
+    double rx_sensitivity_dBm;  /* receiver rx_sensitivity_dBm (device.py:74-80; gate at simulator.py:123,149) */
+    double tx_rb_bandwidth_kHz; /* transmitter rb_bandwidth_kHz (device.py:93-95; simulator.py:150) */
+    int32_t link_type;          /* d2d_link_type */
+    int32_t reserved0;
+} d2d_link_t;
+
+/* Buffers of one step.  All pointers are device pointers for d2d_step and host pointers for
+ * d2d_step_host.  `actions` is required; any output may be NULL to skip it. */
+typedef struct d2d_step_io {
+    const int32_t *actions;     /* [E][N] raw Discrete actions (envs/d2d_env.py:36-40); < 0 = agent absent this step */
+    float *obs;                 /* [E][N][6] compact LinearObsFunction table (envs/obs_fn.py:55-61):
+                                   (tx_x, tx_y, rx_x, rx_y, sinr_dB, snr_dB); agent i's reference vector is
+                                   rows [i, others...] of this table (envs/obs_fn.py:43-53) */
+    float *capacity_mbps;       /* [E][N]  simulator.py:144-154 */
+    float *reward;              /* [E]     SystemCapacityRewardFunction scalar (envs/reward_fn.py:27-44) */
+    uint8_t *done;              /* [E]     num_steps >= episode_length (envs/d2d_env.py:68) */
+    float *rate_bps;            /* [E][N]  simulator.py:118-127 (info['rate_bps'], envs/d2d_env.py:114) */
+    int16_t *rb;                /* [E][N]  decoded resource block (envs/d2d_env.py:95) */
+    int16_t *tx_pwr_dBm;        /* [E][N]  decoded Tx power (envs/d2d_env.py:96) */
+} d2d_step_io_t;
+
+/* Episode statistics accumulated on the device by d2d_step when a stats buffer is bound;
+ * this is the vector the multi-GPU shell all-reduces over NCCL (never inside the step). */
+#define D2D_STATS_REPLICAS 32   /* the stats buffer is [D2D_STATS_REPLICAS][D2D_NUM_STATS]; readers sum over replicas */
+enum { D2D_STAT_SUM_REWARD = 0, D2D_STAT_SUM_CAPACITY = 1, D2D_STAT_SUM_REWARD_SQ = 2,
+       D2D_STAT_ENV_STEPS = 3, D2D_STAT_PENALTIES = 4, D2D_STAT_RESCUES = 5, D2D_NUM_STATS = 8 };
+
+D2D_API int d2d_abi_version(void);
+D2D_API const char *d2d_last_error(void);
+
+/* Replaces Simulator.__init__ + create_devices (simulator.py:18-59) and the plugin construction of
+ * D2DEnv.__init__ (envs/d2d_env.py:24-43).  `links` is [N] on the host. */
+D2D_API int d2d_create(const d2d_config_t *config, const d2d_link_t *links, d2d_handle_t **out);
+D2D_API int d2d_destroy(d2d_handle_t *h);
+
+/* Sizes of the caller-owned state: positions float32 [E][V][2], per-env step counters uint8 [E],
+ * stats float64 [D2D_STATS_REPLICAS][D2D_NUM_STATS] (blocks spread their atomics over the replicas). */
+D2D_API int d2d_state_bytes(const d2d_handle_t *h, size_t *positions_bytes, size_t *step_count_bytes,
+                            size_t *stats_bytes);
+/* Binds the device buffers that hold Device.position (device.py:48,82-83) for every env, D2DEnv.num_steps
+ * (envs/d2d_env.py:43) and the statistics accumulators (stats may be NULL). */
+D2D_API int d2d_bind_state(d2d_handle_t *h, float *positions, uint8_t *step_count, double *stats);
+
+/* Replaces Device.set_position over a batch (device.py:82-83; device_config_file positions,
+ * simulator.py:65-66).  src is float64 [count][V][2], host memory if src_on_device == 0 (the call then
+ * synchronises the stream).  Device 0 (MBS) is pinned to (0,0) as simulator.py:63-64 does. */
+D2D_API int d2d_set_positions(d2d_handle_t *h, const double *src, int src_on_device, int64_t first_env,
+                              int64_t count, void *stream);
+
+/* Replaces Simulator.reset position sampling (simulator.py:61-75, position.py:18-45) and
+ * `num_steps = 0` (envs/d2d_env.py:46) for every env whose env_mask byte is non-zero (NULL = all).
+ * Counter-based Philox4x32-10 keyed by (seed, first_global_env + local index, device index), so a
+ * sharded batch draws the same scenario for a given global env whatever the number of GPUs. */
+D2D_API int d2d_reset(d2d_handle_t *h, uint64_t seed, uint64_t first_global_env, const uint8_t *env_mask,
+                      void *stream);
+
+/* Replaces D2DEnv.step (envs/d2d_env.py:62-71): _decode_action (:93-101), Simulator.step
+ * (simulator.py:77-154), LinearObsFunction (envs/obs_fn.py:43-61), SystemCapacityRewardFunction
+ * (envs/reward_fn.py:27-44), the done flag (:68) and the info fields (:106-116), for all E envs. */
+D2D_API int d2d_step(d2d_handle_t *h, const d2d_step_io_t *io, void *stream);
+
+/* Same call with HOST buffers: copies the actions to the device, steps, copies every non-NULL output
+ * back and synchronises the stream.  This is the end-to-end path a CPU-side caller (the reference's
+ * own env.step loop) would bind. */
+D2D_API int d2d_step_host(d2d_handle_t *h, const d2d_step_io_t *host_io, void *stream);
+
+/* Materialises the reference's per-agent observation layout (envs/obs_fn.py:43-53) from the compact
+ * table: out[e][i] = concat(table[e][i], table[e][k] for k != i), float32 [E][N][6N].  O(N^2) bytes:
+ * provided for drop-in use at small E only. */
+D2D_API int d2d_per_agent_obs(d2d_handle_t *h, const float *obs_table, float *out, int64_t num_envs,
+                              void *stream);
+
+/* Zeroes the bound statistics accumulators. */
+D2D_API int d2d_stats_reset(d2d_handle_t *h, void *stream);
+
+/* Introspection for tests and the bench: number of kernel launches issued through this handle, and the
+ * launch geometry the step kernel uses for the bound configuration. */
+D2D_API int64_t d2d_launch_count(const d2d_handle_t *h);
+D2D_API int d2d_step_geometry(const d2d_handle_t *h, int32_t *grid, int32_t *block, int32_t *smem_bytes,
+                              int32_t *envs_per_block);
+
+#endif /* D2D_B200_H */

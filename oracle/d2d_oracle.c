@@ -1,0 +1,262 @@
+/*
+ * d2d_oracle.c - float64 CPU restatement of the GymD2D step path.  TEST INFRASTRUCTURE ONLY
+ * (see d2d_oracle.h for the rules on who may load this and for the parity-pinning status).
+ *
+ * The code deliberately mirrors the reference's *evaluation order* (left-to-right Python float
+ * arithmetic, math.pow / math.log10 / math.log2 from libm) so that it agrees with the running
+ * reference to ~1e-14 relative; the only intentional difference is that the interference sum is
+ * taken in link order instead of Python set order (simulator.py:95-101), which the reference itself
+ * does not fix.
+ */
+#include "d2d_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define SPEED_OF_LIGHT 299792458.0 /* path_loss.py:9 */
+
+/* conversion.py:4-13   pow(10, dB / 10) */
+double d2d_oracle_dB_to_linear(double dB) { return pow(10.0, dB / 10.0); }
+
+/* conversion.py:16-25  10 * log10(linear) */
+double d2d_oracle_linear_to_dB(double lin) { return 10.0 * log10(lin); }
+
+/* path_loss.py:28-39   10*ple*log10(f_GHz*1e9) + 10*ple*log10(4*pi/c) */
+double d2d_oracle_pl_constant_dB(double f_GHz, double ple) {
+    return 10.0 * ple * log10(f_GHz * 1e9) + 10.0 * ple * log10((4.0 * M_PI) / SPEED_OF_LIGHT);
+}
+
+/* path_loss.py:65-66    10*ple*log10(d) + pl_constant_dB */
+double d2d_oracle_log_distance_pl(double dist_m, double f_GHz, double ple) {
+    return 10.0 * ple * log10(dist_m) + d2d_oracle_pl_constant_dB(f_GHz, ple);
+}
+
+/* position.py:11-12     ((dx)**2 + (dy)**2) ** 0.5 */
+double d2d_oracle_distance(double x1, double y1, double x2, double y2) {
+    double dx = x1 - x2, dy = y1 - y2;
+    return sqrt(dx * dx + dy * dy);
+}
+
+/* device.py:51-60 base; BaseStation :134-135 adds -cable +masthead; UserEquipment :158-159 adds -body */
+double d2d_oracle_eirp_dBm(const d2d_oracle_device *d, double p) {
+    double base = p + d->tx_antenna_gain_dBi - d->ix_margin_dB;
+    if (d->is_bs) return base - d->cable_loss_dB + d->masthead_amplifier_gain_dB;
+    return base - d->body_loss_dB;
+}
+
+/* device.py:62-72 base; BaseStation :137-140; UserEquipment :161-162 */
+double d2d_oracle_rx_signal_level_dBm(const d2d_oracle_device *d, double eirp, double pl) {
+    double base = eirp - pl + d->rx_antenna_gain_dBi;
+    if (d->is_bs) return base - d->cable_loss_dB + d->masthead_amplifier_gain_dB;
+    return base - d->body_loss_dB;
+}
+
+/* device.py:74-80   (noise_figure + thermal_noise) + sinr_dB */
+double d2d_oracle_rx_sensitivity_dBm(const d2d_oracle_device *d) {
+    return (d->noise_figure_dB + d->thermal_noise_dBm) + d->sinr_dB;
+}
+
+/* device.py:85-95   int(num_subcarriers) * int(subcarrier_spacing_kHz) */
+double d2d_oracle_rb_bandwidth_kHz(const d2d_oracle_device *d) {
+    return (double)((int64_t)d->num_subcarriers * (int64_t)d->subcarrier_spacing_kHz);
+}
+
+/* envs/d2d_env.py:93-101  Python floor division / modulo (n_pwr > 0), so a = -1 -> rb = -1, p = n-1 */
+void d2d_oracle_decode_action(int64_t a, int64_t n_pwr, int64_t *rb, int64_t *pwr) {
+    int64_t q = a / n_pwr, r = a % n_pwr;
+    if (r != 0 && ((r < 0) != (n_pwr < 0))) { q -= 1; r += n_pwr; }
+    *rb = q;
+    *pwr = r;
+}
+
+/* One environment.  Returns 0 / -1 (zero-distance link). */
+static int step_one(const d2d_oracle_cfg *cfg, const d2d_oracle_device *dev, const double *pos,
+                    const int32_t *act, const uint8_t *active,
+                    int32_t *rb_o, int32_t *pwr_o, double *sinr_o, double *snr_o, double *rate_o,
+                    double *cap_o, double *obs_o, double *reward_o,
+                    int64_t *rb, int64_t *pw, int32_t *txd, int32_t *rxd, double *sinr, double *cap) {
+    const int C = cfg->num_cues, D = cfg->num_due_pairs, N = C + D;
+    const double K = d2d_oracle_pl_constant_dB(cfg->carrier_freq_GHz, cfg->ple);
+    int status = 0;
+
+    /* devices.py:20-25 device order; envs/d2d_env.py:55-60 link order; :80-91 link type by tx */
+    for (int j = 0; j < N; ++j) {
+        if (j < C) { txd[j] = 1 + j; rxd[j] = 0; }
+        else { txd[j] = 1 + C + 2 * (j - C); rxd[j] = txd[j] + 1; }
+        d2d_oracle_decode_action((int64_t)act[j], j < C ? cfg->n_pwr_cue : cfg->n_pwr_due, &rb[j], &pw[j]);
+    }
+
+    int n_present = 0;
+    double cap_sum = 0.0;
+    for (int j = 0; j < N; ++j) {
+        const int present = active ? active[j] != 0 : 1;
+        double sinr_db = 0.0, snr_db = 0.0, rate = 0.0, capacity = 0.0;
+        if (present) {
+            const d2d_oracle_device *tx = &dev[txd[j]], *rx = &dev[rxd[j]];
+            const double *pt = pos + 2 * txd[j], *pr = pos + 2 * rxd[j];
+            /* simulator.py:93 */
+            double d = d2d_oracle_distance(pt[0], pt[1], pr[0], pr[1]);
+            if (!(d > 0.0)) status = -1;
+            double pl = 10.0 * cfg->ple * log10(d) + K;
+            double rx_pwr = d2d_oracle_rx_signal_level_dBm(rx, d2d_oracle_eirp_dBm(tx, (double)pw[j]), pl);
+            /* simulator.py:95-101: same-RB actions minus self; NO rx gain on interferers */
+            double sum_ix = 0.0;
+            for (int k = 0; k < N; ++k) {
+                if (k == j || rb[k] != rb[j]) continue;
+                if (active && !active[k]) continue;
+                const double *pk = pos + 2 * txd[k];
+                double dk = d2d_oracle_distance(pk[0], pk[1], pr[0], pr[1]);
+                if (!(dk > 0.0)) status = -1;
+                double ix_eirp = d2d_oracle_eirp_dBm(&dev[txd[k]], (double)pw[k]);
+                double ix_pl = 10.0 * cfg->ple * log10(dk) + K;
+                sum_ix += d2d_oracle_dB_to_linear(ix_eirp - ix_pl);
+            }
+            /* simulator.py:106-107 */
+            sinr_db = rx_pwr - d2d_oracle_linear_to_dB(sum_ix + d2d_oracle_dB_to_linear(rx->thermal_noise_dBm));
+            /* simulator.py:110-116 */
+            snr_db = rx_pwr - rx->thermal_noise_dBm;
+            /* simulator.py:118-127 and :144-154 (dB compared with dBm, as written) */
+            if (sinr_db > d2d_oracle_rx_sensitivity_dBm(rx)) {
+                rate = log2(1.0 + d2d_oracle_dB_to_linear(sinr_db));
+                double b = d2d_oracle_rb_bandwidth_kHz(tx) * 1000.0;
+                capacity = 1e-6 * b * log2(1.0 + d2d_oracle_dB_to_linear(sinr_db));
+            }
+            cap_sum += capacity;
+            ++n_present;
+        }
+        sinr[j] = sinr_db;
+        cap[j] = capacity;
+        if (rb_o) rb_o[j] = present ? (int32_t)rb[j] : 0;
+        if (pwr_o) pwr_o[j] = present ? (int32_t)pw[j] : 0;
+        if (sinr_o) sinr_o[j] = sinr_db;
+        if (snr_o) snr_o[j] = snr_db;
+        if (rate_o) rate_o[j] = rate;
+        if (cap_o) cap_o[j] = capacity;
+        if (obs_o) { /* envs/obs_fn.py:55-61 */
+            double *row = obs_o + 6 * j;
+            if (present) {
+                row[0] = pos[2 * txd[j]]; row[1] = pos[2 * txd[j] + 1];
+                row[2] = pos[2 * rxd[j]]; row[3] = pos[2 * rxd[j] + 1];
+                row[4] = sinr_db; row[5] = snr_db;
+            } else {
+                memset(row, 0, 6 * sizeof(double));
+            }
+        }
+    }
+
+    if (reward_o) { /* envs/reward_fn.py:27-44 */
+        int bad = 0;
+        for (int i = C; i < N && !bad; ++i) {            /* SIDELINK actions */
+            if (active && !active[i]) continue;
+            for (int k = 0; k < C; ++k) {                /* non-SIDELINK actions on the same RB */
+                if (active && !active[k]) continue;
+                if (rb[k] == rb[i] && cap[k] <= cfg->min_capacity_mbps) { bad = 1; break; }
+            }
+        }
+        /* len(actions) == 0 raises ZeroDivisionError in the reference; report NaN */
+        *reward_o = bad ? -1.0 : (n_present ? cap_sum / (double)n_present : NAN);
+    }
+    return status;
+}
+
+int d2d_oracle_step_batch(const d2d_oracle_cfg *cfg, const d2d_oracle_device *devices,
+                          int64_t E, const double *positions, const int32_t *actions,
+                          const uint8_t *active, int32_t *rb, int32_t *pwr,
+                          double *sinr_db, double *snr_db, double *rate, double *cap,
+                          double *obs, double *reward, int nthreads) {
+    const int C = cfg->num_cues, D = cfg->num_due_pairs, N = C + D, V = 1 + C + 2 * D;
+    int status = 0;
+#ifdef _OPENMP
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel num_threads(nthreads) reduction(min : status)
+#endif
+    {
+        int64_t *s_rb = (int64_t *)malloc(sizeof(int64_t) * 2 * (size_t)(N ? N : 1));
+        int64_t *s_pw = s_rb + N;
+        int32_t *s_tx = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)(N ? N : 1));
+        int32_t *s_rx = s_tx + N;
+        double *s_sinr = (double *)malloc(sizeof(double) * 2 * (size_t)(N ? N : 1));
+        double *s_cap = s_sinr + N;
+#ifdef _OPENMP
+#pragma omp for schedule(static)
+#endif
+        for (int64_t e = 0; e < E; ++e) {
+            int st = step_one(cfg, devices, positions + (size_t)e * V * 2, actions + (size_t)e * N,
+                              active ? active + (size_t)e * N : NULL,
+                              rb ? rb + (size_t)e * N : NULL, pwr ? pwr + (size_t)e * N : NULL,
+                              sinr_db ? sinr_db + (size_t)e * N : NULL, snr_db ? snr_db + (size_t)e * N : NULL,
+                              rate ? rate + (size_t)e * N : NULL, cap ? cap + (size_t)e * N : NULL,
+                              obs ? obs + (size_t)e * N * 6 : NULL, reward ? reward + e : NULL,
+                              s_rb, s_pw, s_tx, s_rx, s_sinr, s_cap);
+            if (st < status) status = st;
+        }
+        free(s_rb); free(s_tx); free(s_sinr);
+    }
+    return status;
+}
+
+/* envs/obs_fn.py:43-53 */
+void d2d_oracle_per_agent_obs(const double *table, const int32_t *present, int32_t n, double *out) {
+    for (int32_t i = 0; i < n; ++i) {
+        double *dst = out + (size_t)i * 6 * n;
+        memcpy(dst, table + 6 * present[i], 6 * sizeof(double));
+        dst += 6;
+        for (int32_t k = 0; k < n; ++k) {
+            if (k == i) continue;
+            memcpy(dst, table + 6 * present[k], 6 * sizeof(double));
+            dst += 6;
+        }
+    }
+}
+
+/* ---- Philox4x32-10 (Salmon et al., SC'11): the product's counter-based reset sampler ---- */
+void d2d_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* uniform-in-disc draw: theta = 2*pi*u1, r = radius*sqrt(u2)  (position.py:24-28, 41-44) */
+static void disc_draw(uint64_t seed, uint64_t genv, uint32_t dev, uint32_t attempt, double radius,
+                      double *x, double *y) {
+    uint32_t ctr[4] = {(uint32_t)genv, (uint32_t)(genv >> 32), dev, attempt};
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, o[4];
+    d2d_oracle_philox4x32_10(ctr, key, o);
+    double u1 = (double)(o[0] >> 8) * (1.0 / 16777216.0), u2 = (double)(o[1] >> 8) * (1.0 / 16777216.0);
+    double r = radius * sqrt(u2);
+    *x = r * cos(2.0 * M_PI * u1);
+    *y = r * sin(2.0 * M_PI * u1);
+}
+
+void d2d_oracle_reset_positions(const d2d_oracle_cfg *cfg, double cell_radius_m, double d2d_radius_m,
+                                uint64_t seed, uint64_t first_global_env, int64_t E, double *positions) {
+    const int C = cfg->num_cues, D = cfg->num_due_pairs, V = 1 + C + 2 * D;
+    for (int64_t e = 0; e < E; ++e) {
+        double *p = positions + (size_t)e * V * 2;
+        uint64_t g = first_global_env + (uint64_t)e;
+        p[0] = 0.0; p[1] = 0.0;                                    /* simulator.py:63-64 */
+        for (int v = 1; v <= C; ++v) disc_draw(seed, g, (uint32_t)v, 0, cell_radius_m, &p[2 * v], &p[2 * v + 1]);
+        for (int d = 0; d < D; ++d) {
+            int t = 1 + C + 2 * d, r = t + 1;
+            disc_draw(seed, g, (uint32_t)t, 0, cell_radius_m, &p[2 * t], &p[2 * t + 1]);
+            /* position.py:38-44: redraw until inside the cell (bounded to 64 attempts here) */
+            for (uint32_t a = 0; a < 64; ++a) {
+                double ox, oy;
+                disc_draw(seed, g, (uint32_t)r, a, d2d_radius_m, &ox, &oy);
+                p[2 * r] = p[2 * t] + ox; p[2 * r + 1] = p[2 * t + 1] + oy;
+                if (p[2 * r] * p[2 * r] + p[2 * r + 1] * p[2 * r + 1] <= cell_radius_m * cell_radius_m) break;
+            }
+        }
+    }
+}
