@@ -62,6 +62,7 @@ SIGNATURES = {
     'd2d_destroy': (C.c_int, [_vp]),
     'd2d_state_bytes': (C.c_int, [_vp, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     'd2d_bind_state': (C.c_int, [_vp, _vp, _vp, _vp]),
+    'd2d_bind_positions_f64': (C.c_int, [_vp, _vp]),
     'd2d_set_positions': (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _vp]),
     'd2d_reset': (C.c_int, [_vp, _u64, _u64, _vp, _vp]),
     'd2d_step': (C.c_int, [_vp, C.POINTER(D2DStepIO), _vp]),

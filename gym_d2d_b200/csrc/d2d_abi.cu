@@ -51,6 +51,7 @@ struct d2d_handle {
     double *dPwrD = nullptr;
     // bound state (caller-owned)
     float *pos = nullptr;
+    double *pos64 = nullptr;
     uint8_t *step_count = nullptr;
     double *stats = nullptr;
     // staging for d2d_step_host / d2d_set_positions (handle-owned, allocated on first use)
@@ -81,9 +82,16 @@ D2DParams make_params(const d2d_handle *h, const d2d_step_io_t *io) {
     P.snr_slope = (float)(5.0 * h->ple * std::log10(2.0));
     P.min_cap = (float)h->cfg.min_capacity_mbps;
     P.rescue_band_dB = h->ple2 ? 0.125f : 1.0f;
+    if (h->pos64) {
+        // positions were rounded to fp32: each coordinate is off by <= ulp(R)/2, a distance by <= ~sqrt(2) ulp(R),
+        // i.e. 10 ple log10(e) * sqrt(2) ulp(R) / d dB per term; recompute whatever that could push past 1e-4 relative
+        const double ulp = std::ldexp(1.0, std::ilogb(std::max(h->cfg.cell_radius_m, 1.0)) - 23);
+        P.rescue_c = (float)(2.0 * 1e4 * 4.3429448190325 * h->ple * std::sqrt(2.0) * ulp);
+        P.rescue_dmin2 = (float)std::pow(2.0 * 1e4 * 0.5 * h->ple * std::sqrt(2.0) * ulp, 2.0);   // capacity: d(ln r) = ple * dd/d
+    }
     P.ple_d = h->ple;
     P.linkA = h->dA; P.linkB = h->dB; P.linkD = h->dD; P.pwr_lin = h->dPwr; P.pwr_lin_d = h->dPwrD;
-    P.pos = h->pos; P.step_count = h->step_count; P.stats = h->stats;
+    P.pos = h->pos; P.pos64 = h->pos64; P.step_count = h->step_count; P.stats = h->stats;
     P.actions = io->actions; P.obs = io->obs; P.cap = io->capacity_mbps; P.reward = io->reward;
     P.done = io->done; P.rate = io->rate_bps; P.rb_out = io->rb; P.pwr_out = io->tx_pwr_dBm;
     return P;
@@ -204,7 +212,8 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
     D2D_CUDA_BAIL(cudaMemcpy(h->dPwr, pwr, sizeof(pwr), cudaMemcpyHostToDevice));
 #undef D2D_CUDA_BAIL
 
-    h->use_warp = h->N <= D2D_WARP_MAX_LINKS;
+    // the warp kernel's cross-slot bin table is exact for RB keys < 64
+    h->use_warp = h->N <= D2D_WARP_MAX_LINKS && cfg->num_rbs <= 64;
     int rc;
     if (h->use_warp) {
         rc = h->ple2 ? plan_geometry(h, d2d_step_warp_kernel<true>, D2D_WARP_WARPS_PER_BLOCK * 32, sizeof(D2DWarpSmem),
@@ -247,6 +256,14 @@ D2D_API int d2d_bind_state(d2d_handle_t *h, float *positions, uint8_t *step_coun
     return D2D_OK;
 }
 
+D2D_API int d2d_bind_positions_f64(d2d_handle_t *h, double *positions_f64) {
+    if (!h) return fail(D2D_ERR_INVALID_ARG, "d2d_bind_positions_f64: null handle");
+    if (positions_f64 && ((uintptr_t)positions_f64 % 16))
+        return fail(D2D_ERR_INVALID_ARG, "d2d_bind_positions_f64: buffer must be 16-byte aligned");
+    h->pos64 = positions_f64;
+    return D2D_OK;
+}
+
 D2D_API int d2d_set_positions(d2d_handle_t *h, const double *src, int src_on_device, int64_t first_env, int64_t count,
                               void *stream) {
     if (!h || !src) return fail(D2D_ERR_INVALID_ARG, "d2d_set_positions: null argument");
@@ -270,7 +287,8 @@ D2D_API int d2d_set_positions(d2d_handle_t *h, const double *src, int src_on_dev
     }
     const int64_t total = count * h->V;
     const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->num_sms * 8);
-    d2d_set_positions_kernel<<<grid, 256, 0, st>>>(dsrc, h->pos + first_env * h->V * 2, count, h->V);
+    d2d_set_positions_kernel<<<grid, 256, 0, st>>>(dsrc, h->pos + first_env * h->V * 2,
+                                                    h->pos64 ? h->pos64 + first_env * h->V * 2 : nullptr, count, h->V);
     D2D_CUDA(cudaGetLastError());
     ++h->launches;
     if (!src_on_device) D2D_CUDA(cudaStreamSynchronize(st));
@@ -284,7 +302,7 @@ D2D_API int d2d_reset(d2d_handle_t *h, uint64_t seed, uint64_t first_global_env,
     if (rc) return rc;
     const int64_t total = h->cfg.num_envs * h->N;
     const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->num_sms * 16);
-    d2d_reset_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->pos, h->step_count, env_mask, h->cfg.num_envs, h->cfg.num_cues,
+    d2d_reset_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->pos, h->pos64, h->step_count, env_mask, h->cfg.num_envs, h->cfg.num_cues,
                                                              h->cfg.num_due_pairs, (float)h->cfg.cell_radius_m,
                                                              (float)h->cfg.d2d_radius_m, seed, first_global_env);
     D2D_CUDA(cudaGetLastError());

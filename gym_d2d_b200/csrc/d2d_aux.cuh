@@ -6,12 +6,15 @@
 
 // Device.set_position over a batch (device.py:82-83): float64 [count][V][2] -> float32 state.
 // Device 0 (the MBS) is pinned to the origin like simulator.py:63-64.
-__global__ void d2d_set_positions_kernel(const double *__restrict__ src, float *__restrict__ dst, int64_t count, int V) {
+__global__ void d2d_set_positions_kernel(const double *__restrict__ src, float *__restrict__ dst,
+                                         double *__restrict__ dst64, int64_t count, int V) {
     const int64_t total = count * V;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int v = (int)(i % V);
-        const double2 s = reinterpret_cast<const double2 *>(src)[i];
-        reinterpret_cast<float2 *>(dst)[i] = v == 0 ? make_float2(0.f, 0.f) : make_float2((float)s.x, (float)s.y);
+        double2 s = reinterpret_cast<const double2 *>(src)[i];
+        if (v == 0) s = make_double2(0.0, 0.0);
+        reinterpret_cast<float2 *>(dst)[i] = make_float2((float)s.x, (float)s.y);
+        if (dst64) reinterpret_cast<double2 *>(dst64)[i] = s;      // unrounded shadow for the fp64 rescue path
     }
 }
 
@@ -32,7 +35,8 @@ __device__ __forceinline__ uint4 d2d_philox4x32_10(uint4 c, uint2 k) {
 __device__ __forceinline__ float2 d2d_disc_draw(uint64_t seed, uint64_t genv, uint32_t dev, uint32_t attempt, float radius) {
     const uint4 o = d2d_philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32), dev, attempt),
                                       make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-    const float u1 = (float)(o.x >> 8) * (1.0f / 16777216.0f), u2 = (float)(o.y >> 8) * (1.0f / 16777216.0f);
+    // 24-bit uniforms centred in their cell, so u is never 0 (r = 0 would put a receiver on its transmitter)
+    const float u1 = ((float)(o.x >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = ((float)(o.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
     float s, c;
     sincospif(2.0f * u1, &s, &c);
     const float r = radius * sqrtf(u2);
@@ -41,7 +45,7 @@ __device__ __forceinline__ float2 d2d_disc_draw(uint64_t seed, uint64_t genv, ui
 
 // Simulator.reset (simulator.py:61-75): one thread per (env, link slot); a DUE thread draws its tx in
 // the cell and re-draws its rx around the tx until it falls inside the cell (position.py:31-45).
-__global__ void d2d_reset_kernel(float *__restrict__ pos, uint8_t *__restrict__ step_count,
+__global__ void d2d_reset_kernel(float *__restrict__ pos, double *__restrict__ pos64, uint8_t *__restrict__ step_count,
                                  const uint8_t *__restrict__ env_mask, int64_t num_envs, int C, int D, float cell_radius,
                                  float d2d_radius, uint64_t seed, uint64_t first_global_env) {
     const int N = C + D, V = 1 + C + 2 * D;
@@ -52,12 +56,16 @@ __global__ void d2d_reset_kernel(float *__restrict__ pos, uint8_t *__restrict__ 
         if (env_mask && !env_mask[e]) continue;
         float2 *pe = reinterpret_cast<float2 *>(pos) + e * V;
         const uint64_t g = first_global_env + (uint64_t)e;
+        double2 *pe64 = pos64 ? reinterpret_cast<double2 *>(pos64) + e * V : nullptr;
         if (j == 0) {
             pe[0] = make_float2(0.f, 0.f);                       // simulator.py:63-64
+            if (pe64) pe64[0] = make_double2(0.0, 0.0);
             if (step_count) step_count[e] = 0;                   // envs/d2d_env.py:46
         }
         if (j < C) {
-            pe[1 + j] = d2d_disc_draw(seed, g, (uint32_t)(1 + j), 0, cell_radius);
+            const float2 c = d2d_disc_draw(seed, g, (uint32_t)(1 + j), 0, cell_radius);
+            pe[1 + j] = c;
+            if (pe64) pe64[1 + j] = make_double2((double)c.x, (double)c.y);
         } else {
             const int t = 1 + C + 2 * (j - C);
             const float2 tx = d2d_disc_draw(seed, g, (uint32_t)t, 0, cell_radius);
@@ -69,6 +77,7 @@ __global__ void d2d_reset_kernel(float *__restrict__ pos, uint8_t *__restrict__ 
             }
             pe[t] = tx;
             pe[t + 1] = rx;
+            if (pe64) { pe64[t] = make_double2((double)tx.x, (double)tx.y); pe64[t + 1] = make_double2((double)rx.x, (double)rx.y); }
         }
     }
 }

@@ -57,7 +57,9 @@ struct D2DParams {
     float neg_half_ple;          // -ple/2           : g = exp2(neg_half_ple * log2(d^2))
     float snr_slope;             // 5*ple*log10(2)   : SNR_dB = p + snr0 - snr_slope*log2(d^2)
     float min_cap;               // SystemCapacityRewardFunction.min_capacity_mbps
-    float rescue_band_dB;        // |SINR_dB| below this is recomputed in fp64
+    float rescue_band_dB;        // |SINR_dB| or |SNR_dB| below rescue_band_dB + rescue_c / d_min is recomputed in fp64
+    float rescue_c;              // 0 unless an fp64 position shadow is bound (covers the fp32 rounding of positions)
+    float rescue_dmin2;          // with a shadow: links with a distance^2 below this are always recomputed
     double ple_d;                // fp64 copy for the rescue path
     const D2DLinkA *linkA;       // [N]
     const D2DLinkB *linkB;       // [N]
@@ -66,6 +68,7 @@ struct D2DParams {
     const double *pwr_lin_d;     // same table in fp64 (rescue path)
     // state
     const float *pos;            // [E][V][2]
+    const double *pos64;         // [E][V][2] optional fp64 shadow of caller-supplied positions (rescue path only)
     uint8_t *step_count;         // [E]
     double *stats;               // [D2D_NUM_STATS] or nullptr
     // step io
@@ -93,6 +96,15 @@ __device__ __forceinline__ float d2d_rcp(float x) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+
+// envs/d2d_env.py:95: rb = a // n_pwr for a >= 0.  n_pwr is a runtime value, so divide by multiplying
+// with magic = ceil(2^32 / n) (exact for a < 2^32 / n; n = 1 has no 32-bit magic and is passed through).
+__host__ __device__ __forceinline__ uint32_t d2d_div_magic(int n) {
+    return n <= 1 ? 0u : (uint32_t)((0x100000000ull + (uint32_t)n - 1) / (uint32_t)n);
+}
+__device__ __forceinline__ int d2d_div(int a, uint32_t magic) {
+    return magic ? (int)__umulhi((uint32_t)a, magic) : a;
 }
 
 // Path gain g(d^2) = d^-ple.  PLE2: one MUFU.RCP; otherwise MUFU.LG2 + MUFU.EX2.
@@ -139,14 +151,17 @@ __device__ __forceinline__ D2DLinkOut d2d_link_epilogue(int p, float p_lin, floa
 }
 
 // ---- fp64 rescue ------------------------------------------------------------------------------------
-// A pure relative tolerance on SINR_dB is ill-conditioned where SINR_dB crosses 0: fp32 leaves ~1e-6 dB
-// of absolute error there.  (Rate, capacity and reward are well-conditioned at r ~ 1 and need nothing.)
-// Links whose fp32 SINR lands within rescue_band_dB of 0 dB therefore get SINR_dB recomputed in fp64
-// from the same fp32 inputs, in the linear domain with fp64-folded constants.  It is written without
-// libm calls on purpose: log10/pow would raise the whole kernel's register allocation for a path that
-// ~1e-4 of links take.  The kernels run it AFTER the env's outputs are stored, when nothing else is live.
+// A pure relative tolerance on a dB value is ill-conditioned where the value crosses 0: fp32 leaves
+// ~1e-6 dB of absolute error, and - when the caller supplied float64 positions that had to be rounded to
+// the fp32 device state - up to ~8.7 * ulp / d dB more for a link or interferer d metres away.  A link is
+// therefore recomputed in fp64 when   |SINR_dB| or |SNR_dB| < rescue_band_dB + rescue_c / d_min
+// (d_min = the smallest distance that entered its sums), or d_min^2 < rescue_dmin2.  rescue_c and
+// rescue_dmin2 are 0 unless an fp64 shadow of the positions is bound (d2d_bind_positions_f64), in which
+// case the recomputation also reads the unrounded positions.  The kernels run it AFTER the env's outputs
+// are stored, when nothing else is live, and overwrite that link's four values.  It is written without
+// libm calls on purpose: log10/pow would raise the whole kernel's register allocation for a rare path.
 
-// ln(r) for r in [0.7, 1.45]: 2 atanh((r-1)/(r+1)), odd series to s^19 (truncation < 1e-16 relative)
+// ln(r) for r in [0.7, 1.55]: 2 atanh((r-1)/(r+1)), odd series to s^19 (truncation < 1e-16 relative)
 __device__ __forceinline__ double d2d_ln_near1(double r) {
     const double s = (r - 1.0) / (r + 1.0), s2 = s * s;
     double q = 1.0 / 19.0;
@@ -187,20 +202,42 @@ __device__ __forceinline__ int d2d_pwr_of(const int32_t *act_env, int k, const D
     const int npw = k < P.C ? P.n_pwr_cue : P.n_pwr_due;
     return (a - (a / npw) * npw) & (D2D_MAX_PWR_LEVELS - 1);
 }
-// interferer k's fp64 contribution at receiver (rxx, rxy): w_k * g(d)
+__device__ __forceinline__ int d2d_tx_dev(int k, int C) { return k < C ? 1 + k : 1 + C + 2 * (k - C); }
+__device__ __forceinline__ int d2d_rx_dev(int k, int C) { return k < C ? 0 : 2 + C + 2 * (k - C); }
+// position of device v of this env: the fp64 shadow when bound, else the fp32 state (exact in that case)
+__device__ __forceinline__ double2 d2d_pos_f64(const float2 *pe32, const double2 *pe64, int v) {
+    if (pe64) return pe64[v];
+    const float2 p = pe32[v];
+    return make_double2((double)p.x, (double)p.y);
+}
+// interferer k's fp64 contribution at receiver rx: w_k * g(d)
 template <bool PLE2>
-__device__ __forceinline__ double d2d_ix_term_f64(int k, const float4 &rk, float rxx, float rxy, const int32_t *act_env,
-                                                  const D2DParams &P) {
-    const double ex = (double)rk.x - (double)rxx, ey = (double)rk.y - (double)rxy;
+__device__ __forceinline__ double d2d_ix_term_f64(int k, double2 rx, const float2 *pe32, const double2 *pe64,
+                                                  const int32_t *act_env, const D2DParams &P) {
+    const double2 tk = d2d_pos_f64(pe32, pe64, d2d_tx_dev(k, P.C));
+    const double ex = tk.x - rx.x, ey = tk.y - rx.y;
     return P.pwr_lin_d[d2d_pwr_of(act_env, k, P)] * P.linkD[k].t_lin * d2d_gain_f64<PLE2>(ex * ex + ey * ey, P.ple_d);
 }
-// SINR_dB of link j from its fp64 interference sum (simulator.py:106-107 in the linear domain)
+// all four outputs of link j from its fp64 interference sum (simulator.py:93,106-107,115,118-154)
 template <bool PLE2>
-__device__ __forceinline__ float d2d_sinr_f64(int j, float txx, float txy, float rxx, float rxy, double I,
-                                              const int32_t *act_env, const D2DParams &P) {
+__device__ __forceinline__ D2DLinkOut d2d_link_f64(int j, double2 tx, double2 rx, double I, float sens_dBm,
+                                                   const int32_t *act_env, const D2DParams &P) {
     const D2DLinkD Lj = P.linkD[j];
-    const double dx = (double)txx - (double)rxx, dy = (double)txy - (double)rxy;
+    const double dx = tx.x - rx.x, dy = tx.y - rx.y;
     const double S = P.pwr_lin_d[d2d_pwr_of(act_env, j, P)] * Lj.a_lin * d2d_gain_f64<PLE2>(dx * dx + dy * dy, P.ple_d);
     const double r = S / fma(I, Lj.inv_noise, 1.0);            // a_lin already carries 1/noise
-    return (float)(4.3429448190325182765 * d2d_ln_near1(r));   // 10 log10(r), |r - 1| small by construction
+    const double sinr = 4.3429448190325182765 * d2d_ln_f64(r); // 10 log10
+    const double rate = 1.4426950408889634074 * d2d_ln_f64(1.0 + r);
+    const bool ok = sinr > (double)sens_dBm;
+    D2DLinkOut o;
+    o.sinr_dB = (float)sinr;
+    o.snr_dB = (float)(4.3429448190325182765 * d2d_ln_f64(S));
+    o.rate = ok ? (float)rate : 0.0f;
+    o.cap = ok ? (float)(Lj.bw_MHz * rate) : 0.0f;
+    return o;
+}
+// does this link need the fp64 pass?  dmin2 = smallest squared distance that entered its sums
+__device__ __forceinline__ bool d2d_needs_rescue(const D2DLinkOut &o, float dmin2, const D2DParams &P) {
+    const float band = fmaf(P.rescue_c, rsqrtf(dmin2), P.rescue_band_dB);
+    return fminf(fabsf(o.sinr_dB), fabsf(o.snr_dB)) < band || dmin2 < P.rescue_dmin2;
 }

@@ -63,8 +63,7 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_kernel(const
         S.linkB[i] = reinterpret_cast<const float4 *>(P.linkB)[i];
     }
     for (int i = tid; i < D2D_MAX_PWR_LEVELS; i += D2D_BLOCK_THREADS) S.pwr_lin[i] = P.pwr_lin[i];
-    const uint32_t magic_cue = (uint32_t)((0x100000000ull + (uint32_t)P.n_pwr_cue - 1) / (uint32_t)P.n_pwr_cue);
-    const uint32_t magic_due = (uint32_t)((0x100000000ull + (uint32_t)P.n_pwr_due - 1) / (uint32_t)P.n_pwr_due);
+    const uint32_t magic_cue = d2d_div_magic(P.n_pwr_cue), magic_due = d2d_div_magic(P.n_pwr_due);
 
     double st_reward = 0.0, st_cap = 0.0, st_reward2 = 0.0, st_pen = 0.0, st_resc = 0.0, st_n = 0.0;
 
@@ -82,7 +81,7 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_kernel(const
             const float2 t = __ldg(pe + txd), r = __ldg(pe + rxd);
             const bool active = a >= 0;
             const int npw = cue ? P.n_pwr_cue : P.n_pwr_due;
-            const int rb = (int)__umulhi((uint32_t)a, cue ? magic_cue : magic_due), p = a - rb * npw;
+            const int rb = d2d_div(a, cue ? magic_cue : magic_due), p = a - rb * npw;
             const uint32_t key = active ? (uint32_t)rb : (D2D_INACTIVE_KEY | (uint32_t)j);
             const float pl = active ? S.pwr_lin[p & (D2D_MAX_PWR_LEVELS - 1)] : 0.0f;
             S.rec[j] = make_float4(t.x, t.y, pl * S.linkA[j].x, __uint_as_float(key));
@@ -123,14 +122,16 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_kernel(const
             D2DLinkOut o = {0.f, 0.f, 0.f, 0.f};
             if (active) {
                 const int b = key % (uint32_t)nbins, beg = S.bin_off[b], end = beg + S.bin_cnt[b];
-                float I = 0.0f;
+                float I = 0.0f, dmin2 = 3.0e38f;
                 bool side = false;
                 for (int q = beg; q < end; ++q) {
                     const int k = S.sorted[q];
                     const float4 rk = S.rec[k];
                     if (k != j && __float_as_uint(rk.w) == key) {
                         const float dx = rk.x - xj.x, dy = rk.y - xj.y;
-                        I = fmaf(rk.z, d2d_gain<PLE2>(fmaf(dx, dx, dy * dy), P.neg_half_ple), I);
+                        const float d2 = fmaf(dx, dx, dy * dy);
+                        I = fmaf(rk.z, d2d_gain<PLE2>(d2, P.neg_half_ple), I);
+                        dmin2 = fminf(dmin2, d2);
                         side |= (k >= C);
                     }
                 }
@@ -138,15 +139,17 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_kernel(const
                 const D2DLinkA A = {Av.x, Av.y, Av.z, Av.w};
                 const D2DLinkB B = {Bv.x, Bv.y, 0, 0};
                 const float dx = rj.x - xj.x, dy = rj.y - xj.y;
-                o = d2d_link_epilogue<PLE2>(p, xj.z, fmaf(dx, dx, dy * dy), I, A, B, P);
-                if (fabsf(o.sinr_dB) < P.rescue_band_dB) {   // rare: fp64 SINR_dB near 0 dB (d2d_common.cuh)
+                const float d2own = fmaf(dx, dx, dy * dy);
+                o = d2d_link_epilogue<PLE2>(p, xj.z, d2own, I, A, B, P);
+                if (D2D_RESCUE_ENABLED && d2d_needs_rescue(o, fminf(dmin2, d2own), P)) {   // rare: fp64 pass (d2d_common.cuh)
+                    const double2 *pe64 = P.pos64 ? reinterpret_cast<const double2 *>(P.pos64) + e * V : nullptr;
+                    const double2 rx = d2d_pos_f64(pe, pe64, d2d_rx_dev(j, C));
                     double I64 = 0.0;
                     for (int q = beg; q < end; ++q) {
                         const int k = S.sorted[q];
-                        const float4 rk = S.rec[k];
-                        if (k != j && __float_as_uint(rk.w) == key) I64 += d2d_ix_term_f64<PLE2>(k, rk, xj.x, xj.y, act, P);
+                        if (k != j && __float_as_uint(S.rec[k].w) == key) I64 += d2d_ix_term_f64<PLE2>(k, rx, pe, pe64, act, P);
                     }
-                    o.sinr_dB = d2d_sinr_f64<PLE2>(j, rj.x, rj.y, xj.x, xj.y, I64, act, P);
+                    o = d2d_link_f64<PLE2>(j, d2d_pos_f64(pe, pe64, d2d_tx_dev(j, C)), rx, I64, B.sens_dBm, act, P);
                     ++resc;
                 }
                 cap_part += o.cap;

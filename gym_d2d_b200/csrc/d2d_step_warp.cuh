@@ -40,7 +40,7 @@ struct D2DWarpSmem {
 
 template <bool PLE2>
 __device__ __forceinline__ float d2d_walk_peers(uint32_t mask, int base, uint32_t key, float rxx, float rxy,
-                                                const float4 *rec, int C, float nhp, bool &sidelink_peer) {
+                                                const float4 *rec, int C, float nhp, bool &sidelink_peer, float &dmin2) {
     float I = 0.0f;
     while (mask) {
         const int k = base + __ffs(mask) - 1;
@@ -50,6 +50,7 @@ __device__ __forceinline__ float d2d_walk_peers(uint32_t mask, int base, uint32_
             const float dx = r.x - rxx, dy = r.y - rxy;
             const float d2 = fmaf(dx, dx, dy * dy);
             I = fmaf(r.z, d2d_gain<PLE2>(d2, nhp), I);
+            dmin2 = fminf(dmin2, d2);
             sidelink_peer |= (k >= C);
         }
     }
@@ -70,6 +71,9 @@ d2d_step_warp_kernel(const D2DParams P) {
     }
     for (int i = threadIdx.x; i < D2D_MAX_PWR_LEVELS; i += blockDim.x) S.pwr_lin[i] = P.pwr_lin[i];
     if (threadIdx.x < 8) S.stats[threadIdx.x] = 0.0;
+    // bin tags start at 0 and `iter` at 1: shared memory left behind by an earlier block can never look current
+    for (int i = threadIdx.x; i < D2D_WARP_WARPS_PER_BLOCK * 128; i += blockDim.x)
+        S.w[i >> 7].bins[(i >> 6) & 1][i & 63] = make_uint2(0u, 0u);
     __syncthreads();
 
     D2DWarpSmem::PerWarp &W = S.w[warp];
@@ -77,9 +81,7 @@ d2d_step_warp_kernel(const D2DParams P) {
     const bool has0 = j0 < N, has1 = j1 < N;
     const bool cue0 = j0 < C, cue1 = j1 < C;
     const int npw0 = cue0 ? P.n_pwr_cue : P.n_pwr_due, npw1 = cue1 ? P.n_pwr_cue : P.n_pwr_due;
-    // exact unsigned division by the (runtime) number of power levels for a < 2^32 / n_pwr
-    const uint32_t magic0 = (uint32_t)((0x100000000ull + (uint32_t)npw0 - 1) / (uint32_t)npw0);
-    const uint32_t magic1 = (uint32_t)((0x100000000ull + (uint32_t)npw1 - 1) / (uint32_t)npw1);
+    const uint32_t magic0 = d2d_div_magic(npw0), magic1 = d2d_div_magic(npw1);
     const int tx0 = cue0 ? 1 + j0 : 1 + C + 2 * (j0 - C), rx0 = cue0 ? 0 : tx0 + 1;
     const int tx1 = cue1 ? 1 + j1 : 1 + C + 2 * (j1 - C), rx1 = cue1 ? 0 : tx1 + 1;
     const uint32_t lane_bit = 1u << lane;
@@ -100,8 +102,8 @@ d2d_step_warp_kernel(const D2DParams P) {
         const bool act0 = a0 >= 0, act1 = a1 >= 0;
 
         // envs/d2d_env.py:93-101: rb = a // n_pwr, p = a % n_pwr
-        const int rb0 = (int)__umulhi((uint32_t)a0, magic0), p0 = a0 - rb0 * npw0;
-        const int rb1 = (int)__umulhi((uint32_t)a1, magic1), p1 = a1 - rb1 * npw1;
+        const int rb0 = d2d_div(a0, magic0), p0 = a0 - rb0 * npw0;
+        const int rb1 = d2d_div(a1, magic1), p1 = a1 - rb1 * npw1;
         const uint32_t key0 = act0 ? (uint32_t)rb0 : (D2D_INACTIVE_KEY | (uint32_t)lane);
         const uint32_t key1 = act1 ? (uint32_t)rb1 : (D2D_INACTIVE_KEY | 32u | (uint32_t)lane);
 
@@ -124,14 +126,14 @@ d2d_step_warp_kernel(const D2DParams P) {
 
         // simulator.py:95-101 interference at each victim's receiver
         bool side0 = false, side1 = false;
-        float I0 = 0.0f, I1 = 0.0f;
+        float I0 = 0.0f, I1 = 0.0f, dmin0 = 3.0e38f, dmin1 = 3.0e38f;
         if (act0) {
-            I0 = d2d_walk_peers<PLE2>(m00 & ~lane_bit, 0, key0, r0.x, r0.y, W.rec, C, P.neg_half_ple, side0);
-            I0 += d2d_walk_peers<PLE2>(m01, 32, key0, r0.x, r0.y, W.rec, C, P.neg_half_ple, side0);
+            I0 = d2d_walk_peers<PLE2>(m00 & ~lane_bit, 0, key0, r0.x, r0.y, W.rec, C, P.neg_half_ple, side0, dmin0);
+            I0 += d2d_walk_peers<PLE2>(m01, 32, key0, r0.x, r0.y, W.rec, C, P.neg_half_ple, side0, dmin0);
         }
         if (act1) {
-            I1 = d2d_walk_peers<PLE2>(m10, 0, key1, r1.x, r1.y, W.rec, C, P.neg_half_ple, side1);
-            I1 += d2d_walk_peers<PLE2>(m11 & ~lane_bit, 32, key1, r1.x, r1.y, W.rec, C, P.neg_half_ple, side1);
+            I1 = d2d_walk_peers<PLE2>(m10, 0, key1, r1.x, r1.y, W.rec, C, P.neg_half_ple, side1, dmin1);
+            I1 += d2d_walk_peers<PLE2>(m11 & ~lane_bit, 32, key1, r1.x, r1.y, W.rec, C, P.neg_half_ple, side1, dmin1);
         }
 
         // per-link epilogue (simulator.py:93,106-107,110-127,144-154)
@@ -141,15 +143,17 @@ d2d_step_warp_kernel(const D2DParams P) {
             const float4 Bv = S.linkB[j0];
             const D2DLinkB B0 = {Bv.x, Bv.y, 0, 0};
             const float dx = t0.x - r0.x, dy = t0.y - r0.y;
-            o0 = d2d_link_epilogue<PLE2>(p0, pl0, fmaf(dx, dx, dy * dy), I0, A0, B0, P);
-            if (fabsf(o0.sinr_dB) < P.rescue_band_dB) need |= 1;
+            const float d2 = fmaf(dx, dx, dy * dy);
+            o0 = d2d_link_epilogue<PLE2>(p0, pl0, d2, I0, A0, B0, P);
+            if (d2d_needs_rescue(o0, fminf(dmin0, d2), P)) need |= 1;
         }
         if (act1) {
             const float4 Bv = S.linkB[j1];
             const D2DLinkB B1 = {Bv.x, Bv.y, 0, 0};
             const float dx = t1.x - r1.x, dy = t1.y - r1.y;
-            o1 = d2d_link_epilogue<PLE2>(p1, pl1, fmaf(dx, dx, dy * dy), I1, A1, B1, P);
-            if (fabsf(o1.sinr_dB) < P.rescue_band_dB) need |= 2;
+            const float d2 = fmaf(dx, dx, dy * dy);
+            o1 = d2d_link_epilogue<PLE2>(p1, pl1, d2, I1, A1, B1, P);
+            if (d2d_needs_rescue(o1, fminf(dmin1, d2), P)) need |= 2;
         }
 
         // envs/reward_fn.py:27-44
@@ -204,30 +208,31 @@ d2d_step_warp_kernel(const D2DParams P) {
         st_reward += reward; st_cap += cap_sum; st_reward2 = fmaf(reward, reward, st_reward2);
         st_pen += bad ? 1 : 0;
 
-        // rare: fp64 SINR_dB for links that landed within the band around 0 dB.  Runs after the stores so
-        // none of the per-link state above is live; the whole warp cooperates on each flagged link.
+        // rare: fp64 recomputation of flagged links (d2d_common.cuh).  Runs after the stores so none of the
+        // per-link state above is live; the whole warp cooperates on each flagged link.
         if (D2D_RESCUE_ENABLED && __any_sync(0xffffffffu, need != 0)) {
+            const double2 *pe64 = P.pos64 ? reinterpret_cast<const double2 *>(P.pos64) + e * V : nullptr;
 #pragma unroll 1
             for (int s = 0; s < 2; ++s) {
                 uint32_t todo = __ballot_sync(0xffffffffu, (need >> s) & 1);
                 while (todo) {
                     const int j = 32 * s + __ffs(todo) - 1;
                     todo &= todo - 1;
-                    const float4 rj = W.rec[j];
-                    const uint32_t key = __float_as_uint(rj.w);
-                    const int rxd = j < C ? 0 : 2 + C + 2 * (j - C);
-                    const float2 rx = __ldg(pe + rxd);
+                    const uint32_t key = __float_as_uint(W.rec[j].w);
+                    const double2 rx = d2d_pos_f64(pe, pe64, d2d_rx_dev(j, C));
                     double I = 0.0;
 #pragma unroll 1
-                    for (int k = lane; k < N; k += 32) {
-                        const float4 rk = W.rec[k];
-                        if (k != j && __float_as_uint(rk.w) == key) I += d2d_ix_term_f64<PLE2>(k, rk, rx.x, rx.y, act, P);
-                    }
+                    for (int k = lane; k < N; k += 32)
+                        if (k != j && __float_as_uint(W.rec[k].w) == key) I += d2d_ix_term_f64<PLE2>(k, rx, pe, pe64, act, P);
 #pragma unroll
                     for (int sh = 16; sh > 0; sh >>= 1) I += __shfl_xor_sync(0xffffffffu, I, sh);
                     if (lane == 0) {
-                        const float sinr = d2d_sinr_f64<PLE2>(j, rj.x, rj.y, rx.x, rx.y, I, act, P);
-                        if (P.obs) P.obs[(e * N + j) * 6 + 4] = sinr;
+                        const D2DLinkOut o = d2d_link_f64<PLE2>(j, d2d_pos_f64(pe, pe64, d2d_tx_dev(j, C)), rx, I,
+                                                                S.linkB[j].x, act, P);
+                        const int64_t g = e * N + j;
+                        if (P.obs) *reinterpret_cast<float2 *>(P.obs + g * 6 + 4) = make_float2(o.sinr_dB, o.snr_dB);
+                        if (P.cap) P.cap[g] = o.cap;
+                        if (P.rate) P.rate[g] = o.rate;
                         ++st_resc;
                     }
                 }

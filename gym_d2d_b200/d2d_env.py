@@ -31,7 +31,7 @@ class D2DEnv:
     def __init__(self, env_config: Optional[dict] = None, device: Any = 'cuda', seed: int = 0) -> None:
         env_config = env_config or {}
         # VecD2DEnv pops 'obs_fn' / 'reward_fn' from the caller's dict exactly like envs/d2d_env.py:27-28
-        self.vec = VecD2DEnv(1, env_config, device=device, seed=seed, info=True)
+        self.vec = VecD2DEnv(1, env_config, device=device, seed=seed, info=True, exact_positions=True)
         cfg = self.vec.config
         self.config = cfg
         r = cfg.cell_radius_m
@@ -111,7 +111,7 @@ class D2DEnv:
         self.vec.reset(mask=np_mask_all(self.vec))                    # positions + counters only
         file_devices = self.config.devices
         if file_devices:                                               # simulator.py:65-66
-            pos = self.vec.positions[0].cpu().numpy().astype(np.float64)
+            pos = self.vec.positions_f64[0].cpu().numpy()
             for idx, id_ in enumerate(self.device_ids):
                 if idx and id_ in file_devices and 'position' in file_devices[id_]:
                     pos[idx] = file_devices[id_]['position']
@@ -157,12 +157,12 @@ class D2DEnv:
 
     # ---- device config I/O (envs/d2d_env.py:124-134, envs/env_config.py:32-37) -----------------------
     def device_positions(self) -> Dict[str, Tuple[float, float]]:
-        pos = self.vec.positions[0].cpu().numpy()
+        pos = self.vec.positions_f64[0].cpu().numpy()
         return {id_: (float(pos[i, 0]), float(pos[i, 1])) for i, id_ in enumerate(self.device_ids)}
 
     def set_device_positions(self, positions: Dict[str, Tuple[float, float]]) -> None:
         """Batch form of Device.set_position (device.py:82-83) for this env."""
-        pos = self.vec.positions[0].cpu().numpy().astype(np.float64)
+        pos = self.vec.positions_f64[0].cpu().numpy()
         index = {id_: i for i, id_ in enumerate(self.device_ids)}
         for id_, xy in positions.items():
             pos[index[id_]] = xy                                       # KeyError on unknown id, like devices.py:28

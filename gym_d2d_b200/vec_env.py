@@ -34,10 +34,15 @@ class VecD2DEnv:
     device : CUDA device.
     seed, global_env_offset : Philox key and the global index of local env 0; a sharded batch draws the
         same scenario for a given global env whatever the number of GPUs.
+    info : also return rate_bps / rb / tx_pwr_dbm tensors (the reference's info dict, envs/d2d_env.py:106-116).
+    exact_positions : keep a float64 shadow of positions given through set_positions().  The hot path still
+        reads the fp32 state; the shadow is read only by the kernels' rare fp64 recomputation path, so that
+        results stay within 1e-4 relative of the reference evaluated on the caller's UNROUNDED float64
+        positions (device-config files).  Not needed for positions drawn on the device by reset().
     """
 
     def __init__(self, num_envs: int, env_config: Optional[dict] = None, device: Any = 'cuda', seed: int = 0,
-                 global_env_offset: int = 0, info: bool = False) -> None:
+                 global_env_offset: int = 0, info: bool = False, exact_positions: bool = False) -> None:
         env_config = env_config if env_config is not None else {}
         obs_enum = resolve_obs_fn(env_config.pop('obs_fn', LinearObsFunction))
         reward_enum, min_cap = resolve_reward_fn(env_config.pop('reward_fn', SystemCapacityRewardFunction))
@@ -79,6 +84,9 @@ class VecD2DEnv:
         self.step_count = torch.zeros((E,), dtype=torch.uint8, device=dev)
         self._stats = torch.zeros((_lib.STATS_REPLICAS, _lib.NUM_STATS), dtype=torch.float64, device=dev)
         self._bind(True)
+        self.positions_f64 = torch.zeros((E, V, 2), dtype=torch.float64, device=dev) if exact_positions else None
+        if exact_positions:
+            _lib.check(self._lib.d2d_bind_positions_f64(self._h, self.positions_f64.data_ptr()))
         # output buffers, reused by every step (clone what you keep)
         self.obs = torch.zeros((E, N, 6), dtype=torch.float32, device=dev)
         self.capacity_mbps = torch.zeros((E, N), dtype=torch.float32, device=dev)

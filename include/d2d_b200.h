@@ -128,6 +128,12 @@ D2D_API int d2d_state_bytes(const d2d_handle_t *h, size_t *positions_bytes, size
  * (envs/d2d_env.py:43) and the statistics accumulators (stats may be NULL). */
 D2D_API int d2d_bind_state(d2d_handle_t *h, float *positions, uint8_t *step_count, double *stats);
 
+/* Optional float64 shadow of the positions, float64 [E][V][2] (NULL unbinds).  When bound, d2d_set_positions /
+ * d2d_reset also write it, and the step kernels read it in their rare fp64 recomputation path only: links whose
+ * results the fp32 rounding of caller-supplied float64 positions could move by more than 1e-4 relative are
+ * recomputed from the unrounded positions.  The hot path still reads only the fp32 state. */
+D2D_API int d2d_bind_positions_f64(d2d_handle_t *h, double *positions_f64);
+
 /* Replaces Device.set_position over a batch (device.py:82-83; device_config_file positions,
  * simulator.py:65-66).  src is float64 [count][V][2], host memory if src_on_device == 0 (the call then
  * synchronises the stream).  Device 0 (MBS) is pinned to (0,0) as simulator.py:63-64 does. */

@@ -233,7 +233,7 @@ static void disc_draw(uint64_t seed, uint64_t genv, uint32_t dev, uint32_t attem
     uint32_t ctr[4] = {(uint32_t)genv, (uint32_t)(genv >> 32), dev, attempt};
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, o[4];
     d2d_oracle_philox4x32_10(ctr, key, o);
-    double u1 = (double)(o[0] >> 8) * (1.0 / 16777216.0), u2 = (double)(o[1] >> 8) * (1.0 / 16777216.0);
+    double u1 = ((double)(o[0] >> 8) + 0.5) * (1.0 / 16777216.0), u2 = ((double)(o[1] >> 8) + 0.5) * (1.0 / 16777216.0);
     double r = radius * sqrt(u2);
     *x = r * cos(2.0 * M_PI * u1);
     *y = r * sin(2.0 * M_PI * u1);

@@ -1,0 +1,207 @@
+"""CPU tier: host-side logic of the product package and the shape of the C ABI (no compute calls)."""
+import ctypes as C
+import functools
+import json
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+import gym_d2d_b200 as G
+from gym_d2d_b200 import _lib, config as cfgmod, plugins
+from oracle import d2d_oracle as O
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+# ---- C ABI ---------------------------------------------------------------------------------------------
+def _declared_symbols():
+    text = (ROOT / 'include' / 'd2d_b200.h').read_text()
+    return sorted(set(re.findall(r'^D2D_API\s+[\w\s\*]+?\b(d2d_\w+)\s*\(', text, flags=re.M)))
+
+
+def test_library_exports_every_declared_symbol():
+    declared = _declared_symbols()
+    assert len(declared) >= 14 and 'd2d_step' in declared and 'd2d_step_host' in declared
+    lib = C.CDLL(str(_lib.lib_path()))
+    for name in declared:
+        assert hasattr(lib, name), f'{name} is declared in include/d2d_b200.h but not exported'
+    assert sorted(_lib.SIGNATURES) == declared        # the ctypes binding covers exactly the header
+    assert _lib.load().d2d_abi_version() == _lib.ABI_VERSION
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(_lib.D2DConfig) == 2 * 4 + 8 + 10 * 4 + 5 * 8
+    assert C.sizeof(_lib.D2DLink) == 5 * 8 + 2 * 4
+    assert C.sizeof(_lib.D2DStepIO) == 8 * C.sizeof(C.c_void_p)
+
+
+def test_error_paths_without_gpu():
+    """Argument errors are reported through codes + d2d_last_error, never by aborting."""
+    lib = _lib.load()
+    assert lib.d2d_create(None, None, None) == _lib.ERR_INVALID_ARG
+    assert b'null' in lib.d2d_last_error()
+    cfg = cfgmod.to_c_config(G.EnvConfig(), 4, 0, 0, 0, 0.0)
+    links = (_lib.D2DLink * 50)(*[_lib.D2DLink(**r) for r in cfgmod.link_table(G.EnvConfig())])
+    h = C.c_void_p()
+    cfg.abi_version = 99
+    assert lib.d2d_create(C.byref(cfg), links, C.byref(h)) == _lib.ERR_INVALID_ARG
+    cfg.abi_version = _lib.ABI_VERSION
+    cfg.path_loss_model = 7
+    assert lib.d2d_create(C.byref(cfg), links, C.byref(h)) == _lib.ERR_UNSUPPORTED
+    assert lib.d2d_step(None, None, None) == _lib.ERR_INVALID_ARG
+    assert lib.d2d_launch_count(None) == -1
+
+
+def test_product_never_imports_the_oracle():
+    for py in (ROOT / 'gym_d2d_b200').glob('*.py'):
+        src = py.read_text()
+        assert 'oracle' not in re.sub(r'""".*?"""', '', src, flags=re.S).replace('# oracle', ''), py.name
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is present')
+    with pytest.raises(Exception):
+        G.VecD2DEnv(4, {})
+    with pytest.raises(_lib.D2DError):
+        G.VecD2DEnv(4, {}, device='cpu')
+
+
+# ---- EnvConfig surface (envs/env_config.py:12-27) -------------------------------------------------------------
+def test_env_config_defaults_and_keys():
+    c = G.EnvConfig()
+    expect = dict(num_rbs=25, num_cues=25, num_due_pairs=25, cell_radius_m=500.0, d2d_radius_m=20.0,
+                  due_min_tx_power_dBm=0, due_max_tx_power_dBm=20, cue_max_tx_power_dBm=23, mbs_max_tx_power_dBm=46,
+                  carrier_freq_GHz=2.1, num_subcarriers=12, subcarrier_spacing_kHz=15, channel_bandwidth_MHz=20.0,
+                  device_config_file=None)
+    for k, v in expect.items():
+        assert getattr(c, k) == v
+    assert c.path_loss_model is G.LogDistancePathLoss and c.traffic_model is G.UplinkTrafficModel
+    assert c.num_pwr_actions == {'due': 21, 'cue': 24, 'mbs': 47}           # envs/d2d_env.py:31-35
+    with pytest.raises(TypeError):
+        G.EnvConfig(unknown_key=1)
+
+
+def test_device_and_link_order():
+    """test/gym_d2d/test_simulator.py:5-18 + devices.py:20-25 + envs/d2d_env.py:55-60"""
+    c = G.EnvConfig(num_cues=3, num_due_pairs=2)
+    assert c.device_ids() == ['mbs', 'cue00', 'cue01', 'cue02', 'due00', 'due01', 'due02', 'due03']
+    assert c.link_keys() == ['cue00:mbs', 'cue01:mbs', 'cue02:mbs', 'due00:due01', 'due02:due03']
+    assert c.device_ids() == O.OracleConfig(num_cues=3, num_due_pairs=2).device_ids()
+    wide = G.EnvConfig(num_cues=1, num_due_pairs=500)
+    assert wide.link_keys()[-1] == 'due998:due999'
+    cfgs = c.device_configs()
+    assert cfgs['cue00']['max_tx_power_dBm'] == 23 and cfgs['due00']['max_tx_power_dBm'] == 20
+    assert cfgs['mbs']['max_tx_power_dBm'] == 46.0                            # Appendix B.5: not propagated
+
+
+def test_link_table_matches_oracle_device_arithmetic(golden_dir):
+    """The product folds device.py's link budget per link; the oracle evaluates it per call.  Same numbers."""
+    dev = json.loads((golden_dir / 'overrides_device_config.json').read_text())
+    for kw, overrides, path in [({}, {}, None),
+                                (dict(num_rbs=3, num_cues=3, num_due_pairs=4), {k: v['config'] for k, v in dev.items()},
+                                 golden_dir / 'overrides_device_config.json')]:
+        c = G.EnvConfig(**kw, device_config_file=path)
+        oc = O.OracleConfig(**kw, device_overrides=overrides)
+        devs, L = O.device_table(oc), O.lib()
+        for j, row in enumerate(cfgmod.link_table(c)):
+            t = 1 + j if j < c.num_cues else 1 + c.num_cues + 2 * (j - c.num_cues)
+            r = 0 if j < c.num_cues else t + 1
+            assert row['tx_eirp_offset_dB'] == pytest.approx(L.d2d_oracle_eirp_dBm(C.byref(devs[t]), 0.0), abs=1e-12)
+            assert row['rx_offset_dB'] == pytest.approx(L.d2d_oracle_rx_signal_level_dBm(C.byref(devs[r]), 0.0, 0.0), abs=1e-12)
+            assert row['rx_noise_dBm'] == devs[r].thermal_noise_dBm
+            assert row['rx_sensitivity_dBm'] == pytest.approx(L.d2d_oracle_rx_sensitivity_dBm(C.byref(devs[r])), abs=1e-12)
+            assert row['tx_rb_bandwidth_kHz'] == L.d2d_oracle_rb_bandwidth_kHz(C.byref(devs[t]))
+    t0 = cfgmod.link_table(G.EnvConfig())
+    assert (t0[0]['tx_eirp_offset_dB'], t0[0]['rx_offset_dB'], t0[0]['rx_sensitivity_dBm']) == (-6.0, 17.5, pytest.approx(-123.4))
+    assert (t0[-1]['rx_offset_dB'], t0[-1]['rx_noise_dBm'], t0[-1]['rx_sensitivity_dBm']) == (-3.0, -104.5, -107.5)
+
+
+# ---- plugin resolution ------------------------------------------------------------------------------------------
+def test_supported_plugins_resolve():
+    assert plugins.resolve_path_loss(G.LogDistancePathLoss) == (_lib.PL_LOG_DISTANCE, 2.0)
+    assert plugins.resolve_path_loss(G.FreeSpacePathLoss) == (_lib.PL_FREE_SPACE, 2.0)
+    assert plugins.resolve_path_loss(functools.partial(G.LogDistancePathLoss, ple=3.5)) == (_lib.PL_LOG_DISTANCE, 3.5)
+    assert plugins.resolve_obs_fn(G.LinearObsFunction) == _lib.OBS_LINEAR
+    assert plugins.resolve_reward_fn(G.SystemCapacityRewardFunction) == (_lib.REWARD_SYSTEM_CAPACITY, 0.0)
+    assert plugins.resolve_reward_fn(functools.partial(G.SystemCapacityRewardFunction, min_capacity_mbps=0.5))[1] == 0.5
+
+
+def test_reference_classes_are_accepted_by_identity():
+    from oracle import ref_runner as R
+    if R.import_reference() is None:
+        pytest.skip('reference not importable here')
+    from gym_d2d.envs.obs_fn import LinearObsFunction as RefObs
+    from gym_d2d.envs.reward_fn import ShannonRewardFunction as RefShannon, SystemCapacityRewardFunction as RefRew
+    from gym_d2d.path_loss import CostHataPathLoss as RefHata, LogDistancePathLoss as RefLD
+    assert plugins.resolve_path_loss(RefLD) == (_lib.PL_LOG_DISTANCE, 2.0)
+    assert plugins.resolve_obs_fn(RefObs) == _lib.OBS_LINEAR
+    assert plugins.resolve_reward_fn(RefRew) == (_lib.REWARD_SYSTEM_CAPACITY, 0.0)
+    for bad in (RefHata,):
+        with pytest.raises(G.UnsupportedPluginError):
+            plugins.resolve_path_loss(bad)
+    with pytest.raises(G.UnsupportedPluginError):
+        plugins.resolve_reward_fn(RefShannon)
+
+
+def test_custom_and_unimplemented_plugins_are_rejected():
+    class CustomPathLoss(G.LogDistancePathLoss):      # examples/custom_path_loss.py
+        def __call__(self, tx, rx):
+            return 100.0
+
+    class CustomObs(G.LinearObsFunction):
+        pass
+
+    for bad in (CustomPathLoss, G.ShadowingPathLoss, G.CostHataPathLoss, functools.partial(G.FreeSpacePathLoss, ple=3.0)):
+        with pytest.raises(G.UnsupportedPluginError):
+            plugins.resolve_path_loss(bad)
+    with pytest.raises(G.UnsupportedPluginError):
+        plugins.resolve_obs_fn(CustomObs)
+    for bad in (G.ShannonRewardFunction, G.CueSinrShannonRewardFunction):
+        with pytest.raises(G.UnsupportedPluginError):
+            plugins.resolve_reward_fn(bad)
+    with pytest.raises(TypeError):
+        plugins.resolve_path_loss(G.LogDistancePathLoss(2.1))   # an instance, not a class
+
+
+def test_make_rejects_unknown_id():
+    with pytest.raises(ValueError):
+        G.make('NotAnEnv-v0')
+
+
+# ---- the integer decode the kernel uses (envs/d2d_env.py:93-101) ----------------------------------------------------
+def _kernel_decode(a: int, n: int):
+    """Bit-for-bit model of the device code (d2d_div_magic / d2d_div in csrc/d2d_common.cuh):
+    rb = umulhi(a, ceil(2^32 / n)) for n > 1, a for n == 1; p = a - rb * n."""
+    magic = 0 if n <= 1 else ((1 << 32) + n - 1) // n
+    assert magic < 1 << 32
+    rb = (a * magic) >> 32 if magic else a
+    return rb, a - rb * n
+
+
+@settings(max_examples=400, deadline=None)
+@given(n=st.integers(1, 128), a=st.integers(0, 2 ** 24))
+def test_magic_division_is_exact(n, a):
+    assert _kernel_decode(a, n) == (a // n, a % n)
+
+
+def test_magic_division_exhaustive_for_default_spaces():
+    for n, hi in ((21, 25 * 21), (24, 25 * 24), (47, 25 * 47), (24, 100 * 24), (21, 100 * 21)):
+        a = np.arange(hi, dtype=np.int64)
+        magic = ((1 << 32) + n - 1) // n
+        rb = (a * magic) >> 32
+        assert (rb == a // n).all() and (a - rb * n == a % n).all()
+
+
+def test_shard_range_partitions_the_batch():
+    from gym_d2d_b200.dist import shard_range
+    for total, world in [(1048576, 8), (4096, 3), (5, 8), (1000, 7)]:
+        spans = [shard_range(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == total
+        for (f0, c0), (f1, _c1) in zip(spans, spans[1:]):
+            assert f0 + c0 == f1
+        assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
