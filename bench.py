@@ -1,0 +1,461 @@
+#!/usr/bin/env python
+"""bench.py - batched env-steps/s of the GymD2D step path on N B200s (one process per GPU).
+
+    python bench.py --gpus 1 --steps K --warmup W                       # this repo's CUDA path
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...    # N > 1 (contiguous env slices)
+    python bench.py --impl reference --steps K --warmup W               # the reference's CPU env.step loop
+
+A "step" is one env.step of the whole batch: ONE fused kernel launch over E envs per GPU (decode ->
+per-RB interference -> SINR/SNR -> Shannon capacity -> observation table -> reward -> done).  The workload
+is BASELINE.json configs[1]: 4096 default-config (25 RB / 25 CUE / 25 DUE-pair) envs per GPU, positions
+resident in HBM, pre-generated uniform random RB/power actions.  Weak scaling: every rank owns
+--envs-per-gpu envs.  Prints ONE JSON line on rank 0 (see the keys below and DESIGN.md section 5).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+METRIC = 'batched_env_steps_per_sec'
+UNIT = 'env-steps/s'
+RING = 32           # distinct action / output buffer sets cycled through, so per-step I/O never sits in L2
+
+
+def algorithmic_bytes_per_env_step(N: int, V: int) -> int:
+    """read actions 4N + positions 8V; write obs 24N + capacity 4N + reward 4 + done 1."""
+    return 32 * N + 8 * V + 5
+
+
+def hbm_peak():
+    f = ROOT / 'MEASURED_PEAKS.json'
+    if f.exists():
+        try:
+            return float(json.loads(f.read_text())['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks: sampled through NVML in a background thread while the benchmark runs
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: 'gpu_idle', 0x2: 'applications_clocks_setting', 0x4: 'sw_power_cap', 0x8: 'hw_slowdown',
+               0x10: 'sync_boost', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown',
+               0x80: 'hw_power_brake_slowdown', 0x100: 'display_clock_setting'}
+
+    def __init__(self, index: int) -> None:
+        self.samples = []           # (t, sm_mhz, reasons_bitmask)
+        self.sm_max = None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _run(self) -> None:
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append((time.perf_counter(), int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                     int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))))
+            except Exception:  # noqa: BLE001
+                try:
+                    self.samples.append((time.perf_counter(), int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)),
+                                         int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))))
+                except Exception:  # noqa: BLE001
+                    break
+            time.sleep(0.002)
+
+    def start(self) -> None:
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self) -> None:
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(1.0)
+
+    def summary(self, windows) -> dict:
+        """Median SM clock over the samples that fall inside the timed windows [(t0, t1), ...]."""
+        if not self.samples:
+            return {'sm_mhz': None, 'sm_max_mhz': self.sm_max, 'reasons': [], 'samples': 0}
+        inside = [s for s in self.samples if any(t0 <= s[0] <= t1 for t0, t1 in windows)]
+        note = 'timed regions'
+        if len(inside) < 3:     # the timed region is shorter than the NVML polling period: fall back to every
+            inside = [s for s in self.samples if not (s[2] & 0x1)] or self.samples   # sample taken under load
+            note = 'whole bench (timed region shorter than the NVML period)'
+        clocks = sorted(s[1] for s in inside)
+        mask = 0
+        for s in inside:
+            mask |= s[2]
+        reasons = [name for bit, name in self.REASONS.items() if mask & bit and name != 'gpu_idle']
+        return {'sm_mhz': clocks[len(clocks) // 2], 'sm_max_mhz': self.sm_max, 'reasons': reasons,
+                'samples': len(inside), 'window': note}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arms: the unmodified reference (baseline/_ref, kind "reference") or the C oracle (kind "port")
+# ------------------------------------------------------------------------------------------------------------
+_REF_ENV = None
+
+
+def _ref_worker_init(seed: int) -> None:
+    global _REF_ENV
+    import random
+    sys.path.insert(0, str(ROOT))
+    from oracle import ref_runner as R
+    random.seed(seed + os.getpid())
+    _REF_ENV = R.make_env({})
+    _REF_ENV.reset()
+
+
+def _ref_worker_steps(m: int) -> int:
+    """m env.step calls on the reference's default D2DEnv with pre-sampled random actions."""
+    env = _REF_ENV
+    cue_keys = [k for k in env.actions.keys()]   # (tx, rx) id pairs in canonical order
+    keys = [':'.join(k) for k in cue_keys]
+    import random
+    n_cue = env.action_space['cue'].n
+    n_due = env.action_space['due'].n
+    acts = [{k: random.randrange(n_cue if k.startswith('cue') else n_due) for k in keys} for _ in range(m)]
+    t0 = time.perf_counter()
+    for a in acts:
+        env.step(a)
+    return m if time.perf_counter() - t0 >= 0 else 0
+
+
+class CpuArm:
+    """Times the reference's own CPU implementation of the step path on all host cores."""
+
+    def __init__(self) -> None:
+        from oracle import ref_runner as R
+        self.cores = os.cpu_count() or 1
+        self.kind = 'reference' if R.reference_src() is not None else 'port'
+        self.pool = None
+        if self.kind == 'reference':
+            import multiprocessing as mp
+            ctx = mp.get_context('spawn')
+            self.pool = ctx.Pool(self.cores, initializer=_ref_worker_init, initargs=(1234,))
+            self.pool.map(_ref_worker_steps, [2] * self.cores)       # spin the workers up
+        else:
+            import numpy as np
+            from oracle import d2d_oracle as O
+            self.O, self.np = O, np
+            self.cfg = O.OracleConfig()
+            self.rng = np.random.default_rng(0)
+
+    def run(self, env_steps_per_core: int) -> float:
+        """Processes cores * env_steps_per_core env-steps of the default config; returns seconds."""
+        t0 = time.perf_counter()
+        if self.kind == 'reference':
+            self.pool.map(_ref_worker_steps, [env_steps_per_core] * self.cores)
+        else:
+            E = env_steps_per_core * self.cores
+            pos = self.O.random_positions(self.cfg, E, self.rng)
+            act = self.O.random_actions(self.cfg, E, self.rng)
+            t0 = time.perf_counter()
+            self.O.step_batch(self.cfg, pos, act, nthreads=self.cores)
+        return time.perf_counter() - t0
+
+    def close(self) -> None:
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+
+
+def cpu_baseline(budget_s: float = 12.0) -> dict:
+    arm = CpuArm()
+    per_core = 256 if arm.kind == 'reference' else 4096
+    t = arm.run(per_core)
+    reps = max(1, int(budget_s / max(t, 1e-3)) - 1)
+    total_t, total_n = 0.0, 0
+    for _ in range(reps):
+        total_t += arm.run(per_core)
+        total_n += per_core * arm.cores
+    out = {'value': total_n / total_t, 'unit': UNIT, 'cores': arm.cores, 'kind': arm.kind,
+           'sample': f'{total_n} env-steps of the default 25/25/25 config ({arm.cores} processes x {reps} x {per_core} '
+                     f'env.step calls, one D2DEnv each, random actions) in {total_t:.1f} s'}
+    arm.close()
+    if arm.kind == 'reference':      # also time the compiled float64 restatement, for context
+        try:
+            import numpy as np
+            from oracle import d2d_oracle as O
+            cfg = O.OracleConfig()
+            rng = np.random.default_rng(0)
+            E = 65536
+            pos, act = O.random_positions(cfg, E, rng), O.random_actions(cfg, E, rng)
+            O.step_batch(cfg, pos[:1024], act[:1024], nthreads=arm.cores)
+            t0 = time.perf_counter()
+            O.step_batch(cfg, pos, act, nthreads=arm.cores)
+            out['port'] = {'value': E / (time.perf_counter() - t0), 'unit': UNIT, 'cores': arm.cores,
+                           'kind': 'port', 'sample': f'{E} env-steps, C oracle with OpenMP'}
+        except Exception as exc:  # noqa: BLE001
+            out['port'] = {'error': str(exc)}
+    return out
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    arm = CpuArm()
+    per_core = 128 if arm.kind == 'reference' else 8192
+    for _ in range(args.warmup):
+        arm.run(per_core)
+    t = 0.0
+    for _ in range(args.steps):
+        t += arm.run(per_core)
+    n = per_core * arm.cores * args.steps
+    value = n / t
+    sample = (f'each step = {arm.cores} x {per_core} env.step calls of the default 25/25/25 config '
+              f'({"unmodified reference via baseline/_ref" if arm.kind == "reference" else "C oracle port, OpenMP"})')
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1e3 * t / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic', 'impl': 'reference',
+            'config': {'workload': 'D2DEnv-v0 defaults (25 RB / 25 CUE / 25 DUE pairs), random actions, CPU env.step loop',
+                       'env_steps_per_step': per_core * arm.cores},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': arm.cores, 'kind': arm.kind, 'sample': sample},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    arm.close()
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# the CUDA arm
+# ------------------------------------------------------------------------------------------------------------
+def timed_steps(env, torch, actions, outs, steps, warmup, dist, use_graph=True):
+    """W untimed + EXACTLY K timed steps; step i reads actions[i % RING] and writes outs[i % RING].
+    Returns (seconds [max over ranks], perf_counter window, launches)."""
+    ring = len(actions)
+
+    def eager(i0, n):
+        for i in range(i0, i0 + n):
+            env.step(actions[i % ring], out=outs[i % ring])
+
+    graph = None
+    if use_graph and steps >= ring:
+        eager(0, ring)                                   # module load + first-touch before capture
+        graph = env.capture_steps(actions, outs)         # one graph = RING consecutive steps
+    eager(0, warmup)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = env.launch_count
+    t0 = time.perf_counter()
+    start.record()
+    done = 0
+    if graph is not None:
+        for _ in range(steps // ring):
+            graph.replay()
+        done = (steps // ring) * ring
+    eager(done, steps - done)
+    stop.record()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    secs = start.elapsed_time(stop) * 1e-3
+    launches = (env.launch_count - l0) + done          # graph replays launch `done` step kernels
+    if dist is not None:
+        t = torch.tensor([secs], dtype=torch.float64, device=env.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        secs = float(t.item())
+        dist.barrier()
+    return secs, (t0, t1), launches
+
+
+def run_cuda_arm(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    import gym_d2d_b200 as G
+    from gym_d2d_b200.dist import all_reduce_stats, shard_range, summarise
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: gym_d2d_b200 has no CPU path (use --impl reference for the CPU arm)')
+    torch.cuda.set_device(local)
+    pg = None
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+        pg = dist
+    n_gpus = world
+    E = args.envs_per_gpu
+    first, _ = shard_range(E * world, rank, world)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    windows = []
+
+    def build(num_envs, seed=0):
+        env = G.VecD2DEnv(num_envs, {}, device=torch.device('cuda', local), seed=seed, global_env_offset=first)
+        env.reset()
+        gen = torch.Generator(device=env.device)
+        gen.manual_seed(1000 + rank)
+        acts = [env.sample_actions(gen) for _ in range(RING)]
+        outs = [env.alloc_outputs() for _ in range(RING)]
+        return env, acts, outs
+
+    # ---- headline: configs[1], E envs per GPU --------------------------------------------------------------
+    env, acts, outs = build(E)
+    N, V = env.num_links, env.num_devices
+    B = algorithmic_bytes_per_env_step(N, V)
+    comm_stream = torch.cuda.Stream() if world > 1 else None
+    secs, win, launches = timed_steps(env, torch, acts, outs, args.steps, args.warmup, pg)
+    windows.append(win)
+    if world > 1:   # episode statistics: one tiny all-reduce, off the step stream (never inside the step)
+        stats = env.stats_tensor()
+        comm_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(comm_stream):
+            all_reduce_stats(stats)
+        torch.cuda.current_stream().wait_stream(comm_stream)
+        stats_summary = summarise(stats)
+    else:
+        stats_summary = summarise(env.stats_tensor())
+    value = world * E * args.steps / secs
+    peak, peak_src = hbm_peak()
+    per_launch_s = secs / args.steps
+    achieved = B * E / per_launch_s / 1e9
+    geometry = env.step_geometry()
+    ring_bytes = RING * (acts[0].numel() * 4 + outs[0].nbytes())
+
+    traffic = None
+    prof = ROOT / 'profiles' / 'roofline_r01.json'
+    if prof.exists():
+        try:
+            traffic = json.loads(prof.read_text()).get(f'dram_bytes_per_launch_E{E}')
+        except Exception:  # noqa: BLE001
+            traffic = None
+
+    # ---- end to end through the C ABI with HOST buffers (d2d_step_host): H2D actions + D2H results per step ----
+    e2e = None
+    if not args.skip_e2e:
+        host_out = env.alloc_host_outputs(pinned=True, info=False)
+        host_acts = [torch.empty((E, N), dtype=torch.int32, pin_memory=True) for _ in range(4)]
+        for h, a in zip(host_acts, acts):
+            h.copy_(a)
+        host_np = [h.numpy() for h in host_acts]
+        e2e_steps = max(10, min(args.steps, 200))
+        for i in range(3):
+            env.step_host(host_np[i % 4], host_out)
+        torch.cuda.synchronize()
+        if pg is not None:
+            pg.barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            env.step_host(host_np[i % 4], host_out)      # synchronous: returns with the results on the host
+        t1 = time.perf_counter()
+        windows.append((t0, t1))
+        dt = t1 - t0
+        if pg is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device=env.device)
+            pg.all_reduce(t, op=pg.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {'value': world * E * e2e_steps / dt, 'unit': UNIT, 'h2d_bytes_per_step': E * N * 4,
+               'd2h_bytes_per_step': E * N * 24 + E * N * 4 + E * 4 + E, 'steps': e2e_steps,
+               'api': 'd2d_step_host via VecD2DEnv.step_host (pinned host buffers; obs + capacity + reward + done copied back)'}
+    env.close()
+    del env, acts, outs
+
+    # ---- large batch: BASELINE configs[4]'s per-GPU slice (131072 envs, working set 290 MB > L2) ---------------
+    large = None
+    if args.large_envs_per_gpu > 0:
+        envL, actsL, outsL = build(args.large_envs_per_gpu, seed=1)
+        stepsL = max(RING, min(args.steps, 4 * RING))
+        secsL, winL, _ = timed_steps(envL, torch, actsL[:8], outsL[:8], stepsL, max(3, min(args.warmup, 8)), pg)
+        windows.append(winL)
+        EL = args.large_envs_per_gpu
+        achL = B * EL / (secsL / stepsL) / 1e9
+        large = {'workload': f'{EL} default-config envs per GPU (BASELINE configs[4] slice; working set > L2)',
+                 'value': world * EL * stepsL / secsL, 'unit': UNIT, 'steps': stepsL, 'ms_per_step': 1e3 * secsL / stepsL,
+                 'roofline': {'bound': 'hbm', 'achieved': achL, 'peak': peak, 'unit': 'GB/s', 'frac': achL / peak,
+                              'traffic': None}}
+        if prof.exists():
+            try:
+                large['roofline']['traffic'] = json.loads(prof.read_text()).get(f'dram_bytes_per_launch_E{EL}')
+            except Exception:  # noqa: BLE001
+                pass
+        envL.close()
+        del envL, actsL, outsL
+
+    sampler.stop()
+    clocks = sampler.summary(windows)
+
+    base = None
+    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        base = cpu_baseline()
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': n_gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1e3 * secs / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'BASELINE configs[1]: {E} batched default-config envs per GPU (25 RB / 25 CUE / 25 DUE pairs, '
+                                   'LogDistancePathLoss), device-resident positions, uniform random RB/power actions',
+                       'envs_per_gpu': E, 'num_links': N, 'num_devices': V, 'obs': 'compact [E][N][6] float32 table',
+                       'parallelism': f'env-sharded x{world}', 'launch': f'CUDA graph of {RING} step kernels' if args.steps >= RING else 'eager',
+                       'grid': geometry['grid'], 'block': geometry['block'], 'smem_bytes': geometry['smem_bytes'],
+                       'l2': f'ring of {RING} action/output buffer sets ({ring_bytes / 1e6:.0f} MB > 126 MB L2) so per-step I/O is '
+                             'never L2-resident; the {:.1f} MB position state stays L2-resident by design'.format(E * V * 8 / 1e6),
+                       'stats_allreduce': 'once per run on a side stream' if world > 1 else 'none (1 GPU)'},
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                         'traffic': traffic, 'algorithmic_bytes_per_env_step': B, 'bytes_per_launch': B * E,
+                         'peak_source': peak_src,
+                         'note': 'duration = timed region / K launches (launch gaps included); E envs = '
+                                 f'{E / (geometry["grid"] * geometry["envs_per_block"]):.2f} envs per resident warp slot'},
+            'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks, 'episode_stats': stats_summary,
+        }
+        if large is not None:
+            line['large_batch'] = large
+        if base is not None:
+            line['cpu_baseline'] = base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=2048)
+    ap.add_argument('--warmup', type=int, default=64)
+    ap.add_argument('--impl', choices=['cuda', 'reference'], default='cuda')
+    ap.add_argument('--envs-per-gpu', type=int, default=4096)
+    ap.add_argument('--large-envs-per-gpu', type=int, default=131072)
+    ap.add_argument('--skip-e2e', action='store_true')
+    ap.add_argument('--skip-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == 'reference':
+        if args.steps == 2048 and args.warmup == 64:       # defaults sized for the GPU arm; keep the CPU arm to ~1 min
+            args.steps, args.warmup = 20, 3
+        run_reference_arm(args)
+    else:
+        run_cuda_arm(args)
+
+
+if __name__ == '__main__':
+    main()

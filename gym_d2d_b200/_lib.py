@@ -77,17 +77,20 @@ _lib = None
 
 
 def lib_path() -> Path:
-    return LIB
+    """The in-tree library; D2D_B200_LIB points tuning runs at an alternative build of the same sources."""
+    import os
+    return Path(os.environ.get('D2D_B200_LIB', LIB))
 
 
 def load():
     """dlopen libd2d_b200.so.  Raises if it has not been built - there is no CPU fallback."""
     global _lib
     if _lib is None:
-        if not LIB.exists():
-            raise D2DError(f'{LIB} is missing: build it with `python -m gym_d2d_b200.build` (needs nvcc). '
+        LIB_ = lib_path()
+        if not LIB_.exists():
+            raise D2DError(f'{LIB_} is missing: build it with `python -m gym_d2d_b200.build` (needs nvcc). '
                            'gym_d2d_b200 has no CPU fallback.')
-        lib = C.CDLL(str(LIB))
+        lib = C.CDLL(str(LIB_))
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args

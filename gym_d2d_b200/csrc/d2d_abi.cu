@@ -77,11 +77,15 @@ D2DParams make_params(const d2d_handle *h, const d2d_step_io_t *io) {
     P.n_pwr_cue = h->cfg.n_pwr_cue; P.n_pwr_due = h->cfg.n_pwr_due;
     P.episode_length = h->cfg.episode_length;
     P.nbins = h->cfg.num_rbs;
+    P.magic_cue = d2d_div_magic(h->cfg.n_pwr_cue);
+    P.magic_due = d2d_div_magic(h->cfg.n_pwr_due);
+    P.align4 = (h->V % 2 == 0) && ((1 + h->cfg.num_cues) % 2 == 0) && ((uintptr_t)h->pos % 16 == 0);
     P.ple = (float)h->ple;
     P.neg_half_ple = (float)(-0.5 * h->ple);
     P.snr_slope = (float)(5.0 * h->ple * std::log10(2.0));
     P.min_cap = (float)h->cfg.min_capacity_mbps;
-    P.rescue_band_dB = h->ple2 ? 0.125f : 1.0f;
+    // worst-case fp32 error of SINR_dB is ~6e-6 dB for ple = 2 (d2d_common.cuh); x 1e4 for a 1e-4 relative bound
+    P.rescue_band_dB = h->ple2 ? 0.0625f : 0.5f;
     if (h->pos64) {
         // positions were rounded to fp32: each coordinate is off by <= ulp(R)/2, a distance by <= ~sqrt(2) ulp(R),
         // i.e. 10 ple log10(e) * sqrt(2) ulp(R) / d dB per term; recompute whatever that could push past 1e-4 relative
@@ -212,14 +216,12 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
     D2D_CUDA_BAIL(cudaMemcpy(h->dPwr, pwr, sizeof(pwr), cudaMemcpyHostToDevice));
 #undef D2D_CUDA_BAIL
 
-    // the warp kernel's cross-slot bin table is exact for RB keys < 64
-    h->use_warp = h->N <= D2D_WARP_MAX_LINKS && cfg->num_rbs <= 64;
+    // warp kernel: one lane slot per CUE and per DUE pair; its cross-slot bin table is exact for RB keys < 64
+    h->use_warp = cfg->num_cues <= 32 && cfg->num_due_pairs <= 32 && cfg->num_rbs <= 64;
     int rc;
     if (h->use_warp) {
-        rc = h->ple2 ? plan_geometry(h, d2d_step_warp_kernel<true>, D2D_WARP_WARPS_PER_BLOCK * 32, sizeof(D2DWarpSmem),
-                                     D2D_WARP_WARPS_PER_BLOCK)
-                     : plan_geometry(h, d2d_step_warp_kernel<false>, D2D_WARP_WARPS_PER_BLOCK * 32, sizeof(D2DWarpSmem),
-                                     D2D_WARP_WARPS_PER_BLOCK);
+        rc = h->ple2 ? plan_geometry(h, d2d_step_warp_kernel<true, false>, D2D_WARP_WARPS_PER_BLOCK * 32, 0, D2D_WARP_WARPS_PER_BLOCK)
+                     : plan_geometry(h, d2d_step_warp_kernel<false, false>, D2D_WARP_WARPS_PER_BLOCK * 32, 0, D2D_WARP_WARPS_PER_BLOCK);
     } else {
         const size_t smem = d2d_block_smem_bytes(h->N, cfg->num_rbs);
         if (smem > 227 * 1024) return bail(fail(D2D_ERR_UNSUPPORTED, "d2d_create: too many links / RBs for one SM's shared memory"));
@@ -314,17 +316,43 @@ D2D_API int d2d_step(d2d_handle_t *h, const d2d_step_io_t *io, void *stream) {
     if (!h || !io || !io->actions) return fail(D2D_ERR_INVALID_ARG, "d2d_step: handle, io and io->actions are required");
     if (!h->pos) return fail(D2D_ERR_STATE, "d2d_step: call d2d_bind_state first");
     if (io->obs && ((uintptr_t)io->obs % 8)) return fail(D2D_ERR_INVALID_ARG, "d2d_step: obs must be 8-byte aligned");
-    const D2DParams P = make_params(h, io);
+    D2DParams P = make_params(h, io);
     cudaStream_t st = (cudaStream_t)stream;
-    if (h->use_warp) {
-        if (h->ple2) d2d_step_warp_kernel<true><<<h->grid, h->block, h->smem, st>>>(P);
-        else d2d_step_warp_kernel<false><<<h->grid, h->block, h->smem, st>>>(P);
-    } else {
-        if (h->ple2) d2d_step_block_kernel<true><<<h->grid, h->block, h->smem, st>>>(P);
-        else d2d_step_block_kernel<false><<<h->grid, h->block, h->smem, st>>>(P);
+    // the kernels index with 32 bits: batches beyond 2^31 / max(6N, 2V) envs (> 7 million default envs) go in chunks
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)0x7fffffff / std::max(6 * h->N, 2 * h->V));
+    for (int64_t e0 = 0; e0 < h->cfg.num_envs; e0 += chunk) {
+        const int64_t n = std::min<int64_t>(chunk, h->cfg.num_envs - e0);
+        if (e0 > 0) {
+            const int64_t dl = chunk * h->N;
+            P.actions += dl; P.pos += chunk * h->V * 2;
+            if (P.pos64) P.pos64 += chunk * h->V * 2;
+            if (P.step_count) P.step_count += chunk;
+            if (P.obs) P.obs += dl * 6;
+            if (P.cap) P.cap += dl;
+            if (P.reward) P.reward += chunk;
+            if (P.done) P.done += chunk;
+            if (P.rate) P.rate += dl;
+            if (P.rb_out) P.rb_out += dl;
+            if (P.pwr_out) P.pwr_out += dl;
+        }
+        P.num_envs = n;
+        const int grid = (int)std::min<int64_t>(h->grid, (n + h->envs_per_block - 1) / h->envs_per_block);
+        if (h->use_warp) {
+            const bool exact = h->pos64 != nullptr;
+            if (h->ple2) {
+                if (exact) d2d_step_warp_kernel<true, true><<<grid, h->block, 0, st>>>(P);
+                else d2d_step_warp_kernel<true, false><<<grid, h->block, 0, st>>>(P);
+            } else {
+                if (exact) d2d_step_warp_kernel<false, true><<<grid, h->block, 0, st>>>(P);
+                else d2d_step_warp_kernel<false, false><<<grid, h->block, 0, st>>>(P);
+            }
+        } else {
+            if (h->ple2) d2d_step_block_kernel<true><<<grid, h->block, h->smem, st>>>(P);
+            else d2d_step_block_kernel<false><<<grid, h->block, h->smem, st>>>(P);
+        }
+        ++h->launches;
     }
     D2D_CUDA(cudaGetLastError());
-    ++h->launches;
     return D2D_OK;
 }
 

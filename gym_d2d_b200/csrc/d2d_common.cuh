@@ -53,6 +53,8 @@ struct D2DParams {
     int32_t n_pwr_cue, n_pwr_due;
     int32_t episode_length;
     int32_t nbins;               // block kernel: number of RB bins
+    int32_t align4;              // warp kernel: every env's DUE (tx, rx) pair is a 16-byte aligned float4
+    uint32_t magic_cue, magic_due;  // d2d_div_magic(n_pwr_cue / n_pwr_due)
     float ple;                   // path-loss exponent
     float neg_half_ple;          // -ple/2           : g = exp2(neg_half_ple * log2(d^2))
     float snr_slope;             // 5*ple*log10(2)   : SNR_dB = p + snr0 - snr_slope*log2(d^2)
@@ -132,21 +134,20 @@ struct D2DLinkOut {
     float sinr_dB, snr_dB, rate, cap;
 };
 
-// Per-link epilogue in fp32 (Appendix A).  p_lin = 10^(p/10), d2 = own-link distance^2, I = interference.
+// Per-link epilogue in fp32 (Appendix A).  p_lin = 10^(p/10); lg_d2 = log2(d^2) and g = d^-ple of the own link;
+// I = interference [mW]; cA = (tx_lin0, a_lin, inv_noise, snr0_dB); sb = (sens_dBm, bw_MHz).
 template <bool PLE2>
-__device__ __forceinline__ D2DLinkOut d2d_link_epilogue(int p, float p_lin, float d2, float I, const D2DLinkA &A,
-                                                        const D2DLinkB &B, const D2DParams &P) {
+__device__ __forceinline__ D2DLinkOut d2d_link_epilogue(int p, float p_lin, float lg_d2, float g, float I, const float4 &cA,
+                                                        const float2 &sb, const D2DParams &P) {
     D2DLinkOut o;
-    const float lg_d2 = d2d_lg2(d2);
-    const float g = PLE2 ? d2d_rcp(d2) : d2d_ex2(P.neg_half_ple * lg_d2);
-    const float snr_lin = p_lin * A.a_lin * g;
-    const float r = snr_lin * d2d_rcp(fmaf(I, A.inv_noise, 1.0f));
-    o.snr_dB = ((float)p + A.snr0_dB) - P.snr_slope * lg_d2;
+    const float snr_lin = p_lin * cA.y * g;
+    const float r = snr_lin * d2d_rcp(fmaf(I, cA.z, 1.0f));
+    o.snr_dB = ((float)p + cA.w) - P.snr_slope * lg_d2;
     o.sinr_dB = 3.0102999566398120f * d2d_lg2(r);
-    const bool ok = o.sinr_dB > B.sens_dBm;
+    const bool ok = o.sinr_dB > sb.x;
     const float rate = d2d_log2_1p(r);
     o.rate = ok ? rate : 0.0f;
-    o.cap = ok ? B.bw_MHz * rate : 0.0f;
+    o.cap = ok ? sb.y * rate : 0.0f;
     return o;
 }
 
@@ -236,8 +237,10 @@ __device__ __forceinline__ D2DLinkOut d2d_link_f64(int j, double2 tx, double2 rx
     o.cap = ok ? (float)(Lj.bw_MHz * rate) : 0.0f;
     return o;
 }
-// does this link need the fp64 pass?  dmin2 = smallest squared distance that entered its sums
+// does this link need the fp64 pass?  dmin2 = smallest squared distance that entered its sums (EXACT only)
+template <bool EXACT>
 __device__ __forceinline__ bool d2d_needs_rescue(const D2DLinkOut &o, float dmin2, const D2DParams &P) {
-    const float band = fmaf(P.rescue_c, rsqrtf(dmin2), P.rescue_band_dB);
-    return fminf(fabsf(o.sinr_dB), fabsf(o.snr_dB)) < band || dmin2 < P.rescue_dmin2;
+    const float lo = fminf(fabsf(o.sinr_dB), fabsf(o.snr_dB));
+    if (!EXACT) return lo < P.rescue_band_dB;
+    return lo < fmaf(P.rescue_c, rsqrtf(dmin2), P.rescue_band_dB) || dmin2 < P.rescue_dmin2;
 }

@@ -136,12 +136,12 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_kernel(const
                     }
                 }
                 const float4 Av = S.linkA[j], Bv = S.linkB[j];
-                const D2DLinkA A = {Av.x, Av.y, Av.z, Av.w};
-                const D2DLinkB B = {Bv.x, Bv.y, 0, 0};
+                const float2 sb = make_float2(Bv.x, Bv.y);
                 const float dx = rj.x - xj.x, dy = rj.y - xj.y;
                 const float d2own = fmaf(dx, dx, dy * dy);
-                o = d2d_link_epilogue<PLE2>(p, xj.z, d2own, I, A, B, P);
-                if (D2D_RESCUE_ENABLED && d2d_needs_rescue(o, fminf(dmin2, d2own), P)) {   // rare: fp64 pass (d2d_common.cuh)
+                const float lg = d2d_lg2(d2own);
+                o = d2d_link_epilogue<PLE2>(p, xj.z, lg, PLE2 ? d2d_rcp(d2own) : d2d_ex2(P.neg_half_ple * lg), I, Av, sb, P);
+                if (D2D_RESCUE_ENABLED && d2d_needs_rescue<true>(o, fminf(dmin2, d2own), P)) {   // rare: fp64 pass (d2d_common.cuh)
                     const double2 *pe64 = P.pos64 ? reinterpret_cast<const double2 *>(P.pos64) + e * V : nullptr;
                     const double2 rx = d2d_pos_f64(pe, pe64, d2d_rx_dev(j, C));
                     double I64 = 0.0;
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_kernel(const
                         const int k = S.sorted[q];
                         if (k != j && __float_as_uint(S.rec[k].w) == key) I64 += d2d_ix_term_f64<PLE2>(k, rx, pe, pe64, act, P);
                     }
-                    o = d2d_link_f64<PLE2>(j, d2d_pos_f64(pe, pe64, d2d_tx_dev(j, C)), rx, I64, B.sens_dBm, act, P);
+                    o = d2d_link_f64<PLE2>(j, d2d_pos_f64(pe, pe64, d2d_tx_dev(j, C)), rx, I64, sb.x, act, P);
                     ++resc;
                 }
                 cap_part += o.cap;

@@ -22,6 +22,23 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+class StepBuffers:
+    """One set of device output tensors of a step (the tensors a d2d_step_io_t points at)."""
+
+    def __init__(self, num_envs: int, num_links: int, device: torch.device, info: bool) -> None:
+        E, N = num_envs, num_links
+        self.obs = torch.zeros((E, N, 6), dtype=torch.float32, device=device)
+        self.capacity_mbps = torch.zeros((E, N), dtype=torch.float32, device=device)
+        self.reward = torch.zeros((E,), dtype=torch.float32, device=device)
+        self.done = torch.zeros((E,), dtype=torch.uint8, device=device)
+        self.rate_bps = torch.zeros((E, N), dtype=torch.float32, device=device) if info else None
+        self.rb = torch.zeros((E, N), dtype=torch.int16, device=device) if info else None
+        self.tx_pwr_dbm = torch.zeros((E, N), dtype=torch.int16, device=device) if info else None
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in vars(self).values() if t is not None)
+
+
 class VecD2DEnv:
     """Batched GymD2D step path on one B200.
 
@@ -87,14 +104,11 @@ class VecD2DEnv:
         self.positions_f64 = torch.zeros((E, V, 2), dtype=torch.float64, device=dev) if exact_positions else None
         if exact_positions:
             _lib.check(self._lib.d2d_bind_positions_f64(self._h, self.positions_f64.data_ptr()))
-        # output buffers, reused by every step (clone what you keep)
-        self.obs = torch.zeros((E, N, 6), dtype=torch.float32, device=dev)
-        self.capacity_mbps = torch.zeros((E, N), dtype=torch.float32, device=dev)
-        self.reward = torch.zeros((E,), dtype=torch.float32, device=dev)
-        self.done = torch.zeros((E,), dtype=torch.uint8, device=dev)
-        self.rate_bps = torch.zeros((E, N), dtype=torch.float32, device=dev) if self.want_info else None
-        self.rb = torch.zeros((E, N), dtype=torch.int16, device=dev) if self.want_info else None
-        self.tx_pwr_dbm = torch.zeros((E, N), dtype=torch.int16, device=dev) if self.want_info else None
+        # default output buffers, reused by every step (clone what you keep, or pass out=alloc_outputs())
+        self._out = self.alloc_outputs()
+        self.obs, self.capacity_mbps, self.reward, self.done = (self._out.obs, self._out.capacity_mbps,
+                                                                self._out.reward, self._out.done)
+        self.rate_bps, self.rb, self.tx_pwr_dbm = self._out.rate_bps, self._out.rb, self._out.tx_pwr_dbm
         self._io = _lib.D2DStepIO()
         self._nvec_dev = torch.as_tensor(self.action_nvec, device=dev)
         self._nvec_f = self._nvec_dev.to(torch.float32)
@@ -108,6 +122,10 @@ class VecD2DEnv:
 
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    def alloc_outputs(self) -> StepBuffers:
+        """A fresh set of output tensors to pass as step(..., out=...), e.g. one per in-flight step."""
+        return StepBuffers(self.num_envs, self.num_links, self.device, self.want_info)
 
     def close(self) -> None:
         if getattr(self, '_h', None):
@@ -171,23 +189,24 @@ class VecD2DEnv:
         return self.obs
 
     # ---- the hot path --------------------------------------------------------------------------
-    def _launch(self, actions: torch.Tensor) -> None:
+    def _launch(self, actions: torch.Tensor, out: Optional[StepBuffers] = None) -> None:
         if actions.dtype != torch.int32 or not actions.is_cuda or not actions.is_contiguous():
             raise ValueError('actions must be a contiguous int32 CUDA tensor [num_envs][num_links]')
         if tuple(actions.shape) != (self.num_envs, self.num_links):
             raise ValueError(f'actions must have shape {(self.num_envs, self.num_links)}, got {tuple(actions.shape)}')
+        o = out if out is not None else self._out
         io = self._io
         io.actions = actions.data_ptr()
-        io.obs = self.obs.data_ptr()
-        io.capacity_mbps = self.capacity_mbps.data_ptr()
-        io.reward = self.reward.data_ptr()
-        io.done = self.done.data_ptr()
-        io.rate_bps = _ptr(self.rate_bps)
-        io.rb = _ptr(self.rb)
-        io.tx_pwr_dBm = _ptr(self.tx_pwr_dbm)
+        io.obs = o.obs.data_ptr()
+        io.capacity_mbps = o.capacity_mbps.data_ptr()
+        io.reward = o.reward.data_ptr()
+        io.done = o.done.data_ptr()
+        io.rate_bps = _ptr(o.rate_bps)
+        io.rb = _ptr(o.rb)
+        io.tx_pwr_dBm = _ptr(o.tx_pwr_dbm)
         _lib.check(self._lib.d2d_step(self._h, C.byref(io), self._stream()))
 
-    def step(self, actions: torch.Tensor, validate: bool = False
+    def step(self, actions: torch.Tensor, validate: bool = False, out: Optional[StepBuffers] = None
              ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, Dict[str, torch.Tensor]]:
         """One env.step for all E envs: a single fused kernel launch on the current stream, no host sync.
 
@@ -197,12 +216,27 @@ class VecD2DEnv:
         are otherwise the caller's responsibility (the reference accepts them silently, Appendix B.9)."""
         if validate and bool((actions >= self._nvec_dev.to(actions.dtype)).any()):
             raise ValueError('action out of range for its Discrete space')
-        self._launch(actions)
-        info = {'capacity_mbps': self.capacity_mbps}
+        self._launch(actions, out)
+        o = out if out is not None else self._out
+        info = {'capacity_mbps': o.capacity_mbps}
         if self.want_info:
-            info.update(rate_bps=self.rate_bps, rb=self.rb, tx_pwr_dbm=self.tx_pwr_dbm,
-                        sinr_db=self.obs[..., 4], snr_db=self.obs[..., 5])
-        return self.obs, self.reward, self.done, info
+            info.update(rate_bps=o.rate_bps, rb=o.rb, tx_pwr_dbm=o.tx_pwr_dbm,
+                        sinr_db=o.obs[..., 4], snr_db=o.obs[..., 5])
+        return o.obs, o.reward, o.done, info
+
+    def capture_steps(self, actions_seq, outs_seq=None) -> 'torch.cuda.CUDAGraph':
+        """Capture len(actions_seq) consecutive steps (step i reads actions_seq[i], writes outs_seq[i] or the
+        default buffers) into one CUDA graph: replay() then costs one launch for the whole sequence."""
+        outs_seq = outs_seq if outs_seq is not None else [None] * len(actions_seq)
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                for a, o in zip(actions_seq, outs_seq):
+                    self._launch(a, o)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        return graph
 
     def step_host(self, actions: np.ndarray, out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
         """End-to-end host call (d2d_step_host): host int32 actions in, host arrays out, copies included.
