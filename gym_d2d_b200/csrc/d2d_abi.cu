@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -42,6 +43,8 @@ struct d2d_handle {
     int num_sms = 0;
     bool ple2 = true;
     bool use_warp = true;
+    int wpb = 4;               // warps per block of the warp kernel
+    bool pdl = true;           // programmatic dependent launch (D2D_B200_PDL=0 disables)
     int grid = 0, block = 0, smem = 0, envs_per_block = 0;
     double K_dB = 0.0, ple = 2.0;
     D2DLinkA *dA = nullptr;
@@ -99,6 +102,23 @@ D2DParams make_params(const d2d_handle *h, const d2d_step_io_t *io) {
     P.actions = io->actions; P.obs = io->obs; P.cap = io->capacity_mbps; P.reward = io->reward;
     P.done = io->done; P.rate = io->rate_bps; P.rb_out = io->rb; P.pwr_out = io->tx_pwr_dBm;
     return P;
+}
+
+// Launch a step kernel with programmatic stream serialisation (PDL): it may begin launching while the previous
+// kernel in the stream drains; the kernel itself orders its memory accesses with griddepcontrol.wait.
+template <typename K>
+cudaError_t launch_step(K kernel, int grid, int block, size_t smem, cudaStream_t st, const D2DParams &P, bool pdl) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, P);
 }
 
 template <typename K>
@@ -218,10 +238,19 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
 
     // warp kernel: one lane slot per CUE and per DUE pair; its cross-slot bin table is exact for RB keys < 64
     h->use_warp = cfg->num_cues <= 32 && cfg->num_due_pairs <= 32 && cfg->num_rbs <= 64;
+    const char *pdl = std::getenv("D2D_B200_PDL");
+    h->pdl = !(pdl && std::strcmp(pdl, "0") == 0);
     int rc;
     if (h->use_warp) {
-        rc = h->ple2 ? plan_geometry(h, d2d_step_warp_kernel<true, false>, D2D_WARP_WARPS_PER_BLOCK * 32, 0, D2D_WARP_WARPS_PER_BLOCK)
-                     : plan_geometry(h, d2d_step_warp_kernel<false, false>, D2D_WARP_WARPS_PER_BLOCK * 32, 0, D2D_WARP_WARPS_PER_BLOCK);
+        // launch shape by batch size (d2d_step_warp.cuh): about one wave of envs -> 4-warp blocks, many waves -> 8-warp blocks
+        h->wpb = cfg->num_envs >= 32768 ? 8 : 4;
+        if (const char *w = std::getenv("D2D_B200_WPB")) h->wpb = std::atoi(w) == 8 ? 8 : 4;
+        if (h->wpb == 8)
+            rc = h->ple2 ? plan_geometry(h, d2d_step_warp_kernel<true, false, 8>, 256, 0, 8)
+                         : plan_geometry(h, d2d_step_warp_kernel<false, false, 8>, 256, 0, 8);
+        else
+            rc = h->ple2 ? plan_geometry(h, d2d_step_warp_kernel<true, false, 4>, 128, 0, 4)
+                         : plan_geometry(h, d2d_step_warp_kernel<false, false, 4>, 128, 0, 4);
     } else {
         const size_t smem = d2d_block_smem_bytes(h->N, cfg->num_rbs);
         if (smem > 227 * 1024) return bail(fail(D2D_ERR_UNSUPPORTED, "d2d_create: too many links / RBs for one SM's shared memory"));
@@ -337,19 +366,23 @@ D2D_API int d2d_step(d2d_handle_t *h, const d2d_step_io_t *io, void *stream) {
         }
         P.num_envs = n;
         const int grid = (int)std::min<int64_t>(h->grid, (n + h->envs_per_block - 1) / h->envs_per_block);
-        if (h->use_warp) {
-            const bool exact = h->pos64 != nullptr;
-            if (h->ple2) {
-                if (exact) d2d_step_warp_kernel<true, true><<<grid, h->block, 0, st>>>(P);
-                else d2d_step_warp_kernel<true, false><<<grid, h->block, 0, st>>>(P);
-            } else {
-                if (exact) d2d_step_warp_kernel<false, true><<<grid, h->block, 0, st>>>(P);
-                else d2d_step_warp_kernel<false, false><<<grid, h->block, 0, st>>>(P);
-            }
+        const bool exact = h->pos64 != nullptr;
+        cudaError_t err;
+        if (h->use_warp && h->wpb == 8) {
+            err = h->ple2 ? (exact ? launch_step(d2d_step_warp_kernel<true, true, 8>, grid, 256, 0, st, P, h->pdl)
+                                   : launch_step(d2d_step_warp_kernel<true, false, 8>, grid, 256, 0, st, P, h->pdl))
+                          : (exact ? launch_step(d2d_step_warp_kernel<false, true, 8>, grid, 256, 0, st, P, h->pdl)
+                                   : launch_step(d2d_step_warp_kernel<false, false, 8>, grid, 256, 0, st, P, h->pdl));
+        } else if (h->use_warp) {
+            err = h->ple2 ? (exact ? launch_step(d2d_step_warp_kernel<true, true, 4>, grid, 128, 0, st, P, h->pdl)
+                                   : launch_step(d2d_step_warp_kernel<true, false, 4>, grid, 128, 0, st, P, h->pdl))
+                          : (exact ? launch_step(d2d_step_warp_kernel<false, true, 4>, grid, 128, 0, st, P, h->pdl)
+                                   : launch_step(d2d_step_warp_kernel<false, false, 4>, grid, 128, 0, st, P, h->pdl));
         } else {
-            if (h->ple2) d2d_step_block_kernel<true><<<grid, h->block, h->smem, st>>>(P);
-            else d2d_step_block_kernel<false><<<grid, h->block, h->smem, st>>>(P);
+            err = h->ple2 ? launch_step(d2d_step_block_kernel<true>, grid, h->block, h->smem, st, P, h->pdl)
+                          : launch_step(d2d_step_block_kernel<false>, grid, h->block, h->smem, st, P, h->pdl);
         }
+        if (err != cudaSuccess) return fail(D2D_ERR_CUDA, std::string("step kernel launch: ") + cudaGetErrorString(err));
         ++h->launches;
     }
     D2D_CUDA(cudaGetLastError());
@@ -413,3 +446,9 @@ D2D_API int d2d_step_geometry(const d2d_handle_t *h, int32_t *grid, int32_t *blo
     if (envs_per_block) *envs_per_block = h->envs_per_block;
     return D2D_OK;
 }
+
+#ifdef D2D_TIMELINE
+extern "C" __attribute__((visibility("default"))) int d2d_debug_timeline(unsigned long long *out16) {
+    return (int)cudaMemcpyFromSymbol(out16, d2d_dbg, sizeof(unsigned long long) * 16);
+}
+#endif

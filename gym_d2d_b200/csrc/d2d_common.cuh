@@ -100,6 +100,13 @@ __device__ __forceinline__ float d2d_rcp(float x) {
     return y;
 }
 
+// Programmatic dependent launch (PDL).  Every step kernel lets its successor start launching right away
+// (launch_dependents) and itself waits for its predecessor's memory to be complete and visible (wait) only after
+// its own prologue - constant tables, shared-memory setup - so back-to-back steps hide launch latency.  Everything
+// a previous kernel may have written (actions, positions, counters, output buffers) is touched after the wait.
+__device__ __forceinline__ void d2d_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void d2d_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // envs/d2d_env.py:95: rb = a // n_pwr for a >= 0.  n_pwr is a runtime value, so divide by multiplying
 // with magic = ceil(2^32 / n) (exact for a < 2^32 / n; n = 1 has no 32-bit magic and is passed through).
 __host__ __device__ __forceinline__ uint32_t d2d_div_magic(int n) {

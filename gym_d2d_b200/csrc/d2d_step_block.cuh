@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_kernel(const
     const int N = P.N, C = P.C, V = P.V, nbins = P.nbins;
     D2DBlockSmemView S = d2d_block_carve(d2d_smem_raw, N, nbins);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    d2d_pdl_launch_dependents();
 
     for (int i = tid; i < N; i += D2D_BLOCK_THREADS) {
         S.linkA[i] = reinterpret_cast<const float4 *>(P.linkA)[i];
@@ -66,6 +67,7 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_kernel(const
     const uint32_t magic_cue = d2d_div_magic(P.n_pwr_cue), magic_due = d2d_div_magic(P.n_pwr_due);
 
     double st_reward = 0.0, st_cap = 0.0, st_reward2 = 0.0, st_pen = 0.0, st_resc = 0.0, st_n = 0.0;
+    d2d_pdl_wait();
 
     for (int64_t e = blockIdx.x; e < P.num_envs; e += gridDim.x) {
         const int32_t *act = P.actions + e * N;

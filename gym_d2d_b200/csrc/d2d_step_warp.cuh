@@ -1,63 +1,61 @@
-// d2d_step_warp.cuh - fused env.step, one warp per environment, for C <= 32 CUEs and D <= 32 DUE pairs
-// (the reference's default 25/25/25 configuration and everything around it).
+// d2d_step_warp.cuh - fused env.step, one warp per environment, for C <= 32 CUEs, D <= 32 DUE pairs and
+// R <= 64 RBs (the reference's default 25/25/25 configuration and everything around it).
 //
 // Replaces, for E environments at once, the reference call chain
 //   D2DEnv.step (envs/d2d_env.py:62-71) -> _decode_action (:93-101) -> Simulator.step (simulator.py:77-154)
 //   -> LinearObsFunction (envs/obs_fn.py:43-61) -> SystemCapacityRewardFunction (envs/reward_fn.py:27-44).
 //
-// Mapping: lane l owns CUE link l (slot A) and DUE pair l (slot B); peers are addressed by slot index
-// (A: l, B: 32 + l).  The masked per-RB interference sum (Actions.get_actions_by_rb, actions.py:27-31 +
-// simulator.py:95-101) is a warp-level segmented reduction:
-//   * MATCH.ANY on the RB key gives every lane the mask of same-RB links inside its own slot;
-//   * the two cross-slot masks go through a 64-entry shared-memory bin table per slot, tagged with the
-//     warp's iteration number (all links of one RB store the same mask, so plain stores suffice);
-//   * each lane walks the set bits of its peer masks.  All CUE links share one receiver (the MBS at the
-//     origin), so an interferer's contribution there, u_k = w_k * g(|tx_k|), is a per-link scalar
-//     computed once and a CUE victim's walk is a plain sum of u_k; a DUE victim's walk reads the peer's
-//     (tx_x, tx_y, w_k) record and evaluates the gain to its own receiver.
-// The sum always EXCLUDES the victim itself instead of subtracting it from a per-RB total: with SNRs of
-// 70 dB the subtraction would cancel every significant bit of a weak interferer.
+// Mapping: lane l owns CUE link l (slot A) and DUE pair l (slot B).
 //
-// HBM traffic per env-step is the compulsory 32N + 8V + 5 bytes: one coalesced pass over the
-// env's actions and positions, one over its outputs; nothing is re-read.  There is no block-level
-// prologue and no block barrier: a warp needs only its own 2 KB of shared memory.
+// The masked per-RB interference sum (Actions.get_actions_by_rb, actions.py:27-31 + simulator.py:95-101) is a
+// segmented reduction over links grouped by RB.  The grouping is a per-warp counting sort in shared memory:
+//   rank   = atomicAdd(count[rb], 1)            one shared atomic per link (the DUE count rides in the high half)
+//   offset = exclusive warp-shuffle scan of the 64 counts (two bins per lane, packed in one register)
+//   sorted[offset[rb] + rank] = (tx_x, tx_y, w, u)   the link's peer record
+// after which a victim's co-channel peers are ONE contiguous range of records.  Its first five entries are
+// handled branch-free (plain indexed LDS, predicated terms, so the loads and gains of a lane's two victims
+// overlap); an RB with more than five links (1.4 % of RBs at the default load) falls into a short serial loop.
+// Measured alternatives this replaced: MATCH.ANY costs ~290 cycles per call on sm_100a, and a bit-serial walk over
+// peer masks ~100 cycles per trip (FLO -> shift -> branch is one dependent chain).
+//
+// All CUE links share one receiver (the MBS at the origin), so there an interferer contributes a per-link scalar
+// u_k = w_k g(|tx_k|) computed once, and a CUE victim's walk is a sum of u_k; a DUE victim evaluates
+// w_k g(|tx_k - rx|).  The victim is excluded from its own range by index - never subtracted from a per-RB total,
+// which would cancel a weak interferer against a 70 dB stronger self term.
+//
+// HBM traffic per env-step is the compulsory 32N + 8V + 5 bytes: one coalesced pass over the env's
+// actions and positions (software-pipelined one env ahead), one over its outputs; nothing is re-read.  There is no
+// block-level prologue and no block barrier: a warp needs only its own 2.4 KB of shared memory.
 #pragma once
 
 #include "d2d_common.cuh"
 
-#ifndef D2D_WARP_WARPS_PER_BLOCK
-#define D2D_WARP_WARPS_PER_BLOCK 4
-#endif
-#ifndef D2D_WARP_MIN_BLOCKS
-#define D2D_WARP_MIN_BLOCKS 8
-#endif
+// Two launch shapes, picked by the host from the batch size (measured on B200, profiles/README.md):
+//   WPB = 4, >= 7 blocks/SM (72 registers): finest block granularity - best when the batch is about one wave (E = 4096)
+//   WPB = 8, >= 4 blocks/SM (64 registers): best sustained throughput for batches of many waves
+#define D2D_WARP_MIN_BLOCKS(WPB) ((WPB) == 4 ? 7 : 4)
 #ifndef D2D_STATS_REPLICAS
 #define D2D_STATS_REPLICAS 32
 #endif
+#define D2D_WALK_INLINE 5      // range entries handled branch-free before the serial loop
 
-// Per warp: float4 rec[64]  [slot index] = (tx_x, tx_y, w, u):  w = 10^(p/10) tx_lin0,  u = w g(|tx|) (at the MBS)
-//           uint2 bins[2][64] [slot][rb & 63] = (mask of that slot's lanes on this RB, iteration tag)
+// Per-warp shared memory, addressed through one 32-bit base held in a register (explicit ld/st.shared, so the
+// compiler never re-derives generic addresses from threadIdx).  Byte layout:
+#define D2D_W_SORTED 0u        // float4 sorted[64 + 8]: peer records grouped by RB (+ slack for the inline over-read)
+#define D2D_W_CNT 1152u        // u32 count[2][64]: per-RB link count, double-buffered by iteration parity
+#define D2D_W_OFF 1664u        // u32 offset[64]: exclusive scan of count
+#define D2D_W_PWR 1920u        // float pwr_lin[128]: the warp's copy of the integer-dBm -> mW table
+#define D2D_W_BYTES 2432u
 
-// Per-warp shared memory is addressed through one 32-bit base held in a register (explicit ld/st.shared), so the
-// compiler never re-derives generic addresses from threadIdx.  Byte layout per warp:
-#define D2D_W_REC 0u        // float4 rec[64]
-#define D2D_W_BINS 1024u    // uint2 bins[2][64]
-#define D2D_W_PWR 2048u     // float pwr_lin[128]: the warp's own copy of the integer-dBm -> mW table
-#define D2D_W_BYTES 2560u
 __device__ __forceinline__ void d2d_sts128(uint32_t a, float x, float y, float z, float w) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
-__device__ __forceinline__ void d2d_sts64(uint32_t a, uint32_t x, uint32_t y) {
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+__device__ __forceinline__ void d2d_sts32(uint32_t a, uint32_t x) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(x) : "memory");
 }
 __device__ __forceinline__ float4 d2d_lds128(uint32_t a) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
-    return v;
-}
-__device__ __forceinline__ uint2 d2d_lds64(uint32_t a) {
-    uint2 v;
-    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
     return v;
 }
 __device__ __forceinline__ float d2d_lds32(uint32_t a) {
@@ -65,8 +63,17 @@ __device__ __forceinline__ float d2d_lds32(uint32_t a) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a) : "memory");
     return v;
 }
-
-// index of the highest set bit (FLO) and removal of that bit
+__device__ __forceinline__ uint32_t d2d_lds32u(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t d2d_atoms_add(uint32_t a, uint32_t x) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(a), "r"(x) : "memory");
+    return old;
+}
+// index of the highest set bit (FLO) and removal of that bit - rescue path only
 __device__ __forceinline__ uint32_t d2d_pop_bit(uint32_t &mask) {
     uint32_t k;
     asm("bfind.u32 %0, %1;" : "=r"(k) : "r"(mask));
@@ -74,23 +81,38 @@ __device__ __forceinline__ uint32_t d2d_pop_bit(uint32_t &mask) {
     return k;
 }
 
-// CUE victim: every interferer is received at the MBS, so the walk sums the precomputed u_k (rec[k].w)
-__device__ __forceinline__ float d2d_walk_mbs(uint32_t mask, uint32_t rec) {
+// One interferer's term at a general receiver: w_k g(|tx_k - rx|)
+template <bool PLE2, bool EXACT>
+__device__ __forceinline__ float d2d_term_rx(uint32_t addr, bool valid, float rxx, float rxy, float nhp, float &dmin2) {
+    const float4 r = d2d_lds128(addr);
+    const float dx = r.x - rxx, dy = r.y - rxy;
+    const float d2 = fmaf(dx, dx, dy * dy);
+    if (EXACT) dmin2 = valid ? fminf(dmin2, d2) : dmin2;
+    return valid ? r.z * d2d_gain<PLE2>(d2, nhp) : 0.0f;
+}
+// Interference at a general receiver from the records [beg, beg + n) minus the victim's own record `self`
+template <bool PLE2, bool EXACT>
+__device__ __forceinline__ float d2d_walk_rx(uint32_t sorted, uint32_t beg, uint32_t n, uint32_t self, float rxx, float rxy,
+                                             float nhp, float &dmin2) {
     float I = 0.0f;
-    while (mask) I += d2d_lds32(rec + 12u + (d2d_pop_bit(mask) << 4));
+#pragma unroll
+    for (uint32_t t = 0; t < D2D_WALK_INLINE; ++t)
+        I += d2d_term_rx<PLE2, EXACT>(sorted + ((beg + t) << 4), t < n && beg + t != self, rxx, rxy, nhp, dmin2);
+    for (uint32_t t = D2D_WALK_INLINE; t < n; ++t)       // rare: more than D2D_WALK_INLINE links on one RB
+        I += d2d_term_rx<PLE2, EXACT>(sorted + ((beg + t) << 4), beg + t != self, rxx, rxy, nhp, dmin2);
     return I;
 }
-
-// general victim: gain from each interferer's transmitter to this victim's receiver
-template <bool PLE2, bool EXACT>
-__device__ __forceinline__ float d2d_walk_rx(uint32_t mask, uint32_t rec, float rxx, float rxy, float nhp, float &dmin2) {
+// Interference at the MBS: the records carry u_k = w_k g(|tx_k|) in .w
+__device__ __forceinline__ float d2d_walk_mbs(uint32_t sorted, uint32_t beg, uint32_t n, uint32_t self) {
     float I = 0.0f;
-    while (mask) {
-        const float4 r = d2d_lds128(rec + (d2d_pop_bit(mask) << 4));
-        const float dx = r.x - rxx, dy = r.y - rxy;
-        const float d2 = fmaf(dx, dx, dy * dy);
-        I = fmaf(r.z, d2d_gain<PLE2>(d2, nhp), I);
-        if (EXACT) dmin2 = fminf(dmin2, d2);
+#pragma unroll
+    for (uint32_t t = 0; t < D2D_WALK_INLINE; ++t) {
+        const float u = d2d_lds32(sorted + 12u + ((beg + t) << 4));
+        I += (t < n && beg + t != self) ? u : 0.0f;
+    }
+    for (uint32_t t = D2D_WALK_INLINE; t < n; ++t) {
+        const float u = d2d_lds32(sorted + 12u + ((beg + t) << 4));
+        I += (beg + t != self) ? u : 0.0f;
     }
     return I;
 }
@@ -98,8 +120,8 @@ __device__ __forceinline__ float d2d_walk_rx(uint32_t mask, uint32_t rec, float 
 // One env's inputs as a lane sees them: its CUE action + transmitter, its DUE action + (tx, rx) pair.
 struct D2DLaneIn {
     int aA, aB, ns;   // ns: this env's step counter (lane 0 only)
-    float2 tA;      // CUE transmitter (its receiver is the MBS at the origin)
-    float4 pB;      // DUE (tx_x, tx_y, rx_x, rx_y)
+    float2 tA;        // CUE transmitter (its receiver is the MBS at the origin)
+    float4 pB;        // DUE (tx_x, tx_y, rx_x, rx_y)
 };
 __device__ __forceinline__ D2DLaneIn d2d_load_inputs(const D2DParams &P, uint32_t e, uint32_t lane, bool hasA, bool hasB) {
     D2DLaneIn in;
@@ -123,24 +145,31 @@ __device__ __forceinline__ D2DLaneIn d2d_load_inputs(const D2DParams &P, uint32_
     return in;
 }
 
-template <bool PLE2, bool EXACT>
-__global__ void __launch_bounds__(D2D_WARP_WARPS_PER_BLOCK * 32, D2D_WARP_MIN_BLOCKS)
+#ifdef D2D_TIMELINE   // debug builds only: SM-clock timestamps of one warp's phases (profiles/timeline.py)
+__device__ unsigned long long d2d_dbg[16];
+#define D2D_TICK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) d2d_dbg[i] = clock64(); } while (0)
+#else
+#define D2D_TICK(i) do { } while (0)
+#endif
+
+template <bool PLE2, bool EXACT, int WPB>
+__global__ void __launch_bounds__(WPB * 32, D2D_WARP_MIN_BLOCKS(WPB))
 d2d_step_warp_kernel(const D2DParams P) {
-    __shared__ __align__(16) unsigned char smem[D2D_WARP_WARPS_PER_BLOCK * D2D_W_BYTES];
+    constexpr int D2D_WARP_WARPS_PER_BLOCK = WPB;
+    __shared__ __align__(16) unsigned char smem[WPB * D2D_W_BYTES];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = P.N, C = P.C, V = P.V, D = N - C;
+    D2D_TICK(0);
+    d2d_pdl_launch_dependents();
     uint32_t wb = (uint32_t)__cvta_generic_to_shared(smem) + (uint32_t)warp * D2D_W_BYTES;
     asm volatile("mov.u32 %0, %0;" : "+r"(wb));      // opaque: keep the base in a register instead of re-deriving it
-    const uint32_t recA = wb + D2D_W_REC, recB = recA + 512u, bins0 = wb + D2D_W_BINS, bins1 = bins0 + 512u;
+    const uint32_t sorted = wb + D2D_W_SORTED, offs = wb + D2D_W_OFF;
 
-    // bin tags start at 0 and `iter` at 1: shared memory left behind by an earlier block can never look current
-    d2d_sts128(bins0 + (lane << 4), 0.f, 0.f, 0.f, 0.f);
-    d2d_sts128(bins1 + (lane << 4), 0.f, 0.f, 0.f, 0.f);
-    {   // 10^(p/10) table -> shared, so the lookup that depends on the action is an LDS, not a second global round trip
-        const float4 t = __ldg(reinterpret_cast<const float4 *>(P.pwr_lin) + lane);
-        d2d_sts128(wb + D2D_W_PWR + (lane << 4), t.x, t.y, t.z, t.w);
-    }
-    __syncwarp();
+    // both parity buffers of the RB counters start at zero; each iteration re-zeroes the one it is not using
+    d2d_sts128(wb + D2D_W_CNT + (lane << 4), 0.f, 0.f, 0.f, 0.f);
+    // 10^(p/10) table -> shared, so the lookup that depends on the action is an LDS, not a second global round trip;
+    // the load is issued here and parked in shared memory only after the first env's inputs are in flight
+    const float4 lut = __ldg(reinterpret_cast<const float4 *>(P.pwr_lin) + lane);
 
     const bool hasA = lane < C, hasB = lane < D;
     const uint32_t jA = lane, jB = C + lane;                  // canonical link indices (envs/d2d_env.py:55-60)
@@ -150,7 +179,6 @@ d2d_step_warp_kernel(const D2DParams P) {
     const float2 sA = hasA ? __ldg(reinterpret_cast<const float2 *>(P.linkB + jA)) : make_float2(0.f, 0.f);   // (sens, bw)
     const float2 sB = hasB ? __ldg(reinterpret_cast<const float2 *>(P.linkB + jB)) : make_float2(0.f, 0.f);
     const uint32_t magicA = P.magic_cue, magicB = P.magic_due;   // ceil(2^32 / n_pwr), folded on the host
-    const uint32_t lane_bit = 1u << lane;
 
     // per-warp partial statistics (fp32 over the few envs one warp visits; flushed once as fp64 atomics)
     float st_reward = 0.f, st_cap = 0.f, st_reward2 = 0.f;
@@ -161,11 +189,15 @@ d2d_step_warp_kernel(const D2DParams P) {
     const uint32_t num_envs = (uint32_t)P.num_envs, stride = gridDim.x * D2D_WARP_WARPS_PER_BLOCK;
     uint32_t e = blockIdx.x * D2D_WARP_WARPS_PER_BLOCK + warp;
     D2DLaneIn nxt;
+    D2D_TICK(1);
+    d2d_pdl_wait();
+    D2D_TICK(2);
     if (e < num_envs) nxt = d2d_load_inputs(P, e, lane, hasA, hasB);
+    d2d_sts128(wb + D2D_W_PWR + (lane << 4), lut.x, lut.y, lut.z, lut.w);
+    __syncwarp();
     for (; e < num_envs; e += stride, ++iter) {
         const uint32_t row0 = e * (uint32_t)N;
-        const int32_t *act = P.actions + row0;
-        const float2 *pe = reinterpret_cast<const float2 *>(P.pos) + e * (uint32_t)V;
+        const uint32_t cnt = wb + D2D_W_CNT + ((iter & 1u) << 8), cnt_other = wb + D2D_W_CNT + (((iter & 1u) ^ 1u) << 8);
 
         // ---- one coalesced pass over the env's inputs, software-pipelined: the NEXT env's loads are in flight
         // while this env computes, so a warp hides its own HBM latency ----------------------------------------
@@ -175,12 +207,16 @@ d2d_step_warp_kernel(const D2DParams P) {
         const int ns_prev = nxt.ns;
         if (e + stride < num_envs) nxt = d2d_load_inputs(P, e + stride, lane, hasA, hasB);
         const bool actA = aA >= 0, actB = aB >= 0;
+        if (actA || actB) D2D_TICK(3);     // inputs arrived
 
-        // ---- envs/d2d_env.py:93-101: rb = a // n_pwr, p = a % n_pwr -----------------------------------------------
+        // ---- envs/d2d_env.py:93-101: rb = a // n_pwr, p = a % n_pwr; rank inside the RB (actions.py:27-31) -------------
         const int rbA = d2d_div(aA, magicA), pA = aA - rbA * P.n_pwr_cue;
         const int rbB = d2d_div(aB, magicB), pB_ = aB - rbB * P.n_pwr_due;
-        const uint32_t keyA = actA ? (uint32_t)rbA : (D2D_INACTIVE_KEY | (uint32_t)lane);
-        const uint32_t keyB = actB ? (uint32_t)rbB : (D2D_INACTIVE_KEY | 32u | (uint32_t)lane);
+        const uint32_t binA = (uint32_t)rbA & 63u, binB = (uint32_t)rbB & 63u;
+        uint32_t rankA = 0, rankB = 0;
+        if (actA) rankA = d2d_atoms_add(cnt + (binA << 2), 1u) & 0xffffu;
+        if (actB) rankB = d2d_atoms_add(cnt + (binB << 2), 0x10001u) & 0xffffu;     // high half counts the SIDELINKs
+        if (lane < 16) d2d_sts128(cnt_other + (lane << 4), 0.f, 0.f, 0.f, 0.f);       // next iteration's counters
         const float plA = actA ? d2d_lds32(wb + D2D_W_PWR + ((pA & (D2D_MAX_PWR_LEVELS - 1)) << 2)) : 0.0f;   // 10^(p/10)
         const float plB = actB ? d2d_lds32(wb + D2D_W_PWR + ((pB_ & (D2D_MAX_PWR_LEVELS - 1)) << 2)) : 0.0f;
 
@@ -191,29 +227,44 @@ d2d_step_warp_kernel(const D2DParams P) {
         const float wA = plA * cA.x;
         const float d2Bm = fmaf(pB.x, pB.x, pB.y * pB.y);                      // DUE tx -> MBS distance^2 (as interferer)
         const float wB = plB * cB.x;
-        if (hasA) d2d_sts128(recA + (lane << 4), tA.x, tA.y, wA, wA * gA);
-        if (hasB) d2d_sts128(recB + (lane << 4), pB.x, pB.y, wB, wB * d2d_gain<PLE2>(d2Bm, P.neg_half_ple));
+        const float uB = wB * d2d_gain<PLE2>(d2Bm, P.neg_half_ple);
+        D2D_TICK(4);
 
-        // ---- same-RB masks (actions.py:27-31) ------------------------------------------------------------------
-        const uint32_t mAA = __match_any_sync(0xffffffffu, keyA);
-        const uint32_t mBB = __match_any_sync(0xffffffffu, keyB);
-        if (actA) d2d_sts64(bins0 + ((keyA & 63u) << 3), mAA, iter);
-        if (actB) d2d_sts64(bins1 + ((keyB & 63u) << 3), mBB, iter);
+        // ---- exclusive scan of the 64 RB counts: lane l scans bins l and l + 32, packed 16 + 16 bits ---------------
         __syncwarp();
-        uint32_t mAB = 0, mBA = 0;                                             // DUE peers of my CUE / CUE peers of my DUE
-        if (actA) { const uint2 b = d2d_lds64(bins1 + ((keyA & 63u) << 3)); mAB = b.y == iter ? b.x : 0u; }
-        if (actB) { const uint2 b = d2d_lds64(bins0 + ((keyB & 63u) << 3)); mBA = b.y == iter ? b.x : 0u; }
-
-        // ---- simulator.py:95-101: interference at each victim's receiver --------------------------------------------
-        float IA = 0.0f, IB = 0.0f, dminA = 3.0e38f, dminB = 3.0e38f;
-        if (EXACT) {
-            if (actA) IA = d2d_walk_rx<PLE2, true>(mAA & ~lane_bit, recA, 0.f, 0.f, P.neg_half_ple, dminA) +
-                           d2d_walk_rx<PLE2, true>(mAB, recB, 0.f, 0.f, P.neg_half_ple, dminA);
-        } else {
-            if (actA) IA = d2d_walk_mbs(mAA & ~lane_bit, recA) + d2d_walk_mbs(mAB, recB);
+        const uint32_t c0 = d2d_lds32u(cnt + (lane << 2)) & 0xffffu, c1 = d2d_lds32u(cnt + ((lane + 32) << 2)) & 0xffffu;
+        uint32_t incl = c0 | (c1 << 16);
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, s);
+            if (lane >= s) incl += up;
         }
-        if (actB) IB = d2d_walk_rx<PLE2, EXACT>(mBA, recA, pB.z, pB.w, P.neg_half_ple, dminB) +
-                       d2d_walk_rx<PLE2, EXACT>(mBB & ~lane_bit, recB, pB.z, pB.w, P.neg_half_ple, dminB);
+        const uint32_t total0 = __shfl_sync(0xffffffffu, incl, 31) & 0xffffu;   // links in bins 0..31
+        d2d_sts32(offs + (lane << 2), (incl & 0xffffu) - c0);
+        d2d_sts32(offs + ((lane + 32) << 2), total0 + (incl >> 16) - c1);
+        __syncwarp();
+        // ---- scatter the records into RB order --------------------------------------------------------------------
+        uint32_t begA = 0, begB = 0, nA = 0, nB = 0, sideA = 0;
+        if (actA) {
+            begA = d2d_lds32u(offs + (binA << 2));
+            const uint32_t c = d2d_lds32u(cnt + (binA << 2));
+            nA = c & 0xffffu; sideA = c >> 16;
+            d2d_sts128(sorted + ((begA + rankA) << 4), tA.x, tA.y, wA, wA * gA);
+        }
+        if (actB) {
+            begB = d2d_lds32u(offs + (binB << 2));
+            nB = d2d_lds32u(cnt + (binB << 2)) & 0xffffu;
+            d2d_sts128(sorted + ((begB + rankB) << 4), pB.x, pB.y, wB, uB);
+        }
+        __syncwarp();
+        D2D_TICK(5);
+
+        // ---- simulator.py:95-101: interference at each victim's receiver (an absent victim has an empty range) ----------
+        float dminA = 3.0e38f, dminB = 3.0e38f;
+        const float IA = EXACT ? d2d_walk_rx<PLE2, true>(sorted, begA, nA, begA + rankA, 0.f, 0.f, P.neg_half_ple, dminA)
+                               : d2d_walk_mbs(sorted, begA, nA, begA + rankA);
+        const float IB = d2d_walk_rx<PLE2, EXACT>(sorted, begB, nB, begB + rankB, pB.z, pB.w, P.neg_half_ple, dminB);
+        if (IA + IB >= 0.f) D2D_TICK(6);
 
         // ---- per-link epilogue (simulator.py:93,106-107,110-127,144-154) --------------------------------------------
         D2DLinkOut oA = {0.f, 0.f, 0.f, 0.f}, oB = oA;
@@ -229,14 +280,16 @@ d2d_step_warp_kernel(const D2DParams P) {
             oB = d2d_link_epilogue<PLE2>(pB_, plB, lg, PLE2 ? d2d_rcp(d2) : d2d_ex2(P.neg_half_ple * lg), IB, cB, sB, P);
             if (d2d_needs_rescue<EXACT>(oB, fminf(dminB, d2), P)) need |= 2;
         }
+        if (oA.cap + oB.cap >= 0.f) D2D_TICK(7);
 
         // ---- envs/reward_fn.py:27-44 -----------------------------------------------------------------------------------
-        const bool bad = __any_sync(0xffffffffu, actA && mAB != 0u && oA.cap <= P.min_cap);
+        const bool bad = __any_sync(0xffffffffu, actA && sideA != 0u && oA.cap <= P.min_cap);
         const int n_act = __popc(__ballot_sync(0xffffffffu, actA)) + __popc(__ballot_sync(0xffffffffu, actB));
         float cap_sum = oA.cap + oB.cap;
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) cap_sum += __shfl_xor_sync(0xffffffffu, cap_sum, s);
         const float reward = bad ? -1.0f : __fdividef(cap_sum, (float)n_act);
+        if (reward > -2.f) D2D_TICK(8);
 
         // ---- outputs: compact observation table (envs/obs_fn.py:55-61), capacity, optional info -----------------------
         if (P.obs) {
@@ -281,13 +334,18 @@ d2d_step_warp_kernel(const D2DParams P) {
             if (P.reward) P.reward[e] = reward;
             if (P.done) P.done[e] = ns >= P.episode_length ? 1 : 0;
         }
+        D2D_TICK(9);
         st_reward += reward; st_cap += cap_sum; st_reward2 = fmaf(reward, reward, st_reward2);
         st_pen += bad ? 1 : 0;
 
         // ---- rare: fp64 recomputation of flagged links (d2d_common.cuh).  Runs after the stores, when none of the
         // per-link state above is live; the whole warp cooperates on each flagged link. -------------------------------
         if (D2D_RESCUE_ENABLED && __any_sync(0xffffffffu, need != 0)) {
+            const int32_t *act = P.actions + row0;
+            const float2 *pe = reinterpret_cast<const float2 *>(P.pos) + e * (uint32_t)V;
             const double2 *pe64 = P.pos64 ? reinterpret_cast<const double2 *>(P.pos64) + (int64_t)e * V : nullptr;
+            const uint32_t keyA = actA ? (uint32_t)rbA : (D2D_INACTIVE_KEY | (uint32_t)lane);
+            const uint32_t keyB = actB ? (uint32_t)rbB : (D2D_INACTIVE_KEY | 32u | (uint32_t)lane);
 #pragma unroll 1
             for (int s = 0; s < 2; ++s) {
                 uint32_t todo = __ballot_sync(0xffffffffu, (need >> s) & 1);
@@ -312,9 +370,9 @@ d2d_step_warp_kernel(const D2DParams P) {
                 }
             }
         }
-        __syncwarp();
     }
 
+    D2D_TICK(10);
     if (P.stats && lane < 6) {
         // one fire-and-forget fp64 reduction per statistic and warp, spread over the replicas
         const int resc0 = __shfl_sync(0x3fu, st_resc, 0);
