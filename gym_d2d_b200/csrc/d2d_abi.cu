@@ -82,6 +82,8 @@ D2DParams make_params(const d2d_handle *h, const d2d_step_io_t *io) {
     P.nbins = h->cfg.num_rbs;
     P.magic_cue = d2d_div_magic(h->cfg.n_pwr_cue);
     P.magic_due = d2d_div_magic(h->cfg.n_pwr_due);
+    P.npw1_cue = h->cfg.n_pwr_cue == 1 ? 0xffffffffu : 0u;
+    P.npw1_due = h->cfg.n_pwr_due == 1 ? 0xffffffffu : 0u;
     P.align4 = (h->V % 2 == 0) && ((1 + h->cfg.num_cues) % 2 == 0) && ((uintptr_t)h->pos % 16 == 0);
     P.ple = (float)h->ple;
     P.neg_half_ple = (float)(-0.5 * h->ple);
@@ -246,11 +248,11 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
         h->wpb = cfg->num_envs >= 32768 ? 8 : 4;
         if (const char *w = std::getenv("D2D_B200_WPB")) h->wpb = std::atoi(w) == 8 ? 8 : 4;
         if (h->wpb == 8)
-            rc = h->ple2 ? plan_geometry(h, d2d_step_warp_kernel<true, false, 8>, 256, 0, 8)
-                         : plan_geometry(h, d2d_step_warp_kernel<false, false, 8>, 256, 0, 8);
+            rc = h->ple2 ? plan_geometry(h, d2d_step_warp_kernel<true, false, 8, true>, 256, 0, 8)
+                         : plan_geometry(h, d2d_step_warp_kernel<false, false, 8, true>, 256, 0, 8);
         else
-            rc = h->ple2 ? plan_geometry(h, d2d_step_warp_kernel<true, false, 4>, 128, 0, 4)
-                         : plan_geometry(h, d2d_step_warp_kernel<false, false, 4>, 128, 0, 4);
+            rc = h->ple2 ? plan_geometry(h, d2d_step_warp_kernel<true, false, 4, true>, 128, 0, 4)
+                         : plan_geometry(h, d2d_step_warp_kernel<false, false, 4, true>, 128, 0, 4);
     } else {
         const size_t smem = d2d_block_smem_bytes(h->N, cfg->num_rbs);
         if (smem > 227 * 1024) return bail(fail(D2D_ERR_UNSUPPORTED, "d2d_create: too many links / RBs for one SM's shared memory"));
@@ -368,16 +370,16 @@ D2D_API int d2d_step(d2d_handle_t *h, const d2d_step_io_t *io, void *stream) {
         const int grid = (int)std::min<int64_t>(h->grid, (n + h->envs_per_block - 1) / h->envs_per_block);
         const bool exact = h->pos64 != nullptr;
         cudaError_t err;
+        // FULL: exactly the core outputs were passed, so the kernel tests no output pointer on its hot path
+        const bool full = io->obs && io->capacity_mbps && io->reward && io->done && !io->rate_bps && !io->rb && !io->tx_pwr_dBm;
+#define D2D_LAUNCH_WARP(PLE2_, EXACT_, WPB_, FULL_) \
+    launch_step(d2d_step_warp_kernel<PLE2_, EXACT_, WPB_, FULL_>, grid, WPB_ * 32, 0, st, P, h->pdl)
+#define D2D_PICK_FULL(PLE2_, EXACT_, WPB_) (full ? D2D_LAUNCH_WARP(PLE2_, EXACT_, WPB_, true) : D2D_LAUNCH_WARP(PLE2_, EXACT_, WPB_, false))
+#define D2D_PICK_EXACT(PLE2_, WPB_) (exact ? D2D_PICK_FULL(PLE2_, true, WPB_) : D2D_PICK_FULL(PLE2_, false, WPB_))
         if (h->use_warp && h->wpb == 8) {
-            err = h->ple2 ? (exact ? launch_step(d2d_step_warp_kernel<true, true, 8>, grid, 256, 0, st, P, h->pdl)
-                                   : launch_step(d2d_step_warp_kernel<true, false, 8>, grid, 256, 0, st, P, h->pdl))
-                          : (exact ? launch_step(d2d_step_warp_kernel<false, true, 8>, grid, 256, 0, st, P, h->pdl)
-                                   : launch_step(d2d_step_warp_kernel<false, false, 8>, grid, 256, 0, st, P, h->pdl));
+            err = h->ple2 ? D2D_PICK_EXACT(true, 8) : D2D_PICK_EXACT(false, 8);
         } else if (h->use_warp) {
-            err = h->ple2 ? (exact ? launch_step(d2d_step_warp_kernel<true, true, 4>, grid, 128, 0, st, P, h->pdl)
-                                   : launch_step(d2d_step_warp_kernel<true, false, 4>, grid, 128, 0, st, P, h->pdl))
-                          : (exact ? launch_step(d2d_step_warp_kernel<false, true, 4>, grid, 128, 0, st, P, h->pdl)
-                                   : launch_step(d2d_step_warp_kernel<false, false, 4>, grid, 128, 0, st, P, h->pdl));
+            err = h->ple2 ? D2D_PICK_EXACT(true, 4) : D2D_PICK_EXACT(false, 4);
         } else {
             err = h->ple2 ? launch_step(d2d_step_block_kernel<true>, grid, h->block, h->smem, st, P, h->pdl)
                           : launch_step(d2d_step_block_kernel<false>, grid, h->block, h->smem, st, P, h->pdl);

@@ -54,7 +54,8 @@ struct D2DParams {
     int32_t episode_length;
     int32_t nbins;               // block kernel: number of RB bins
     int32_t align4;              // warp kernel: every env's DUE (tx, rx) pair is a 16-byte aligned float4
-    uint32_t magic_cue, magic_due;  // d2d_div_magic(n_pwr_cue / n_pwr_due)
+    uint32_t magic_cue, magic_due;  // d2d_div_magic(n_pwr_cue / n_pwr_due): rb = umulhi(a, magic) + (a & npw1)
+    uint32_t npw1_cue, npw1_due;    // 0xffffffff when n_pwr == 1 (then magic = 0 and rb = a), else 0
     float ple;                   // path-loss exponent
     float neg_half_ple;          // -ple/2           : g = exp2(neg_half_ple * log2(d^2))
     float snr_slope;             // 5*ple*log10(2)   : SNR_dB = p + snr0 - snr_slope*log2(d^2)

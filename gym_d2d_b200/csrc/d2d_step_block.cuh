@@ -161,8 +161,8 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_kernel(const
             const int64_t g = e * N + j;
             if (P.obs) {
                 float2 *ob = reinterpret_cast<float2 *>(P.obs + g * 6);
-                ob[0] = active ? make_float2(rj.x, rj.y) : make_float2(0.f, 0.f);
-                ob[1] = active ? make_float2(xj.x, xj.y) : make_float2(0.f, 0.f);
+                ob[0] = make_float2(rj.x, rj.y);      // an absent agent's row keeps its positions (sinr = snr = 0)
+                ob[1] = make_float2(xj.x, xj.y);
                 ob[2] = make_float2(o.sinr_dB, o.snr_dB);
             }
             if (P.cap) P.cap[g] = o.cap;

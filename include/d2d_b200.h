@@ -97,7 +97,8 @@ typedef struct d2d_step_io {
     const int32_t *actions;     /* [E][N] raw Discrete actions (envs/d2d_env.py:36-40); < 0 = agent absent this step */
     float *obs;                 /* [E][N][6] compact LinearObsFunction table (envs/obs_fn.py:55-61):
                                    (tx_x, tx_y, rx_x, rx_y, sinr_dB, snr_dB); agent i's reference vector is
-                                   rows [i, others...] of this table (envs/obs_fn.py:43-53) */
+                                   rows [i, others...] of this table (envs/obs_fn.py:43-53); the row of an absent agent
+                                   keeps its positions and has sinr = snr = 0 */
     float *capacity_mbps;       /* [E][N]  simulator.py:144-154 */
     float *reward;              /* [E]     SystemCapacityRewardFunction scalar (envs/reward_fn.py:27-44) */
     uint8_t *done;              /* [E]     num_steps >= episode_length (envs/d2d_env.py:68) */

@@ -138,14 +138,11 @@ static int step_one(const d2d_oracle_cfg *cfg, const d2d_oracle_device *dev, con
         if (rate_o) rate_o[j] = rate;
         if (cap_o) cap_o[j] = capacity;
         if (obs_o) { /* envs/obs_fn.py:55-61 */
+            /* the reference has no row at all for an absent agent; the batched table keeps its positions and zeros */
             double *row = obs_o + 6 * j;
-            if (present) {
-                row[0] = pos[2 * txd[j]]; row[1] = pos[2 * txd[j] + 1];
-                row[2] = pos[2 * rxd[j]]; row[3] = pos[2 * rxd[j] + 1];
-                row[4] = sinr_db; row[5] = snr_db;
-            } else {
-                memset(row, 0, 6 * sizeof(double));
-            }
+            row[0] = pos[2 * txd[j]]; row[1] = pos[2 * txd[j] + 1];
+            row[2] = pos[2 * rxd[j]]; row[3] = pos[2 * rxd[j] + 1];
+            row[4] = present ? sinr_db : 0.0; row[5] = present ? snr_db : 0.0;
         }
     }
 

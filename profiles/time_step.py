@@ -8,10 +8,13 @@ import torch  # noqa: E402
 import gym_d2d_b200 as G  # noqa: E402
 
 E = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
-env = G.VecD2DEnv(E, {}, device='cuda', seed=0)
+iters = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 20
+dense = 'dense' in sys.argv
+cfg = dict(num_rbs=100, num_cues=100, num_due_pairs=500, path_loss_model=G.FreeSpacePathLoss) if dense else {}
+env = G.VecD2DEnv(E, cfg, device='cuda', seed=0)
 env.reset()
-ring = 32 if E <= 16384 else 8
+ring = 32 if E <= 16384 and not dense else (8 if not dense else 4)
+B = 32 * env.num_links + 8 * env.num_devices + 5
 acts = [env.sample_actions() for _ in range(ring)]
 outs = [env.alloc_outputs() for _ in range(ring)]
 for a, o in zip(acts, outs):
@@ -27,4 +30,4 @@ for _ in range(iters):
 t.record()
 torch.cuda.synchronize()
 us = s.elapsed_time(t) * 1e3 / (iters * ring)
-print(f'E={E} {us:.2f} us/step  {E / us * 1e6:.3e} env-steps/s  frac={2213 * E / us / 1e3 / 6546.2:.3f}  geom={env.step_geometry()} rescues/env-step={env.stats()["rescues"] / env.stats()["env_steps"]:.4f}')
+print(f'E={E} {us:.2f} us/step  {E / us * 1e6:.3e} env-steps/s  frac={B * E / us / 1e3 / 6546.2:.3f}  geom={env.step_geometry()} rescues/env-step={env.stats()["rescues"] / env.stats()["env_steps"]:.4f}')
