@@ -351,20 +351,25 @@ def run_cuda_arm(args) -> None:
     # ---- end to end through the C ABI with HOST buffers (d2d_step_host): H2D actions + D2H results per step ----
     e2e = None
     if not args.skip_e2e:
-        host_out = env.alloc_host_outputs(pinned=True, info=False)
+        host_outs = [env.alloc_host_outputs(pinned=True, info=False), env.alloc_host_outputs(pinned=True, info=False)]
         host_acts = [torch.empty((E, N), dtype=torch.int32, pin_memory=True) for _ in range(4)]
         for h, a in zip(host_acts, acts):
             h.copy_(a)
         host_np = [h.numpy() for h in host_acts]
         e2e_steps = max(10, min(args.steps, 200))
         for i in range(3):
-            env.step_host(host_np[i % 4], host_out)
+            env.step_host(host_np[i % 4], host_outs[0])
         torch.cuda.synchronize()
         if pg is not None:
             pg.barrier()
+        # two steps in flight: upload(i+1) and download(i-1) overlap kernel(i); every step's results reach the host
         t0 = time.perf_counter()
         for i in range(e2e_steps):
-            env.step_host(host_np[i % 4], host_out)      # synchronous: returns with the results on the host
+            if i >= 2:
+                env.step_host_wait(i & 1)
+            env.step_host_async(host_np[i % 4], host_outs[i & 1], i & 1)
+        env.step_host_wait(0)
+        env.step_host_wait(1)
         t1 = time.perf_counter()
         windows.append((t0, t1))
         dt = t1 - t0
@@ -374,7 +379,8 @@ def run_cuda_arm(args) -> None:
             dt = float(t.item())
         e2e = {'value': world * E * e2e_steps / dt, 'unit': UNIT, 'h2d_bytes_per_step': E * N * 4,
                'd2h_bytes_per_step': E * N * 24 + E * N * 4 + E * 4 + E, 'steps': e2e_steps,
-               'api': 'd2d_step_host via VecD2DEnv.step_host (pinned host buffers; obs + capacity + reward + done copied back)'}
+               'api': 'd2d_step_host_async/_wait via VecD2DEnv.step_host_async (pinned host buffers, two steps in flight; actions '
+                      'copied in, obs + capacity + reward + done copied back, every step)'}
     env.close()
     del env, acts, outs
 

@@ -67,6 +67,8 @@ SIGNATURES = {
     'd2d_reset': (C.c_int, [_vp, _u64, _u64, _vp, _vp]),
     'd2d_step': (C.c_int, [_vp, C.POINTER(D2DStepIO), _vp]),
     'd2d_step_host': (C.c_int, [_vp, C.POINTER(D2DStepIO), _vp]),
+    'd2d_step_host_async': (C.c_int, [_vp, C.POINTER(D2DStepIO), C.c_int, _vp]),
+    'd2d_step_host_wait': (C.c_int, [_vp, C.c_int]),
     'd2d_per_agent_obs': (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     'd2d_stats_reset': (C.c_int, [_vp, _vp]),
     'd2d_launch_count': (_i64, [_vp]),

@@ -58,7 +58,11 @@ struct d2d_handle {
     uint8_t *step_count = nullptr;
     double *stats = nullptr;
     // staging for d2d_step_host / d2d_set_positions (handle-owned, allocated on first use)
-    void *stage[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void *stage2[2][8] = {};
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {}, ev_kernel[2] = {}, ev_out[2] = {};
+    bool slot_used[2] = {false, false};
+    bool pipe_ready = false;
     double *stage_pos = nullptr;
     int64_t stage_pos_envs = 0;
     int64_t launches = 0;
@@ -267,7 +271,12 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
 D2D_API int d2d_destroy(d2d_handle_t *h) {
     if (!h) return D2D_OK;
     cudaFree(h->dA); cudaFree(h->dB); cudaFree(h->dD); cudaFree(h->dPwr); cudaFree(h->dPwrD); cudaFree(h->stage_pos);
-    for (void *p : h->stage) cudaFree(p);
+    for (auto &slot : h->stage2)
+        for (void *p : slot) cudaFree(p);
+    if (h->pipe_ready) {
+        cudaStreamDestroy(h->s_in); cudaStreamDestroy(h->s_out);
+        for (int s = 0; s < 2; ++s) { cudaEventDestroy(h->ev_in[s]); cudaEventDestroy(h->ev_kernel[s]); cudaEventDestroy(h->ev_out[s]); }
+    }
     delete h;
     return D2D_OK;
 }
@@ -391,33 +400,79 @@ D2D_API int d2d_step(d2d_handle_t *h, const d2d_step_io_t *io, void *stream) {
     return D2D_OK;
 }
 
-D2D_API int d2d_step_host(d2d_handle_t *h, const d2d_step_io_t *hio, void *stream) {
-    if (!h || !hio || !hio->actions) return fail(D2D_ERR_INVALID_ARG, "d2d_step_host: handle, io and io->actions are required");
-    if (!h->pos) return fail(D2D_ERR_STATE, "d2d_step_host: call d2d_bind_state first");
+// ---- host-buffer steps: a two-slot pipeline (copy-in stream -> caller's stream for the kernel -> copy-out stream) ----
+namespace {
+
+int host_pipeline_init(d2d_handle *h) {
+    if (h->pipe_ready) return D2D_OK;
+    D2D_CUDA(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    D2D_CUDA(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    for (int s = 0; s < 2; ++s) {
+        D2D_CUDA(cudaEventCreateWithFlags(&h->ev_in[s], cudaEventDisableTiming));
+        D2D_CUDA(cudaEventCreateWithFlags(&h->ev_kernel[s], cudaEventDisableTiming));
+        D2D_CUDA(cudaEventCreateWithFlags(&h->ev_out[s], cudaEventDisableTiming));
+    }
+    h->pipe_ready = true;
+    return D2D_OK;
+}
+
+}  // namespace
+
+D2D_API int d2d_step_host_async(d2d_handle_t *h, const d2d_step_io_t *hio, int slot, void *stream) {
+    if (!h || !hio || !hio->actions) return fail(D2D_ERR_INVALID_ARG, "d2d_step_host_async: handle, io and io->actions are required");
+    if (slot < 0 || slot > 1) return fail(D2D_ERR_INVALID_ARG, "d2d_step_host_async: slot must be 0 or 1");
+    if (!h->pos) return fail(D2D_ERR_STATE, "d2d_step_host_async: call d2d_bind_state first");
     int rc = ensure_device(h);
+    if (rc) return rc;
+    rc = host_pipeline_init(h);
     if (rc) return rc;
     const size_t E = (size_t)h->cfg.num_envs, EN = E * h->N;
     const size_t bytes[8] = {EN * 4, EN * 24, EN * 4, E * 4, E, EN * 4, EN * 2, EN * 2};
     void *host[8] = {(void *)hio->actions, hio->obs, hio->capacity_mbps, hio->reward, hio->done, hio->rate_bps, hio->rb, hio->tx_pwr_dBm};
+    void **stage = h->stage2[slot];
     for (int i = 0; i < 8; ++i)
-        if (host[i] && !h->stage[i]) D2D_CUDA(cudaMalloc(&h->stage[i], bytes[i]));
+        if (host[i] && !stage[i]) D2D_CUDA(cudaMalloc(&stage[i], bytes[i]));
     cudaStream_t st = (cudaStream_t)stream;
-    D2D_CUDA(cudaMemcpyAsync(h->stage[0], host[0], bytes[0], cudaMemcpyHostToDevice, st));
+    // copy-in: this slot's action staging is free once the kernel that last read it has run
+    if (h->slot_used[slot]) D2D_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_kernel[slot], 0));
+    D2D_CUDA(cudaMemcpyAsync(stage[0], host[0], bytes[0], cudaMemcpyHostToDevice, h->s_in));
+    D2D_CUDA(cudaEventRecord(h->ev_in[slot], h->s_in));
+    // kernel on the caller's stream (steps stay ordered there): needs the actions in, and this slot's previous
+    // outputs copied out
+    D2D_CUDA(cudaStreamWaitEvent(st, h->ev_in[slot], 0));
+    if (h->slot_used[slot]) D2D_CUDA(cudaStreamWaitEvent(st, h->ev_out[slot], 0));
     d2d_step_io_t dio{};
-    dio.actions = (const int32_t *)h->stage[0];
-    dio.obs = hio->obs ? (float *)h->stage[1] : nullptr;
-    dio.capacity_mbps = hio->capacity_mbps ? (float *)h->stage[2] : nullptr;
-    dio.reward = hio->reward ? (float *)h->stage[3] : nullptr;
-    dio.done = hio->done ? (uint8_t *)h->stage[4] : nullptr;
-    dio.rate_bps = hio->rate_bps ? (float *)h->stage[5] : nullptr;
-    dio.rb = hio->rb ? (int16_t *)h->stage[6] : nullptr;
-    dio.tx_pwr_dBm = hio->tx_pwr_dBm ? (int16_t *)h->stage[7] : nullptr;
+    dio.actions = (const int32_t *)stage[0];
+    dio.obs = hio->obs ? (float *)stage[1] : nullptr;
+    dio.capacity_mbps = hio->capacity_mbps ? (float *)stage[2] : nullptr;
+    dio.reward = hio->reward ? (float *)stage[3] : nullptr;
+    dio.done = hio->done ? (uint8_t *)stage[4] : nullptr;
+    dio.rate_bps = hio->rate_bps ? (float *)stage[5] : nullptr;
+    dio.rb = hio->rb ? (int16_t *)stage[6] : nullptr;
+    dio.tx_pwr_dBm = hio->tx_pwr_dBm ? (int16_t *)stage[7] : nullptr;
     rc = d2d_step(h, &dio, stream);
     if (rc) return rc;
+    D2D_CUDA(cudaEventRecord(h->ev_kernel[slot], st));
+    // copy-out
+    D2D_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_kernel[slot], 0));
     for (int i = 1; i < 8; ++i)
-        if (host[i]) D2D_CUDA(cudaMemcpyAsync(host[i], h->stage[i], bytes[i], cudaMemcpyDeviceToHost, st));
-    D2D_CUDA(cudaStreamSynchronize(st));
+        if (host[i]) D2D_CUDA(cudaMemcpyAsync(host[i], stage[i], bytes[i], cudaMemcpyDeviceToHost, h->s_out));
+    D2D_CUDA(cudaEventRecord(h->ev_out[slot], h->s_out));
+    h->slot_used[slot] = true;
     return D2D_OK;
+}
+
+D2D_API int d2d_step_host_wait(d2d_handle_t *h, int slot) {
+    if (!h || slot < 0 || slot > 1) return fail(D2D_ERR_INVALID_ARG, "d2d_step_host_wait: bad handle or slot");
+    if (!h->slot_used[slot]) return D2D_OK;
+    D2D_CUDA(cudaEventSynchronize(h->ev_out[slot]));
+    return D2D_OK;
+}
+
+D2D_API int d2d_step_host(d2d_handle_t *h, const d2d_step_io_t *hio, void *stream) {
+    int rc = d2d_step_host_async(h, hio, 0, stream);
+    if (rc) return rc;
+    return d2d_step_host_wait(h, 0);
 }
 
 D2D_API int d2d_per_agent_obs(d2d_handle_t *h, const float *table, float *out, int64_t num_envs, void *stream) {

@@ -238,23 +238,34 @@ class VecD2DEnv:
         torch.cuda.current_stream(self.device).wait_stream(side)
         return graph
 
+    def _host_io(self, actions: np.ndarray, out: Dict[str, np.ndarray]) -> '_lib.D2DStepIO':
+        if actions.dtype != np.int32 or not actions.flags['C_CONTIGUOUS'] or actions.shape != (self.num_envs, self.num_links):
+            raise ValueError(f'actions must be a C-contiguous int32 array of shape {(self.num_envs, self.num_links)}')
+        return _lib.D2DStepIO(actions=actions.ctypes.data, obs=out['obs'].ctypes.data,
+                              capacity_mbps=out['capacity_mbps'].ctypes.data, reward=out['reward'].ctypes.data,
+                              done=out['done'].ctypes.data,
+                              rate_bps=out['rate_bps'].ctypes.data if 'rate_bps' in out else None,
+                              rb=out['rb'].ctypes.data if 'rb' in out else None,
+                              tx_pwr_dBm=out['tx_pwr_dbm'].ctypes.data if 'tx_pwr_dbm' in out else None)
+
     def step_host(self, actions: np.ndarray, out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
         """End-to-end host call (d2d_step_host): host int32 actions in, host arrays out, copies included.
         This is the entry the reference's CPU-side loop would bind."""
         a = np.ascontiguousarray(actions, dtype=np.int32)
-        E, N = self.num_envs, self.num_links
-        if a.shape != (E, N):
-            raise ValueError(f'actions must have shape {(E, N)}')
         if out is None:
             out = self.alloc_host_outputs()
-        io = _lib.D2DStepIO(actions=a.ctypes.data, obs=out['obs'].ctypes.data,
-                            capacity_mbps=out['capacity_mbps'].ctypes.data, reward=out['reward'].ctypes.data,
-                            done=out['done'].ctypes.data,
-                            rate_bps=out['rate_bps'].ctypes.data if 'rate_bps' in out else None,
-                            rb=out['rb'].ctypes.data if 'rb' in out else None,
-                            tx_pwr_dBm=out['tx_pwr_dbm'].ctypes.data if 'tx_pwr_dbm' in out else None)
+        io = self._host_io(a, out)
         _lib.check(self._lib.d2d_step_host(self._h, C.byref(io), self._stream()))
         return out
+
+    def step_host_async(self, actions: np.ndarray, out: Dict[str, np.ndarray], slot: int) -> None:
+        """Pipelined host step (d2d_step_host_async): enqueue upload -> kernel -> download for `slot` (0 or 1) and
+        return at once; the arrays must stay alive (and should be pinned) until step_host_wait(slot)."""
+        io = self._host_io(actions, out)
+        _lib.check(self._lib.d2d_step_host_async(self._h, C.byref(io), int(slot), self._stream()))
+
+    def step_host_wait(self, slot: int) -> None:
+        _lib.check(self._lib.d2d_step_host_wait(self._h, int(slot)))
 
     def alloc_host_outputs(self, pinned: bool = False, info: bool = True) -> Dict[str, np.ndarray]:
         E, N = self.num_envs, self.num_links
@@ -263,8 +274,8 @@ class VecD2DEnv:
         if info:
             spec.update({'rate_bps': ((E, N), torch.float32), 'rb': ((E, N), torch.int16),
                          'tx_pwr_dbm': ((E, N), torch.int16)})
-        self._host_keepalive = {k: torch.zeros(s, dtype=d, pin_memory=pinned) for k, (s, d) in spec.items()}
-        return {k: t.numpy() for k, t in self._host_keepalive.items()}
+        # the ndarrays keep their (optionally pinned) torch storage alive
+        return {k: torch.zeros(s, dtype=d, pin_memory=pinned).numpy() for k, (s, d) in spec.items()}
 
     def per_agent_obs(self, obs: Optional[torch.Tensor] = None, num_envs: Optional[int] = None) -> torch.Tensor:
         """Materialise the reference's per-agent layout (envs/obs_fn.py:43-53): [E][N][6N].  O(N^2) bytes."""

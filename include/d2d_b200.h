@@ -158,6 +158,14 @@ D2D_API int d2d_step(d2d_handle_t *h, const d2d_step_io_t *io, void *stream);
  * own env.step loop) would bind. */
 D2D_API int d2d_step_host(d2d_handle_t *h, const d2d_step_io_t *host_io, void *stream);
 
+/* Pipelined form of d2d_step_host for a CPU-side loop that keeps two steps in flight: slot 0 / 1 select one of two
+ * device staging sets; the action upload runs on the library's copy-in stream, the kernel on `stream` (so steps stay
+ * ordered), the result download on its copy-out stream.  d2d_step_host_wait(slot) blocks until that slot's results
+ * are in the host buffers; a slot may be re-submitted only after it has been waited for.  Host buffers should be
+ * pinned.  d2d_step_host(...) == d2d_step_host_async(..., 0, ...) + d2d_step_host_wait(0). */
+D2D_API int d2d_step_host_async(d2d_handle_t *h, const d2d_step_io_t *host_io, int slot, void *stream);
+D2D_API int d2d_step_host_wait(d2d_handle_t *h, int slot);
+
 /* Materialises the reference's per-agent observation layout (envs/obs_fn.py:43-53) from the compact
  * table: out[e][i] = concat(table[e][i], table[e][k] for k != i), float32 [E][N][6N].  O(N^2) bytes:
  * provided for drop-in use at small E only. */

@@ -417,6 +417,33 @@ def test_host_call_equals_device_call():
     env.close()
 
 
+def test_pipelined_host_steps_equal_synchronous_ones():
+    """d2d_step_host_async / _wait with two steps in flight deliver, step for step, what d2d_step_host delivers."""
+    cfg = O.OracleConfig()
+    E, T = 500, 7
+    rng = np.random.default_rng(8)
+    pos = O.random_positions(cfg, E, rng)
+    acts = [O.random_actions(cfg, E, rng) for _ in range(T)]
+    sync_env, pipe_env = make_vec(E), make_vec(E)
+    sync_env.set_positions(pos); pipe_env.set_positions(pos)
+    want = [{k: v.copy() for k, v in sync_env.step_host(a).items()} for a in acts]
+    outs = [pipe_env.alloc_host_outputs(pinned=True), pipe_env.alloc_host_outputs(pinned=True)]
+    got = []
+    for i, a in enumerate(acts):
+        if i >= 2:
+            pipe_env.step_host_wait(i & 1)
+            got.append({k: v.copy() for k, v in outs[i & 1].items()})
+        pipe_env.step_host_async(a, outs[i & 1], i & 1)
+    for i in (T - 2, T - 1):
+        pipe_env.step_host_wait(i & 1)
+        got.append({k: v.copy() for k, v in outs[i & 1].items()})
+    for w, g in zip(want, got):
+        for k in w:
+            np.testing.assert_array_equal(w[k], g[k], err_msg=k)
+    assert (got[-1]['done'] == 0).all() and (pipe_env.step_count == T).all()
+    sync_env.close(); pipe_env.close()
+
+
 @pytest.mark.parametrize('E', [100, 40000])      # both launch shapes of the warp kernel (4- and 8-warp blocks)
 def test_core_output_fast_path_equals_general_path(E):
     """VecD2DEnv(info=False) passes exactly the core outputs and takes the kernel instantiation that tests no output
