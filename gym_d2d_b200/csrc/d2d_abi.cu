@@ -44,6 +44,7 @@ struct d2d_handle {
     bool ple2 = true;
     bool use_warp = true;
     int wpb = 4;               // warps per block of the warp kernel
+    int64_t chunk_override = 0;  // D2D_B200_CHUNK: force small launch chunks (tests of the > 2^31-element path)
     bool pdl = true;           // programmatic dependent launch (D2D_B200_PDL=0 disables)
     int grid = 0, block = 0, smem = 0, envs_per_block = 0;
     double K_dB = 0.0, ple = 2.0;
@@ -244,6 +245,7 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
 
     // warp kernel: one lane slot per CUE and per DUE pair; its cross-slot bin table is exact for RB keys < 64
     h->use_warp = cfg->num_cues <= 32 && cfg->num_due_pairs <= 32 && cfg->num_rbs <= 64;
+    if (const char *c = std::getenv("D2D_B200_CHUNK")) h->chunk_override = std::atoll(c);
     const char *pdl = std::getenv("D2D_B200_PDL");
     h->pdl = !(pdl && std::strcmp(pdl, "0") == 0);
     int rc;
@@ -359,7 +361,8 @@ D2D_API int d2d_step(d2d_handle_t *h, const d2d_step_io_t *io, void *stream) {
     D2DParams P = make_params(h, io);
     cudaStream_t st = (cudaStream_t)stream;
     // the kernels index with 32 bits: batches beyond 2^31 / max(6N, 2V) envs (> 7 million default envs) go in chunks
-    const int64_t chunk = std::max<int64_t>(1, (int64_t)0x7fffffff / std::max(6 * h->N, 2 * h->V));
+    int64_t chunk = std::max<int64_t>(1, (int64_t)0x7fffffff / std::max(6 * h->N, 2 * h->V));
+    if (h->chunk_override > 0) chunk = std::min(chunk, h->chunk_override);
     for (int64_t e0 = 0; e0 < h->cfg.num_envs; e0 += chunk) {
         const int64_t n = std::min<int64_t>(chunk, h->cfg.num_envs - e0);
         if (e0 > 0) {

@@ -417,6 +417,53 @@ def test_host_call_equals_device_call():
     env.close()
 
 
+@pytest.mark.parametrize('name', ['default', 'block_min'])
+def test_chunked_launch_equals_single_launch(name, monkeypatch):
+    """Batches beyond 2^31 / max(6N, 2V) envs are stepped in several launches with offset pointers; force tiny
+    chunks (D2D_B200_CHUNK) and require bit-identical results, counters and statistics."""
+    kw = CONFIGS[name]
+    cfg = O.OracleConfig(**kw)
+    E = 1000
+    rng = np.random.default_rng(4)
+    pos, act = O.random_positions(cfg, E, rng), O.random_actions(cfg, E, rng)
+    whole = make_vec(E, kw)
+    monkeypatch.setenv('D2D_B200_CHUNK', '300')
+    parts = make_vec(E, kw)
+    monkeypatch.delenv('D2D_B200_CHUNK')
+    for env in (whole, parts):
+        env.reset_stats()
+    a, b = run_step(whole, pos, act), run_step(parts, pos, act)
+    assert parts.launch_count - whole.launch_count == 3          # 4 launches instead of 1
+    for k in a:
+        if name == 'default' or a[k].dtype.kind in 'iu':
+            np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+        else:   # block kernel: the order of links inside an RB bin follows the shared-memory atomics, so the fp32
+            np.testing.assert_allclose(a[k], b[k], rtol=2e-5, atol=0, err_msg=k)   # interference sum may differ in the last bit
+    assert torch.equal(whole.step_count, parts.step_count)
+    sa, sb = whole.stats(), parts.stats()
+    assert sa['env_steps'] == sb['env_steps'] == E and sa['sum_reward'] == pytest.approx(sb['sum_reward'], rel=1e-6)
+    whole.close(); parts.close()
+
+
+def test_out_of_range_actions_cannot_corrupt_memory():
+    """Appendix B.9: the reference decodes out-of-range actions silently.  The tensor API leaves their result
+    unspecified but must stay memory-safe and must not disturb other envs (run under compute-sanitizer too)."""
+    cfg = O.OracleConfig()
+    E = 256
+    rng = np.random.default_rng(12)
+    pos, act = O.random_positions(cfg, E, rng), O.random_actions(cfg, E, rng)
+    bad = act.copy()
+    bad[::2, ::7] = 2 ** 31 - 1
+    bad[::2, 1::7] = 600 * 50
+    env = make_vec(E)
+    out = run_step(env, pos, bad)
+    ref = O.step_batch(cfg, pos, act, nthreads=4)
+    clean = np.arange(1, E, 2)
+    assert_rel(out['obs'][clean, :, 4], ref['sinr_db'][clean], RTOL, 'untouched envs')
+    assert_rel(out['reward'][clean], ref['reward'][clean], RTOL, 'untouched envs reward')
+    env.close()
+
+
 def test_pipelined_host_steps_equal_synchronous_ones():
     """d2d_step_host_async / _wait with two steps in flight deliver, step for step, what d2d_step_host delivers."""
     cfg = O.OracleConfig()
