@@ -43,6 +43,7 @@ struct d2d_handle {
     int num_sms = 0;
     bool ple2 = true;
     bool use_warp = true;
+    bool spec = false;         // warp kernel instantiated for the reference's default EnvConfig shape
     int wpb = 4;               // warps per block of the warp kernel
     int64_t chunk_override = 0;  // D2D_B200_CHUNK: force small launch chunks (tests of the > 2^31-element path)
     bool pdl = true;           // programmatic dependent launch (D2D_B200_PDL=0 disables)
@@ -129,9 +130,25 @@ cudaError_t launch_step(K kernel, int grid, int block, size_t smem, cudaStream_t
 }
 
 template <typename K>
+int allow_smem(K kernel, size_t smem) {
+    if (smem > 48 * 1024) D2D_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return D2D_OK;
+}
+
+// every (EXACT, FULL) instantiation d2d_step may launch for this handle needs the dynamic shared-memory opt-in
+template <bool PLE2, int WPB, bool SPEC>
+int allow_smem_warp(size_t smem) {
+    int rc = allow_smem(d2d_step_warp_kernel<PLE2, false, WPB, false, SPEC>, smem);
+    if (!rc) rc = allow_smem(d2d_step_warp_kernel<PLE2, false, WPB, true, SPEC>, smem);
+    if (!rc) rc = allow_smem(d2d_step_warp_kernel<PLE2, true, WPB, false, SPEC>, smem);
+    if (!rc) rc = allow_smem(d2d_step_warp_kernel<PLE2, true, WPB, true, SPEC>, smem);
+    return rc;
+}
+
+template <typename K>
 int plan_geometry(d2d_handle *h, K kernel, int block, size_t smem, int envs_per_block) {
-    if (smem > 48 * 1024)
-        D2D_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int rc = allow_smem(kernel, smem);
+    if (rc) return rc;
     int occ = 0;
     D2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem));
     if (occ < 1) return fail(D2D_ERR_UNSUPPORTED, "step kernel does not fit on an SM for this configuration");
@@ -142,6 +159,22 @@ int plan_geometry(d2d_handle *h, K kernel, int block, size_t smem, int envs_per_
     h->smem = (int)smem;
     h->envs_per_block = envs_per_block;
     return D2D_OK;
+}
+
+template <int WPB>
+int plan_warp(d2d_handle *h, size_t smem) {
+    int rc;
+    if (h->spec) {          // the reference's default EnvConfig shape: counts and division magics are immediates
+        rc = allow_smem_warp<true, WPB, true>(smem);
+        if (!rc) rc = plan_geometry(h, d2d_step_warp_kernel<true, false, WPB, true, true>, WPB * 32, smem, WPB);
+    } else if (h->ple2) {
+        rc = allow_smem_warp<true, WPB, false>(smem);
+        if (!rc) rc = plan_geometry(h, d2d_step_warp_kernel<true, false, WPB, true, false>, WPB * 32, smem, WPB);
+    } else {
+        rc = allow_smem_warp<false, WPB, false>(smem);
+        if (!rc) rc = plan_geometry(h, d2d_step_warp_kernel<false, false, WPB, true, false>, WPB * 32, smem, WPB);
+    }
+    return rc;
 }
 
 }  // namespace
@@ -243,7 +276,7 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
     D2D_CUDA_BAIL(cudaMemcpy(h->dPwr, pwr, sizeof(pwr), cudaMemcpyHostToDevice));
 #undef D2D_CUDA_BAIL
 
-    // warp kernel: one lane slot per CUE and per DUE pair; its cross-slot bin table is exact for RB keys < 64
+    // warp kernel: one lane slot per CUE and per DUE pair, one shared-memory bin per RB
     h->use_warp = cfg->num_cues <= 32 && cfg->num_due_pairs <= 32 && cfg->num_rbs <= 64;
     if (const char *c = std::getenv("D2D_B200_CHUNK")) h->chunk_override = std::atoll(c);
     const char *pdl = std::getenv("D2D_B200_PDL");
@@ -253,12 +286,11 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
         // launch shape by batch size (d2d_step_warp.cuh): about one wave of envs -> 4-warp blocks, many waves -> 8-warp blocks
         h->wpb = cfg->num_envs >= 32768 ? 8 : 4;
         if (const char *w = std::getenv("D2D_B200_WPB")) h->wpb = std::atoi(w) == 8 ? 8 : 4;
-        if (h->wpb == 8)
-            rc = h->ple2 ? plan_geometry(h, d2d_step_warp_kernel<true, false, 8, true>, 256, 0, 8)
-                         : plan_geometry(h, d2d_step_warp_kernel<false, false, 8, true>, 256, 0, 8);
-        else
-            rc = h->ple2 ? plan_geometry(h, d2d_step_warp_kernel<true, false, 4, true>, 128, 0, 4)
-                         : plan_geometry(h, d2d_step_warp_kernel<false, false, 4, true>, 128, 0, 4);
+        h->spec = h->ple2 && cfg->num_rbs == 25 && cfg->num_cues == 25 && cfg->num_due_pairs == 25 && cfg->n_pwr_cue == 24 &&
+                  cfg->n_pwr_due == 21;
+        if (const char *sp = std::getenv("D2D_B200_SPEC")) h->spec = h->spec && std::atoi(sp) != 0;   // tests: force the generic shape
+        const size_t smem = d2d_warp_smem_bytes(cfg->num_rbs, h->wpb);
+        rc = h->wpb == 8 ? plan_warp<8>(h, smem) : plan_warp<4>(h, smem);
     } else {
         const size_t smem = d2d_block_smem_bytes(h->N, cfg->num_rbs);
         if (smem > 227 * 1024) return bail(fail(D2D_ERR_UNSUPPORTED, "d2d_create: too many links / RBs for one SM's shared memory"));
@@ -383,15 +415,19 @@ D2D_API int d2d_step(d2d_handle_t *h, const d2d_step_io_t *io, void *stream) {
         const bool exact = h->pos64 != nullptr;
         cudaError_t err;
         // FULL: exactly the core outputs were passed, so the kernel tests no output pointer on its hot path
-        const bool full = io->obs && io->capacity_mbps && io->reward && io->done && !io->rate_bps && !io->rb && !io->tx_pwr_dBm;
-#define D2D_LAUNCH_WARP(PLE2_, EXACT_, WPB_, FULL_) \
-    launch_step(d2d_step_warp_kernel<PLE2_, EXACT_, WPB_, FULL_>, grid, WPB_ * 32, 0, st, P, h->pdl)
-#define D2D_PICK_FULL(PLE2_, EXACT_, WPB_) (full ? D2D_LAUNCH_WARP(PLE2_, EXACT_, WPB_, true) : D2D_LAUNCH_WARP(PLE2_, EXACT_, WPB_, false))
-#define D2D_PICK_EXACT(PLE2_, WPB_) (exact ? D2D_PICK_FULL(PLE2_, true, WPB_) : D2D_PICK_FULL(PLE2_, false, WPB_))
+        const bool full = io->obs && io->capacity_mbps && io->reward && io->done && !io->rate_bps && !io->rb && !io->tx_pwr_dBm &&
+                          h->step_count;
+#define D2D_LAUNCH_WARP(PLE2_, EXACT_, WPB_, FULL_, SPEC_) \
+    launch_step(d2d_step_warp_kernel<PLE2_, EXACT_, WPB_, FULL_, SPEC_>, grid, WPB_ * 32, h->smem, st, P, h->pdl)
+#define D2D_PICK_FULL(PLE2_, EXACT_, WPB_, SPEC_) \
+    (full ? D2D_LAUNCH_WARP(PLE2_, EXACT_, WPB_, true, SPEC_) : D2D_LAUNCH_WARP(PLE2_, EXACT_, WPB_, false, SPEC_))
+#define D2D_PICK_EXACT(PLE2_, WPB_, SPEC_) (exact ? D2D_PICK_FULL(PLE2_, true, WPB_, SPEC_) : D2D_PICK_FULL(PLE2_, false, WPB_, SPEC_))
+#define D2D_PICK_SHAPE(WPB_) \
+    (h->spec ? D2D_PICK_EXACT(true, WPB_, true) : h->ple2 ? D2D_PICK_EXACT(true, WPB_, false) : D2D_PICK_EXACT(false, WPB_, false))
         if (h->use_warp && h->wpb == 8) {
-            err = h->ple2 ? D2D_PICK_EXACT(true, 8) : D2D_PICK_EXACT(false, 8);
+            err = D2D_PICK_SHAPE(8);
         } else if (h->use_warp) {
-            err = h->ple2 ? D2D_PICK_EXACT(true, 4) : D2D_PICK_EXACT(false, 4);
+            err = D2D_PICK_SHAPE(4);
         } else {
             err = h->ple2 ? launch_step(d2d_step_block_kernel<true>, grid, h->block, h->smem, st, P, h->pdl)
                           : launch_step(d2d_step_block_kernel<false>, grid, h->block, h->smem, st, P, h->pdl);
@@ -507,8 +543,3 @@ D2D_API int d2d_step_geometry(const d2d_handle_t *h, int32_t *grid, int32_t *blo
     return D2D_OK;
 }
 
-#ifdef D2D_TIMELINE
-extern "C" __attribute__((visibility("default"))) int d2d_debug_timeline(unsigned long long *out16) {
-    return (int)cudaMemcpyFromSymbol(out16, d2d_dbg, sizeof(unsigned long long) * 16);
-}
-#endif

@@ -7,57 +7,123 @@
 //
 // Mapping: lane l owns CUE link l (slot A) and DUE pair l (slot B).
 //
-// The masked per-RB interference sum (Actions.get_actions_by_rb, actions.py:27-31 + simulator.py:95-101) is a
-// segmented reduction over links grouped by RB.  The grouping is a per-warp counting sort in shared memory:
-//   rank   = atomicAdd(count[rb], 1)            one shared atomic per link (the DUE count rides in the high half)
-//   offset = exclusive warp-shuffle scan of the 64 counts (two bins per lane, packed in one register)
-//   sorted[offset[rb] + rank] = (tx_x, tx_y, w, u)   the link's peer record
-// after which a victim's co-channel peers are ONE contiguous range of records.  Its first five entries are
-// handled branch-free (plain indexed LDS, predicated terms, so the loads and gains of a lane's two victims
-// overlap); an RB with more than five links (1.4 % of RBs at the default load) falls into a short serial loop.
-// Measured alternatives this replaced: MATCH.ANY costs ~290 cycles per call on sm_100a, and a bit-serial walk over
-// peer masks ~100 cycles per trip (FLO -> shift -> branch is one dependent chain).
+// INPUTS.  Each lane copies its own four items of the NEXT env (CUE action, DUE action, CUE transmitter, DUE
+// transmitter + receiver) with cp.async (LDGSTS) into a private 32-byte slot of the warp's staging buffer while the
+// current env computes, and reads the current env's slot back with two LDS.128.  The prefetch therefore holds no
+// registers and no scoreboard, and the global reads stay coalesced (consecutive lanes copy consecutive elements).
+//
+// GROUPING.  The masked per-RB interference sum (Actions.get_actions_by_rb, actions.py:27-31 + simulator.py:95-101)
+// is a segmented reduction over links grouped by RB.  The grouping is a per-warp BINNED table in shared memory:
+//   rank = atomicAdd(count[rb], 1)                 one shared atomic per link
+//   bin[rb][rank] = (tx_x, tx_y, w, u)             the link's peer record, D2D_BIN_CAP record slots per RB
+// after which a victim's co-channel peers are the first count[rb] records of ITS bin: no prefix scan, no offsets, no
+// scatter pass.  The first D2D_WALK_INLINE records are handled branch-free (immediate-offset LDS, predicated terms, so
+// the loads and gains of a lane's two victims overlap); fuller bins take a short serial loop.  An RB that holds more
+// than D2D_BIN_CAP links (~0.6 % of envs at the default load, but a policy may put every agent on one RB) sends the
+// env down an all-pairs shuffle path that needs no table at all - slower, same results.
 //
 // All CUE links share one receiver (the MBS at the origin), so there an interferer contributes a per-link scalar
 // u_k = w_k g(|tx_k|) computed once, and a CUE victim's walk is a sum of u_k; a DUE victim evaluates
-// w_k g(|tx_k - rx|).  The victim is excluded from its own range by index - never subtracted from a per-RB total,
+// w_k g(|tx_k - rx|).  The victim is excluded from its own bin by index - never subtracted from a per-RB total,
 // which would cancel a weak interferer against a 70 dB stronger self term.
 //
+// SHAPE.  D2DShape<true> instantiates the kernel for the reference's default EnvConfig (25 RBs, 25 CUEs, 25 DUE
+// pairs, 24 / 21 power levels: envs/env_config.py:12-27, envs/d2d_env.py:31-35) with every count, stride and division
+// magic an immediate; D2DShape<false> reads them from the launch parameters.  Same code, same results.
+//
 // HBM traffic per env-step is the compulsory 32N + 8V + 5 bytes: one coalesced pass over the env's
-// actions and positions (software-pipelined one env ahead), one over its outputs; nothing is re-read.  There is no
-// block-level prologue and no block barrier: a warp needs only its own 2.4 KB of shared memory.
+// actions and positions, one over its outputs; nothing is re-read.
 #pragma once
 
 #include "d2d_common.cuh"
 
-// Two launch shapes, picked by the host from the batch size (measured on B200, profiles/README.md):
-//   WPB = 4, >= 7 blocks/SM (72 registers): finest block granularity - best when the batch is about one wave (E = 4096)
-//   WPB = 8, >= 4 blocks/SM (64 registers): best sustained throughput for batches of many waves
-#define D2D_WARP_MIN_BLOCKS(WPB) ((WPB) == 4 ? 7 : 4)
+// Launch shapes, picked by the host from the batch size (measured on B200, profiles/README.md):
+//   WPB = 4: finest block granularity - best when the batch is about one wave (E = 4096)
+//   WPB = 8: best sustained throughput for batches of many waves
+#ifndef D2D_MINB8
+#define D2D_MINB8 4
+#endif
+#ifndef D2D_MINB4
+#define D2D_MINB4 8
+#endif
+#define D2D_WARP_MIN_BLOCKS(WPB) ((WPB) == 4 ? D2D_MINB4 : D2D_MINB8)
 #ifndef D2D_STATS_REPLICAS
 #define D2D_STATS_REPLICAS 32
 #endif
-#define D2D_WALK_INLINE 5      // range entries handled branch-free before the serial loop
+#ifndef D2D_BIN_CAP
+#define D2D_BIN_CAP 8          // peer records per RB bin on the fast path
+#endif
+#ifndef D2D_WALK_INLINE
+#define D2D_WALK_INLINE 5      // records handled branch-free before the serial loop
+#endif
 
-// Per-warp shared memory, addressed through one 32-bit base held in a register (explicit ld/st.shared, so the
-// compiler never re-derives generic addresses from threadIdx).  Byte layout:
-#define D2D_W_SORTED 0u        // float4 sorted[64 + 8]: peer records grouped by RB; the 8 slack records take the dead
-                               // lanes' records (dummy bin 64) and the inline walk's over-read
-#define D2D_W_CNT 1152u        // u32 count[2][68]: per-RB link count (bin 64 = dummy), double-buffered by iteration parity
-#define D2D_W_CNT_STRIDE 272u
-#define D2D_W_OFF 1696u        // u32 offset[68]: exclusive scan of count; offset[64] = 64 (the slack records)
-#define D2D_W_PWR 1968u        // float pwr_lin[128]: the warp's copy of the integer-dBm -> mW table
-#define D2D_W_BYTES 2480u
+// ---- shared memory layout ---------------------------------------------------------------------------------------------
+// block:    pwr_lin[128] f32 | linkA[64] float4 (slot A: lane, slot B: 32 + lane) | linkS[64] float2 (sens, bw)
+// per warp: stage[2][32 lanes][32 B] = (aA, aB, tA.x, tA.y, pB.x, pB.y, pB.z, pB.w) | (R + 1) bins of D2D_BIN_STRIDE bytes
+// A bin = D2D_BIN_CAP records of 16 B + a 16 B tail: {link count, 1 if a SIDELINK is on this RB}; the odd stride also
+// spreads consecutive bins over the banks.  Bin R is the dummy bin of dead lanes (no link, or agent absent this step).
+#define D2D_BLK_PWR 0u
+#define D2D_BLK_LINKA (D2D_MAX_PWR_LEVELS * 4u)
+#define D2D_BLK_LINKS (D2D_BLK_LINKA + 64u * 16u)
+#define D2D_BLK_BYTES (D2D_BLK_LINKS + 64u * 8u)
+#define D2D_STAGE_BYTES 1024u
+#define D2D_BIN_STRIDE (D2D_BIN_CAP * 16u + 16u)
+#define D2D_BIN_CNT (D2D_BIN_CAP * 16u)
+__host__ __device__ inline uint32_t d2d_warp_smem_per_warp(int R) { return 2u * D2D_STAGE_BYTES + (uint32_t)(R + 1) * D2D_BIN_STRIDE; }
+__host__ __device__ inline uint32_t d2d_warp_smem_bytes(int R, int wpb) { return D2D_BLK_BYTES + (uint32_t)wpb * d2d_warp_smem_per_warp(R); }
 
+// Link / device / RB counts of the batch: immediates for the default EnvConfig, launch parameters otherwise.
+template <bool SPEC>
+struct D2DShape {
+    uint32_t c_, n_, v_, r_, npc_, npd_, mc_, md_, n1c_, n1d_;
+    __device__ __forceinline__ explicit D2DShape(const D2DParams &P) {
+        if (!SPEC) {
+            c_ = (uint32_t)P.C; n_ = (uint32_t)P.N; v_ = (uint32_t)P.V; r_ = (uint32_t)P.R;
+            npc_ = (uint32_t)P.n_pwr_cue; npd_ = (uint32_t)P.n_pwr_due;
+            mc_ = P.magic_cue; md_ = P.magic_due; n1c_ = P.npw1_cue; n1d_ = P.npw1_due;
+        }
+    }
+    __device__ __forceinline__ uint32_t C() const { return SPEC ? 25u : c_; }
+    __device__ __forceinline__ uint32_t N() const { return SPEC ? 50u : n_; }
+    __device__ __forceinline__ uint32_t D() const { return SPEC ? 25u : n_ - c_; }
+    __device__ __forceinline__ uint32_t V() const { return SPEC ? 76u : v_; }
+    __device__ __forceinline__ uint32_t R() const { return SPEC ? 25u : r_; }
+    __device__ __forceinline__ uint32_t npc() const { return SPEC ? 24u : npc_; }
+    __device__ __forceinline__ uint32_t npd() const { return SPEC ? 21u : npd_; }
+    // envs/d2d_env.py:95: rb = a // n_pwr for 0 <= a <= R n_pwr, by the multiply-high magic of d2d_div_magic
+    __device__ __forceinline__ uint32_t rb_cue(uint32_t a) const {
+        return SPEC ? __umulhi(a, 178956971u) : __umulhi(a, mc_) + (a & n1c_);      // ceil(2^32 / 24)
+    }
+    __device__ __forceinline__ uint32_t rb_due(uint32_t a) const {
+        return SPEC ? __umulhi(a, 204522253u) : __umulhi(a, md_) + (a & n1d_);      // ceil(2^32 / 21)
+    }
+};
+
+// Explicit ld/st.shared on 32-bit shared-window addresses: the compiler never re-derives generic addresses.
 __device__ __forceinline__ void d2d_sts128(uint32_t a, float x, float y, float z, float w) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
-__device__ __forceinline__ void d2d_sts32(uint32_t a, uint32_t x) {
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(x) : "memory");
+__device__ __forceinline__ void d2d_sts128_if(bool p, uint32_t a, float x, float y, float z, float w) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.shared.v4.f32 [%1], {%2, %3, %4, %5}; }"
+                 ::"r"((uint32_t)p), "r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ void d2d_sts32_if(bool p, uint32_t a, uint32_t x) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.shared.u32 [%1], %2; }" ::"r"((uint32_t)p), "r"(a), "r"(x) : "memory");
+}
+__device__ __forceinline__ void d2d_sts64_if(bool p, uint32_t a, uint32_t x, uint32_t y) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.shared.v2.u32 [%1], {%2, %3}; }" ::"r"((uint32_t)p), "r"(a), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void d2d_sts64f(uint32_t a, float x, float y) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
 }
 __device__ __forceinline__ float4 d2d_lds128(uint32_t a) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 d2d_lds64(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
     return v;
 }
 __device__ __forceinline__ float d2d_lds32(uint32_t a) {
@@ -78,17 +144,41 @@ __device__ __forceinline__ float d2d_lds32_at(uint32_t a) {
     asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(a), "n"(OFF) : "memory");
     return v;
 }
-__device__ __forceinline__ uint32_t d2d_lds32u(uint32_t a) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+template <int OFF>
+__device__ __forceinline__ uint2 d2d_lds64u_at(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(a), "n"(OFF) : "memory");
     return v;
 }
-// predicated shared atomic add (returns 0 when the predicate is off): no branch around a one-instruction body
-__device__ __forceinline__ uint32_t d2d_atoms_add_if(bool p, uint32_t a, uint32_t x) {
-    uint32_t old = 0;
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %1, 0; @q atom.shared.add.u32 %0, [%2], %3; }"
-                 : "+r"(old) : "r"((uint32_t)p), "r"(a), "r"(x) : "memory");
+template <int OFF>
+__device__ __forceinline__ uint32_t d2d_lds32u_at(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(a), "n"(OFF) : "memory");
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ uint32_t d2d_atoms_inc_at(uint32_t a) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1+%2], 1;" : "=r"(old) : "r"(a), "n"(OFF) : "memory");
     return old;
+}
+// cp.async (LDGSTS): predicated per-lane global -> shared copies of 4 / 8 / 16 bytes
+__device__ __forceinline__ void d2d_cp4_if(bool p, uint32_t dst, const void *src) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q cp.async.ca.shared.global [%1], [%2], 4; }" ::"r"((uint32_t)p), "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void d2d_cp8_if(bool p, uint32_t dst, const void *src) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q cp.async.ca.shared.global [%1], [%2], 8; }" ::"r"((uint32_t)p), "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void d2d_cp16_if(bool p, uint32_t dst, const void *src) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q cp.async.cg.shared.global [%1], [%2], 16; }" ::"r"((uint32_t)p), "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void d2d_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void d2d_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// warp-wide integer sum in one instruction (REDUX)
+__device__ __forceinline__ uint32_t d2d_redux_add(uint32_t x) {
+    uint32_t r;
+    asm volatile("redux.sync.add.u32 %0, %1, 0xffffffff;" : "=r"(r) : "r"(x));
+    return r;
 }
 // index of the highest set bit (FLO) and removal of that bit - rescue path only
 __device__ __forceinline__ uint32_t d2d_pop_bit(uint32_t &mask) {
@@ -96,15 +186,6 @@ __device__ __forceinline__ uint32_t d2d_pop_bit(uint32_t &mask) {
     asm("bfind.u32 %0, %1;" : "=r"(k) : "r"(mask));
     mask ^= 1u << k;
     return k;
-}
-
-// A victim's co-channel records are the range [beg, beg + n) of `sorted`; `valid` has bit t set when entry t exists
-// and is not the victim itself.  The first D2D_WALK_INLINE entries are straight-line code with immediate offsets.
-
-// (an RB may hold up to 64 links - the one-RB corner case - so entries 32.. are walked by index in a second rare loop)
-__device__ __forceinline__ uint32_t d2d_valid_mask(uint32_t n, uint32_t rank) {
-    const uint32_t m = n >= 32u ? 0xffffffffu : (1u << n) - 1u;
-    return rank < 32u ? m & ~(1u << rank) : m;
 }
 
 // One interferer's term at a general receiver: w_k g(|tx_k - rx|)
@@ -115,171 +196,315 @@ __device__ __forceinline__ float d2d_term_rx(const float4 r, bool valid, float r
     if (EXACT) dmin2 = valid ? fminf(dmin2, d2) : dmin2;
     return valid ? r.z * d2d_gain<PLE2>(d2, nhp) : 0.0f;
 }
+// A victim's co-channel records are the first records of its bin; `valid` has bit t set when record t exists and is
+// not the victim itself (at most D2D_BIN_CAP bits on the fast path).
 template <bool PLE2, bool EXACT, int T>
-__device__ __forceinline__ void d2d_inline_rx(float &I, uint32_t base, uint32_t valid, float rxx, float rxy, float nhp, float &dmin2) {
+__device__ __forceinline__ void d2d_inline_rx(float &I, uint32_t bin, uint32_t valid, float rxx, float rxy, float nhp, float &dmin2) {
     if constexpr (T < D2D_WALK_INLINE) {
-        I += d2d_term_rx<PLE2, EXACT>(d2d_lds128_at<16 * T>(base), (valid >> T) & 1u, rxx, rxy, nhp, dmin2);
-        d2d_inline_rx<PLE2, EXACT, T + 1>(I, base, valid, rxx, rxy, nhp, dmin2);
+        I += d2d_term_rx<PLE2, EXACT>(d2d_lds128_at<16 * T>(bin), (valid >> T) & 1u, rxx, rxy, nhp, dmin2);
+        d2d_inline_rx<PLE2, EXACT, T + 1>(I, bin, valid, rxx, rxy, nhp, dmin2);
     }
 }
 template <bool PLE2, bool EXACT>
-__device__ __forceinline__ float d2d_walk_rx(uint32_t sorted, uint32_t beg, uint32_t valid, uint32_t n, uint32_t rank,
-                                             float rxx, float rxy, float nhp, float &dmin2) {
+__device__ __forceinline__ float d2d_walk_rx(uint32_t bin, uint32_t valid, float rxx, float rxy, float nhp, float &dmin2) {
     float I = 0.0f;
-    const uint32_t base = sorted + (beg << 4);
-    d2d_inline_rx<PLE2, EXACT, 0>(I, base, valid, rxx, rxy, nhp, dmin2);
+    d2d_inline_rx<PLE2, EXACT, 0>(I, bin, valid, rxx, rxy, nhp, dmin2);
     valid >>= D2D_WALK_INLINE;
-    for (uint32_t a = base + 16u * D2D_WALK_INLINE; valid; valid >>= 1, a += 16u)   // rare: > D2D_WALK_INLINE links on one RB
+    for (uint32_t a = bin + 16u * D2D_WALK_INLINE; valid; valid >>= 1, a += 16u)   // > D2D_WALK_INLINE links on one RB
         I += d2d_term_rx<PLE2, EXACT>(d2d_lds128(a), valid & 1u, rxx, rxy, nhp, dmin2);
-    for (uint32_t t = 32u; t < n; ++t)                                              // corner case: > 32 links on one RB
-        I += d2d_term_rx<PLE2, EXACT>(d2d_lds128(base + (t << 4)), t != rank, rxx, rxy, nhp, dmin2);
     return I;
 }
 // Interference at the MBS: the records carry u_k = w_k g(|tx_k|) in .w
 template <int T>
-__device__ __forceinline__ void d2d_inline_mbs(float &I, uint32_t base, uint32_t valid) {
+__device__ __forceinline__ void d2d_inline_mbs(float &I, uint32_t bin, uint32_t valid) {
     if constexpr (T < D2D_WALK_INLINE) {
-        const float u = d2d_lds32_at<16 * T + 12>(base);
+        const float u = d2d_lds32_at<16 * T + 12>(bin);
         I += ((valid >> T) & 1u) ? u : 0.0f;
-        d2d_inline_mbs<T + 1>(I, base, valid);
+        d2d_inline_mbs<T + 1>(I, bin, valid);
     }
 }
-__device__ __forceinline__ float d2d_walk_mbs(uint32_t sorted, uint32_t beg, uint32_t valid, uint32_t n, uint32_t rank) {
+__device__ __forceinline__ float d2d_walk_mbs(uint32_t bin, uint32_t valid) {
     float I = 0.0f;
-    const uint32_t base = sorted + (beg << 4);
-    d2d_inline_mbs<0>(I, base, valid);
+    d2d_inline_mbs<0>(I, bin, valid);
     valid >>= D2D_WALK_INLINE;
-    for (uint32_t a = base + 16u * D2D_WALK_INLINE + 12u; valid; valid >>= 1, a += 16u) {
+    for (uint32_t a = bin + 16u * D2D_WALK_INLINE + 12u; valid; valid >>= 1, a += 16u) {
         const float u = d2d_lds32(a);
         I += (valid & 1u) ? u : 0.0f;
-    }
-    for (uint32_t t = 32u; t < n; ++t) {
-        const float u = d2d_lds32(base + 12u + (t << 4));
-        I += t != rank ? u : 0.0f;
     }
     return I;
 }
 
 // Predicated global stores (no branch, no reconvergence bookkeeping around a two-line body)
-__device__ __forceinline__ void d2d_stg64_if(bool p, float2 *ptr, float x, float y) {
+__device__ __forceinline__ void d2d_stg64_if(bool p, void *ptr, float x, float y) {
     asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.global.v2.f32 [%1], {%2, %3}; }" ::"r"((uint32_t)p), "l"(ptr), "f"(x), "f"(y) : "memory");
 }
-__device__ __forceinline__ void d2d_stg32_if(bool p, float *ptr, float x) {
+__device__ __forceinline__ void d2d_stg32_if(bool p, void *ptr, float x) {
     asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.global.f32 [%1], %2; }" ::"r"((uint32_t)p), "l"(ptr), "f"(x) : "memory");
 }
-__device__ __forceinline__ void d2d_stg16_if(bool p, int16_t *ptr, int x) {
+__device__ __forceinline__ void d2d_stg16_if(bool p, void *ptr, int x) {
     asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.global.u16 [%1], %2; }" ::"r"((uint32_t)p), "l"(ptr), "h"((short)x) : "memory");
 }
 
-// One env's inputs as a lane sees them: its CUE action + transmitter, its DUE action + (tx, rx) pair.
-// Lanes without a link (lane >= C or >= D) and agents absent this step (action < 0) are "dead": they keep running
-// the same straight-line code on benign values, sort into a dummy RB bin and are masked out of every sum and store.
-struct D2DLaneIn {
-    int aA, aB, ns;   // ns: this env's step counter (lane 0 only)
-    float2 tA;        // CUE transmitter (its receiver is the MBS at the origin)
-    float4 pB;        // DUE (tx_x, tx_y, rx_x, rx_y)
-};
-__device__ __forceinline__ D2DLaneIn d2d_load_inputs(const D2DParams &P, uint32_t e, uint32_t lane, bool hasA, bool hasB) {
-    D2DLaneIn in;
-    in.aA = -1; in.aB = -1;
-    in.tA = make_float2(1.f, 0.f);                    // benign: unit distance
-    in.pB = make_float4(1.f, 0.f, 0.f, 0.f);
-    const uint32_t row0 = e * (uint32_t)P.N, pos0 = e * (uint32_t)P.V;
+// Issue the copies of one env's inputs into a stage: lane l fetches its CUE action and transmitter (device 1 + l) and
+// its DUE action and (tx, rx) pair (devices 1 + C + 2l, + 1).  Lanes without a link copy nothing: their slots keep the
+// benign values written at kernel start.  iA = e N + lane, qA = e V + 1 + lane.
+template <bool SPEC>
+__device__ __forceinline__ void d2d_prefetch_inputs(const D2DParams &P, const D2DShape<SPEC> &S, uint32_t slot, uint32_t iA, uint32_t qA,
+                                                    uint32_t lane, bool pa, bool pb) {
     const float2 *pos = reinterpret_cast<const float2 *>(P.pos);
-    if (hasA) { in.aA = __ldg(P.actions + (row0 + lane)); in.tA = __ldg(pos + (pos0 + 1u + lane)); }
-    if (hasB) {
-        in.aB = __ldg(P.actions + (row0 + (uint32_t)P.C + lane));
-        const uint32_t q = pos0 + 1u + (uint32_t)P.C + 2u * lane;
-        if (P.align4) {
-            in.pB = __ldg(reinterpret_cast<const float4 *>(pos + q));
-        } else {
-            const float2 t = __ldg(pos + q), r = __ldg(pos + (q + 1u));
-            in.pB = make_float4(t.x, t.y, r.x, r.y);
-        }
+    d2d_cp4_if(pa, slot, P.actions + iA);
+    d2d_cp4_if(pb, slot + 4u, P.actions + (iA + S.C()));
+    d2d_cp8_if(pa, slot + 8u, pos + qA);
+    const float2 *pq = pos + (qA + S.C() + lane);
+    if (SPEC || P.align4) {
+        d2d_cp16_if(pb, slot + 16u, pq);
+    } else {
+        d2d_cp8_if(pb, slot + 16u, pq);
+        d2d_cp8_if(pb, slot + 24u, pq + 1);
     }
-    in.ns = (lane == 0 && P.step_count) ? (int)P.step_count[e] : 0;
-    return in;
+    d2d_cp_commit();
 }
 
-#ifdef D2D_TIMELINE   // debug builds only: SM-clock timestamps of one warp's phases (profiles/timeline.py)
-__device__ unsigned long long d2d_dbg[16];
-#define D2D_TICK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) d2d_dbg[i] = clock64(); } while (0)
-#else
-#define D2D_TICK(i) do { } while (0)
-#endif
+// log2(1 + r), branch-free form of d2d_log2_1p (both sides are a handful of instructions; a divergent branch costs more)
+__device__ __forceinline__ float d2d_log2_1p_sel(float r) {
+    const float s = r * d2d_rcp(2.0f + r);
+    const float s2 = s * s;
+    const float poly = fmaf(s2, fmaf(s2, fmaf(s2, (1.0f / 7.0f), 0.2f), (1.0f / 3.0f)), 1.0f);
+    const float small = (2.8853900817779268f * s) * poly;
+    const float big = d2d_lg2(1.0f + r);
+    return r < 0.25f ? small : big;
+}
+// Per-link epilogue in fp32 (Appendix A), dead lanes zeroed.  Same arithmetic as d2d_link_epilogue (d2d_common.cuh).
+__device__ __forceinline__ D2DLinkOut d2d_link_epilogue_warp(bool live, int p, float p_lin, float lg_d2, float g, float I,
+                                                              const float4 &cA, const float2 &sb, float snr_slope) {
+    D2DLinkOut o;
+    const float snr_lin = p_lin * cA.y * g;
+    const float r = snr_lin * d2d_rcp(fmaf(I, cA.z, 1.0f));
+    const float snr = fmaf(-snr_slope, lg_d2, (float)p + cA.w);
+    const float sinr = 3.0102999566398120f * d2d_lg2(r);
+    const bool ok = live && sinr > sb.x;
+    const float rate = d2d_log2_1p_sel(r);
+    o.snr_dB = live ? snr : 0.0f;
+    o.sinr_dB = live ? sinr : 0.0f;
+    o.rate = ok ? rate : 0.0f;
+    o.cap = ok ? sb.y * rate : 0.0f;
+    return o;
+}
 
-// FULL: the caller passed exactly the core outputs (obs, capacity, reward, done) - the VecD2DEnv default - so no
-// pointer is tested on the hot path; otherwise every output is optional and checked.
-template <bool PLE2, bool EXACT, int WPB, bool FULL>
+// ---- rare paths -----------------------------------------------------------------------------------------------------------
+
+// Some RB holds more links than a bin has record slots: all-pairs pass over the 64 link slots by shuffle (no table).
+// A term counts when the RB keys match and it is not the victim itself.  Returns (I_A, I_B, dmin2_A, dmin2_B).
+template <bool PLE2, bool EXACT>
+__device__ __forceinline__ float4 d2d_all_pairs_warp(uint32_t lane, uint32_t keyA, uint32_t keyB, float4 recA, float4 pB, float wB, float uB,
+                                                      float nhp) {
+    float IA = 0.f, IB = 0.f, dminA = 3.0e38f, dminB = 3.0e38f;
+#pragma unroll 1
+    for (uint32_t k = 0; k < 32u; ++k) {
+        const uint32_t kA = __shfl_sync(0xffffffffu, keyA, k), kB = __shfl_sync(0xffffffffu, keyB, k);
+        const float4 ra = make_float4(__shfl_sync(0xffffffffu, recA.x, k), __shfl_sync(0xffffffffu, recA.y, k),
+                                      __shfl_sync(0xffffffffu, recA.z, k), __shfl_sync(0xffffffffu, recA.w, k));
+        const float4 rb = make_float4(__shfl_sync(0xffffffffu, pB.x, k), __shfl_sync(0xffffffffu, pB.y, k),
+                                      __shfl_sync(0xffffffffu, wB, k), __shfl_sync(0xffffffffu, uB, k));
+        if (EXACT) {
+            IA += d2d_term_rx<PLE2, true>(ra, kA == keyA && k != lane, 0.f, 0.f, nhp, dminA);
+            IA += d2d_term_rx<PLE2, true>(rb, kB == keyA, 0.f, 0.f, nhp, dminA);
+        } else {
+            IA += (kA == keyA && k != lane) ? ra.w : 0.f;
+            IA += (kB == keyA) ? rb.w : 0.f;
+        }
+        IB += d2d_term_rx<PLE2, EXACT>(ra, kA == keyB, pB.z, pB.w, nhp, dminB);
+        IB += d2d_term_rx<PLE2, EXACT>(rb, kB == keyB && k != lane, pB.z, pB.w, nhp, dminB);
+    }
+    return make_float4(IA, IB, dminA, dminB);
+}
+
+// 1 / x in fp64 from the fp32 reciprocal and three Newton steps (x normal, > 0): no division subroutine
+__device__ __forceinline__ double d2d_rcp_f64(double x) {
+    double y = (double)d2d_rcp((float)x);
+    y = fma(y, fma(-x, y, 1.0), y);
+    y = fma(y, fma(-x, y, 1.0), y);
+    y = fma(y, fma(-x, y, 1.0), y);
+    return y;
+}
+template <bool PLE2>
+__device__ __forceinline__ double d2d_gain_f64_fast(double d2, double ple) {
+    if (PLE2) return d2d_rcp_f64(d2);
+    return d2d_exp_f64(-0.5 * ple * d2d_ln_f64(d2));
+}
+// ln(x) in fp64.  |x - 1| < 1/16 - every value the fp32 trigger sends here unless an fp64 position shadow is bound -
+// needs no exponent split and five series terms; everything else takes the general d2d_ln_f64.
+// 10 log10(x) in fp64 for the rescue.  |x - 1| < 1/16 needs no exponent split and five series terms.  Outside that range
+// the dB value is > 0.26 dB from zero: without a position shadow the fp32 value `keep` is already accurate there (this
+// link was flagged for its other dB value); with a shadow (EXACT) the positions changed, so take the general logarithm.
+template <bool EXACT>
+__device__ __forceinline__ double d2d_db_rescue(double x, float keep) {
+    if (fabs(x - 1.0) < 0.0625) {
+        const double s = (x - 1.0) * d2d_rcp_f64(x + 1.0), s2 = s * s;      // |s| < 1/31: s^11 / 11 < 1e-17
+        double q = 1.0 / 9.0;
+        q = fma(q, s2, 1.0 / 7.0); q = fma(q, s2, 1.0 / 5.0); q = fma(q, s2, 1.0 / 3.0); q = fma(q, s2, 1.0);
+        return 8.6858896380650365530 * s * q;                               // 2 * 10 / ln 10
+    }
+    return EXACT ? 4.3429448190325182765 * d2d_ln_f64(x) : (double)keep;
+}
+__device__ __forceinline__ double d2d_shfl_f64(double v, int src) {
+    return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src), __shfl_sync(0xffffffffu, __double2loint(v), src));
+}
+__device__ __forceinline__ double d2d_shfl_xor_f64(double v, int m) {
+    return __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(v), m), __shfl_xor_sync(0xffffffffu, __double2loint(v), m));
+}
+
+// fp64 recomputation of the links flagged by needA / needB (see d2d_common.cuh for why and when).  Per flagged link the
+// whole warp cooperates: every lane evaluates its own two links' interference terms at the victim's receiver in fp64
+// (positions are exact in fp64: they ARE the fp32 state, or the bound fp64 shadow), a butterfly sums them, and the
+// victim's own lane - which holds its link's inputs in registers - recomputes and overwrites that link's outputs.
+// Without a position shadow only the ill-conditioned dB values are rewritten (rate and capacity are well conditioned in
+// fp32 there) unless the recomputed SINR flips the sensitivity gate.  Returns the number of links recomputed.
+template <bool PLE2, bool EXACT, bool SPEC>
+__device__ __forceinline__ int d2d_rescue_warp(const D2DParams &P, const D2DShape<SPEC> &S, uint32_t e, uint32_t lane, uint32_t jA,
+                                               uint32_t keyA, uint32_t keyB, bool needA, bool needB, uint32_t pA, uint32_t pB_,
+                                               float2 tA, float4 pB, const D2DLinkOut &oA, const D2DLinkOut &oB, float sensA,
+                                               float sensB) {
+    const uint32_t C = S.C(), V = S.V();
+    // this lane's two transmitters and the DUE receiver, in fp64
+    double2 txA = make_double2((double)tA.x, (double)tA.y), txB = make_double2((double)pB.x, (double)pB.y);
+    double2 rxB = make_double2((double)pB.z, (double)pB.w);
+    if (EXACT) {
+        const double2 *pe64 = reinterpret_cast<const double2 *>(P.pos64) + (int64_t)e * V;
+        if (lane < C) txA = pe64[1u + lane];
+        if (lane < S.D()) { txB = pe64[1u + C + 2u * lane]; rxB = pe64[2u + C + 2u * lane]; }
+    }
+    // radiated weights w = 10^(p/10) 10^((eo - K)/10) in fp64 (tables are tiny and cache-resident)
+    const double wA = P.pwr_lin_d[pA & (D2D_MAX_PWR_LEVELS - 1)] * P.linkD[min(lane, S.N() - 1u)].t_lin;
+    const double wB = P.pwr_lin_d[pB_ & (D2D_MAX_PWR_LEVELS - 1)] * P.linkD[min(C + lane, S.N() - 1u)].t_lin;
+    int done = 0;
+#pragma unroll 1
+    for (int s = 0; s < 2; ++s) {
+        uint32_t todo = __ballot_sync(0xffffffffu, s ? needB : needA);
+        while (todo) {
+            const int L = (int)d2d_pop_bit(todo);
+            const uint32_t key = __shfl_sync(0xffffffffu, s ? keyB : keyA, L);
+            const double rxx = s ? d2d_shfl_f64(rxB.x, L) : 0.0, rxy = s ? d2d_shfl_f64(rxB.y, L) : 0.0;   // MBS at the origin
+            double I = 0.0;
+            if (keyA == key && !(s == 0 && (int)lane == L)) {
+                const double ex = txA.x - rxx, ey = txA.y - rxy;
+                I += wA * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, P.ple_d);
+            }
+            if (keyB == key && !(s == 1 && (int)lane == L)) {
+                const double ex = txB.x - rxx, ey = txB.y - rxy;
+                I += wB * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, P.ple_d);
+            }
+#pragma unroll
+            for (int sh = 16; sh > 0; sh >>= 1) I += d2d_shfl_xor_f64(I, sh);
+            if ((int)lane == L) {
+                const uint32_t j = s ? C + lane : lane;
+                const D2DLinkD Lj = P.linkD[j];
+                const double2 tx = s ? txB : txA;
+                const double dx = tx.x - rxx, dy = tx.y - rxy;
+                const double Sg = P.pwr_lin_d[(s ? pB_ : pA) & (D2D_MAX_PWR_LEVELS - 1)] * Lj.a_lin * d2d_gain_f64_fast<PLE2>(dx * dx + dy * dy, P.ple_d);
+                const double r = Sg * d2d_rcp_f64(fma(I, Lj.inv_noise, 1.0));          // a_lin already carries 1 / noise
+                const D2DLinkOut &o = s ? oB : oA;
+                const double sinr = d2d_db_rescue<EXACT>(r, o.sinr_dB), snr = d2d_db_rescue<EXACT>(Sg, o.snr_dB);
+                const float sens = s ? sensB : sensA;
+                const bool ok = sinr > (double)sens;
+                const uint32_t row = (s ? jA + C : jA);
+                if (P.obs) *reinterpret_cast<float2 *>(P.obs + (uint64_t)row * 6u + 4u) = make_float2((float)sinr, (float)snr);
+                if (EXACT || ok != (o.sinr_dB > sens)) {
+                    const double rate = ok ? 1.4426950408889634074 * d2d_ln_f64(1.0 + r) : 0.0;
+                    if (P.cap) P.cap[row] = (float)(Lj.bw_MHz * rate);
+                    if (P.rate) P.rate[row] = (float)rate;
+                }
+                ++done;
+            }
+        }
+    }
+    return (int)__reduce_add_sync(0xffffffffu, (unsigned)done);
+}
+
+// FULL: the caller passed exactly the core outputs (obs, capacity, reward, done) and a step counter is bound - the
+// VecD2DEnv default - so no pointer is tested on the hot path; otherwise every output is optional and checked.
+template <bool PLE2, bool EXACT, int WPB, bool FULL, bool SPEC>
 __global__ void __launch_bounds__(WPB * 32, D2D_WARP_MIN_BLOCKS(WPB))
-d2d_step_warp_kernel(const D2DParams P) {
-    __shared__ __align__(16) unsigned char smem[WPB * D2D_W_BYTES];
+d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
+    extern __shared__ __align__(16) unsigned char d2d_warp_smem[];
+    const D2DShape<SPEC> S(P);
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t N = (uint32_t)P.N, C = (uint32_t)P.C, V = (uint32_t)P.V, D = N - C;
-    D2D_TICK(0);
+    const uint32_t C = S.C(), N = S.N(), V = S.V(), R = S.R();
     d2d_pdl_launch_dependents();
-    uint32_t wb = (uint32_t)__cvta_generic_to_shared(smem) + warp * D2D_W_BYTES;
-    asm volatile("mov.u32 %0, %0;" : "+r"(wb));      // opaque: keep the base in a register instead of re-deriving it
-    const uint32_t sorted = wb + D2D_W_SORTED, offs = wb + D2D_W_OFF;
+    uint32_t blk = (uint32_t)__cvta_generic_to_shared(d2d_warp_smem);
+    asm volatile("mov.u32 %0, %0;" : "+r"(blk));      // opaque: keep the base in a register instead of re-deriving it
+    const uint32_t wb = blk + D2D_BLK_BYTES + warp * d2d_warp_smem_per_warp((int)R);
+    const uint32_t bins = wb + 2u * D2D_STAGE_BYTES;
+    const bool hasA = lane < C, hasB = lane < S.D();
 
-    // both parity buffers of the RB counters (64 bins + the dummy bin each) start at zero; each iteration re-zeroes the
-    // one it is not using.  offset[64] = 64 forever: the dummy bin's records land in the slack behind the sorted array.
-    for (uint32_t i = lane; i < 2u * D2D_W_CNT_STRIDE / 16u; i += 32u) d2d_sts128(wb + D2D_W_CNT + (i << 4), 0.f, 0.f, 0.f, 0.f);
-    if (lane == 0) d2d_sts32(offs + 64u * 4u, 64u);
-    // 10^(p/10) table -> shared, so the lookup that depends on the action is an LDS, not a second global round trip;
-    // the load is issued here and parked in shared memory only after the first env's inputs are in flight
-    const float4 lut = __ldg(reinterpret_cast<const float4 *>(P.pwr_lin) + lane);
+    // ---- prologue (constant tables only: nothing a previous kernel in the stream may have written) ------------------
+    // block tables: 10^(p/10) for integer dBm, and the per-link constants by lane slot (zeros where there is no link)
+    for (uint32_t i = threadIdx.x; i < D2D_MAX_PWR_LEVELS / 4u; i += WPB * 32u) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(P.pwr_lin) + i);
+        d2d_sts128(blk + D2D_BLK_PWR + (i << 4), v.x, v.y, v.z, v.w);
+    }
+    for (uint32_t i = threadIdx.x; i < 64u; i += WPB * 32u) {
+        const uint32_t l = i & 31u, j = i < 32u ? l : C + l;
+        const bool has = i < 32u ? l < C : l < S.D();
+        const float4 a = has ? __ldg(reinterpret_cast<const float4 *>(P.linkA) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float2 b = has ? __ldg(reinterpret_cast<const float2 *>(P.linkB + j)) : make_float2(0.f, 0.f);
+        d2d_sts128(blk + D2D_BLK_LINKA + (i << 4), a.x, a.y, a.z, a.w);
+        d2d_sts64f(blk + D2D_BLK_LINKS + (i << 3), b.x, b.y);
+    }
+    // this warp's bins: every counter (and the dummy bin's) starts at zero; each env re-zeroes them after use.
+    for (uint32_t r = lane; r <= R; r += 32u) d2d_sts64_if(true, bins + r * D2D_BIN_STRIDE + D2D_BIN_CNT, 0u, 0u);
+    // both stages: benign inputs for lanes that own no link (action -1 = absent, unit distances)
+    d2d_sts128(wb + (lane << 5), __int_as_float(-1), __int_as_float(-1), 1.f, 0.f);
+    d2d_sts128(wb + (lane << 5) + 16u, 1.f, 0.f, 0.f, 0.f);
+    d2d_sts128(wb + D2D_STAGE_BYTES + (lane << 5), __int_as_float(-1), __int_as_float(-1), 1.f, 0.f);
+    d2d_sts128(wb + D2D_STAGE_BYTES + (lane << 5) + 16u, 1.f, 0.f, 0.f, 0.f);
+    __syncthreads();
 
-    const bool hasA = lane < C, hasB = lane < D;
-    const uint32_t jA = lane, jB = C + lane;                  // canonical link indices (envs/d2d_env.py:55-60)
-    // per-lane link constants stay in registers for every env this warp visits
-    const float4 cA = hasA ? __ldg(reinterpret_cast<const float4 *>(P.linkA) + jA) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 cB = hasB ? __ldg(reinterpret_cast<const float4 *>(P.linkA) + jB) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float2 sA = hasA ? __ldg(reinterpret_cast<const float2 *>(P.linkB + jA)) : make_float2(0.f, 0.f);   // (sens, bw)
-    const float2 sB = hasB ? __ldg(reinterpret_cast<const float2 *>(P.linkB + jB)) : make_float2(0.f, 0.f);
-    const uint32_t dump = 64u + (lane & 7u);                  // where a dead lane parks its record
+    const uint32_t lkA = blk + D2D_BLK_LINKA + (lane << 4), lkS = blk + D2D_BLK_LINKS + (lane << 3);
+    const uint32_t zero0 = bins + lane * D2D_BIN_STRIDE + D2D_BIN_CNT;       // this lane's share of the counter re-zeroing
+    // a valid action is 0 <= a < R n_pwr (envs/d2d_env.py:36-40); anything else marks the agent absent this step.
+    // The sentinel action R n_pwr decodes to (rb = R, p = 0): the dummy bin.
+    const uint32_t limA = R * S.npc(), limB = R * S.npd();
 
     // per-warp partial statistics (fp32 over the few envs one warp visits; flushed once as fp64 atomics)
     float st_reward = 0.f, st_cap = 0.f, st_reward2 = 0.f;
-    int st_pen = 0, st_resc = 0;
+    uint32_t st_pen = 0, st_resc = 0;
 
     // 32-bit indexing: the host launches at most 2^31 / max(6N, 2V) envs per call (d2d_step chunks larger batches)
-    uint32_t iter = 1;
     const uint32_t num_envs = (uint32_t)P.num_envs, stride = gridDim.x * WPB;
     uint32_t e = blockIdx.x * WPB + warp;
-    D2DLaneIn nxt;
-    D2D_TICK(1);
+    uint32_t iA = e * N + lane, qA = e * V + 1u + lane;           // slot-A link / device index of env e
+    uint32_t slot = wb + (lane << 5);                             // this lane's slot in the stage holding env e
+    uint32_t sd = D2D_STAGE_BYTES;                                // distance to the other stage
+    uint32_t iters = 0;
     d2d_pdl_wait();
-    D2D_TICK(2);
-    if (e < num_envs) nxt = d2d_load_inputs(P, e, lane, hasA, hasB);
-    d2d_sts128(wb + D2D_W_PWR + (lane << 4), lut.x, lut.y, lut.z, lut.w);
-    __syncwarp();
-    for (; e < num_envs; e += stride, ++iter) {
-        const uint32_t row0 = e * N;
-        const uint32_t cnt = wb + D2D_W_CNT + (iter & 1u) * D2D_W_CNT_STRIDE;
-        const uint32_t cnt_other = wb + D2D_W_CNT + ((iter & 1u) ^ 1u) * D2D_W_CNT_STRIDE;
-
-        // ---- one coalesced pass over the env's inputs, software-pipelined: the NEXT env's loads are in flight
-        // while this env computes, so a warp hides its own HBM latency ----------------------------------------
-        const int aA = nxt.aA, aB = nxt.aB;
-        const float2 tA = nxt.tA;
-        const float4 pB = nxt.pB;
-        const int ns_prev = nxt.ns;
-        if (e + stride < num_envs) nxt = d2d_load_inputs(P, e + stride, lane, hasA, hasB);
-        const bool liveA = aA >= 0, liveB = aB >= 0;       // has a link AND the agent acts this step
-        if (liveA || liveB) D2D_TICK(3);     // inputs arrived
+    d2d_prefetch_inputs<SPEC>(P, S, slot, iA, qA, lane, hasA && e < num_envs, hasB && e < num_envs);
+    for (; e < num_envs; e += stride, ++iters) {
+        // ---- this env's inputs (copied while the previous env computed); start the next env's copies --------------
+        int ns_prev = 0;
+        if (lane == 0 && (FULL || P.step_count)) ns_prev = (int)P.step_count[e];
+        d2d_cp_wait_all();
+        const float4 in0 = d2d_lds128_at<0>(slot), pB = d2d_lds128_at<16>(slot);
+        const uint32_t aA = __float_as_uint(in0.x), aB = __float_as_uint(in0.y);
+        const float2 tA = make_float2(in0.z, in0.w);
+        const uint32_t jA = iA, jB = iA + C;                        // this env's link indices (outputs)
+        {
+            const bool more = e + stride < num_envs;
+            d2d_prefetch_inputs<SPEC>(P, S, slot + sd, iA + stride * N, qA + stride * V, lane, hasA && more, hasB && more);
+        }
+        const bool liveA = hasA && aA < limA, liveB = hasB && aB < limB;   // has a link AND the agent acts this step
 
         // ---- envs/d2d_env.py:93-101: rb = a // n_pwr, p = a % n_pwr; rank inside the RB (actions.py:27-31) -------------
-        const uint32_t rbA = __umulhi((uint32_t)aA, P.magic_cue) + ((uint32_t)aA & P.npw1_cue);
-        const uint32_t rbB = __umulhi((uint32_t)aB, P.magic_due) + ((uint32_t)aB & P.npw1_due);
-        const uint32_t pA = (uint32_t)aA - rbA * (uint32_t)P.n_pwr_cue, pB_ = (uint32_t)aB - rbB * (uint32_t)P.n_pwr_due;
-        const uint32_t binA = liveA ? (rbA & 63u) : 64u, binB = liveB ? (rbB & 63u) : 64u;    // dead lanes: dummy bin (never counted)
-        const uint32_t rankA = d2d_atoms_add_if(liveA, cnt + (binA << 2), 1u) & 0xffffu;
-        const uint32_t rankB = d2d_atoms_add_if(liveB, cnt + (binB << 2), 0x10001u) & 0xffffu;   // high half counts the SIDELINKs
-        if (lane < D2D_W_CNT_STRIDE / 16u) d2d_sts128(cnt_other + (lane << 4), 0.f, 0.f, 0.f, 0.f);   // next iteration's counters
-        const float lutA = d2d_lds32(wb + D2D_W_PWR + ((pA & (D2D_MAX_PWR_LEVELS - 1)) << 2));   // 10^(p/10)
-        const float lutB = d2d_lds32(wb + D2D_W_PWR + ((pB_ & (D2D_MAX_PWR_LEVELS - 1)) << 2));
-        const float plA = liveA ? lutA : 0.0f, plB = liveB ? lutB : 0.0f;
+        const uint32_t asA = liveA ? aA : limA, asB = liveB ? aB : limB;      // dead lanes -> (rb = R, p = 0)
+        const uint32_t rbA = S.rb_cue(asA), rbB = S.rb_due(asB);
+        const uint32_t pA = asA - rbA * S.npc(), pB_ = asB - rbB * S.npd();
+        const uint32_t binA = bins + rbA * D2D_BIN_STRIDE, binB = bins + rbB * D2D_BIN_STRIDE;
+        const uint32_t rankA = d2d_atoms_inc_at<D2D_BIN_CNT>(binA);
+        const uint32_t rankB = d2d_atoms_inc_at<D2D_BIN_CNT>(binB);
+        d2d_sts32_if(liveB, binB + D2D_BIN_CNT + 4u, 1u);                       // a SIDELINK is on this RB (reward_fn.py:31-37)
+        const float plA = d2d_lds32(blk + D2D_BLK_PWR + (pA << 2));            // 10^(p/10)
+        const float plB = d2d_lds32(blk + D2D_BLK_PWR + (pB_ << 2));
+        const float4 cA = d2d_lds128_at<0>(lkA), cB = d2d_lds128_at<512>(lkA);  // (tx_lin0, a_lin, inv_noise, snr0_dB)
 
         // ---- peer records: position, radiated weight w, and its value u at the MBS -------------------------------
         const float d2A = fmaf(tA.x, tA.x, tA.y * tA.y);                       // CUE -> MBS distance^2 (own link)
@@ -288,142 +513,107 @@ d2d_step_warp_kernel(const D2DParams P) {
         const float wA = plA * cA.x;
         const float d2Bm = fmaf(pB.x, pB.x, pB.y * pB.y);                      // DUE tx -> MBS distance^2 (as interferer)
         const float wB = plB * cB.x;
-        const float uB = wB * d2d_gain<PLE2>(d2Bm, P.neg_half_ple);
+        const float uA = wA * gA, uB = wB * d2d_gain<PLE2>(d2Bm, P.neg_half_ple);
         const float dxB = pB.x - pB.z, dyB = pB.y - pB.w;                      // DUE own link
         const float d2B = fmaf(dxB, dxB, dyB * dyB);
         const float lgB = d2d_lg2(d2B);
         const float gB = PLE2 ? d2d_rcp(d2B) : d2d_ex2(P.neg_half_ple * lgB);
-        D2D_TICK(4);
-
-        // ---- exclusive scan of the 64 RB counts: lane l scans bins l and l + 32, packed 16 + 16 bits ---------------
+        d2d_sts128_if(liveA && rankA < D2D_BIN_CAP, binA + (rankA << 4), tA.x, tA.y, wA, uA);
+        d2d_sts128_if(liveB && rankB < D2D_BIN_CAP, binB + (rankB << 4), pB.x, pB.y, wB, uB);
         __syncwarp();
-        const uint32_t c0 = d2d_lds32u(cnt + (lane << 2)) & 0xffffu, c1 = d2d_lds32u(cnt + ((lane + 32u) << 2)) & 0xffffu;
-        uint32_t incl = c0 | (c1 << 16);
-#pragma unroll
-        for (int s = 1; s < 32; s <<= 1) {
-            const uint32_t up = __shfl_up_sync(0xffffffffu, incl, s);
-            incl += lane >= (uint32_t)s ? up : 0u;
-        }
-        const uint32_t total0 = __shfl_sync(0xffffffffu, incl, 31) & 0xffffu;   // links in bins 0..31
-        d2d_sts32(offs + (lane << 2), (incl & 0xffffu) - c0);
-        d2d_sts32(offs + ((lane + 32u) << 2), total0 + (incl >> 16) - c1);
-        __syncwarp();
-        // ---- scatter the records into RB order (dead lanes: offset[64] = 64 -> the slack records) ----------------------
-        const uint32_t begA = d2d_lds32u(offs + (binA << 2)), begB = d2d_lds32u(offs + (binB << 2));
-        const uint32_t ctA = d2d_lds32u(cnt + (binA << 2)), ctB = d2d_lds32u(cnt + (binB << 2));
-        const uint32_t nA = ctA & 0xffffu, nB = ctB & 0xffffu;
-        // validA/B: bit t set <=> entry t of the victim's RB range exists and is not the victim (dead lane: 0)
-        const uint32_t validA = liveA ? d2d_valid_mask(nA, rankA) : 0u, validB = liveB ? d2d_valid_mask(nB, rankB) : 0u;
-        d2d_sts128(sorted + ((liveA ? begA + rankA : dump) << 4), tA.x, tA.y, wA, wA * gA);
-        d2d_sts128(sorted + ((liveB ? begB + rankB : dump) << 4), pB.x, pB.y, wB, uB);
-        __syncwarp();
-        D2D_TICK(5);
 
         // ---- simulator.py:95-101: interference at each victim's receiver (a dead lane has an empty range) ----------
-        float dminA = 3.0e38f, dminB = 3.0e38f;
-        const float IA = EXACT ? d2d_walk_rx<PLE2, true>(sorted, begA, validA, nA, rankA, 0.f, 0.f, P.neg_half_ple, dminA)
-                               : d2d_walk_mbs(sorted, begA, validA, nA, rankA);
-        const float IB = d2d_walk_rx<PLE2, EXACT>(sorted, begB, validB, nB, rankB, pB.z, pB.w, P.neg_half_ple, dminB);
-        if (IA + IB >= 0.f) D2D_TICK(6);
+        const uint2 ctA = d2d_lds64u_at<D2D_BIN_CNT>(binA);                    // (links on the victim's RB, SIDELINK flag)
+        const uint32_t nA = ctA.x, nB = d2d_lds32u_at<D2D_BIN_CNT>(binB);
+        float IA, IB, dminA = 3.0e38f, dminB = 3.0e38f;
+        if (__any_sync(0xffffffffu, (liveA && nA > D2D_BIN_CAP) || (liveB && nB > D2D_BIN_CAP))) {
+            // rare: some RB holds more links than a bin has record slots
+            const uint32_t keyA = liveA ? rbA : (D2D_INACTIVE_KEY | lane), keyB = liveB ? rbB : (D2D_INACTIVE_KEY | 32u | lane);
+            const float4 r = d2d_all_pairs_warp<PLE2, EXACT>(lane, keyA, keyB, make_float4(tA.x, tA.y, wA, uA), pB, wB, uB, P.neg_half_ple);
+            IA = r.x; IB = r.y; dminA = r.z; dminB = r.w;
+        } else {
+            // bit t of valid <=> record t of the victim's bin exists and is not the victim (dead lane: 0)
+            const uint32_t validA = liveA ? (((1u << nA) - 1u) ^ (1u << rankA)) : 0u;
+            const uint32_t validB = liveB ? (((1u << nB) - 1u) ^ (1u << rankB)) : 0u;
+            IA = EXACT ? d2d_walk_rx<PLE2, true>(binA, validA, 0.f, 0.f, P.neg_half_ple, dminA) : d2d_walk_mbs(binA, validA);
+            IB = d2d_walk_rx<PLE2, EXACT>(binB, validB, pB.z, pB.w, P.neg_half_ple, dminB);
+        }
 
         // ---- per-link epilogue (simulator.py:93,106-107,110-127,144-154); dead lanes are zeroed ------------------------
-        D2DLinkOut oA = d2d_link_epilogue<PLE2>((int)pA, plA, lgA, gA, IA, cA, sA, P);
-        D2DLinkOut oB = d2d_link_epilogue<PLE2>((int)pB_, plB, lgB, gB, IB, cB, sB, P);
-        oA.sinr_dB = liveA ? oA.sinr_dB : 0.f; oA.snr_dB = liveA ? oA.snr_dB : 0.f; oA.cap = liveA ? oA.cap : 0.f;
-        oB.sinr_dB = liveB ? oB.sinr_dB : 0.f; oB.snr_dB = liveB ? oB.snr_dB : 0.f; oB.cap = liveB ? oB.cap : 0.f;
+        const float2 sA = d2d_lds64(lkS), sB = d2d_lds64(lkS + 256u);          // (sensitivity, RB bandwidth in MHz)
+        const float slope = PLE2 ? 3.0102999566398120f : P.snr_slope;
+        const D2DLinkOut oA = d2d_link_epilogue_warp(liveA, (int)pA, plA, lgA, gA, IA, cA, sA, slope);
+        const D2DLinkOut oB = d2d_link_epilogue_warp(liveB, (int)pB_, plB, lgB, gB, IB, cB, sB, slope);
         const bool needA = liveA && d2d_needs_rescue<EXACT>(oA, fminf(dminA, d2A), P);
         const bool needB = liveB && d2d_needs_rescue<EXACT>(oB, fminf(dminB, d2B), P);
-        if (oA.cap + oB.cap >= 0.f) D2D_TICK(7);
 
         // ---- envs/reward_fn.py:27-44 -----------------------------------------------------------------------------------
-        const bool bad = __any_sync(0xffffffffu, liveA && (ctA >> 16) != 0u && oA.cap <= P.min_cap);
-        const int n_act = __popc(__ballot_sync(0xffffffffu, liveA)) + __popc(__ballot_sync(0xffffffffu, liveB));
+        const bool bad = __any_sync(0xffffffffu, liveA && ctA.y != 0u && oA.cap <= P.min_cap);
+        const uint32_t n_act = d2d_redux_add((liveA ? 1u : 0u) + (liveB ? 1u : 0u));
         float cap_sum = oA.cap + oB.cap;
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) cap_sum += __shfl_xor_sync(0xffffffffu, cap_sum, s);
-        const float reward = bad ? -1.0f : __fdividef(cap_sum, (float)n_act);
-        if (reward > -2.f) D2D_TICK(8);
+        const float reward = bad ? -1.0f : cap_sum * d2d_rcp((float)n_act);
+        // every lane has read its counters (its capacity fed the reduction above): clear them for the next env
+        __syncwarp();
+        d2d_sts64_if(lane < R, zero0, 0u, 0u);
+        if (!SPEC && R > 32u) d2d_sts64_if(lane + 32u < R, zero0 + 32u * D2D_BIN_STRIDE, 0u, 0u);
 
         // ---- outputs: compact observation table (envs/obs_fn.py:55-61), capacity, optional info.  Rows of absent
         // agents carry their positions and zeros (the reference has no row for them). ---------------------------------
-        const uint32_t iA = row0 + jA, iB = row0 + jB;
         if (FULL || P.obs) {
-            float2 *oa = reinterpret_cast<float2 *>(P.obs) + iA * 3u, *ob = reinterpret_cast<float2 *>(P.obs) + iB * 3u;
+            char *oa = reinterpret_cast<char *>(P.obs) + (uint64_t)jA * 24u, *ob = reinterpret_cast<char *>(P.obs) + (uint64_t)jB * 24u;
             d2d_stg64_if(hasA, oa, tA.x, tA.y);
-            d2d_stg64_if(hasA, oa + 1, 0.f, 0.f);
-            d2d_stg64_if(hasA, oa + 2, oA.sinr_dB, oA.snr_dB);
+            d2d_stg64_if(hasA, oa + 8, 0.f, 0.f);
+            d2d_stg64_if(hasA, oa + 16, oA.sinr_dB, oA.snr_dB);
             d2d_stg64_if(hasB, ob, pB.x, pB.y);
-            d2d_stg64_if(hasB, ob + 1, pB.z, pB.w);
-            d2d_stg64_if(hasB, ob + 2, oB.sinr_dB, oB.snr_dB);
+            d2d_stg64_if(hasB, ob + 8, pB.z, pB.w);
+            d2d_stg64_if(hasB, ob + 16, oB.sinr_dB, oB.snr_dB);
         }
         if (FULL || P.cap) {
-            d2d_stg32_if(hasA, P.cap + iA, oA.cap);
-            d2d_stg32_if(hasB, P.cap + iB, oB.cap);
+            d2d_stg32_if(hasA, P.cap + jA, oA.cap);
+            d2d_stg32_if(hasB, P.cap + jB, oB.cap);
         }
         if (!FULL) {
             if (P.rate) {
-                d2d_stg32_if(hasA, P.rate + iA, liveA ? oA.rate : 0.f);
-                d2d_stg32_if(hasB, P.rate + iB, liveB ? oB.rate : 0.f);
+                d2d_stg32_if(hasA, P.rate + jA, oA.rate);
+                d2d_stg32_if(hasB, P.rate + jB, oB.rate);
             }
             if (P.rb_out) {
-                d2d_stg16_if(hasA, P.rb_out + iA, liveA ? (int)rbA : 0);
-                d2d_stg16_if(hasB, P.rb_out + iB, liveB ? (int)rbB : 0);
+                d2d_stg16_if(hasA, P.rb_out + jA, liveA ? (int)rbA : 0);
+                d2d_stg16_if(hasB, P.rb_out + jB, liveB ? (int)rbB : 0);
             }
             if (P.pwr_out) {
-                d2d_stg16_if(hasA, P.pwr_out + iA, liveA ? (int)pA : 0);
-                d2d_stg16_if(hasB, P.pwr_out + iB, liveB ? (int)pB_ : 0);
+                d2d_stg16_if(hasA, P.pwr_out + jA, liveA ? (int)pA : 0);
+                d2d_stg16_if(hasB, P.pwr_out + jB, liveB ? (int)pB_ : 0);
             }
         }
         if (lane == 0) {
             // envs/d2d_env.py:65,68: num_steps += 1; done = num_steps >= EPISODE_LENGTH
             const int ns = min(ns_prev + 1, 255);
-            if (P.step_count) P.step_count[e] = (uint8_t)ns;
+            if (FULL || P.step_count) P.step_count[e] = (uint8_t)ns;
             if (FULL || P.reward) P.reward[e] = reward;
             if (FULL || P.done) P.done[e] = ns >= P.episode_length ? 1 : 0;
         }
-        D2D_TICK(9);
         st_reward += reward; st_cap += cap_sum; st_reward2 = fmaf(reward, reward, st_reward2);
-        st_pen += bad ? 1 : 0;
+        st_pen += bad ? 1u : 0u;
 
-        // ---- rare: fp64 recomputation of flagged links (d2d_common.cuh).  Runs after the stores, when none of the
-        // per-link state above is live; the whole warp cooperates on each flagged link. -------------------------------
+        // ---- rare: fp64 recomputation of flagged links, after the env's outputs are stored ----------------------------------
         if (D2D_RESCUE_ENABLED && __any_sync(0xffffffffu, needA || needB)) {
-            const int32_t *act = P.actions + row0;
-            const float2 *pe = reinterpret_cast<const float2 *>(P.pos) + e * V;
-            const double2 *pe64 = P.pos64 ? reinterpret_cast<const double2 *>(P.pos64) + (int64_t)e * V : nullptr;
             const uint32_t keyA = liveA ? rbA : (D2D_INACTIVE_KEY | lane), keyB = liveB ? rbB : (D2D_INACTIVE_KEY | 32u | lane);
-#pragma unroll 1
-            for (int s = 0; s < 2; ++s) {
-                uint32_t todo = __ballot_sync(0xffffffffu, s ? needB : needA);
-                while (todo) {
-                    const int L = (int)d2d_pop_bit(todo);
-                    const int j = s ? (int)C + L : L;
-                    const uint32_t key = __shfl_sync(0xffffffffu, s ? keyB : keyA, L);
-                    const double2 rx = d2d_pos_f64(pe, pe64, d2d_rx_dev(j, (int)C));
-                    double I = 0.0;
-                    if (keyA == key && (int)jA != j) I += d2d_ix_term_f64<PLE2>((int)jA, rx, pe, pe64, act, P);
-                    if (keyB == key && (int)jB != j) I += d2d_ix_term_f64<PLE2>((int)jB, rx, pe, pe64, act, P);
-#pragma unroll
-                    for (int sh = 16; sh > 0; sh >>= 1) I += __shfl_xor_sync(0xffffffffu, I, sh);
-                    if (lane == 0) {
-                        const D2DLinkOut o = d2d_link_f64<PLE2>(j, d2d_pos_f64(pe, pe64, d2d_tx_dev(j, (int)C)), rx, I,
-                                                                P.linkB[j].sens_dBm, act, P);
-                        if (P.obs) *reinterpret_cast<float2 *>(P.obs + (int64_t)(row0 + j) * 6 + 4) = make_float2(o.sinr_dB, o.snr_dB);
-                        if (P.cap) P.cap[row0 + j] = o.cap;
-                        if (P.rate) P.rate[row0 + j] = o.rate;
-                        ++st_resc;
-                    }
-                }
-            }
+            st_resc += (uint32_t)d2d_rescue_warp<PLE2, EXACT, SPEC>(P, S, e, lane, jA, keyA, keyB, needA, needB, pA, pB_, tA, pB, oA, oB,
+                                                                    sA.x, sB.x);
         }
+        iA += stride * N; qA += stride * V;
+        slot += sd; sd = 0u - sd;
+        __syncwarp();     // every lane is done with this env's records and counters before the next env's are written
     }
+    d2d_cp_wait_all();
 
-    D2D_TICK(10);
     if (P.stats && lane < 6) {
         // one fire-and-forget fp64 reduction per statistic and warp, spread over the replicas
-        const int resc0 = __shfl_sync(0x3fu, st_resc, 0);
         const double v = lane == 0 ? (double)st_reward : lane == 1 ? (double)st_cap : lane == 2 ? (double)st_reward2
-                       : lane == 3 ? (double)(iter - 1) : lane == 4 ? (double)st_pen : (double)resc0;
+                       : lane == 3 ? (double)iters : lane == 4 ? (double)st_pen : (double)st_resc;
         const unsigned w_global = blockIdx.x * WPB + warp;
         if (v != 0.0) atomicAdd(P.stats + (w_global % D2D_STATS_REPLICAS) * 8 + lane, v);
     }
