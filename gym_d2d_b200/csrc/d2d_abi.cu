@@ -44,6 +44,9 @@ struct d2d_handle {
     bool ple2 = true;
     bool use_warp = true;
     bool spec = false;         // warp kernel instantiated for the reference's default EnvConfig shape
+    bool uniform = false;      // every CUE link has the same constants, and every DUE link (no per-device overrides)
+    D2DLinkA u_cue{}, u_due{};
+    float us_cue[2] = {0, 0}, us_due[2] = {0, 0};
     int wpb = 4;               // warps per block of the warp kernel
     int64_t chunk_override = 0;  // D2D_B200_CHUNK: force small launch chunks (tests of the > 2^31-element path)
     bool pdl = true;           // programmatic dependent launch (D2D_B200_PDL=0 disables)
@@ -104,6 +107,10 @@ D2DParams make_params(const d2d_handle *h, const d2d_step_io_t *io) {
         P.rescue_c = (float)(2.0 * 1e4 * 4.3429448190325 * h->ple * std::sqrt(2.0) * ulp);
         P.rescue_dmin2 = (float)std::pow(2.0 * 1e4 * 0.5 * h->ple * std::sqrt(2.0) * ulp, 2.0);   // capacity: d(ln r) = ple * dd/d
     }
+    P.u_cue = make_float4(h->u_cue.tx_lin0, h->u_cue.a_lin, h->u_cue.inv_noise, h->u_cue.snr0_dB);
+    P.u_due = make_float4(h->u_due.tx_lin0, h->u_due.a_lin, h->u_due.inv_noise, h->u_due.snr0_dB);
+    P.us_cue = make_float2(h->us_cue[0], h->us_cue[1]);
+    P.us_due = make_float2(h->us_due[0], h->us_due[1]);
     P.ple_d = h->ple;
     P.linkA = h->dA; P.linkB = h->dB; P.linkD = h->dD; P.pwr_lin = h->dPwr; P.pwr_lin_d = h->dPwrD;
     P.pos = h->pos; P.pos64 = h->pos64; P.step_count = h->step_count; P.stats = h->stats;
@@ -251,6 +258,18 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
         Dv[j].inv_noise = std::pow(10.0, -L.rx_noise_dBm / 10.0);
         Dv[j].bw_MHz = 1e-6 * (L.tx_rb_bandwidth_kHz * 1000.0);
     }
+    // one set of constants per link type (no per-device overrides)?  Then the default-shape kernel reads them from
+    // the constant bank instead of a shared-memory table
+    h->uniform = true;
+    for (int j = 0; j < h->N; ++j) {
+        const int j0 = j < cfg->num_cues ? 0 : cfg->num_cues;
+        if (std::memcmp(&A[j], &A[j0], sizeof(D2DLinkA)) != 0 || B[j].sens_dBm != B[j0].sens_dBm || B[j].bw_MHz != B[j0].bw_MHz)
+            h->uniform = false;
+    }
+    if (cfg->num_cues > 0) { h->u_cue = A[0]; h->us_cue[0] = B[0].sens_dBm; h->us_cue[1] = B[0].bw_MHz; }
+    if (cfg->num_due_pairs > 0) {
+        h->u_due = A[cfg->num_cues]; h->us_due[0] = B[cfg->num_cues].sens_dBm; h->us_due[1] = B[cfg->num_cues].bw_MHz;
+    }
     float pwr[D2D_MAX_PWR_LEVELS];
     double pwr_d[D2D_MAX_PWR_LEVELS];
     for (int p = 0; p < D2D_MAX_PWR_LEVELS; ++p) {   // conversion.py:4-13
@@ -286,7 +305,7 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
         // launch shape by batch size (d2d_step_warp.cuh): about one wave of envs -> 4-warp blocks, many waves -> 8-warp blocks
         h->wpb = cfg->num_envs >= 32768 ? 8 : 4;
         if (const char *w = std::getenv("D2D_B200_WPB")) h->wpb = std::atoi(w) == 8 ? 8 : 4;
-        h->spec = h->ple2 && cfg->num_rbs == 25 && cfg->num_cues == 25 && cfg->num_due_pairs == 25 && cfg->n_pwr_cue == 24 &&
+        h->spec = h->ple2 && h->uniform && cfg->num_rbs == 25 && cfg->num_cues == 25 && cfg->num_due_pairs == 25 && cfg->n_pwr_cue == 24 &&
                   cfg->n_pwr_due == 21;
         if (const char *sp = std::getenv("D2D_B200_SPEC")) h->spec = h->spec && std::atoi(sp) != 0;   // tests: force the generic shape
         const size_t smem = d2d_warp_smem_bytes(cfg->num_rbs, h->wpb);

@@ -63,6 +63,8 @@ struct D2DParams {
     float rescue_band_dB;        // |SINR_dB| or |SNR_dB| below rescue_band_dB + rescue_c / d_min is recomputed in fp64
     float rescue_c;              // 0 unless an fp64 position shadow is bound (covers the fp32 rounding of positions)
     float rescue_dmin2;          // with a shadow: links with a distance^2 below this are always recomputed
+    float4 u_cue, u_due;         // default-shape kernel: the one D2DLinkA of every CUE link / every DUE link (constant bank)
+    float2 us_cue, us_due;       // ... and the (sens_dBm, bw_MHz) of D2DLinkB
     double ple_d;                // fp64 copy for the rescue path
     const D2DLinkA *linkA;       // [N]
     const D2DLinkB *linkB;       // [N]

@@ -7,10 +7,11 @@
 //
 // Mapping: lane l owns CUE link l (slot A) and DUE pair l (slot B).
 //
-// INPUTS.  Each lane copies its own four items of the NEXT env (CUE action, DUE action, CUE transmitter, DUE
-// transmitter + receiver) with cp.async (LDGSTS) into a private 32-byte slot of the warp's staging buffer while the
-// current env computes, and reads the current env's slot back with two LDS.128.  The prefetch therefore holds no
-// registers and no scoreboard, and the global reads stay coalesced (consecutive lanes copy consecutive elements).
+// The kernel is bound by the SM's load/store data pipe (shared-memory + global wavefronts, profiles/README.md), so
+// the design minimises wavefronts per env, not instructions: inputs go straight to registers (LDG, software-pipelined
+// one env ahead; staging them through shared memory with cp.async was measured and costs 60 more wavefronts per env),
+// peer-record loads are predicated on the record being a real co-channel peer, dead lanes count into private dummy
+// words, and the default EnvConfig reads its link constants from the constant bank.
 //
 // GROUPING.  The masked per-RB interference sum (Actions.get_actions_by_rb, actions.py:27-31 + simulator.py:95-101)
 // is a segmented reduction over links grouped by RB.  The grouping is a per-warp BINNED table in shared memory:
@@ -41,10 +42,10 @@
 //   WPB = 4: finest block granularity - best when the batch is about one wave (E = 4096)
 //   WPB = 8: best sustained throughput for batches of many waves
 #ifndef D2D_MINB8
-#define D2D_MINB8 4
+#define D2D_MINB8 3
 #endif
 #ifndef D2D_MINB4
-#define D2D_MINB4 8
+#define D2D_MINB4 7
 #endif
 #define D2D_WARP_MIN_BLOCKS(WPB) ((WPB) == 4 ? D2D_MINB4 : D2D_MINB8)
 #ifndef D2D_STATS_REPLICAS
@@ -59,17 +60,18 @@
 
 // ---- shared memory layout ---------------------------------------------------------------------------------------------
 // block:    pwr_lin[128] f32 | linkA[64] float4 (slot A: lane, slot B: 32 + lane) | linkS[64] float2 (sens, bw)
-// per warp: stage[2][32 lanes][32 B] = (aA, aB, tA.x, tA.y, pB.x, pB.y, pB.z, pB.w) | (R + 1) bins of D2D_BIN_STRIDE bytes
+// per warp: R bins of D2D_BIN_STRIDE bytes | 64 dummy counter pairs (8 B each: slot A lanes, then slot B lanes) | a zero record
 // A bin = D2D_BIN_CAP records of 16 B + a 16 B tail: {link count, 1 if a SIDELINK is on this RB}; the odd stride also
-// spreads consecutive bins over the banks.  Bin R is the dummy bin of dead lanes (no link, or agent absent this step).
+// spreads consecutive bins over the banks.  Dead lanes (no link, or agent absent this step) run the same straight-line
+// code: they count into their own dummy word (no same-address serialisation) and store / load no record.
 #define D2D_BLK_PWR 0u
 #define D2D_BLK_LINKA (D2D_MAX_PWR_LEVELS * 4u)
 #define D2D_BLK_LINKS (D2D_BLK_LINKA + 64u * 16u)
 #define D2D_BLK_BYTES (D2D_BLK_LINKS + 64u * 8u)
-#define D2D_STAGE_BYTES 1024u
+#define D2D_DUMMY_BYTES 528u
 #define D2D_BIN_STRIDE (D2D_BIN_CAP * 16u + 16u)
 #define D2D_BIN_CNT (D2D_BIN_CAP * 16u)
-__host__ __device__ inline uint32_t d2d_warp_smem_per_warp(int R) { return 2u * D2D_STAGE_BYTES + (uint32_t)(R + 1) * D2D_BIN_STRIDE; }
+__host__ __device__ inline uint32_t d2d_warp_smem_per_warp(int R) { return (uint32_t)R * D2D_BIN_STRIDE + D2D_DUMMY_BYTES; }
 __host__ __device__ inline uint32_t d2d_warp_smem_bytes(int R, int wpb) { return D2D_BLK_BYTES + (uint32_t)wpb * d2d_warp_smem_per_warp(R); }
 
 // Link / device / RB counts of the batch: immediates for the default EnvConfig, launch parameters otherwise.
@@ -197,40 +199,41 @@ __device__ __forceinline__ float d2d_term_rx(const float4 r, bool valid, float r
     return valid ? r.z * d2d_gain<PLE2>(d2, nhp) : 0.0f;
 }
 // A victim's co-channel records are the first records of its bin; `valid` has bit t set when record t exists and is
-// not the victim itself (at most D2D_BIN_CAP bits on the fast path).
+// not the victim itself (at most D2D_BIN_CAP bits on the fast path).  A lane whose record t is not a peer reads the
+// warp's all-zero record instead (`zrec`: one address for every such lane, so a broadcast, not a bank conflict): the
+// load / store data pipe, not instruction issue, bounds this kernel, and 60 % of the (lane, t) pairs are not peers.
 template <bool PLE2, bool EXACT, int T>
-__device__ __forceinline__ void d2d_inline_rx(float &I, uint32_t bin, uint32_t valid, float rxx, float rxy, float nhp, float &dmin2) {
+__device__ __forceinline__ void d2d_inline_rx(float &I, uint32_t bin, uint32_t zrec, uint32_t valid, float rxx, float rxy, float nhp,
+                                              float &dmin2) {
     if constexpr (T < D2D_WALK_INLINE) {
-        I += d2d_term_rx<PLE2, EXACT>(d2d_lds128_at<16 * T>(bin), (valid >> T) & 1u, rxx, rxy, nhp, dmin2);
-        d2d_inline_rx<PLE2, EXACT, T + 1>(I, bin, valid, rxx, rxy, nhp, dmin2);
+        const bool v = valid & (1u << T);
+        I += d2d_term_rx<PLE2, EXACT>(d2d_lds128(v ? bin + 16u * T : zrec), v, rxx, rxy, nhp, dmin2);
+        d2d_inline_rx<PLE2, EXACT, T + 1>(I, bin, zrec, valid, rxx, rxy, nhp, dmin2);
     }
 }
 template <bool PLE2, bool EXACT>
-__device__ __forceinline__ float d2d_walk_rx(uint32_t bin, uint32_t valid, float rxx, float rxy, float nhp, float &dmin2) {
+__device__ __forceinline__ float d2d_walk_rx(uint32_t bin, uint32_t zrec, uint32_t valid, float rxx, float rxy, float nhp, float &dmin2) {
     float I = 0.0f;
-    d2d_inline_rx<PLE2, EXACT, 0>(I, bin, valid, rxx, rxy, nhp, dmin2);
+    d2d_inline_rx<PLE2, EXACT, 0>(I, bin, zrec, valid, rxx, rxy, nhp, dmin2);
     valid >>= D2D_WALK_INLINE;
     for (uint32_t a = bin + 16u * D2D_WALK_INLINE; valid; valid >>= 1, a += 16u)   // > D2D_WALK_INLINE links on one RB
-        I += d2d_term_rx<PLE2, EXACT>(d2d_lds128(a), valid & 1u, rxx, rxy, nhp, dmin2);
+        if (valid & 1u) I += d2d_term_rx<PLE2, EXACT>(d2d_lds128(a), true, rxx, rxy, nhp, dmin2);
     return I;
 }
-// Interference at the MBS: the records carry u_k = w_k g(|tx_k|) in .w
+// Interference at the MBS: the records carry u_k = w_k g(|tx_k|) in .w (the zero record adds nothing)
 template <int T>
-__device__ __forceinline__ void d2d_inline_mbs(float &I, uint32_t bin, uint32_t valid) {
+__device__ __forceinline__ void d2d_inline_mbs(float &I, uint32_t bin, uint32_t zrec, uint32_t valid) {
     if constexpr (T < D2D_WALK_INLINE) {
-        const float u = d2d_lds32_at<16 * T + 12>(bin);
-        I += ((valid >> T) & 1u) ? u : 0.0f;
-        d2d_inline_mbs<T + 1>(I, bin, valid);
+        I += d2d_lds32((valid & (1u << T)) ? bin + (16u * T + 12u) : zrec);
+        d2d_inline_mbs<T + 1>(I, bin, zrec, valid);
     }
 }
-__device__ __forceinline__ float d2d_walk_mbs(uint32_t bin, uint32_t valid) {
+__device__ __forceinline__ float d2d_walk_mbs(uint32_t bin, uint32_t zrec, uint32_t valid) {
     float I = 0.0f;
-    d2d_inline_mbs<0>(I, bin, valid);
+    d2d_inline_mbs<0>(I, bin, zrec, valid);
     valid >>= D2D_WALK_INLINE;
-    for (uint32_t a = bin + 16u * D2D_WALK_INLINE + 12u; valid; valid >>= 1, a += 16u) {
-        const float u = d2d_lds32(a);
-        I += (valid & 1u) ? u : 0.0f;
-    }
+    for (uint32_t a = bin + 16u * D2D_WALK_INLINE + 12u; valid; valid >>= 1, a += 16u)
+        if (valid & 1u) I += d2d_lds32(a);
     return I;
 }
 
@@ -245,24 +248,34 @@ __device__ __forceinline__ void d2d_stg16_if(bool p, void *ptr, int x) {
     asm volatile("{ .reg .pred q; setp.ne.u32 q, %0, 0; @q st.global.u16 [%1], %2; }" ::"r"((uint32_t)p), "l"(ptr), "h"((short)x) : "memory");
 }
 
-// Issue the copies of one env's inputs into a stage: lane l fetches its CUE action and transmitter (device 1 + l) and
-// its DUE action and (tx, rx) pair (devices 1 + C + 2l, + 1).  Lanes without a link copy nothing: their slots keep the
-// benign values written at kernel start.  iA = e N + lane, qA = e V + 1 + lane.
+// One env's inputs as a lane sees them: its CUE action + transmitter (device 1 + l), its DUE action + (tx, rx) pair
+// (devices 1 + C + 2l, + 1).  Lanes without a link keep benign values (action -1 = absent, unit distances).
+struct D2DLaneIn {
+    uint32_t aA, aB;
+    float2 tA;        // CUE transmitter (its receiver is the MBS at the origin)
+    float4 pB;        // DUE (tx_x, tx_y, rx_x, rx_y)
+};
+// iA = e N + lane, qA = e V + 1 + lane
 template <bool SPEC>
-__device__ __forceinline__ void d2d_prefetch_inputs(const D2DParams &P, const D2DShape<SPEC> &S, uint32_t slot, uint32_t iA, uint32_t qA,
-                                                    uint32_t lane, bool pa, bool pb) {
+__device__ __forceinline__ D2DLaneIn d2d_load_inputs(const D2DParams &P, const D2DShape<SPEC> &S, uint32_t iA, uint32_t qA, uint32_t lane,
+                                                      bool hasA, bool hasB) {
+    D2DLaneIn in;
+    in.aA = 0xffffffffu; in.aB = 0xffffffffu;
+    in.tA = make_float2(1.f, 0.f);
+    in.pB = make_float4(1.f, 0.f, 0.f, 0.f);
     const float2 *pos = reinterpret_cast<const float2 *>(P.pos);
-    d2d_cp4_if(pa, slot, P.actions + iA);
-    d2d_cp4_if(pb, slot + 4u, P.actions + (iA + S.C()));
-    d2d_cp8_if(pa, slot + 8u, pos + qA);
-    const float2 *pq = pos + (qA + S.C() + lane);
-    if (SPEC || P.align4) {
-        d2d_cp16_if(pb, slot + 16u, pq);
-    } else {
-        d2d_cp8_if(pb, slot + 16u, pq);
-        d2d_cp8_if(pb, slot + 24u, pq + 1);
+    if (hasA) { in.aA = (uint32_t)__ldg(P.actions + iA); in.tA = __ldg(pos + qA); }
+    if (hasB) {
+        in.aB = (uint32_t)__ldg(P.actions + (iA + S.C()));
+        const float2 *pq = pos + (qA + S.C() + lane);
+        if (SPEC || P.align4) {
+            in.pB = __ldg(reinterpret_cast<const float4 *>(pq));
+        } else {
+            const float2 t = __ldg(pq), r = __ldg(pq + 1);
+            in.pB = make_float4(t.x, t.y, r.x, r.y);
+        }
     }
-    d2d_cp_commit();
+    return in;
 }
 
 // log2(1 + r), branch-free form of d2d_log2_1p (both sides are a handful of instructions; a divergent branch costs more)
@@ -334,18 +347,12 @@ __device__ __forceinline__ double d2d_gain_f64_fast(double d2, double ple) {
 }
 // ln(x) in fp64.  |x - 1| < 1/16 - every value the fp32 trigger sends here unless an fp64 position shadow is bound -
 // needs no exponent split and five series terms; everything else takes the general d2d_ln_f64.
-// 10 log10(x) in fp64 for the rescue.  |x - 1| < 1/16 needs no exponent split and five series terms.  Outside that range
-// the dB value is > 0.26 dB from zero: without a position shadow the fp32 value `keep` is already accurate there (this
-// link was flagged for its other dB value); with a shadow (EXACT) the positions changed, so take the general logarithm.
-template <bool EXACT>
-__device__ __forceinline__ double d2d_db_rescue(double x, float keep) {
-    if (fabs(x - 1.0) < 0.0625) {
-        const double s = (x - 1.0) * d2d_rcp_f64(x + 1.0), s2 = s * s;      // |s| < 1/31: s^11 / 11 < 1e-17
-        double q = 1.0 / 9.0;
-        q = fma(q, s2, 1.0 / 7.0); q = fma(q, s2, 1.0 / 5.0); q = fma(q, s2, 1.0 / 3.0); q = fma(q, s2, 1.0);
-        return 8.6858896380650365530 * s * q;                               // 2 * 10 / ln 10
-    }
-    return EXACT ? 4.3429448190325182765 * d2d_ln_f64(x) : (double)keep;
+// 10 log10(x) in fp64 for |x - 1| < 1/16: no exponent split, five series terms
+__device__ __forceinline__ double d2d_db_near1(double x) {
+    const double s = (x - 1.0) * d2d_rcp_f64(x + 1.0), s2 = s * s;      // |s| < 1/31: s^11 / 11 < 1e-17
+    double q = 1.0 / 9.0;
+    q = fma(q, s2, 1.0 / 7.0); q = fma(q, s2, 1.0 / 5.0); q = fma(q, s2, 1.0 / 3.0); q = fma(q, s2, 1.0);
+    return 8.6858896380650365530 * s * q;                               // 2 * 10 / ln 10
 }
 __device__ __forceinline__ double d2d_shfl_f64(double v, int src) {
     return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src), __shfl_sync(0xffffffffu, __double2loint(v), src));
@@ -357,26 +364,16 @@ __device__ __forceinline__ double d2d_shfl_xor_f64(double v, int m) {
 // fp64 recomputation of the links flagged by needA / needB (see d2d_common.cuh for why and when).  Per flagged link the
 // whole warp cooperates: every lane evaluates its own two links' interference terms at the victim's receiver in fp64
 // (positions are exact in fp64: they ARE the fp32 state, or the bound fp64 shadow), a butterfly sums them, and the
-// victim's own lane - which holds its link's inputs in registers - recomputes and overwrites that link's outputs.
-// Without a position shadow only the ill-conditioned dB values are rewritten (rate and capacity are well conditioned in
-// fp32 there) unless the recomputed SINR flips the sensitivity gate.  Returns the number of links recomputed.
+// victim's own lane recomputes and overwrites that link's outputs.  Everything is re-read from global memory (this path
+// runs for ~7 % of the envs and must not hold registers of the hot loop).
+// Without a position shadow a dB value is rewritten only when its linear ratio is within 1/16 of one - the only place the
+// fp32 value is ill-conditioned; rate and capacity are well conditioned there and are rewritten only if the sensitivity
+// gate (simulator.py:123,149) could sit inside that band.  With a shadow every output of the link is rewritten.
+// Returns the number of links recomputed.
 template <bool PLE2, bool EXACT, bool SPEC>
 __device__ __forceinline__ int d2d_rescue_warp(const D2DParams &P, const D2DShape<SPEC> &S, uint32_t e, uint32_t lane, uint32_t jA,
-                                               uint32_t keyA, uint32_t keyB, bool needA, bool needB, uint32_t pA, uint32_t pB_,
-                                               float2 tA, float4 pB, const D2DLinkOut &oA, const D2DLinkOut &oB, float sensA,
-                                               float sensB) {
+                                               uint32_t keyA, uint32_t keyB, bool needA, bool needB, uint32_t pA, uint32_t pB_) {
     const uint32_t C = S.C(), V = S.V();
-    // this lane's two transmitters and the DUE receiver, in fp64
-    double2 txA = make_double2((double)tA.x, (double)tA.y), txB = make_double2((double)pB.x, (double)pB.y);
-    double2 rxB = make_double2((double)pB.z, (double)pB.w);
-    if (EXACT) {
-        const double2 *pe64 = reinterpret_cast<const double2 *>(P.pos64) + (int64_t)e * V;
-        if (lane < C) txA = pe64[1u + lane];
-        if (lane < S.D()) { txB = pe64[1u + C + 2u * lane]; rxB = pe64[2u + C + 2u * lane]; }
-    }
-    // radiated weights w = 10^(p/10) 10^((eo - K)/10) in fp64 (tables are tiny and cache-resident)
-    const double wA = P.pwr_lin_d[pA & (D2D_MAX_PWR_LEVELS - 1)] * P.linkD[min(lane, S.N() - 1u)].t_lin;
-    const double wB = P.pwr_lin_d[pB_ & (D2D_MAX_PWR_LEVELS - 1)] * P.linkD[min(C + lane, S.N() - 1u)].t_lin;
     int done = 0;
 #pragma unroll 1
     for (int s = 0; s < 2; ++s) {
@@ -384,33 +381,53 @@ __device__ __forceinline__ int d2d_rescue_warp(const D2DParams &P, const D2DShap
         while (todo) {
             const int L = (int)d2d_pop_bit(todo);
             const uint32_t key = __shfl_sync(0xffffffffu, s ? keyB : keyA, L);
+            // this lane's two transmitters and the DUE receiver, in fp64
+            double2 txA = make_double2(1.0, 0.0), txB = make_double2(1.0, 0.0), rxB = make_double2(0.0, 0.0);
+            if (EXACT) {
+                const double2 *pe64 = reinterpret_cast<const double2 *>(P.pos64) + (int64_t)e * V;
+                if (lane < C) txA = pe64[1u + lane];
+                if (lane < S.D()) { txB = pe64[1u + C + 2u * lane]; rxB = pe64[2u + C + 2u * lane]; }
+            } else {
+                const float2 *pe = reinterpret_cast<const float2 *>(P.pos) + e * V;
+                if (lane < C) { const float2 t = pe[1u + lane]; txA = make_double2((double)t.x, (double)t.y); }
+                if (lane < S.D()) {
+                    const float2 t = pe[1u + C + 2u * lane], r = pe[2u + C + 2u * lane];
+                    txB = make_double2((double)t.x, (double)t.y); rxB = make_double2((double)r.x, (double)r.y);
+                }
+            }
             const double rxx = s ? d2d_shfl_f64(rxB.x, L) : 0.0, rxy = s ? d2d_shfl_f64(rxB.y, L) : 0.0;   // MBS at the origin
             double I = 0.0;
             if (keyA == key && !(s == 0 && (int)lane == L)) {
+                // radiated weight w = 10^(p/10) 10^((eo - K)/10) in fp64 (tables are tiny and cache-resident)
+                const double w = P.pwr_lin_d[pA & (D2D_MAX_PWR_LEVELS - 1)] * P.linkD[lane].t_lin;
                 const double ex = txA.x - rxx, ey = txA.y - rxy;
-                I += wA * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, P.ple_d);
+                I += w * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, P.ple_d);
             }
             if (keyB == key && !(s == 1 && (int)lane == L)) {
+                const double w = P.pwr_lin_d[pB_ & (D2D_MAX_PWR_LEVELS - 1)] * P.linkD[C + lane].t_lin;
                 const double ex = txB.x - rxx, ey = txB.y - rxy;
-                I += wB * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, P.ple_d);
+                I += w * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, P.ple_d);
             }
 #pragma unroll
             for (int sh = 16; sh > 0; sh >>= 1) I += d2d_shfl_xor_f64(I, sh);
             if ((int)lane == L) {
-                const uint32_t j = s ? C + lane : lane;
+                const uint32_t j = s ? C + lane : lane, row = s ? jA + C : jA;
                 const D2DLinkD Lj = P.linkD[j];
                 const double2 tx = s ? txB : txA;
                 const double dx = tx.x - rxx, dy = tx.y - rxy;
                 const double Sg = P.pwr_lin_d[(s ? pB_ : pA) & (D2D_MAX_PWR_LEVELS - 1)] * Lj.a_lin * d2d_gain_f64_fast<PLE2>(dx * dx + dy * dy, P.ple_d);
                 const double r = Sg * d2d_rcp_f64(fma(I, Lj.inv_noise, 1.0));          // a_lin already carries 1 / noise
-                const D2DLinkOut &o = s ? oB : oA;
-                const double sinr = d2d_db_rescue<EXACT>(r, o.sinr_dB), snr = d2d_db_rescue<EXACT>(Sg, o.snr_dB);
-                const float sens = s ? sensB : sensA;
-                const bool ok = sinr > (double)sens;
-                const uint32_t row = (s ? jA + C : jA);
-                if (P.obs) *reinterpret_cast<float2 *>(P.obs + (uint64_t)row * 6u + 4u) = make_float2((float)sinr, (float)snr);
-                if (EXACT || ok != (o.sinr_dB > sens)) {
-                    const double rate = ok ? 1.4426950408889634074 * d2d_ln_f64(1.0 + r) : 0.0;
+                const bool r1 = fabs(r - 1.0) < 0.0625, s1 = fabs(Sg - 1.0) < 0.0625;
+                const float sens = P.linkB[j].sens_dBm;
+                double sinr = 0.0;
+                if (EXACT || r1) {
+                    sinr = r1 ? d2d_db_near1(r) : 4.3429448190325182765 * d2d_ln_f64(r);
+                    if (P.obs) P.obs[(uint64_t)row * 6u + 4u] = (float)sinr;
+                }
+                if ((EXACT || s1) && P.obs)
+                    P.obs[(uint64_t)row * 6u + 5u] = (float)(s1 ? d2d_db_near1(Sg) : 4.3429448190325182765 * d2d_ln_f64(Sg));
+                if (EXACT || (r1 && fabsf(sens) < 0.5f)) {
+                    const double rate = sinr > (double)sens ? 1.4426950408889634074 * d2d_ln_f64(1.0 + r) : 0.0;
                     if (P.cap) P.cap[row] = (float)(Lj.bw_MHz * rate);
                     if (P.rate) P.rate[row] = (float)rate;
                 }
@@ -433,8 +450,9 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
     d2d_pdl_launch_dependents();
     uint32_t blk = (uint32_t)__cvta_generic_to_shared(d2d_warp_smem);
     asm volatile("mov.u32 %0, %0;" : "+r"(blk));      // opaque: keep the base in a register instead of re-deriving it
-    const uint32_t wb = blk + D2D_BLK_BYTES + warp * d2d_warp_smem_per_warp((int)R);
-    const uint32_t bins = wb + 2u * D2D_STAGE_BYTES;
+    const uint32_t bins = blk + D2D_BLK_BYTES + warp * d2d_warp_smem_per_warp((int)R);
+    const uint32_t dumA = bins + R * D2D_BIN_STRIDE + (lane << 3);        // this lane's dummy (count, flag) pairs: A, B at + 256
+    const uint32_t zrec = bins + R * D2D_BIN_STRIDE + 512u;               // the warp's all-zero peer record
     const bool hasA = lane < C, hasB = lane < S.D();
 
     // ---- prologue (constant tables only: nothing a previous kernel in the stream may have written) ------------------
@@ -443,7 +461,7 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         const float4 v = __ldg(reinterpret_cast<const float4 *>(P.pwr_lin) + i);
         d2d_sts128(blk + D2D_BLK_PWR + (i << 4), v.x, v.y, v.z, v.w);
     }
-    for (uint32_t i = threadIdx.x; i < 64u; i += WPB * 32u) {
+    for (uint32_t i = threadIdx.x; !SPEC && i < 64u; i += WPB * 32u) {
         const uint32_t l = i & 31u, j = i < 32u ? l : C + l;
         const bool has = i < 32u ? l < C : l < S.D();
         const float4 a = has ? __ldg(reinterpret_cast<const float4 *>(P.linkA) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -451,47 +469,50 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         d2d_sts128(blk + D2D_BLK_LINKA + (i << 4), a.x, a.y, a.z, a.w);
         d2d_sts64f(blk + D2D_BLK_LINKS + (i << 3), b.x, b.y);
     }
-    // this warp's bins: every counter (and the dummy bin's) starts at zero; each env re-zeroes them after use.
-    for (uint32_t r = lane; r <= R; r += 32u) d2d_sts64_if(true, bins + r * D2D_BIN_STRIDE + D2D_BIN_CNT, 0u, 0u);
-    // both stages: benign inputs for lanes that own no link (action -1 = absent, unit distances)
-    d2d_sts128(wb + (lane << 5), __int_as_float(-1), __int_as_float(-1), 1.f, 0.f);
-    d2d_sts128(wb + (lane << 5) + 16u, 1.f, 0.f, 0.f, 0.f);
-    d2d_sts128(wb + D2D_STAGE_BYTES + (lane << 5), __int_as_float(-1), __int_as_float(-1), 1.f, 0.f);
-    d2d_sts128(wb + D2D_STAGE_BYTES + (lane << 5) + 16u, 1.f, 0.f, 0.f, 0.f);
+    // this warp's bins: every counter starts at zero; each env re-zeroes them after use (the dummy words just run on)
+    for (uint32_t r = lane; r < R; r += 32u) d2d_sts64_if(true, bins + r * D2D_BIN_STRIDE + D2D_BIN_CNT, 0u, 0u);
+    d2d_sts64_if(true, dumA, 0u, 0u);
+    d2d_sts64_if(true, dumA + 256u, 0u, 0u);
+    if (lane < 4u) d2d_sts32_if(true, zrec + (lane << 2), 0u);
     __syncthreads();
 
     const uint32_t lkA = blk + D2D_BLK_LINKA + (lane << 4), lkS = blk + D2D_BLK_LINKS + (lane << 3);
     const uint32_t zero0 = bins + lane * D2D_BIN_STRIDE + D2D_BIN_CNT;       // this lane's share of the counter re-zeroing
     // a valid action is 0 <= a < R n_pwr (envs/d2d_env.py:36-40); anything else marks the agent absent this step.
-    // The sentinel action R n_pwr decodes to (rb = R, p = 0): the dummy bin.
+    // The sentinel action R n_pwr decodes to (rb = R, p = 0): a valid table index and an address inside the warp's slice.
     const uint32_t limA = R * S.npc(), limB = R * S.npd();
 
     // per-warp partial statistics (fp32 over the few envs one warp visits; flushed once as fp64 atomics)
     float st_reward = 0.f, st_cap = 0.f, st_reward2 = 0.f;
     uint32_t st_pen = 0, st_resc = 0;
 
-    // 32-bit indexing: the host launches at most 2^31 / max(6N, 2V) envs per call (d2d_step chunks larger batches)
-    const uint32_t num_envs = (uint32_t)P.num_envs, stride = gridDim.x * WPB;
-    uint32_t e = blockIdx.x * WPB + warp;
-    uint32_t iA = e * N + lane, qA = e * V + 1u + lane;           // slot-A link / device index of env e
-    uint32_t slot = wb + (lane << 5);                             // this lane's slot in the stage holding env e
-    uint32_t sd = D2D_STAGE_BYTES;                                // distance to the other stage
-    uint32_t iters = 0;
+    // 32-bit indexing: the host launches at most 2^31 / max(6N, 2V) envs per call (d2d_step chunks larger batches).
+    // Each warp steps a CONTIGUOUS range of envs, so the per-env scalars (step counter, reward, done) are kept in
+    // registers - env i of a group of 32 lives in lane i - and read / written once per group as full sectors.  (One byte
+    // per env read and written by 32 different warps per sector cost a quarter of the kernel's time in L2 read-modify-
+    // write stalls: profiles/README.md.)
+    const uint32_t num_envs = (uint32_t)P.num_envs, num_warps = gridDim.x * WPB;
+    const uint32_t per_warp = (num_envs + num_warps - 1u) / num_warps;
+    const uint32_t e0 = min((blockIdx.x * WPB + warp) * per_warp, num_envs), e_end = min(e0 + per_warp, num_envs);
+    uint32_t e = e0;
+    uint32_t iA = e * N + lane;                                    // slot-A link index of the env being computed
+    uint32_t qN = e * V + 1u + lane;                               // slot-A device index of the env being prefetched
+    uint32_t g = 0;                                                // position of env e in its group of 32
+    int ns_keep = 0;                                               // lane i: step counter of the group's env i
+    float rew_keep = 0.f;                                          // lane i: reward of the group's env i
+    D2DLaneIn nxt;
     d2d_pdl_wait();
-    d2d_prefetch_inputs<SPEC>(P, S, slot, iA, qA, lane, hasA && e < num_envs, hasB && e < num_envs);
-    for (; e < num_envs; e += stride, ++iters) {
-        // ---- this env's inputs (copied while the previous env computed); start the next env's copies --------------
-        int ns_prev = 0;
-        if (lane == 0 && (FULL || P.step_count)) ns_prev = (int)P.step_count[e];
-        d2d_cp_wait_all();
-        const float4 in0 = d2d_lds128_at<0>(slot), pB = d2d_lds128_at<16>(slot);
-        const uint32_t aA = __float_as_uint(in0.x), aB = __float_as_uint(in0.y);
-        const float2 tA = make_float2(in0.z, in0.w);
+    if (e < e_end) nxt = d2d_load_inputs<SPEC>(P, S, iA, qN, lane, hasA, hasB);
+    for (; e < e_end; ++e, iA += N) {
+        // ---- one coalesced pass over the env's inputs, software-pipelined: the NEXT env's loads are in flight while
+        // this env computes, so a warp hides its own HBM latency --------------------------------------------------------
+        const uint32_t aA = nxt.aA, aB = nxt.aB;
+        const float2 tA = nxt.tA;
+        const float4 pB = nxt.pB;
         const uint32_t jA = iA, jB = iA + C;                        // this env's link indices (outputs)
-        {
-            const bool more = e + stride < num_envs;
-            d2d_prefetch_inputs<SPEC>(P, S, slot + sd, iA + stride * N, qA + stride * V, lane, hasA && more, hasB && more);
-        }
+        qN += V;
+        if (e + 1u < e_end) nxt = d2d_load_inputs<SPEC>(P, S, iA + N, qN, lane, hasA, hasB);
+        if (g == 0u && (FULL || P.step_count)) ns_keep = e + lane < e_end ? (int)P.step_count[e + lane] : 0;   // consumed 32 envs later
         const bool liveA = hasA && aA < limA, liveB = hasB && aB < limB;   // has a link AND the agent acts this step
 
         // ---- envs/d2d_env.py:93-101: rb = a // n_pwr, p = a % n_pwr; rank inside the RB (actions.py:27-31) -------------
@@ -499,12 +520,14 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         const uint32_t rbA = S.rb_cue(asA), rbB = S.rb_due(asB);
         const uint32_t pA = asA - rbA * S.npc(), pB_ = asB - rbB * S.npd();
         const uint32_t binA = bins + rbA * D2D_BIN_STRIDE, binB = bins + rbB * D2D_BIN_STRIDE;
-        const uint32_t rankA = d2d_atoms_inc_at<D2D_BIN_CNT>(binA);
-        const uint32_t rankB = d2d_atoms_inc_at<D2D_BIN_CNT>(binB);
-        d2d_sts32_if(liveB, binB + D2D_BIN_CNT + 4u, 1u);                       // a SIDELINK is on this RB (reward_fn.py:31-37)
+        const uint32_t cntA = liveA ? binA + D2D_BIN_CNT : dumA, cntB = liveB ? binB + D2D_BIN_CNT : dumA + 256u;
+        const uint32_t rankA = d2d_atoms_inc_at<0>(cntA);
+        const uint32_t rankB = d2d_atoms_inc_at<0>(cntB);
+        d2d_sts32_if(liveB, cntB + 4u, 1u);                                     // a SIDELINK is on this RB (reward_fn.py:31-37)
         const float plA = d2d_lds32(blk + D2D_BLK_PWR + (pA << 2));            // 10^(p/10)
         const float plB = d2d_lds32(blk + D2D_BLK_PWR + (pB_ << 2));
-        const float4 cA = d2d_lds128_at<0>(lkA), cB = d2d_lds128_at<512>(lkA);  // (tx_lin0, a_lin, inv_noise, snr0_dB)
+        // (tx_lin0, a_lin, inv_noise, snr0_dB): the default EnvConfig has one set per link type, held in the constant bank
+        const float4 cA = SPEC ? P.u_cue : d2d_lds128_at<0>(lkA), cB = SPEC ? P.u_due : d2d_lds128_at<512>(lkA);
 
         // ---- peer records: position, radiated weight w, and its value u at the MBS -------------------------------
         const float d2A = fmaf(tA.x, tA.x, tA.y * tA.y);                       // CUE -> MBS distance^2 (own link)
@@ -523,8 +546,8 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         __syncwarp();
 
         // ---- simulator.py:95-101: interference at each victim's receiver (a dead lane has an empty range) ----------
-        const uint2 ctA = d2d_lds64u_at<D2D_BIN_CNT>(binA);                    // (links on the victim's RB, SIDELINK flag)
-        const uint32_t nA = ctA.x, nB = d2d_lds32u_at<D2D_BIN_CNT>(binB);
+        const uint2 ctA = d2d_lds64u_at<0>(cntA);                              // (links on the victim's RB, SIDELINK flag)
+        const uint32_t nA = ctA.x, nB = d2d_lds32u_at<0>(cntB);
         float IA, IB, dminA = 3.0e38f, dminB = 3.0e38f;
         if (__any_sync(0xffffffffu, (liveA && nA > D2D_BIN_CAP) || (liveB && nB > D2D_BIN_CAP))) {
             // rare: some RB holds more links than a bin has record slots
@@ -535,12 +558,12 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
             // bit t of valid <=> record t of the victim's bin exists and is not the victim (dead lane: 0)
             const uint32_t validA = liveA ? (((1u << nA) - 1u) ^ (1u << rankA)) : 0u;
             const uint32_t validB = liveB ? (((1u << nB) - 1u) ^ (1u << rankB)) : 0u;
-            IA = EXACT ? d2d_walk_rx<PLE2, true>(binA, validA, 0.f, 0.f, P.neg_half_ple, dminA) : d2d_walk_mbs(binA, validA);
-            IB = d2d_walk_rx<PLE2, EXACT>(binB, validB, pB.z, pB.w, P.neg_half_ple, dminB);
+            IA = EXACT ? d2d_walk_rx<PLE2, true>(binA, zrec, validA, 0.f, 0.f, P.neg_half_ple, dminA) : d2d_walk_mbs(binA, zrec, validA);
+            IB = d2d_walk_rx<PLE2, EXACT>(binB, zrec, validB, pB.z, pB.w, P.neg_half_ple, dminB);
         }
 
         // ---- per-link epilogue (simulator.py:93,106-107,110-127,144-154); dead lanes are zeroed ------------------------
-        const float2 sA = d2d_lds64(lkS), sB = d2d_lds64(lkS + 256u);          // (sensitivity, RB bandwidth in MHz)
+        const float2 sA = SPEC ? P.us_cue : d2d_lds64(lkS), sB = SPEC ? P.us_due : d2d_lds64(lkS + 256u);   // (sensitivity, RB bandwidth in MHz)
         const float slope = PLE2 ? 3.0102999566398120f : P.snr_slope;
         const D2DLinkOut oA = d2d_link_epilogue_warp(liveA, (int)pA, plA, lgA, gA, IA, cA, sA, slope);
         const D2DLinkOut oB = d2d_link_epilogue_warp(liveB, (int)pB_, plB, lgB, gB, IB, cB, sB, slope);
@@ -561,39 +584,44 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
 
         // ---- outputs: compact observation table (envs/obs_fn.py:55-61), capacity, optional info.  Rows of absent
         // agents carry their positions and zeros (the reference has no row for them). ---------------------------------
-        if (FULL || P.obs) {
-            char *oa = reinterpret_cast<char *>(P.obs) + (uint64_t)jA * 24u, *ob = reinterpret_cast<char *>(P.obs) + (uint64_t)jB * 24u;
-            d2d_stg64_if(hasA, oa, tA.x, tA.y);
-            d2d_stg64_if(hasA, oa + 8, 0.f, 0.f);
-            d2d_stg64_if(hasA, oa + 16, oA.sinr_dB, oA.snr_dB);
-            d2d_stg64_if(hasB, ob, pB.x, pB.y);
-            d2d_stg64_if(hasB, ob + 8, pB.z, pB.w);
-            d2d_stg64_if(hasB, ob + 16, oB.sinr_dB, oB.snr_dB);
-        }
-        if (FULL || P.cap) {
-            d2d_stg32_if(hasA, P.cap + jA, oA.cap);
-            d2d_stg32_if(hasB, P.cap + jB, oB.cap);
-        }
-        if (!FULL) {
-            if (P.rate) {
-                d2d_stg32_if(hasA, P.rate + jA, oA.rate);
-                d2d_stg32_if(hasB, P.rate + jB, oB.rate);
+        // (one divergent branch per slot: cheaper than predicating every store, and the two merge when C == D)
+        if (hasA) {
+            if (FULL || P.obs) {
+                float2 *oa = reinterpret_cast<float2 *>(reinterpret_cast<char *>(P.obs) + (uint64_t)jA * 24u);
+                oa[0] = make_float2(tA.x, tA.y); oa[1] = make_float2(0.f, 0.f); oa[2] = make_float2(oA.sinr_dB, oA.snr_dB);
             }
-            if (P.rb_out) {
-                d2d_stg16_if(hasA, P.rb_out + jA, liveA ? (int)rbA : 0);
-                d2d_stg16_if(hasB, P.rb_out + jB, liveB ? (int)rbB : 0);
-            }
-            if (P.pwr_out) {
-                d2d_stg16_if(hasA, P.pwr_out + jA, liveA ? (int)pA : 0);
-                d2d_stg16_if(hasB, P.pwr_out + jB, liveB ? (int)pB_ : 0);
+            if (FULL || P.cap) P.cap[jA] = oA.cap;
+            if (!FULL) {
+                if (P.rate) P.rate[jA] = oA.rate;
+                if (P.rb_out) P.rb_out[jA] = (int16_t)(liveA ? rbA : 0u);
+                if (P.pwr_out) P.pwr_out[jA] = (int16_t)(liveA ? pA : 0u);
             }
         }
-        if (lane == 0) {
-            // envs/d2d_env.py:65,68: num_steps += 1; done = num_steps >= EPISODE_LENGTH
-            const int ns = min(ns_prev + 1, 255);
-            if (FULL || P.step_count) P.step_count[e] = (uint8_t)ns;
-            if (FULL || P.reward) P.reward[e] = reward;
-            if (FULL || P.done) P.done[e] = ns >= P.episode_length ? 1 : 0;
+        if (hasB) {
+            if (FULL || P.obs) {
+                float2 *ob = reinterpret_cast<float2 *>(reinterpret_cast<char *>(P.obs) + (uint64_t)jB * 24u);
+                ob[0] = make_float2(pB.x, pB.y); ob[1] = make_float2(pB.z, pB.w); ob[2] = make_float2(oB.sinr_dB, oB.snr_dB);
+            }
+            if (FULL || P.cap) P.cap[jB] = oB.cap;
+            if (!FULL) {
+                if (P.rate) P.rate[jB] = oB.rate;
+                if (P.rb_out) P.rb_out[jB] = (int16_t)(liveB ? rbB : 0u);
+                if (P.pwr_out) P.pwr_out[jB] = (int16_t)(liveB ? pB_ : 0u);
+            }
+        }
+        rew_keep = lane == g ? reward : rew_keep;
+        if (g == 31u || e + 1u == e_end) {
+            // envs/d2d_env.py:65,68 for the whole group: num_steps += 1; done = num_steps >= EPISODE_LENGTH
+            if (lane <= g) {
+                const uint32_t eg = e - g + lane;
+                const int ns = min(ns_keep + 1, 255);
+                if (FULL || P.step_count) P.step_count[eg] = (uint8_t)ns;
+                if (FULL || P.reward) P.reward[eg] = rew_keep;
+                if (FULL || P.done) P.done[eg] = ns >= P.episode_length ? 1 : 0;
+            }
+            g = 0u;
+        } else {
+            ++g;
         }
         st_reward += reward; st_cap += cap_sum; st_reward2 = fmaf(reward, reward, st_reward2);
         st_pen += bad ? 1u : 0u;
@@ -601,19 +629,16 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         // ---- rare: fp64 recomputation of flagged links, after the env's outputs are stored ----------------------------------
         if (D2D_RESCUE_ENABLED && __any_sync(0xffffffffu, needA || needB)) {
             const uint32_t keyA = liveA ? rbA : (D2D_INACTIVE_KEY | lane), keyB = liveB ? rbB : (D2D_INACTIVE_KEY | 32u | lane);
-            st_resc += (uint32_t)d2d_rescue_warp<PLE2, EXACT, SPEC>(P, S, e, lane, jA, keyA, keyB, needA, needB, pA, pB_, tA, pB, oA, oB,
-                                                                    sA.x, sB.x);
+            st_resc += (uint32_t)d2d_rescue_warp<PLE2, EXACT, SPEC>(P, S, e, lane, iA, keyA, keyB, needA, needB, pA, pB_);
         }
-        iA += stride * N; qA += stride * V;
-        slot += sd; sd = 0u - sd;
         __syncwarp();     // every lane is done with this env's records and counters before the next env's are written
     }
-    d2d_cp_wait_all();
 
     if (P.stats && lane < 6) {
         // one fire-and-forget fp64 reduction per statistic and warp, spread over the replicas
         const double v = lane == 0 ? (double)st_reward : lane == 1 ? (double)st_cap : lane == 2 ? (double)st_reward2
-                       : lane == 3 ? (double)iters : lane == 4 ? (double)st_pen : (double)st_resc;
+                       : lane == 3 ? (double)(e_end - e0)                  // envs this warp stepped
+                       : lane == 4 ? (double)st_pen : (double)st_resc;
         const unsigned w_global = blockIdx.x * WPB + warp;
         if (v != 0.0) atomicAdd(P.stats + (w_global % D2D_STATS_REPLICAS) * 8 + lane, v);
     }
