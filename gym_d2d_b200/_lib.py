@@ -66,6 +66,7 @@ SIGNATURES = {
     'd2d_set_positions': (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _vp]),
     'd2d_reset': (C.c_int, [_vp, _u64, _u64, _vp, _vp]),
     'd2d_step': (C.c_int, [_vp, C.POINTER(D2DStepIO), _vp]),
+    'd2d_step_many': (C.c_int, [_vp, C.POINTER(D2DStepIO), _i32, _vp]),
     'd2d_step_host': (C.c_int, [_vp, C.POINTER(D2DStepIO), _vp]),
     'd2d_step_host_async': (C.c_int, [_vp, C.POINTER(D2DStepIO), C.c_int, _vp]),
     'd2d_step_host_wait': (C.c_int, [_vp, C.c_int]),

@@ -145,10 +145,12 @@ int allow_smem(K kernel, size_t smem) {
 // every (EXACT, FULL) instantiation d2d_step may launch for this handle needs the dynamic shared-memory opt-in
 template <bool PLE2, int WPB, bool SPEC>
 int allow_smem_warp(size_t smem) {
-    int rc = allow_smem(d2d_step_warp_kernel<PLE2, false, WPB, false, SPEC>, smem);
-    if (!rc) rc = allow_smem(d2d_step_warp_kernel<PLE2, false, WPB, true, SPEC>, smem);
-    if (!rc) rc = allow_smem(d2d_step_warp_kernel<PLE2, true, WPB, false, SPEC>, smem);
-    if (!rc) rc = allow_smem(d2d_step_warp_kernel<PLE2, true, WPB, true, SPEC>, smem);
+    int rc = allow_smem(d2d_step_warp_kernel<PLE2, false, WPB, false, SPEC, false>, smem);
+    if (!rc) rc = allow_smem(d2d_step_warp_kernel<PLE2, false, WPB, true, SPEC, false>, smem);
+    if (!rc) rc = allow_smem(d2d_step_warp_kernel<PLE2, true, WPB, false, SPEC, false>, smem);
+    if (!rc) rc = allow_smem(d2d_step_warp_kernel<PLE2, true, WPB, true, SPEC, false>, smem);
+    if (!rc) rc = allow_smem(d2d_step_warp_kernel<PLE2, false, WPB, false, SPEC, true>, smem);
+    if (!rc) rc = allow_smem(d2d_step_warp_kernel<PLE2, true, WPB, false, SPEC, true>, smem);
     return rc;
 }
 
@@ -173,13 +175,13 @@ int plan_warp(d2d_handle *h, size_t smem) {
     int rc;
     if (h->spec) {          // the reference's default EnvConfig shape: counts and division magics are immediates
         rc = allow_smem_warp<true, WPB, true>(smem);
-        if (!rc) rc = plan_geometry(h, d2d_step_warp_kernel<true, false, WPB, true, true>, WPB * 32, smem, WPB);
+        if (!rc) rc = plan_geometry(h, d2d_step_warp_kernel<true, false, WPB, true, true, false>, WPB * 32, smem, WPB);
     } else if (h->ple2) {
         rc = allow_smem_warp<true, WPB, false>(smem);
-        if (!rc) rc = plan_geometry(h, d2d_step_warp_kernel<true, false, WPB, true, false>, WPB * 32, smem, WPB);
+        if (!rc) rc = plan_geometry(h, d2d_step_warp_kernel<true, false, WPB, true, false, false>, WPB * 32, smem, WPB);
     } else {
         rc = allow_smem_warp<false, WPB, false>(smem);
-        if (!rc) rc = plan_geometry(h, d2d_step_warp_kernel<false, false, WPB, true, false>, WPB * 32, smem, WPB);
+        if (!rc) rc = plan_geometry(h, d2d_step_warp_kernel<false, false, WPB, true, false, false>, WPB * 32, smem, WPB);
     }
     return rc;
 }
@@ -405,15 +407,19 @@ D2D_API int d2d_reset(d2d_handle_t *h, uint64_t seed, uint64_t first_global_env,
     return D2D_OK;
 }
 
-D2D_API int d2d_step(d2d_handle_t *h, const d2d_step_io_t *io, void *stream) {
-    if (!h || !io || !io->actions) return fail(D2D_ERR_INVALID_ARG, "d2d_step: handle, io and io->actions are required");
-    if (!h->pos) return fail(D2D_ERR_STATE, "d2d_step: call d2d_bind_state first");
-    if (io->obs && ((uintptr_t)io->obs % 8)) return fail(D2D_ERR_INVALID_ARG, "d2d_step: obs must be 8-byte aligned");
+namespace {
+
+// One launch (per chunk of envs) that makes T consecutive steps: T == 1 is d2d_step; T > 1 needs the warp kernel.
+int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, void *stream) {
     D2DParams P = make_params(h, io);
+    P.T = T;
+    P.t_stride = h->cfg.num_envs;
     cudaStream_t st = (cudaStream_t)stream;
-    // the kernels index with 32 bits: batches beyond 2^31 / max(6N, 2V) envs (> 7 million default envs) go in chunks
+    const bool many = T > 1;
+    // the kernels index with 32 bits: batches beyond 2^31 / (T max(6N, 2V)) envs (> 7 million default envs) go in chunks
     int64_t chunk = std::max<int64_t>(1, (int64_t)0x7fffffff / std::max(6 * h->N, 2 * h->V));
-    if (h->chunk_override > 0) chunk = std::min(chunk, h->chunk_override);
+    if (many) chunk = h->cfg.num_envs;        // d2d_step_many checked that T slices fit 32-bit indices
+    if (h->chunk_override > 0 && !many) chunk = std::min(chunk, h->chunk_override);
     for (int64_t e0 = 0; e0 < h->cfg.num_envs; e0 += chunk) {
         const int64_t n = std::min<int64_t>(chunk, h->cfg.num_envs - e0);
         if (e0 > 0) {
@@ -436,10 +442,11 @@ D2D_API int d2d_step(d2d_handle_t *h, const d2d_step_io_t *io, void *stream) {
         // FULL: exactly the core outputs were passed, so the kernel tests no output pointer on its hot path
         const bool full = io->obs && io->capacity_mbps && io->reward && io->done && !io->rate_bps && !io->rb && !io->tx_pwr_dBm &&
                           h->step_count;
-#define D2D_LAUNCH_WARP(PLE2_, EXACT_, WPB_, FULL_, SPEC_) \
-    launch_step(d2d_step_warp_kernel<PLE2_, EXACT_, WPB_, FULL_, SPEC_>, grid, WPB_ * 32, h->smem, st, P, h->pdl)
-#define D2D_PICK_FULL(PLE2_, EXACT_, WPB_, SPEC_) \
-    (full ? D2D_LAUNCH_WARP(PLE2_, EXACT_, WPB_, true, SPEC_) : D2D_LAUNCH_WARP(PLE2_, EXACT_, WPB_, false, SPEC_))
+#define D2D_LAUNCH_WARP(PLE2_, EXACT_, WPB_, FULL_, SPEC_, MANY_) \
+    launch_step(d2d_step_warp_kernel<PLE2_, EXACT_, WPB_, FULL_, SPEC_, MANY_>, grid, WPB_ * 32, h->smem, st, P, h->pdl)
+#define D2D_PICK_FULL(PLE2_, EXACT_, WPB_, SPEC_)                                               \
+    (many ? D2D_LAUNCH_WARP(PLE2_, EXACT_, WPB_, false, SPEC_, true)                             \
+          : full ? D2D_LAUNCH_WARP(PLE2_, EXACT_, WPB_, true, SPEC_, false) : D2D_LAUNCH_WARP(PLE2_, EXACT_, WPB_, false, SPEC_, false))
 #define D2D_PICK_EXACT(PLE2_, WPB_, SPEC_) (exact ? D2D_PICK_FULL(PLE2_, true, WPB_, SPEC_) : D2D_PICK_FULL(PLE2_, false, WPB_, SPEC_))
 #define D2D_PICK_SHAPE(WPB_) \
     (h->spec ? D2D_PICK_EXACT(true, WPB_, true) : h->ple2 ? D2D_PICK_EXACT(true, WPB_, false) : D2D_PICK_EXACT(false, WPB_, false))
@@ -455,6 +462,43 @@ D2D_API int d2d_step(d2d_handle_t *h, const d2d_step_io_t *io, void *stream) {
         ++h->launches;
     }
     D2D_CUDA(cudaGetLastError());
+    return D2D_OK;
+}
+
+}  // namespace
+
+D2D_API int d2d_step(d2d_handle_t *h, const d2d_step_io_t *io, void *stream) {
+    if (!h || !io || !io->actions) return fail(D2D_ERR_INVALID_ARG, "d2d_step: handle, io and io->actions are required");
+    if (!h->pos) return fail(D2D_ERR_STATE, "d2d_step: call d2d_bind_state first");
+    if (io->obs && ((uintptr_t)io->obs % 8)) return fail(D2D_ERR_INVALID_ARG, "d2d_step: obs must be 8-byte aligned");
+    return step_launch(h, io, 1, stream);
+}
+
+D2D_API int d2d_step_many(d2d_handle_t *h, const d2d_step_io_t *io, int32_t num_steps, void *stream) {
+    if (!h || !io || !io->actions) return fail(D2D_ERR_INVALID_ARG, "d2d_step_many: handle, io and io->actions are required");
+    if (!h->pos) return fail(D2D_ERR_STATE, "d2d_step_many: call d2d_bind_state first");
+    if (num_steps < 1) return fail(D2D_ERR_INVALID_ARG, "d2d_step_many: num_steps must be >= 1");
+    if (io->obs && ((uintptr_t)io->obs % 8)) return fail(D2D_ERR_INVALID_ARG, "d2d_step_many: obs must be 8-byte aligned");
+    const int64_t E = h->cfg.num_envs, per_env = std::max(6 * h->N, 2 * h->V);
+    // fused launches of as many steps as 32-bit indices allow (all of them unless T E N is astronomically large);
+    // configurations served by the block kernel take one launch per step
+    int64_t fuse = h->use_warp ? std::min<int64_t>(num_steps, (int64_t)0x7fffffff / (E * per_env)) : 1;
+    if (fuse < 1) fuse = 1;
+    d2d_step_io_t cur = *io;
+    for (int64_t t0 = 0; t0 < num_steps; t0 += fuse) {
+        const int T = (int)std::min<int64_t>(fuse, num_steps - t0);
+        int rc = step_launch(h, &cur, T, stream);
+        if (rc) return rc;
+        const int64_t dl = (int64_t)T * E * h->N, de = (int64_t)T * E;
+        cur.actions += dl;
+        if (cur.obs) cur.obs += dl * 6;
+        if (cur.capacity_mbps) cur.capacity_mbps += dl;
+        if (cur.reward) cur.reward += de;
+        if (cur.done) cur.done += de;
+        if (cur.rate_bps) cur.rate_bps += dl;
+        if (cur.rb) cur.rb += dl;
+        if (cur.tx_pwr_dBm) cur.tx_pwr_dBm += dl;
+    }
     return D2D_OK;
 }
 

@@ -54,6 +54,8 @@ struct D2DParams {
     int32_t episode_length;
     int32_t nbins;               // block kernel: number of RB bins
     int32_t align4;              // warp kernel: every env's DUE (tx, rx) pair is a 16-byte aligned float4
+    int32_t T;                   // d2d_step_many: steps per env in this launch (1 for d2d_step)
+    int64_t t_stride;            // d2d_step_many: envs between consecutive step slices of the io buffers
     uint32_t magic_cue, magic_due;  // d2d_div_magic(n_pwr_cue / n_pwr_due): rb = umulhi(a, magic) + (a & npw1)
     uint32_t npw1_cue, npw1_due;    // 0xffffffff when n_pwr == 1 (then magic = 0 and rb = a), else 0
     float ple;                   // path-loss exponent

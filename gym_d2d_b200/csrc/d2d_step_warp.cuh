@@ -278,6 +278,15 @@ __device__ __forceinline__ D2DLaneIn d2d_load_inputs(const D2DParams &P, const D
     return in;
 }
 
+// d2d_step_many: the next step's two actions of the same env (positions stay in registers)
+template <bool SPEC>
+__device__ __forceinline__ void d2d_load_actions(const D2DParams &P, const D2DShape<SPEC> &S, uint32_t iA, bool hasA, bool hasB,
+                                                 D2DLaneIn &in) {
+    in.aA = 0xffffffffu; in.aB = 0xffffffffu;
+    if (hasA) in.aA = (uint32_t)__ldg(P.actions + iA);
+    if (hasB) in.aB = (uint32_t)__ldg(P.actions + (iA + S.C()));
+}
+
 // log2(1 + r), branch-free form of d2d_log2_1p (both sides are a handful of instructions; a divergent branch costs more)
 __device__ __forceinline__ float d2d_log2_1p_sel(float r) {
     const float s = r * d2d_rcp(2.0f + r);
@@ -440,7 +449,10 @@ __device__ __forceinline__ int d2d_rescue_warp(const D2DParams &P, const D2DShap
 
 // FULL: the caller passed exactly the core outputs (obs, capacity, reward, done) and a step counter is bound - the
 // VecD2DEnv default - so no pointer is tested on the hot path; otherwise every output is optional and checked.
-template <bool PLE2, bool EXACT, int WPB, bool FULL, bool SPEC>
+// MANY: d2d_step_many - P.T consecutive steps per env in ONE launch (the agent loop of examples/simple_env.py:20-33
+// with the actions of all T steps given up front).  An env's positions are read once and stay in registers for its T
+// steps; step t reads actions[t][e] and writes the [t][e] slice of every output (slices P.t_stride envs apart).
+template <bool PLE2, bool EXACT, int WPB, bool FULL, bool SPEC, bool MANY>
 __global__ void __launch_bounds__(WPB * 32, D2D_WARP_MIN_BLOCKS(WPB))
 d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
     extern __shared__ __align__(16) unsigned char d2d_warp_smem[];
@@ -501,18 +513,29 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
     int ns_keep = 0;                                               // lane i: step counter of the group's env i
     float rew_keep = 0.f;                                          // lane i: reward of the group's env i
     D2DLaneIn nxt;
+    // d2d_step_many state: step index inside the env, the link / env offsets of output slice t, the env's positions
+    uint32_t t = 0, tN = 0, tE = 0;
+    const uint32_t T = MANY ? (uint32_t)P.T : 1u, strideE = MANY ? (uint32_t)P.t_stride : 0u, strideN = strideE * N;
+    float2 tA_keep = make_float2(1.f, 0.f);
+    float4 pB_keep = make_float4(1.f, 0.f, 0.f, 0.f);
     d2d_pdl_wait();
     if (e < e_end) nxt = d2d_load_inputs<SPEC>(P, S, iA, qN, lane, hasA, hasB);
-    for (; e < e_end; ++e, iA += N) {
-        // ---- one coalesced pass over the env's inputs, software-pipelined: the NEXT env's loads are in flight while
-        // this env computes, so a warp hides its own HBM latency --------------------------------------------------------
+    while (e < e_end) {
+        // ---- one coalesced pass over the env's inputs, software-pipelined: the NEXT env's (or step's) loads are in
+        // flight while this one computes, so a warp hides its own HBM latency -------------------------------------------
         const uint32_t aA = nxt.aA, aB = nxt.aB;
-        const float2 tA = nxt.tA;
-        const float4 pB = nxt.pB;
-        const uint32_t jA = iA, jB = iA + C;                        // this env's link indices (outputs)
-        qN += V;
-        if (e + 1u < e_end) nxt = d2d_load_inputs<SPEC>(P, S, iA + N, qN, lane, hasA, hasB);
-        if (g == 0u && (FULL || P.step_count)) ns_keep = e + lane < e_end ? (int)P.step_count[e + lane] : 0;   // consumed 32 envs later
+        if (!MANY || t == 0u) { tA_keep = nxt.tA; pB_keep = nxt.pB; }
+        const float2 tA = tA_keep;
+        const float4 pB = pB_keep;
+        const uint32_t jA = iA + tN, jB = jA + C;                   // this env-step's link indices (outputs)
+        const bool last_t = !MANY || t + 1u == T;
+        if (last_t) {
+            qN += V;
+            if (e + 1u < e_end) nxt = d2d_load_inputs<SPEC>(P, S, iA + N, qN, lane, hasA, hasB);
+        } else {
+            d2d_load_actions<SPEC>(P, S, jA + strideN, hasA, hasB, nxt);
+        }
+        if (g == 0u && t == 0u && (FULL || P.step_count)) ns_keep = e + lane < e_end ? (int)P.step_count[e + lane] : 0;   // consumed 32 envs later
         const bool liveA = hasA && aA < limA, liveB = hasB && aB < limB;   // has a link AND the agent acts this step
 
         // ---- envs/d2d_env.py:93-101: rb = a // n_pwr, p = a % n_pwr; rank inside the RB (actions.py:27-31) -------------
@@ -609,19 +632,27 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
                 if (P.pwr_out) P.pwr_out[jB] = (int16_t)(liveB ? pB_ : 0u);
             }
         }
-        rew_keep = lane == g ? reward : rew_keep;
-        if (g == 31u || e + 1u == e_end) {
+        if (MANY) {
+            // per-step scalars straight to slice t (write-only, so partial sectors merge in L2); the step counter stays
+            // in the group's registers until the env's last step
+            if (lane == g) {
+                const int ns = min(ns_keep + (int)t + 1, 255);
+                if (P.reward) P.reward[tE + e] = reward;
+                if (P.done) P.done[tE + e] = ns >= P.episode_length ? 1 : 0;
+                if (last_t) ns_keep = ns;
+            }
+        } else {
+            rew_keep = lane == g ? reward : rew_keep;
+        }
+        if (last_t && (g == 31u || e + 1u == e_end)) {
             // envs/d2d_env.py:65,68 for the whole group: num_steps += 1; done = num_steps >= EPISODE_LENGTH
             if (lane <= g) {
                 const uint32_t eg = e - g + lane;
-                const int ns = min(ns_keep + 1, 255);
+                const int ns = MANY ? ns_keep : min(ns_keep + 1, 255);
                 if (FULL || P.step_count) P.step_count[eg] = (uint8_t)ns;
-                if (FULL || P.reward) P.reward[eg] = rew_keep;
-                if (FULL || P.done) P.done[eg] = ns >= P.episode_length ? 1 : 0;
+                if (!MANY && (FULL || P.reward)) P.reward[eg] = rew_keep;
+                if (!MANY && (FULL || P.done)) P.done[eg] = ns >= P.episode_length ? 1 : 0;
             }
-            g = 0u;
-        } else {
-            ++g;
         }
         st_reward += reward; st_cap += cap_sum; st_reward2 = fmaf(reward, reward, st_reward2);
         st_pen += bad ? 1u : 0u;
@@ -629,7 +660,15 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         // ---- rare: fp64 recomputation of flagged links, after the env's outputs are stored ----------------------------------
         if (D2D_RESCUE_ENABLED && __any_sync(0xffffffffu, needA || needB)) {
             const uint32_t keyA = liveA ? rbA : (D2D_INACTIVE_KEY | lane), keyB = liveB ? rbB : (D2D_INACTIVE_KEY | 32u | lane);
-            st_resc += (uint32_t)d2d_rescue_warp<PLE2, EXACT, SPEC>(P, S, e, lane, iA, keyA, keyB, needA, needB, pA, pB_);
+            st_resc += (uint32_t)d2d_rescue_warp<PLE2, EXACT, SPEC>(P, S, e, lane, jA, keyA, keyB, needA, needB, pA, pB_);
+        }
+        if (last_t) {
+            g = (g + 1u) & 31u;
+            if (e + 1u == e_end) g = 0u;
+            t = 0u; tN = 0u; tE = 0u;
+            ++e; iA += N;
+        } else {
+            ++t; tN += strideN; tE += strideE;
         }
         __syncwarp();     // every lane is done with this env's records and counters before the next env's are written
     }
@@ -637,7 +676,7 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
     if (P.stats && lane < 6) {
         // one fire-and-forget fp64 reduction per statistic and warp, spread over the replicas
         const double v = lane == 0 ? (double)st_reward : lane == 1 ? (double)st_cap : lane == 2 ? (double)st_reward2
-                       : lane == 3 ? (double)(e_end - e0)                  // envs this warp stepped
+                       : lane == 3 ? (double)((e_end - e0) * T)            // env-steps this warp made
                        : lane == 4 ? (double)st_pen : (double)st_resc;
         const unsigned w_global = blockIdx.x * WPB + warp;
         if (v != 0.0) atomicAdd(P.stats + (w_global % D2D_STATS_REPLICAS) * 8 + lane, v);

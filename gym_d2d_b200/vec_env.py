@@ -224,6 +224,39 @@ class VecD2DEnv:
                         sinr_db=o.obs[..., 4], snr_db=o.obs[..., 5])
         return o.obs, o.reward, o.done, info
 
+    def step_many(self, actions: torch.Tensor, out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """T consecutive env.step calls in ONE kernel launch (d2d_step_many): the reference's agent loop
+        (examples/simple_env.py:20-33) when the actions of every step are known up front.
+
+        actions: int32 [T][E][N].  Returns {'obs': [T][E][N][6], 'capacity_mbps': [T][E][N], 'reward': [T][E],
+        'done': [T][E] uint8 (+ 'rate_bps', 'rb', 'tx_pwr_dbm' with info=True)}; slice t is exactly what the t-th step()
+        call would have returned.  Pass `out` (from alloc_many_outputs) to reuse buffers."""
+        if actions.dtype != torch.int32 or not actions.is_cuda or not actions.is_contiguous() or actions.dim() != 3:
+            raise ValueError('actions must be a contiguous int32 CUDA tensor [T][num_envs][num_links]')
+        T = int(actions.shape[0])
+        if tuple(actions.shape[1:]) != (self.num_envs, self.num_links) or T < 1:
+            raise ValueError(f'actions must have shape (T, {self.num_envs}, {self.num_links}), got {tuple(actions.shape)}')
+        o = out if out is not None else self.alloc_many_outputs(T)
+        if int(o['obs'].shape[0]) != T:
+            raise ValueError('out was allocated for a different number of steps')
+        io = _lib.D2DStepIO(actions=actions.data_ptr(), obs=o['obs'].data_ptr(), capacity_mbps=o['capacity_mbps'].data_ptr(),
+                            reward=o['reward'].data_ptr(), done=o['done'].data_ptr(), rate_bps=_ptr(o.get('rate_bps')),
+                            rb=_ptr(o.get('rb')), tx_pwr_dBm=_ptr(o.get('tx_pwr_dbm')))
+        _lib.check(self._lib.d2d_step_many(self._h, C.byref(io), T, self._stream()))
+        return o
+
+    def alloc_many_outputs(self, T: int) -> Dict[str, torch.Tensor]:
+        E, N, dev = self.num_envs, self.num_links, self.device
+        o = {'obs': torch.empty((T, E, N, 6), dtype=torch.float32, device=dev),
+             'capacity_mbps': torch.empty((T, E, N), dtype=torch.float32, device=dev),
+             'reward': torch.empty((T, E), dtype=torch.float32, device=dev),
+             'done': torch.empty((T, E), dtype=torch.uint8, device=dev)}
+        if self.want_info:
+            o.update(rate_bps=torch.empty((T, E, N), dtype=torch.float32, device=dev),
+                     rb=torch.empty((T, E, N), dtype=torch.int16, device=dev),
+                     tx_pwr_dbm=torch.empty((T, E, N), dtype=torch.int16, device=dev))
+        return o
+
     def capture_steps(self, actions_seq, outs_seq=None) -> 'torch.cuda.CUDAGraph':
         """Capture len(actions_seq) consecutive steps (step i reads actions_seq[i], writes outs_seq[i] or the
         default buffers) into one CUDA graph: replay() then costs one launch for the whole sequence."""

@@ -153,6 +153,13 @@ D2D_API int d2d_reset(d2d_handle_t *h, uint64_t seed, uint64_t first_global_env,
  * (envs/reward_fn.py:27-44), the done flag (:68) and the info fields (:106-116), for all E envs. */
 D2D_API int d2d_step(d2d_handle_t *h, const d2d_step_io_t *io, void *stream);
 
+/* num_steps consecutive d2d_step calls in ONE kernel launch: the agent loop of the reference's examples
+ * (examples/simple_env.py:20-33: `for _ in range(EPISODE_LENGTH): env.step(actions)`) when the actions of every step
+ * are known up front (scripted / random policies, replay, evaluation of recorded trajectories).  Every io buffer gains a
+ * leading [num_steps] dimension: actions [T][E][N], obs [T][E][N][6], reward [T][E], ...; slice t holds exactly what the
+ * t-th d2d_step call would have written.  An env's positions are read once for its T steps. */
+D2D_API int d2d_step_many(d2d_handle_t *h, const d2d_step_io_t *io, int32_t num_steps, void *stream);
+
 /* Same call with HOST buffers: copies the actions to the device, steps, copies every non-NULL output
  * back and synchronises the stream.  This is the end-to-end path a CPU-side caller (the reference's
  * own env.step loop) would bind. */
