@@ -48,6 +48,7 @@ struct d2d_handle {
     D2DLinkA u_cue{}, u_due{};
     float us_cue[2] = {0, 0}, us_due[2] = {0, 0};
     int wpb = 4;               // warps per block of the warp kernel
+    int lpt = 0;               // block kernel: links per thread held in registers (0 = the generic shared-memory kernel)
     int64_t chunk_override = 0;  // D2D_B200_CHUNK: force small launch chunks (tests of the > 2^31-element path)
     bool pdl = true;           // programmatic dependent launch (D2D_B200_PDL=0 disables)
     int grid = 0, block = 0, smem = 0, envs_per_block = 0;
@@ -111,6 +112,7 @@ D2DParams make_params(const d2d_handle *h, const d2d_step_io_t *io) {
     P.u_due = make_float4(h->u_due.tx_lin0, h->u_due.a_lin, h->u_due.inv_noise, h->u_due.snr0_dB);
     P.us_cue = make_float2(h->us_cue[0], h->us_cue[1]);
     P.us_due = make_float2(h->us_due[0], h->us_due[1]);
+    P.uniform = h->uniform ? 1 : 0;
     P.ple_d = h->ple;
     P.linkA = h->dA; P.linkB = h->dB; P.linkD = h->dD; P.pwr_lin = h->dPwr; P.pwr_lin_d = h->dPwrD;
     P.pos = h->pos; P.pos64 = h->pos64; P.step_count = h->step_count; P.stats = h->stats;
@@ -313,10 +315,22 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
         const size_t smem = d2d_warp_smem_bytes(cfg->num_rbs, h->wpb);
         rc = h->wpb == 8 ? plan_warp<8>(h, smem) : plan_warp<4>(h, smem);
     } else {
-        const size_t smem = d2d_block_smem_bytes(h->N, cfg->num_rbs);
+        // <= 1024 links: the register-resident block kernel, LPT links per thread; beyond: everything staged in shared memory
+        h->lpt = h->N <= D2D_BLOCK_THREADS * D2D_BLOCK_MAX_LPT ? (h->N + D2D_BLOCK_THREADS - 1) / D2D_BLOCK_THREADS : 0;
+        const size_t smem = h->lpt ? d2d_block2_smem_bytes(h->N, cfg->num_rbs) : d2d_block_smem_bytes(h->N, cfg->num_rbs);
         if (smem > 227 * 1024) return bail(fail(D2D_ERR_UNSUPPORTED, "d2d_create: too many links / RBs for one SM's shared memory"));
-        rc = h->ple2 ? plan_geometry(h, d2d_step_block_kernel<true>, D2D_BLOCK_THREADS, smem, 1)
-                     : plan_geometry(h, d2d_step_block_kernel<false>, D2D_BLOCK_THREADS, smem, 1);
+#define D2D_PLAN_BLOCK(LPT_) (h->ple2 ? plan_geometry(h, d2d_step_block_kernel<true, LPT_>, D2D_BLOCK_THREADS, smem, 1) \
+                                      : plan_geometry(h, d2d_step_block_kernel<false, LPT_>, D2D_BLOCK_THREADS, smem, 1))
+        switch (h->lpt) {
+            case 1: rc = D2D_PLAN_BLOCK(1); break;
+            case 2: rc = D2D_PLAN_BLOCK(2); break;
+            case 3: rc = D2D_PLAN_BLOCK(3); break;
+            case 4: rc = D2D_PLAN_BLOCK(4); break;
+            default:
+                rc = h->ple2 ? plan_geometry(h, d2d_step_block_generic_kernel<true>, D2D_BLOCK_THREADS, smem, 1)
+                             : plan_geometry(h, d2d_step_block_generic_kernel<false>, D2D_BLOCK_THREADS, smem, 1);
+        }
+#undef D2D_PLAN_BLOCK
     }
     if (rc != D2D_OK) return bail(rc);
     *out = h;
@@ -455,8 +469,18 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, void *stream) {
         } else if (h->use_warp) {
             err = D2D_PICK_SHAPE(4);
         } else {
-            err = h->ple2 ? launch_step(d2d_step_block_kernel<true>, grid, h->block, h->smem, st, P, h->pdl)
-                          : launch_step(d2d_step_block_kernel<false>, grid, h->block, h->smem, st, P, h->pdl);
+#define D2D_LAUNCH_BLOCK(LPT_) (h->ple2 ? launch_step(d2d_step_block_kernel<true, LPT_>, grid, h->block, h->smem, st, P, h->pdl) \
+                                        : launch_step(d2d_step_block_kernel<false, LPT_>, grid, h->block, h->smem, st, P, h->pdl))
+            switch (h->lpt) {
+                case 1: err = D2D_LAUNCH_BLOCK(1); break;
+                case 2: err = D2D_LAUNCH_BLOCK(2); break;
+                case 3: err = D2D_LAUNCH_BLOCK(3); break;
+                case 4: err = D2D_LAUNCH_BLOCK(4); break;
+                default:
+                    err = h->ple2 ? launch_step(d2d_step_block_generic_kernel<true>, grid, h->block, h->smem, st, P, h->pdl)
+                                  : launch_step(d2d_step_block_generic_kernel<false>, grid, h->block, h->smem, st, P, h->pdl);
+            }
+#undef D2D_LAUNCH_BLOCK
         }
         if (err != cudaSuccess) return fail(D2D_ERR_CUDA, std::string("step kernel launch: ") + cudaGetErrorString(err));
         ++h->launches;

@@ -54,6 +54,7 @@ struct D2DParams {
     int32_t episode_length;
     int32_t nbins;               // block kernel: number of RB bins
     int32_t align4;              // warp kernel: every env's DUE (tx, rx) pair is a 16-byte aligned float4
+    int32_t uniform;             // every CUE link shares one set of constants, and every DUE link (u_cue / u_due below)
     int32_t T;                   // d2d_step_many: steps per env in this launch (1 for d2d_step)
     int64_t t_stride;            // d2d_step_many: envs between consecutive step slices of the io buffers
     uint32_t magic_cue, magic_due;  // d2d_div_magic(n_pwr_cue / n_pwr_due): rb = umulhi(a, magic) + (a & npw1)
@@ -255,4 +256,28 @@ __device__ __forceinline__ bool d2d_needs_rescue(const D2DLinkOut &o, float dmin
     const float lo = fminf(fabsf(o.sinr_dB), fabsf(o.snr_dB));
     if (!EXACT) return lo < P.rescue_band_dB;
     return lo < fmaf(P.rescue_c, rsqrtf(dmin2), P.rescue_band_dB) || dmin2 < P.rescue_dmin2;
+}
+
+// ---- cheap fp64 building blocks of the rescue passes (no division or libm subroutines) ------------------------------------
+// 1 / x in fp64 from the fp32 reciprocal and three Newton steps (x normal, > 0): no division subroutine
+__device__ __forceinline__ double d2d_rcp_f64(double x) {
+    double y = (double)d2d_rcp((float)x);
+    y = fma(y, fma(-x, y, 1.0), y);
+    y = fma(y, fma(-x, y, 1.0), y);
+    y = fma(y, fma(-x, y, 1.0), y);
+    return y;
+}
+template <bool PLE2>
+__device__ __forceinline__ double d2d_gain_f64_fast(double d2, double ple) {
+    if (PLE2) return d2d_rcp_f64(d2);
+    return d2d_exp_f64(-0.5 * ple * d2d_ln_f64(d2));
+}
+// ln(x) in fp64.  |x - 1| < 1/16 - every value the fp32 trigger sends here unless an fp64 position shadow is bound -
+// needs no exponent split and five series terms; everything else takes the general d2d_ln_f64.
+// 10 log10(x) in fp64 for |x - 1| < 1/16: no exponent split, five series terms
+__device__ __forceinline__ double d2d_db_near1(double x) {
+    const double s = (x - 1.0) * d2d_rcp_f64(x + 1.0), s2 = s * s;      // |s| < 1/31: s^11 / 11 < 1e-17
+    double q = 1.0 / 9.0;
+    q = fma(q, s2, 1.0 / 7.0); q = fma(q, s2, 1.0 / 5.0); q = fma(q, s2, 1.0 / 3.0); q = fma(q, s2, 1.0);
+    return 8.6858896380650365530 * s * q;                               // 2 * 10 / ln 10
 }

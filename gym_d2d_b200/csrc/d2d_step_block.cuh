@@ -5,6 +5,10 @@
 // (actions.py:27-31) is a shared-memory counting sort by RB: count -> exclusive scan -> scatter; each
 // victim link then walks its own bin (expected N/R peers) instead of all N links, so the work per
 // env-step is O(N + N^2/R) pair evaluations, like the reference, not the dense N*Q product.
+//
+// Two kernels: d2d_step_block_kernel<PLE2, LPT> keeps a thread's <= LPT links in registers between the phases and
+// scatters full peer records (N <= 256 LPT, LPT <= 4: every configuration up to 1024 links, incl. config #3);
+// d2d_step_block_generic_kernel stages everything in shared memory and takes any N <= 65535.
 #pragma once
 
 #include "d2d_common.cuh"
@@ -52,7 +56,7 @@ __device__ __forceinline__ D2DBlockSmemView d2d_block_carve(unsigned char *raw, 
 }
 
 template <bool PLE2>
-__global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_kernel(const D2DParams P) {
+__global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_generic_kernel(const D2DParams P) {
     extern __shared__ __align__(16) unsigned char d2d_smem_raw[];
     const int N = P.N, C = P.C, V = P.V, nbins = P.nbins;
     D2DBlockSmemView S = d2d_block_carve(d2d_smem_raw, N, nbins);
@@ -197,5 +201,270 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_kernel(const
         double *dst = P.stats + (blockIdx.x % 32) * 8;
         atomicAdd(dst + 0, st_reward); atomicAdd(dst + 1, st_cap); atomicAdd(dst + 2, st_reward2);
         atomicAdd(dst + 3, st_n); atomicAdd(dst + 4, st_pen); atomicAdd(dst + 5, st_resc);
+    }
+}
+
+
+// ---- register-resident block kernel ------------------------------------------------------------------------------------------
+// Per env (4 block barriers):
+//   1. every thread loads its <= LPT links' inputs (coalesced), decodes them and takes a rank in its RB's counter
+//   2. warp 0 turns the counts into offsets (exclusive scan) and re-zeroes the counters for the next env
+//   3. every link writes its 16-byte peer record (tx_x, tx_y, w, u) at offset[rb] + rank: an RB's records are contiguous
+//   4. every victim walks its RB's range - a CUE victim sums the u scalars (all CUE links share the MBS receiver), a DUE
+//      victim evaluates w g(|tx - rx|) - then the epilogue, the stores and the block reduction for the reward.
+// A block steps a CONTIGUOUS range of envs; the per-env scalars (step counter, reward, done) of a group of 256 envs live
+// in the registers of thread (env - group start) and are read / written as full sectors, like the warp kernel does.
+#define D2D_BLOCK_MAX_LPT 4
+
+__host__ __device__ inline size_t d2d_block2_smem_bytes(int N, int nbins) {
+    size_t b = (size_t)N * sizeof(float4);                        // rec
+    b += D2D_MAX_PWR_LEVELS * sizeof(float);                      // pwr_lin
+    b += ((size_t)(nbins + 1) * 2 * sizeof(uint32_t) + 15) & ~(size_t)15;   // cnt (count | SIDELINK count << 16), off
+    b += ((size_t)N * sizeof(uint32_t) + 15) & ~(size_t)15;       // who: (link index | Tx power << 16) of each sorted record (fp64 pass only)
+    b += 2 * 32 * sizeof(float);                                  // red[2][32]
+    return b;
+}
+
+template <bool PLE2, int LPT>
+__global__ void __launch_bounds__(D2D_BLOCK_THREADS, LPT <= 2 ? 4 : 3) d2d_step_block_kernel(const __grid_constant__ D2DParams P) {
+    extern __shared__ __align__(16) unsigned char d2d_smem_raw[];
+    const uint32_t N = (uint32_t)P.N, C = (uint32_t)P.C, V = (uint32_t)P.V, nbins = (uint32_t)P.nbins;
+    float4 *rec = reinterpret_cast<float4 *>(d2d_smem_raw);
+    float *pwr = reinterpret_cast<float *>(rec + N);
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(pwr + D2D_MAX_PWR_LEVELS);
+    uint32_t *off = cnt + (nbins + 1);
+    float *red = reinterpret_cast<float *>(d2d_smem_raw + d2d_block2_smem_bytes((int)N, (int)nbins) - 2 * 32 * sizeof(float));
+    uint32_t *who = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(red) - (((size_t)N * sizeof(uint32_t) + 15) & ~(size_t)15));
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    d2d_pdl_launch_dependents();
+
+    for (uint32_t i = tid; i < D2D_MAX_PWR_LEVELS; i += D2D_BLOCK_THREADS) pwr[i] = P.pwr_lin[i];
+    for (uint32_t i = tid; i <= nbins; i += D2D_BLOCK_THREADS) cnt[i] = 0u;
+    // this thread's links and their constants (fixed for the whole launch)
+    bool has[LPT], cue[LPT];
+#pragma unroll
+    for (int k = 0; k < LPT; ++k) {
+        const uint32_t j = tid + k * D2D_BLOCK_THREADS;
+        has[k] = j < N; cue[k] = j < C;
+    }
+    // link constants (tx_lin0, a_lin, inv_noise, snr0_dB) and (sens, bw): one set per link type from the constant bank unless
+    // a device-config file overrode single devices (then the per-link tables, through L1)
+    auto link_cA = [&](uint32_t j, bool is_cue) -> float4 {
+        return P.uniform ? (is_cue ? P.u_cue : P.u_due) : __ldg(reinterpret_cast<const float4 *>(P.linkA) + j);
+    };
+    auto link_sB = [&](uint32_t j, bool is_cue) -> float2 {
+        return P.uniform ? (is_cue ? P.us_cue : P.us_due) : __ldg(reinterpret_cast<const float2 *>(P.linkB + j));
+    };
+    float st_reward = 0.f, st_cap = 0.f, st_reward2 = 0.f, st_pen = 0.f, st_resc = 0.f, st_n = 0.f;   // of the envs this thread owns
+
+    const uint32_t num_envs = (uint32_t)P.num_envs;
+    const uint32_t per_block = (num_envs + gridDim.x - 1u) / gridDim.x;
+    const uint32_t e0 = min(blockIdx.x * per_block, num_envs), e_end = min(e0 + per_block, num_envs);
+    uint32_t g = 0;                  // position of the env in its group of 256
+    int ns_keep = 0;                 // thread i: step counter of the group's env i
+    float rew_keep = 0.f;            // thread i: reward of the group's env i
+    d2d_pdl_wait();
+    __syncthreads();
+
+    for (uint32_t e = e0; e < e_end; ++e) {
+        const int32_t *act = P.actions + e * N;
+        const float2 *pe = reinterpret_cast<const float2 *>(P.pos) + e * V;
+        if (g == 0u && P.step_count) ns_keep = e + tid < e_end ? (int)P.step_count[e + tid] : 0;      // consumed at the group's end
+
+        // ---- phase 1: inputs, decode (envs/d2d_env.py:93-101), rank inside the RB (actions.py:27-31) ---------------
+        float2 tx[LPT], rx[LPT];
+        float pl[LPT];
+        uint32_t rb[LPT], pw[LPT], rank[LPT];
+        bool live[LPT];
+#pragma unroll
+        for (int k = 0; k < LPT; ++k) {
+            const uint32_t j = tid + k * D2D_BLOCK_THREADS;
+            uint32_t a = 0xffffffffu;
+            tx[k] = make_float2(1.f, 0.f); rx[k] = make_float2(0.f, 0.f);
+            if (has[k]) {
+                a = (uint32_t)__ldg(act + j);
+                const uint32_t txd = cue[k] ? 1u + j : 1u + C + 2u * (j - C);
+                tx[k] = __ldg(pe + txd);
+                if (!cue[k]) rx[k] = __ldg(pe + txd + 1u);
+            }
+            const uint32_t npw = (uint32_t)(cue[k] ? P.n_pwr_cue : P.n_pwr_due);
+            live[k] = has[k] && a < (uint32_t)P.R * npw;            // valid actions: 0 <= a < R n_pwr (envs/d2d_env.py:36-40)
+            const uint32_t as = live[k] ? a : 0u;
+            rb[k] = __umulhi(as, cue[k] ? P.magic_cue : P.magic_due) + (as & (cue[k] ? P.npw1_cue : P.npw1_due));
+            pw[k] = as - rb[k] * npw;
+            pl[k] = live[k] ? pwr[pw[k]] : 0.0f;
+            rank[k] = 0u;
+            if (live[k]) rank[k] = atomicAdd(&cnt[rb[k]], cue[k] ? 1u : 0x10001u) & 0xffffu;        // high half counts the SIDELINKs
+        }
+        __syncthreads();
+
+        // ---- phase 2: counts -> offsets (warp 0), counters cleared for the next env ------------------------------------
+        if (warp == 0) {
+            const uint32_t chunk = (nbins + 31u) >> 5, lo = lane * chunk, hi = min(lo + chunk, nbins);
+            uint32_t sum = 0;
+            for (uint32_t i = lo; i < hi; ++i) sum += cnt[i] & 0xffffu;
+            uint32_t incl = sum;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, incl, s);
+                if (lane >= (uint32_t)s) incl += n;
+            }
+            uint32_t run = incl - sum;
+            for (uint32_t i = lo; i < hi; ++i) {
+                const uint32_t c = cnt[i];
+                off[i] = run | (c & 0xffff0000u);        // offset in the low half, the RB's SIDELINK count above it
+                run += c & 0xffffu;
+                cnt[i] = 0u;
+            }
+            if (lane == 31u) off[nbins] = run;
+        }
+        __syncthreads();
+
+        // ---- phase 3: peer records, grouped by RB -------------------------------------------------------------------------
+        uint32_t beg[LPT], end[LPT], self[LPT];
+        bool side[LPT];
+        float lg[LPT], gown[LPT];
+#pragma unroll
+        for (int k = 0; k < LPT; ++k) {
+            beg[k] = 0u; end[k] = 0u; self[k] = 0u; side[k] = false;
+            const float dxo = tx[k].x - rx[k].x, dyo = tx[k].y - rx[k].y;       // own link (a CUE's receiver is the MBS at the origin)
+            const float d2own = fmaf(dxo, dxo, dyo * dyo);
+            lg[k] = d2d_lg2(d2own);
+            gown[k] = PLE2 ? d2d_rcp(d2own) : d2d_ex2(P.neg_half_ple * lg[k]);
+            if (live[k]) {
+                const uint32_t o = off[rb[k]];
+                beg[k] = o & 0xffffu; end[k] = off[rb[k] + 1u] & 0xffffu; side[k] = (o >> 16) != 0u;
+                self[k] = beg[k] + rank[k];
+                const float w = pl[k] * link_cA(tid + k * D2D_BLOCK_THREADS, cue[k]).x;
+                const float u = w * (cue[k] ? gown[k] : d2d_gain<PLE2>(fmaf(tx[k].x, tx[k].x, tx[k].y * tx[k].y), P.neg_half_ple));
+                rec[self[k]] = make_float4(tx[k].x, tx[k].y, w, u);             // u = this link's interference at the MBS
+                who[self[k]] = (tid + k * D2D_BLOCK_THREADS) | (pw[k] << 16);
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 4: interference walk (simulator.py:95-101), epilogue, outputs ----------------------------------------------
+        float cap_part = 0.0f;
+        uint32_t n_act = 0, resc = 0;
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < LPT; ++k) {
+            const uint32_t j = tid + k * D2D_BLOCK_THREADS;
+            D2DLinkOut o = {0.f, 0.f, 0.f, 0.f};
+            if (live[k]) {
+                float I = 0.0f, dmin2 = 3.0e38f;
+                if (cue[k] && !P.pos64) {
+                    for (uint32_t q = beg[k]; q < end[k]; ++q)
+                        if (q != self[k]) I += rec[q].w;
+                } else {
+                    for (uint32_t q = beg[k]; q < end[k]; ++q) {
+                        if (q == self[k]) continue;
+                        const float4 rk = rec[q];
+                        const float dx = rk.x - rx[k].x, dy = rk.y - rx[k].y;
+                        const float d2 = fmaf(dx, dx, dy * dy);
+                        I = fmaf(rk.z, d2d_gain<PLE2>(d2, P.neg_half_ple), I);
+                        dmin2 = fminf(dmin2, d2);
+                    }
+                }
+                const float dxo = tx[k].x - rx[k].x, dyo = tx[k].y - rx[k].y;
+                const float2 sBk = link_sB(j, cue[k]);
+                o = d2d_link_epilogue<PLE2>((int)pw[k], pl[k], lg[k], gown[k], I, link_cA(j, cue[k]), sBk, P);
+                if (D2D_RESCUE_ENABLED && d2d_needs_rescue<true>(o, fminf(dmin2, fmaf(dxo, dxo, dyo * dyo)), P)) {
+                    // fp64 pass (d2d_common.cuh; same policy as d2d_rescue_warp): ~0.2 % of the links, i.e. about one per dense
+                    // env, so it works from the RB's records in shared memory - positions are exact in fp64 unless a shadow is
+                    // bound - and patches only what fp32 cannot deliver
+                    const double2 *pe64 = P.pos64 ? reinterpret_cast<const double2 *>(P.pos64) + (int64_t)e * V : nullptr;
+                    const bool exact = pe64 != nullptr;
+                    const double2 rxd = exact ? pe64[d2d_rx_dev((int)j, (int)C)] : make_double2((double)rx[k].x, (double)rx[k].y);
+                    const double2 txd = exact ? pe64[d2d_tx_dev((int)j, (int)C)] : make_double2((double)tx[k].x, (double)tx[k].y);
+                    double I64 = 0.0;
+                    for (uint32_t q = beg[k]; q < end[k]; ++q) {
+                        if (q == self[k]) continue;
+                        const uint32_t wk = who[q], kk = wk & 0xffffu;
+                        const float4 rk = rec[q];
+                        const double2 tk = exact ? pe64[d2d_tx_dev((int)kk, (int)C)] : make_double2((double)rk.x, (double)rk.y);
+                        const double ex = tk.x - rxd.x, ey = tk.y - rxd.y;
+                        I64 += P.pwr_lin_d[wk >> 16] * P.linkD[kk].t_lin * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, P.ple_d);
+                    }
+                    const D2DLinkD Lj = P.linkD[j];
+                    const double ex = txd.x - rxd.x, ey = txd.y - rxd.y;
+                    const double Sg = P.pwr_lin_d[pw[k]] * Lj.a_lin * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, P.ple_d);
+                    const double r = Sg * d2d_rcp_f64(fma(I64, Lj.inv_noise, 1.0));
+                    const bool r1 = fabs(r - 1.0) < 0.0625, s1 = fabs(Sg - 1.0) < 0.0625;
+                    double sinr = (double)o.sinr_dB;
+                    if (exact || r1) { sinr = r1 ? d2d_db_near1(r) : 4.3429448190325182765 * d2d_ln_f64(r); o.sinr_dB = (float)sinr; }
+                    if (exact || s1) o.snr_dB = (float)(s1 ? d2d_db_near1(Sg) : 4.3429448190325182765 * d2d_ln_f64(Sg));
+                    if (exact || (r1 && fabsf(sBk.x) < 0.5f)) {
+                        const double rate = sinr > (double)sBk.x ? 1.4426950408889634074 * d2d_ln_f64(1.0 + r) : 0.0;
+                        o.rate = (float)rate; o.cap = (float)(Lj.bw_MHz * rate);
+                    }
+                    ++resc;
+                }
+                cap_part += o.cap;
+                ++n_act;
+                bad |= cue[k] && side[k] && o.cap <= P.min_cap;      // envs/reward_fn.py:30-39
+            }
+            if (has[k]) {
+                const uint32_t gi = e * N + j;
+                if (P.obs) {
+                    float2 *ob = reinterpret_cast<float2 *>(reinterpret_cast<char *>(P.obs) + (uint64_t)gi * 24u);
+                    ob[0] = tx[k];                                   // an absent agent's row keeps its positions (sinr = snr = 0)
+                    ob[1] = rx[k];
+                    ob[2] = make_float2(o.sinr_dB, o.snr_dB);
+                }
+                if (P.cap) P.cap[gi] = o.cap;
+                if (P.rate) P.rate[gi] = o.rate;
+                if (P.rb_out) P.rb_out[gi] = live[k] ? (int16_t)rb[k] : (int16_t)0;
+                if (P.pwr_out) P.pwr_out[gi] = live[k] ? (int16_t)pw[k] : (int16_t)0;
+            }
+        }
+
+        // ---- block reduction for the reward (envs/reward_fn.py:27-44); the env's owner thread keeps the scalars ------------
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) cap_part += __shfl_xor_sync(0xffffffffu, cap_part, s);
+        const uint32_t n_act_w = __reduce_add_sync(0xffffffffu, n_act), resc_w = __reduce_add_sync(0xffffffffu, resc);
+        float *rd = red + (e & 1u) * 32u;                                // double-buffered: no barrier after the owner's read
+        if (lane == 0) { rd[warp] = cap_part; rd[8 + warp] = (float)n_act_w; rd[16 + warp] = (float)resc_w; }
+        const int any_bad = __syncthreads_or(bad ? 1 : 0);
+        if (tid == g) {
+            float cs = 0.f, na = 0.f, rs = 0.f;
+#pragma unroll
+            for (int w2 = 0; w2 < D2D_BLOCK_THREADS / 32; ++w2) { cs += rd[w2]; na += rd[8 + w2]; rs += rd[16 + w2]; }
+            const float reward = any_bad ? -1.0f : cs / na;
+            rew_keep = reward;
+            st_reward += reward; st_cap += cs; st_reward2 = fmaf(reward, reward, st_reward2);
+            st_pen += any_bad ? 1.f : 0.f; st_resc += rs; st_n += 1.f;
+        }
+        if (g == D2D_BLOCK_THREADS - 1u || e + 1u == e_end) {
+            // envs/d2d_env.py:65,68 for the whole group: num_steps += 1; done = num_steps >= EPISODE_LENGTH
+            if (tid <= g) {
+                const uint32_t eg = e - g + tid;
+                const int ns = min(ns_keep + 1, 255);
+                if (P.step_count) P.step_count[eg] = (uint8_t)ns;
+                if (P.reward) P.reward[eg] = rew_keep;
+                if (P.done) P.done[eg] = ns >= P.episode_length ? 1 : 0;
+            }
+            g = 0u;
+        } else {
+            ++g;
+        }
+    }
+
+    if (P.stats) {
+        // block totals of the six statistics -> one fp64 atomic each
+        float v[6] = {st_reward, st_cap, st_reward2, st_n, st_pen, st_resc};
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], s);
+            if (lane == 0) red[i * 8 + warp] = v[i];
+        }
+        __syncthreads();
+        if (tid < 6) {
+            double t = 0.0;
+            for (int w2 = 0; w2 < D2D_BLOCK_THREADS / 32; ++w2) t += (double)red[tid * 8 + w2];
+            if (t != 0.0) atomicAdd(P.stats + (blockIdx.x % D2D_STATS_REPLICAS) * 8 + tid, t);
+        }
     }
 }

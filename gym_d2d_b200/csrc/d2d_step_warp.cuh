@@ -341,28 +341,6 @@ __device__ __forceinline__ float4 d2d_all_pairs_warp(uint32_t lane, uint32_t key
     return make_float4(IA, IB, dminA, dminB);
 }
 
-// 1 / x in fp64 from the fp32 reciprocal and three Newton steps (x normal, > 0): no division subroutine
-__device__ __forceinline__ double d2d_rcp_f64(double x) {
-    double y = (double)d2d_rcp((float)x);
-    y = fma(y, fma(-x, y, 1.0), y);
-    y = fma(y, fma(-x, y, 1.0), y);
-    y = fma(y, fma(-x, y, 1.0), y);
-    return y;
-}
-template <bool PLE2>
-__device__ __forceinline__ double d2d_gain_f64_fast(double d2, double ple) {
-    if (PLE2) return d2d_rcp_f64(d2);
-    return d2d_exp_f64(-0.5 * ple * d2d_ln_f64(d2));
-}
-// ln(x) in fp64.  |x - 1| < 1/16 - every value the fp32 trigger sends here unless an fp64 position shadow is bound -
-// needs no exponent split and five series terms; everything else takes the general d2d_ln_f64.
-// 10 log10(x) in fp64 for |x - 1| < 1/16: no exponent split, five series terms
-__device__ __forceinline__ double d2d_db_near1(double x) {
-    const double s = (x - 1.0) * d2d_rcp_f64(x + 1.0), s2 = s * s;      // |s| < 1/31: s^11 / 11 < 1e-17
-    double q = 1.0 / 9.0;
-    q = fma(q, s2, 1.0 / 7.0); q = fma(q, s2, 1.0 / 5.0); q = fma(q, s2, 1.0 / 3.0); q = fma(q, s2, 1.0);
-    return 8.6858896380650365530 * s * q;                               // 2 * 10 / ln 10
-}
 __device__ __forceinline__ double d2d_shfl_f64(double v, int src) {
     return __hiloint2double(__shfl_sync(0xffffffffu, __double2hiint(v), src), __shfl_sync(0xffffffffu, __double2loint(v), src));
 }
