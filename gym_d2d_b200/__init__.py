@@ -10,7 +10,7 @@ plus the batched tensor API `VecD2DEnv(num_envs, env_config)`.  The arithmetic r
 library (gym_d2d_b200/libd2d_b200.so, C ABI in include/d2d_b200.h); there is no CPU fallback.
 """
 from .config import EPISODE_LENGTH, EnvConfig  # noqa: F401
-from .plugins import (CostHataPathLoss, CueSinrShannonRewardFunction, DownlinkTrafficModel,  # noqa: F401
+from .plugins import (AreaType, CostHataPathLoss, CueSinrShannonRewardFunction, DownlinkTrafficModel,  # noqa: F401
                       FreeSpacePathLoss, LinearObsFunction, LogDistancePathLoss, ShadowingPathLoss,
                       ShannonRewardFunction, SystemCapacityRewardFunction, UnsupportedPluginError,
                       UplinkTrafficModel)

@@ -10,14 +10,14 @@ from pathlib import Path
 
 from .build import LIB
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 STATS_REPLICAS = 32
 NUM_STATS = 8
 STAT_NAMES = ('sum_reward', 'sum_capacity_mbps', 'sum_reward_sq', 'env_steps', 'penalties', 'rescues')
 
-PL_LOG_DISTANCE, PL_FREE_SPACE = 0, 1
+PL_LOG_DISTANCE, PL_FREE_SPACE, PL_COST_HATA = 0, 1, 2
 OBS_LINEAR = 0
-REWARD_SYSTEM_CAPACITY = 0
+REWARD_SYSTEM_CAPACITY, REWARD_SHANNON, REWARD_CUE_SINR_SHANNON = 0, 1, 2
 LINK_UPLINK, LINK_DOWNLINK, LINK_SIDELINK = 1, 2, 3
 
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_STATE = 0, -1, -2, -3, -4
@@ -30,19 +30,19 @@ class D2DConfig(C.Structure):
                 ('path_loss_model', C.c_int32), ('obs_fn', C.c_int32), ('reward_fn', C.c_int32),
                 ('reserved0', C.c_int32),
                 ('carrier_freq_GHz', C.c_double), ('ple', C.c_double), ('cell_radius_m', C.c_double),
-                ('d2d_radius_m', C.c_double), ('min_capacity_mbps', C.c_double)]
+                ('d2d_radius_m', C.c_double), ('min_capacity_mbps', C.c_double), ('reward_param', C.c_double)]
 
 
 class D2DLink(C.Structure):
     _fields_ = [('tx_eirp_offset_dB', C.c_double), ('rx_offset_dB', C.c_double), ('rx_noise_dBm', C.c_double),
                 ('rx_sensitivity_dBm', C.c_double), ('tx_rb_bandwidth_kHz', C.c_double),
-                ('link_type', C.c_int32), ('reserved0', C.c_int32)]
+                ('link_type', C.c_int32), ('reserved0', C.c_int32), ('path_loss_const_dB', C.c_double)]
 
 
 class D2DStepIO(C.Structure):
     _fields_ = [('actions', C.c_void_p), ('obs', C.c_void_p), ('capacity_mbps', C.c_void_p),
                 ('reward', C.c_void_p), ('done', C.c_void_p), ('rate_bps', C.c_void_p),
-                ('rb', C.c_void_p), ('tx_pwr_dBm', C.c_void_p)]
+                ('rb', C.c_void_p), ('tx_pwr_dBm', C.c_void_p), ('agent_reward', C.c_void_p)]
 
 
 class D2DError(RuntimeError):

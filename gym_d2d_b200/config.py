@@ -14,7 +14,7 @@ from pathlib import Path
 from typing import Any, Dict, List, Optional, Tuple
 
 from . import _lib
-from .plugins import (LogDistancePathLoss, UplinkTrafficModel, resolve_path_loss)
+from .plugins import (LogDistancePathLoss, UnsupportedPluginError, UplinkTrafficModel, cost_hata_terms, resolve_path_loss)
 
 EPISODE_LENGTH = 10                 # envs/d2d_env.py:16
 BASE_STATION_ID = 'mbs'             # simulator.py:15
@@ -129,9 +129,29 @@ def _rx_offset(cfg: dict, is_bs: bool) -> float:
     return off - cfg['cable_loss_dB'] + cfg['masthead_amplifier_gain_dB'] if is_bs else off - cfg['body_loss_dB']
 
 
+def cost_hata_fold(config: EnvConfig) -> Optional[Tuple[float, Dict[str, float]]]:
+    """CostHataPathLoss (path_loss.py:90-123) as (ple, {receiver device id: K_dB}), or None for the other models.  The
+    exponent depends on the transmitter's antenna height, so every transmitter must share one height (they are all
+    UserEquipments on the uplink + sidelink path; a device_config_file may still move receivers' heights freely)."""
+    pl_enum, area = resolve_path_loss(config.path_loss_model)
+    if pl_enum != _lib.PL_COST_HATA:
+        return None
+    dev_cfg = config.device_configs()
+    tx_heights = {float(dev_cfg[tx]['antenna_height_m']) for tx, _ in config.link_ids()}
+    if len(tx_heights) != 1:
+        raise UnsupportedPluginError('CostHataPathLoss: the CUDA path needs one antenna height for all transmitters, got '
+                                     f'{sorted(tx_heights)}')
+    h_tx = tx_heights.pop()
+    ple, consts = 0.0, {}
+    for _, rx in config.link_ids():
+        ple, consts[rx] = cost_hata_terms(float(config.carrier_freq_GHz), int(area), h_tx, float(dev_cfg[rx]['antenna_height_m']))
+    return ple, consts
+
+
 def link_table(config: EnvConfig) -> List[dict]:
     """One dict per link (canonical order) with the fields of d2d_link_t."""
     dev_cfg = config.device_configs()
+    hata = cost_hata_fold(config)
     rows = []
     for j, (tx_id, rx_id) in enumerate(config.link_ids()):
         tx, rx = dev_cfg[tx_id], dev_cfg[rx_id]
@@ -142,13 +162,17 @@ def link_table(config: EnvConfig) -> List[dict]:
             rx_noise_dBm=float(rx['thermal_noise_dBm']),                                               # device.py:117-119
             rx_sensitivity_dBm=float(rx['noise_figure_dB'] + rx['thermal_noise_dBm'] + rx['sinr_dB']),   # device.py:74-80
             tx_rb_bandwidth_kHz=float(int(tx['num_subcarriers']) * int(tx['subcarrier_spacing_kHz'])),   # device.py:85-95
-            link_type=_lib.LINK_UPLINK if j < config.num_cues else _lib.LINK_SIDELINK))
+            link_type=_lib.LINK_UPLINK if j < config.num_cues else _lib.LINK_SIDELINK,
+            path_loss_const_dB=float(hata[1][rx_id]) if hata else 0.0))
     return rows
 
 
 def to_c_config(config: EnvConfig, num_envs: int, cuda_device: int, obs_enum: int, reward_enum: int,
-                min_capacity_mbps: float) -> '_lib.D2DConfig':
+                reward_param: float) -> '_lib.D2DConfig':
     pl_enum, ple = resolve_path_loss(config.path_loss_model)
+    hata = cost_hata_fold(config)
+    if hata:
+        ple = hata[0]
     npw = config.num_pwr_actions
     for name in ('num_rbs', 'num_cues', 'num_due_pairs'):
         v = getattr(config, name)
@@ -160,4 +184,5 @@ def to_c_config(config: EnvConfig, num_envs: int, cuda_device: int, obs_enum: in
                           path_loss_model=pl_enum, obs_fn=obs_enum, reward_fn=reward_enum,
                           carrier_freq_GHz=float(config.carrier_freq_GHz), ple=ple,
                           cell_radius_m=float(config.cell_radius_m), d2d_radius_m=float(config.d2d_radius_m),
-                          min_capacity_mbps=float(min_capacity_mbps))
+                          min_capacity_mbps=float(reward_param) if reward_enum == _lib.REWARD_SYSTEM_CAPACITY else 0.0,
+                          reward_param=float(reward_param))

@@ -64,7 +64,7 @@ struct d2d_handle {
     uint8_t *step_count = nullptr;
     double *stats = nullptr;
     // staging for d2d_step_host / d2d_set_positions (handle-owned, allocated on first use)
-    void *stage2[2][8] = {};
+    void *stage2[2][9] = {};
     cudaStream_t s_in = nullptr, s_out = nullptr;
     cudaEvent_t ev_in[2] = {}, ev_kernel[2] = {}, ev_out[2] = {};
     bool slot_used[2] = {false, false};
@@ -113,6 +113,7 @@ D2DParams make_params(const d2d_handle *h, const d2d_step_io_t *io) {
     P.us_cue = make_float2(h->us_cue[0], h->us_cue[1]);
     P.us_due = make_float2(h->us_due[0], h->us_due[1]);
     P.uniform = h->uniform ? 1 : 0;
+    P.reward_fn = h->cfg.reward_fn;
     P.ple_d = h->ple;
     P.linkA = h->dA; P.linkB = h->dB; P.linkD = h->dD; P.pwr_lin = h->dPwr; P.pwr_lin_d = h->dPwrD;
     P.pos = h->pos; P.pos64 = h->pos64; P.step_count = h->step_count; P.stats = h->stats;
@@ -204,11 +205,13 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
     if (cfg->n_pwr_cue < 1 || cfg->n_pwr_due < 1 || cfg->n_pwr_cue > D2D_MAX_PWR_LEVELS || cfg->n_pwr_due > D2D_MAX_PWR_LEVELS)
         return fail(D2D_ERR_UNSUPPORTED, "d2d_create: power levels per link must be in [1, 128]");
     if (cfg->num_rbs > 32767) return fail(D2D_ERR_UNSUPPORTED, "d2d_create: num_rbs must be <= 32767");
-    if (cfg->path_loss_model != D2D_PL_LOG_DISTANCE && cfg->path_loss_model != D2D_PL_FREE_SPACE)
-        return fail(D2D_ERR_UNSUPPORTED, "d2d_create: unsupported path_loss_model (LogDistance / FreeSpace only)");
+    if (cfg->path_loss_model != D2D_PL_LOG_DISTANCE && cfg->path_loss_model != D2D_PL_FREE_SPACE &&
+        cfg->path_loss_model != D2D_PL_COST_HATA)
+        return fail(D2D_ERR_UNSUPPORTED, "d2d_create: unsupported path_loss_model (LogDistance / FreeSpace / CostHata only)");
     if (cfg->obs_fn != D2D_OBS_LINEAR) return fail(D2D_ERR_UNSUPPORTED, "d2d_create: unsupported obs_fn (LinearObsFunction only)");
-    if (cfg->reward_fn != D2D_REWARD_SYSTEM_CAPACITY)
-        return fail(D2D_ERR_UNSUPPORTED, "d2d_create: unsupported reward_fn (SystemCapacityRewardFunction only)");
+    if (cfg->reward_fn != D2D_REWARD_SYSTEM_CAPACITY && cfg->reward_fn != D2D_REWARD_SHANNON &&
+        cfg->reward_fn != D2D_REWARD_CUE_SINR_SHANNON)
+        return fail(D2D_ERR_UNSUPPORTED, "d2d_create: unsupported reward_fn (SystemCapacity / Shannon / CueSinrShannon only)");
     if (!(cfg->carrier_freq_GHz > 0.0)) return fail(D2D_ERR_INVALID_ARG, "d2d_create: carrier_freq_GHz must be > 0");
     const double ple = cfg->path_loss_model == D2D_PL_FREE_SPACE ? 2.0 : cfg->ple;
     if (!(ple > 0.0) || ple > 8.0) return fail(D2D_ERR_INVALID_ARG, "d2d_create: ple must be in (0, 8]");
@@ -248,18 +251,21 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
         if (L.link_type != expect)
             return bail(fail(D2D_ERR_UNSUPPORTED, "d2d_create: link " + std::to_string(j) +
                                                       " has an unsupported link_type (CUE uplinks then DUE sidelinks)"));
-        A[j].tx_lin0 = (float)std::pow(10.0, (L.tx_eirp_offset_dB - h->K_dB) / 10.0);
-        const double snr0 = L.tx_eirp_offset_dB + L.rx_offset_dB - h->K_dB - L.rx_noise_dBm;
+        // the path-loss constant K belongs to the RECEIVER (CostHata: A(h_tx, h_rx) - 3 B; log-distance: one K for all), so it
+        // is folded into the victim's constants and the radiated weights w carry none: I_true = 10^(-K_rx/10) sum w_k g_k
+        const double Kj = cfg->path_loss_model == D2D_PL_COST_HATA ? L.path_loss_const_dB : h->K_dB;
+        A[j].tx_lin0 = (float)std::pow(10.0, L.tx_eirp_offset_dB / 10.0);
+        const double snr0 = L.tx_eirp_offset_dB + L.rx_offset_dB - Kj - L.rx_noise_dBm;
         A[j].a_lin = (float)std::pow(10.0, snr0 / 10.0);
-        A[j].inv_noise = (float)std::pow(10.0, -L.rx_noise_dBm / 10.0);
+        A[j].inv_noise = (float)std::pow(10.0, -(Kj + L.rx_noise_dBm) / 10.0);
         A[j].snr0_dB = (float)snr0;
         B[j].sens_dBm = (float)L.rx_sensitivity_dBm;
         B[j].bw_MHz = (float)(1e-6 * (L.tx_rb_bandwidth_kHz * 1000.0));
         B[j].tx_dev = cue ? 1 + j : 1 + cfg->num_cues + 2 * (j - cfg->num_cues);
         B[j].rx_dev = cue ? 0 : B[j].tx_dev + 1;
         Dv[j].a_lin = std::pow(10.0, snr0 / 10.0);
-        Dv[j].t_lin = std::pow(10.0, (L.tx_eirp_offset_dB - h->K_dB) / 10.0);
-        Dv[j].inv_noise = std::pow(10.0, -L.rx_noise_dBm / 10.0);
+        Dv[j].t_lin = std::pow(10.0, L.tx_eirp_offset_dB / 10.0);
+        Dv[j].inv_noise = std::pow(10.0, -(Kj + L.rx_noise_dBm) / 10.0);
         Dv[j].bw_MHz = 1e-6 * (L.tx_rb_bandwidth_kHz * 1000.0);
     }
     // one set of constants per link type (no per-device overrides)?  Then the default-shape kernel reads them from
@@ -309,7 +315,7 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
         // launch shape by batch size (d2d_step_warp.cuh): about one wave of envs -> 4-warp blocks, many waves -> 8-warp blocks
         h->wpb = cfg->num_envs >= 32768 ? 8 : 4;
         if (const char *w = std::getenv("D2D_B200_WPB")) h->wpb = std::atoi(w) == 8 ? 8 : 4;
-        h->spec = h->ple2 && h->uniform && cfg->num_rbs == 25 && cfg->num_cues == 25 && cfg->num_due_pairs == 25 && cfg->n_pwr_cue == 24 &&
+        h->spec = h->ple2 && h->uniform && cfg->path_loss_model != D2D_PL_COST_HATA && cfg->num_rbs == 25 && cfg->num_cues == 25 && cfg->num_due_pairs == 25 && cfg->n_pwr_cue == 24 &&
                   cfg->n_pwr_due == 21;
         if (const char *sp = std::getenv("D2D_B200_SPEC")) h->spec = h->spec && std::atoi(sp) != 0;   // tests: force the generic shape
         const size_t smem = d2d_warp_smem_bytes(cfg->num_rbs, h->wpb);
@@ -486,6 +492,28 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, void *stream) {
         ++h->launches;
     }
     D2D_CUDA(cudaGetLastError());
+    // per-agent rewards (SHANNON / CUE_SINR_SHANNON always; SYSTEM_CAPACITY when the caller asked for the broadcast): one more
+    // small kernel over the T x E env-steps just written
+    if (h->cfg.reward_fn != D2D_REWARD_SYSTEM_CAPACITY || io->agent_reward) {
+        if (!io->obs || !io->reward)
+            return fail(D2D_ERR_INVALID_ARG, "per-agent rewards need the obs and reward outputs");
+        const int64_t total = (int64_t)T * h->cfg.num_envs;
+        const bool warp_team = h->N <= 64;
+        const int teams = warp_team ? 8 : 1;
+        const int grid = (int)std::min<int64_t>((total + teams - 1) / teams, (int64_t)h->num_sms * 8);
+        const size_t smem = (size_t)teams * h->cfg.num_rbs * sizeof(uint32_t);
+        double *stats = h->cfg.reward_fn != D2D_REWARD_SYSTEM_CAPACITY ? h->stats : nullptr;
+        if (warp_team)
+            d2d_agent_reward_kernel<32><<<grid, 256, smem, st>>>(io->actions, io->obs, io->agent_reward, io->reward, stats, total, h->N,
+                                                                h->cfg.num_cues, h->cfg.num_rbs, h->cfg.n_pwr_cue, h->cfg.n_pwr_due,
+                                                                h->cfg.reward_fn, (float)h->cfg.reward_param);
+        else
+            d2d_agent_reward_kernel<256><<<grid, 256, smem, st>>>(io->actions, io->obs, io->agent_reward, io->reward, stats, total, h->N,
+                                                                 h->cfg.num_cues, h->cfg.num_rbs, h->cfg.n_pwr_cue, h->cfg.n_pwr_due,
+                                                                 h->cfg.reward_fn, (float)h->cfg.reward_param);
+        D2D_CUDA(cudaGetLastError());
+        ++h->launches;
+    }
     return D2D_OK;
 }
 
@@ -522,6 +550,7 @@ D2D_API int d2d_step_many(d2d_handle_t *h, const d2d_step_io_t *io, int32_t num_
         if (cur.rate_bps) cur.rate_bps += dl;
         if (cur.rb) cur.rb += dl;
         if (cur.tx_pwr_dBm) cur.tx_pwr_dBm += dl;
+        if (cur.agent_reward) cur.agent_reward += dl;
     }
     return D2D_OK;
 }
@@ -553,10 +582,11 @@ D2D_API int d2d_step_host_async(d2d_handle_t *h, const d2d_step_io_t *hio, int s
     rc = host_pipeline_init(h);
     if (rc) return rc;
     const size_t E = (size_t)h->cfg.num_envs, EN = E * h->N;
-    const size_t bytes[8] = {EN * 4, EN * 24, EN * 4, E * 4, E, EN * 4, EN * 2, EN * 2};
-    void *host[8] = {(void *)hio->actions, hio->obs, hio->capacity_mbps, hio->reward, hio->done, hio->rate_bps, hio->rb, hio->tx_pwr_dBm};
+    const size_t bytes[9] = {EN * 4, EN * 24, EN * 4, E * 4, E, EN * 4, EN * 2, EN * 2, EN * 4};
+    void *host[9] = {(void *)hio->actions, hio->obs, hio->capacity_mbps, hio->reward, hio->done, hio->rate_bps, hio->rb, hio->tx_pwr_dBm,
+                     hio->agent_reward};
     void **stage = h->stage2[slot];
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 9; ++i)
         if (host[i] && !stage[i]) D2D_CUDA(cudaMalloc(&stage[i], bytes[i]));
     cudaStream_t st = (cudaStream_t)stream;
     // copy-in: this slot's action staging is free once the kernel that last read it has run
@@ -576,12 +606,13 @@ D2D_API int d2d_step_host_async(d2d_handle_t *h, const d2d_step_io_t *hio, int s
     dio.rate_bps = hio->rate_bps ? (float *)stage[5] : nullptr;
     dio.rb = hio->rb ? (int16_t *)stage[6] : nullptr;
     dio.tx_pwr_dBm = hio->tx_pwr_dBm ? (int16_t *)stage[7] : nullptr;
+    dio.agent_reward = hio->agent_reward ? (float *)stage[8] : nullptr;
     rc = d2d_step(h, &dio, stream);
     if (rc) return rc;
     D2D_CUDA(cudaEventRecord(h->ev_kernel[slot], st));
     // copy-out
     D2D_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_kernel[slot], 0));
-    for (int i = 1; i < 8; ++i)
+    for (int i = 1; i < 9; ++i)
         if (host[i]) D2D_CUDA(cudaMemcpyAsync(host[i], stage[i], bytes[i], cudaMemcpyDeviceToHost, h->s_out));
     D2D_CUDA(cudaEventRecord(h->ev_out[slot], h->s_out));
     h->slot_used[slot] = true;

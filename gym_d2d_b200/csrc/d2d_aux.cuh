@@ -95,3 +95,83 @@ __global__ void d2d_per_agent_obs_kernel(const float *__restrict__ table, float 
         dst[m] = src[link * 3 + part];
     }
 }
+
+
+// Per-agent rewards from a step's results, one TEAM of threads per env (a warp for N <= 64, a block beyond):
+//   mode 0  SystemCapacityRewardFunction's scalar broadcast to the acting agents (envs/reward_fn.py:44)
+//   mode 1  ShannonRewardFunction (envs/reward_fn.py:47-57): log2(1 + 10^(sinr/10)) if sinr >= param else -1
+//   mode 2  CueSinrShannonRewardFunction (envs/reward_fn.py:60-78): -1 if some OTHER action on the agent's RB is a
+//           non-SIDELINK link with sinr < param, else log2(1 + 10^(sinr/10))
+// Reads the decoded step results (sinr_dB from the observation table - after the fp64 pass, so threshold decisions see the
+// rescued values) and re-derives the RB from the raw action (envs/d2d_env.py:93-101).  For modes 1 / 2 reward[e] becomes
+// the mean agent reward and the reward statistics are accumulated here (the step kernel skips them).
+template <int TEAM>
+__global__ void d2d_agent_reward_kernel(const int32_t *__restrict__ actions, const float *__restrict__ obs,
+                                        float *__restrict__ agent_reward, float *__restrict__ reward, double *__restrict__ stats,
+                                        int64_t num_envs, int N, int C, int R, int n_pwr_cue, int n_pwr_due, int mode, float param) {
+    extern __shared__ uint32_t d2d_weak_smem[];
+    const int teams = blockDim.x / TEAM, team = threadIdx.x / TEAM, tl = threadIdx.x % TEAM;
+    uint32_t *weak = d2d_weak_smem + (size_t)team * R;
+    auto team_sync = [&]() { if (TEAM == 32) __syncwarp(); else __syncthreads(); };
+    float st_r = 0.f, st_r2 = 0.f;
+    const int64_t rounds = (num_envs + (int64_t)gridDim.x * teams - 1) / ((int64_t)gridDim.x * teams);
+    for (int64_t it = 0; it < rounds; ++it) {
+        const int64_t e = (it * gridDim.x + blockIdx.x) * teams + team;
+        const bool in = e < num_envs;                 // whole teams drop out together; barriers stay uniform per block
+        const int32_t *act = actions + (in ? e : 0) * N;
+        const float *ob = obs + (in ? e : 0) * N * 6;
+        if (mode == 2) {
+            for (int r = tl; r < R; r += TEAM) weak[r] = 0u;
+            team_sync();
+            for (int j = tl; in && j < N; j += TEAM) {
+                const int npw = j < C ? n_pwr_cue : n_pwr_due;
+                const uint32_t a = (uint32_t)act[j];
+                if (j < C && a < (uint32_t)(R * npw) && ob[j * 6 + 4] < param) atomicAdd(&weak[a / (uint32_t)npw], 1u);
+            }
+            team_sync();
+        }
+        float sum = 0.f;
+        int n_act = 0;
+        for (int j = tl; in && j < N; j += TEAM) {
+            const int npw = j < C ? n_pwr_cue : n_pwr_due;
+            const uint32_t a = (uint32_t)act[j];
+            const bool live = a < (uint32_t)(R * npw);
+            float rw = 0.f;
+            if (live) {
+                const float sinr = ob[j * 6 + 4];
+                const float shannon = d2d_log2_1p(d2d_ex2(sinr * 0.33219280948873623f));     // log2(1 + 10^(sinr/10))
+                if (mode == 0) rw = reward[e];
+                else if (mode == 1) rw = sinr >= param ? shannon : -1.0f;
+                else rw = weak[a / (uint32_t)npw] - ((j < C && sinr < param) ? 1u : 0u) > 0u ? -1.0f : shannon;
+                sum += rw;
+                ++n_act;
+            }
+            if (agent_reward) agent_reward[e * N + j] = rw;
+        }
+        if (mode != 0) {
+            // mean over the acting agents -> reward[e]; team reduction through the warp, then shared memory for blocks
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, s); n_act += __shfl_xor_sync(0xffffffffu, n_act, s); }
+            if (TEAM > 32) {
+                __shared__ float red_s[8];
+                __shared__ int red_n[8];
+                team_sync();
+                if ((tl & 31) == 0) { red_s[tl >> 5] = sum; red_n[tl >> 5] = n_act; }
+                team_sync();
+                sum = 0.f; n_act = 0;
+                for (int w = 0; w < TEAM / 32; ++w) { sum += red_s[w]; n_act += red_n[w]; }
+            }
+            if (in && tl == 0) {
+                const float r = n_act ? sum / (float)n_act : 0.f;
+                reward[e] = r;
+                st_r += r; st_r2 = fmaf(r, r, st_r2);
+            }
+        }
+        team_sync();
+    }
+    if (mode != 0 && stats && tl == 0 && (st_r != 0.f || st_r2 != 0.f)) {
+        double *dst = stats + ((blockIdx.x * teams + team) % 32) * 8;
+        atomicAdd(dst + 0, (double)st_r);
+        atomicAdd(dst + 2, (double)st_r2);
+    }
+}

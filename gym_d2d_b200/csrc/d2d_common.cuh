@@ -54,6 +54,7 @@ struct D2DParams {
     int32_t episode_length;
     int32_t nbins;               // block kernel: number of RB bins
     int32_t align4;              // warp kernel: every env's DUE (tx, rx) pair is a 16-byte aligned float4
+    int32_t reward_fn;           // d2d_reward_fn: per-agent reward functions take their reward statistics from the post-pass kernel
     int32_t uniform;             // every CUE link shares one set of constants, and every DUE link (u_cue / u_due below)
     int32_t T;                   // d2d_step_many: steps per env in this launch (1 for d2d_step)
     int64_t t_stride;            // d2d_step_many: envs between consecutive step slices of the io buffers

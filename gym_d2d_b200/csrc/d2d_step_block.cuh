@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_generic_kern
             if (P.step_count) P.step_count[e] = (uint8_t)ns;
             if (P.reward) P.reward[e] = reward;
             if (P.done) P.done[e] = ns >= P.episode_length ? 1 : 0;
-            st_reward += reward; st_cap += cs; st_reward2 += (double)reward * reward;
+            if (P.reward_fn == 0) { st_reward += reward; st_reward2 += (double)reward * reward; }
+            st_cap += cs;
             st_pen += any_bad ? 1.0 : 0.0; st_resc += rs; st_n += 1.0;
         }
         __syncthreads();
@@ -432,7 +433,8 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS, LPT <= 2 ? 4 : 3) d2d_step_
             for (int w2 = 0; w2 < D2D_BLOCK_THREADS / 32; ++w2) { cs += rd[w2]; na += rd[8 + w2]; rs += rd[16 + w2]; }
             const float reward = any_bad ? -1.0f : cs / na;
             rew_keep = reward;
-            st_reward += reward; st_cap += cs; st_reward2 = fmaf(reward, reward, st_reward2);
+            if (P.reward_fn == 0) { st_reward += reward; st_reward2 = fmaf(reward, reward, st_reward2); }
+            st_cap += cs;
             st_pen += any_bad ? 1.f : 0.f; st_resc += rs; st_n += 1.f;
         }
         if (g == D2D_BLOCK_THREADS - 1u || e + 1u == e_end) {

@@ -632,7 +632,8 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
                 if (!MANY && (FULL || P.done)) P.done[eg] = ns >= P.episode_length ? 1 : 0;
             }
         }
-        st_reward += reward; st_cap += cap_sum; st_reward2 = fmaf(reward, reward, st_reward2);
+        if (P.reward_fn == 0) { st_reward += reward; st_reward2 = fmaf(reward, reward, st_reward2); }
+        st_cap += cap_sum;
         st_pen += bad ? 1u : 0u;
 
         // ---- rare: fp64 recomputation of flagged links, after the env's outputs are stored ----------------------------------

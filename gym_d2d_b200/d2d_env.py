@@ -133,8 +133,11 @@ class D2DEnv:
         self.actions = self._actions_view(keys)
         self.state = self._state(keys)
         obs = self._obs_dict(keys)
-        reward = float(self._host['reward'][0])
-        rewards = {k: reward for k in keys}                            # envs/reward_fn.py:44
+        if self.vec.per_agent_reward:                                  # envs/reward_fn.py:47-78: one reward per agent
+            rewards = {k: float(self._host['agent_reward'][0, self._link_index[k]]) for k in keys}
+        else:
+            reward = float(self._host['reward'][0])
+            rewards = {k: reward for k in keys}                        # envs/reward_fn.py:44
         game_over = {'__all__': self.num_steps >= EPISODE_LENGTH}      # envs/d2d_env.py:68
         info = {k: self._info(k) for k in keys}
         return obs, rewards, game_over, info

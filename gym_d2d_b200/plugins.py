@@ -10,8 +10,10 @@ implement yet - is rejected at construction: no Python callback ever runs inside
 """
 from __future__ import annotations
 
+import enum
 import functools
-from typing import Any, Tuple
+import math
+from typing import Any, Dict, Tuple
 
 from . import _lib
 
@@ -49,8 +51,37 @@ class ShadowingPathLoss(PathLoss):      # path_loss.py:69-81 (stochastic per eva
     pass
 
 
-class CostHataPathLoss(PathLoss):       # path_loss.py:90-123 - not implemented
-    pass
+class AreaType(enum.Enum):
+    """path_loss.py:84-87."""
+    RURAL = 0
+    SUBURBAN = 1
+    URBAN = 2
+
+
+class CostHataPathLoss(PathLoss):
+    """path_loss.py:90-123: Lb = 46.3 + 33.9 log10(f) - 13.82 log10(h_tx) - a(h_rx, f) + (44.9 - 6.55 log10(h_tx)) log10(d_km) + C.
+
+    With one transmitter antenna height (every transmitter of the uplink + sidelink step path is a UserEquipment) this is
+    a log-distance law: exponent ple = (44.9 - 6.55 log10(h_tx)) / 10 and a constant that depends on the RECEIVER's height.
+    cost_hata_terms() folds both on the host; the kernels run their general-exponent path."""
+    kernel_enum = _lib.PL_COST_HATA
+
+    def __init__(self, carrier_freq_GHz: float, area_type: AreaType = AreaType.SUBURBAN) -> None:
+        super().__init__(carrier_freq_GHz)
+        self.area_type = area_type
+
+
+def cost_hata_terms(carrier_freq_GHz: float, area_type: int, h_tx_m: float, h_rx_m: float) -> Tuple[float, float]:
+    """-> (ple, K_dB) with PL = 10 ple log10(d_m) + K_dB, restating path_loss.py:100-123 for one (h_tx, h_rx) pair."""
+    f = carrier_freq_GHz * 1000.0                                             # :100 MHz
+    if area_type == AreaType.URBAN.value:                                     # :116-120
+        a_hc = 8.29 * math.log10(1.54 * h_rx_m) ** 2 - 1.1 if f >= 200 else 3.2 * math.log10(11.75 * h_rx_m) ** 2 - 4.97
+    else:
+        a_hc = (1.1 * math.log10(f) - 0.7) * h_rx_m - (1.56 * math.log10(f) - 0.8)   # :122
+    c = 3.0 if area_type == AreaType.URBAN.value else 0.0                     # :107
+    b = 44.9 - 6.55 * math.log10(h_tx_m)
+    a = 46.3 + 33.9 * math.log10(f) - 13.82 * math.log10(h_tx_m) - a_hc + c   # :108 without the distance term
+    return b / 10.0, a - 3.0 * b                                              # log10(d_km) = log10(d_m) - 3
 
 
 # ---- observation / reward (envs/obs_fn.py, envs/reward_fn.py) --------------------------------------
@@ -75,12 +106,20 @@ class SystemCapacityRewardFunction(RewardFunction):
         self.min_capacity_mbps = float(min_capacity_mbps)
 
 
-class ShannonRewardFunction(RewardFunction):          # envs/reward_fn.py:47-57 - not implemented
-    pass
+class ShannonRewardFunction(RewardFunction):
+    """envs/reward_fn.py:47-57: per agent log2(1 + 10^(sinr/10)) if sinr >= min_sinr else -1."""
+    kernel_enum = _lib.REWARD_SHANNON
+
+    def __init__(self, min_sinr: float = -70.0) -> None:
+        self.min_sinr = float(min_sinr)
 
 
-class CueSinrShannonRewardFunction(RewardFunction):   # envs/reward_fn.py:60-78 - not implemented
-    pass
+class CueSinrShannonRewardFunction(RewardFunction):
+    """envs/reward_fn.py:60-78: per agent -1 if another action on its RB is a cellular link with sinr < threshold."""
+    kernel_enum = _lib.REWARD_CUE_SINR_SHANNON
+
+    def __init__(self, sinr_threshold_dB: float = 0.0) -> None:
+        self.sinr_threshold_dB = float(sinr_threshold_dB)
 
 
 # ---- traffic models (traffic_model.py): instantiated by the reference but never called (simulator.py:58,78)
@@ -103,12 +142,13 @@ _REFERENCE_MODULES = {
     'reward_fn': ('gym_d2d.envs.reward_fn',),
 }
 _OURS = {
-    'path_loss': {'LogDistancePathLoss': LogDistancePathLoss, 'FreeSpacePathLoss': FreeSpacePathLoss},
+    'path_loss': {'LogDistancePathLoss': LogDistancePathLoss, 'FreeSpacePathLoss': FreeSpacePathLoss,
+                  'CostHataPathLoss': CostHataPathLoss},
     'obs_fn': {'LinearObsFunction': LinearObsFunction},
-    'reward_fn': {'SystemCapacityRewardFunction': SystemCapacityRewardFunction},
+    'reward_fn': {'SystemCapacityRewardFunction': SystemCapacityRewardFunction, 'ShannonRewardFunction': ShannonRewardFunction,
+                  'CueSinrShannonRewardFunction': CueSinrShannonRewardFunction},
 }
-_KNOWN_UNSUPPORTED = {'ShadowingPathLoss', 'CostHataPathLoss', 'ShannonRewardFunction',
-                      'CueSinrShannonRewardFunction'}
+_KNOWN_UNSUPPORTED = {'ShadowingPathLoss'}
 
 
 def _unwrap_partial(obj: Any) -> Tuple[Any, dict]:
@@ -141,8 +181,14 @@ def _resolve(kind: str, obj: Any):
 
 
 def resolve_path_loss(obj: Any) -> Tuple[int, float]:
-    """-> (d2d_path_loss_model enum, path-loss exponent)."""
+    """-> (d2d_path_loss_model enum, path-loss exponent; for CostHata the AreaType value instead of the exponent)."""
     cls, kwargs = _resolve('path_loss', obj)
+    if cls is CostHataPathLoss:
+        extra = set(kwargs) - {'area_type'}
+        if extra:
+            raise UnsupportedPluginError(f'unsupported CostHataPathLoss arguments {sorted(extra)}')
+        area = kwargs.get('area_type', AreaType.SUBURBAN)                     # path_loss.py:91 default
+        return cls.kernel_enum, float(getattr(area, 'value', area))          # ours or the reference's AreaType member
     extra = set(kwargs) - {'ple'}
     if extra:
         raise UnsupportedPluginError(f'unsupported path-loss arguments {sorted(extra)}')
@@ -160,10 +206,18 @@ def resolve_obs_fn(obj: Any) -> int:
     return cls.kernel_enum
 
 
+_REWARD_PARAM: Dict[type, Tuple[str, float]] = {
+    SystemCapacityRewardFunction: ('min_capacity_mbps', 0.0),       # envs/reward_fn.py:23
+    ShannonRewardFunction: ('min_sinr', -70.0),                     # envs/reward_fn.py:48
+    CueSinrShannonRewardFunction: ('sinr_threshold_dB', 0.0),       # envs/reward_fn.py:61
+}
+
+
 def resolve_reward_fn(obj: Any) -> Tuple[int, float]:
-    """-> (d2d_reward_fn enum, min_capacity_mbps)."""
+    """-> (d2d_reward_fn enum, the class's one parameter: min_capacity_mbps / min_sinr / sinr_threshold_dB)."""
     cls, kwargs = _resolve('reward_fn', obj)
-    extra = set(kwargs) - {'min_capacity_mbps'}
+    name, default = _REWARD_PARAM[cls]
+    extra = set(kwargs) - {name}
     if extra:
         raise UnsupportedPluginError(f'unsupported reward_fn arguments {sorted(extra)}')
-    return cls.kernel_enum, float(kwargs.get('min_capacity_mbps', 0.0))   # envs/reward_fn.py:23 default
+    return cls.kernel_enum, float(kwargs.get(name, default))

@@ -25,8 +25,9 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 class StepBuffers:
     """One set of device output tensors of a step (the tensors a d2d_step_io_t points at)."""
 
-    def __init__(self, num_envs: int, num_links: int, device: torch.device, info: bool) -> None:
+    def __init__(self, num_envs: int, num_links: int, device: torch.device, info: bool, agent_reward: bool = False) -> None:
         E, N = num_envs, num_links
+        self.agent_reward = torch.zeros((E, N), dtype=torch.float32, device=device) if agent_reward else None
         self.obs = torch.zeros((E, N, 6), dtype=torch.float32, device=device)
         self.capacity_mbps = torch.zeros((E, N), dtype=torch.float32, device=device)
         self.reward = torch.zeros((E,), dtype=torch.float32, device=device)
@@ -63,6 +64,7 @@ class VecD2DEnv:
         env_config = env_config if env_config is not None else {}
         obs_enum = resolve_obs_fn(env_config.pop('obs_fn', LinearObsFunction))
         reward_enum, min_cap = resolve_reward_fn(env_config.pop('reward_fn', SystemCapacityRewardFunction))
+        self.per_agent_reward = reward_enum != _lib.REWARD_SYSTEM_CAPACITY   # envs/reward_fn.py:47-78 reward every agent separately
         self.config = EnvConfig(**env_config)          # unknown key -> TypeError, like the reference dataclass
         self.num_envs = int(num_envs)
         if self.num_envs < 1:
@@ -125,7 +127,7 @@ class VecD2DEnv:
 
     def alloc_outputs(self) -> StepBuffers:
         """A fresh set of output tensors to pass as step(..., out=...), e.g. one per in-flight step."""
-        return StepBuffers(self.num_envs, self.num_links, self.device, self.want_info)
+        return StepBuffers(self.num_envs, self.num_links, self.device, self.want_info, self.per_agent_reward)
 
     def close(self) -> None:
         if getattr(self, '_h', None):
@@ -204,6 +206,7 @@ class VecD2DEnv:
         io.rate_bps = _ptr(o.rate_bps)
         io.rb = _ptr(o.rb)
         io.tx_pwr_dBm = _ptr(o.tx_pwr_dbm)
+        io.agent_reward = _ptr(o.agent_reward)
         _lib.check(self._lib.d2d_step(self._h, C.byref(io), self._stream()))
 
     def step(self, actions: torch.Tensor, validate: bool = False, out: Optional[StepBuffers] = None
@@ -219,6 +222,8 @@ class VecD2DEnv:
         self._launch(actions, out)
         o = out if out is not None else self._out
         info = {'capacity_mbps': o.capacity_mbps}
+        if o.agent_reward is not None:
+            info['agent_reward'] = o.agent_reward      # [E][N]; `reward` is then its mean over the acting agents
         if self.want_info:
             info.update(rate_bps=o.rate_bps, rb=o.rb, tx_pwr_dbm=o.tx_pwr_dbm,
                         sinr_db=o.obs[..., 4], snr_db=o.obs[..., 5])
@@ -241,7 +246,7 @@ class VecD2DEnv:
             raise ValueError('out was allocated for a different number of steps')
         io = _lib.D2DStepIO(actions=actions.data_ptr(), obs=o['obs'].data_ptr(), capacity_mbps=o['capacity_mbps'].data_ptr(),
                             reward=o['reward'].data_ptr(), done=o['done'].data_ptr(), rate_bps=_ptr(o.get('rate_bps')),
-                            rb=_ptr(o.get('rb')), tx_pwr_dBm=_ptr(o.get('tx_pwr_dbm')))
+                            rb=_ptr(o.get('rb')), tx_pwr_dBm=_ptr(o.get('tx_pwr_dbm')), agent_reward=_ptr(o.get('agent_reward')))
         _lib.check(self._lib.d2d_step_many(self._h, C.byref(io), T, self._stream()))
         return o
 
@@ -251,6 +256,8 @@ class VecD2DEnv:
              'capacity_mbps': torch.empty((T, E, N), dtype=torch.float32, device=dev),
              'reward': torch.empty((T, E), dtype=torch.float32, device=dev),
              'done': torch.empty((T, E), dtype=torch.uint8, device=dev)}
+        if self.per_agent_reward:
+            o['agent_reward'] = torch.empty((T, E, N), dtype=torch.float32, device=dev)
         if self.want_info:
             o.update(rate_bps=torch.empty((T, E, N), dtype=torch.float32, device=dev),
                      rb=torch.empty((T, E, N), dtype=torch.int16, device=dev),
@@ -279,7 +286,8 @@ class VecD2DEnv:
                               done=out['done'].ctypes.data,
                               rate_bps=out['rate_bps'].ctypes.data if 'rate_bps' in out else None,
                               rb=out['rb'].ctypes.data if 'rb' in out else None,
-                              tx_pwr_dBm=out['tx_pwr_dbm'].ctypes.data if 'tx_pwr_dbm' in out else None)
+                              tx_pwr_dBm=out['tx_pwr_dbm'].ctypes.data if 'tx_pwr_dbm' in out else None,
+                              agent_reward=out['agent_reward'].ctypes.data if 'agent_reward' in out else None)
 
     def step_host(self, actions: np.ndarray, out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
         """End-to-end host call (d2d_step_host): host int32 actions in, host arrays out, copies included.
@@ -304,6 +312,8 @@ class VecD2DEnv:
         E, N = self.num_envs, self.num_links
         spec = {'obs': ((E, N, 6), torch.float32), 'capacity_mbps': ((E, N), torch.float32),
                 'reward': ((E,), torch.float32), 'done': ((E,), torch.uint8)}
+        if self.per_agent_reward:
+            spec['agent_reward'] = ((E, N), torch.float32)
         if info:
             spec.update({'rate_bps': ((E, N), torch.float32), 'rb': ((E, N), torch.int16),
                          'tx_pwr_dbm': ((E, N), torch.int16)})

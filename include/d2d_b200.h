@@ -34,7 +34,7 @@
 #define D2D_API __attribute__((visibility("default")))
 #endif
 
-#define D2D_ABI_VERSION 1
+#define D2D_ABI_VERSION 2
 
 typedef struct d2d_handle d2d_handle_t;
 
@@ -46,13 +46,19 @@ typedef enum d2d_status {
     D2D_ERR_STATE = -4          /* state buffers not bound / called out of order */
 } d2d_status;
 
-/* path_loss_model plugin (envs/env_config.py:21; classes in path_loss.py:42-66).  FREE_SPACE is
- * LogDistancePathLoss with ple = 2 (path_loss.py:43,45): it is not a separate class in the reference. */
-typedef enum d2d_path_loss_model { D2D_PL_LOG_DISTANCE = 0, D2D_PL_FREE_SPACE = 1 } d2d_path_loss_model;
+/* path_loss_model plugin (envs/env_config.py:21; classes in path_loss.py:42-66, 90-123).  FREE_SPACE is
+ * LogDistancePathLoss with ple = 2 (path_loss.py:43,45): it is not a separate class in the reference.
+ * COST_HATA (path_loss.py:90-123) is A(h_tx, h_rx) + B(h_tx) log10(d_km): with one transmitter antenna height it is a
+ * log-distance law with exponent ple = B / 10 and a per-receiver constant, both folded by the caller: d2d_config.ple and
+ * d2d_link.path_loss_const_dB (= A - 3 B for the link's receiver). */
+typedef enum d2d_path_loss_model { D2D_PL_LOG_DISTANCE = 0, D2D_PL_FREE_SPACE = 1, D2D_PL_COST_HATA = 2 } d2d_path_loss_model;
 /* obs_fn plugin (envs/d2d_env.py:27; envs/obs_fn.py:35-61) */
 typedef enum d2d_obs_fn { D2D_OBS_LINEAR = 0 } d2d_obs_fn;
-/* reward_fn plugin (envs/d2d_env.py:28; envs/reward_fn.py:22-44) */
-typedef enum d2d_reward_fn { D2D_REWARD_SYSTEM_CAPACITY = 0 } d2d_reward_fn;
+/* reward_fn plugin (envs/d2d_env.py:28).  SYSTEM_CAPACITY (envs/reward_fn.py:22-44) is one scalar per env, computed inside
+ * the step kernel.  SHANNON (:47-57, parameter min_sinr) and CUE_SINR_SHANNON (:60-78, parameter sinr_threshold_dB) are per
+ * agent: a second small kernel derives them from the step's results into d2d_step_io.agent_reward, and `reward` then
+ * holds their mean over the acting agents. */
+typedef enum d2d_reward_fn { D2D_REWARD_SYSTEM_CAPACITY = 0, D2D_REWARD_SHANNON = 1, D2D_REWARD_CUE_SINR_SHANNON = 2 } d2d_reward_fn;
 /* link_type.py:4-7 */
 typedef enum d2d_link_type { D2D_LINK_UPLINK = 1, D2D_LINK_DOWNLINK = 2, D2D_LINK_SIDELINK = 3 } d2d_link_type;
 
@@ -76,6 +82,7 @@ typedef struct d2d_config {
     double cell_radius_m;       /* envs/env_config.py:15 */
     double d2d_radius_m;        /* :16 */
     double min_capacity_mbps;   /* envs/reward_fn.py:23 */
+    double reward_param;        /* SHANNON: min_sinr (envs/reward_fn.py:48); CUE_SINR_SHANNON: sinr_threshold_dB (:61) */
 } d2d_config_t;
 
 /* Per-link link-budget constants, folded on the host from the per-device config dicts
@@ -89,6 +96,7 @@ typedef struct d2d_link {
     double tx_rb_bandwidth_kHz; /* transmitter rb_bandwidth_kHz (device.py:93-95; simulator.py:150) */
     int32_t link_type;          /* d2d_link_type */
     int32_t reserved0;
+    double path_loss_const_dB;  /* D2D_PL_COST_HATA only: the path-loss constant toward this link's receiver */
 } d2d_link_t;
 
 /* Buffers of one step.  All pointers are device pointers for d2d_step and host pointers for
@@ -105,6 +113,8 @@ typedef struct d2d_step_io {
     float *rate_bps;            /* [E][N]  simulator.py:118-127 (info['rate_bps'], envs/d2d_env.py:114) */
     int16_t *rb;                /* [E][N]  decoded resource block (envs/d2d_env.py:95) */
     int16_t *tx_pwr_dBm;        /* [E][N]  decoded Tx power (envs/d2d_env.py:96) */
+    float *agent_reward;        /* [E][N]  per-agent reward of SHANNON / CUE_SINR_SHANNON (0 for absent agents); with
+                                   SYSTEM_CAPACITY the env's scalar broadcast to its acting agents (envs/reward_fn.py:44) */
 } d2d_step_io_t;
 
 /* Episode statistics accumulated on the device by d2d_step when a stats buffer is bound;

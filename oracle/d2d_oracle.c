@@ -74,6 +74,28 @@ void d2d_oracle_decode_action(int64_t a, int64_t n_pwr, int64_t *rb, int64_t *pw
     *pwr = r;
 }
 
+/* path_loss.py:96-123 CostHataPathLoss.__call__ and _ms_h_correction (AreaType: 0 RURAL, 1 SUBURBAN, 2 URBAN) */
+double d2d_oracle_cost_hata_pl(double dist_m, double f_GHz, int area_type, double h_tx, double h_rx) {
+    const double f = f_GHz * 1000.0;            /* :100 MHz */
+    const double d = dist_m / 1000.0;           /* :101 km */
+    double a_hc;
+    if (area_type == 2) {                       /* :116-120 */
+        if (f >= 200.0) { const double l = log10(1.54 * h_rx); a_hc = 8.29 * l * l - 1.1; }
+        else { const double l = log10(11.75 * h_rx); a_hc = 3.2 * l * l - 4.97; }
+    } else {
+        a_hc = (1.1 * log10(f) - 0.7) * h_rx - (1.56 * log10(f) - 0.8);     /* :122 */
+    }
+    const double c = area_type == 2 ? 3.0 : 0.0;                             /* :107 */
+    return 46.3 + 33.9 * log10(f) - 13.82 * log10(h_tx) - a_hc + (44.9 - 6.55 * log10(h_tx)) * log10(d) + c;   /* :108 */
+}
+
+/* PathLoss.__call__(tx, rx) for the configured model (simulator.py:59,93,99) */
+static double path_loss_dB(const d2d_oracle_cfg *cfg, double K, const d2d_oracle_device *tx, const d2d_oracle_device *rx, double d) {
+    if (cfg->path_loss_model == 2)
+        return d2d_oracle_cost_hata_pl(d, cfg->carrier_freq_GHz, cfg->area_type, tx->antenna_height_m, rx->antenna_height_m);
+    return 10.0 * cfg->ple * log10(d) + K;      /* path_loss.py:65-66 */
+}
+
 /* One environment.  Returns 0 / -1 (zero-distance link). */
 static int step_one(const d2d_oracle_cfg *cfg, const d2d_oracle_device *dev, const double *pos,
                     const int32_t *act, const uint8_t *active,
@@ -102,7 +124,7 @@ static int step_one(const d2d_oracle_cfg *cfg, const d2d_oracle_device *dev, con
             /* simulator.py:93 */
             double d = d2d_oracle_distance(pt[0], pt[1], pr[0], pr[1]);
             if (!(d > 0.0)) status = -1;
-            double pl = 10.0 * cfg->ple * log10(d) + K;
+            double pl = path_loss_dB(cfg, K, tx, rx, d);
             double rx_pwr = d2d_oracle_rx_signal_level_dBm(rx, d2d_oracle_eirp_dBm(tx, (double)pw[j]), pl);
             /* simulator.py:95-101: same-RB actions minus self; NO rx gain on interferers */
             double sum_ix = 0.0;
@@ -113,7 +135,7 @@ static int step_one(const d2d_oracle_cfg *cfg, const d2d_oracle_device *dev, con
                 double dk = d2d_oracle_distance(pk[0], pk[1], pr[0], pr[1]);
                 if (!(dk > 0.0)) status = -1;
                 double ix_eirp = d2d_oracle_eirp_dBm(&dev[txd[k]], (double)pw[k]);
-                double ix_pl = 10.0 * cfg->ple * log10(dk) + K;
+                double ix_pl = path_loss_dB(cfg, K, &dev[txd[k]], rx, dk);
                 sum_ix += d2d_oracle_dB_to_linear(ix_eirp - ix_pl);
             }
             /* simulator.py:106-107 */

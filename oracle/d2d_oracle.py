@@ -29,24 +29,26 @@ class _Device(C.Structure):
                 ('sinr_dB', C.c_double), ('ix_margin_dB', C.c_double),
                 ('body_loss_dB', C.c_double), ('cable_loss_dB', C.c_double),
                 ('masthead_amplifier_gain_dB', C.c_double),
-                ('num_subcarriers', C.c_double), ('subcarrier_spacing_kHz', C.c_double)]
+                ('num_subcarriers', C.c_double), ('subcarrier_spacing_kHz', C.c_double),
+                ('antenna_height_m', C.c_double)]
 
 
 class _Cfg(C.Structure):
     _fields_ = [('num_rbs', C.c_int32), ('num_cues', C.c_int32), ('num_due_pairs', C.c_int32),
-                ('n_pwr_cue', C.c_int32), ('n_pwr_due', C.c_int32), ('_pad', C.c_int32),
-                ('carrier_freq_GHz', C.c_double), ('ple', C.c_double), ('min_capacity_mbps', C.c_double)]
+                ('n_pwr_cue', C.c_int32), ('n_pwr_due', C.c_int32), ('path_loss_model', C.c_int32),
+                ('carrier_freq_GHz', C.c_double), ('ple', C.c_double), ('min_capacity_mbps', C.c_double),
+                ('area_type', C.c_int32), ('_pad', C.c_int32)]
 
 
 # device.py:12-41 (merged with DEFAULT_DEVICE_CONFIG :12-16)
 UE_DEFAULTS = dict(is_bs=0, tx_antenna_gain_dBi=0.0, rx_antenna_gain_dBi=0.0, thermal_noise_dBm=-104.5,
                    noise_figure_dB=7.0, sinr_dB=-10.0, ix_margin_dB=3.0, body_loss_dB=3.0,
                    cable_loss_dB=0.0, masthead_amplifier_gain_dB=0.0,
-                   num_subcarriers=12, subcarrier_spacing_kHz=15.0)
+                   num_subcarriers=12, subcarrier_spacing_kHz=15.0, antenna_height_m=1.5)
 BS_DEFAULTS = dict(is_bs=1, tx_antenna_gain_dBi=17.5, rx_antenna_gain_dBi=17.5, thermal_noise_dBm=-118.4,
                    noise_figure_dB=2.0, sinr_dB=-7.0, ix_margin_dB=2.0, body_loss_dB=0.0,
                    cable_loss_dB=2.0, masthead_amplifier_gain_dB=2.0,
-                   num_subcarriers=12, subcarrier_spacing_kHz=15.0)
+                   num_subcarriers=12, subcarrier_spacing_kHz=15.0, antenna_height_m=23.0)
 
 
 @dataclass
@@ -65,6 +67,8 @@ class OracleConfig:
     subcarrier_spacing_kHz: int = 15
     ple: float = 2.0
     min_capacity_mbps: float = 0.0
+    path_loss_model: str = 'log_distance'      # or 'cost_hata' (path_loss.py:90-123)
+    area_type: int = 1                         # path_loss.py:84-87 AreaType value (CostHata only; default SUBURBAN, :91)
     # per-device overrides {device_id: {field: value}} as a device_config_file's 'config' dicts would give
     device_overrides: Dict[str, dict] = field(default_factory=dict)
 
@@ -117,6 +121,8 @@ def lib():
         L.d2d_oracle_decode_action.argtypes = [C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.d2d_oracle_decode_action.restype = None
         vp = C.c_void_p
+        L.d2d_oracle_cost_hata_pl.argtypes = [d, d, C.c_int, d, d]
+        L.d2d_oracle_cost_hata_pl.restype = d
         L.d2d_oracle_step_batch.argtypes = [C.POINTER(_Cfg), C.POINTER(_Device), C.c_int64] + [vp] * 11 + [C.c_int]
         L.d2d_oracle_step_batch.restype = C.c_int
         L.d2d_oracle_per_agent_obs.argtypes = [vp, vp, C.c_int32, vp]
@@ -139,7 +145,8 @@ def _c_cfg(cfg: OracleConfig) -> _Cfg:
     return _Cfg(num_rbs=cfg.num_rbs, num_cues=cfg.num_cues, num_due_pairs=cfg.num_due_pairs,
                 n_pwr_cue=cfg.cue_max_tx_power_dBm + 1,                               # envs/d2d_env.py:33
                 n_pwr_due=cfg.due_max_tx_power_dBm - cfg.due_min_tx_power_dBm + 1,    # envs/d2d_env.py:32
-                carrier_freq_GHz=cfg.carrier_freq_GHz, ple=cfg.ple, min_capacity_mbps=cfg.min_capacity_mbps)
+                carrier_freq_GHz=cfg.carrier_freq_GHz, ple=cfg.ple, min_capacity_mbps=cfg.min_capacity_mbps,
+                path_loss_model=2 if cfg.path_loss_model == 'cost_hata' else 0, area_type=int(cfg.area_type))
 
 
 def device_table(cfg: OracleConfig):
@@ -178,6 +185,32 @@ def step_batch(cfg: OracleConfig, positions, actions, active=None, nthreads: int
                                      int(nthreads))
     out['status'] = st
     return out
+
+
+def agent_rewards(cfg: OracleConfig, res: Dict[str, np.ndarray], kind: str, param: float, active=None) -> np.ndarray:
+    """The reference's per-agent reward functions, restated on the oracle's float64 step results (numpy; integer /
+    comparison logic plus one log2).  Returns (E, N); absent agents (no entry in the reference's dict) get 0.
+
+    kind 'shannon' - ShannonRewardFunction (envs/reward_fn.py:47-57): log2(1 + 10^(sinr/10)) if sinr >= min_sinr else -1.
+    kind 'cue_sinr_shannon' - CueSinrShannonRewardFunction (envs/reward_fn.py:60-78): -1 if some OTHER action on the
+        agent's RB is a non-SIDELINK (CUE) link with sinr < sinr_threshold_dB, else log2(1 + 10^(sinr/10))."""
+    sinr, rb = res['sinr_db'], res['rb']
+    E, N = sinr.shape
+    act = np.ones((E, N), bool) if active is None else np.asarray(active, bool)
+    shannon = np.log2(1.0 + np.power(10.0, sinr / 10.0))                 # conversion.py:4-13 + reward_fn.py:56,76
+    if kind == 'shannon':
+        out = np.where(sinr >= param, shannon, -1.0)                      # reward_fn.py:56
+    elif kind == 'cue_sinr_shannon':
+        is_cue = np.arange(N)[None, :] < cfg.num_cues                    # link_type != SIDELINK (reward_fn.py:71)
+        weak = act & is_cue & (sinr < param)                             # reward_fn.py:72-73
+        nweak = np.zeros((E, int(rb.max()) + 2), np.int64)
+        ee = np.broadcast_to(np.arange(E)[:, None], (E, N))
+        np.add.at(nweak, (ee[weak], rb[weak]), 1)                        # weak CUE links per RB (actions.py:27-31 grouping)
+        others = nweak[ee, np.where(act, rb, 0)] - weak                  # .difference({action}) (reward_fn.py:69)
+        out = np.where(others > 0, -1.0, shannon)
+    else:
+        raise ValueError(kind)
+    return np.where(act, out, 0.0)
 
 
 def per_agent_obs(table: np.ndarray, present) -> np.ndarray:

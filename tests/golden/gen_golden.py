@@ -169,8 +169,85 @@ def fixed_scenario_10k():
     print('fixed_scenario_10k ok', reward[:3], capsum[:3])
 
 
+def cost_hata():
+    """CostHataPathLoss (path_loss.py:90-123) through the unmodified reference, SUBURBAN (the class
+    default, what `path_loss_model=CostHataPathLoss` gives through simulator.py:59) and URBAN (functools.partial)."""
+    import functools
+    from gym_d2d.path_loss import AreaType, CostHataPathLoss
+    base = dict(num_rbs=3, num_cues=5, num_due_pairs=7)
+    cfg = O.OracleConfig(**base)
+    rng = np.random.default_rng(41)
+    num_envs, steps = 4, 3
+    pos = O.random_positions(cfg, num_envs, rng)
+    acts = np.stack([O.random_actions(cfg, num_envs, rng) for _ in range(steps)])
+    out = dict(positions=pos, actions=acts.astype(np.int32))
+    for name, model in [('suburban', CostHataPathLoss), ('urban', functools.partial(CostHataPathLoss, area_type=AreaType.URBAN))]:
+        env = R.make_env(dict(base, path_loss_model=model))
+        env.reset()
+        keys = R.link_keys(env)
+        res = {k: np.zeros((steps, num_envs, len(keys))) for k in ['sinr_db', 'snr_db', 'rate_bps', 'capacity_mbps']}
+        rew = np.zeros((steps, num_envs))
+        for s in range(steps):
+            for e in range(num_envs):
+                R.set_positions(env, pos[e])
+                ref = R.step(env, acts[s, e], keys)
+                for k in res:
+                    res[k][s, e] = ref[k]
+                rew[s, e] = ref['reward'][0]
+        for k in res:
+            out[f'{name}_{k}'] = res[k]
+        out[f'{name}_reward'] = rew
+    np.savez_compressed(HERE / 'cost_hata.npz', **out)
+    print('cost_hata ok', out['suburban_sinr_db'][0, 0, :4], out['urban_sinr_db'][0, 0, :4])
+
+
+def reward_plugins():
+    """the reference's two per-agent reward functions (envs/reward_fn.py:47-78), run through the unmodified
+    reference with `reward_fn=<class>` in env_config (envs/d2d_env.py:28).  Stores every agent's reward."""
+    from gym_d2d.envs.reward_fn import CueSinrShannonRewardFunction, ShannonRewardFunction
+    base = dict(num_rbs=4, num_cues=6, num_due_pairs=9)
+    cfg = O.OracleConfig(**base)
+    rng = np.random.default_rng(31)
+    num_envs, steps = 5, 4
+    pos = O.random_positions(cfg, num_envs, rng)
+    acts = np.stack([O.random_actions(cfg, num_envs, rng) for _ in range(steps)])
+    out = dict(positions=pos, actions=acts.astype(np.int32))
+    for name, cls in [('shannon', ShannonRewardFunction), ('cue_sinr_shannon', CueSinrShannonRewardFunction)]:
+        env = R.make_env(dict(base, reward_fn=cls))
+        env.reset()
+        keys = R.link_keys(env)
+        rew = np.zeros((steps, num_envs, len(keys)))
+        sinr = np.zeros((steps, num_envs, len(keys)))
+        for s in range(steps):
+            for e in range(num_envs):
+                R.set_positions(env, pos[e])
+                ref = R.step(env, acts[s, e], keys)
+                rew[s, e] = ref['reward']
+                sinr[s, e] = ref['sinr_db']
+        out[f'{name}_reward'] = rew
+        out['sinr_db'] = sinr
+        out['keys'] = np.array(keys)
+    # a subset of agents (absent agents get no reward entry) for the CUE-SINR rule
+    env = R.make_env(dict(base, reward_fn=CueSinrShannonRewardFunction))
+    env.reset()
+    keys = R.link_keys(env)
+    present = [0, 2, 3, 6, 7, 8, 11, 14]
+    R.set_positions(env, pos[0])
+    ref = R.step(env, [acts[0, 0, i] for i in present], [keys[i] for i in present])
+    out['subset_present'] = np.array(present)
+    out['subset_cue_sinr_shannon_reward'] = ref['reward']
+    out['subset_sinr_db'] = ref['sinr_db']
+    np.savez_compressed(HERE / 'reward_plugins.npz', **out)
+    print('reward_plugins ok', out['shannon_reward'][0, 0, :4], out['cue_sinr_shannon_reward'][0, 0, :4],
+          'penalised', float((out['cue_sinr_shannon_reward'] == -1).mean()))
+
+
 if __name__ == '__main__':
     assert R.import_reference() is not None, 'the reference must be importable to (re)generate fixtures'
+    if len(sys.argv) > 1:                      # regenerate single fixtures: python gen_golden.py reward_plugins ...
+        for fn in sys.argv[1:]:
+            globals()[fn]()
+        sys.exit(0)
     appendix_c()
     subset_and_order()
     overrides_penalty()
@@ -183,3 +260,5 @@ if __name__ == '__main__':
     kw = dict(num_rbs=1, num_cues=1, num_due_pairs=1)
     run_cases('tiny_1_1_1', kw, O.OracleConfig(**kw), num_envs=4, steps=3, seed=15)
     fixed_scenario_10k()
+    reward_plugins()
+    cost_hata()

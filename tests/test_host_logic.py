@@ -2,6 +2,7 @@
 import ctypes as C
 import functools
 import json
+import math
 import re
 from pathlib import Path
 
@@ -33,9 +34,9 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(_lib.D2DConfig) == 2 * 4 + 8 + 10 * 4 + 5 * 8
-    assert C.sizeof(_lib.D2DLink) == 5 * 8 + 2 * 4
-    assert C.sizeof(_lib.D2DStepIO) == 8 * C.sizeof(C.c_void_p)
+    assert C.sizeof(_lib.D2DConfig) == 2 * 4 + 8 + 10 * 4 + 6 * 8
+    assert C.sizeof(_lib.D2DLink) == 5 * 8 + 2 * 4 + 8
+    assert C.sizeof(_lib.D2DStepIO) == 9 * C.sizeof(C.c_void_p)
 
 
 def test_error_paths_without_gpu():
@@ -129,6 +130,27 @@ def test_supported_plugins_resolve():
     assert plugins.resolve_obs_fn(G.LinearObsFunction) == _lib.OBS_LINEAR
     assert plugins.resolve_reward_fn(G.SystemCapacityRewardFunction) == (_lib.REWARD_SYSTEM_CAPACITY, 0.0)
     assert plugins.resolve_reward_fn(functools.partial(G.SystemCapacityRewardFunction, min_capacity_mbps=0.5))[1] == 0.5
+    # SURVEY 8(f)-3 plugins: parameters and defaults of envs/reward_fn.py:48,61 and path_loss.py:91
+    assert plugins.resolve_reward_fn(G.ShannonRewardFunction) == (_lib.REWARD_SHANNON, -70.0)
+    assert plugins.resolve_reward_fn(functools.partial(G.CueSinrShannonRewardFunction, sinr_threshold_dB=3.0)) == (_lib.REWARD_CUE_SINR_SHANNON, 3.0)
+    assert plugins.resolve_path_loss(G.CostHataPathLoss) == (_lib.PL_COST_HATA, float(G.AreaType.SUBURBAN.value))
+    assert plugins.resolve_path_loss(functools.partial(G.CostHataPathLoss, area_type=G.AreaType.URBAN))[1] == 2.0
+
+
+def test_cost_hata_fold_matches_the_oracle_restatement():
+    """config.cost_hata_fold turns CostHataPathLoss (path_loss.py:90-123) into (exponent, per-receiver constant); the pair must
+    reproduce the oracle's restatement of the reference formula at any distance, for both receiver classes and area types."""
+    L = O.lib()
+    for area in (G.AreaType.RURAL, G.AreaType.SUBURBAN, G.AreaType.URBAN):
+        c = G.EnvConfig(num_rbs=3, num_cues=2, num_due_pairs=2, path_loss_model=functools.partial(G.CostHataPathLoss, area_type=area))
+        ple, consts = cfgmod.cost_hata_fold(c)
+        for rx, h_rx in [('mbs', 23.0), ('due01', 1.5)]:
+            for d in (3.0, 77.0, 499.0):
+                want = L.d2d_oracle_cost_hata_pl(d, 2.1, area.value, 1.5, h_rx)
+                assert 10 * ple * math.log10(d) + consts[rx] == pytest.approx(want, rel=1e-12)
+    rows = cfgmod.link_table(c)
+    assert rows[0]['path_loss_const_dB'] == consts['mbs'] and rows[-1]['path_loss_const_dB'] == consts['due03']
+    assert cfgmod.cost_hata_fold(G.EnvConfig()) is None
 
 
 def test_reference_classes_are_accepted_by_identity():
@@ -141,11 +163,12 @@ def test_reference_classes_are_accepted_by_identity():
     assert plugins.resolve_path_loss(RefLD) == (_lib.PL_LOG_DISTANCE, 2.0)
     assert plugins.resolve_obs_fn(RefObs) == _lib.OBS_LINEAR
     assert plugins.resolve_reward_fn(RefRew) == (_lib.REWARD_SYSTEM_CAPACITY, 0.0)
-    for bad in (RefHata,):
-        with pytest.raises(G.UnsupportedPluginError):
-            plugins.resolve_path_loss(bad)
+    from gym_d2d.path_loss import AreaType as RefArea, ShadowingPathLoss as RefShadow
+    assert plugins.resolve_path_loss(RefHata) == (_lib.PL_COST_HATA, 1.0)
+    assert plugins.resolve_path_loss(functools.partial(RefHata, area_type=RefArea.URBAN)) == (_lib.PL_COST_HATA, 2.0)
+    assert plugins.resolve_reward_fn(RefShannon) == (_lib.REWARD_SHANNON, -70.0)
     with pytest.raises(G.UnsupportedPluginError):
-        plugins.resolve_reward_fn(RefShannon)
+        plugins.resolve_path_loss(RefShadow)
 
 
 def test_custom_and_unimplemented_plugins_are_rejected():
@@ -156,12 +179,16 @@ def test_custom_and_unimplemented_plugins_are_rejected():
     class CustomObs(G.LinearObsFunction):
         pass
 
-    for bad in (CustomPathLoss, G.ShadowingPathLoss, G.CostHataPathLoss, functools.partial(G.FreeSpacePathLoss, ple=3.0)):
+    for bad in (CustomPathLoss, G.ShadowingPathLoss, functools.partial(G.CostHataPathLoss, ple=3.0),
+                functools.partial(G.FreeSpacePathLoss, ple=3.0)):
         with pytest.raises(G.UnsupportedPluginError):
             plugins.resolve_path_loss(bad)
     with pytest.raises(G.UnsupportedPluginError):
         plugins.resolve_obs_fn(CustomObs)
-    for bad in (G.ShannonRewardFunction, G.CueSinrShannonRewardFunction):
+    class CustomReward(G.ShannonRewardFunction):
+        pass
+
+    for bad in (CustomReward, functools.partial(G.ShannonRewardFunction, min_capacity_mbps=1.0)):
         with pytest.raises(G.UnsupportedPluginError):
             plugins.resolve_reward_fn(bad)
     with pytest.raises(TypeError):

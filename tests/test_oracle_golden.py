@@ -207,3 +207,43 @@ def test_reset_positions_geometry():
     assert (np.sqrt(((tx - rx) ** 2).sum(-1)) <= cfg.d2d_radius_m * (1 + 1e-12)).all()
     # shard independence: env g is the same whichever slice it is drawn in
     np.testing.assert_array_equal(O.reset_positions(cfg, 7, 40, 8), pos[40:48])
+
+
+def test_reward_plugins_match_reference_fixture(golden_dir):
+    """ShannonRewardFunction / CueSinrShannonRewardFunction (envs/reward_fn.py:47-78): the oracle's restatement against
+    per-agent rewards produced by the unmodified reference (tests/golden/reward_plugins.npz)."""
+    g = np.load(golden_dir / "reward_plugins.npz")
+    cfg = O.OracleConfig(num_rbs=4, num_cues=6, num_due_pairs=9)
+    steps, E, N = g['actions'].shape
+    for s in range(steps):
+        res = O.step_batch(cfg, g['positions'], g['actions'][s])
+        np.testing.assert_allclose(res['sinr_db'], g['sinr_db'][s], rtol=1e-9)
+        np.testing.assert_allclose(O.agent_rewards(cfg, res, 'shannon', -70.0), g['shannon_reward'][s], rtol=1e-9)
+        np.testing.assert_allclose(O.agent_rewards(cfg, res, 'cue_sinr_shannon', 0.0), g['cue_sinr_shannon_reward'][s], rtol=1e-9)
+    assert (g['cue_sinr_shannon_reward'] == -1).any() and (g['cue_sinr_shannon_reward'] > 0).any()
+    # a subset of agents: absent agents neither transmit nor count as weak CUEs
+    present = g['subset_present']
+    active = np.zeros((1, N), np.uint8)
+    active[0, present] = 1
+    res = O.step_batch(cfg, g['positions'][:1], g['actions'][0, :1], active=active)
+    rew = O.agent_rewards(cfg, res, 'cue_sinr_shannon', 0.0, active=active)
+    np.testing.assert_allclose(rew[0, present], g['subset_cue_sinr_shannon_reward'], rtol=1e-9)
+    assert (rew[0, np.setdiff1d(np.arange(N), present)] == 0).all()
+
+
+def test_cost_hata_known_answers_and_fixture(golden_dir):
+    """CostHataPathLoss: the reference's own known-answer vectors (test/gym_d2d/test_path_loss.py:42-52: URBAN, f = 2.1 GHz,
+    default BaseStation (23 m) and UserEquipment (1.5 m) heights, both directions) and step results of the unmodified reference (cost_hata.npz)."""
+    L = O.lib()
+    for d, h_tx, h_rx, want in [(250.0, 23.0, 1.5, 121.44557455875727), (250.0, 1.5, 23.0, 114.35415557446962),
+                                (500.0, 23.0, 1.5, 132.2768393081241), (500.0, 1.5, 23.0, 127.5231950610599)]:
+        assert L.d2d_oracle_cost_hata_pl(d, 2.1, 2, h_tx, h_rx) == pytest.approx(want, rel=1e-12)   # test_path_loss.py:42-52
+    g = np.load(golden_dir / 'cost_hata.npz')
+    steps = g['actions'].shape[0]
+    for name, area in [('suburban', 1), ('urban', 2)]:
+        cfg = O.OracleConfig(num_rbs=3, num_cues=5, num_due_pairs=7, path_loss_model='cost_hata', area_type=area)
+        for s in range(steps):
+            res = O.step_batch(cfg, g['positions'], g['actions'][s])
+            for k in ['sinr_db', 'snr_db', 'rate_bps', 'capacity_mbps']:
+                np.testing.assert_allclose(res[k], g[f'{name}_{k}'][s], rtol=1e-9, atol=1e-12, err_msg=f'{name} {k}')
+            np.testing.assert_allclose(res['reward'], g[f'{name}_reward'][s], rtol=1e-9)
