@@ -496,7 +496,11 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
     const uint32_t T = MANY ? (uint32_t)P.T : 1u, strideE = MANY ? (uint32_t)P.t_stride : 0u, strideN = strideE * N;
     float2 tA_keep = make_float2(1.f, 0.f);
     float4 pB_keep = make_float4(1.f, 0.f, 0.f, 0.f);
-    d2d_pdl_wait();
+    // Programmatic dependent launch: the kernel BEFORE this one in the stream may still be running.  If it is one of this
+    // library's step kernels it never writes actions or positions (and anything else - a policy kernel, a reset, a copy -
+    // does not release its dependents early), so this env-step's inputs are read and its whole chain computed right away;
+    // griddepcontrol.wait comes only before the first access to memory a previous step wrote: the step counters and the
+    // output buffers.  Back-to-back steps thus overlap one step's tail with the next step's loads and arithmetic.
     if (e < e_end) nxt = d2d_load_inputs<SPEC>(P, S, iA, qN, lane, hasA, hasB);
     while (e < e_end) {
         // ---- one coalesced pass over the env's inputs, software-pipelined: the NEXT env's (or step's) loads are in
@@ -513,7 +517,6 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         } else {
             d2d_load_actions<SPEC>(P, S, jA + strideN, hasA, hasB, nxt);
         }
-        if (g == 0u && t == 0u && (FULL || P.step_count)) ns_keep = e + lane < e_end ? (int)P.step_count[e + lane] : 0;   // consumed 32 envs later
         const bool liveA = hasA && aA < limA, liveB = hasB && aB < limB;   // has a link AND the agent acts this step
 
         // ---- envs/d2d_env.py:93-101: rb = a // n_pwr, p = a % n_pwr; rank inside the RB (actions.py:27-31) -------------
@@ -583,6 +586,8 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         d2d_sts64_if(lane < R, zero0, 0u, 0u);
         if (!SPEC && R > 32u) d2d_sts64_if(lane + 32u < R, zero0 + 32u * D2D_BIN_STRIDE, 0u, 0u);
 
+        if (e == e0 && t == 0u) d2d_pdl_wait();       // first output of this warp: every earlier kernel's memory is complete from here on
+        if (g == 0u && t == 0u && (FULL || P.step_count)) ns_keep = e + lane < e_end ? (int)P.step_count[e + lane] : 0;   // consumed at the group's end
         // ---- outputs: compact observation table (envs/obs_fn.py:55-61), capacity, optional info.  Rows of absent
         // agents carry their positions and zeros (the reference has no row for them). ---------------------------------
         // (one divergent branch per slot: cheaper than predicating every store, and the two merge when C == D)
