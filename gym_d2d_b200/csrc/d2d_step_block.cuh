@@ -216,12 +216,14 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_generic_kern
 // A block steps a CONTIGUOUS range of envs; the per-env scalars (step counter, reward, done) of a group of 256 envs live
 // in the registers of thread (env - group start) and are read / written as full sectors, like the warp kernel does.
 #define D2D_BLOCK_MAX_LPT 4
+#define D2D_BLOCK_RESQ 32          // links per env the cooperative fp64 pass takes (more are recomputed inline by their thread)
 
 __host__ __device__ inline size_t d2d_block2_smem_bytes(int N, int nbins) {
     size_t b = (size_t)N * sizeof(float4);                        // rec
     b += D2D_MAX_PWR_LEVELS * sizeof(float);                      // pwr_lin
     b += ((size_t)(nbins + 1) * 2 * sizeof(uint32_t) + 15) & ~(size_t)15;   // cnt (count | SIDELINK count << 16), off
     b += ((size_t)N * sizeof(uint32_t) + 15) & ~(size_t)15;       // who: (link index | Tx power << 16) of each sorted record (fp64 pass only)
+    b += 2 * (D2D_BLOCK_RESQ * 8 + 4) * sizeof(uint32_t);         // resq[2]: links queued for the cooperative fp64 pass
     b += 2 * 32 * sizeof(float);                                  // red[2][32]
     return b;
 }
@@ -235,12 +237,14 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS, LPT <= 2 ? 4 : 3) d2d_step_
     uint32_t *cnt = reinterpret_cast<uint32_t *>(pwr + D2D_MAX_PWR_LEVELS);
     uint32_t *off = cnt + (nbins + 1);
     float *red = reinterpret_cast<float *>(d2d_smem_raw + d2d_block2_smem_bytes((int)N, (int)nbins) - 2 * 32 * sizeof(float));
-    uint32_t *who = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(red) - (((size_t)N * sizeof(uint32_t) + 15) & ~(size_t)15));
+    uint32_t *resq = reinterpret_cast<uint32_t *>(red) - 2 * (D2D_BLOCK_RESQ * 8 + 4);      // [2][4 + 32 * 8]: word 0 = count
+    uint32_t *who = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(resq) - (((size_t)N * sizeof(uint32_t) + 15) & ~(size_t)15));
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     d2d_pdl_launch_dependents();
 
     for (uint32_t i = tid; i < D2D_MAX_PWR_LEVELS; i += D2D_BLOCK_THREADS) pwr[i] = P.pwr_lin[i];
     for (uint32_t i = tid; i <= nbins; i += D2D_BLOCK_THREADS) cnt[i] = 0u;
+    if (tid < 2u) resq[tid * (D2D_BLOCK_RESQ * 8 + 4)] = 0u;
     // this thread's links and their constants (fixed for the whole launch)
     bool has[LPT], cue[LPT];
 #pragma unroll
@@ -264,13 +268,12 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS, LPT <= 2 ? 4 : 3) d2d_step_
     uint32_t g = 0;                  // position of the env in its group of 256
     int ns_keep = 0;                 // thread i: step counter of the group's env i
     float rew_keep = 0.f;            // thread i: reward of the group's env i
-    d2d_pdl_wait();
     __syncthreads();
+    // (griddepcontrol.wait comes before the first access to memory an earlier step wrote - see d2d_step_warp.cuh)
 
     for (uint32_t e = e0; e < e_end; ++e) {
         const int32_t *act = P.actions + e * N;
         const float2 *pe = reinterpret_cast<const float2 *>(P.pos) + e * V;
-        if (g == 0u && P.step_count) ns_keep = e + tid < e_end ? (int)P.step_count[e + tid] : 0;      // consumed at the group's end
 
         // ---- phase 1: inputs, decode (envs/d2d_env.py:93-101), rank inside the RB (actions.py:27-31) ---------------
         float2 tx[LPT], rx[LPT];
@@ -345,6 +348,9 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS, LPT <= 2 ? 4 : 3) d2d_step_
         __syncthreads();
 
         // ---- phase 4: interference walk (simulator.py:95-101), epilogue, outputs ----------------------------------------------
+        if (e == e0) d2d_pdl_wait();
+        if (g == 0u && P.step_count) ns_keep = e + tid < e_end ? (int)P.step_count[e + tid] : 0;      // consumed at the group's end
+        uint32_t *rq = resq + (e & 1u) * (D2D_BLOCK_RESQ * 8 + 4);      // this env's queue; the other one is cleared below
         float cap_part = 0.0f;
         uint32_t n_act = 0, resc = 0;
         bool bad = false;
@@ -370,10 +376,22 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS, LPT <= 2 ? 4 : 3) d2d_step_
                 const float dxo = tx[k].x - rx[k].x, dyo = tx[k].y - rx[k].y;
                 const float2 sBk = link_sB(j, cue[k]);
                 o = d2d_link_epilogue<PLE2>((int)pw[k], pl[k], lg[k], gown[k], I, link_cA(j, cue[k]), sBk, P);
-                if (D2D_RESCUE_ENABLED && d2d_needs_rescue<true>(o, fminf(dmin2, fmaf(dxo, dxo, dyo * dyo)), P)) {
+                uint32_t qslot = D2D_BLOCK_RESQ;
+                const bool need = D2D_RESCUE_ENABLED && d2d_needs_rescue<true>(o, fminf(dmin2, fmaf(dxo, dxo, dyo * dyo)), P);
+                if (need) {
                     // fp64 pass (d2d_common.cuh; same policy as d2d_rescue_warp): ~0.2 % of the links, i.e. about one per dense
-                    // env, so it works from the RB's records in shared memory - positions are exact in fp64 unless a shadow is
-                    // bound - and patches only what fp32 cannot deliver
+                    // env.  A thread recomputing its link alone would stall the other 255 at the next barrier, so the link is
+                    // queued and a whole warp takes it after the barrier (below); only a full queue is served inline.
+                    qslot = atomicAdd(rq, 1u);
+                    ++resc;
+                    if (qslot < D2D_BLOCK_RESQ) {
+                        uint32_t *q8 = rq + 4 + qslot * 8;
+                        q8[0] = j | (pw[k] << 16); q8[1] = beg[k] | (end[k] << 16); q8[2] = self[k];
+                        q8[3] = __float_as_uint(tx[k].x); q8[4] = __float_as_uint(tx[k].y);
+                        q8[5] = __float_as_uint(rx[k].x); q8[6] = __float_as_uint(rx[k].y);
+                    }
+                }
+                if (need && qslot >= D2D_BLOCK_RESQ) {
                     const double2 *pe64 = P.pos64 ? reinterpret_cast<const double2 *>(P.pos64) + (int64_t)e * V : nullptr;
                     const bool exact = pe64 != nullptr;
                     const double2 rxd = exact ? pe64[d2d_rx_dev((int)j, (int)C)] : make_double2((double)rx[k].x, (double)rx[k].y);
@@ -399,7 +417,6 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS, LPT <= 2 ? 4 : 3) d2d_step_
                         const double rate = sinr > (double)sBk.x ? 1.4426950408889634074 * d2d_ln_f64(1.0 + r) : 0.0;
                         o.rate = (float)rate; o.cap = (float)(Lj.bw_MHz * rate);
                     }
-                    ++resc;
                 }
                 cap_part += o.cap;
                 ++n_act;
@@ -427,6 +444,54 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS, LPT <= 2 ? 4 : 3) d2d_step_
         float *rd = red + (e & 1u) * 32u;                                // double-buffered: no barrier after the owner's read
         if (lane == 0) { rd[warp] = cap_part; rd[8 + warp] = (float)n_act_w; rd[16 + warp] = (float)resc_w; }
         const int any_bad = __syncthreads_or(bad ? 1 : 0);
+        // ---- cooperative fp64 pass: warp w takes queued links w, w + 8, ...; its lanes split the RB's peer records, a
+        // butterfly sums their terms, lane 0 rewrites what fp32 could not deliver (after the owner's stores above) --------
+        {
+            const uint32_t nq = min(rq[0], (uint32_t)D2D_BLOCK_RESQ);
+            if (tid == 0) resq[((e & 1u) ^ 1u) * (D2D_BLOCK_RESQ * 8 + 4)] = 0u;      // the next env's queue
+            const double2 *pe64 = P.pos64 ? reinterpret_cast<const double2 *>(P.pos64) + (int64_t)e * V : nullptr;
+            const bool exact = pe64 != nullptr;
+            for (uint32_t i = warp; i < nq; i += D2D_BLOCK_THREADS / 32) {
+                const uint32_t *q8 = rq + 4 + i * 8;
+                const uint32_t j = q8[0] & 0xffffu, pwj = q8[0] >> 16, qb = q8[1] & 0xffffu, qe = q8[1] >> 16, qs = q8[2];
+                const double2 txd = exact ? pe64[d2d_tx_dev((int)j, (int)C)]
+                                          : make_double2((double)__uint_as_float(q8[3]), (double)__uint_as_float(q8[4]));
+                const double2 rxd = exact ? pe64[d2d_rx_dev((int)j, (int)C)]
+                                          : make_double2((double)__uint_as_float(q8[5]), (double)__uint_as_float(q8[6]));
+                double I64 = 0.0;
+                for (uint32_t q = qb + lane; q < qe; q += 32u) {
+                    if (q == qs) continue;
+                    const uint32_t wk = who[q], kk = wk & 0xffffu;
+                    const float4 rk = rec[q];
+                    const double2 tk = exact ? pe64[d2d_tx_dev((int)kk, (int)C)] : make_double2((double)rk.x, (double)rk.y);
+                    const double ex = tk.x - rxd.x, ey = tk.y - rxd.y;
+                    I64 += P.pwr_lin_d[wk >> 16] * P.linkD[kk].t_lin * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, P.ple_d);
+                }
+#pragma unroll
+                for (int sh = 16; sh > 0; sh >>= 1)
+                    I64 += __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(I64), sh), __shfl_xor_sync(0xffffffffu, __double2loint(I64), sh));
+                if (lane == 0) {
+                    const D2DLinkD Lj = P.linkD[j];
+                    const float sens = link_sB(j, j < C).x;
+                    const double ex = txd.x - rxd.x, ey = txd.y - rxd.y;
+                    const double Sg = P.pwr_lin_d[pwj] * Lj.a_lin * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, P.ple_d);
+                    const double r = Sg * d2d_rcp_f64(fma(I64, Lj.inv_noise, 1.0));
+                    const bool r1 = fabs(r - 1.0) < 0.0625, s1 = fabs(Sg - 1.0) < 0.0625;
+                    const uint64_t gi = (uint64_t)e * N + j;
+                    double sinr = 0.0;
+                    if (exact || r1) {
+                        sinr = r1 ? d2d_db_near1(r) : 4.3429448190325182765 * d2d_ln_f64(r);
+                        if (P.obs) P.obs[gi * 6u + 4u] = (float)sinr;
+                    }
+                    if ((exact || s1) && P.obs) P.obs[gi * 6u + 5u] = (float)(s1 ? d2d_db_near1(Sg) : 4.3429448190325182765 * d2d_ln_f64(Sg));
+                    if (exact || (r1 && fabsf(sens) < 0.5f)) {
+                        const double rate = sinr > (double)sens ? 1.4426950408889634074 * d2d_ln_f64(1.0 + r) : 0.0;
+                        if (P.cap) P.cap[gi] = (float)(Lj.bw_MHz * rate);
+                        if (P.rate) P.rate[gi] = (float)rate;
+                    }
+                }
+            }
+        }
         if (tid == g) {
             float cs = 0.f, na = 0.f, rs = 0.f;
 #pragma unroll
