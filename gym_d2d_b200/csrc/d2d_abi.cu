@@ -313,7 +313,7 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
     int rc;
     if (h->use_warp) {
         // launch shape by batch size (d2d_step_warp.cuh): about one wave of envs -> 4-warp blocks, many waves -> 8-warp blocks
-        h->wpb = cfg->num_envs >= 32768 ? 8 : 4;
+        h->wpb = cfg->num_envs >= 65536 ? 8 : 4;
         if (const char *w = std::getenv("D2D_B200_WPB")) h->wpb = std::atoi(w) == 8 ? 8 : 4;
         h->spec = h->ple2 && h->uniform && cfg->path_loss_model != D2D_PL_COST_HATA && cfg->num_rbs == 25 && cfg->num_cues == 25 && cfg->num_due_pairs == 25 && cfg->n_pwr_cue == 24 &&
                   cfg->n_pwr_due == 21;
