@@ -764,3 +764,23 @@ def test_cost_hata_matches_reference_fixture(golden_dir):
             assert_rel(out['capacity_mbps'], g[f'{name}_capacity_mbps'][s], RTOL, f'{name} capacity')
             assert_rel(out['reward'], g[f'{name}_reward'][s], RTOL, f'{name} reward')
         env.close()
+
+
+def test_step_many_with_per_agent_rewards():
+    """d2d_step_many + a per-agent reward function: the post-pass kernel covers all T x E env-steps of the fused launch."""
+    import gym_d2d_b200 as G
+    cfg = O.OracleConfig()
+    E, T = 64, 5
+    rng = np.random.default_rng(8)
+    pos = O.random_positions(cfg, E, rng)
+    acts = np.stack([O.random_actions(cfg, E, rng) for _ in range(T)])
+    env = make_vec(E, dict(reward_fn=G.ShannonRewardFunction))
+    env.set_positions(pos)
+    out = env.step_many(torch.as_tensor(acts, dtype=torch.int32, device='cuda').contiguous())
+    torch.cuda.synchronize()
+    for t in range(T):
+        ref = O.step_batch(cfg, pos, acts[t], nthreads=4)
+        want = O.agent_rewards(cfg, ref, 'shannon', -70.0)
+        assert_rel(out['agent_reward'][t].cpu().numpy(), want, RTOL, f'slice {t}')
+        np.testing.assert_allclose(out['reward'][t].cpu().numpy(), want.mean(axis=1), rtol=1e-5)
+    env.close()
