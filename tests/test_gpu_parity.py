@@ -491,7 +491,7 @@ def test_pipelined_host_steps_equal_synchronous_ones():
     sync_env.close(); pipe_env.close()
 
 
-@pytest.mark.parametrize('E', [100, 40000])      # both launch shapes of the warp kernel (4- and 8-warp blocks)
+@pytest.mark.parametrize('E', [100, 70000])      # both launch shapes of the warp kernel (4- and 8-warp blocks)
 def test_core_output_fast_path_equals_general_path(E):
     """VecD2DEnv(info=False) passes exactly the core outputs and takes the kernel instantiation that tests no output
     pointer; it must produce bit-identical obs / capacity / reward / done to the general instantiation."""
@@ -576,6 +576,35 @@ def test_config2_4096_default_envs_properties():
     assert_rel(obs3[idx, :, 4].cpu().numpy(), ref['sinr_db'], RTOL, 'sinr_db')
     assert_rel(cap3[idx].cpu().numpy(), ref['capacity_mbps'], RTOL, 'capacity')
     assert_rel(reward3[idx].cpu().numpy(), ref['reward'], RTOL, 'reward')
+    env.close()
+
+
+def test_config5_slice_131072_default_envs_properties():
+    """BASELINE configs[4]: one GPU's slice (131 072 envs) of the 1M-env run.  Every warp steps a contiguous range of 37 envs
+    here, so the per-group scalar I/O (groups of 32 + a partial group) is exercised: reward / done / step counters of ALL
+    envs are checked against the per-link outputs, sampled envs against the oracle, statistics against the outputs."""
+    cfg = O.OracleConfig()
+    E = 131072
+    env = make_vec(E)
+    env.reset(seed=5)
+    env.reset_stats()
+    a = env.sample_actions()
+    obs, reward, cap = _properties(env, cfg, a)                    # counted step 1 (incl. reward == mean capacity for every env)
+    assert (env.step_count == 1).all() and (env.done == 0).all()
+    for _ in range(9):
+        env.step(a)
+    torch.cuda.synchronize()
+    assert (env.step_count == 10).all() and (env.done == 1).all()        # EPISODE_LENGTH = 10 (envs/d2d_env.py:16,68)
+    assert torch.equal(env.reward, reward)                               # same actions, same positions: same reward
+    st = env.stats()
+    assert st['env_steps'] == 10 * E
+    assert st['sum_reward'] == pytest.approx(10 * float(reward.double().sum()), rel=1e-5)
+    assert st['sum_capacity_mbps'] == pytest.approx(10 * float(cap.double().sum()), rel=1e-5)
+    idx = torch.arange(17, E, 2048, device='cuda')
+    ref = O.step_batch(cfg, env.positions[idx].double().cpu().numpy(), a[idx].cpu().numpy(), nthreads=4)
+    assert_rel(obs[idx, :, 4].cpu().numpy(), ref['sinr_db'], RTOL, 'sinr_db')
+    assert_rel(cap[idx].cpu().numpy(), ref['capacity_mbps'], RTOL, 'capacity')
+    assert_rel(reward[idx].cpu().numpy(), ref['reward'], RTOL, 'reward')
     env.close()
 
 
