@@ -381,6 +381,36 @@ def run_cuda_arm(args) -> None:
                'd2h_bytes_per_step': E * N * 24 + E * N * 4 + E * 4 + E, 'steps': e2e_steps,
                'api': 'd2d_step_host_async/_wait via VecD2DEnv.step_host_async (pinned host buffers, two steps in flight; actions '
                       'copied in, obs + capacity + reward + done copied back, every step)'}
+    # ---- fused rollouts: d2d_step_many, T steps of every env per launch -----------------------------------
+    fused = None
+    if args.fused_steps > 1:
+        T = args.fused_steps
+        nbuf = max(2, min(8, (192 << 20) // (E * T * (B - 8 * V)) + 1))      # > L2 worth of outputs in flight
+        many_acts = [torch.stack([env.sample_actions(gen_many) for _ in range(T)]).contiguous()
+                     for gen_many in [torch.Generator(device=env.device).manual_seed(7 + rank)] for _ in range(nbuf)]
+        many_outs = [env.alloc_many_outputs(T) for _ in range(nbuf)]
+        for a_, o_ in zip(many_acts, many_outs):
+            env.step_many(a_, o_)
+        torch.cuda.synchronize()
+        if pg is not None:
+            pg.barrier()
+        reps = max(4, min(64, args.steps // T))
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        for i in range(reps):
+            env.step_many(many_acts[i % nbuf], many_outs[i % nbuf])
+        ev1.record()
+        torch.cuda.synchronize()
+        windows.append((t0, time.perf_counter()))
+        secs_f = ev0.elapsed_time(ev1) * 1e-3
+        if pg is not None:
+            tt = torch.tensor([secs_f], dtype=torch.float64, device=env.device)
+            pg.all_reduce(tt, op=pg.ReduceOp.MAX)
+            secs_f = float(tt.item())
+        fused = {'workload': f'd2d_step_many: {T} consecutive steps of the same {E} envs per launch (positions read once), {reps} launches',
+                 'value': world * E * T * reps / secs_f, 'unit': UNIT, 'steps_per_launch': T, 'us_per_step': 1e6 * secs_f / (reps * T)}
+        del many_acts, many_outs
     env.close()
     del env, acts, outs
 
@@ -432,6 +462,8 @@ def run_cuda_arm(args) -> None:
                                  f'{E / (geometry["grid"] * geometry["envs_per_block"]):.2f} envs per resident warp slot'},
             'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks, 'episode_stats': stats_summary,
         }
+        if fused is not None:
+            line['fused_rollout'] = fused
         if large is not None:
             line['large_batch'] = large
         if base is not None:
@@ -450,6 +482,7 @@ def main() -> None:
     ap.add_argument('--impl', choices=['cuda', 'reference'], default='cuda')
     ap.add_argument('--envs-per-gpu', type=int, default=4096)
     ap.add_argument('--large-envs-per-gpu', type=int, default=131072)
+    ap.add_argument('--fused-steps', type=int, default=10, help='T of the d2d_step_many leg (EPISODE_LENGTH); 0/1 skips it')
     ap.add_argument('--skip-e2e', action='store_true')
     ap.add_argument('--skip-cpu-baseline', action='store_true')
     args = ap.parse_args()
