@@ -28,7 +28,7 @@ class D2DConfig(C.Structure):
                 ('num_rbs', C.c_int32), ('num_cues', C.c_int32), ('num_due_pairs', C.c_int32),
                 ('n_pwr_cue', C.c_int32), ('n_pwr_due', C.c_int32), ('episode_length', C.c_int32),
                 ('path_loss_model', C.c_int32), ('obs_fn', C.c_int32), ('reward_fn', C.c_int32),
-                ('reserved0', C.c_int32),
+                ('num_downlinks', C.c_int32), ('n_pwr_mbs', C.c_int32), ('reserved0', C.c_int32),
                 ('carrier_freq_GHz', C.c_double), ('ple', C.c_double), ('cell_radius_m', C.c_double),
                 ('d2d_radius_m', C.c_double), ('min_capacity_mbps', C.c_double), ('reward_param', C.c_double)]
 

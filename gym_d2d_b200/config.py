@@ -53,6 +53,9 @@ class EnvConfig:
     channel_bandwidth_MHz: float = 20.0
     device_config_file: Optional[Path] = None
     devices: Dict[str, dict] = field(init=False, default_factory=dict)
+    # not a reference field: set by VecD2DEnv(downlink=True) to append the DOWNLINK links 'mbs:cueXX' that D2DEnv.step
+    # accepts (envs/d2d_env.py:87-89) after the canonical uplink + sidelink ones
+    downlinks: bool = field(init=False, default=False)
 
     def __post_init__(self) -> None:
         self.devices = self.load_device_config()
@@ -67,7 +70,7 @@ class EnvConfig:
     # ---- derived sizes -----------------------------------------------------------------------
     @property
     def num_links(self) -> int:
-        return self.num_cues + self.num_due_pairs
+        return self.num_cues + self.num_due_pairs + (self.num_cues if self.downlinks else 0)
 
     @property
     def num_devices(self) -> int:
@@ -93,6 +96,8 @@ class EnvConfig:
         C = self.num_cues
         links = [(ids[1 + j], BASE_STATION_ID) for j in range(C)]
         links += [(ids[1 + C + 2 * d], ids[2 + C + 2 * d]) for d in range(self.num_due_pairs)]
+        if self.downlinks:
+            links += [(BASE_STATION_ID, ids[1 + j]) for j in range(C)]      # envs/d2d_env.py:87-89
         return links
 
     def link_keys(self) -> List[str]:
@@ -162,7 +167,8 @@ def link_table(config: EnvConfig) -> List[dict]:
             rx_noise_dBm=float(rx['thermal_noise_dBm']),                                               # device.py:117-119
             rx_sensitivity_dBm=float(rx['noise_figure_dB'] + rx['thermal_noise_dBm'] + rx['sinr_dB']),   # device.py:74-80
             tx_rb_bandwidth_kHz=float(int(tx['num_subcarriers']) * int(tx['subcarrier_spacing_kHz'])),   # device.py:85-95
-            link_type=_lib.LINK_UPLINK if j < config.num_cues else _lib.LINK_SIDELINK,
+            link_type=(_lib.LINK_UPLINK if j < config.num_cues else
+                       _lib.LINK_SIDELINK if j < config.num_cues + config.num_due_pairs else _lib.LINK_DOWNLINK),
             path_loss_const_dB=float(hata[1][rx_id]) if hata else 0.0))
     return rows
 
@@ -182,6 +188,7 @@ def to_c_config(config: EnvConfig, num_envs: int, cuda_device: int, obs_enum: in
                           num_rbs=config.num_rbs, num_cues=config.num_cues, num_due_pairs=config.num_due_pairs,
                           n_pwr_cue=npw['cue'], n_pwr_due=npw['due'], episode_length=EPISODE_LENGTH,
                           path_loss_model=pl_enum, obs_fn=obs_enum, reward_fn=reward_enum,
+                          num_downlinks=config.num_cues if config.downlinks else 0, n_pwr_mbs=npw['mbs'],
                           carrier_freq_GHz=float(config.carrier_freq_GHz), ple=ple,
                           cell_radius_m=float(config.cell_radius_m), d2d_radius_m=float(config.d2d_radius_m),
                           min_capacity_mbps=float(reward_param) if reward_enum == _lib.REWARD_SYSTEM_CAPACITY else 0.0,

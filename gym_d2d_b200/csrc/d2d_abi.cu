@@ -56,6 +56,7 @@ struct d2d_handle {
     D2DLinkA *dA = nullptr;
     D2DLinkB *dB = nullptr;
     D2DLinkD *dD = nullptr;
+    int32_t *dMeta = nullptr;  // [N] power levels | SIDELINK << 16 (general-topology kernel, fp64 helpers)
     float *dPwr = nullptr;
     double *dPwrD = nullptr;
     // bound state (caller-owned)
@@ -115,7 +116,7 @@ D2DParams make_params(const d2d_handle *h, const d2d_step_io_t *io) {
     P.uniform = h->uniform ? 1 : 0;
     P.reward_fn = h->cfg.reward_fn;
     P.ple_d = h->ple;
-    P.linkA = h->dA; P.linkB = h->dB; P.linkD = h->dD; P.pwr_lin = h->dPwr; P.pwr_lin_d = h->dPwrD;
+    P.linkA = h->dA; P.linkB = h->dB; P.linkD = h->dD; P.link_meta = h->dMeta; P.pwr_lin = h->dPwr; P.pwr_lin_d = h->dPwrD;
     P.pos = h->pos; P.pos64 = h->pos64; P.step_count = h->step_count; P.stats = h->stats;
     P.actions = io->actions; P.obs = io->obs; P.cap = io->capacity_mbps; P.reward = io->reward;
     P.done = io->done; P.rate = io->rate_bps; P.rb_out = io->rb; P.pwr_out = io->tx_pwr_dBm;
@@ -202,6 +203,10 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
     if (cfg->num_envs < 1) return fail(D2D_ERR_INVALID_ARG, "d2d_create: num_envs must be >= 1");
     if (cfg->num_rbs < 1 || cfg->num_cues < 0 || cfg->num_due_pairs < 0 || cfg->num_cues + cfg->num_due_pairs < 1)
         return fail(D2D_ERR_INVALID_ARG, "d2d_create: need num_rbs >= 1 and at least one link");
+    if (cfg->num_downlinks != 0 && cfg->num_downlinks != cfg->num_cues)
+        return fail(D2D_ERR_INVALID_ARG, "d2d_create: num_downlinks must be 0 or num_cues (one 'mbs:cueXX' link per CUE)");
+    if (cfg->num_downlinks && (cfg->n_pwr_mbs < 1 || cfg->n_pwr_mbs > D2D_MAX_PWR_LEVELS))
+        return fail(D2D_ERR_UNSUPPORTED, "d2d_create: n_pwr_mbs must be in [1, 128]");
     if (cfg->n_pwr_cue < 1 || cfg->n_pwr_due < 1 || cfg->n_pwr_cue > D2D_MAX_PWR_LEVELS || cfg->n_pwr_due > D2D_MAX_PWR_LEVELS)
         return fail(D2D_ERR_UNSUPPORTED, "d2d_create: power levels per link must be in [1, 128]");
     if (cfg->num_rbs > 32767) return fail(D2D_ERR_UNSUPPORTED, "d2d_create: num_rbs must be <= 32767");
@@ -221,7 +226,7 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
     d2d_handle *h = new (std::nothrow) d2d_handle();
     if (!h) return fail(D2D_ERR_INVALID_ARG, "d2d_create: out of host memory");
     h->cfg = *cfg;
-    h->N = cfg->num_cues + cfg->num_due_pairs;
+    h->N = cfg->num_cues + cfg->num_due_pairs + cfg->num_downlinks;
     h->V = 1 + cfg->num_cues + 2 * cfg->num_due_pairs;
     h->ple = ple;
     h->ple2 = ple == 2.0;
@@ -244,13 +249,14 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
     std::vector<D2DLinkA> A(h->N);
     std::vector<D2DLinkB> B(h->N);
     std::vector<D2DLinkD> Dv(h->N);
+    std::vector<int32_t> meta(h->N);
     for (int j = 0; j < h->N; ++j) {
         const d2d_link_t &L = links[j];
-        const bool cue = j < cfg->num_cues;
-        const int expect = cue ? D2D_LINK_UPLINK : D2D_LINK_SIDELINK;
+        const bool cue = j < cfg->num_cues, down = j >= cfg->num_cues + cfg->num_due_pairs;
+        const int expect = cue ? D2D_LINK_UPLINK : down ? D2D_LINK_DOWNLINK : D2D_LINK_SIDELINK;
         if (L.link_type != expect)
             return bail(fail(D2D_ERR_UNSUPPORTED, "d2d_create: link " + std::to_string(j) +
-                                                      " has an unsupported link_type (CUE uplinks then DUE sidelinks)"));
+                                                      " has an unsupported link_type (CUE uplinks, DUE sidelinks, then MBS downlinks)"));
         // the path-loss constant K belongs to the RECEIVER (CostHata: A(h_tx, h_rx) - 3 B; log-distance: one K for all), so it
         // is folded into the victim's constants and the radiated weights w carry none: I_true = 10^(-K_rx/10) sum w_k g_k
         const double Kj = cfg->path_loss_model == D2D_PL_COST_HATA ? L.path_loss_const_dB : h->K_dB;
@@ -261,8 +267,10 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
         A[j].snr0_dB = (float)snr0;
         B[j].sens_dBm = (float)L.rx_sensitivity_dBm;
         B[j].bw_MHz = (float)(1e-6 * (L.tx_rb_bandwidth_kHz * 1000.0));
-        B[j].tx_dev = cue ? 1 + j : 1 + cfg->num_cues + 2 * (j - cfg->num_cues);
-        B[j].rx_dev = cue ? 0 : B[j].tx_dev + 1;
+        // envs/d2d_env.py:80-91: uplink cue j -> mbs; sidelink due pair; downlink mbs -> cue (j - C - D)
+        B[j].tx_dev = cue ? 1 + j : down ? 0 : 1 + cfg->num_cues + 2 * (j - cfg->num_cues);
+        B[j].rx_dev = cue ? 0 : down ? 1 + (j - cfg->num_cues - cfg->num_due_pairs) : B[j].tx_dev + 1;
+        meta[j] = (cue ? cfg->n_pwr_cue : down ? cfg->n_pwr_mbs : cfg->n_pwr_due) | ((!cue && !down) ? 1 << 16 : 0);
         Dv[j].a_lin = std::pow(10.0, snr0 / 10.0);
         Dv[j].t_lin = std::pow(10.0, L.tx_eirp_offset_dB / 10.0);
         Dv[j].inv_noise = std::pow(10.0, -(Kj + L.rx_noise_dBm) / 10.0);
@@ -270,8 +278,8 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
     }
     // one set of constants per link type (no per-device overrides)?  Then the default-shape kernel reads them from
     // the constant bank instead of a shared-memory table
-    h->uniform = true;
-    for (int j = 0; j < h->N; ++j) {
+    h->uniform = cfg->num_downlinks == 0;
+    for (int j = 0; j < h->N && !cfg->num_downlinks; ++j) {
         const int j0 = j < cfg->num_cues ? 0 : cfg->num_cues;
         if (std::memcmp(&A[j], &A[j0], sizeof(D2DLinkA)) != 0 || B[j].sens_dBm != B[j0].sens_dBm || B[j].bw_MHz != B[j0].bw_MHz)
             h->uniform = false;
@@ -296,6 +304,8 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
     D2D_CUDA_BAIL(cudaMalloc(&h->dA, sizeof(D2DLinkA) * h->N));
     D2D_CUDA_BAIL(cudaMalloc(&h->dB, sizeof(D2DLinkB) * h->N));
     D2D_CUDA_BAIL(cudaMalloc(&h->dD, sizeof(D2DLinkD) * h->N));
+    D2D_CUDA_BAIL(cudaMalloc(&h->dMeta, sizeof(int32_t) * h->N));
+    D2D_CUDA_BAIL(cudaMemcpy(h->dMeta, meta.data(), sizeof(int32_t) * h->N, cudaMemcpyHostToDevice));
     D2D_CUDA_BAIL(cudaMalloc(&h->dPwr, sizeof(pwr)));
     D2D_CUDA_BAIL(cudaMalloc(&h->dPwrD, sizeof(pwr_d)));
     D2D_CUDA_BAIL(cudaMemcpy(h->dPwrD, pwr_d, sizeof(pwr_d), cudaMemcpyHostToDevice));
@@ -306,7 +316,7 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
 #undef D2D_CUDA_BAIL
 
     // warp kernel: one lane slot per CUE and per DUE pair, one shared-memory bin per RB
-    h->use_warp = cfg->num_cues <= 32 && cfg->num_due_pairs <= 32 && cfg->num_rbs <= 64;
+    h->use_warp = cfg->num_cues <= 32 && cfg->num_due_pairs <= 32 && cfg->num_rbs <= 64 && cfg->num_downlinks == 0;
     if (const char *c = std::getenv("D2D_B200_CHUNK")) h->chunk_override = std::atoll(c);
     const char *pdl = std::getenv("D2D_B200_PDL");
     h->pdl = !(pdl && std::strcmp(pdl, "0") == 0);
@@ -322,7 +332,8 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
         rc = h->wpb == 8 ? plan_warp<8>(h, smem) : plan_warp<4>(h, smem);
     } else {
         // <= 1024 links: the register-resident block kernel, LPT links per thread; beyond: everything staged in shared memory
-        h->lpt = h->N <= D2D_BLOCK_THREADS * D2D_BLOCK_MAX_LPT ? (h->N + D2D_BLOCK_THREADS - 1) / D2D_BLOCK_THREADS : 0;
+        h->lpt = (h->N <= D2D_BLOCK_THREADS * D2D_BLOCK_MAX_LPT && cfg->num_downlinks == 0)
+                     ? (h->N + D2D_BLOCK_THREADS - 1) / D2D_BLOCK_THREADS : 0;      // downlinks: the general-topology kernel
         const size_t smem = h->lpt ? d2d_block2_smem_bytes(h->N, cfg->num_rbs) : d2d_block_smem_bytes(h->N, cfg->num_rbs);
         if (smem > 227 * 1024) return bail(fail(D2D_ERR_UNSUPPORTED, "d2d_create: too many links / RBs for one SM's shared memory"));
 #define D2D_PLAN_BLOCK(LPT_) (h->ple2 ? plan_geometry(h, d2d_step_block_kernel<true, LPT_>, D2D_BLOCK_THREADS, smem, 1) \
@@ -345,7 +356,7 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
 
 D2D_API int d2d_destroy(d2d_handle_t *h) {
     if (!h) return D2D_OK;
-    cudaFree(h->dA); cudaFree(h->dB); cudaFree(h->dD); cudaFree(h->dPwr); cudaFree(h->dPwrD); cudaFree(h->stage_pos);
+    cudaFree(h->dA); cudaFree(h->dB); cudaFree(h->dD); cudaFree(h->dMeta); cudaFree(h->dPwr); cudaFree(h->dPwrD); cudaFree(h->stage_pos);
     for (auto &slot : h->stage2)
         for (void *p : slot) cudaFree(p);
     if (h->pipe_ready) {
@@ -505,12 +516,10 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, void *stream) {
         double *stats = h->cfg.reward_fn != D2D_REWARD_SYSTEM_CAPACITY ? h->stats : nullptr;
         if (warp_team)
             d2d_agent_reward_kernel<32><<<grid, 256, smem, st>>>(io->actions, io->obs, io->agent_reward, io->reward, stats, total, h->N,
-                                                                h->cfg.num_cues, h->cfg.num_rbs, h->cfg.n_pwr_cue, h->cfg.n_pwr_due,
-                                                                h->cfg.reward_fn, (float)h->cfg.reward_param);
+                                                                h->dMeta, h->cfg.num_rbs, h->cfg.reward_fn, (float)h->cfg.reward_param);
         else
             d2d_agent_reward_kernel<256><<<grid, 256, smem, st>>>(io->actions, io->obs, io->agent_reward, io->reward, stats, total, h->N,
-                                                                 h->cfg.num_cues, h->cfg.num_rbs, h->cfg.n_pwr_cue, h->cfg.n_pwr_due,
-                                                                 h->cfg.reward_fn, (float)h->cfg.reward_param);
+                                                                 h->dMeta, h->cfg.num_rbs, h->cfg.reward_fn, (float)h->cfg.reward_param);
         D2D_CUDA(cudaGetLastError());
         ++h->launches;
     }

@@ -108,7 +108,7 @@ __global__ void d2d_per_agent_obs_kernel(const float *__restrict__ table, float 
 template <int TEAM>
 __global__ void d2d_agent_reward_kernel(const int32_t *__restrict__ actions, const float *__restrict__ obs,
                                         float *__restrict__ agent_reward, float *__restrict__ reward, double *__restrict__ stats,
-                                        int64_t num_envs, int N, int C, int R, int n_pwr_cue, int n_pwr_due, int mode, float param) {
+                                        int64_t num_envs, int N, const int32_t *__restrict__ link_meta, int R, int mode, float param) {
     extern __shared__ uint32_t d2d_weak_smem[];
     const int teams = blockDim.x / TEAM, team = threadIdx.x / TEAM, tl = threadIdx.x % TEAM;
     uint32_t *weak = d2d_weak_smem + (size_t)team * R;
@@ -124,16 +124,16 @@ __global__ void d2d_agent_reward_kernel(const int32_t *__restrict__ actions, con
             for (int r = tl; r < R; r += TEAM) weak[r] = 0u;
             team_sync();
             for (int j = tl; in && j < N; j += TEAM) {
-                const int npw = j < C ? n_pwr_cue : n_pwr_due;
+                const int meta = link_meta[j], npw = meta & 0xffff;          // power levels | SIDELINK << 16
                 const uint32_t a = (uint32_t)act[j];
-                if (j < C && a < (uint32_t)(R * npw) && ob[j * 6 + 4] < param) atomicAdd(&weak[a / (uint32_t)npw], 1u);
+                if (!(meta >> 16) && a < (uint32_t)(R * npw) && ob[j * 6 + 4] < param) atomicAdd(&weak[a / (uint32_t)npw], 1u);
             }
             team_sync();
         }
         float sum = 0.f;
         int n_act = 0;
         for (int j = tl; in && j < N; j += TEAM) {
-            const int npw = j < C ? n_pwr_cue : n_pwr_due;
+            const int meta = link_meta[j], npw = meta & 0xffff;
             const uint32_t a = (uint32_t)act[j];
             const bool live = a < (uint32_t)(R * npw);
             float rw = 0.f;
@@ -142,7 +142,7 @@ __global__ void d2d_agent_reward_kernel(const int32_t *__restrict__ actions, con
                 const float shannon = d2d_log2_1p(d2d_ex2(sinr * 0.33219280948873623f));     // log2(1 + 10^(sinr/10))
                 if (mode == 0) rw = reward[e];
                 else if (mode == 1) rw = sinr >= param ? shannon : -1.0f;
-                else rw = weak[a / (uint32_t)npw] - ((j < C && sinr < param) ? 1u : 0u) > 0u ? -1.0f : shannon;
+                else rw = weak[a / (uint32_t)npw] - ((!(meta >> 16) && sinr < param) ? 1u : 0u) > 0u ? -1.0f : shannon;
                 sum += rw;
                 ++n_act;
             }

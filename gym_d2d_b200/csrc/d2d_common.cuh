@@ -73,6 +73,7 @@ struct D2DParams {
     const D2DLinkA *linkA;       // [N]
     const D2DLinkB *linkB;       // [N]
     const D2DLinkD *linkD;       // [N]
+    const int32_t *link_meta;    // [N] general-topology kernel: power levels of the link's action space | (1 << 16 if SIDELINK)
     const float *pwr_lin;        // [D2D_MAX_PWR_LEVELS] 10^(p/10), correctly rounded from fp64
     const double *pwr_lin_d;     // same table in fp64 (rescue path)
     // state
@@ -214,7 +215,7 @@ __device__ __forceinline__ double d2d_gain_f64(double d2, double ple) {
 // integer Tx power of link k re-derived from the env's raw action row (envs/d2d_env.py:96)
 __device__ __forceinline__ int d2d_pwr_of(const int32_t *act_env, int k, const D2DParams &P) {
     const int a = act_env[k];
-    const int npw = k < P.C ? P.n_pwr_cue : P.n_pwr_due;
+    const int npw = P.link_meta[k] & 0xffff;
     return (a - (a / npw) * npw) & (D2D_MAX_PWR_LEVELS - 1);
 }
 __device__ __forceinline__ int d2d_tx_dev(int k, int C) { return k < C ? 1 + k : 1 + C + 2 * (k - C); }
@@ -229,7 +230,7 @@ __device__ __forceinline__ double2 d2d_pos_f64(const float2 *pe32, const double2
 template <bool PLE2>
 __device__ __forceinline__ double d2d_ix_term_f64(int k, double2 rx, const float2 *pe32, const double2 *pe64,
                                                   const int32_t *act_env, const D2DParams &P) {
-    const double2 tk = d2d_pos_f64(pe32, pe64, d2d_tx_dev(k, P.C));
+    const double2 tk = d2d_pos_f64(pe32, pe64, P.linkB[k].tx_dev);
     const double ex = tk.x - rx.x, ey = tk.y - rx.y;
     return P.pwr_lin_d[d2d_pwr_of(act_env, k, P)] * P.linkD[k].t_lin * d2d_gain_f64<PLE2>(ex * ex + ey * ey, P.ple_d);
 }

@@ -8,7 +8,8 @@
 //
 // Two kernels: d2d_step_block_kernel<PLE2, LPT> keeps a thread's <= LPT links in registers between the phases and
 // scatters full peer records (N <= 256 LPT, LPT <= 4: every configuration up to 1024 links, incl. config #3);
-// d2d_step_block_generic_kernel stages everything in shared memory and takes any N <= 65535.
+// d2d_step_block_generic_kernel stages everything in shared memory, takes any N <= 65535 and any link topology (each
+// link's transmitter / receiver device and action space come from tables): it also serves envs with DOWNLINK actions.
 #pragma once
 
 #include "d2d_common.cuh"
@@ -58,7 +59,7 @@ __device__ __forceinline__ D2DBlockSmemView d2d_block_carve(unsigned char *raw, 
 template <bool PLE2>
 __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_generic_kernel(const D2DParams P) {
     extern __shared__ __align__(16) unsigned char d2d_smem_raw[];
-    const int N = P.N, C = P.C, V = P.V, nbins = P.nbins;
+    const int N = P.N, V = P.V, nbins = P.nbins;
     D2DBlockSmemView S = d2d_block_carve(d2d_smem_raw, N, nbins);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     d2d_pdl_launch_dependents();
@@ -68,7 +69,6 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_generic_kern
         S.linkB[i] = reinterpret_cast<const float4 *>(P.linkB)[i];
     }
     for (int i = tid; i < D2D_MAX_PWR_LEVELS; i += D2D_BLOCK_THREADS) S.pwr_lin[i] = P.pwr_lin[i];
-    const uint32_t magic_cue = d2d_div_magic(P.n_pwr_cue), magic_due = d2d_div_magic(P.n_pwr_due);
 
     double st_reward = 0.0, st_cap = 0.0, st_reward2 = 0.0, st_pen = 0.0, st_resc = 0.0, st_n = 0.0;
     d2d_pdl_wait();
@@ -79,20 +79,21 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_generic_kern
         for (int i = tid; i < nbins; i += D2D_BLOCK_THREADS) S.bin_cnt[i] = 0;
         __syncthreads();
 
-        // phase 1: decode (envs/d2d_env.py:93-101), stage link records, count links per RB bin
+        // phase 1: decode (envs/d2d_env.py:93-101), stage link records, count links per RB bin.  Transmitter / receiver
+        // devices and the action space's power levels come from the link tables (envs/d2d_env.py:80-91: by tx membership)
         for (int j = tid; j < N; j += D2D_BLOCK_THREADS) {
-            const bool cue = j < C;
-            const int txd = cue ? 1 + j : 1 + C + 2 * (j - C), rxd = cue ? 0 : txd + 1;
+            const int meta = P.link_meta[j], npw = meta & 0xffff;
+            const int txd = __float_as_int(S.linkB[j].z), rxd = __float_as_int(S.linkB[j].w);
             const int a = __ldg(act + j);
             const float2 t = __ldg(pe + txd), r = __ldg(pe + rxd);
-            const bool active = a >= 0;
-            const int npw = cue ? P.n_pwr_cue : P.n_pwr_due;
-            const int rb = d2d_div(a, cue ? magic_cue : magic_due), p = a - rb * npw;
-            const uint32_t key = active ? (uint32_t)rb : (D2D_INACTIVE_KEY | (uint32_t)j);
+            const bool active = a >= 0 && a < P.R * npw;         // valid actions: 0 <= a < R n_pwr (envs/d2d_env.py:36-40)
+            const int rb = active ? a / npw : 0, p = active ? a - rb * npw : 0;
+            // key: the RB, bit 29 marks a SIDELINK (reward_fn.py:31-37); absent agents get a key nobody shares
+            const uint32_t key = active ? (uint32_t)rb | ((uint32_t)(meta >> 16) << 29) : (D2D_INACTIVE_KEY | (uint32_t)j);
             const float pl = active ? S.pwr_lin[p & (D2D_MAX_PWR_LEVELS - 1)] : 0.0f;
             S.rec[j] = make_float4(t.x, t.y, pl * S.linkA[j].x, __uint_as_float(key));
             S.aux[j] = make_float4(r.x, r.y, pl, __int_as_float(active ? p : -1));
-            if (active) S.slot[j] = atomicAdd(&S.bin_cnt[key % (uint32_t)nbins], 1);
+            if (active) S.slot[j] = atomicAdd(&S.bin_cnt[rb % nbins], 1);
         }
         __syncthreads();
 
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_generic_kern
         __syncthreads();
         for (int j = tid; j < N; j += D2D_BLOCK_THREADS) {
             const uint32_t key = __float_as_uint(S.rec[j].w);
-            if (!(key & D2D_INACTIVE_KEY)) S.sorted[S.bin_off[key % (uint32_t)nbins] + S.slot[j]] = (uint16_t)j;
+            if (!(key & D2D_INACTIVE_KEY)) S.sorted[S.bin_off[(key & 0x1fffffffu) % (uint32_t)nbins] + S.slot[j]] = (uint16_t)j;
         }
         __syncthreads();
 
@@ -127,18 +128,19 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_generic_kern
             const bool active = p >= 0;
             D2DLinkOut o = {0.f, 0.f, 0.f, 0.f};
             if (active) {
-                const int b = key % (uint32_t)nbins, beg = S.bin_off[b], end = beg + S.bin_cnt[b];
+                const uint32_t rbkey = key & 0x1fffffffu;
+                const int b = rbkey % (uint32_t)nbins, beg = S.bin_off[b], end = beg + S.bin_cnt[b];
                 float I = 0.0f, dmin2 = 3.0e38f;
                 bool side = false;
                 for (int q = beg; q < end; ++q) {
                     const int k = S.sorted[q];
                     const float4 rk = S.rec[k];
-                    if (k != j && __float_as_uint(rk.w) == key) {
+                    if (k != j && (__float_as_uint(rk.w) & 0x9fffffffu) == rbkey) {
                         const float dx = rk.x - xj.x, dy = rk.y - xj.y;
                         const float d2 = fmaf(dx, dx, dy * dy);
                         I = fmaf(rk.z, d2d_gain<PLE2>(d2, P.neg_half_ple), I);
                         dmin2 = fminf(dmin2, d2);
-                        side |= (k >= C);
+                        side |= (__float_as_uint(rk.w) >> 29) & 1u;
                     }
                 }
                 const float4 Av = S.linkA[j], Bv = S.linkB[j];
@@ -149,18 +151,18 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_generic_kern
                 o = d2d_link_epilogue<PLE2>(p, xj.z, lg, PLE2 ? d2d_rcp(d2own) : d2d_ex2(P.neg_half_ple * lg), I, Av, sb, P);
                 if (D2D_RESCUE_ENABLED && d2d_needs_rescue<true>(o, fminf(dmin2, d2own), P)) {   // rare: fp64 pass (d2d_common.cuh)
                     const double2 *pe64 = P.pos64 ? reinterpret_cast<const double2 *>(P.pos64) + e * V : nullptr;
-                    const double2 rx = d2d_pos_f64(pe, pe64, d2d_rx_dev(j, C));
+                    const double2 rx = d2d_pos_f64(pe, pe64, __float_as_int(Bv.w));
                     double I64 = 0.0;
                     for (int q = beg; q < end; ++q) {
                         const int k = S.sorted[q];
-                        if (k != j && __float_as_uint(S.rec[k].w) == key) I64 += d2d_ix_term_f64<PLE2>(k, rx, pe, pe64, act, P);
+                        if (k != j && (__float_as_uint(S.rec[k].w) & 0x9fffffffu) == rbkey) I64 += d2d_ix_term_f64<PLE2>(k, rx, pe, pe64, act, P);
                     }
-                    o = d2d_link_f64<PLE2>(j, d2d_pos_f64(pe, pe64, d2d_tx_dev(j, C)), rx, I64, sb.x, act, P);
+                    o = d2d_link_f64<PLE2>(j, d2d_pos_f64(pe, pe64, __float_as_int(Bv.z)), rx, I64, sb.x, act, P);
                     ++resc;
                 }
                 cap_part += o.cap;
                 ++n_act;
-                bad |= (j < C && side && o.cap <= P.min_cap);   // envs/reward_fn.py:30-39
+                bad |= (!((key >> 29) & 1u) && side && o.cap <= P.min_cap);   // envs/reward_fn.py:30-39: a non-SIDELINK link
             }
             const int64_t g = e * N + j;
             if (P.obs) {
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_generic_kern
             }
             if (P.cap) P.cap[g] = o.cap;
             if (P.rate) P.rate[g] = o.rate;
-            if (P.rb_out) P.rb_out[g] = active ? (int16_t)key : (int16_t)0;
+            if (P.rb_out) P.rb_out[g] = active ? (int16_t)(key & 0x1fffffffu) : (int16_t)0;
             if (P.pwr_out) P.pwr_out[g] = active ? (int16_t)p : (int16_t)0;
         }
 

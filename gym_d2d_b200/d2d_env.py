@@ -9,7 +9,7 @@ dict building only.
 Documented divergences from the reference:
   * custom / unimplemented plugin classes are rejected at construction (north star);
   * negative or out-of-range integer actions raise ValueError (the reference decodes them silently, B.9);
-  * 'mbs:cueXX' downlink keys raise NotImplementedError (B.8; SURVEY section 8f rank 3);
+  * the first 'mbs:cueXX' downlink key (B.8) moves the env to the general-topology kernel (2C + D links);
   * device positions come from a Philox stream keyed by `seed`, not Python's global `random` (section 3.2).
 """
 from __future__ import annotations
@@ -30,13 +30,21 @@ class D2DEnv:
 
     def __init__(self, env_config: Optional[dict] = None, device: Any = 'cuda', seed: int = 0) -> None:
         env_config = env_config or {}
+        self._ctor = (dict(env_config), device, seed)      # to rebuild the env with DOWNLINK links on the first 'mbs:' key
         # VecD2DEnv pops 'obs_fn' / 'reward_fn' from the caller's dict exactly like envs/d2d_env.py:27-28
         self.vec = VecD2DEnv(1, env_config, device=device, seed=seed, info=True, exact_positions=True)
+        self._bind_vec()
+        self.actions: Optional[Dict[str, Tuple[int, int]]] = None
+        self.state: Optional[dict] = None
+        self.num_steps = 0
+        self._present: List[int] = []
+
+    def _bind_vec(self) -> None:
         cfg = self.vec.config
         self.config = cfg
         r = cfg.cell_radius_m
         # envs/obs_fn.py:36-41
-        self.observation_space = Box(low=-r, high=r, shape=(6 * cfg.num_links,))
+        self.observation_space = Box(low=-r, high=r, shape=(6 * (cfg.num_cues + cfg.num_due_pairs),))
         self.num_pwr_actions = cfg.num_pwr_actions                               # envs/d2d_env.py:31-35
         self.action_space = DictSpace({k: Discrete(cfg.num_rbs * n) for k, n in
                                        (('due', self.num_pwr_actions['due']), ('cue', self.num_pwr_actions['cue']),
@@ -48,10 +56,19 @@ class D2DEnv:
         self._cues = set(self.device_ids[1:1 + cfg.num_cues])
         self._due_tx = {t for (t, _r) in cfg.link_ids()[cfg.num_cues:]}
         self._host = self.vec.alloc_host_outputs(pinned=False, info=True)
-        self.actions: Optional[Dict[str, Tuple[int, int]]] = None
-        self.state: Optional[dict] = None
-        self.num_steps = 0
-        self._present: List[int] = []
+
+    def _enable_downlink(self) -> None:
+        """envs/d2d_env.py:87-89: a key whose transmitter is neither a DUE nor a CUE is a DOWNLINK action of the MBS.  The
+        canonical uplink / sidelink link indices are unchanged; C downlink links are appended."""
+        cfg, device, seed = self._ctor
+        old = self.vec
+        new = VecD2DEnv(1, dict(cfg), device=device, seed=seed, info=True, exact_positions=True, downlink=True)
+        new.set_positions(old.positions_f64)
+        new.step_count.copy_(old.step_count)
+        new._episode = old._episode
+        old.close()
+        self.vec = new
+        self._bind_vec()
 
     # ---- helpers ------------------------------------------------------------------------------
     def _decode_action(self, key: str, action: Any) -> int:
@@ -63,8 +80,6 @@ class D2DEnv:
             if id_ not in self._device_set:
                 raise KeyError(id_)                                   # devices.py:28
         if key not in self._link_index:
-            if tx_id == BASE_STATION_ID:
-                raise NotImplementedError(f'downlink action "{key}" is not implemented by the CUDA path')
             raise KeyError(key)
         j = self._link_index[key]
         n = int(self.vec.action_nvec[j])
@@ -74,6 +89,9 @@ class D2DEnv:
         return a
 
     def _step_arrays(self, raw_actions: Dict[str, Any]) -> List[str]:
+        if not self.vec.config.downlinks and any(isinstance(k, str) and k.startswith(BASE_STATION_ID + ':') and
+                                                 k.partition(':')[2] in self._cues for k in raw_actions):
+            self._enable_downlink()                                    # envs/d2d_env.py:87-89: DOWNLINK actions of the MBS
         acts = np.full((1, self.config.num_links), -1, np.int32)      # -1: agent absent (Appendix B.8)
         keys = []
         for key, action in raw_actions.items():                       # caller's insertion order (envs/d2d_env.py:75)
@@ -116,7 +134,8 @@ class D2DEnv:
                 if idx and id_ in file_devices and 'position' in file_devices[id_]:
                     pos[idx] = file_devices[id_]['position']
             self.vec.set_positions(pos[None])
-        raw = {k: self.action_space['cue' if k.startswith('cue') else 'due'].sample() for k in self.link_keys}
+        raw = {k: self.action_space['cue' if k.startswith('cue') else 'due'].sample() for k in self.link_keys
+               if not k.startswith(BASE_STATION_ID + ':')}             # envs/d2d_env.py:54-60: uplinks and sidelinks only
         self.vec._bind(False)                                          # the reset step is not counted
         try:
             keys = self._step_arrays(raw)

@@ -53,6 +53,8 @@ class VecD2DEnv:
     seed, global_env_offset : Philox key and the global index of local env 0; a sharded batch draws the
         same scenario for a given global env whatever the number of GPUs.
     info : also return rate_bps / rb / tx_pwr_dbm tensors (the reference's info dict, envs/d2d_env.py:106-116).
+    downlink : also carry one DOWNLINK link 'mbs:cueXX' per CUE after the canonical links (N = 2C + D; absent unless an
+        action >= 0 is given).  Such envs run on the general-topology kernel.
     exact_positions : keep a float64 shadow of positions given through set_positions().  The hot path still
         reads the fp32 state; the shadow is read only by the kernels' rare fp64 recomputation path, so that
         results stay within 1e-4 relative of the reference evaluated on the caller's UNROUNDED float64
@@ -60,12 +62,13 @@ class VecD2DEnv:
     """
 
     def __init__(self, num_envs: int, env_config: Optional[dict] = None, device: Any = 'cuda', seed: int = 0,
-                 global_env_offset: int = 0, info: bool = False, exact_positions: bool = False) -> None:
+                 global_env_offset: int = 0, info: bool = False, exact_positions: bool = False, downlink: bool = False) -> None:
         env_config = env_config if env_config is not None else {}
         obs_enum = resolve_obs_fn(env_config.pop('obs_fn', LinearObsFunction))
         reward_enum, min_cap = resolve_reward_fn(env_config.pop('reward_fn', SystemCapacityRewardFunction))
         self.per_agent_reward = reward_enum != _lib.REWARD_SYSTEM_CAPACITY   # envs/reward_fn.py:47-78 reward every agent separately
         self.config = EnvConfig(**env_config)          # unknown key -> TypeError, like the reference dataclass
+        self.config.downlinks = bool(downlink)         # also carry the 'mbs:cueXX' DOWNLINK links (envs/d2d_env.py:87-89)
         self.num_envs = int(num_envs)
         if self.num_envs < 1:
             raise ValueError('num_envs must be >= 1')
@@ -83,7 +86,8 @@ class VecD2DEnv:
         npw = self.num_pwr_actions
         # envs/d2d_env.py:36-40: Discrete(num_rbs * n_pwr) per transmitter type
         self.action_nvec = np.array([self.config.num_rbs * npw['cue']] * self.config.num_cues
-                                    + [self.config.num_rbs * npw['due']] * self.config.num_due_pairs, np.int64)
+                                    + [self.config.num_rbs * npw['due']] * self.config.num_due_pairs
+                                    + [self.config.num_rbs * npw['mbs']] * (self.config.num_cues if downlink else 0), np.int64)
         self.episode_length = EPISODE_LENGTH
         self.want_info = bool(info)
         self._episode = 0
@@ -160,7 +164,10 @@ class VecD2DEnv:
     def sample_actions(self, generator: Optional[torch.Generator] = None) -> torch.Tensor:
         """Uniform draw from the reference's Discrete action spaces (envs/d2d_env.py:36-40, :54-60)."""
         u = torch.rand((self.num_envs, self.num_links), device=self.device, generator=generator)
-        return torch.minimum((u * self._nvec_f).to(torch.int32), self._nvec_m1)
+        a = torch.minimum((u * self._nvec_f).to(torch.int32), self._nvec_m1)
+        if self.config.downlinks:      # reset() draws uplink and sidelink actions only (envs/d2d_env.py:54-60)
+            a[:, self.config.num_cues + self.config.num_due_pairs:] = -1
+        return a
 
     def reset(self, seed: Optional[int] = None, mask: Optional[torch.Tensor] = None,
               initial_actions: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:

@@ -76,6 +76,10 @@ typedef struct d2d_config {
     int32_t path_loss_model;    /* d2d_path_loss_model */
     int32_t obs_fn;             /* d2d_obs_fn */
     int32_t reward_fn;          /* d2d_reward_fn */
+    int32_t num_downlinks;      /* 0, or num_cues: links C+D .. C+D+C-1 are the DOWNLINK actions 'mbs:cueXX' (envs/d2d_env.py:87-89,
+                                   Appendix B.8: never produced by reset(), accepted by step()); the link table then has 2C + D rows
+                                   and the step runs on the general-topology kernel */
+    int32_t n_pwr_mbs;          /* envs/d2d_env.py:34  mbs_max_tx_power_dBm + 1 */
     int32_t reserved0;
     double carrier_freq_GHz;    /* envs/env_config.py:23 */
     double ple;                 /* path_loss.py:43 path-loss exponent (ignored, = 2, for FREE_SPACE) */

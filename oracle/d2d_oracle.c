@@ -102,15 +102,18 @@ static int step_one(const d2d_oracle_cfg *cfg, const d2d_oracle_device *dev, con
                     int32_t *rb_o, int32_t *pwr_o, double *sinr_o, double *snr_o, double *rate_o,
                     double *cap_o, double *obs_o, double *reward_o,
                     int64_t *rb, int64_t *pw, int32_t *txd, int32_t *rxd, double *sinr, double *cap) {
-    const int C = cfg->num_cues, D = cfg->num_due_pairs, N = C + D;
+    const int C = cfg->num_cues, D = cfg->num_due_pairs, N = C + D + (cfg->downlinks ? C : 0);
     const double K = d2d_oracle_pl_constant_dB(cfg->carrier_freq_GHz, cfg->ple);
     int status = 0;
 
-    /* devices.py:20-25 device order; envs/d2d_env.py:55-60 link order; :80-91 link type by tx */
+    /* devices.py:20-25 device order; envs/d2d_env.py:55-60 link order; :80-91 link type by tx:
+     * tx in due_pairs -> SIDELINK / 'due'; tx in cues -> UPLINK / 'cue'; else (the MBS) -> DOWNLINK / 'mbs' */
     for (int j = 0; j < N; ++j) {
-        if (j < C) { txd[j] = 1 + j; rxd[j] = 0; }
-        else { txd[j] = 1 + C + 2 * (j - C); rxd[j] = txd[j] + 1; }
-        d2d_oracle_decode_action((int64_t)act[j], j < C ? cfg->n_pwr_cue : cfg->n_pwr_due, &rb[j], &pw[j]);
+        int64_t n_pwr;
+        if (j < C) { txd[j] = 1 + j; rxd[j] = 0; n_pwr = cfg->n_pwr_cue; }
+        else if (j < C + D) { txd[j] = 1 + C + 2 * (j - C); rxd[j] = txd[j] + 1; n_pwr = cfg->n_pwr_due; }
+        else { txd[j] = 0; rxd[j] = 1 + (j - C - D); n_pwr = cfg->n_pwr_mbs; }
+        d2d_oracle_decode_action((int64_t)act[j], n_pwr, &rb[j], &pw[j]);
     }
 
     int n_present = 0;
@@ -170,9 +173,10 @@ static int step_one(const d2d_oracle_cfg *cfg, const d2d_oracle_device *dev, con
 
     if (reward_o) { /* envs/reward_fn.py:27-44 */
         int bad = 0;
-        for (int i = C; i < N && !bad; ++i) {            /* SIDELINK actions */
+        for (int i = C; i < C + D && !bad; ++i) {        /* SIDELINK actions */
             if (active && !active[i]) continue;
-            for (int k = 0; k < C; ++k) {                /* non-SIDELINK actions on the same RB */
+            for (int k = 0; k < N; ++k) {                /* non-SIDELINK actions (uplink, downlink) on the same RB */
+                if (k >= C && k < C + D) continue;
                 if (active && !active[k]) continue;
                 if (rb[k] == rb[i] && cap[k] <= cfg->min_capacity_mbps) { bad = 1; break; }
             }
@@ -188,7 +192,7 @@ int d2d_oracle_step_batch(const d2d_oracle_cfg *cfg, const d2d_oracle_device *de
                           const uint8_t *active, int32_t *rb, int32_t *pwr,
                           double *sinr_db, double *snr_db, double *rate, double *cap,
                           double *obs, double *reward, int nthreads) {
-    const int C = cfg->num_cues, D = cfg->num_due_pairs, N = C + D, V = 1 + C + 2 * D;
+    const int C = cfg->num_cues, D = cfg->num_due_pairs, N = C + D + (cfg->downlinks ? C : 0), V = 1 + C + 2 * D;
     int status = 0;
 #ifdef _OPENMP
     if (nthreads < 1) nthreads = 1;

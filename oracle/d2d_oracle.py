@@ -37,7 +37,7 @@ class _Cfg(C.Structure):
     _fields_ = [('num_rbs', C.c_int32), ('num_cues', C.c_int32), ('num_due_pairs', C.c_int32),
                 ('n_pwr_cue', C.c_int32), ('n_pwr_due', C.c_int32), ('path_loss_model', C.c_int32),
                 ('carrier_freq_GHz', C.c_double), ('ple', C.c_double), ('min_capacity_mbps', C.c_double),
-                ('area_type', C.c_int32), ('_pad', C.c_int32)]
+                ('area_type', C.c_int32), ('downlinks', C.c_int32), ('n_pwr_mbs', C.c_int32), ('_pad', C.c_int32)]
 
 
 # device.py:12-41 (merged with DEFAULT_DEVICE_CONFIG :12-16)
@@ -67,6 +67,8 @@ class OracleConfig:
     subcarrier_spacing_kHz: int = 15
     ple: float = 2.0
     min_capacity_mbps: float = 0.0
+    mbs_max_tx_power_dBm: int = 46
+    downlinks: bool = False                    # append the DOWNLINK links 'mbs:cueXX' (envs/d2d_env.py:87-89): N = 2C + D
     path_loss_model: str = 'log_distance'      # or 'cost_hata' (path_loss.py:90-123)
     area_type: int = 1                         # path_loss.py:84-87 AreaType value (CostHata only; default SUBURBAN, :91)
     # per-device overrides {device_id: {field: value}} as a device_config_file's 'config' dicts would give
@@ -74,7 +76,7 @@ class OracleConfig:
 
     @property
     def num_links(self) -> int:
-        return self.num_cues + self.num_due_pairs
+        return self.num_cues + self.num_due_pairs + (self.num_cues if self.downlinks else 0)
 
     @property
     def num_devices(self) -> int:
@@ -91,6 +93,8 @@ class OracleConfig:
         """'tx:rx' keys in the canonical link order of envs/d2d_env.py:55-60."""
         keys = [f'cue{i:02d}:mbs' for i in range(self.num_cues)]
         keys += [f'due{i:02d}:due{i + 1:02d}' for i in range(0, 2 * self.num_due_pairs, 2)]
+        if self.downlinks:
+            keys += [f'mbs:cue{i:02d}' for i in range(self.num_cues)]       # envs/d2d_env.py:87-89 DOWNLINK actions
         return keys
 
 
@@ -146,7 +150,8 @@ def _c_cfg(cfg: OracleConfig) -> _Cfg:
                 n_pwr_cue=cfg.cue_max_tx_power_dBm + 1,                               # envs/d2d_env.py:33
                 n_pwr_due=cfg.due_max_tx_power_dBm - cfg.due_min_tx_power_dBm + 1,    # envs/d2d_env.py:32
                 carrier_freq_GHz=cfg.carrier_freq_GHz, ple=cfg.ple, min_capacity_mbps=cfg.min_capacity_mbps,
-                path_loss_model=2 if cfg.path_loss_model == 'cost_hata' else 0, area_type=int(cfg.area_type))
+                path_loss_model=2 if cfg.path_loss_model == 'cost_hata' else 0, area_type=int(cfg.area_type),
+                downlinks=int(bool(cfg.downlinks)), n_pwr_mbs=cfg.mbs_max_tx_power_dBm + 1)            # envs/d2d_env.py:34
 
 
 def device_table(cfg: OracleConfig):
@@ -275,6 +280,9 @@ def random_actions(cfg: OracleConfig, num_envs: int, rng: np.random.Generator) -
     n_cue = cfg.num_rbs * (cfg.cue_max_tx_power_dBm + 1)
     n_due = cfg.num_rbs * (cfg.due_max_tx_power_dBm - cfg.due_min_tx_power_dBm + 1)
     a = np.empty((num_envs, cfg.num_links), np.int32)
-    a[:, :cfg.num_cues] = rng.integers(0, n_cue, (num_envs, cfg.num_cues))
-    a[:, cfg.num_cues:] = rng.integers(0, n_due, (num_envs, cfg.num_due_pairs))
+    C, D = cfg.num_cues, cfg.num_due_pairs
+    a[:, :C] = rng.integers(0, n_cue, (num_envs, C))
+    a[:, C:C + D] = rng.integers(0, n_due, (num_envs, D))
+    if cfg.downlinks:
+        a[:, C + D:] = rng.integers(0, cfg.num_rbs * (cfg.mbs_max_tx_power_dBm + 1), (num_envs, C))
     return a

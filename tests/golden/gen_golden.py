@@ -201,6 +201,46 @@ def cost_hata():
     print('cost_hata ok', out['suburban_sinr_db'][0, 0, :4], out['urban_sinr_db'][0, 0, :4])
 
 
+def downlink():
+    """Appendix B.8 / envs/d2d_env.py:87-89: 'mbs:cueXX' keys create DOWNLINK actions (MBS transmitter, 'mbs' action space with
+    47 power levels).  Uplinks use RBs 0-1, downlinks RBs 2-3 (an uplink and a downlink on one RB put the MBS transmitter at
+    distance 0 from the MBS receiver: math domain error in the reference), sidelinks anywhere; a few agents are absent."""
+    base = dict(num_rbs=4, num_cues=5, num_due_pairs=6)
+    cfg = O.OracleConfig(**base, downlinks=True)
+    rng = np.random.default_rng(61)
+    num_envs, steps = 4, 3
+    pos = O.random_positions(cfg, num_envs, rng)
+    C, D, N = 5, 6, 16
+    env = R.make_env(dict(base))
+    env.reset()
+    keys = cfg.link_keys()
+    out = dict(positions=pos, actions=np.zeros((steps, num_envs, N), np.int32), active=np.zeros((steps, num_envs, N), np.uint8))
+    res = {k: np.zeros((steps, num_envs, N)) for k in ['rb', 'tx_pwr_dbm', 'sinr_db', 'snr_db', 'rate_bps', 'capacity_mbps']}
+    rew = np.zeros((steps, num_envs))
+    for s in range(steps):
+        for e in range(num_envs):
+            act = np.zeros(N, np.int64)
+            act[:C] = rng.integers(0, 2, C) * 24 + rng.integers(0, 24, C)                  # uplink: RB 0-1
+            act[C:C + D] = rng.integers(0, 4, D) * 21 + rng.integers(0, 21, D)             # sidelink: any RB
+            act[C + D:] = rng.integers(2, 4, C) * 47 + rng.integers(0, 47, C)              # downlink: RB 2-3, up to 46 dBm
+            active = rng.random(N) < 0.8
+            active[0] = active[C] = active[C + D] = True
+            present = [i for i in range(N) if active[i]]
+            R.set_positions(env, pos[e])
+            ref = R.step(env, [act[i] for i in present], [keys[i] for i in present])
+            out['actions'][s, e] = act
+            out['active'][s, e] = active
+            for k in res:
+                res[k][s, e, present] = ref[k]
+            assert np.all(ref['reward'] == ref['reward'][0])
+            rew[s, e] = ref['reward'][0]
+    out.update(res)
+    out['reward'] = rew
+    out['keys'] = np.array(keys)
+    np.savez_compressed(HERE / 'downlink.npz', **out)
+    print('downlink ok', res['sinr_db'][0, 0], rew[0])
+
+
 def reward_plugins():
     """the reference's two per-agent reward functions (envs/reward_fn.py:47-78), run through the unmodified
     reference with `reward_fn=<class>` in env_config (envs/d2d_env.py:28).  Stores every agent's reward."""
@@ -262,3 +302,4 @@ if __name__ == '__main__':
     fixed_scenario_10k()
     reward_plugins()
     cost_hata()
+    downlink()

@@ -813,3 +813,44 @@ def test_step_many_with_per_agent_rewards():
         assert_rel(out['agent_reward'][t].cpu().numpy(), want, RTOL, f'slice {t}')
         np.testing.assert_allclose(out['reward'][t].cpu().numpy(), want.mean(axis=1), rtol=1e-5)
     env.close()
+
+
+def test_downlink_actions_tensor_api_and_dict_api(golden_dir):
+    """'mbs:cueXX' DOWNLINK actions (envs/d2d_env.py:87-89, Appendix B.8): the general-topology kernel against the oracle on
+    random scenarios, and against step results of the unmodified reference (tests/golden/downlink.npz) through the dict API
+    (the first 'mbs:' key switches the env to the 2C + D link table; uplink / sidelink indices do not move)."""
+    import gym_d2d_b200 as G
+    kw = dict(num_rbs=4, num_cues=5, num_due_pairs=6)
+    cfg = O.OracleConfig(**kw, downlinks=True)
+    C, D, N = 5, 6, 16
+    rng = np.random.default_rng(71)
+    E = 96
+    pos = O.random_positions(cfg, E, rng)
+    act = O.random_actions(cfg, E, rng)
+    act[:, :C] = rng.integers(0, 2, (E, C)) * 24 + rng.integers(0, 24, (E, C))            # uplinks on RB 0-1
+    act[:, C + D:] = rng.integers(2, 4, (E, C)) * 47 + rng.integers(0, 47, (E, C))        # downlinks on RB 2-3
+    active = (rng.random(act.shape) < 0.8).astype(np.uint8)
+    ref = O.step_batch(cfg, pos, act, active=active, nthreads=4)
+    env = make_vec(E, kw, downlink=True)
+    assert env.num_links == N and env.link_keys[-1] == 'mbs:cue04'
+    out = run_step(env, pos, np.where(active > 0, act, -1).astype(np.int32))
+    check_against_oracle(out, ref)
+    assert out['tx_pwr_dbm'][:, C + D:].max() > 23
+    env.close()
+
+    g = np.load(golden_dir / 'downlink.npz')
+    keys = [str(k) for k in g['keys']]
+    denv = G.make('D2DEnv-v0', env_config=dict(kw))
+    denv.reset()
+    ids = denv.device_ids
+    for s in range(g['actions'].shape[0]):
+        for e in range(g['actions'].shape[1]):
+            denv.set_device_positions({ids[i]: tuple(g['positions'][e, i]) for i in range(len(ids))})
+            present = [i for i in range(N) if g['active'][s, e, i]]
+            _, rewards, _, info = denv.step({keys[i]: int(g['actions'][s, e, i]) for i in present})
+            assert list(rewards) == [keys[i] for i in present]
+            for k in ['sinr_db', 'snr_db', 'rate_bps', 'capacity_mbps']:
+                assert_rel(np.array([info[keys[i]][k] for i in present]), g[k][s, e][present], RTOL, f'downlink {k}')
+            assert [info[keys[i]]['tx_pwr_dbm'] for i in present] == [int(v) for v in g['tx_pwr_dbm'][s, e][present]]
+            assert_rel(np.array([rewards[keys[present[0]]]]), g['reward'][s, e:e + 1], RTOL, 'downlink reward')
+    denv.close()

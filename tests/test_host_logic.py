@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(_lib.D2DConfig) == 2 * 4 + 8 + 10 * 4 + 6 * 8
+    assert C.sizeof(_lib.D2DConfig) == 2 * 4 + 8 + 12 * 4 + 6 * 8
     assert C.sizeof(_lib.D2DLink) == 5 * 8 + 2 * 4 + 8
     assert C.sizeof(_lib.D2DStepIO) == 9 * C.sizeof(C.c_void_p)
 

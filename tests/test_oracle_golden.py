@@ -247,3 +247,20 @@ def test_cost_hata_known_answers_and_fixture(golden_dir):
             for k in ['sinr_db', 'snr_db', 'rate_bps', 'capacity_mbps']:
                 np.testing.assert_allclose(res[k], g[f'{name}_{k}'][s], rtol=1e-9, atol=1e-12, err_msg=f'{name} {k}')
             np.testing.assert_allclose(res['reward'], g[f'{name}_reward'][s], rtol=1e-9)
+
+
+def test_downlink_actions_match_reference_fixture(golden_dir):
+    """'mbs:cueXX' DOWNLINK actions (envs/d2d_env.py:87-89; Appendix B.8): MBS transmitter, 47 power levels, decoded and
+    stepped by the unmodified reference together with uplinks, sidelinks and absent agents (tests/golden/downlink.npz)."""
+    g = np.load(golden_dir / 'downlink.npz')
+    cfg = O.OracleConfig(num_rbs=4, num_cues=5, num_due_pairs=6, downlinks=True)
+    assert cfg.link_keys() == [str(k) for k in g['keys']]
+    for s in range(g['actions'].shape[0]):
+        res = O.step_batch(cfg, g['positions'], g['actions'][s], active=g['active'][s])
+        on = g['active'][s] > 0
+        np.testing.assert_array_equal(res['rb'][on], g['rb'][s][on])
+        np.testing.assert_array_equal(res['tx_pwr_dbm'][on], g['tx_pwr_dbm'][s][on])
+        for k in ['sinr_db', 'snr_db', 'rate_bps', 'capacity_mbps']:
+            np.testing.assert_allclose(res[k][on], g[k][s][on], rtol=1e-9, atol=1e-12, err_msg=k)
+        np.testing.assert_allclose(res['reward'], g['reward'][s], rtol=1e-9)
+    assert g['tx_pwr_dbm'][..., 11:].max() > 23            # downlink powers beyond any UE's range were drawn
