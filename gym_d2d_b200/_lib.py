@@ -15,7 +15,7 @@ STATS_REPLICAS = 32
 NUM_STATS = 8
 STAT_NAMES = ('sum_reward', 'sum_capacity_mbps', 'sum_reward_sq', 'env_steps', 'penalties', 'rescues')
 
-PL_LOG_DISTANCE, PL_FREE_SPACE, PL_COST_HATA = 0, 1, 2
+PL_LOG_DISTANCE, PL_FREE_SPACE, PL_COST_HATA, PL_SHADOWING = 0, 1, 2, 3
 OBS_LINEAR = 0
 REWARD_SYSTEM_CAPACITY, REWARD_SHANNON, REWARD_CUE_SINR_SHANNON = 0, 1, 2
 LINK_UPLINK, LINK_DOWNLINK, LINK_SIDELINK = 1, 2, 3
@@ -30,7 +30,8 @@ class D2DConfig(C.Structure):
                 ('path_loss_model', C.c_int32), ('obs_fn', C.c_int32), ('reward_fn', C.c_int32),
                 ('num_downlinks', C.c_int32), ('n_pwr_mbs', C.c_int32), ('reserved0', C.c_int32),
                 ('carrier_freq_GHz', C.c_double), ('ple', C.c_double), ('cell_radius_m', C.c_double),
-                ('d2d_radius_m', C.c_double), ('min_capacity_mbps', C.c_double), ('reward_param', C.c_double)]
+                ('d2d_radius_m', C.c_double), ('min_capacity_mbps', C.c_double), ('reward_param', C.c_double),
+                ('shadow_d0_m', C.c_double), ('shadow_chi_dB', C.c_double), ('rng_seed', C.c_uint64), ('first_global_env', C.c_uint64)]
 
 
 class D2DLink(C.Structure):

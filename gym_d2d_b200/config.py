@@ -14,7 +14,8 @@ from pathlib import Path
 from typing import Any, Dict, List, Optional, Tuple
 
 from . import _lib
-from .plugins import (LogDistancePathLoss, UnsupportedPluginError, UplinkTrafficModel, cost_hata_terms, resolve_path_loss)
+from .plugins import (LogDistancePathLoss, UnsupportedPluginError, UplinkTrafficModel, cost_hata_terms, resolve_path_loss,
+                      shadowing_params)
 
 EPISODE_LENGTH = 10                 # envs/d2d_env.py:16
 BASE_STATION_ID = 'mbs'             # simulator.py:15
@@ -174,7 +175,7 @@ def link_table(config: EnvConfig) -> List[dict]:
 
 
 def to_c_config(config: EnvConfig, num_envs: int, cuda_device: int, obs_enum: int, reward_enum: int,
-                reward_param: float) -> '_lib.D2DConfig':
+                reward_param: float, rng_seed: int = 0, first_global_env: int = 0) -> '_lib.D2DConfig':
     pl_enum, ple = resolve_path_loss(config.path_loss_model)
     hata = cost_hata_fold(config)
     if hata:
@@ -192,4 +193,6 @@ def to_c_config(config: EnvConfig, num_envs: int, cuda_device: int, obs_enum: in
                           carrier_freq_GHz=float(config.carrier_freq_GHz), ple=ple,
                           cell_radius_m=float(config.cell_radius_m), d2d_radius_m=float(config.d2d_radius_m),
                           min_capacity_mbps=float(reward_param) if reward_enum == _lib.REWARD_SYSTEM_CAPACITY else 0.0,
-                          reward_param=float(reward_param))
+                          reward_param=float(reward_param), shadow_d0_m=shadowing_params(config.path_loss_model)[0],
+                          shadow_chi_dB=shadowing_params(config.path_loss_model)[1],
+                          rng_seed=int(rng_seed) & 0xFFFFFFFFFFFFFFFF, first_global_env=int(first_global_env))

@@ -73,6 +73,7 @@ struct d2d_handle {
     double *stage_pos = nullptr;
     int64_t stage_pos_envs = 0;
     int64_t launches = 0;
+    uint64_t rng_calls = 0;      // ShadowingPathLoss: number of step calls so far (every call draws fresh values)
 };
 
 namespace {
@@ -101,7 +102,13 @@ D2DParams make_params(const d2d_handle *h, const d2d_step_io_t *io) {
     P.snr_slope = (float)(5.0 * h->ple * std::log10(2.0));
     P.min_cap = (float)h->cfg.min_capacity_mbps;
     // worst-case fp32 error of SINR_dB is ~6e-6 dB for ple = 2 (d2d_common.cuh); x 1e4 for a 1e-4 relative bound
-    P.rescue_band_dB = h->ple2 ? 0.0625f : 0.5f;
+    const bool shadowing = h->cfg.path_loss_model == D2D_PL_SHADOWING;
+    P.rescue_band_dB = (h->ple2 && !shadowing) ? 0.0625f : 0.5f;
+    P.shadow_chi_dB = shadowing ? (float)h->cfg.shadow_chi_dB : 0.0f;
+    P.shadow_d0sq = (float)(h->cfg.shadow_d0_m * h->cfg.shadow_d0_m);
+    P.shadow_chi_d = shadowing ? h->cfg.shadow_chi_dB : 0.0;
+    P.shadow_d0sq_d = h->cfg.shadow_d0_m * h->cfg.shadow_d0_m;
+    P.rng_seed = h->cfg.rng_seed; P.first_global_env = h->cfg.first_global_env; P.rng_step = h->rng_calls;
     if (h->pos64) {
         // positions were rounded to fp32: each coordinate is off by <= ulp(R)/2, a distance by <= ~sqrt(2) ulp(R),
         // i.e. 10 ple log10(e) * sqrt(2) ulp(R) / d dB per term; recompute whatever that could push past 1e-4 relative
@@ -211,8 +218,10 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
         return fail(D2D_ERR_UNSUPPORTED, "d2d_create: power levels per link must be in [1, 128]");
     if (cfg->num_rbs > 32767) return fail(D2D_ERR_UNSUPPORTED, "d2d_create: num_rbs must be <= 32767");
     if (cfg->path_loss_model != D2D_PL_LOG_DISTANCE && cfg->path_loss_model != D2D_PL_FREE_SPACE &&
-        cfg->path_loss_model != D2D_PL_COST_HATA)
-        return fail(D2D_ERR_UNSUPPORTED, "d2d_create: unsupported path_loss_model (LogDistance / FreeSpace / CostHata only)");
+        cfg->path_loss_model != D2D_PL_COST_HATA && cfg->path_loss_model != D2D_PL_SHADOWING)
+        return fail(D2D_ERR_UNSUPPORTED, "d2d_create: unsupported path_loss_model (LogDistance / FreeSpace / CostHata / Shadowing only)");
+    if (cfg->path_loss_model == D2D_PL_SHADOWING && (!(cfg->shadow_chi_dB >= 0.0) || !(cfg->shadow_d0_m >= 0.0)))
+        return fail(D2D_ERR_INVALID_ARG, "d2d_create: shadow_chi_dB and shadow_d0_m must be >= 0");
     if (cfg->obs_fn != D2D_OBS_LINEAR) return fail(D2D_ERR_UNSUPPORTED, "d2d_create: unsupported obs_fn (LinearObsFunction only)");
     if (cfg->reward_fn != D2D_REWARD_SYSTEM_CAPACITY && cfg->reward_fn != D2D_REWARD_SHANNON &&
         cfg->reward_fn != D2D_REWARD_CUE_SINR_SHANNON)
@@ -316,7 +325,9 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
 #undef D2D_CUDA_BAIL
 
     // warp kernel: one lane slot per CUE and per DUE pair, one shared-memory bin per RB
-    h->use_warp = cfg->num_cues <= 32 && cfg->num_due_pairs <= 32 && cfg->num_rbs <= 64 && cfg->num_downlinks == 0;
+    // downlink links and ShadowingPathLoss run on the general-topology kernel
+    const bool general = cfg->num_downlinks != 0 || cfg->path_loss_model == D2D_PL_SHADOWING;
+    h->use_warp = cfg->num_cues <= 32 && cfg->num_due_pairs <= 32 && cfg->num_rbs <= 64 && !general;
     if (const char *c = std::getenv("D2D_B200_CHUNK")) h->chunk_override = std::atoll(c);
     const char *pdl = std::getenv("D2D_B200_PDL");
     h->pdl = !(pdl && std::strcmp(pdl, "0") == 0);
@@ -332,7 +343,7 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
         rc = h->wpb == 8 ? plan_warp<8>(h, smem) : plan_warp<4>(h, smem);
     } else {
         // <= 1024 links: the register-resident block kernel, LPT links per thread; beyond: everything staged in shared memory
-        h->lpt = (h->N <= D2D_BLOCK_THREADS * D2D_BLOCK_MAX_LPT && cfg->num_downlinks == 0)
+        h->lpt = (h->N <= D2D_BLOCK_THREADS * D2D_BLOCK_MAX_LPT && !general)
                      ? (h->N + D2D_BLOCK_THREADS - 1) / D2D_BLOCK_THREADS : 0;      // downlinks: the general-topology kernel
         const size_t smem = h->lpt ? d2d_block2_smem_bytes(h->N, cfg->num_rbs) : d2d_block_smem_bytes(h->N, cfg->num_rbs);
         if (smem > 227 * 1024) return bail(fail(D2D_ERR_UNSUPPORTED, "d2d_create: too many links / RBs for one SM's shared memory"));
@@ -447,6 +458,7 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, void *stream) {
     P.t_stride = h->cfg.num_envs;
     cudaStream_t st = (cudaStream_t)stream;
     const bool many = T > 1;
+    h->rng_calls += (uint64_t)T;
     // the kernels index with 32 bits: batches beyond 2^31 / (T max(6N, 2V)) envs (> 7 million default envs) go in chunks
     int64_t chunk = std::max<int64_t>(1, (int64_t)0x7fffffff / std::max(6 * h->N, 2 * h->V));
     if (many) chunk = h->cfg.num_envs;        // d2d_step_many checked that T slices fit 32-bit indices
@@ -455,6 +467,7 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, void *stream) {
         const int64_t n = std::min<int64_t>(chunk, h->cfg.num_envs - e0);
         if (e0 > 0) {
             const int64_t dl = chunk * h->N;
+            P.first_global_env += (uint64_t)chunk;
             P.actions += dl; P.pos += chunk * h->V * 2;
             if (P.pos64) P.pos64 += chunk * h->V * 2;
             if (P.step_count) P.step_count += chunk;

@@ -18,19 +18,6 @@ __global__ void d2d_set_positions_kernel(const double *__restrict__ src, float *
     }
 }
 
-// Philox4x32-10 (Salmon et al. 2011); same constants as the oracle's restatement.
-__device__ __forceinline__ uint4 d2d_philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += 0x9E3779B9u;
-        k.y += 0xBB67AE85u;
-    }
-    return c;
-}
-
 // uniform-in-disc draw (position.py:24-28): theta = 2 pi u1, r = radius sqrt(u2)
 __device__ __forceinline__ float2 d2d_disc_draw(uint64_t seed, uint64_t genv, uint32_t dev, uint32_t attempt, float radius) {
     const uint4 o = d2d_philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32), dev, attempt),

@@ -69,6 +69,12 @@ struct D2DParams {
     float rescue_dmin2;          // with a shadow: links with a distance^2 below this are always recomputed
     float4 u_cue, u_due;         // default-shape kernel: the one D2DLinkA of every CUE link / every DUE link (constant bank)
     float2 us_cue, us_due;       // ... and the (sens_dBm, bw_MHz) of D2DLinkB
+    // ShadowingPathLoss (path_loss.py:69-81; general-topology kernel only): gauss(0, chi) added beyond d0 at EVERY path-loss
+    // evaluation.  Counter-based draws: Philox4x32-10 keyed by rng_seed, counter (global env, victim | source << 16, kind, rng_step)
+    float shadow_chi_dB;         // 0 = no shadowing
+    float shadow_d0sq;           // d0^2
+    uint64_t rng_seed, first_global_env, rng_step;
+    double shadow_chi_d, shadow_d0sq_d;   // unrounded copies for the fp64 rescue path
     double ple_d;                // fp64 copy for the rescue path
     const D2DLinkA *linkA;       // [N]
     const D2DLinkB *linkB;       // [N]
@@ -122,6 +128,48 @@ __host__ __device__ __forceinline__ uint32_t d2d_div_magic(int n) {
 }
 __device__ __forceinline__ int d2d_div(int a, uint32_t magic) {
     return magic ? (int)__umulhi((uint32_t)a, magic) : a;
+}
+
+// Philox4x32-10 (Salmon et al. 2011); same constants as the oracle's restatement.
+__device__ __forceinline__ uint4 d2d_philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// The N(0,1) draw of one ShadowingPathLoss evaluation (kind 0: the terms of the SINR, 1: the SNR's own-link evaluation): Box-Muller
+// on two 24-bit uniforms of one Philox block.  Restated value for value by the oracle (d2d_oracle_shadow_normal).
+__device__ __forceinline__ uint2 d2d_shadow_bits(const D2DParams &P, uint64_t genv, uint32_t victim, uint32_t source, uint32_t kind) {
+    const uint64_t step = P.rng_step;
+    const uint4 o = d2d_philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32) ^ (kind << 31) ^ ((uint32_t)(step >> 32) << 8),
+                                                 victim | (source << 16), (uint32_t)step),
+                                      make_uint2((uint32_t)P.rng_seed ^ 0x5bd1e995u, (uint32_t)(P.rng_seed >> 32)));
+    return make_uint2(o.x >> 8, o.y >> 8);
+}
+__device__ __forceinline__ float d2d_shadow_normal(const D2DParams &P, uint64_t genv, uint32_t victim, uint32_t source, uint32_t kind) {
+    const uint2 b = d2d_shadow_bits(P, genv, victim, source, kind);
+    const float u1 = ((float)b.x + 0.5f) * (1.0f / 16777216.0f), u2 = ((float)b.y + 0.5f) * (1.0f / 16777216.0f);
+    return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+__device__ __forceinline__ double d2d_shadow_normal_f64(const D2DParams &P, uint64_t genv, uint32_t victim, uint32_t source, uint32_t kind) {
+    const uint2 b = d2d_shadow_bits(P, genv, victim, source, kind);
+    const double u1 = ((double)b.x + 0.5) * (1.0 / 16777216.0), u2 = ((double)b.y + 0.5) * (1.0 / 16777216.0);
+    return sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+}
+// linear gain factor 10^(-chi z / 10) of one evaluation at squared distance d2 (1 within d0, path_loss.py:75-81)
+__device__ __forceinline__ float d2d_shadow_factor(const D2DParams &P, float d2, uint64_t genv, uint32_t victim, uint32_t source, uint32_t kind) {
+    if (!(P.shadow_chi_dB > 0.f) || !(d2 > P.shadow_d0sq)) return 1.0f;
+    return exp2f(-0.33219280948873623f * P.shadow_chi_dB * d2d_shadow_normal(P, genv, victim, source, kind));
+}
+__device__ __forceinline__ double d2d_shadow_factor_f64(const D2DParams &P, double d2, uint64_t genv, uint32_t victim, uint32_t source, uint32_t kind) {
+    if (!(P.shadow_chi_dB > 0.f) || !(d2 > P.shadow_d0sq_d)) return 1.0;
+    return exp2(-0.33219280948873623 * P.shadow_chi_d * d2d_shadow_normal_f64(P, genv, victim, source, kind));
 }
 
 // Path gain g(d^2) = d^-ple.  PLE2: one MUFU.RCP; otherwise MUFU.LG2 + MUFU.EX2.
@@ -229,19 +277,22 @@ __device__ __forceinline__ double2 d2d_pos_f64(const float2 *pe32, const double2
 // interferer k's fp64 contribution at receiver rx: w_k * g(d)
 template <bool PLE2>
 __device__ __forceinline__ double d2d_ix_term_f64(int k, double2 rx, const float2 *pe32, const double2 *pe64,
-                                                  const int32_t *act_env, const D2DParams &P) {
+                                                  const int32_t *act_env, const D2DParams &P, uint64_t genv = 0, int victim = 0) {
     const double2 tk = d2d_pos_f64(pe32, pe64, P.linkB[k].tx_dev);
-    const double ex = tk.x - rx.x, ey = tk.y - rx.y;
-    return P.pwr_lin_d[d2d_pwr_of(act_env, k, P)] * P.linkD[k].t_lin * d2d_gain_f64<PLE2>(ex * ex + ey * ey, P.ple_d);
+    const double ex = tk.x - rx.x, ey = tk.y - rx.y, d2 = ex * ex + ey * ey;
+    return P.pwr_lin_d[d2d_pwr_of(act_env, k, P)] * P.linkD[k].t_lin * d2d_gain_f64<PLE2>(d2, P.ple_d) *
+           d2d_shadow_factor_f64(P, d2, genv, (uint32_t)victim, (uint32_t)k, 0);
 }
 // all four outputs of link j from its fp64 interference sum (simulator.py:93,106-107,115,118-154)
 template <bool PLE2>
 __device__ __forceinline__ D2DLinkOut d2d_link_f64(int j, double2 tx, double2 rx, double I, float sens_dBm,
-                                                   const int32_t *act_env, const D2DParams &P) {
+                                                   const int32_t *act_env, const D2DParams &P, uint64_t genv = 0) {
     const D2DLinkD Lj = P.linkD[j];
-    const double dx = tx.x - rx.x, dy = tx.y - rx.y;
-    const double S = P.pwr_lin_d[d2d_pwr_of(act_env, j, P)] * Lj.a_lin * d2d_gain_f64<PLE2>(dx * dx + dy * dy, P.ple_d);
-    const double r = S / fma(I, Lj.inv_noise, 1.0);            // a_lin already carries 1/noise
+    const double dx = tx.x - rx.x, dy = tx.y - rx.y, d2 = dx * dx + dy * dy;
+    const double S0 = P.pwr_lin_d[d2d_pwr_of(act_env, j, P)] * Lj.a_lin * d2d_gain_f64<PLE2>(d2, P.ple_d);
+    // under ShadowingPathLoss the SINR's and the SNR's own-link evaluations draw separately (simulator.py:93 and :113)
+    const double S = S0 * d2d_shadow_factor_f64(P, d2, genv, (uint32_t)j, (uint32_t)j, 1);
+    const double r = S0 * d2d_shadow_factor_f64(P, d2, genv, (uint32_t)j, (uint32_t)j, 0) / fma(I, Lj.inv_noise, 1.0);   // a_lin already carries 1/noise
     const double sinr = 4.3429448190325182765 * d2d_ln_f64(r); // 10 log10
     const double rate = 1.4426950408889634074 * d2d_ln_f64(1.0 + r);
     const bool ok = sinr > (double)sens_dBm;

@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_generic_kern
     for (int64_t e = blockIdx.x; e < P.num_envs; e += gridDim.x) {
         const int32_t *act = P.actions + e * N;
         const float2 *pe = reinterpret_cast<const float2 *>(P.pos) + e * V;
+        const uint64_t genv = P.first_global_env + (uint64_t)e;         // ShadowingPathLoss draws are keyed by the global env
         for (int i = tid; i < nbins; i += D2D_BLOCK_THREADS) S.bin_cnt[i] = 0;
         __syncthreads();
 
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_generic_kern
                     if (k != j && (__float_as_uint(rk.w) & 0x9fffffffu) == rbkey) {
                         const float dx = rk.x - xj.x, dy = rk.y - xj.y;
                         const float d2 = fmaf(dx, dx, dy * dy);
-                        I = fmaf(rk.z, d2d_gain<PLE2>(d2, P.neg_half_ple), I);
+                        I = fmaf(rk.z, d2d_gain<PLE2>(d2, P.neg_half_ple) * d2d_shadow_factor(P, d2, genv, (uint32_t)j, (uint32_t)k, 0), I);
                         dmin2 = fminf(dmin2, d2);
                         side |= (__float_as_uint(rk.w) >> 29) & 1u;
                     }
@@ -148,16 +149,19 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_generic_kern
                 const float dx = rj.x - xj.x, dy = rj.y - xj.y;
                 const float d2own = fmaf(dx, dx, dy * dy);
                 const float lg = d2d_lg2(d2own);
-                o = d2d_link_epilogue<PLE2>(p, xj.z, lg, PLE2 ? d2d_rcp(d2own) : d2d_ex2(P.neg_half_ple * lg), I, Av, sb, P);
+                const float gown = PLE2 ? d2d_rcp(d2own) : d2d_ex2(P.neg_half_ple * lg);
+                o = d2d_link_epilogue<PLE2>(p, xj.z, lg, gown * d2d_shadow_factor(P, d2own, genv, (uint32_t)j, (uint32_t)j, 0), I, Av, sb, P);
+                if (P.shadow_chi_dB > 0.f && d2own > P.shadow_d0sq)      // the SNR's own evaluation of the path loss (simulator.py:113)
+                    o.snr_dB -= P.shadow_chi_dB * d2d_shadow_normal(P, genv, (uint32_t)j, (uint32_t)j, 1);
                 if (D2D_RESCUE_ENABLED && d2d_needs_rescue<true>(o, fminf(dmin2, d2own), P)) {   // rare: fp64 pass (d2d_common.cuh)
                     const double2 *pe64 = P.pos64 ? reinterpret_cast<const double2 *>(P.pos64) + e * V : nullptr;
                     const double2 rx = d2d_pos_f64(pe, pe64, __float_as_int(Bv.w));
                     double I64 = 0.0;
                     for (int q = beg; q < end; ++q) {
                         const int k = S.sorted[q];
-                        if (k != j && (__float_as_uint(S.rec[k].w) & 0x9fffffffu) == rbkey) I64 += d2d_ix_term_f64<PLE2>(k, rx, pe, pe64, act, P);
+                        if (k != j && (__float_as_uint(S.rec[k].w) & 0x9fffffffu) == rbkey) I64 += d2d_ix_term_f64<PLE2>(k, rx, pe, pe64, act, P, genv, j);
                     }
-                    o = d2d_link_f64<PLE2>(j, d2d_pos_f64(pe, pe64, __float_as_int(Bv.z)), rx, I64, sb.x, act, P);
+                    o = d2d_link_f64<PLE2>(j, d2d_pos_f64(pe, pe64, __float_as_int(Bv.z)), rx, I64, sb.x, act, P, genv);
                     ++resc;
                 }
                 cap_part += o.cap;

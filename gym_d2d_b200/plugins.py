@@ -47,8 +47,14 @@ class FreeSpacePathLoss(PathLoss):
     ple = 2.0
 
 
-class ShadowingPathLoss(PathLoss):      # path_loss.py:69-81 (stochastic per evaluation) - not implemented
-    pass
+class ShadowingPathLoss(PathLoss):
+    """path_loss.py:69-81: log-distance plus gauss(0, chi_dB) beyond d0_m, drawn at every evaluation.  The CUDA path draws from
+    a counter-based Philox stream (seeded by VecD2DEnv's seed), so it matches the reference in distribution only."""
+    kernel_enum = _lib.PL_SHADOWING
+
+    def __init__(self, carrier_freq_GHz: float, ple: float = 2.0, d0_m: float = 100.0, chi_dB: float = 2.7) -> None:
+        super().__init__(carrier_freq_GHz)
+        self.ple, self.d0_m, self.chi_dB = float(ple), float(d0_m), float(chi_dB)
 
 
 class AreaType(enum.Enum):
@@ -143,12 +149,12 @@ _REFERENCE_MODULES = {
 }
 _OURS = {
     'path_loss': {'LogDistancePathLoss': LogDistancePathLoss, 'FreeSpacePathLoss': FreeSpacePathLoss,
-                  'CostHataPathLoss': CostHataPathLoss},
+                  'CostHataPathLoss': CostHataPathLoss, 'ShadowingPathLoss': ShadowingPathLoss},
     'obs_fn': {'LinearObsFunction': LinearObsFunction},
     'reward_fn': {'SystemCapacityRewardFunction': SystemCapacityRewardFunction, 'ShannonRewardFunction': ShannonRewardFunction,
                   'CueSinrShannonRewardFunction': CueSinrShannonRewardFunction},
 }
-_KNOWN_UNSUPPORTED = {'ShadowingPathLoss'}
+_KNOWN_UNSUPPORTED: set = set()
 
 
 def _unwrap_partial(obj: Any) -> Tuple[Any, dict]:
@@ -189,7 +195,7 @@ def resolve_path_loss(obj: Any) -> Tuple[int, float]:
             raise UnsupportedPluginError(f'unsupported CostHataPathLoss arguments {sorted(extra)}')
         area = kwargs.get('area_type', AreaType.SUBURBAN)                     # path_loss.py:91 default
         return cls.kernel_enum, float(getattr(area, 'value', area))          # ours or the reference's AreaType member
-    extra = set(kwargs) - {'ple'}
+    extra = set(kwargs) - ({'ple', 'd0_m', 'chi_dB'} if cls is ShadowingPathLoss else {'ple'})
     if extra:
         raise UnsupportedPluginError(f'unsupported path-loss arguments {sorted(extra)}')
     if cls is FreeSpacePathLoss:
@@ -197,6 +203,14 @@ def resolve_path_loss(obj: Any) -> Tuple[int, float]:
             raise UnsupportedPluginError('FreeSpacePathLoss has a fixed exponent of 2')
         return cls.kernel_enum, 2.0
     return cls.kernel_enum, float(kwargs.get('ple', 2.0))   # path_loss.py:43 default
+
+
+def shadowing_params(obj: Any) -> Tuple[float, float]:
+    """-> (d0_m, chi_dB) of a ShadowingPathLoss plugin (path_loss.py:70 defaults), or (0, 0) for the other models."""
+    cls, kwargs = _resolve('path_loss', obj)
+    if cls is not ShadowingPathLoss:
+        return 0.0, 0.0
+    return float(kwargs.get('d0_m', 100.0)), float(kwargs.get('chi_dB', 2.7))
 
 
 def resolve_obs_fn(obj: Any) -> int:

@@ -95,7 +95,8 @@ class VecD2DEnv:
         self._lib = _lib.load()
         links = link_table(self.config)
         c_links = (_lib.D2DLink * len(links))(*[_lib.D2DLink(**row) for row in links])
-        c_cfg = to_c_config(self.config, self.num_envs, self.device.index, obs_enum, reward_enum, min_cap)
+        c_cfg = to_c_config(self.config, self.num_envs, self.device.index, obs_enum, reward_enum, min_cap,
+                            rng_seed=self.seed, first_global_env=self.global_env_offset)
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self._lib.d2d_create(C.byref(c_cfg), c_links, C.byref(handle)))

@@ -50,8 +50,12 @@ typedef enum d2d_status {
  * LogDistancePathLoss with ple = 2 (path_loss.py:43,45): it is not a separate class in the reference.
  * COST_HATA (path_loss.py:90-123) is A(h_tx, h_rx) + B(h_tx) log10(d_km): with one transmitter antenna height it is a
  * log-distance law with exponent ple = B / 10 and a per-receiver constant, both folded by the caller: d2d_config.ple and
- * d2d_link.path_loss_const_dB (= A - 3 B for the link's receiver). */
-typedef enum d2d_path_loss_model { D2D_PL_LOG_DISTANCE = 0, D2D_PL_FREE_SPACE = 1, D2D_PL_COST_HATA = 2 } d2d_path_loss_model;
+ * d2d_link.path_loss_const_dB (= A - 3 B for the link's receiver).
+ * SHADOWING (path_loss.py:69-81) is the log-distance law plus gauss(0, shadow_chi_dB) beyond shadow_d0_m, drawn anew at EVERY
+ * path-loss evaluation (the own link twice per step: once for the SINR, once for the SNR).  The reference draws from
+ * Python's global RNG; here the draws are counter-based (Philox4x32-10 keyed by rng_seed; counter = global env, victim link,
+ * source link, evaluation kind, step call number), so only distributions match the reference.  General-topology kernel. */
+typedef enum d2d_path_loss_model { D2D_PL_LOG_DISTANCE = 0, D2D_PL_FREE_SPACE = 1, D2D_PL_COST_HATA = 2, D2D_PL_SHADOWING = 3 } d2d_path_loss_model;
 /* obs_fn plugin (envs/d2d_env.py:27; envs/obs_fn.py:35-61) */
 typedef enum d2d_obs_fn { D2D_OBS_LINEAR = 0 } d2d_obs_fn;
 /* reward_fn plugin (envs/d2d_env.py:28).  SYSTEM_CAPACITY (envs/reward_fn.py:22-44) is one scalar per env, computed inside
@@ -87,6 +91,10 @@ typedef struct d2d_config {
     double d2d_radius_m;        /* :16 */
     double min_capacity_mbps;   /* envs/reward_fn.py:23 */
     double reward_param;        /* SHANNON: min_sinr (envs/reward_fn.py:48); CUE_SINR_SHANNON: sinr_threshold_dB (:61) */
+    double shadow_d0_m;         /* SHADOWING: close-in reference distance (path_loss.py:72) */
+    double shadow_chi_dB;       /* SHADOWING: standard deviation of the per-evaluation Gaussian (path_loss.py:73) */
+    uint64_t rng_seed;          /* SHADOWING: Philox key */
+    uint64_t first_global_env;  /* SHADOWING: global index of local env 0, so a sharded batch draws the same values whatever the GPU count */
 } d2d_config_t;
 
 /* Per-link link-budget constants, folded on the host from the per-device config dicts

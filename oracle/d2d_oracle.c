@@ -89,15 +89,31 @@ double d2d_oracle_cost_hata_pl(double dist_m, double f_GHz, int area_type, doubl
     return 46.3 + 33.9 * log10(f) - 13.82 * log10(h_tx) - a_hc + (44.9 - 6.55 * log10(h_tx)) * log10(d) + c;   /* :108 */
 }
 
-/* PathLoss.__call__(tx, rx) for the configured model (simulator.py:59,93,99) */
-static double path_loss_dB(const d2d_oracle_cfg *cfg, double K, const d2d_oracle_device *tx, const d2d_oracle_device *rx, double d) {
+void d2d_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+/* The product's N(0,1) draw for one path-loss evaluation: Box-Muller on two 24-bit uniforms of one Philox block. */
+double d2d_oracle_shadow_normal(uint64_t seed, uint64_t genv, uint32_t victim, uint32_t source, uint32_t kind, uint64_t step) {
+    uint32_t ctr[4] = {(uint32_t)genv, (uint32_t)(genv >> 32) ^ (kind << 31) ^ ((uint32_t)(step >> 32) << 8), victim | (source << 16), (uint32_t)step};
+    uint32_t key[2] = {(uint32_t)seed ^ 0x5bd1e995u, (uint32_t)(seed >> 32)}, o[4];
+    d2d_oracle_philox4x32_10(ctr, key, o);
+    const double u1 = ((double)(o[0] >> 8) + 0.5) * (1.0 / 16777216.0), u2 = ((double)(o[1] >> 8) + 0.5) * (1.0 / 16777216.0);
+    return sqrt(-2.0 * log(u1)) * cos(2.0 * M_PI * u2);
+}
+
+/* PathLoss.__call__(tx, rx) for the configured model (simulator.py:59,93,99).  (genv, victim, source, kind) identify the
+ * evaluation for ShadowingPathLoss's per-call draw. */
+static double path_loss_dB(const d2d_oracle_cfg *cfg, double K, const d2d_oracle_device *tx, const d2d_oracle_device *rx, double d,
+                           uint64_t genv, uint32_t victim, uint32_t source, uint32_t kind) {
     if (cfg->path_loss_model == 2)
         return d2d_oracle_cost_hata_pl(d, cfg->carrier_freq_GHz, cfg->area_type, tx->antenna_height_m, rx->antenna_height_m);
-    return 10.0 * cfg->ple * log10(d) + K;      /* path_loss.py:65-66 */
+    double pl = 10.0 * cfg->ple * log10(d) + K;      /* path_loss.py:65-66 */
+    if (cfg->path_loss_model == 3 && d > cfg->shadow_d0_m)     /* path_loss.py:76-79: ldpl(d0) + 10 ple log10(d / d0) + gauss(0, chi) */
+        pl += cfg->shadow_chi_dB * d2d_oracle_shadow_normal(cfg->rng_seed, genv, victim, source, kind, cfg->rng_step);
+    return pl;
 }
 
 /* One environment.  Returns 0 / -1 (zero-distance link). */
-static int step_one(const d2d_oracle_cfg *cfg, const d2d_oracle_device *dev, const double *pos,
+static int step_one(const d2d_oracle_cfg *cfg, uint64_t genv, const d2d_oracle_device *dev, const double *pos,
                     const int32_t *act, const uint8_t *active,
                     int32_t *rb_o, int32_t *pwr_o, double *sinr_o, double *snr_o, double *rate_o,
                     double *cap_o, double *obs_o, double *reward_o,
@@ -127,7 +143,7 @@ static int step_one(const d2d_oracle_cfg *cfg, const d2d_oracle_device *dev, con
             /* simulator.py:93 */
             double d = d2d_oracle_distance(pt[0], pt[1], pr[0], pr[1]);
             if (!(d > 0.0)) status = -1;
-            double pl = path_loss_dB(cfg, K, tx, rx, d);
+            double pl = path_loss_dB(cfg, K, tx, rx, d, genv, (uint32_t)j, (uint32_t)j, 0);
             double rx_pwr = d2d_oracle_rx_signal_level_dBm(rx, d2d_oracle_eirp_dBm(tx, (double)pw[j]), pl);
             /* simulator.py:95-101: same-RB actions minus self; NO rx gain on interferers */
             double sum_ix = 0.0;
@@ -138,13 +154,17 @@ static int step_one(const d2d_oracle_cfg *cfg, const d2d_oracle_device *dev, con
                 double dk = d2d_oracle_distance(pk[0], pk[1], pr[0], pr[1]);
                 if (!(dk > 0.0)) status = -1;
                 double ix_eirp = d2d_oracle_eirp_dBm(&dev[txd[k]], (double)pw[k]);
-                double ix_pl = path_loss_dB(cfg, K, &dev[txd[k]], rx, dk);
+                double ix_pl = path_loss_dB(cfg, K, &dev[txd[k]], rx, dk, genv, (uint32_t)j, (uint32_t)k, 0);
                 sum_ix += d2d_oracle_dB_to_linear(ix_eirp - ix_pl);
             }
             /* simulator.py:106-107 */
             sinr_db = rx_pwr - d2d_oracle_linear_to_dB(sum_ix + d2d_oracle_dB_to_linear(rx->thermal_noise_dBm));
-            /* simulator.py:110-116 */
-            snr_db = rx_pwr - rx->thermal_noise_dBm;
+            /* simulator.py:110-116: the SNR evaluates the path loss of the own link AGAIN (a second draw under shadowing) */
+            if (cfg->path_loss_model == 3)
+                snr_db = d2d_oracle_rx_signal_level_dBm(rx, d2d_oracle_eirp_dBm(tx, (double)pw[j]),
+                                                        path_loss_dB(cfg, K, tx, rx, d, genv, (uint32_t)j, (uint32_t)j, 1)) - rx->thermal_noise_dBm;
+            else
+                snr_db = rx_pwr - rx->thermal_noise_dBm;
             /* simulator.py:118-127 and :144-154 (dB compared with dBm, as written) */
             if (sinr_db > d2d_oracle_rx_sensitivity_dBm(rx)) {
                 rate = log2(1.0 + d2d_oracle_dB_to_linear(sinr_db));
@@ -209,7 +229,7 @@ int d2d_oracle_step_batch(const d2d_oracle_cfg *cfg, const d2d_oracle_device *de
 #pragma omp for schedule(static)
 #endif
         for (int64_t e = 0; e < E; ++e) {
-            int st = step_one(cfg, devices, positions + (size_t)e * V * 2, actions + (size_t)e * N,
+            int st = step_one(cfg, cfg->first_global_env + (uint64_t)e, devices, positions + (size_t)e * V * 2, actions + (size_t)e * N,
                               active ? active + (size_t)e * N : NULL,
                               rb ? rb + (size_t)e * N : NULL, pwr ? pwr + (size_t)e * N : NULL,
                               sinr_db ? sinr_db + (size_t)e * N : NULL, snr_db ? snr_db + (size_t)e * N : NULL,

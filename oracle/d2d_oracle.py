@@ -37,7 +37,9 @@ class _Cfg(C.Structure):
     _fields_ = [('num_rbs', C.c_int32), ('num_cues', C.c_int32), ('num_due_pairs', C.c_int32),
                 ('n_pwr_cue', C.c_int32), ('n_pwr_due', C.c_int32), ('path_loss_model', C.c_int32),
                 ('carrier_freq_GHz', C.c_double), ('ple', C.c_double), ('min_capacity_mbps', C.c_double),
-                ('area_type', C.c_int32), ('downlinks', C.c_int32), ('n_pwr_mbs', C.c_int32), ('_pad', C.c_int32)]
+                ('area_type', C.c_int32), ('downlinks', C.c_int32), ('n_pwr_mbs', C.c_int32), ('_pad', C.c_int32),
+                ('shadow_d0_m', C.c_double), ('shadow_chi_dB', C.c_double), ('rng_seed', C.c_uint64),
+                ('first_global_env', C.c_uint64), ('rng_step', C.c_uint64)]
 
 
 # device.py:12-41 (merged with DEFAULT_DEVICE_CONFIG :12-16)
@@ -69,7 +71,12 @@ class OracleConfig:
     min_capacity_mbps: float = 0.0
     mbs_max_tx_power_dBm: int = 46
     downlinks: bool = False                    # append the DOWNLINK links 'mbs:cueXX' (envs/d2d_env.py:87-89): N = 2C + D
-    path_loss_model: str = 'log_distance'      # or 'cost_hata' (path_loss.py:90-123)
+    path_loss_model: str = 'log_distance'      # or 'cost_hata' (path_loss.py:90-123), 'shadowing' (path_loss.py:69-81)
+    shadow_d0_m: float = 100.0                 # path_loss.py:70
+    shadow_chi_dB: float = 2.7                 # path_loss.py:70
+    rng_seed: int = 0                          # shadowing draws: the product's counter-based scheme (d2d_oracle.h)
+    first_global_env: int = 0
+    rng_step: int = 0
     area_type: int = 1                         # path_loss.py:84-87 AreaType value (CostHata only; default SUBURBAN, :91)
     # per-device overrides {device_id: {field: value}} as a device_config_file's 'config' dicts would give
     device_overrides: Dict[str, dict] = field(default_factory=dict)
@@ -125,6 +132,8 @@ def lib():
         L.d2d_oracle_decode_action.argtypes = [C.c_int64, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.d2d_oracle_decode_action.restype = None
         vp = C.c_void_p
+        L.d2d_oracle_shadow_normal.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64]
+        L.d2d_oracle_shadow_normal.restype = d
         L.d2d_oracle_cost_hata_pl.argtypes = [d, d, C.c_int, d, d]
         L.d2d_oracle_cost_hata_pl.restype = d
         L.d2d_oracle_step_batch.argtypes = [C.POINTER(_Cfg), C.POINTER(_Device), C.c_int64] + [vp] * 11 + [C.c_int]
@@ -150,7 +159,9 @@ def _c_cfg(cfg: OracleConfig) -> _Cfg:
                 n_pwr_cue=cfg.cue_max_tx_power_dBm + 1,                               # envs/d2d_env.py:33
                 n_pwr_due=cfg.due_max_tx_power_dBm - cfg.due_min_tx_power_dBm + 1,    # envs/d2d_env.py:32
                 carrier_freq_GHz=cfg.carrier_freq_GHz, ple=cfg.ple, min_capacity_mbps=cfg.min_capacity_mbps,
-                path_loss_model=2 if cfg.path_loss_model == 'cost_hata' else 0, area_type=int(cfg.area_type),
+                path_loss_model={'cost_hata': 2, 'shadowing': 3}.get(cfg.path_loss_model, 0), area_type=int(cfg.area_type),
+                shadow_d0_m=cfg.shadow_d0_m, shadow_chi_dB=cfg.shadow_chi_dB, rng_seed=cfg.rng_seed,
+                first_global_env=cfg.first_global_env, rng_step=cfg.rng_step,
                 downlinks=int(bool(cfg.downlinks)), n_pwr_mbs=cfg.mbs_max_tx_power_dBm + 1)            # envs/d2d_env.py:34
 
 

@@ -241,6 +241,33 @@ def downlink():
     print('downlink ok', res['sinr_db'][0, 0], rew[0])
 
 
+def shadowing_stats():
+    """ShadowingPathLoss (path_loss.py:69-81) draws gauss(0, chi) from Python's global RNG at every evaluation, so its
+    results can only be pinned as DISTRIBUTIONS: per-link mean / std of SINR_dB, SNR_dB and capacity over K steps of one
+    fixed scenario with fixed actions, from the unmodified reference."""
+    from gym_d2d.path_loss import ShadowingPathLoss
+    base = dict(num_rbs=3, num_cues=4, num_due_pairs=6, cell_radius_m=500.0, d2d_radius_m=150.0)   # some D2D links beyond d0 = 100 m
+    cfg = O.OracleConfig(**{k: v for k, v in base.items()})
+    rng = np.random.default_rng(81)
+    random.seed(81)
+    pos = O.random_positions(cfg, 1, rng)[0]
+    act = O.random_actions(cfg, 1, rng)[0]
+    env = R.make_env(dict(base, path_loss_model=ShadowingPathLoss))
+    env.reset()
+    keys = R.link_keys(env)
+    R.set_positions(env, pos)
+    K = 6000
+    sinr = np.zeros((K, len(keys))); snr = np.zeros((K, len(keys))); cap = np.zeros((K, len(keys)))
+    for t in range(K):
+        ref = R.step(env, act, keys)
+        sinr[t], snr[t], cap[t] = ref['sinr_db'], ref['snr_db'], ref['capacity_mbps']
+    np.savez_compressed(HERE / 'shadowing_stats.npz', positions=pos, actions=act.astype(np.int32), K=K,
+                        sinr_mean=sinr.mean(0), sinr_std=sinr.std(0), snr_mean=snr.mean(0), snr_std=snr.std(0),
+                        cap_mean=cap.mean(0), cap_std=cap.std(0), corr_sinr_snr=np.array([np.corrcoef(sinr[:, j], snr[:, j])[0, 1]
+                                                                                     if snr[:, j].std() > 0 else 0.0 for j in range(len(keys))]))
+    print('shadowing_stats ok', sinr.std(0).round(2), snr.std(0).round(2))
+
+
 def reward_plugins():
     """the reference's two per-agent reward functions (envs/reward_fn.py:47-78), run through the unmodified
     reference with `reward_fn=<class>` in env_config (envs/d2d_env.py:28).  Stores every agent's reward."""
@@ -303,3 +330,4 @@ if __name__ == '__main__':
     reward_plugins()
     cost_hata()
     downlink()
+    shadowing_stats()

@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(_lib.D2DConfig) == 2 * 4 + 8 + 12 * 4 + 6 * 8
+    assert C.sizeof(_lib.D2DConfig) == 2 * 4 + 8 + 12 * 4 + 10 * 8
     assert C.sizeof(_lib.D2DLink) == 5 * 8 + 2 * 4 + 8
     assert C.sizeof(_lib.D2DStepIO) == 9 * C.sizeof(C.c_void_p)
 
@@ -164,11 +164,11 @@ def test_reference_classes_are_accepted_by_identity():
     assert plugins.resolve_obs_fn(RefObs) == _lib.OBS_LINEAR
     assert plugins.resolve_reward_fn(RefRew) == (_lib.REWARD_SYSTEM_CAPACITY, 0.0)
     from gym_d2d.path_loss import AreaType as RefArea, ShadowingPathLoss as RefShadow
+    assert plugins.resolve_path_loss(RefShadow) == (_lib.PL_SHADOWING, 2.0) and plugins.shadowing_params(RefShadow) == (100.0, 2.7)
     assert plugins.resolve_path_loss(RefHata) == (_lib.PL_COST_HATA, 1.0)
     assert plugins.resolve_path_loss(functools.partial(RefHata, area_type=RefArea.URBAN)) == (_lib.PL_COST_HATA, 2.0)
     assert plugins.resolve_reward_fn(RefShannon) == (_lib.REWARD_SHANNON, -70.0)
-    with pytest.raises(G.UnsupportedPluginError):
-        plugins.resolve_path_loss(RefShadow)
+    assert plugins.shadowing_params(functools.partial(RefShadow, chi_dB=3.5, d0_m=50.0)) == (50.0, 3.5)
 
 
 def test_custom_and_unimplemented_plugins_are_rejected():
@@ -179,7 +179,7 @@ def test_custom_and_unimplemented_plugins_are_rejected():
     class CustomObs(G.LinearObsFunction):
         pass
 
-    for bad in (CustomPathLoss, G.ShadowingPathLoss, functools.partial(G.CostHataPathLoss, ple=3.0),
+    for bad in (CustomPathLoss, functools.partial(G.ShadowingPathLoss, sigma=1.0), functools.partial(G.CostHataPathLoss, ple=3.0),
                 functools.partial(G.FreeSpacePathLoss, ple=3.0)):
         with pytest.raises(G.UnsupportedPluginError):
             plugins.resolve_path_loss(bad)

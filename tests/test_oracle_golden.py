@@ -264,3 +264,28 @@ def test_downlink_actions_match_reference_fixture(golden_dir):
             np.testing.assert_allclose(res[k][on], g[k][s][on], rtol=1e-9, atol=1e-12, err_msg=k)
         np.testing.assert_allclose(res['reward'], g['reward'][s], rtol=1e-9)
     assert g['tx_pwr_dbm'][..., 11:].max() > 23            # downlink powers beyond any UE's range were drawn
+
+
+def test_shadowing_distribution_matches_reference(golden_dir):
+    """ShadowingPathLoss (path_loss.py:69-81): the oracle uses the product's counter-based draws, the reference Python's global
+    RNG, so the comparison is distributional: per-link mean and standard deviation of SINR_dB / SNR_dB / capacity over K
+    steps of one fixed scenario (tests/golden/shadowing_stats.npz), and the independence of the SINR and SNR draws."""
+    g = np.load(golden_dir / 'shadowing_stats.npz')
+    cfg = O.OracleConfig(num_rbs=3, num_cues=4, num_due_pairs=6, d2d_radius_m=150.0, path_loss_model='shadowing', rng_seed=5)
+    K = 4000
+    sinr = np.zeros((K, cfg.num_links)); snr = np.zeros_like(sinr); cap = np.zeros_like(sinr)
+    for t in range(K):
+        cfg.rng_step = t
+        r = O.step_batch(cfg, g['positions'][None], g['actions'][None])
+        sinr[t], snr[t], cap[t] = r['sinr_db'][0], r['snr_db'][0], r['capacity_mbps'][0]
+    se = lambda std: 6.0 * np.maximum(std, 1e-9) * np.sqrt(1.0 / K + 1.0 / float(g['K']))     # six standard errors
+    assert (np.abs(sinr.mean(0) - g['sinr_mean']) <= se(g['sinr_std']) + 1e-9).all()
+    assert (np.abs(snr.mean(0) - g['snr_mean']) <= se(g['snr_std']) + 1e-9).all()
+    assert (np.abs(cap.mean(0) - g['cap_mean']) <= se(g['cap_std']) + 1e-9).all()
+    np.testing.assert_allclose(sinr.std(0), g['sinr_std'], rtol=0.08, atol=1e-9)
+    np.testing.assert_allclose(snr.std(0), g['snr_std'], rtol=0.08, atol=1e-9)
+    far = g['snr_std'] > 1e-6                              # links longer than d0 = 100 m: SNR std = chi = 2.7 dB
+    assert far.any() and (~far).any()
+    np.testing.assert_allclose(snr.std(0)[far], 2.7, rtol=0.08)
+    corr = np.array([np.corrcoef(sinr[:, j], snr[:, j])[0, 1] for j in np.nonzero(far)[0]])
+    assert (np.abs(corr - g['corr_sinr_snr'][far]) < 0.1).all()          # separate evaluations: (nearly) uncorrelated
