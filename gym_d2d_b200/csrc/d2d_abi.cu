@@ -13,7 +13,13 @@
 #include "d2d_aux.cuh"
 #include "d2d_common.cuh"
 #include "d2d_step_block.cuh"
+#include "d2d_step_dense.cuh"
 #include "d2d_step_warp.cuh"
+
+// (links per thread, threads per block) instantiations of the dense kernel
+#define D2D_DENSE_SHAPES(X) X(1, 256) X(2, 256) X(3, 256) X(4, 256) X(2, 320)
+#define D2D_DENSE_PLAN_CASE(LPT_, BT_) if (h->lpt == LPT_ && h->dense_bt == BT_) rc = D2D_PLAN_DENSE(LPT_, BT_);
+#define D2D_DENSE_LAUNCH_CASE(LPT_, BT_) if (h->lpt == LPT_ && h->dense_bt == BT_) err = D2D_LAUNCH_DENSE(LPT_, BT_);
 
 static_assert(D2D_STATS_REPLICAS * 8 * sizeof(double) == 2048, "stats layout");
 
@@ -48,7 +54,9 @@ struct d2d_handle {
     D2DLinkA u_cue{}, u_due{};
     float us_cue[2] = {0, 0}, us_due[2] = {0, 0};
     int wpb = 4;               // warps per block of the warp kernel
-    int lpt = 0;               // block kernel: links per thread held in registers (0 = the generic shared-memory kernel)
+    int dense_bt = 0;          // dense kernel (d2d_step_dense.cuh): threads per block, 0 = not used
+    int bin_cap = 0;           // dense kernel: record slots per RB bin
+    int lpt = 0;               // block / dense kernel: links per thread held in registers (0 = the generic shared-memory kernel)
     int64_t chunk_override = 0;  // D2D_B200_CHUNK: force small launch chunks (tests of the > 2^31-element path)
     bool pdl = true;           // programmatic dependent launch (D2D_B200_PDL=0 disables)
     int grid = 0, block = 0, smem = 0, envs_per_block = 0;
@@ -92,6 +100,7 @@ D2DParams make_params(const d2d_handle *h, const d2d_step_io_t *io) {
     P.n_pwr_cue = h->cfg.n_pwr_cue; P.n_pwr_due = h->cfg.n_pwr_due;
     P.episode_length = h->cfg.episode_length;
     P.nbins = h->cfg.num_rbs;
+    P.bin_cap = h->bin_cap;
     P.magic_cue = d2d_div_magic(h->cfg.n_pwr_cue);
     P.magic_due = d2d_div_magic(h->cfg.n_pwr_due);
     P.npw1_cue = h->cfg.n_pwr_cue == 1 ? 0xffffffffu : 0u;
@@ -179,6 +188,16 @@ int plan_geometry(d2d_handle *h, K kernel, int block, size_t smem, int envs_per_
     h->smem = (int)smem;
     h->envs_per_block = envs_per_block;
     return D2D_OK;
+}
+
+// every (FULL, EXACT) instantiation d2d_step may launch for this handle needs the dynamic shared-memory opt-in
+template <bool PLE2, int LPT, int BT>
+int plan_dense(d2d_handle *h, size_t smem) {
+    int rc = allow_smem(d2d_step_dense_kernel<PLE2, LPT, BT, false, false>, smem);
+    if (!rc) rc = allow_smem(d2d_step_dense_kernel<PLE2, LPT, BT, false, true>, smem);
+    if (!rc) rc = allow_smem(d2d_step_dense_kernel<PLE2, LPT, BT, true, true>, smem);
+    if (!rc) rc = plan_geometry(h, d2d_step_dense_kernel<PLE2, LPT, BT, true, false>, BT, smem, 1);
+    return rc;
 }
 
 template <int WPB>
@@ -342,14 +361,31 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
         const size_t smem = d2d_warp_smem_bytes(cfg->num_rbs, h->wpb);
         rc = h->wpb == 8 ? plan_warp<8>(h, smem) : plan_warp<4>(h, smem);
     } else {
-        // <= 1024 links: the register-resident block kernel, LPT links per thread; beyond: everything staged in shared memory
+        // <= 1024 links: the binned one-barrier kernel (d2d_step_dense.cuh), LPT links per thread; when its double-buffered
+        // bins do not fit (many RBs) the sorting block kernel; beyond 1024 links / other topologies: everything staged in shared memory
         h->lpt = (h->N <= D2D_BLOCK_THREADS * D2D_BLOCK_MAX_LPT && !general)
                      ? (h->N + D2D_BLOCK_THREADS - 1) / D2D_BLOCK_THREADS : 0;      // downlinks: the general-topology kernel
-        const size_t smem = h->lpt ? d2d_block2_smem_bytes(h->N, cfg->num_rbs) : d2d_block_smem_bytes(h->N, cfg->num_rbs);
+        h->bin_cap = d2d_dense_bin_cap(h->N, cfg->num_rbs);
+        const char *dn = std::getenv("D2D_B200_DENSE");
+        bool dense = h->lpt > 0 && d2d_dense_layout(h->N, cfg->num_rbs, h->bin_cap).total <= 72 * 1024 && !(dn && std::atoi(dn) == 0);
+        if (dense) {
+            // threads per block / links per thread: the shape that wastes the fewest link slots
+            int bt = 256;
+            if (dn && std::atoi(dn) >= 64) bt = std::atoi(dn);
+            h->dense_bt = bt;
+            h->lpt = (h->N + bt - 1) / bt;
+        }
+        const size_t smem = dense ? d2d_dense_layout(h->N, cfg->num_rbs, h->bin_cap).total
+                          : h->lpt ? d2d_block2_smem_bytes(h->N, cfg->num_rbs) : d2d_block_smem_bytes(h->N, cfg->num_rbs);
         if (smem > 227 * 1024) return bail(fail(D2D_ERR_UNSUPPORTED, "d2d_create: too many links / RBs for one SM's shared memory"));
 #define D2D_PLAN_BLOCK(LPT_) (h->ple2 ? plan_geometry(h, d2d_step_block_kernel<true, LPT_>, D2D_BLOCK_THREADS, smem, 1) \
                                       : plan_geometry(h, d2d_step_block_kernel<false, LPT_>, D2D_BLOCK_THREADS, smem, 1))
-        switch (h->lpt) {
+#define D2D_PLAN_DENSE(LPT_, BT_) (h->ple2 ? plan_dense<true, LPT_, BT_>(h, smem) \
+                                           : plan_dense<false, LPT_, BT_>(h, smem))
+        if (dense) {
+            rc = fail(D2D_ERR_UNSUPPORTED, "d2d_create: no dense kernel instantiation for this shape");
+            D2D_DENSE_SHAPES(D2D_DENSE_PLAN_CASE)
+        } else switch (h->lpt) {
             case 1: rc = D2D_PLAN_BLOCK(1); break;
             case 2: rc = D2D_PLAN_BLOCK(2); break;
             case 3: rc = D2D_PLAN_BLOCK(3); break;
@@ -358,9 +394,12 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
                 rc = h->ple2 ? plan_geometry(h, d2d_step_block_generic_kernel<true>, D2D_BLOCK_THREADS, smem, 1)
                              : plan_geometry(h, d2d_step_block_generic_kernel<false>, D2D_BLOCK_THREADS, smem, 1);
         }
+#undef D2D_PLAN_DENSE
 #undef D2D_PLAN_BLOCK
     }
     if (rc != D2D_OK) return bail(rc);
+    if (const char *gs = std::getenv("D2D_B200_GRID"))      // tests: few blocks, so every block steps many envs
+        if (std::atoi(gs) > 0) h->grid = std::min(h->grid, std::atoi(gs));
     *out = h;
     return D2D_OK;
 }
@@ -501,6 +540,16 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, void *stream) {
         } else {
 #define D2D_LAUNCH_BLOCK(LPT_) (h->ple2 ? launch_step(d2d_step_block_kernel<true, LPT_>, grid, h->block, h->smem, st, P, h->pdl) \
                                         : launch_step(d2d_step_block_kernel<false, LPT_>, grid, h->block, h->smem, st, P, h->pdl))
+#define D2D_LAUNCH_DENSE4(PLE2_, LPT_, BT_, FULL_, EXACT_) \
+    launch_step(d2d_step_dense_kernel<PLE2_, LPT_, BT_, FULL_, EXACT_>, grid, h->block, h->smem, st, P, h->pdl)
+#define D2D_LAUNCH_DENSE3(PLE2_, LPT_, BT_)                                                                                    \
+    (full && h->uniform ? (exact ? D2D_LAUNCH_DENSE4(PLE2_, LPT_, BT_, true, true) : D2D_LAUNCH_DENSE4(PLE2_, LPT_, BT_, true, false)) \
+                        : (exact ? D2D_LAUNCH_DENSE4(PLE2_, LPT_, BT_, false, true) : D2D_LAUNCH_DENSE4(PLE2_, LPT_, BT_, false, false)))
+#define D2D_LAUNCH_DENSE(LPT_, BT_) (h->ple2 ? D2D_LAUNCH_DENSE3(true, LPT_, BT_) : D2D_LAUNCH_DENSE3(false, LPT_, BT_))
+            if (h->dense_bt) {
+                err = cudaErrorInvalidValue;
+                D2D_DENSE_SHAPES(D2D_DENSE_LAUNCH_CASE)
+            } else
             switch (h->lpt) {
                 case 1: err = D2D_LAUNCH_BLOCK(1); break;
                 case 2: err = D2D_LAUNCH_BLOCK(2); break;
@@ -511,6 +560,9 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, void *stream) {
                                   : launch_step(d2d_step_block_generic_kernel<false>, grid, h->block, h->smem, st, P, h->pdl);
             }
 #undef D2D_LAUNCH_BLOCK
+#undef D2D_LAUNCH_DENSE
+#undef D2D_LAUNCH_DENSE3
+#undef D2D_LAUNCH_DENSE4
         }
         if (err != cudaSuccess) return fail(D2D_ERR_CUDA, std::string("step kernel launch: ") + cudaGetErrorString(err));
         ++h->launches;

@@ -53,6 +53,7 @@ struct D2DParams {
     int32_t n_pwr_cue, n_pwr_due;
     int32_t episode_length;
     int32_t nbins;               // block kernel: number of RB bins
+    int32_t bin_cap;             // dense kernel: record slots per RB bin
     int32_t align4;              // warp kernel: every env's DUE (tx, rx) pair is a 16-byte aligned float4
     int32_t reward_fn;           // d2d_reward_fn: per-agent reward functions take their reward statistics from the post-pass kernel
     int32_t uniform;             // every CUE link shares one set of constants, and every DUE link (u_cue / u_due below)

@@ -1,0 +1,392 @@
+// d2d_step_dense.cuh - fused env.step for 65 <= N <= 1024 links, one thread block per environment, ONE block barrier per env
+// (BASELINE config #3: 100 RBs / 100 CUEs / 500 DUE pairs -> N = 600, V = 1101).
+//
+// Same arithmetic contract as d2d_step_warp.cuh (simulator.py:89-154).  What differs from the sorting block
+// kernel (d2d_step_block.cuh: count -> scan -> scatter -> walk, four barriers per env) is the same-RB grouping of
+// Actions.get_actions_by_rb (actions.py:27-31): like the warp kernel it is a BINNED table - rank = atomicAdd(count[rb]) and the
+// link's 16-byte peer record goes straight to bin[rb][rank] - so there is no scan and no scatter pass, and the tables are
+// multi-buffered so that consecutive envs overlap inside a block:
+//
+//   per env e (bins buffer e & 1, counter buffer e % 3):
+//     phase 1  take the env's inputs (prefetched into registers one env ahead), decode (envs/d2d_env.py:93-101), rank, record
+//     barrier  (the only one)
+//     deferred the reward / done / statistics of env e - 1 (its warps' partial sums are complete now), zero env e - 1's counters
+//     phase 2  every victim walks its RB's bin (simulator.py:95-101), epilogue, rare warp-cooperative fp64 pass, stores,
+//              per-warp partial sums of the reward reduction (envs/reward_fn.py:27-44)
+//
+// A warp that is still in phase 2 of env e never collides with one that already fills the tables of env e + 1 (other
+// buffers); the counters of env e - 1 are cleared after the barrier of env e and reused by env e + 2, after the barrier of
+// env e + 1.  A bin holds `bin_cap` records (mean + 4 sigma of the per-RB load, odd so that consecutive bins start on different
+// banks); links beyond that (a crowded RB: 0.7 % of the dense envs, or a policy that puts everyone on one RB) go to a
+// per-env overflow list that only the victims of an overflowing RB scan; an env that used it ends with a second barrier,
+// so the list needs one buffer only.
+//
+// A record is (tx_x, tx_y, w, who): w = 10^(p/10) 10^((eo-K)/10) is the radiated weight, who = link | Tx power << 16 (read by
+// the fp64 pass only).  CUE victims - whose receiver is the MBS - take the same walk as DUE victims with rx = (0, 0).
+#pragma once
+
+#include "d2d_common.cuh"
+
+#define D2D_DENSE_MAX_LPT 5
+#define D2D_DENSE_MAX_WARPS 16
+// blocks per SM the register allocation has to allow (80 registers at 256 threads)
+#define D2D_DENSE_MINB(BT) ((BT) <= 128 ? 6 : (BT) <= 160 ? 5 : (BT) <= 192 ? 4 : (BT) <= 256 ? 3 : 2)
+
+struct D2DDenseLayout {
+    uint32_t bins, ovrec, pwr, cnt, red, ovrb, total, cnt_words;
+};
+
+__host__ __device__ inline D2DDenseLayout d2d_dense_layout(int N, int R, int cap) {
+    D2DDenseLayout L;
+    uint32_t b = 0;
+    L.pwr = b;   b += D2D_MAX_PWR_LEVELS * 4u;                            // 10^(p/10)                        (fixed offsets first)
+    L.red = b;   b += 2u * 4u * D2D_DENSE_MAX_WARPS * 4u;                 // [2][4][warps]: capacity, acting agents, rescues, penalty
+    L.cnt_words = ((uint32_t)R + 2u + 3u) & ~3u;                          // per buffer: R counters (links | SIDELINKs << 16), overflow count
+    L.cnt = b;   b += 3u * L.cnt_words * 4u;
+    L.bins = b;  b += 2u * (uint32_t)R * (uint32_t)cap * 16u;            // [2][R][cap] float4 peer records
+    L.ovrec = b; b += (uint32_t)N * 16u;                                  // [N] overflow records
+    L.ovrb = b;  b += ((uint32_t)N * 2u + 15u) & ~15u;                    // [N] RB of each overflow record
+    L.total = b;
+    return L;
+}
+
+// bin capacity for an expected per-RB load of N / R links: mean + 4 sigma, at least 8, odd
+__host__ inline int d2d_dense_bin_cap(int N, int R) {
+    const double m = (double)N / (double)(R > 0 ? R : 1);
+    int cap = (int)(m + 4.0 * sqrt(m) + 2.0);
+    if (cap < 8) cap = 8;
+    if (cap > N) cap = N;
+    return cap | 1;
+}
+
+// interferer record rk's fp64 term at receiver rxd (the cooperative fp64 pass)
+template <bool PLE2>
+__device__ __forceinline__ double d2d_dense_term_f64(const float4 rk, const double2 rxd, const double2 *pe64, uint32_t C, const D2DParams &P) {
+    const uint32_t wk = __float_as_uint(rk.w), kk = wk & 0xffffu;
+    const double2 tk = pe64 ? pe64[d2d_tx_dev((int)kk, (int)C)] : make_double2((double)rk.x, (double)rk.y);
+    const double ex = tk.x - rxd.x, ey = tk.y - rxd.y;
+    return P.pwr_lin_d[wk >> 16] * P.linkD[kk].t_lin * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, P.ple_d);
+}
+
+// What the fp64 pass changes of a link's outputs: flag 1 = sinr_dB, 2 = snr_dB, 4 = rate and capacity
+struct D2DDenseFix {
+    float sinr_dB, snr_dB, rate, cap;
+    uint32_t flags;
+};
+
+// Warp-cooperative fp64 recomputation of link vj of env e (rb, slot in its bin and Tx power given): the lanes split the RB's
+// peer records, a butterfly sums their terms, every lane returns the same result.  Kept out of line: rare, and its fp64
+// registers must not count against the hot loop's allocation.
+template <bool PLE2>
+__device__ __noinline__ D2DDenseFix d2d_dense_rescue(const D2DParams &P, uint32_t e, uint32_t vj, uint32_t vrb, uint32_t vself, uint32_t vpw,
+                                                     const float4 *bp, const uint32_t *cn, const float4 *ovrec, const uint16_t *ovrb,
+                                                     uint32_t ovn, uint32_t lane) {
+    const uint32_t C = (uint32_t)P.C, V = (uint32_t)P.V, CAP = (uint32_t)P.bin_cap;
+    const bool exact = P.pos64 != nullptr;
+    const double2 *pe64 = exact ? reinterpret_cast<const double2 *>(P.pos64) + (int64_t)e * V : nullptr;
+    const float2 *pe = reinterpret_cast<const float2 *>(P.pos) + (uint64_t)e * V;
+    const double2 txd = d2d_pos_f64(pe, pe64, d2d_tx_dev((int)vj, (int)C));
+    const double2 rxd = vj < C ? make_double2(0.0, 0.0) : d2d_pos_f64(pe, pe64, d2d_rx_dev((int)vj, (int)C));    // the MBS sits at the origin
+    const uint32_t vn = cn[vrb] & 0xffffu, vnb = min(vn, CAP);
+    const float4 *vbase = bp + vrb * CAP;
+    double I64 = 0.0;
+    for (uint32_t q = lane; q < vnb; q += 32u)
+        if (q != vself) I64 += d2d_dense_term_f64<PLE2>(vbase[q], rxd, pe64, C, P);
+    if (vn > CAP)
+        for (uint32_t q = lane; q < ovn; q += 32u)
+            if (ovrb[q] == (uint16_t)vrb && CAP + q != vself) I64 += d2d_dense_term_f64<PLE2>(ovrec[q], rxd, pe64, C, P);
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1)
+        I64 += __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(I64), sh), __shfl_xor_sync(0xffffffffu, __double2loint(I64), sh));
+    const D2DLinkD Lj = P.linkD[vj];
+    const float sens = P.uniform ? (vj < C ? P.us_cue.x : P.us_due.x) : P.linkB[vj].sens_dBm;
+    const double ex = txd.x - rxd.x, ey = txd.y - rxd.y;
+    const double Sg = P.pwr_lin_d[vpw] * Lj.a_lin * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, P.ple_d);
+    const double r = Sg * d2d_rcp_f64(fma(I64, Lj.inv_noise, 1.0));
+    const bool r1 = fabs(r - 1.0) < 0.0625, s1 = fabs(Sg - 1.0) < 0.0625;
+    D2DDenseFix f = {0.f, 0.f, 0.f, 0.f, 0u};
+    double sinr = 0.0;
+    if (exact || r1) { sinr = r1 ? d2d_db_near1(r) : 4.3429448190325182765 * d2d_ln_f64(r); f.sinr_dB = (float)sinr; f.flags |= 1u; }
+    if (exact || s1) { f.snr_dB = (float)(s1 ? d2d_db_near1(Sg) : 4.3429448190325182765 * d2d_ln_f64(Sg)); f.flags |= 2u; }
+    if (exact || (r1 && fabsf(sens) < 0.5f)) {
+        const double rate = sinr > (double)sens ? 1.4426950408889634074 * d2d_ln_f64(1.0 + r) : 0.0;
+        f.rate = (float)rate; f.cap = (float)(Lj.bw_MHz * rate); f.flags |= 4u;
+    }
+    return f;
+}
+
+// FULL: exactly the core outputs (obs, capacity, reward, done) and the step counters are bound and every link of a type shares
+// one set of constants (no per-device overrides) - the VecD2DEnv default - so the hot path tests no pointer and selects its
+// constants from the constant bank.  EXACT: an fp64 shadow of the positions is bound (the fp64 pass then needs d_min).
+template <bool PLE2, int LPT, int BT, bool FULL, bool EXACT>
+__global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(const __grid_constant__ D2DParams P) {
+    extern __shared__ __align__(16) unsigned char d2d_dense_smem[];
+    constexpr uint32_t NW = BT / 32;
+    const uint32_t N = (uint32_t)P.N, C = (uint32_t)P.C, V = (uint32_t)P.V, R = (uint32_t)P.R, CAP = (uint32_t)P.bin_cap;
+    const D2DDenseLayout L = d2d_dense_layout((int)N, (int)R, (int)CAP);
+    float4 *bins = reinterpret_cast<float4 *>(d2d_dense_smem + L.bins);
+    float4 *ovrec = reinterpret_cast<float4 *>(d2d_dense_smem + L.ovrec);
+    float *pwr = reinterpret_cast<float *>(d2d_dense_smem + L.pwr);
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(d2d_dense_smem + L.cnt);
+    float *red = reinterpret_cast<float *>(d2d_dense_smem + L.red);
+    uint16_t *ovrb = reinterpret_cast<uint16_t *>(d2d_dense_smem + L.ovrb);
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    d2d_pdl_launch_dependents();
+
+    for (uint32_t i = tid; i < D2D_MAX_PWR_LEVELS; i += BT) pwr[i] = P.pwr_lin[i];
+    for (uint32_t i = tid; i < 3u * L.cnt_words; i += BT) cnt[i] = 0u;
+    bool has[LPT], cue[LPT];
+#pragma unroll
+    for (int k = 0; k < LPT; ++k) {
+        const uint32_t j = tid + k * BT;
+        has[k] = j < N; cue[k] = j < C;
+    }
+    // link constants (tx_lin0, a_lin, inv_noise, snr0_dB) and (sens, bw): one set per link type from the constant bank unless
+    // a device-config file overrode single devices (then the per-link tables, through L1)
+    auto link_cA = [&](uint32_t j, bool is_cue) -> float4 {
+        return (FULL || P.uniform) ? (is_cue ? P.u_cue : P.u_due) : __ldg(reinterpret_cast<const float4 *>(P.linkA) + j);
+    };
+    auto link_sB = [&](uint32_t j, bool is_cue) -> float2 {
+        return (FULL || P.uniform) ? (is_cue ? P.us_cue : P.us_due) : __ldg(reinterpret_cast<const float2 *>(P.linkB + j));
+    };
+    // one coalesced pass over an env's inputs: action, transmitter and (DUE) receiver position of each of this thread's links
+    auto load_inputs = [&](uint32_t e, uint32_t (&a)[LPT], float2 (&tx)[LPT], float2 (&rx)[LPT]) {
+        const int32_t *act = P.actions + e * N;
+        const float2 *pe = reinterpret_cast<const float2 *>(P.pos) + e * V;
+#pragma unroll
+        for (int k = 0; k < LPT; ++k) {
+            const uint32_t j = tid + k * BT;
+            a[k] = 0xffffffffu; tx[k] = make_float2(1.f, 0.f); rx[k] = make_float2(0.f, 0.f);
+            if (has[k]) {
+                a[k] = (uint32_t)__ldg(act + j);
+                const uint32_t txd = cue[k] ? 1u + j : 1u + C + 2u * (j - C);
+                tx[k] = __ldg(pe + txd);
+                if (!cue[k]) rx[k] = __ldg(pe + txd + 1u);
+            }
+        }
+    };
+    float st_reward = 0.f, st_cap = 0.f, st_reward2 = 0.f, st_pen = 0.f, st_resc = 0.f, st_n = 0.f;   // of the envs this thread owns
+
+    const uint32_t num_envs = (uint32_t)P.num_envs;
+    const uint32_t per_block = (num_envs + gridDim.x - 1u) / gridDim.x;
+    const uint32_t e0 = min(blockIdx.x * per_block, num_envs), e_end = min(e0 + per_block, num_envs);
+    uint32_t g = 0;                  // position of the env in its group of BT
+    int ns_keep = 0;                 // thread i: step counter of the group's env i
+    float rew_keep = 0.f;            // thread i: reward of the group's env i
+
+    // reward / statistics of env `ep` (buffer pb of red), by the thread that owns it; the group's scalars when it is complete
+    auto finalise = [&](uint32_t ep, uint32_t gp, bool flush) {
+        if (tid == gp) {
+            const float *rd = red + (ep & 1u) * 4u * D2D_DENSE_MAX_WARPS;
+            float cs = 0.f, na = 0.f, rs = 0.f, bd = 0.f;
+#pragma unroll
+            for (uint32_t w2 = 0; w2 < NW; ++w2) {
+                cs += rd[w2]; na += rd[D2D_DENSE_MAX_WARPS + w2]; rs += rd[2 * D2D_DENSE_MAX_WARPS + w2]; bd += rd[3 * D2D_DENSE_MAX_WARPS + w2];
+            }
+            const bool any_bad = bd != 0.f;
+            const float reward = any_bad ? -1.0f : cs / na;
+            rew_keep = reward;
+            if (P.reward_fn == 0) { st_reward += reward; st_reward2 = fmaf(reward, reward, st_reward2); }
+            st_cap += cs;
+            st_pen += any_bad ? 1.f : 0.f; st_resc += rs; st_n += 1.f;
+        }
+        if (flush && tid <= gp) {
+            // envs/d2d_env.py:65,68 for the whole group: num_steps += 1; done = num_steps >= EPISODE_LENGTH
+            const uint32_t eg = ep - gp + tid;
+            const int ns = min(ns_keep + 1, 255);
+            if (FULL || P.step_count) P.step_count[eg] = (uint8_t)ns;
+            if (FULL || P.reward) P.reward[eg] = rew_keep;
+            if (FULL || P.done) P.done[eg] = ns >= P.episode_length ? 1 : 0;
+        }
+    };
+
+    uint32_t an[LPT];
+    float2 txn[LPT], rxn[LPT];
+    if (e0 < e_end) load_inputs(e0, an, txn, rxn);
+    __syncthreads();
+    // (griddepcontrol.wait comes before the first access to memory an earlier step wrote - see d2d_step_warp.cuh)
+
+    uint32_t c3 = 0;                 // e % 3 without the division
+    for (uint32_t e = e0; e < e_end; ++e) {
+        uint32_t *cn = cnt + c3 * L.cnt_words;
+        float4 *bp = bins + (e & 1u) * R * CAP;
+
+        // ---- phase 1: inputs (the next env's loads go out first), decode, rank inside the RB, peer record --------------------
+        uint32_t a[LPT];
+        float2 tx[LPT], rx[LPT];
+#pragma unroll
+        for (int k = 0; k < LPT; ++k) { a[k] = an[k]; tx[k] = txn[k]; rx[k] = rxn[k]; }
+        if (e + 1u < e_end) load_inputs(e + 1u, an, txn, rxn);
+        float pl[LPT];
+        uint32_t rb[LPT], pw[LPT], selfq[LPT];
+        bool live[LPT];
+#pragma unroll
+        for (int k = 0; k < LPT; ++k) {
+            const uint32_t j = tid + k * BT;
+            const uint32_t npw = (uint32_t)(cue[k] ? P.n_pwr_cue : P.n_pwr_due);
+            live[k] = has[k] && a[k] < R * npw;                   // valid actions: 0 <= a < R n_pwr (envs/d2d_env.py:36-40)
+            const uint32_t as = live[k] ? a[k] : 0u;
+            rb[k] = __umulhi(as, cue[k] ? P.magic_cue : P.magic_due) + (as & (cue[k] ? P.npw1_cue : P.npw1_due));
+            pw[k] = as - rb[k] * npw;
+            pl[k] = live[k] ? pwr[pw[k]] : 0.0f;
+            selfq[k] = 0u;
+            if (live[k]) {
+                const uint32_t rank = atomicAdd(&cn[rb[k]], cue[k] ? 1u : 0x10001u) & 0xffffu;      // high half counts the SIDELINKs
+                const float4 rec = make_float4(tx[k].x, tx[k].y, pl[k] * link_cA(j, cue[k]).x, __uint_as_float(j | (pw[k] << 16)));
+                if (rank < CAP) {
+                    selfq[k] = rank;
+                    bp[rb[k] * CAP + rank] = rec;
+                } else {                                                                         // crowded RB: the env's overflow list
+                    const uint32_t s = atomicAdd(&cn[R], 1u);
+                    selfq[k] = CAP + s;
+                    ovrec[s] = rec;
+                    ovrb[s] = (uint16_t)rb[k];
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- deferred: env e - 1 is complete (every warp's partial sums are in), its counters can go ------------------------
+        if (e == e0) d2d_pdl_wait();
+        if (e > e0) finalise(e - 1u, g == 0u ? BT - 1u : g - 1u, g == 0u);
+        if (g == 0u && (FULL || P.step_count)) ns_keep = e + tid < e_end ? (int)P.step_count[e + tid] : 0;      // consumed at the group's flush
+        {
+            uint32_t *cprev = cnt + (c3 == 0u ? 2u : c3 - 1u) * L.cnt_words;
+            for (uint32_t i = tid; i <= R; i += BT) cprev[i] = 0u;
+        }
+        const uint32_t ovn = cn[R];                               // block-uniform: the env spilled into the overflow list
+
+        // ---- phase 2: interference walk (simulator.py:95-101), epilogue, outputs --------------------------------------------------
+        float cap_part = 0.0f;
+        float capk[LPT];
+        uint32_t n_act = 0, resc = 0, badbits = 0, needbits = 0;     // needbits: bit k = slot k needs the fp64 pass, bit 8 + k = it is a CUE sharing its RB with a SIDELINK
+#pragma unroll
+        for (int k = 0; k < LPT; ++k) {
+            const uint32_t j = tid + k * BT;
+            D2DLinkOut o = {0.f, 0.f, 0.f, 0.f};
+            bool need = false, side = false;
+            float2 sBk = make_float2(0.f, 0.f);
+            if (live[k]) {
+                const uint32_t cw = cn[rb[k]], n = cw & 0xffffu, nb = min(n, CAP);
+                side = (cw >> 16) != 0u;
+                const float4 *base = bp + rb[k] * CAP;
+                float I = 0.0f, dmin2 = 3.0e38f;
+#pragma unroll 2
+                for (uint32_t q = 0; q < nb; ++q) {
+                    const float4 rk = base[q];
+                    const float dx = rk.x - rx[k].x, dy = rk.y - rx[k].y;
+                    const float d2 = fmaf(dx, dx, dy * dy);
+                    const float gq = d2d_gain<PLE2>(d2, P.neg_half_ple);
+                    I = fmaf(rk.z, q == selfq[k] ? 0.0f : gq, I);             // the victim's own record is skipped by index
+                    if (EXACT) dmin2 = fminf(dmin2, d2);
+                }
+                if (n > CAP) {
+                    for (uint32_t q = 0; q < ovn; ++q) {
+                        if (ovrb[q] != (uint16_t)rb[k] || CAP + q == selfq[k]) continue;
+                        const float4 rk = ovrec[q];
+                        const float dx = rk.x - rx[k].x, dy = rk.y - rx[k].y;
+                        const float d2 = fmaf(dx, dx, dy * dy);
+                        I = fmaf(rk.z, d2d_gain<PLE2>(d2, P.neg_half_ple), I);
+                        dmin2 = fminf(dmin2, d2);
+                    }
+                }
+                const float dxo = tx[k].x - rx[k].x, dyo = tx[k].y - rx[k].y;       // own link (a CUE's receiver is the MBS at the origin)
+                const float d2own = fmaf(dxo, dxo, dyo * dyo);
+                const float lg = d2d_lg2(d2own);
+                const float gown = PLE2 ? d2d_rcp(d2own) : d2d_ex2(P.neg_half_ple * lg);
+                sBk = link_sB(j, cue[k]);
+                o = d2d_link_epilogue<PLE2>((int)pw[k], pl[k], lg, gown, I, link_cA(j, cue[k]), sBk, P);
+                need = D2D_RESCUE_ENABLED && d2d_needs_rescue<EXACT>(o, fminf(dmin2, d2own), P);
+            }
+            if (live[k]) {
+                cap_part += o.cap;
+                ++n_act;
+                if (cue[k] && side && o.cap <= P.min_cap) badbits |= 1u << k;      // envs/reward_fn.py:30-39
+                if (need) needbits |= 1u << k;
+                if (cue[k] && side) needbits |= 0x100u << k;
+            }
+            capk[k] = o.cap;
+            if (has[k]) {
+                const uint32_t gi = e * N + j;
+                if (FULL || P.obs) {
+                    float2 *ob = reinterpret_cast<float2 *>(reinterpret_cast<char *>(P.obs) + (uint64_t)gi * 24u);
+                    ob[0] = tx[k];                                   // an absent agent's row keeps its positions (sinr = snr = 0)
+                    ob[1] = rx[k];
+                    ob[2] = make_float2(o.sinr_dB, o.snr_dB);
+                }
+                if (FULL || P.cap) P.cap[gi] = o.cap;
+                if (!FULL) {
+                    if (P.rate) P.rate[gi] = o.rate;
+                    if (P.rb_out) P.rb_out[gi] = live[k] ? (int16_t)rb[k] : (int16_t)0;
+                    if (P.pwr_out) P.pwr_out[gi] = live[k] ? (int16_t)pw[k] : (int16_t)0;
+                }
+            }
+        }
+
+        // ---- rare fp64 pass (d2d_common.cuh; same policy as d2d_rescue_warp): ~0.2 % of the links, about one per dense env.
+        // The victim's warp takes it together - its lanes split the RB's peer records, a butterfly sums their terms - so the
+        // block's other warps are not held up at the next barrier by one thread's serial fp64 loop.  The victim's lane then
+        // rewrites (after its own stores above) what fp32 could not deliver.
+        if (D2D_RESCUE_ENABLED && __any_sync(0xffffffffu, (needbits & 0xffu) != 0u)) {
+#pragma unroll
+            for (int k = 0; k < LPT; ++k) {
+                uint32_t mask = __ballot_sync(0xffffffffu, (needbits >> k) & 1u);
+                while (mask) {
+                    const int src = __ffs((int)mask) - 1;
+                    mask &= mask - 1u;
+                    ++resc;
+                    const uint32_t vj = (tid - lane) + (uint32_t)src + k * BT;
+                    const D2DDenseFix f = d2d_dense_rescue<PLE2>(P, e, vj, __shfl_sync(0xffffffffu, rb[k], src), __shfl_sync(0xffffffffu, selfq[k], src),
+                                                                 __shfl_sync(0xffffffffu, pw[k], src), bp, cn, ovrec, ovrb, ovn, lane);
+                    if ((int)lane == src) {
+                        const uint64_t gi = (uint64_t)e * N + vj;
+                        if ((f.flags & 1u) && (FULL || P.obs)) P.obs[gi * 6u + 4u] = f.sinr_dB;
+                        if ((f.flags & 2u) && (FULL || P.obs)) P.obs[gi * 6u + 5u] = f.snr_dB;
+                        if (f.flags & 4u) {
+                            if (FULL || P.cap) P.cap[gi] = f.cap;
+                            if (!FULL && P.rate) P.rate[gi] = f.rate;
+                            cap_part += f.cap - capk[k];
+                            badbits &= ~(1u << k);
+                            if (((needbits >> (8 + k)) & 1u) && f.cap <= P.min_cap) badbits |= 1u << k;
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- per-warp partial sums of the reward reduction (envs/reward_fn.py:27-44); the env's owner adds them up after the
+        // next barrier (finalise) ----------------------------------------------------------------------------------------------------
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) cap_part += __shfl_xor_sync(0xffffffffu, cap_part, s);
+        const uint32_t n_act_w = __reduce_add_sync(0xffffffffu, n_act);
+        const bool bad_w = __any_sync(0xffffffffu, badbits != 0u);
+        if (lane == 0) {
+            float *rd = red + (e & 1u) * 4u * D2D_DENSE_MAX_WARPS;
+            rd[warp] = cap_part; rd[D2D_DENSE_MAX_WARPS + warp] = (float)n_act_w;
+            rd[2 * D2D_DENSE_MAX_WARPS + warp] = (float)resc; rd[3 * D2D_DENSE_MAX_WARPS + warp] = bad_w ? 1.f : 0.f;     // resc is warp-uniform
+        }
+        if (ovn != 0u) __syncthreads();      // the overflow list has one buffer: everybody is done with it before the next env fills it
+        g = g + 1u == BT ? 0u : g + 1u;
+        c3 = c3 == 2u ? 0u : c3 + 1u;
+    }
+    __syncthreads();
+    if (e_end > e0) finalise(e_end - 1u, g == 0u ? BT - 1u : g - 1u, true);
+
+    if (P.stats) {
+        // block totals of the six statistics -> one fp64 atomic each
+        float v[6] = {st_reward, st_cap, st_reward2, st_n, st_pen, st_resc};
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], s);
+            if (lane == 0) red[i * D2D_DENSE_MAX_WARPS + warp] = v[i];
+        }
+        __syncthreads();
+        if (tid < 6) {
+            double t = 0.0;
+            for (uint32_t w2 = 0; w2 < NW; ++w2) t += (double)red[tid * D2D_DENSE_MAX_WARPS + w2];
+            if (t != 0.0) atomicAdd(P.stats + (blockIdx.x % D2D_STATS_REPLICAS) * 8 + tid, t);
+        }
+    }
+}

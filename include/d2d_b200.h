@@ -34,7 +34,7 @@
 #define D2D_API __attribute__((visibility("default")))
 #endif
 
-#define D2D_ABI_VERSION 2
+#define D2D_ABI_VERSION 3
 
 typedef struct d2d_handle d2d_handle_t;
 
