@@ -883,3 +883,46 @@ def test_shadowing_path_loss_matches_oracle_draw_for_draw(name):
     far = np.linalg.norm(pos[:, 1 + cfg.num_cues::2] - pos[:, 2 + cfg.num_cues::2], axis=-1) > 90.0
     assert far.any() and (~far).any()
     env.close()
+
+
+@pytest.mark.parametrize('info', [True, False])
+def test_dense_kernel_pipeline_crowded_rbs_and_absent_agents(monkeypatch, info):
+    """The binned one-barrier kernel (d2d_step_dense.cuh) where its bookkeeping is hardest: three blocks stepping 300 envs each
+    (so consecutive envs overlap inside a block, the counter / bin buffers rotate and a group of 256 per-env scalars is flushed
+    mid-range), RBs that hold more links than a bin has slots (everybody on one RB -> the overflow list and its extra
+    barrier), absent agents, two consecutive steps (step counters, done).  info=False runs the FULL instantiation."""
+    import gym_d2d_b200 as G
+    monkeypatch.setenv('D2D_B200_GRID', '3')
+    kw = dict(num_rbs=4, num_cues=40, num_due_pairs=60)            # N = 100, 25 links per RB on average, 47 record slots per bin
+    cfg = O.OracleConfig(**kw)
+    E = 900
+    rng = np.random.default_rng(4242)
+    pos = O.random_positions(cfg, E, rng, fp32_exact=True)
+    env = G.VecD2DEnv(E, dict(kw), device='cuda', info=info)
+    assert env.step_geometry()['grid'] == 3
+    env.set_positions(pos)
+    for s in range(2):
+        act = O.random_actions(cfg, E, rng)
+        npw = np.where(np.arange(cfg.num_links) < cfg.num_cues, cfg.cue_max_tx_power_dBm + 1,
+                       cfg.due_max_tx_power_dBm - cfg.due_min_tx_power_dBm + 1)
+        crowded = np.arange(E) % 5 == 0
+        act[crowded] = act[crowded] % npw                           # rb = 0 for every link: 100 links on one RB
+        two = np.arange(E) % 11 == 3
+        act[two] = act[two] % (2 * npw)                             # two RBs of ~50 links: both overflow
+        absent = (np.arange(E) % 7 == 0)[:, None] & (rng.random((E, cfg.num_links)) < 0.5)
+        ref = O.step_batch(cfg, pos, act, active=(~absent).astype(np.uint8), nthreads=8)
+        obs, reward, done, inf = env.step(torch.as_tensor(np.where(absent, -1, act), dtype=torch.int32, device='cuda').contiguous())
+        torch.cuda.synchronize()
+        on = ~absent
+        assert_rel(obs[..., 4].cpu().numpy()[on], ref['sinr_db'][on], RTOL, 'sinr_db')
+        assert_rel(obs[..., 5].cpu().numpy()[on], ref['snr_db'][on], RTOL, 'snr_db')
+        assert_rel(inf['capacity_mbps'].cpu().numpy()[on], ref['capacity_mbps'][on], RTOL, 'capacity')
+        assert (inf['capacity_mbps'].cpu().numpy()[~on] == 0).all() and (obs[..., 4].cpu().numpy()[~on] == 0).all()
+        assert_rel(reward.cpu().numpy(), ref['reward'], RTOL, 'reward')
+        assert (env.step_count.cpu().numpy() == s + 1).all() and (done.cpu().numpy() == 0).all()
+        if info:
+            np.testing.assert_array_equal(inf['rb'].cpu().numpy()[on], ref['rb'][on])
+            np.testing.assert_array_equal(inf['tx_pwr_dbm'].cpu().numpy()[on], ref['tx_pwr_dbm'][on])
+    st = env.stats()
+    assert st['env_steps'] == 2 * E
+    env.close()
