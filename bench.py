@@ -308,13 +308,13 @@ def run_cuda_arm(args) -> None:
     sampler.start()
     windows = []
 
-    def build(num_envs, seed=0):
-        env = G.VecD2DEnv(num_envs, {}, device=torch.device('cuda', local), seed=seed, global_env_offset=first)
+    def build(num_envs, seed=0, cfg=None, ring=RING):
+        env = G.VecD2DEnv(num_envs, dict(cfg or {}), device=torch.device('cuda', local), seed=seed, global_env_offset=first)
         env.reset()
         gen = torch.Generator(device=env.device)
         gen.manual_seed(1000 + rank)
-        acts = [env.sample_actions(gen) for _ in range(RING)]
-        outs = [env.alloc_outputs() for _ in range(RING)]
+        acts = [env.sample_actions(gen) for _ in range(ring)]
+        outs = [env.alloc_outputs() for _ in range(ring)]
         return env, acts, outs
 
     # ---- headline: configs[1], E envs per GPU --------------------------------------------------------------
@@ -435,6 +435,26 @@ def run_cuda_arm(args) -> None:
         envL.close()
         del envL, actsL, outsL
 
+    # ---- dense cell: BASELINE configs[2] (100 RBs / 100 CUEs / 500 DUE pairs, FreeSpacePathLoss, 65536 envs: 1.8 GB per step) ----
+    dense = None
+    if args.dense_envs_per_gpu > 0:
+        ED = args.dense_envs_per_gpu
+        envD, actsD, outsD = build(ED, seed=2, cfg=dict(num_rbs=100, num_cues=100, num_due_pairs=500, path_loss_model=G.FreeSpacePathLoss), ring=4)
+        BD = algorithmic_bytes_per_env_step(envD.num_links, envD.num_devices)
+        stepsD = max(8, min(args.steps, 32))
+        secsD, winD, _ = timed_steps(envD, torch, actsD, outsD, stepsD, 3, pg)
+        windows.append(winD)
+        achD = BD * ED / (secsD / stepsD) / 1e9
+        gD = envD.step_geometry()
+        dense = {'workload': f'BASELINE configs[2]: {ED} envs per GPU of the dense cell (100 RBs, 100 CUEs, 500 DUE pairs: N = 600 links, '
+                             'V = 1101 devices), FreeSpacePathLoss; 4 action/output buffer sets of 1.3 GB',
+                 'value': world * ED * stepsD / secsD, 'unit': UNIT, 'steps': stepsD, 'ms_per_step': 1e3 * secsD / stepsD,
+                 'kernel': 'd2d_step_dense_kernel', 'grid': gD['grid'], 'block': gD['block'], 'smem_bytes': gD['smem_bytes'],
+                 'roofline': {'bound': 'hbm', 'achieved': achD, 'peak': peak, 'unit': 'GB/s', 'frac': achD / peak,
+                              'algorithmic_bytes_per_env_step': BD, 'traffic': None}}
+        envD.close()
+        del envD, actsD, outsD
+
     sampler.stop()
     clocks = sampler.summary(windows)
 
@@ -466,6 +486,8 @@ def run_cuda_arm(args) -> None:
             line['fused_rollout'] = fused
         if large is not None:
             line['large_batch'] = large
+        if dense is not None:
+            line['dense_cell'] = dense
         if base is not None:
             line['cpu_baseline'] = base
         print(json.dumps(line), flush=True)
@@ -482,6 +504,7 @@ def main() -> None:
     ap.add_argument('--impl', choices=['cuda', 'reference'], default='cuda')
     ap.add_argument('--envs-per-gpu', type=int, default=4096)
     ap.add_argument('--large-envs-per-gpu', type=int, default=131072)
+    ap.add_argument('--dense-envs-per-gpu', type=int, default=65536, help='BASELINE configs[2] leg (0 = skip)')
     ap.add_argument('--fused-steps', type=int, default=10, help='T of the d2d_step_many leg (EPISODE_LENGTH); 0/1 skips it')
     ap.add_argument('--skip-e2e', action='store_true')
     ap.add_argument('--skip-cpu-baseline', action='store_true')

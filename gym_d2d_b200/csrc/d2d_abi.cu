@@ -17,7 +17,7 @@
 #include "d2d_step_warp.cuh"
 
 // (links per thread, threads per block) instantiations of the dense kernel
-#define D2D_DENSE_SHAPES(X) X(1, 256) X(2, 256) X(3, 256) X(4, 256) X(2, 320)
+#define D2D_DENSE_SHAPES(X) X(1, 256) X(2, 256) X(3, 256) X(4, 256) X(1, 320) X(2, 320) X(3, 320)
 #define D2D_DENSE_PLAN_CASE(LPT_, BT_) if (h->lpt == LPT_ && h->dense_bt == BT_) rc = D2D_PLAN_DENSE(LPT_, BT_);
 #define D2D_DENSE_LAUNCH_CASE(LPT_, BT_) if (h->lpt == LPT_ && h->dense_bt == BT_) err = D2D_LAUNCH_DENSE(LPT_, BT_);
 
@@ -369,8 +369,10 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
         const char *dn = std::getenv("D2D_B200_DENSE");
         bool dense = h->lpt > 0 && d2d_dense_layout(h->N, cfg->num_rbs, h->bin_cap).total <= 72 * 1024 && !(dn && std::atoi(dn) == 0);
         if (dense) {
-            // threads per block / links per thread: the shape that wastes the fewest link slots
-            int bt = 256;
+            // threads per block / links per thread: the shape with the fewest (warp, slot) bodies per env - every warp runs the
+            // straight-line code of each of its slots whether or not all 32 lanes hold a link (N = 600: 10 warps x 2 slots,
+            // all but one full, instead of 8 warps x 3 with the third slot three-quarters empty)
+            int bt = ((h->N + 319) / 320) * 10 < ((h->N + 255) / 256) * 8 && (h->N + 319) / 320 <= 3 ? 320 : 256;
             if (dn && std::atoi(dn) >= 64) bt = std::atoi(dn);
             h->dense_bt = bt;
             h->lpt = (h->N + bt - 1) / bt;

@@ -30,7 +30,7 @@
 #define D2D_DENSE_MAX_LPT 5
 #define D2D_DENSE_MAX_WARPS 16
 // blocks per SM the register allocation has to allow (80 registers at 256 threads)
-#define D2D_DENSE_MINB(BT) ((BT) <= 128 ? 6 : (BT) <= 160 ? 5 : (BT) <= 192 ? 4 : (BT) <= 256 ? 3 : 2)
+#define D2D_DENSE_MINB(BT) ((BT) <= 128 ? 6 : (BT) <= 160 ? 5 : (BT) <= 192 ? 4 : 3)
 
 struct D2DDenseLayout {
     uint32_t bins, ovrec, pwr, cnt, red, ovrb, total, cnt_words;
@@ -269,15 +269,17 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
             if (live[k]) {
                 const uint32_t cw = cn[rb[k]], n = cw & 0xffffu, nb = min(n, CAP);
                 side = (cw >> 16) != 0u;
-                const float4 *base = bp + rb[k] * CAP;
+                // one induction variable - the record's shared-window address; the victim's own record is skipped by address
+                const uint32_t pb = (uint32_t)__cvta_generic_to_shared(bp + rb[k] * CAP), pend = pb + nb * 16u, pself = pb + selfq[k] * 16u;
                 float I = 0.0f, dmin2 = 3.0e38f;
 #pragma unroll 2
-                for (uint32_t q = 0; q < nb; ++q) {
-                    const float4 rk = base[q];
+                for (uint32_t pa = pb; pa < pend; pa += 16u) {
+                    float4 rk;
+                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(rk.x), "=f"(rk.y), "=f"(rk.z), "=f"(rk.w) : "r"(pa));
                     const float dx = rk.x - rx[k].x, dy = rk.y - rx[k].y;
                     const float d2 = fmaf(dx, dx, dy * dy);
                     const float gq = d2d_gain<PLE2>(d2, P.neg_half_ple);
-                    I = fmaf(rk.z, q == selfq[k] ? 0.0f : gq, I);             // the victim's own record is skipped by index
+                    I = fmaf(rk.z, pa == pself ? 0.0f : gq, I);
                     if (EXACT) dmin2 = fminf(dmin2, d2);
                 }
                 if (n > CAP) {

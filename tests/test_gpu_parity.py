@@ -885,17 +885,19 @@ def test_shadowing_path_loss_matches_oracle_draw_for_draw(name):
     env.close()
 
 
-@pytest.mark.parametrize('info', [True, False])
-def test_dense_kernel_pipeline_crowded_rbs_and_absent_agents(monkeypatch, info):
+@pytest.mark.parametrize('info,kw', [(True, dict(num_rbs=4, num_cues=40, num_due_pairs=60)),         # N = 100: 256 threads x 1 link
+                                     (False, dict(num_rbs=4, num_cues=40, num_due_pairs=60)),
+                                     (False, dict(num_rbs=6, num_cues=60, num_due_pairs=240)),       # N = 300: 320 threads x 1 link
+                                     (True, dict(num_rbs=12, num_cues=100, num_due_pairs=500))])     # N = 600: 320 threads x 2 links
+def test_dense_kernel_pipeline_crowded_rbs_and_absent_agents(monkeypatch, info, kw):
     """The binned one-barrier kernel (d2d_step_dense.cuh) where its bookkeeping is hardest: three blocks stepping 300 envs each
     (so consecutive envs overlap inside a block, the counter / bin buffers rotate and a group of 256 per-env scalars is flushed
     mid-range), RBs that hold more links than a bin has slots (everybody on one RB -> the overflow list and its extra
     barrier), absent agents, two consecutive steps (step counters, done).  info=False runs the FULL instantiation."""
     import gym_d2d_b200 as G
     monkeypatch.setenv('D2D_B200_GRID', '3')
-    kw = dict(num_rbs=4, num_cues=40, num_due_pairs=60)            # N = 100, 25 links per RB on average, 47 record slots per bin
     cfg = O.OracleConfig(**kw)
-    E = 900
+    E = 900 if cfg.num_links <= 300 else 780
     rng = np.random.default_rng(4242)
     pos = O.random_positions(cfg, E, rng, fp32_exact=True)
     env = G.VecD2DEnv(E, dict(kw), device='cuda', info=info)
@@ -906,9 +908,9 @@ def test_dense_kernel_pipeline_crowded_rbs_and_absent_agents(monkeypatch, info):
         npw = np.where(np.arange(cfg.num_links) < cfg.num_cues, cfg.cue_max_tx_power_dBm + 1,
                        cfg.due_max_tx_power_dBm - cfg.due_min_tx_power_dBm + 1)
         crowded = np.arange(E) % 5 == 0
-        act[crowded] = act[crowded] % npw                           # rb = 0 for every link: 100 links on one RB
+        act[crowded] = act[crowded] % npw                           # rb = 0 for every link: all N links on one RB
         two = np.arange(E) % 11 == 3
-        act[two] = act[two] % (2 * npw)                             # two RBs of ~50 links: both overflow
+        act[two] = act[two] % (2 * npw)                             # two RBs of ~N/2 links: both overflow
         absent = (np.arange(E) % 7 == 0)[:, None] & (rng.random((E, cfg.num_links)) < 0.5)
         ref = O.step_batch(cfg, pos, act, active=(~absent).astype(np.uint8), nthreads=8)
         obs, reward, done, inf = env.step(torch.as_tensor(np.where(absent, -1, act), dtype=torch.int32, device='cuda').contiguous())
