@@ -52,6 +52,7 @@ struct d2d_handle {
     bool spec = false;         // warp kernel instantiated for the reference's default EnvConfig shape
     bool uniform = false;      // every CUE link has the same constants, and every DUE link (no per-device overrides)
     D2DLinkA u_cue{}, u_due{};
+    D2DLinkD ud_cue{}, ud_due{};
     float us_cue[2] = {0, 0}, us_due[2] = {0, 0};
     int wpb = 4;               // warps per block of the warp kernel
     int dense_bt = 0;          // dense kernel (d2d_step_dense.cuh): threads per block, 0 = not used
@@ -130,6 +131,7 @@ D2DParams make_params(const d2d_handle *h, const d2d_step_io_t *io) {
     P.us_cue = make_float2(h->us_cue[0], h->us_cue[1]);
     P.us_due = make_float2(h->us_due[0], h->us_due[1]);
     P.uniform = h->uniform ? 1 : 0;
+    P.ud_cue = h->ud_cue; P.ud_due = h->ud_due;
     P.reward_fn = h->cfg.reward_fn;
     P.ple_d = h->ple;
     P.linkA = h->dA; P.linkB = h->dB; P.linkD = h->dD; P.link_meta = h->dMeta; P.pwr_lin = h->dPwr; P.pwr_lin_d = h->dPwrD;
@@ -309,9 +311,12 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
     h->uniform = cfg->num_downlinks == 0;
     for (int j = 0; j < h->N && !cfg->num_downlinks; ++j) {
         const int j0 = j < cfg->num_cues ? 0 : cfg->num_cues;
-        if (std::memcmp(&A[j], &A[j0], sizeof(D2DLinkA)) != 0 || B[j].sens_dBm != B[j0].sens_dBm || B[j].bw_MHz != B[j0].bw_MHz)
+        if (std::memcmp(&A[j], &A[j0], sizeof(D2DLinkA)) != 0 || std::memcmp(&Dv[j], &Dv[j0], sizeof(D2DLinkD)) != 0 ||
+            B[j].sens_dBm != B[j0].sens_dBm || B[j].bw_MHz != B[j0].bw_MHz)
             h->uniform = false;
     }
+    if (cfg->num_cues > 0) h->ud_cue = Dv[0];
+    if (cfg->num_due_pairs > 0) h->ud_due = Dv[cfg->num_cues];
     if (cfg->num_cues > 0) { h->u_cue = A[0]; h->us_cue[0] = B[0].sens_dBm; h->us_cue[1] = B[0].bw_MHz; }
     if (cfg->num_due_pairs > 0) {
         h->u_due = A[cfg->num_cues]; h->us_due[0] = B[cfg->num_cues].sens_dBm; h->us_due[1] = B[cfg->num_cues].bw_MHz;

@@ -70,6 +70,7 @@ struct D2DParams {
     float rescue_dmin2;          // with a shadow: links with a distance^2 below this are always recomputed
     float4 u_cue, u_due;         // default-shape kernel: the one D2DLinkA of every CUE link / every DUE link (constant bank)
     float2 us_cue, us_due;       // ... and the (sens_dBm, bw_MHz) of D2DLinkB
+    D2DLinkD ud_cue, ud_due;     // ... and their fp64 twins for the fp64 pass (valid when `uniform`)
     // ShadowingPathLoss (path_loss.py:69-81; general-topology kernel only): gauss(0, chi) added beyond d0 at EVERY path-loss
     // evaluation.  Counter-based draws: Philox4x32-10 keyed by rng_seed, counter (global env, victim | source << 16, kind, rng_step)
     float shadow_chi_dB;         // 0 = no shadowing

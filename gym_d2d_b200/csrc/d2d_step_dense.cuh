@@ -33,13 +33,14 @@
 #define D2D_DENSE_MINB(BT) ((BT) <= 128 ? 6 : (BT) <= 160 ? 5 : (BT) <= 192 ? 4 : 3)
 
 struct D2DDenseLayout {
-    uint32_t bins, ovrec, pwr, cnt, red, ovrb, total, cnt_words;
+    uint32_t bins, ovrec, pwr, pwr_d, cnt, red, ovrb, total, cnt_words;
 };
 
 __host__ __device__ inline D2DDenseLayout d2d_dense_layout(int N, int R, int cap) {
     D2DDenseLayout L;
     uint32_t b = 0;
-    L.pwr = b;   b += D2D_MAX_PWR_LEVELS * 4u;                            // 10^(p/10)                        (fixed offsets first)
+    L.pwr_d = b; b += D2D_MAX_PWR_LEVELS * 8u;                            // 10^(p/10) in fp64 (the fp64 pass)  (fixed offsets first)
+    L.pwr = b;   b += D2D_MAX_PWR_LEVELS * 4u;                            // 10^(p/10)
     L.red = b;   b += 2u * 4u * D2D_DENSE_MAX_WARPS * 4u;                 // [2][4][warps]: capacity, acting agents, rescues, penalty
     L.cnt_words = ((uint32_t)R + 2u + 3u) & ~3u;                          // per buffer: R counters (links | SIDELINKs << 16), overflow count
     L.cnt = b;   b += 3u * L.cnt_words * 4u;
@@ -59,13 +60,15 @@ __host__ inline int d2d_dense_bin_cap(int N, int R) {
     return cap | 1;
 }
 
-// interferer record rk's fp64 term at receiver rxd (the cooperative fp64 pass)
+// interferer record rk's fp64 term at receiver rxd (the cooperative fp64 pass); pwd = the fp64 power table in shared memory
 template <bool PLE2>
-__device__ __forceinline__ double d2d_dense_term_f64(const float4 rk, const double2 rxd, const double2 *pe64, uint32_t C, const D2DParams &P) {
+__device__ __forceinline__ double d2d_dense_term_f64(const float4 rk, const double2 rxd, const double2 *pe64, uint32_t C, const double *pwd,
+                                                     const D2DParams &P) {
     const uint32_t wk = __float_as_uint(rk.w), kk = wk & 0xffffu;
     const double2 tk = pe64 ? pe64[d2d_tx_dev((int)kk, (int)C)] : make_double2((double)rk.x, (double)rk.y);
     const double ex = tk.x - rxd.x, ey = tk.y - rxd.y;
-    return P.pwr_lin_d[wk >> 16] * P.linkD[kk].t_lin * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, P.ple_d);
+    const double t_lin = P.uniform ? (kk < C ? P.ud_cue.t_lin : P.ud_due.t_lin) : P.linkD[kk].t_lin;
+    return pwd[wk >> 16] * t_lin * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, P.ple_d);
 }
 
 // What the fp64 pass changes of a link's outputs: flag 1 = sinr_dB, 2 = snr_dB, 4 = rate and capacity
@@ -79,29 +82,36 @@ struct D2DDenseFix {
 // registers must not count against the hot loop's allocation.
 template <bool PLE2>
 __device__ __noinline__ D2DDenseFix d2d_dense_rescue(const D2DParams &P, uint32_t e, uint32_t vj, uint32_t vrb, uint32_t vself, uint32_t vpw,
-                                                     const float4 *bp, const uint32_t *cn, const float4 *ovrec, const uint16_t *ovrb,
-                                                     uint32_t ovn, uint32_t lane) {
+                                                     const float4 *bp, const uint32_t *cn, const float4 *ovrec,
+                                                     const uint16_t *ovrb, const double *pwd, uint32_t ovn, uint32_t lane) {
+    // (without an fp64 shadow of the positions and with uniform link constants the only global access is the victim's receiver
+    // position: the transmitters come from the peer records, the tables from shared memory and the constant bank - the pass
+    // sits between two block barriers, so its latency is what the other warps wait for)
     const uint32_t C = (uint32_t)P.C, V = (uint32_t)P.V, CAP = (uint32_t)P.bin_cap;
     const bool exact = P.pos64 != nullptr;
     const double2 *pe64 = exact ? reinterpret_cast<const double2 *>(P.pos64) + (int64_t)e * V : nullptr;
-    const float2 *pe = reinterpret_cast<const float2 *>(P.pos) + (uint64_t)e * V;
-    const double2 txd = d2d_pos_f64(pe, pe64, d2d_tx_dev((int)vj, (int)C));
-    const double2 rxd = vj < C ? make_double2(0.0, 0.0) : d2d_pos_f64(pe, pe64, d2d_rx_dev((int)vj, (int)C));    // the MBS sits at the origin
+    const float4 own = vself < CAP ? bp[vrb * CAP + vself] : ovrec[vself - CAP];                 // the victim's own record: (tx_x, tx_y, ..)
+    const double2 txd = exact ? pe64[d2d_tx_dev((int)vj, (int)C)] : make_double2((double)own.x, (double)own.y);
+    double2 rxd = make_double2(0.0, 0.0);                                                          // a CUE's receiver: the MBS at the origin
+    if (vj >= C) {
+        if (exact) rxd = pe64[d2d_rx_dev((int)vj, (int)C)];
+        else { const float2 r = (reinterpret_cast<const float2 *>(P.pos) + (uint64_t)e * V)[d2d_rx_dev((int)vj, (int)C)]; rxd = make_double2((double)r.x, (double)r.y); }
+    }
     const uint32_t vn = cn[vrb] & 0xffffu, vnb = min(vn, CAP);
     const float4 *vbase = bp + vrb * CAP;
     double I64 = 0.0;
     for (uint32_t q = lane; q < vnb; q += 32u)
-        if (q != vself) I64 += d2d_dense_term_f64<PLE2>(vbase[q], rxd, pe64, C, P);
+        if (q != vself) I64 += d2d_dense_term_f64<PLE2>(vbase[q], rxd, pe64, C, pwd, P);
     if (vn > CAP)
         for (uint32_t q = lane; q < ovn; q += 32u)
-            if (ovrb[q] == (uint16_t)vrb && CAP + q != vself) I64 += d2d_dense_term_f64<PLE2>(ovrec[q], rxd, pe64, C, P);
+            if (ovrb[q] == (uint16_t)vrb && CAP + q != vself) I64 += d2d_dense_term_f64<PLE2>(ovrec[q], rxd, pe64, C, pwd, P);
 #pragma unroll
     for (int sh = 16; sh > 0; sh >>= 1)
         I64 += __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(I64), sh), __shfl_xor_sync(0xffffffffu, __double2loint(I64), sh));
-    const D2DLinkD Lj = P.linkD[vj];
+    const D2DLinkD Lj = P.uniform ? (vj < C ? P.ud_cue : P.ud_due) : P.linkD[vj];
     const float sens = P.uniform ? (vj < C ? P.us_cue.x : P.us_due.x) : P.linkB[vj].sens_dBm;
     const double ex = txd.x - rxd.x, ey = txd.y - rxd.y;
-    const double Sg = P.pwr_lin_d[vpw] * Lj.a_lin * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, P.ple_d);
+    const double Sg = pwd[vpw] * Lj.a_lin * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, P.ple_d);
     const double r = Sg * d2d_rcp_f64(fma(I64, Lj.inv_noise, 1.0));
     const bool r1 = fabs(r - 1.0) < 0.0625, s1 = fabs(Sg - 1.0) < 0.0625;
     D2DDenseFix f = {0.f, 0.f, 0.f, 0.f, 0u};
@@ -127,13 +137,14 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
     float4 *bins = reinterpret_cast<float4 *>(d2d_dense_smem + L.bins);
     float4 *ovrec = reinterpret_cast<float4 *>(d2d_dense_smem + L.ovrec);
     float *pwr = reinterpret_cast<float *>(d2d_dense_smem + L.pwr);
+    double *pwd = reinterpret_cast<double *>(d2d_dense_smem + L.pwr_d);
     uint32_t *cnt = reinterpret_cast<uint32_t *>(d2d_dense_smem + L.cnt);
     float *red = reinterpret_cast<float *>(d2d_dense_smem + L.red);
     uint16_t *ovrb = reinterpret_cast<uint16_t *>(d2d_dense_smem + L.ovrb);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     d2d_pdl_launch_dependents();
 
-    for (uint32_t i = tid; i < D2D_MAX_PWR_LEVELS; i += BT) pwr[i] = P.pwr_lin[i];
+    for (uint32_t i = tid; i < D2D_MAX_PWR_LEVELS; i += BT) { pwr[i] = P.pwr_lin[i]; pwd[i] = P.pwr_lin_d[i]; }
     for (uint32_t i = tid; i < 3u * L.cnt_words; i += BT) cnt[i] = 0u;
     bool has[LPT], cue[LPT];
 #pragma unroll
@@ -339,7 +350,7 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
                     ++resc;
                     const uint32_t vj = (tid - lane) + (uint32_t)src + k * BT;
                     const D2DDenseFix f = d2d_dense_rescue<PLE2>(P, e, vj, __shfl_sync(0xffffffffu, rb[k], src), __shfl_sync(0xffffffffu, selfq[k], src),
-                                                                 __shfl_sync(0xffffffffu, pw[k], src), bp, cn, ovrec, ovrb, ovn, lane);
+                                                                 __shfl_sync(0xffffffffu, pw[k], src), bp, cn, ovrec, ovrb, pwd, ovn, lane);
                     if ((int)lane == src) {
                         const uint64_t gi = (uint64_t)e * N + vj;
                         if ((f.flags & 1u) && (FULL || P.obs)) P.obs[gi * 6u + 4u] = f.sinr_dB;
