@@ -227,7 +227,6 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
         float2 tx[LPT], rx[LPT];
 #pragma unroll
         for (int k = 0; k < LPT; ++k) { a[k] = an[k]; tx[k] = txn[k]; rx[k] = rxn[k]; }
-        if (e + 1u < e_end) load_inputs(e + 1u, an, txn, rxn);
         float pl[LPT];
         uint32_t rb[LPT], pw[LPT], selfq[LPT];
         bool live[LPT];
@@ -266,6 +265,9 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
             for (uint32_t i = tid; i <= R; i += BT) cprev[i] = 0u;
         }
         const uint32_t ovn = cn[R];                               // block-uniform: the env spilled into the overflow list
+        // the next env's inputs: in flight during this env's walk (issued here rather than before phase 1: the previous env's
+        // stores, which read the registers these loads reuse, have drained by now)
+        if (e + 1u < e_end) load_inputs(e + 1u, an, txn, rxn);
 
         // ---- phase 2: interference walk (simulator.py:95-101), epilogue, outputs --------------------------------------------------
         float cap_part = 0.0f;
