@@ -928,3 +928,25 @@ def test_dense_kernel_pipeline_crowded_rbs_and_absent_agents(monkeypatch, info, 
     st = env.stats()
     assert st['env_steps'] == 2 * E
     env.close()
+
+
+def test_dense_kernel_fp64_pass_on_a_crowded_rb():
+    """The dense kernel's warp-cooperative fp64 pass when the victim's RB holds more records than one per lane (and more than a bin:
+    the overflow list): one RB for 70 links, enough envs that some links land within the band around 0 dB; the pure 1e-4
+    relative check only passes if they were recomputed."""
+    kw = dict(num_rbs=1, num_cues=30, num_due_pairs=40)
+    cfg = O.OracleConfig(**kw)
+    E = 512
+    rng = np.random.default_rng(77)
+    env = make_vec(E, kw)
+    env.reset_stats()
+    near = 0
+    for s in range(2):
+        pos = O.random_positions(cfg, E, rng, fp32_exact=True)
+        act = O.random_actions(cfg, E, rng)
+        ref = O.step_batch(cfg, pos, act, nthreads=8)
+        out = run_step(env, pos, act)
+        check_against_oracle(out, ref)
+        near += int((np.minimum(np.abs(ref['sinr_db']), np.abs(ref['snr_db'])) < 0.05).sum())
+    assert near > 0 and env.stats()['rescues'] >= near
+    env.close()
