@@ -452,6 +452,11 @@ def run_cuda_arm(args) -> None:
                  'kernel': 'd2d_step_dense_kernel', 'grid': gD['grid'], 'block': gD['block'], 'smem_bytes': gD['smem_bytes'],
                  'roofline': {'bound': 'hbm', 'achieved': achD, 'peak': peak, 'unit': 'GB/s', 'frac': achD / peak,
                               'algorithmic_bytes_per_env_step': BD, 'traffic': None}}
+        if prof.exists():
+            try:
+                dense['roofline']['traffic'] = json.loads(prof.read_text()).get(f'dram_bytes_per_launch_dense_E{ED}')
+            except Exception:  # noqa: BLE001
+                pass
         envD.close()
         del envD, actsD, outsD
 
