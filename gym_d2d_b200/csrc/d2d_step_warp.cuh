@@ -71,7 +71,7 @@
 #define D2D_DUMMY_BYTES 528u
 #define D2D_BIN_STRIDE (D2D_BIN_CAP * 16u + 16u)
 #define D2D_BIN_CNT (D2D_BIN_CAP * 16u)
-__host__ __device__ inline uint32_t d2d_warp_smem_per_warp(int R) { return (uint32_t)R * D2D_BIN_STRIDE + D2D_DUMMY_BYTES; }
+__host__ __device__ inline uint32_t d2d_warp_smem_per_warp(int R) { return (uint32_t)R * D2D_BIN_STRIDE + D2D_DUMMY_BYTES + (((uint32_t)R * 8u + 15u) & ~15u); }
 __host__ __device__ inline uint32_t d2d_warp_smem_bytes(int R, int wpb) { return D2D_BLK_BYTES + (uint32_t)wpb * d2d_warp_smem_per_warp(R); }
 
 // Link / device / RB counts of the batch: immediates for the default EnvConfig, launch parameters otherwise.
@@ -445,6 +445,17 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
     const uint32_t zrec = bins + R * D2D_BIN_STRIDE + 512u;               // the warp's all-zero peer record
     const bool hasA = lane < C, hasB = lane < S.D();
 
+    const uint32_t num_envs = (uint32_t)P.num_envs, num_warps = gridDim.x * WPB;
+    const uint32_t per_warp = (num_envs + num_warps - 1u) / num_warps;
+    const uint32_t e0 = min((blockIdx.x * WPB + warp) * per_warp, num_envs), e_end = min(e0 + per_warp, num_envs);
+    uint32_t e = e0;
+    uint32_t iA = e * N + lane;                                    // slot-A link index of the env being computed
+    uint32_t qN = e * V + 1u + lane;                               // slot-A device index of the env being prefetched
+    // the first env's inputs go out before anything else: their latency overlaps the table loads of the prologue instead of
+    // following them (a warp of a one-wave batch steps a single env: two serial memory round trips were a tenth of its life)
+    D2DLaneIn nxt;
+    if (e < e_end) nxt = d2d_load_inputs<SPEC>(P, S, iA, qN, lane, hasA, hasB);
+
     // ---- prologue (constant tables only: nothing a previous kernel in the stream may have written) ------------------
     // block tables: 10^(p/10) for integer dBm, and the per-link constants by lane slot (zeros where there is no link)
     for (uint32_t i = threadIdx.x; i < D2D_MAX_PWR_LEVELS / 4u; i += WPB * 32u) {
@@ -460,14 +471,18 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         d2d_sts64f(blk + D2D_BLK_LINKS + (i << 3), b.x, b.y);
     }
     // this warp's bins: every counter starts at zero; each env re-zeroes them after use (the dummy words just run on)
-    for (uint32_t r = lane; r < R; r += 32u) d2d_sts64_if(true, bins + r * D2D_BIN_STRIDE + D2D_BIN_CNT, 0u, 0u);
+    // the RBs' (link count, SIDELINK flag) pairs: a compact array behind the bins, 8 bytes per RB, so that the 25 counters of the
+    // default shape spread over 16 bank pairs (in the bins' tails - 144-byte stride - they fell onto 8 banks: ATOMS took 6.5
+    // wavefronts instead of ~3)
+    const uint32_t cb = bins + R * D2D_BIN_STRIDE + D2D_DUMMY_BYTES;
+    for (uint32_t r = lane; r < R; r += 32u) d2d_sts64_if(true, cb + (r << 3), 0u, 0u);
     d2d_sts64_if(true, dumA, 0u, 0u);
     d2d_sts64_if(true, dumA + 256u, 0u, 0u);
     if (lane < 4u) d2d_sts32_if(true, zrec + (lane << 2), 0u);
     __syncthreads();
 
     const uint32_t lkA = blk + D2D_BLK_LINKA + (lane << 4), lkS = blk + D2D_BLK_LINKS + (lane << 3);
-    const uint32_t zero0 = bins + lane * D2D_BIN_STRIDE + D2D_BIN_CNT;       // this lane's share of the counter re-zeroing
+    const uint32_t zero0 = cb + (lane << 3);                                  // this lane's share of the counter re-zeroing
     // a valid action is 0 <= a < R n_pwr (envs/d2d_env.py:36-40); anything else marks the agent absent this step.
     // The sentinel action R n_pwr decodes to (rb = R, p = 0): a valid table index and an address inside the warp's slice.
     const uint32_t limA = R * S.npc(), limB = R * S.npd();
@@ -481,16 +496,9 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
     // registers - env i of a group of 32 lives in lane i - and read / written once per group as full sectors.  (One byte
     // per env read and written by 32 different warps per sector cost a quarter of the kernel's time in L2 read-modify-
     // write stalls: profiles/README.md.)
-    const uint32_t num_envs = (uint32_t)P.num_envs, num_warps = gridDim.x * WPB;
-    const uint32_t per_warp = (num_envs + num_warps - 1u) / num_warps;
-    const uint32_t e0 = min((blockIdx.x * WPB + warp) * per_warp, num_envs), e_end = min(e0 + per_warp, num_envs);
-    uint32_t e = e0;
-    uint32_t iA = e * N + lane;                                    // slot-A link index of the env being computed
-    uint32_t qN = e * V + 1u + lane;                               // slot-A device index of the env being prefetched
     uint32_t g = 0;                                                // position of env e in its group of 32
     int ns_keep = 0;                                               // lane i: step counter of the group's env i
     float rew_keep = 0.f;                                          // lane i: reward of the group's env i
-    D2DLaneIn nxt;
     // d2d_step_many state: step index inside the env, the link / env offsets of output slice t, the env's positions
     uint32_t t = 0, tN = 0, tE = 0;
     const uint32_t T = MANY ? (uint32_t)P.T : 1u, strideE = MANY ? (uint32_t)P.t_stride : 0u, strideN = strideE * N;
@@ -501,7 +509,6 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
     // does not release its dependents early), so this env-step's inputs are read and its whole chain computed right away;
     // griddepcontrol.wait comes only before the first access to memory a previous step wrote: the step counters and the
     // output buffers.  Back-to-back steps thus overlap one step's tail with the next step's loads and arithmetic.
-    if (e < e_end) nxt = d2d_load_inputs<SPEC>(P, S, iA, qN, lane, hasA, hasB);
     while (e < e_end) {
         // ---- one coalesced pass over the env's inputs, software-pipelined: the NEXT env's (or step's) loads are in
         // flight while this one computes, so a warp hides its own HBM latency -------------------------------------------
@@ -524,7 +531,7 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         const uint32_t rbA = S.rb_cue(asA), rbB = S.rb_due(asB);
         const uint32_t pA = asA - rbA * S.npc(), pB_ = asB - rbB * S.npd();
         const uint32_t binA = bins + rbA * D2D_BIN_STRIDE, binB = bins + rbB * D2D_BIN_STRIDE;
-        const uint32_t cntA = liveA ? binA + D2D_BIN_CNT : dumA, cntB = liveB ? binB + D2D_BIN_CNT : dumA + 256u;
+        const uint32_t cntA = liveA ? cb + (rbA << 3) : dumA, cntB = liveB ? cb + (rbB << 3) : dumA + 256u;
         const uint32_t rankA = d2d_atoms_inc_at<0>(cntA);
         const uint32_t rankB = d2d_atoms_inc_at<0>(cntB);
         d2d_sts32_if(liveB, cntB + 4u, 1u);                                     // a SIDELINK is on this RB (reward_fn.py:31-37)
@@ -584,7 +591,7 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         // every lane has read its counters (its capacity fed the reduction above): clear them for the next env
         __syncwarp();
         d2d_sts64_if(lane < R, zero0, 0u, 0u);
-        if (!SPEC && R > 32u) d2d_sts64_if(lane + 32u < R, zero0 + 32u * D2D_BIN_STRIDE, 0u, 0u);
+        if (!SPEC && R > 32u) d2d_sts64_if(lane + 32u < R, zero0 + 256u, 0u, 0u);
 
         if (e == e0 && t == 0u) d2d_pdl_wait();       // first output of this warp: every earlier kernel's memory is complete from here on
         if (g == 0u && t == 0u && (FULL || P.step_count)) ns_keep = e + lane < e_end ? (int)P.step_count[e + lane] : 0;   // consumed at the group's end
