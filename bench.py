@@ -379,6 +379,7 @@ def run_cuda_arm(args) -> None:
             dt = float(t.item())
         e2e = {'value': world * E * e2e_steps / dt, 'unit': UNIT, 'h2d_bytes_per_step': E * N * 4,
                'd2h_bytes_per_step': E * N * 24 + E * N * 4 + E * 4 + E, 'steps': e2e_steps,
+               'host_link_gbs_per_gpu': (E * N * 4 + E * N * 24 + E * N * 4 + E * 4 + E) * e2e_steps / dt / 1e9,   # copies in both directions: the PCIe link bounds this number
                'api': 'd2d_step_host_async/_wait via VecD2DEnv.step_host_async (pinned host buffers, two steps in flight; actions '
                       'copied in, obs + capacity + reward + done copied back, every step)'}
     # ---- fused rollouts: d2d_step_many, T steps of every env per launch -----------------------------------
