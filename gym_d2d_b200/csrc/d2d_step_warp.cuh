@@ -47,7 +47,10 @@
 #ifndef D2D_MINB4
 #define D2D_MINB4 7
 #endif
-#define D2D_WARP_MIN_BLOCKS(WPB) ((WPB) == 4 ? D2D_MINB4 : D2D_MINB8)
+#ifndef D2D_WPB_SMALL
+#define D2D_WPB_SMALL 4        // warps per block of the small-batch shape
+#endif
+#define D2D_WARP_MIN_BLOCKS(WPB) ((WPB) == D2D_WPB_SMALL ? D2D_MINB4 : D2D_MINB8)
 #ifndef D2D_STATS_REPLICAS
 #define D2D_STATS_REPLICAS 32
 #endif
@@ -573,6 +576,11 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
             IB = d2d_walk_rx<PLE2, EXACT>(binB, zrec, validB, pB.z, pB.w, P.neg_half_ple, dminB);
         }
 
+        // griddepcontrol.wait: from here on every earlier kernel's memory is complete.  It sits before the epilogue rather than at
+        // the first output store so that the step-counter load (state the previous step wrote) has the epilogue's arithmetic to
+        // hide behind - a warp of a one-wave batch steps one env and would otherwise wait out that load's full latency at its end.
+        if (e == e0 && t == 0u) d2d_pdl_wait();
+        if (g == 0u && t == 0u && (FULL || P.step_count)) ns_keep = e + lane < e_end ? (int)P.step_count[e + lane] : 0;   // consumed at the group's end
         // ---- per-link epilogue (simulator.py:93,106-107,110-127,144-154); dead lanes are zeroed ------------------------
         const float2 sA = SPEC ? P.us_cue : d2d_lds64(lkS), sB = SPEC ? P.us_due : d2d_lds64(lkS + 256u);   // (sensitivity, RB bandwidth in MHz)
         const float slope = PLE2 ? 3.0102999566398120f : P.snr_slope;
@@ -593,8 +601,6 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         d2d_sts64_if(lane < R, zero0, 0u, 0u);
         if (!SPEC && R > 32u) d2d_sts64_if(lane + 32u < R, zero0 + 256u, 0u, 0u);
 
-        if (e == e0 && t == 0u) d2d_pdl_wait();       // first output of this warp: every earlier kernel's memory is complete from here on
-        if (g == 0u && t == 0u && (FULL || P.step_count)) ns_keep = e + lane < e_end ? (int)P.step_count[e + lane] : 0;   // consumed at the group's end
         // ---- outputs: compact observation table (envs/obs_fn.py:55-61), capacity, optional info.  Rows of absent
         // agents carry their positions and zeros (the reference has no row for them). ---------------------------------
         // (one divergent branch per slot: cheaper than predicating every store, and the two merge when C == D)
