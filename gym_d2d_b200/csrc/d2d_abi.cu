@@ -327,6 +327,10 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
         pwr_d[p] = std::pow(10.0, p / 10.0);
         pwr[p] = (float)pwr_d[p];
     }
+    {   // the warp kernel's fp64 pass reads the fp64 table from the constant bank (per device: set at every create)
+        cudaError_t err__ = cudaMemcpyToSymbol(d2d_pwr_lin_c, pwr_d, sizeof(pwr_d));
+        if (err__ != cudaSuccess) return bail(fail(D2D_ERR_CUDA, std::string("cudaMemcpyToSymbol(d2d_pwr_lin_c): ") + cudaGetErrorString(err__)));
+    }
 
 #define D2D_CUDA_BAIL(call)                                                                              \
     do {                                                                                                 \
@@ -358,13 +362,13 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
     int rc;
     if (h->use_warp) {
         // launch shape by batch size (d2d_step_warp.cuh): about one wave of envs -> 4-warp blocks, many waves -> 8-warp blocks
-        h->wpb = cfg->num_envs >= 65536 ? 8 : D2D_WPB_SMALL;
-        if (const char *w = std::getenv("D2D_B200_WPB")) h->wpb = std::atoi(w) == 8 ? 8 : D2D_WPB_SMALL;
+        h->wpb = cfg->num_envs >= 65536 ? 8 : cfg->num_envs <= D2D_LATENCY_ENVS ? 2 : 4;
+        if (const char *w = std::getenv("D2D_B200_WPB")) { const int v = std::atoi(w); h->wpb = v == 8 ? 8 : v == 2 ? 2 : 4; }
         h->spec = h->ple2 && h->uniform && cfg->path_loss_model != D2D_PL_COST_HATA && cfg->num_rbs == 25 && cfg->num_cues == 25 && cfg->num_due_pairs == 25 && cfg->n_pwr_cue == 24 &&
                   cfg->n_pwr_due == 21;
         if (const char *sp = std::getenv("D2D_B200_SPEC")) h->spec = h->spec && std::atoi(sp) != 0;   // tests: force the generic shape
         const size_t smem = d2d_warp_smem_bytes(cfg->num_rbs, h->wpb);
-        rc = h->wpb == 8 ? plan_warp<8>(h, smem) : plan_warp<D2D_WPB_SMALL>(h, smem);
+        rc = h->wpb == 8 ? plan_warp<8>(h, smem) : h->wpb == 2 ? plan_warp<2>(h, smem) : plan_warp<4>(h, smem);
     } else {
         // <= 1024 links: the binned one-barrier kernel (d2d_step_dense.cuh), LPT links per thread; when its double-buffered
         // bins do not fit (many RBs) the sorting block kernel; beyond 1024 links / other topologies: everything staged in shared memory
@@ -526,6 +530,9 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, void *stream) {
             if (P.pwr_out) P.pwr_out += dl;
         }
         P.num_envs = n;
+#ifdef D2D_TIMELINE
+        P.tl_slot = (int32_t)(h->launches % D2D_TL_SLOTS);
+#endif
         const int grid = (int)std::min<int64_t>(h->grid, (n + h->envs_per_block - 1) / h->envs_per_block);
         const bool exact = h->pos64 != nullptr;
         cudaError_t err;
@@ -542,8 +549,10 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, void *stream) {
     (h->spec ? D2D_PICK_EXACT(true, WPB_, true) : h->ple2 ? D2D_PICK_EXACT(true, WPB_, false) : D2D_PICK_EXACT(false, WPB_, false))
         if (h->use_warp && h->wpb == 8) {
             err = D2D_PICK_SHAPE(8);
+        } else if (h->use_warp && h->wpb == 2) {
+            err = D2D_PICK_SHAPE(2);
         } else if (h->use_warp) {
-            err = D2D_PICK_SHAPE(D2D_WPB_SMALL);
+            err = D2D_PICK_SHAPE(4);
         } else {
 #define D2D_LAUNCH_BLOCK(LPT_) (h->ple2 ? launch_step(d2d_step_block_kernel<true, LPT_>, grid, h->block, h->smem, st, P, h->pdl) \
                                         : launch_step(d2d_step_block_kernel<false, LPT_>, grid, h->block, h->smem, st, P, h->pdl))
@@ -731,6 +740,15 @@ D2D_API int d2d_stats_reset(d2d_handle_t *h, void *stream) {
     return D2D_OK;
 }
 
+#ifdef D2D_TIMELINE
+// instrumented build only (profiles/timeline.py): copies the stamp table to the host
+D2D_API int d2d_debug_timeline(void *host_out, size_t bytes) {
+    if (bytes > sizeof(d2d_tl_buf)) bytes = sizeof(d2d_tl_buf);
+    D2D_CUDA(cudaDeviceSynchronize());
+    D2D_CUDA(cudaMemcpyFromSymbol(host_out, d2d_tl_buf, bytes));
+    return D2D_OK;
+}
+#endif
 D2D_API int64_t d2d_launch_count(const d2d_handle_t *h) { return h ? h->launches : -1; }
 
 D2D_API int d2d_step_geometry(const d2d_handle_t *h, int32_t *grid, int32_t *block, int32_t *smem_bytes, int32_t *envs_per_block) {

@@ -98,7 +98,22 @@ struct D2DParams {
     float *rate;                 // [E][N]
     int16_t *rb_out;             // [E][N]
     int16_t *pwr_out;            // [E][N]
+#ifdef D2D_TIMELINE
+    int32_t tl_slot;             // instrumented build (profiles/timeline.py): which d2d_tl_buf slot this launch stamps
+#endif
 };
+
+#ifdef D2D_TIMELINE
+// Instrumented build only: every warp of the warp kernel stamps (globaltimer at entry, clock64 at entry / before
+// griddepcontrol.wait / after it / at its end, SM id) so that profiles/timeline.py can lay consecutive launches side by side.
+#define D2D_TL_SLOTS 64
+#define D2D_TL_WARPS 4096
+struct D2DTlRec { unsigned long long g0, c0, c1, c2, c3, smid; };
+__device__ D2DTlRec d2d_tl_buf[D2D_TL_SLOTS][D2D_TL_WARPS];
+__device__ __forceinline__ unsigned long long d2d_tl_clock() { return (unsigned long long)clock64(); }
+__device__ __forceinline__ unsigned long long d2d_tl_gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned d2d_tl_smid() { unsigned s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); return s; }
+#endif
 
 __device__ __forceinline__ float d2d_lg2(float x) {
     float y;

@@ -39,7 +39,9 @@
 #include "d2d_common.cuh"
 
 // Launch shapes, picked by the host from the batch size (measured on B200, profiles/README.md):
-//   WPB = 4: finest block granularity - best when the batch is about one wave (E = 4096)
+//   WPB = 2: latency shape - a batch of well under one wave (E <= D2D_LATENCY_ENVS); the rare fp64 pass runs BEFORE
+//            griddepcontrol.wait (see d2d_rescue_warp), so nothing but stores follows the wait
+//   WPB = 4: finest block granularity at full occupancy - best when the batch is about one wave (E = 4096)
 //   WPB = 8: best sustained throughput for batches of many waves
 #ifndef D2D_MINB8
 #define D2D_MINB8 3
@@ -47,10 +49,13 @@
 #ifndef D2D_MINB4
 #define D2D_MINB4 7
 #endif
-#ifndef D2D_WPB_SMALL
-#define D2D_WPB_SMALL 4        // warps per block of the small-batch shape
+#ifndef D2D_MINB2
+#define D2D_MINB2 14
 #endif
-#define D2D_WARP_MIN_BLOCKS(WPB) ((WPB) == D2D_WPB_SMALL ? D2D_MINB4 : D2D_MINB8)
+#ifndef D2D_LATENCY_ENVS
+#define D2D_LATENCY_ENVS 2048
+#endif
+#define D2D_WARP_MIN_BLOCKS(WPB) ((WPB) == 2 ? D2D_MINB2 : (WPB) == 4 ? D2D_MINB4 : D2D_MINB8)
 #ifndef D2D_STATS_REPLICAS
 #define D2D_STATS_REPLICAS 32
 #endif
@@ -354,16 +359,42 @@ __device__ __forceinline__ double d2d_shfl_xor_f64(double v, int m) {
 // fp64 recomputation of the links flagged by needA / needB (see d2d_common.cuh for why and when).  Per flagged link the
 // whole warp cooperates: every lane evaluates its own two links' interference terms at the victim's receiver in fp64
 // (positions are exact in fp64: they ARE the fp32 state, or the bound fp64 shadow), a butterfly sums them, and the
-// victim's own lane recomputes and overwrites that link's outputs.  Everything is re-read from global memory (this path
-// runs for ~7 % of the envs and must not hold registers of the hot loop).
+// victim's own lane recomputes that link's outputs.  Two placements (d2d_step_warp_kernel picks by launch shape):
+//   STORE = false: the new values replace the lane's registers (oA / oB) BEFORE the env's outputs are stored.  The pass touches
+//                  only inputs (positions, actions, constant tables), so it runs ahead of griddepcontrol.wait like the rest of the
+//                  env's arithmetic - after the wait it sat on the critical path of every back-to-back launch of a one-wave batch
+//                  (profiles/timeline.py: the ~7 % of warps with a flagged link ended 2 us after the others and held the block
+//                  slots of the next launch).  Costs the hot loop a few spilled registers.
+//   STORE = true:  the pass runs after the env's stores and overwrites the link's outputs in global memory - no live output
+//                  registers across it; the throughput shape (many envs per warp, one wait per warp).
+// Nothing of the hot loop's shared-memory state is used: only the lane's own inputs.
 // Without a position shadow a dB value is rewritten only when its linear ratio is within 1/16 of one - the only place the
 // fp32 value is ill-conditioned; rate and capacity are well conditioned there and are rewritten only if the sensitivity
 // gate (simulator.py:123,149) could sit inside that band.  With a shadow every output of the link is rewritten.
 // Returns the number of links recomputed.
-template <bool PLE2, bool EXACT, bool SPEC>
+// 10^(p/10) in fp64 for the warp kernel's fp64 pass: the constant bank instead of a global table (filled by d2d_create)
+__constant__ double d2d_pwr_lin_c[D2D_MAX_PWR_LEVELS];
+
+template <bool PLE2, bool EXACT, bool SPEC, bool STORE>
 __device__ __forceinline__ int d2d_rescue_warp(const D2DParams &P, const D2DShape<SPEC> &S, uint32_t e, uint32_t lane, uint32_t jA,
-                                               uint32_t keyA, uint32_t keyB, bool needA, bool needB, uint32_t pA, uint32_t pB_) {
+                                               uint32_t keyA, uint32_t keyB, bool needA, bool needB, uint32_t pA, uint32_t pB_,
+                                               const float2 &tA, const float4 &pB, D2DLinkOut &oA, D2DLinkOut &oB) {
     const uint32_t C = S.C(), V = S.V();
+    // Without an fp64 shadow the positions ARE the fp32 state the lane already holds; with uniform link constants (one set per
+    // link type: every default-shape batch) those come from the constant bank, like the power table: then the pass reads
+    // no global memory at all - its dependent round trips were most of its ~2 us per link (profiles/timeline.py).
+    const bool uni = SPEC || P.uniform != 0;
+    // this lane's two transmitters and the DUE receiver, in fp64
+    double2 txA = make_double2((double)tA.x, (double)tA.y), txB = make_double2((double)pB.x, (double)pB.y);
+    double2 rxB = make_double2((double)pB.z, (double)pB.w);
+    if (EXACT) {
+        const double2 *pe64 = reinterpret_cast<const double2 *>(P.pos64) + (int64_t)e * V;
+        if (lane < C) txA = pe64[1u + lane];
+        if (lane < S.D()) { txB = pe64[1u + C + 2u * lane]; rxB = pe64[2u + C + 2u * lane]; }
+    }
+    // radiated weights w = 10^(p/10) 10^((eo - K)/10) in fp64
+    const double wA = d2d_pwr_lin_c[pA & (D2D_MAX_PWR_LEVELS - 1)] * (uni ? P.ud_cue.t_lin : lane < C ? P.linkD[lane].t_lin : 0.0);
+    const double wB = d2d_pwr_lin_c[pB_ & (D2D_MAX_PWR_LEVELS - 1)] * (uni ? P.ud_due.t_lin : lane < S.D() ? P.linkD[C + lane].t_lin : 0.0);
     int done = 0;
 #pragma unroll 1
     for (int s = 0; s < 2; ++s) {
@@ -371,56 +402,49 @@ __device__ __forceinline__ int d2d_rescue_warp(const D2DParams &P, const D2DShap
         while (todo) {
             const int L = (int)d2d_pop_bit(todo);
             const uint32_t key = __shfl_sync(0xffffffffu, s ? keyB : keyA, L);
-            // this lane's two transmitters and the DUE receiver, in fp64
-            double2 txA = make_double2(1.0, 0.0), txB = make_double2(1.0, 0.0), rxB = make_double2(0.0, 0.0);
-            if (EXACT) {
-                const double2 *pe64 = reinterpret_cast<const double2 *>(P.pos64) + (int64_t)e * V;
-                if (lane < C) txA = pe64[1u + lane];
-                if (lane < S.D()) { txB = pe64[1u + C + 2u * lane]; rxB = pe64[2u + C + 2u * lane]; }
-            } else {
-                const float2 *pe = reinterpret_cast<const float2 *>(P.pos) + e * V;
-                if (lane < C) { const float2 t = pe[1u + lane]; txA = make_double2((double)t.x, (double)t.y); }
-                if (lane < S.D()) {
-                    const float2 t = pe[1u + C + 2u * lane], r = pe[2u + C + 2u * lane];
-                    txB = make_double2((double)t.x, (double)t.y); rxB = make_double2((double)r.x, (double)r.y);
-                }
-            }
             const double rxx = s ? d2d_shfl_f64(rxB.x, L) : 0.0, rxy = s ? d2d_shfl_f64(rxB.y, L) : 0.0;   // MBS at the origin
             double I = 0.0;
             if (keyA == key && !(s == 0 && (int)lane == L)) {
-                // radiated weight w = 10^(p/10) 10^((eo - K)/10) in fp64 (tables are tiny and cache-resident)
-                const double w = P.pwr_lin_d[pA & (D2D_MAX_PWR_LEVELS - 1)] * P.linkD[lane].t_lin;
                 const double ex = txA.x - rxx, ey = txA.y - rxy;
-                I += w * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, P.ple_d);
+                I += wA * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, P.ple_d);
             }
             if (keyB == key && !(s == 1 && (int)lane == L)) {
-                const double w = P.pwr_lin_d[pB_ & (D2D_MAX_PWR_LEVELS - 1)] * P.linkD[C + lane].t_lin;
                 const double ex = txB.x - rxx, ey = txB.y - rxy;
-                I += w * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, P.ple_d);
+                I += wB * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, P.ple_d);
             }
 #pragma unroll
             for (int sh = 16; sh > 0; sh >>= 1) I += d2d_shfl_xor_f64(I, sh);
             if ((int)lane == L) {
-                const uint32_t j = s ? C + lane : lane, row = s ? jA + C : jA;
-                const D2DLinkD Lj = P.linkD[j];
+                const uint32_t j = s ? C + lane : lane;
+                D2DLinkD Lj = s ? P.ud_due : P.ud_cue;
+                float sens = s ? P.us_due.x : P.us_cue.x;
+                if (!uni) { Lj = P.linkD[j]; sens = P.linkB[j].sens_dBm; }
                 const double2 tx = s ? txB : txA;
                 const double dx = tx.x - rxx, dy = tx.y - rxy;
-                const double Sg = P.pwr_lin_d[(s ? pB_ : pA) & (D2D_MAX_PWR_LEVELS - 1)] * Lj.a_lin * d2d_gain_f64_fast<PLE2>(dx * dx + dy * dy, P.ple_d);
+                const double Sg = d2d_pwr_lin_c[(s ? pB_ : pA) & (D2D_MAX_PWR_LEVELS - 1)] * Lj.a_lin * d2d_gain_f64_fast<PLE2>(dx * dx + dy * dy, P.ple_d);
                 const double r = Sg * d2d_rcp_f64(fma(I, Lj.inv_noise, 1.0));          // a_lin already carries 1 / noise
                 const bool r1 = fabs(r - 1.0) < 0.0625, s1 = fabs(Sg - 1.0) < 0.0625;
-                const float sens = P.linkB[j].sens_dBm;
+                const uint32_t row = s ? jA + C : jA;
+                D2DLinkOut o;
+                if (!STORE) o = s ? oB : oA;
                 double sinr = 0.0;
                 if (EXACT || r1) {
                     sinr = r1 ? d2d_db_near1(r) : 4.3429448190325182765 * d2d_ln_f64(r);
-                    if (P.obs) P.obs[(uint64_t)row * 6u + 4u] = (float)sinr;
+                    o.sinr_dB = (float)sinr;
+                    if (STORE && P.obs) P.obs[(uint64_t)row * 6u + 4u] = o.sinr_dB;
                 }
-                if ((EXACT || s1) && P.obs)
-                    P.obs[(uint64_t)row * 6u + 5u] = (float)(s1 ? d2d_db_near1(Sg) : 4.3429448190325182765 * d2d_ln_f64(Sg));
+                if (EXACT || s1) {
+                    o.snr_dB = (float)(s1 ? d2d_db_near1(Sg) : 4.3429448190325182765 * d2d_ln_f64(Sg));
+                    if (STORE && P.obs) P.obs[(uint64_t)row * 6u + 5u] = o.snr_dB;
+                }
                 if (EXACT || (r1 && fabsf(sens) < 0.5f)) {
                     const double rate = sinr > (double)sens ? 1.4426950408889634074 * d2d_ln_f64(1.0 + r) : 0.0;
-                    if (P.cap) P.cap[row] = (float)(Lj.bw_MHz * rate);
-                    if (P.rate) P.rate[row] = (float)rate;
+                    o.cap = (float)(Lj.bw_MHz * rate);
+                    o.rate = (float)rate;
+                    if (STORE && P.cap) P.cap[row] = o.cap;
+                    if (STORE && P.rate) P.rate[row] = o.rate;
                 }
+                if (!STORE) { if (s) oB = o; else oA = o; }
                 ++done;
             }
         }
@@ -438,8 +462,14 @@ __global__ void __launch_bounds__(WPB * 32, D2D_WARP_MIN_BLOCKS(WPB))
 d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
     extern __shared__ __align__(16) unsigned char d2d_warp_smem[];
     const D2DShape<SPEC> S(P);
+    // latency shape: the fp64 pass runs before griddepcontrol.wait
+    constexpr bool RESCUE_EARLY = WPB == 2;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t C = S.C(), N = S.N(), V = S.V(), R = S.R();
+#ifdef D2D_TIMELINE
+    const unsigned long long tl_g0 = d2d_tl_gtime(), tl_c0 = d2d_tl_clock();
+    unsigned long long tl_c1 = 0, tl_c2 = 0;
+#endif
     d2d_pdl_launch_dependents();
     uint32_t blk = (uint32_t)__cvta_generic_to_shared(d2d_warp_smem);
     asm volatile("mov.u32 %0, %0;" : "+r"(blk));      // opaque: keep the base in a register instead of re-deriving it
@@ -576,23 +606,18 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
             IB = d2d_walk_rx<PLE2, EXACT>(binB, zrec, validB, pB.z, pB.w, P.neg_half_ple, dminB);
         }
 
-        // griddepcontrol.wait: from here on every earlier kernel's memory is complete.  It sits before the epilogue rather than at
-        // the first output store so that the step-counter load (state the previous step wrote) has the epilogue's arithmetic to
-        // hide behind - a warp of a one-wave batch steps one env and would otherwise wait out that load's full latency at its end.
-        if (e == e0 && t == 0u) d2d_pdl_wait();
-        if (g == 0u && t == 0u && (FULL || P.step_count)) ns_keep = e + lane < e_end ? (int)P.step_count[e + lane] : 0;   // consumed at the group's end
         // ---- per-link epilogue (simulator.py:93,106-107,110-127,144-154); dead lanes are zeroed ------------------------
         const float2 sA = SPEC ? P.us_cue : d2d_lds64(lkS), sB = SPEC ? P.us_due : d2d_lds64(lkS + 256u);   // (sensitivity, RB bandwidth in MHz)
         const float slope = PLE2 ? 3.0102999566398120f : P.snr_slope;
-        const D2DLinkOut oA = d2d_link_epilogue_warp(liveA, (int)pA, plA, lgA, gA, IA, cA, sA, slope);
-        const D2DLinkOut oB = d2d_link_epilogue_warp(liveB, (int)pB_, plB, lgB, gB, IB, cB, sB, slope);
-        const bool needA = liveA && d2d_needs_rescue<EXACT>(oA, fminf(dminA, d2A), P);
-        const bool needB = liveB && d2d_needs_rescue<EXACT>(oB, fminf(dminB, d2B), P);
+        const D2DLinkOut oA32 = d2d_link_epilogue_warp(liveA, (int)pA, plA, lgA, gA, IA, cA, sA, slope);
+        const D2DLinkOut oB32 = d2d_link_epilogue_warp(liveB, (int)pB_, plB, lgB, gB, IB, cB, sB, slope);
+        const bool needA = liveA && d2d_needs_rescue<EXACT>(oA32, fminf(dminA, d2A), P);
+        const bool needB = liveB && d2d_needs_rescue<EXACT>(oB32, fminf(dminB, d2B), P);
 
         // ---- envs/reward_fn.py:27-44 -----------------------------------------------------------------------------------
-        const bool bad = __any_sync(0xffffffffu, liveA && ctA.y != 0u && oA.cap <= P.min_cap);
+        const bool bad = __any_sync(0xffffffffu, liveA && ctA.y != 0u && oA32.cap <= P.min_cap);
         const uint32_t n_act = d2d_redux_add((liveA ? 1u : 0u) + (liveB ? 1u : 0u));
-        float cap_sum = oA.cap + oB.cap;
+        float cap_sum = oA32.cap + oB32.cap;
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) cap_sum += __shfl_xor_sync(0xffffffffu, cap_sum, s);
         const float reward = bad ? -1.0f : cap_sum * d2d_rcp((float)n_act);
@@ -601,6 +626,23 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         d2d_sts64_if(lane < R, zero0, 0u, 0u);
         if (!SPEC && R > 32u) d2d_sts64_if(lane + 32u < R, zero0 + 256u, 0u, 0u);
 
+        // ---- rare: fp64 recomputation of flagged links (latency shape: here, replacing the link's values in oA / oB; the
+        // reward and the statistics keep the fp32 capacities either way) -------------------------------------------------
+        D2DLinkOut oA = oA32, oB = oB32;
+        if (D2D_RESCUE_ENABLED && RESCUE_EARLY && __any_sync(0xffffffffu, needA || needB)) {
+            const uint32_t keyA = liveA ? rbA : (D2D_INACTIVE_KEY | lane), keyB = liveB ? rbB : (D2D_INACTIVE_KEY | 32u | lane);
+            st_resc += (uint32_t)d2d_rescue_warp<PLE2, EXACT, SPEC, false>(P, S, e, lane, jA, keyA, keyB, needA, needB, pA, pB_, tA, pB, oA, oB);
+        }
+
+        // griddepcontrol.wait: everything above read only inputs (no step kernel writes actions or positions); from here on every
+        // earlier kernel's memory is complete.  What is left after it is the step-counter load, the stores and the exit - the part
+        // of a launch that cannot overlap its predecessor (profiles/timeline.py).
+#ifdef D2D_TIMELINE
+        if (e == e0 && t == 0u) { tl_c1 = d2d_tl_clock(); d2d_pdl_wait(); tl_c2 = d2d_tl_clock(); }
+#else
+        if (e == e0 && t == 0u) d2d_pdl_wait();
+#endif
+        if (g == 0u && t == 0u && (FULL || P.step_count)) ns_keep = e + lane < e_end ? (int)P.step_count[e + lane] : 0;   // consumed at the group's end
         // ---- outputs: compact observation table (envs/obs_fn.py:55-61), capacity, optional info.  Rows of absent
         // agents carry their positions and zeros (the reference has no row for them). ---------------------------------
         // (one divergent branch per slot: cheaper than predicating every store, and the two merge when C == D)
@@ -654,10 +696,10 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         st_cap += cap_sum;
         st_pen += bad ? 1u : 0u;
 
-        // ---- rare: fp64 recomputation of flagged links, after the env's outputs are stored ----------------------------------
-        if (D2D_RESCUE_ENABLED && __any_sync(0xffffffffu, needA || needB)) {
+        // ---- throughput shape: the rare fp64 pass after the env's outputs are stored (it overwrites them) -------------------
+        if (D2D_RESCUE_ENABLED && !RESCUE_EARLY && __any_sync(0xffffffffu, needA || needB)) {
             const uint32_t keyA = liveA ? rbA : (D2D_INACTIVE_KEY | lane), keyB = liveB ? rbB : (D2D_INACTIVE_KEY | 32u | lane);
-            st_resc += (uint32_t)d2d_rescue_warp<PLE2, EXACT, SPEC>(P, S, e, lane, jA, keyA, keyB, needA, needB, pA, pB_);
+            st_resc += (uint32_t)d2d_rescue_warp<PLE2, EXACT, SPEC, true>(P, S, e, lane, jA, keyA, keyB, needA, needB, pA, pB_, tA, pB, oA, oB);
         }
         if (last_t) {
             g = (g + 1u) & 31u;
@@ -670,6 +712,12 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         __syncwarp();     // every lane is done with this env's records and counters before the next env's are written
     }
 
+#ifdef D2D_TIMELINE
+    if (lane == 0u && blockIdx.x * WPB + warp < D2D_TL_WARPS) {
+        D2DTlRec r; r.g0 = tl_g0; r.c0 = tl_c0; r.c1 = tl_c1; r.c2 = tl_c2; r.c3 = d2d_tl_clock(); r.smid = d2d_tl_smid();
+        d2d_tl_buf[P.tl_slot & (D2D_TL_SLOTS - 1)][blockIdx.x * WPB + warp] = r;
+    }
+#endif
     if (P.stats && lane < 6) {
         // one fire-and-forget fp64 reduction per statistic and warp, spread over the replicas
         const double v = lane == 0 ? (double)st_reward : lane == 1 ? (double)st_cap : lane == 2 ? (double)st_reward2

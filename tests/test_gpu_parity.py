@@ -491,7 +491,7 @@ def test_pipelined_host_steps_equal_synchronous_ones():
     sync_env.close(); pipe_env.close()
 
 
-@pytest.mark.parametrize('E', [100, 70000])      # both launch shapes of the warp kernel (4- and 8-warp blocks)
+@pytest.mark.parametrize('E', [100, 4096, 70000])      # the three launch shapes of the warp kernel (2-, 4- and 8-warp blocks)
 def test_core_output_fast_path_equals_general_path(E):
     """VecD2DEnv(info=False) passes exactly the core outputs and takes the kernel instantiation that tests no output
     pointer; it must produce bit-identical obs / capacity / reward / done to the general instantiation."""
@@ -514,6 +514,51 @@ def test_core_output_fast_path_equals_general_path(E):
     assert_rel(fast.capacity_mbps.cpu().numpy(), ref['capacity_mbps'], RTOL, 'capacity')
     assert_rel(fast.reward.cpu().numpy(), ref['reward'], RTOL, 'reward')
     fast.close(); gen.close()
+
+
+@pytest.mark.parametrize('exact', [False, True])
+def test_warp_launch_shapes_bit_identical(monkeypatch, exact):
+    """The warp kernel's three launch shapes (2-, 4-, 8-warp blocks; D2D_B200_WPB forces one) differ in where the fp64 pass
+    runs - before griddepcontrol.wait with its results kept in registers (2-warp latency shape), or after the env's stores,
+    overwriting them - and must produce bit-identical outputs, counters and statistics, each within tolerance of the oracle.
+    Crowded RBs (all agents on 3 RBs in a third of the envs) take the all-pairs path and several fp64 links per env."""
+    import gym_d2d_b200 as G
+    _need_gpu()
+    cfg = O.OracleConfig()
+    E = 1500
+    rng = np.random.default_rng(77)
+    pos = O.random_positions(cfg, E, rng, fp32_exact=not exact)
+    act = O.random_actions(cfg, E, rng)
+    act[::3, :cfg.num_cues] = (act[::3, :cfg.num_cues] % (3 * 24))        # CUE action = rb * 24 + p
+    act[::3, cfg.num_cues:] = (act[::3, cfg.num_cues:] % (3 * 21))        # DUE action = rb * 21 + p
+    act[::7, ::4] = -1
+    a = torch.as_tensor(act, device='cuda')
+    got = {}
+    for wpb in (2, 4, 8):
+        monkeypatch.setenv('D2D_B200_WPB', str(wpb))
+        env = G.VecD2DEnv(E, {}, info=True, exact_positions=exact)
+        assert env.step_geometry()['block'] == 32 * wpb
+        env.set_positions(pos)
+        for _ in range(3):                          # back-to-back launches: the programmatic-dependent-launch path
+            env.step(a)
+        torch.cuda.synchronize()
+        st = env.stats()
+        assert st['rescues'] > 0
+        got[wpb] = dict(obs=env.obs.clone(), cap=env.capacity_mbps.clone(), reward=env.reward.clone(), done=env.done.clone(),
+                        rate=env.rate_bps.clone(), count=env.step_count.clone(), rescues=st['rescues'], cap_sum=st['sum_capacity_mbps'])
+        env.close()
+    monkeypatch.delenv('D2D_B200_WPB')
+    for wpb in (4, 8):
+        for k in ('obs', 'cap', 'reward', 'done', 'rate', 'count'):
+            assert torch.equal(got[2][k], got[wpb][k]), (wpb, k)
+        assert got[2]['rescues'] == got[wpb]['rescues']
+    assert (got[2]['count'] == 3).all()
+    ref = O.step_batch(cfg, pos, act, active=(act >= 0).astype(np.uint8), nthreads=4)
+    assert_rel(got[2]['obs'][..., 4].cpu().numpy(), ref['sinr_db'], RTOL, 'sinr_db')
+    assert_rel(got[2]['obs'][..., 5].cpu().numpy(), ref['snr_db'], RTOL, 'snr_db')
+    assert_rel(got[2]['cap'].cpu().numpy(), ref['capacity_mbps'], RTOL, 'capacity')
+    assert_rel(got[2]['rate'].cpu().numpy(), ref['rate_bps'], RTOL, 'rate')
+    assert_rel(got[2]['reward'].cpu().numpy(), ref['reward'], RTOL, 'reward')
 
 
 def test_step_is_graph_capturable_and_deterministic():
