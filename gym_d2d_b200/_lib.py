@@ -10,8 +10,8 @@ from pathlib import Path
 
 from .build import LIB
 
-ABI_VERSION = 3
-STATS_REPLICAS = 32
+ABI_VERSION = 4
+STATS_REPLICAS = 1024
 NUM_STATS = 8
 STAT_NAMES = ('sum_reward', 'sum_capacity_mbps', 'sum_reward_sq', 'env_steps', 'penalties', 'rescues')
 

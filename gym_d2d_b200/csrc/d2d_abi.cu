@@ -21,7 +21,7 @@
 #define D2D_DENSE_PLAN_CASE(LPT_, BT_) if (h->lpt == LPT_ && h->dense_bt == BT_) rc = D2D_PLAN_DENSE(LPT_, BT_);
 #define D2D_DENSE_LAUNCH_CASE(LPT_, BT_) if (h->lpt == LPT_ && h->dense_bt == BT_) err = D2D_LAUNCH_DENSE(LPT_, BT_);
 
-static_assert(D2D_STATS_REPLICAS * 8 * sizeof(double) == 2048, "stats layout");
+static_assert(D2D_STATS_REPLICAS * 8 * sizeof(double) == 65536, "stats layout");
 
 namespace {
 
@@ -362,13 +362,13 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
     int rc;
     if (h->use_warp) {
         // launch shape by batch size (d2d_step_warp.cuh): about one wave of envs -> 4-warp blocks, many waves -> 8-warp blocks
-        h->wpb = cfg->num_envs >= 65536 ? 8 : cfg->num_envs <= D2D_LATENCY_ENVS ? 2 : 4;
-        if (const char *w = std::getenv("D2D_B200_WPB")) { const int v = std::atoi(w); h->wpb = v == 8 ? 8 : v == 2 ? 2 : 4; }
+        h->wpb = cfg->num_envs >= 65536 ? 8 : cfg->num_envs <= D2D_LATENCY_ENVS ? 2 : D2D_WPB_MID;
+        if (const char *w = std::getenv("D2D_B200_WPB")) { const int v = std::atoi(w); h->wpb = v == 8 ? 8 : v == 2 ? 2 : D2D_WPB_MID; }
         h->spec = h->ple2 && h->uniform && cfg->path_loss_model != D2D_PL_COST_HATA && cfg->num_rbs == 25 && cfg->num_cues == 25 && cfg->num_due_pairs == 25 && cfg->n_pwr_cue == 24 &&
                   cfg->n_pwr_due == 21;
         if (const char *sp = std::getenv("D2D_B200_SPEC")) h->spec = h->spec && std::atoi(sp) != 0;   // tests: force the generic shape
         const size_t smem = d2d_warp_smem_bytes(cfg->num_rbs, h->wpb);
-        rc = h->wpb == 8 ? plan_warp<8>(h, smem) : h->wpb == 2 ? plan_warp<2>(h, smem) : plan_warp<4>(h, smem);
+        rc = h->wpb == 8 ? plan_warp<8>(h, smem) : h->wpb == 2 ? plan_warp<2>(h, smem) : plan_warp<D2D_WPB_MID>(h, smem);
     } else {
         // <= 1024 links: the binned one-barrier kernel (d2d_step_dense.cuh), LPT links per thread; when its double-buffered
         // bins do not fit (many RBs) the sorting block kernel; beyond 1024 links / other topologies: everything staged in shared memory
@@ -552,7 +552,7 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, void *stream) {
         } else if (h->use_warp && h->wpb == 2) {
             err = D2D_PICK_SHAPE(2);
         } else if (h->use_warp) {
-            err = D2D_PICK_SHAPE(4);
+            err = D2D_PICK_SHAPE(D2D_WPB_MID);
         } else {
 #define D2D_LAUNCH_BLOCK(LPT_) (h->ple2 ? launch_step(d2d_step_block_kernel<true, LPT_>, grid, h->block, h->smem, st, P, h->pdl) \
                                         : launch_step(d2d_step_block_kernel<false, LPT_>, grid, h->block, h->smem, st, P, h->pdl))

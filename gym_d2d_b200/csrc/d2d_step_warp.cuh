@@ -55,9 +55,12 @@
 #ifndef D2D_LATENCY_ENVS
 #define D2D_LATENCY_ENVS 2048
 #endif
-#define D2D_WARP_MIN_BLOCKS(WPB) ((WPB) == 2 ? D2D_MINB2 : (WPB) == 4 ? D2D_MINB4 : D2D_MINB8)
+#ifndef D2D_WPB_MID
+#define D2D_WPB_MID 4          // warps per block of the one-wave shape (build knob of the A/B harness)
+#endif
+#define D2D_WARP_MIN_BLOCKS(WPB) ((WPB) == 2 ? D2D_MINB2 : (WPB) == D2D_WPB_MID ? D2D_MINB4 : D2D_MINB8)
 #ifndef D2D_STATS_REPLICAS
-#define D2D_STATS_REPLICAS 32
+#define D2D_STATS_REPLICAS 1024
 #endif
 #ifndef D2D_BIN_CAP
 #define D2D_BIN_CAP 8          // peer records per RB bin on the fast path
@@ -634,6 +637,22 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
             st_resc += (uint32_t)d2d_rescue_warp<PLE2, EXACT, SPEC, false>(P, S, e, lane, jA, keyA, keyB, needA, needB, pA, pB_, tA, pB, oA, oB);
         }
 
+        // ---- per-warp statistics; flushed with the warp's LAST env, ahead of the wait and of that env's stores: the reductions
+        // commute with every other launch's, and a warp (hence its block's slot) is not retired before its outstanding atomics
+        // are acknowledged - issued at the very end they cost 0.3 us per launch of a one-wave batch (profiles/README.md) --------
+        if (P.reward_fn == 0) { st_reward += reward; st_reward2 = fmaf(reward, reward, st_reward2); }
+        st_cap += cap_sum;
+        st_pen += bad ? 1u : 0u;
+        if (P.stats && last_t && e + 1u == e_end && lane < (RESCUE_EARLY ? 6u : 5u)) {
+            // one fire-and-forget fp64 reduction per statistic and warp, spread over the replicas
+            const double v = lane == 0 ? (double)st_reward : lane == 1 ? (double)st_cap : lane == 2 ? (double)st_reward2
+                           : lane == 3 ? (double)((e_end - e0) * T)            // env-steps this warp made
+                           : lane == 4 ? (double)st_pen : (double)st_resc;
+#ifndef D2D_EXPERIMENT_NOSTATS      // A/B only: what the statistics flush costs
+            if (v != 0.0) atomicAdd(P.stats + ((blockIdx.x * WPB + warp) % D2D_STATS_REPLICAS) * 8 + lane, v);
+#endif
+        }
+
         // griddepcontrol.wait: everything above read only inputs (no step kernel writes actions or positions); from here on every
         // earlier kernel's memory is complete.  What is left after it is the step-counter load, the stores and the exit - the part
         // of a launch that cannot overlap its predecessor (profiles/timeline.py).
@@ -642,7 +661,11 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
 #else
         if (e == e0 && t == 0u) d2d_pdl_wait();
 #endif
+#ifdef D2D_EXPERIMENT_NOCOUNT     // A/B only: how much of the post-wait tail is the step-counter load
+        ns_keep = 0;
+#else
         if (g == 0u && t == 0u && (FULL || P.step_count)) ns_keep = e + lane < e_end ? (int)P.step_count[e + lane] : 0;   // consumed at the group's end
+#endif
         // ---- outputs: compact observation table (envs/obs_fn.py:55-61), capacity, optional info.  Rows of absent
         // agents carry their positions and zeros (the reference has no row for them). ---------------------------------
         // (one divergent branch per slot: cheaper than predicating every store, and the two merge when C == D)
@@ -692,9 +715,6 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
                 if (!MANY && (FULL || P.done)) P.done[eg] = ns >= P.episode_length ? 1 : 0;
             }
         }
-        if (P.reward_fn == 0) { st_reward += reward; st_reward2 = fmaf(reward, reward, st_reward2); }
-        st_cap += cap_sum;
-        st_pen += bad ? 1u : 0u;
 
         // ---- throughput shape: the rare fp64 pass after the env's outputs are stored (it overwrites them) -------------------
         if (D2D_RESCUE_ENABLED && !RESCUE_EARLY && __any_sync(0xffffffffu, needA || needB)) {
@@ -718,12 +738,7 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         d2d_tl_buf[P.tl_slot & (D2D_TL_SLOTS - 1)][blockIdx.x * WPB + warp] = r;
     }
 #endif
-    if (P.stats && lane < 6) {
-        // one fire-and-forget fp64 reduction per statistic and warp, spread over the replicas
-        const double v = lane == 0 ? (double)st_reward : lane == 1 ? (double)st_cap : lane == 2 ? (double)st_reward2
-                       : lane == 3 ? (double)((e_end - e0) * T)            // env-steps this warp made
-                       : lane == 4 ? (double)st_pen : (double)st_resc;
-        const unsigned w_global = blockIdx.x * WPB + warp;
-        if (v != 0.0) atomicAdd(P.stats + (w_global % D2D_STATS_REPLICAS) * 8 + lane, v);
-    }
+    // the throughput shapes run the fp64 pass after the env's stores: its counter follows here (rarely non-zero for a one-env warp)
+    if (!RESCUE_EARLY && P.stats && lane == 5u && st_resc != 0u)
+        atomicAdd(P.stats + ((blockIdx.x * WPB + warp) % D2D_STATS_REPLICAS) * 8 + 5u, (double)st_resc);
 }

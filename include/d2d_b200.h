@@ -34,7 +34,7 @@
 #define D2D_API __attribute__((visibility("default")))
 #endif
 
-#define D2D_ABI_VERSION 3
+#define D2D_ABI_VERSION 4
 
 typedef struct d2d_handle d2d_handle_t;
 
@@ -131,7 +131,7 @@ typedef struct d2d_step_io {
 
 /* Episode statistics accumulated on the device by d2d_step when a stats buffer is bound;
  * this is the vector the multi-GPU shell all-reduces over NCCL (never inside the step). */
-#define D2D_STATS_REPLICAS 32   /* the stats buffer is [D2D_STATS_REPLICAS][D2D_NUM_STATS]; readers sum over replicas */
+#define D2D_STATS_REPLICAS 1024   /* the stats buffer is [D2D_STATS_REPLICAS][D2D_NUM_STATS]; readers sum over replicas */
 enum { D2D_STAT_SUM_REWARD = 0, D2D_STAT_SUM_CAPACITY = 1, D2D_STAT_SUM_REWARD_SQ = 2,
        D2D_STAT_ENV_STEPS = 3, D2D_STAT_PENALTIES = 4, D2D_STAT_RESCUES = 5, D2D_NUM_STATS = 8 };
 

@@ -30,4 +30,4 @@ for _ in range(iters):
 t.record()
 torch.cuda.synchronize()
 us = s.elapsed_time(t) * 1e3 / (iters * ring)
-print(f'E={E} {us:.2f} us/step  {E / us * 1e6:.3e} env-steps/s  frac={B * E / us / 1e3 / 6546.2:.3f}  geom={env.step_geometry()} rescues/env-step={env.stats()["rescues"] / env.stats()["env_steps"]:.4f}')
+print(f'E={E} {us:.2f} us/step  {E / us * 1e6:.3e} env-steps/s  frac={B * E / us / 1e3 / 6546.2:.3f}  geom={env.step_geometry()} rescues/env-step={env.stats()["rescues"] / max(1.0, env.stats()["env_steps"]):.4f}')
