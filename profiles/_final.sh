@@ -9,3 +9,6 @@ for E in 1024 4096 131072; do
   [ $E = 4096 ] || rm -f gpurun_out/prof_final_E$E.ncu-rep
 done
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:d2d_ --csv --log-file gpurun_out/launches_r01c.csv python bench.py --steps 64 --warmup 3 --skip-cpu-baseline > gpurun_out/bench_under_ncu.log 2>&1; wc -l gpurun_out/launches_r01c.csv
+export D2D_B200_LIB=$PWD/gym_d2d_b200/_variants/timeline.so
+for E in 1024 4096; do timeout 100 python profiles/timeline.py $E > gpurun_out/timeline_final_E$E.txt 2>&1; rm -f gpurun_out/timeline_E$E.npy; done
+tail -12 gpurun_out/timeline_final_E1024.txt
