@@ -362,23 +362,30 @@ def run_cuda_arm(args) -> None:
         torch.cuda.synchronize()
         if pg is not None:
             pg.barrier()
-        # two steps in flight: upload(i+1) and download(i-1) overlap kernel(i); every step's results reach the host
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            if i >= 2:
-                env.step_host_wait(i & 1)
-            env.step_host_async(host_np[i % 4], host_outs[i & 1], i & 1)
-        env.step_host_wait(0)
-        env.step_host_wait(1)
-        t1 = time.perf_counter()
-        windows.append((t0, t1))
-        dt = t1 - t0
-        if pg is not None:
-            t = torch.tensor([dt], dtype=torch.float64, device=env.device)
-            pg.all_reduce(t, op=pg.ReduceOp.MAX)
-            dt = float(t.item())
+        # two steps in flight: upload(i+1) and download(i-1) overlap kernel(i); every step's results reach the host.
+        # The window is short (200 steps ~ 25 ms of host-driven copies) and sees the host's other activity, so it is
+        # repeated three times and the MEDIAN window is reported (all three are listed in `window_ms`).
+        dts = []
+        for rep in range(3):
+            t0 = time.perf_counter()
+            for i in range(e2e_steps):
+                if i >= 2:
+                    env.step_host_wait(i & 1)
+                env.step_host_async(host_np[i % 4], host_outs[i & 1], i & 1)
+            env.step_host_wait(0)
+            env.step_host_wait(1)
+            t1 = time.perf_counter()
+            windows.append((t0, t1))
+            dt = t1 - t0
+            if pg is not None:
+                t = torch.tensor([dt], dtype=torch.float64, device=env.device)
+                pg.all_reduce(t, op=pg.ReduceOp.MAX)
+                dt = float(t.item())
+            dts.append(dt)
+        dt = sorted(dts)[1]
         e2e = {'value': world * E * e2e_steps / dt, 'unit': UNIT, 'h2d_bytes_per_step': E * N * 4,
                'd2h_bytes_per_step': E * N * 24 + E * N * 4 + E * 4 + E, 'steps': e2e_steps,
+               'window_ms': [round(1e3 * x, 3) for x in dts],
                'host_link_gbs_per_gpu': (E * N * 4 + E * N * 24 + E * N * 4 + E * 4 + E) * e2e_steps / dt / 1e9,   # copies in both directions: the PCIe link bounds this number
                'api': 'd2d_step_host_async/_wait via VecD2DEnv.step_host_async (pinned host buffers, two steps in flight; actions '
                       'copied in, obs + capacity + reward + done copied back, every step)'}
