@@ -534,6 +534,7 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, void *stream) {
         P.tl_slot = (int32_t)(h->launches % D2D_TL_SLOTS);
 #endif
         const int grid = (int)std::min<int64_t>(h->grid, (n + h->envs_per_block - 1) / h->envs_per_block);
+        if (h->use_warp) { const int64_t warps = (int64_t)grid * h->wpb; P.envs_per_warp = (uint32_t)((n + warps - 1) / warps); }
         const bool exact = h->pos64 != nullptr;
         cudaError_t err;
         // FULL: exactly the core outputs were passed, so the kernel tests no output pointer on its hot path

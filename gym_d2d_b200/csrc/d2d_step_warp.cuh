@@ -481,8 +481,8 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
     const uint32_t zrec = bins + R * D2D_BIN_STRIDE + 512u;               // the warp's all-zero peer record
     const bool hasA = lane < C, hasB = lane < S.D();
 
-    const uint32_t num_envs = (uint32_t)P.num_envs, num_warps = gridDim.x * WPB;
-    const uint32_t per_warp = (num_envs + num_warps - 1u) / num_warps;
+    const uint32_t num_envs = (uint32_t)P.num_envs;
+    const uint32_t per_warp = P.envs_per_warp;
     const uint32_t e0 = min((blockIdx.x * WPB + warp) * per_warp, num_envs), e_end = min(e0 + per_warp, num_envs);
     uint32_t e = e0;
     uint32_t iA = e * N + lane;                                    // slot-A link index of the env being computed

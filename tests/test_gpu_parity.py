@@ -547,6 +547,15 @@ def test_warp_launch_shapes_bit_identical(monkeypatch, exact):
         got[wpb] = dict(obs=env.obs.clone(), cap=env.capacity_mbps.clone(), reward=env.reward.clone(), done=env.done.clone(),
                         rate=env.rate_bps.clone(), count=env.step_count.clone(), rescues=st['rescues'], cap_sum=st['sum_capacity_mbps'])
         env.close()
+        # the same three steps as ONE d2d_step_many launch of this shape
+        many = G.VecD2DEnv(E, {}, info=True, exact_positions=exact)
+        many.set_positions(pos)
+        out = many.step_many(torch.stack([a, a, a]).contiguous())
+        torch.cuda.synchronize()
+        for k, v in dict(obs='obs', cap='capacity_mbps', reward='reward', done='done', rate='rate_bps').items():
+            assert torch.equal(out[v][2], got[wpb][k]), (wpb, 'step_many', k)
+        assert torch.equal(many.step_count, got[wpb]['count']) and many.stats()['rescues'] == st['rescues']
+        many.close()
     monkeypatch.delenv('D2D_B200_WPB')
     for wpb in (4, 8):
         for k in ('obs', 'cap', 'reward', 'done', 'rate', 'count'):
