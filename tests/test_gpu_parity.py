@@ -534,10 +534,12 @@ def test_warp_launch_shapes_bit_identical(monkeypatch, exact):
     act[::7, ::4] = -1
     a = torch.as_tensor(act, device='cuda')
     got = {}
-    for wpb in (2, 4, 8):
-        monkeypatch.setenv('D2D_B200_WPB', str(wpb))
+    for wpb in (2, 4, 8, 102, 104, 108):            # 10x: the same shape on 40 blocks, so every warp steps 5-19 envs
+        monkeypatch.setenv('D2D_B200_WPB', str(wpb % 100))
+        if wpb > 100:
+            monkeypatch.setenv('D2D_B200_GRID', '40')
         env = G.VecD2DEnv(E, {}, info=True, exact_positions=exact)
-        assert env.step_geometry()['block'] == 32 * wpb
+        assert env.step_geometry()['block'] == 32 * (wpb % 100) and (wpb < 100 or env.step_geometry()['grid'] == 40)
         env.set_positions(pos)
         for _ in range(3):                          # back-to-back launches: the programmatic-dependent-launch path
             env.step(a)
@@ -557,7 +559,8 @@ def test_warp_launch_shapes_bit_identical(monkeypatch, exact):
         assert torch.equal(many.step_count, got[wpb]['count']) and many.stats()['rescues'] == st['rescues']
         many.close()
     monkeypatch.delenv('D2D_B200_WPB')
-    for wpb in (4, 8):
+    monkeypatch.delenv('D2D_B200_GRID')
+    for wpb in (4, 8, 102, 104, 108):
         for k in ('obs', 'cap', 'reward', 'done', 'rate', 'count'):
             assert torch.equal(got[2][k], got[wpb][k]), (wpb, k)
         assert got[2]['rescues'] == got[wpb]['rescues']
