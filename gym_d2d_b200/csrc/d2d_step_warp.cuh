@@ -328,8 +328,11 @@ __device__ __forceinline__ D2DLinkOut d2d_link_epilogue_warp(bool live, int p, f
 
 // Some RB holds more links than a bin has record slots: all-pairs pass over the 64 link slots by shuffle (no table).
 // A term counts when the RB keys match and it is not the victim itself.  Returns (I_A, I_B, dmin2_A, dmin2_B).
+#ifndef D2D_RARE_ATTR
+#define D2D_RARE_ATTR __forceinline__     // A/B knob: __noinline__ moves the rare paths out of the hot loop's code
+#endif
 template <bool PLE2, bool EXACT>
-__device__ __forceinline__ float4 d2d_all_pairs_warp(uint32_t lane, uint32_t keyA, uint32_t keyB, float4 recA, float4 pB, float wB, float uB,
+__device__ D2D_RARE_ATTR float4 d2d_all_pairs_warp(uint32_t lane, uint32_t keyA, uint32_t keyB, float4 recA, float4 pB, float wB, float uB,
                                                       float nhp) {
     float IA = 0.f, IB = 0.f, dminA = 3.0e38f, dminB = 3.0e38f;
 #pragma unroll 1
@@ -453,6 +456,15 @@ __device__ __forceinline__ int d2d_rescue_warp(const D2DParams &P, const D2DShap
         }
     }
     return (int)__reduce_add_sync(0xffffffffu, (unsigned)done);
+}
+
+// the throughput shapes' call of the pass (after the stores): one place to take it out of line
+template <bool PLE2, bool EXACT, bool SPEC>
+__device__ D2D_RARE_ATTR int d2d_rescue_warp_late(const D2DParams &P, const D2DShape<SPEC> &S, uint32_t e, uint32_t lane, uint32_t jA,
+                                                  uint32_t keyA, uint32_t keyB, bool needA, bool needB, uint32_t pA, uint32_t pB_,
+                                                  float2 tA, float4 pB) {
+    D2DLinkOut oA, oB;       // unused by the storing variant
+    return d2d_rescue_warp<PLE2, EXACT, SPEC, true>(P, S, e, lane, jA, keyA, keyB, needA, needB, pA, pB_, tA, pB, oA, oB);
 }
 
 // FULL: the caller passed exactly the core outputs (obs, capacity, reward, done) and a step counter is bound - the
@@ -719,7 +731,7 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         // ---- throughput shape: the rare fp64 pass after the env's outputs are stored (it overwrites them) -------------------
         if (D2D_RESCUE_ENABLED && !RESCUE_EARLY && __any_sync(0xffffffffu, needA || needB)) {
             const uint32_t keyA = liveA ? rbA : (D2D_INACTIVE_KEY | lane), keyB = liveB ? rbB : (D2D_INACTIVE_KEY | 32u | lane);
-            st_resc += (uint32_t)d2d_rescue_warp<PLE2, EXACT, SPEC, true>(P, S, e, lane, jA, keyA, keyB, needA, needB, pA, pB_, tA, pB, oA, oB);
+            st_resc += (uint32_t)d2d_rescue_warp_late<PLE2, EXACT, SPEC>(P, S, e, lane, jA, keyA, keyB, needA, needB, pA, pB_, tA, pB);
         }
         if (last_t) {
             g = (g + 1u) & 31u;
