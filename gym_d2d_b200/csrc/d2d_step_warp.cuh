@@ -479,6 +479,9 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
     const D2DShape<SPEC> S(P);
     // latency shape: the fp64 pass runs before griddepcontrol.wait
     constexpr bool RESCUE_EARLY = WPB == 2;
+    // statistics flushed with the warp's last env, ahead of the wait - the shapes where a warp steps one or a few envs; the
+    // throughput shape flushes after its loop (the per-env test costs its 37-env warps more than the late atomics)
+    constexpr bool FLUSH_EARLY = WPB != 8;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const uint32_t C = S.C(), N = S.N(), V = S.V(), R = S.R();
 #ifdef D2D_TIMELINE
@@ -655,11 +658,12 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         if (P.reward_fn == 0) { st_reward += reward; st_reward2 = fmaf(reward, reward, st_reward2); }
         st_cap += cap_sum;
         st_pen += bad ? 1u : 0u;
-        if (P.stats && last_t && e + 1u == e_end && lane < (RESCUE_EARLY ? 6u : 5u)) {
+        if (FLUSH_EARLY && P.stats && last_t && e + 1u == e_end && lane < (RESCUE_EARLY ? 6u : 5u)) {
             // one fire-and-forget fp64 reduction per statistic and warp, spread over the replicas
-            const double v = lane == 0 ? (double)st_reward : lane == 1 ? (double)st_cap : lane == 2 ? (double)st_reward2
-                           : lane == 3 ? (double)((e_end - e0) * T)            // env-steps this warp made
-                           : lane == 4 ? (double)st_pen : (double)st_resc;
+            const float vf = lane == 0 ? st_reward : lane == 1 ? st_cap : st_reward2;
+            const uint32_t vi = lane == 3 ? (e_end - e0) * T                   // env-steps this warp made
+                              : lane == 4 ? st_pen : st_resc;
+            const double v = lane < 3u ? (double)vf : (double)vi;              // (two conversions instead of six)
 #ifndef D2D_EXPERIMENT_NOSTATS      // A/B only: what the statistics flush costs
             if (v != 0.0) atomicAdd(P.stats + ((blockIdx.x * WPB + warp) % D2D_STATS_REPLICAS) * 8 + lane, v);
 #endif
@@ -750,7 +754,15 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         d2d_tl_buf[P.tl_slot & (D2D_TL_SLOTS - 1)][blockIdx.x * WPB + warp] = r;
     }
 #endif
-    // the throughput shapes run the fp64 pass after the env's stores: its counter follows here (rarely non-zero for a one-env warp)
-    if (!RESCUE_EARLY && P.stats && lane == 5u && st_resc != 0u)
+    if (!FLUSH_EARLY) {
+        if (P.stats && lane < 6u) {
+            const float vf = lane == 0 ? st_reward : lane == 1 ? st_cap : st_reward2;
+            const uint32_t vi = lane == 3 ? (e_end - e0) * T : lane == 4 ? st_pen : st_resc;
+            const double v = lane < 3u ? (double)vf : (double)vi;
+            if (v != 0.0) atomicAdd(P.stats + ((blockIdx.x * WPB + warp) % D2D_STATS_REPLICAS) * 8 + lane, v);
+        }
+    } else if (!RESCUE_EARLY && P.stats && lane == 5u && st_resc != 0u) {
+        // the one-wave shape runs the fp64 pass after the env's stores: its counter follows here (rarely non-zero for a one-env warp)
         atomicAdd(P.stats + ((blockIdx.x * WPB + warp) % D2D_STATS_REPLICAS) * 8 + 5u, (double)st_resc);
+    }
 }
