@@ -357,8 +357,9 @@ def run_cuda_arm(args) -> None:
             h.copy_(a)
         host_np = [h.numpy() for h in host_acts]
         e2e_steps = max(10, min(args.steps, 200))
-        for i in range(3):
-            env.step_host(host_np[i % 4], host_outs[0])
+        for i in range(4):                 # warm-up through BOTH pipeline slots (a slot's device staging is allocated on first use)
+            env.step_host_async(host_np[i % 4], host_outs[i & 1], i & 1)
+            env.step_host_wait(i & 1)
         torch.cuda.synchronize()
         if pg is not None:
             pg.barrier()
