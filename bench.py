@@ -242,19 +242,25 @@ def run_reference_arm(args) -> None:
 # the CUDA arm
 # ------------------------------------------------------------------------------------------------------------
 def timed_steps(env, torch, actions, outs, steps, warmup, dist, use_graph=True):
-    """W untimed + EXACTLY K timed steps; step i reads actions[i % RING] and writes outs[i % RING].
-    Returns (seconds [max over ranks], perf_counter window, launches)."""
+    """W untimed + EXACTLY K timed steps; step i reads actions[i % RING] and writes outs[i % RING].  The K steps are issued as
+    replays of ONE CUDA graph of G = min(K, RING) step kernels (+ K mod G eager launches): what a throughput-minded caller
+    does, and independent of how busy the host's Python threads are.  The action buffers are pre-generated, so the steps
+    carry D2D_STEP_INPUTS_STABLE (include/d2d_b200.h, "Ordering rule").
+    Returns (seconds [max over ranks], perf_counter window, launches, launch description)."""
     ring = len(actions)
 
     def eager(i0, n):
         for i in range(i0, i0 + n):
-            env.step(actions[i % ring], out=outs[i % ring])
+            env.step(actions[i % ring], out=outs[i % ring], inputs_stable=True)
 
-    graph = None
-    if use_graph and steps >= ring:
+    graph, G = None, 0
+    if use_graph and steps >= 2:
+        G = min(steps, ring)
         eager(0, ring)                                   # module load + first-touch before capture
-        graph = env.capture_steps(actions, outs)         # one graph = RING consecutive steps
+        graph = env.capture_steps([actions[i % ring] for i in range(G)], [outs[i % ring] for i in range(G)], inputs_stable=True)
     eager(0, warmup)
+    if graph is not None:
+        graph.replay()                                   # untimed: uploads the graph
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -265,9 +271,9 @@ def timed_steps(env, torch, actions, outs, steps, warmup, dist, use_graph=True):
     start.record()
     done = 0
     if graph is not None:
-        for _ in range(steps // ring):
+        for _ in range(steps // G):
             graph.replay()
-        done = (steps // ring) * ring
+        done = (steps // G) * G
     eager(done, steps - done)
     stop.record()
     torch.cuda.synchronize()
@@ -279,7 +285,37 @@ def timed_steps(env, torch, actions, outs, steps, warmup, dist, use_graph=True):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         secs = float(t.item())
         dist.barrier()
-    return secs, (t0, t1), launches
+    how = (f'{steps // G} replay(s) of a CUDA graph of {G} step kernels' + (f' + {steps - done} eager launches' if steps - done else '')
+           if graph is not None else f'{steps} eager launches')
+    return secs, (t0, t1), launches, how + '; pre-generated actions (D2D_STEP_INPUTS_STABLE)'
+
+
+def host_link_peak(torch, device, nbytes_in, nbytes_out, dist, iters=30):
+    """Plain pinned-memory cudaMemcpyAsync of the end-to-end path's per-step sizes, both directions at once, all ranks at
+    once: what the box's host link gives this process - the ceiling of any host-buffer API."""
+    hin = torch.empty(nbytes_in, dtype=torch.uint8, pin_memory=True)
+    hout = torch.empty(nbytes_out, dtype=torch.uint8, pin_memory=True)
+    din = torch.empty(nbytes_in, dtype=torch.uint8, device=device)
+    dout = torch.empty(nbytes_out, dtype=torch.uint8, device=device)
+    s1, s2 = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+    for it in range(2):
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            with torch.cuda.stream(s1):
+                din.copy_(hin, non_blocking=True)
+            with torch.cuda.stream(s2):
+                hout.copy_(dout, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([dt], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    return {'d2h_gbs_per_gpu': nbytes_out * iters / dt / 1e9, 'h2d_gbs_per_gpu': nbytes_in * iters / dt / 1e9,
+            'how': f'{iters} x (H2D {nbytes_in} B || D2H {nbytes_out} B) pinned cudaMemcpyAsync on two streams, every rank at once'}
 
 
 def run_cuda_arm(args) -> None:
@@ -295,6 +331,8 @@ def run_cuda_arm(args) -> None:
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device: gym_d2d_b200 has no CPU path (use --impl reference for the CPU arm)')
     torch.cuda.set_device(local)
+    from gym_d2d_b200.dist import EpisodeStatsReducer, bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local)      # before any pinned allocation: host buffers next to this GPU's PCIe root
     pg = None
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
@@ -322,7 +360,7 @@ def run_cuda_arm(args) -> None:
     N, V = env.num_links, env.num_devices
     B = algorithmic_bytes_per_env_step(N, V)
     comm_stream = torch.cuda.Stream() if world > 1 else None
-    secs, win, launches = timed_steps(env, torch, acts, outs, args.steps, args.warmup, pg)
+    secs, win, launches, launch_how = timed_steps(env, torch, acts, outs, args.steps, args.warmup, pg)
     windows.append(win)
     if world > 1:   # episode statistics: one tiny all-reduce, off the step stream (never inside the step)
         stats = env.stats_tensor()
@@ -348,31 +386,43 @@ def run_cuda_arm(args) -> None:
         except Exception:  # noqa: BLE001
             traffic = None
 
-    # ---- end to end through the C ABI with HOST buffers (d2d_step_host): H2D actions + D2H results per step ----
+    # ---- end to end through the C ABI with HOST buffers (d2d_step_host_async): H2D actions + D2H results per step ----
+    # The per-step results a host loop needs are the columns that change every step: obs_dyn (sinr, snr) + capacity + reward +
+    # done = 12 N + 5 bytes per env-step; the four position columns of the observation table move only on reset and are
+    # fetched once (d2d_get_positions).  Outputs land in the library's packed pinned slot buffers: one copy per direction.
     e2e = None
     if not args.skip_e2e:
-        host_outs = [env.alloc_host_outputs(pinned=True, info=False), env.alloc_host_outputs(pinned=True, info=False)]
+        slots = [env.host_slot_buffers(0), env.host_slot_buffers(1)]
+        obs_static = env.obs_static()              # once per reset, outside the per-step loop (E x N x 16 B)
         host_acts = [torch.empty((E, N), dtype=torch.int32, pin_memory=True) for _ in range(4)]
         for h, a in zip(host_acts, acts):
             h.copy_(a)
         host_np = [h.numpy() for h in host_acts]
-        e2e_steps = max(10, min(args.steps, 200))
-        for i in range(4):                 # warm-up through BOTH pipeline slots (a slot's device staging is allocated on first use)
-            env.step_host_async(host_np[i % 4], host_outs[i & 1], i & 1)
+        h2d, d2h = E * N * 4, E * N * 8 + E * N * 4 + E * 4 + E
+        e2e_steps = max(20, min(args.steps, 400))
+        for i in range(4):                 # warm-up through BOTH pipeline slots
+            env.step_host_async(host_np[i % 4], slots[i & 1], i & 1)
             env.step_host_wait(i & 1)
+        # parity of the transport: the reassembled table equals the full-table device output of the same step
+        env.step_count.zero_()
+        env.step(acts[3], out=outs[0])
+        torch.cuda.synchronize()
+        import numpy as np
+        assert np.array_equal(env.assemble_obs(obs_static, slots[1]['obs_dyn']), outs[0].obs.cpu().numpy()), 'obs_dyn transport mismatch'
+        link = host_link_peak(torch, env.device, h2d, d2h, pg)
         torch.cuda.synchronize()
         if pg is not None:
             pg.barrier()
         # two steps in flight: upload(i+1) and download(i-1) overlap kernel(i); every step's results reach the host.
-        # The window is short (200 steps ~ 25 ms of host-driven copies) and sees the host's other activity, so it is
-        # repeated three times and the MEDIAN window is reported (all three are listed in `window_ms`).
+        # The window is short and sees the host's other activity, so it is repeated three times and the MEDIAN window is
+        # reported (all three are listed in `window_ms`).
         dts = []
         for rep in range(3):
             t0 = time.perf_counter()
             for i in range(e2e_steps):
                 if i >= 2:
                     env.step_host_wait(i & 1)
-                env.step_host_async(host_np[i % 4], host_outs[i & 1], i & 1)
+                env.step_host_async(host_np[i % 4], slots[i & 1], i & 1)
             env.step_host_wait(0)
             env.step_host_wait(1)
             t1 = time.perf_counter()
@@ -384,12 +434,14 @@ def run_cuda_arm(args) -> None:
                 dt = float(t.item())
             dts.append(dt)
         dt = sorted(dts)[1]
-        e2e = {'value': world * E * e2e_steps / dt, 'unit': UNIT, 'h2d_bytes_per_step': E * N * 4,
-               'd2h_bytes_per_step': E * N * 24 + E * N * 4 + E * 4 + E, 'steps': e2e_steps,
-               'window_ms': [round(1e3 * x, 3) for x in dts],
-               'host_link_gbs_per_gpu': (E * N * 4 + E * N * 24 + E * N * 4 + E * 4 + E) * e2e_steps / dt / 1e9,   # copies in both directions: the PCIe link bounds this number
+        e2e = {'value': world * E * e2e_steps / dt, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+               'steps': e2e_steps, 'window_ms': [round(1e3 * x, 3) for x in dts],
+               'host_link_gbs_per_gpu': (h2d + d2h) * e2e_steps / dt / 1e9,   # copies in both directions: the PCIe link bounds this number
+               'd2h_gbs_per_gpu': d2h * e2e_steps / dt / 1e9, 'host_link_peak': link, 'numa': numa,
+               'once_per_reset_bytes': int(obs_static.nbytes),
                'api': 'd2d_step_host_async/_wait via VecD2DEnv.step_host_async (pinned host buffers, two steps in flight; actions '
-                      'copied in, obs + capacity + reward + done copied back, every step)'}
+                      'copied in; obs_dyn (sinr, snr) + capacity + reward + done copied back every step as ONE packed copy; the '
+                      'position columns of the observation table are fetched once per reset with d2d_get_positions)'}
     # ---- fused rollouts: d2d_step_many, T steps of every env per launch -----------------------------------
     fused = None
     if args.fused_steps > 1:
@@ -425,15 +477,16 @@ def run_cuda_arm(args) -> None:
 
     # ---- large batch: BASELINE configs[4]'s per-GPU slice (131072 envs, working set 290 MB > L2) ---------------
     large = None
+    episode = None
     if args.large_envs_per_gpu > 0:
-        envL, actsL, outsL = build(args.large_envs_per_gpu, seed=1)
+        envL, actsL, outsL = build(args.large_envs_per_gpu, seed=1, ring=8)
         stepsL = max(RING, min(args.steps, 4 * RING))
-        secsL, winL, _ = timed_steps(envL, torch, actsL[:8], outsL[:8], stepsL, max(3, min(args.warmup, 8)), pg)
+        secsL, winL, _, howL = timed_steps(envL, torch, actsL, outsL, stepsL, max(3, min(args.warmup, 8)), pg)
         windows.append(winL)
         EL = args.large_envs_per_gpu
         achL = B * EL / (secsL / stepsL) / 1e9
         large = {'workload': f'{EL} default-config envs per GPU (BASELINE configs[4] slice; working set > L2)',
-                 'value': world * EL * stepsL / secsL, 'unit': UNIT, 'steps': stepsL, 'ms_per_step': 1e3 * secsL / stepsL,
+                 'value': world * EL * stepsL / secsL, 'unit': UNIT, 'steps': stepsL, 'ms_per_step': 1e3 * secsL / stepsL, 'launch': howL,
                  'roofline': {'bound': 'hbm', 'achieved': achL, 'peak': peak, 'unit': 'GB/s', 'frac': achL / peak,
                               'traffic': None}}
         if prof.exists():
@@ -441,8 +494,55 @@ def run_cuda_arm(args) -> None:
                 large['roofline']['traffic'] = json.loads(prof.read_text()).get(f'dram_bytes_per_launch_E{EL}')
             except Exception:  # noqa: BLE001
                 pass
+        del actsL, outsL
+        # ---- BASELINE configs[4] as specified: the EPISODE loop.  Per episode ONE d2d_episode launch - Simulator.reset (new
+        # positions), the uncounted reset step and EPISODE_LENGTH counted steps with on-device sampled actions - and one
+        # all-reduce of that episode's reward / capacity statistics over the ranks on a side stream.  Only the counted steps
+        # count as env-steps; every slice's outputs (11 per episode) are written to HBM.
+        if args.episodes > 0:
+            T = 10
+            red = EpisodeStatsReducer(envL, None)      # default process group (NCCL) when world > 1
+            ep_outs = [envL.alloc_many_outputs(T + 1) for _ in range(2)]
+            for i in range(2):
+                red.begin_episode(); envL.episode(T, out=ep_outs[i & 1]); red.end_episode()
+            red.finish()
+            torch.cuda.synchronize()
+            if pg is not None:
+                pg.barrier()
+            nr0 = red.all_reduces
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = envL.launch_count
+            t0 = time.perf_counter()
+            ev0.record()
+            for i in range(args.episodes):
+                red.begin_episode()
+                envL.episode(T, out=ep_outs[i & 1])
+                red.end_episode()
+            red.finish()
+            ev1.record()
+            torch.cuda.synchronize()
+            windows.append((t0, time.perf_counter()))
+            secsE = ev0.elapsed_time(ev1) * 1e-3
+            if pg is not None:
+                tt = torch.tensor([secsE], dtype=torch.float64, device=envL.device)
+                pg.all_reduce(tt, op=pg.ReduceOp.MAX)
+                secsE = float(tt.item())
+            last = summarise(red.results[-1])
+            BE = (T + 1) * (32 * N - 4 * N + 5) + 8 * V + 1           # 11 slices of outputs (no action / position reads) + the positions written once
+            episode = {'workload': f'{args.episodes} episodes of {EL} default-config envs per GPU: d2d_episode (device-side reset + uncounted reset step + '
+                                   f'{T} counted steps, on-device sampled actions) in one launch, statistics all-reduced per episode on a side stream',
+                       'value': world * EL * T * args.episodes / secsE, 'unit': UNIT, 'episodes': args.episodes,
+                       'ms_per_episode': 1e3 * secsE / args.episodes, 'ms_per_counted_step': 1e3 * secsE / (args.episodes * T),
+                       'vs_steps_only': (EL * T * args.episodes / secsE) / (EL * stepsL / secsL),
+                       'launches_per_episode': (envL.launch_count - l0) / args.episodes,
+                       'stats_allreduces': red.all_reduces - nr0, 'allreduce_world': world,
+                       'last_episode_stats': {k: last[k] for k in ('env_steps', 'mean_reward', 'mean_capacity_mbps', 'penalties')},
+                       'roofline': {'bound': 'hbm', 'algorithmic_bytes_per_env_episode': BE,
+                                    'achieved': BE * EL * args.episodes / secsE / 1e9, 'peak': peak, 'unit': 'GB/s',
+                                    'frac': BE * EL * args.episodes / secsE / 1e9 / peak}}
+            del ep_outs
         envL.close()
-        del envL, actsL, outsL
+        del envL
 
     # ---- dense cell: BASELINE configs[2] (100 RBs / 100 CUEs / 500 DUE pairs, FreeSpacePathLoss, 65536 envs: 1.8 GB per step) ----
     dense = None
@@ -451,14 +551,14 @@ def run_cuda_arm(args) -> None:
         envD, actsD, outsD = build(ED, seed=2, cfg=dict(num_rbs=100, num_cues=100, num_due_pairs=500, path_loss_model=G.FreeSpacePathLoss), ring=4)
         BD = algorithmic_bytes_per_env_step(envD.num_links, envD.num_devices)
         stepsD = max(8, min(args.steps, 32))
-        secsD, winD, _ = timed_steps(envD, torch, actsD, outsD, stepsD, 3, pg)
+        secsD, winD, _, howD = timed_steps(envD, torch, actsD, outsD, stepsD, 3, pg)
         windows.append(winD)
         achD = BD * ED / (secsD / stepsD) / 1e9
         gD = envD.step_geometry()
         dense = {'workload': f'BASELINE configs[2]: {ED} envs per GPU of the dense cell (100 RBs, 100 CUEs, 500 DUE pairs: N = 600 links, '
                              'V = 1101 devices), FreeSpacePathLoss; 4 action/output buffer sets of 1.3 GB',
                  'value': world * ED * stepsD / secsD, 'unit': UNIT, 'steps': stepsD, 'ms_per_step': 1e3 * secsD / stepsD,
-                 'kernel': 'd2d_step_dense_kernel', 'grid': gD['grid'], 'block': gD['block'], 'smem_bytes': gD['smem_bytes'],
+                 'kernel': 'd2d_step_dense_kernel', 'launch': howD, 'grid': gD['grid'], 'block': gD['block'], 'smem_bytes': gD['smem_bytes'],
                  'roofline': {'bound': 'hbm', 'achieved': achD, 'peak': peak, 'unit': 'GB/s', 'frac': achD / peak,
                               'algorithmic_bytes_per_env_step': BD, 'traffic': None}}
         if prof.exists():
@@ -468,6 +568,28 @@ def run_cuda_arm(args) -> None:
                 pass
         envD.close()
         del envD, actsD, outsD
+
+    # ---- the reference's own dict API at E = 1 (BASELINE configs[0] through this repo): gym-style D2DEnv.step(dict) ----
+    dict_api = None
+    if rank == 0 and args.dict_steps > 0:
+        import random as _random
+        one = G.D2DEnv({}, device=torch.device('cuda', local))
+        one.reset()
+        keys = list(one.link_keys)
+        n_of = {k: one.action_space['cue' if k.startswith('cue') else 'due'].n for k in keys}
+        rnd = _random.Random(0)
+        acts1 = [{k: rnd.randrange(n_of[k]) for k in keys} for _ in range(args.dict_steps + 20)]
+        for a1 in acts1[:20]:
+            one.step(a1)
+        t0 = time.perf_counter()
+        for a1 in acts1[20:]:
+            one.step(a1)
+        dt1 = time.perf_counter() - t0
+        dict_api = {'value': args.dict_steps / dt1, 'unit': UNIT, 'ms_per_step': 1e3 * dt1 / args.dict_steps, 'steps': args.dict_steps,
+                    'workload': "BASELINE configs[0] through this repo: gym_d2d_b200.D2DEnv({}).step(dict of 50 'tx:rx' -> int) at E = 1, "
+                                'synchronous d2d_step_host per call (H2D actions, one kernel, D2H results), dict / per-agent obs building '
+                                'on one host thread; compare cpu_baseline.value / cpu_baseline.cores (the reference per core)'}
+        one.close()
 
     sampler.stop()
     clocks = sampler.summary(windows)
@@ -484,7 +606,7 @@ def run_cuda_arm(args) -> None:
             'config': {'workload': f'BASELINE configs[1]: {E} batched default-config envs per GPU (25 RB / 25 CUE / 25 DUE pairs, '
                                    'LogDistancePathLoss), device-resident positions, uniform random RB/power actions',
                        'envs_per_gpu': E, 'num_links': N, 'num_devices': V, 'obs': 'compact [E][N][6] float32 table',
-                       'parallelism': f'env-sharded x{world}', 'launch': f'CUDA graph of {RING} step kernels' if args.steps >= RING else 'eager',
+                       'parallelism': f'env-sharded x{world}', 'launch': launch_how,
                        'grid': geometry['grid'], 'block': geometry['block'], 'smem_bytes': geometry['smem_bytes'],
                        'l2': f'ring of {RING} action/output buffer sets ({ring_bytes / 1e6:.0f} MB > 126 MB L2) so per-step I/O is '
                              'never L2-resident; the {:.1f} MB position state stays L2-resident by design'.format(E * V * 8 / 1e6),
@@ -500,6 +622,10 @@ def run_cuda_arm(args) -> None:
             line['fused_rollout'] = fused
         if large is not None:
             line['large_batch'] = large
+        if episode is not None:
+            line['episode_loop'] = episode
+        if dict_api is not None:
+            line['dict_api'] = dict_api
         if dense is not None:
             line['dense_cell'] = dense
         if base is not None:
@@ -520,6 +646,8 @@ def main() -> None:
     ap.add_argument('--large-envs-per-gpu', type=int, default=131072)
     ap.add_argument('--dense-envs-per-gpu', type=int, default=65536, help='BASELINE configs[2] leg (0 = skip)')
     ap.add_argument('--fused-steps', type=int, default=10, help='T of the d2d_step_many leg (EPISODE_LENGTH); 0/1 skips it')
+    ap.add_argument('--episodes', type=int, default=8, help='episodes of the episode_loop leg at --large-envs-per-gpu (0 = skip)')
+    ap.add_argument('--dict-steps', type=int, default=300, help='D2DEnv.step calls of the dict_api leg (0 = skip)')
     ap.add_argument('--skip-e2e', action='store_true')
     ap.add_argument('--skip-cpu-baseline', action='store_true')
     args = ap.parse_args()

@@ -10,7 +10,7 @@ from pathlib import Path
 
 from .build import LIB
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 STATS_REPLICAS = 1024
 NUM_STATS = 8
 STAT_NAMES = ('sum_reward', 'sum_capacity_mbps', 'sum_reward_sq', 'env_steps', 'penalties', 'rescues')
@@ -43,7 +43,14 @@ class D2DLink(C.Structure):
 class D2DStepIO(C.Structure):
     _fields_ = [('actions', C.c_void_p), ('obs', C.c_void_p), ('capacity_mbps', C.c_void_p),
                 ('reward', C.c_void_p), ('done', C.c_void_p), ('rate_bps', C.c_void_p),
-                ('rb', C.c_void_p), ('tx_pwr_dBm', C.c_void_p), ('agent_reward', C.c_void_p)]
+                ('rb', C.c_void_p), ('tx_pwr_dBm', C.c_void_p), ('agent_reward', C.c_void_p),
+                ('obs_dyn', C.c_void_p), ('actions_out', C.c_void_p), ('flags', C.c_uint32), ('reserved0', C.c_uint32)]
+
+
+STEP_INPUTS_STABLE = 1          # d2d_step_io.flags (include/d2d_b200.h, "Ordering rule")
+EPISODE_DRAW_ACTIONS = 1        # d2d_episode flags
+OUT_OBS, OUT_CAPACITY, OUT_REWARD, OUT_DONE, OUT_RATE, OUT_RB, OUT_TX_PWR, OUT_AGENT_REWARD, OUT_OBS_DYN = (
+    1, 2, 4, 8, 16, 32, 64, 128, 256)
 
 
 class D2DError(RuntimeError):
@@ -66,7 +73,11 @@ SIGNATURES = {
     'd2d_bind_positions_f64': (C.c_int, [_vp, _vp]),
     'd2d_set_positions': (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _vp]),
     'd2d_reset': (C.c_int, [_vp, _u64, _u64, _vp, _vp]),
+    'd2d_get_positions': (C.c_int, [_vp, _vp, C.c_int, _i64, _i64, _vp]),
+    'd2d_sample_actions': (C.c_int, [_vp, _vp, _u64, C.c_uint32, _vp]),
     'd2d_step': (C.c_int, [_vp, C.POINTER(D2DStepIO), _vp]),
+    'd2d_episode': (C.c_int, [_vp, C.POINTER(D2DStepIO), _i32, _u64, _u64, C.c_uint32, _vp]),
+    'd2d_host_slot_buffers': (C.c_int, [_vp, C.c_int, C.c_uint32, C.POINTER(D2DStepIO)]),
     'd2d_step_many': (C.c_int, [_vp, C.POINTER(D2DStepIO), _i32, _vp]),
     'd2d_step_host': (C.c_int, [_vp, C.POINTER(D2DStepIO), _vp]),
     'd2d_step_host_async': (C.c_int, [_vp, C.POINTER(D2DStepIO), C.c_int, _vp]),

@@ -1,7 +1,6 @@
 // d2d_abi.cu - the C ABI of libd2d_b200.so (include/d2d_b200.h): handle management, host-side folding of
-// the link-budget constants, and the kernel launches.  sm_100a only; there is no CPU path.
-#include "../../include/d2d_b200.h"
-
+// the link-budget constants, and the kernel launches.  sm_100a only; there is no CPU path.  The step kernels live in
+// their own translation units (d2d_internal.h).
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -10,89 +9,23 @@
 #include <string>
 #include <vector>
 
+#include "d2d_internal.h"
 #include "d2d_aux.cuh"
-#include "d2d_common.cuh"
-#include "d2d_step_block.cuh"
-#include "d2d_step_dense.cuh"
-#include "d2d_step_warp.cuh"
-
-// (links per thread, threads per block) instantiations of the dense kernel
-#define D2D_DENSE_SHAPES(X) X(1, 256) X(2, 256) X(3, 256) X(4, 256) X(1, 320) X(2, 320) X(3, 320)
-#define D2D_DENSE_PLAN_CASE(LPT_, BT_) if (h->lpt == LPT_ && h->dense_bt == BT_) rc = D2D_PLAN_DENSE(LPT_, BT_);
-#define D2D_DENSE_LAUNCH_CASE(LPT_, BT_) if (h->lpt == LPT_ && h->dense_bt == BT_) err = D2D_LAUNCH_DENSE(LPT_, BT_);
 
 static_assert(D2D_STATS_REPLICAS * 8 * sizeof(double) == 65536, "stats layout");
 
 namespace {
-
 thread_local std::string g_last_error;
+constexpr double kSpeedOfLight = 299792458.0;   // path_loss.py:9
+}  // namespace
 
-int fail(int code, const std::string &msg) {
+int d2d_fail(int code, const std::string &msg) {
     g_last_error = msg;
     return code;
 }
-
-#define D2D_CUDA(call)                                                                              \
-    do {                                                                                            \
-        cudaError_t err__ = (call);                                                                 \
-        if (err__ != cudaSuccess)                                                                   \
-            return fail(D2D_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__));        \
-    } while (0)
-
-constexpr double kSpeedOfLight = 299792458.0;   // path_loss.py:9
-
-}  // namespace
-
-struct d2d_handle {
-    d2d_config_t cfg{};
-    int N = 0, V = 0;
-    int num_sms = 0;
-    bool ple2 = true;
-    bool use_warp = true;
-    bool spec = false;         // warp kernel instantiated for the reference's default EnvConfig shape
-    bool uniform = false;      // every CUE link has the same constants, and every DUE link (no per-device overrides)
-    D2DLinkA u_cue{}, u_due{};
-    D2DLinkD ud_cue{}, ud_due{};
-    float us_cue[2] = {0, 0}, us_due[2] = {0, 0};
-    int wpb = 4;               // warps per block of the warp kernel
-    int dense_bt = 0;          // dense kernel (d2d_step_dense.cuh): threads per block, 0 = not used
-    int bin_cap = 0;           // dense kernel: record slots per RB bin
-    int lpt = 0;               // block / dense kernel: links per thread held in registers (0 = the generic shared-memory kernel)
-    int64_t chunk_override = 0;  // D2D_B200_CHUNK: force small launch chunks (tests of the > 2^31-element path)
-    bool pdl = true;           // programmatic dependent launch (D2D_B200_PDL=0 disables)
-    int grid = 0, block = 0, smem = 0, envs_per_block = 0;
-    double K_dB = 0.0, ple = 2.0;
-    D2DLinkA *dA = nullptr;
-    D2DLinkB *dB = nullptr;
-    D2DLinkD *dD = nullptr;
-    int32_t *dMeta = nullptr;  // [N] power levels | SIDELINK << 16 (general-topology kernel, fp64 helpers)
-    float *dPwr = nullptr;
-    double *dPwrD = nullptr;
-    // bound state (caller-owned)
-    float *pos = nullptr;
-    double *pos64 = nullptr;
-    uint8_t *step_count = nullptr;
-    double *stats = nullptr;
-    // staging for d2d_step_host / d2d_set_positions (handle-owned, allocated on first use)
-    void *stage2[2][9] = {};
-    cudaStream_t s_in = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[2] = {}, ev_kernel[2] = {}, ev_out[2] = {};
-    bool slot_used[2] = {false, false};
-    bool pipe_ready = false;
-    double *stage_pos = nullptr;
-    int64_t stage_pos_envs = 0;
-    int64_t launches = 0;
-    uint64_t rng_calls = 0;      // ShadowingPathLoss: number of step calls so far (every call draws fresh values)
-};
+static int fail(int code, const std::string &msg) { return d2d_fail(code, msg); }
 
 namespace {
-
-int ensure_device(const d2d_handle *h) {
-    int cur = -1;
-    D2D_CUDA(cudaGetDevice(&cur));
-    if (cur != h->cfg.cuda_device) D2D_CUDA(cudaSetDevice(h->cfg.cuda_device));
-    return D2D_OK;
-}
 
 D2DParams make_params(const d2d_handle *h, const d2d_step_io_t *io) {
     D2DParams P{};
@@ -118,7 +51,7 @@ D2DParams make_params(const d2d_handle *h, const d2d_step_io_t *io) {
     P.shadow_d0sq = (float)(h->cfg.shadow_d0_m * h->cfg.shadow_d0_m);
     P.shadow_chi_d = shadowing ? h->cfg.shadow_chi_dB : 0.0;
     P.shadow_d0sq_d = h->cfg.shadow_d0_m * h->cfg.shadow_d0_m;
-    P.rng_seed = h->cfg.rng_seed; P.first_global_env = h->cfg.first_global_env; P.rng_step = h->rng_calls;
+    P.rng_seed = h->cfg.rng_seed; P.first_global_env = h->cfg.first_global_env; P.rng_step = 0;
     if (h->pos64) {
         // positions were rounded to fp32: each coordinate is off by <= ulp(R)/2, a distance by <= ~sqrt(2) ulp(R),
         // i.e. 10 ple log10(e) * sqrt(2) ulp(R) / d dB per term; recompute whatever that could push past 1e-4 relative
@@ -133,89 +66,21 @@ D2DParams make_params(const d2d_handle *h, const d2d_step_io_t *io) {
     P.uniform = h->uniform ? 1 : 0;
     P.ud_cue = h->ud_cue; P.ud_due = h->ud_due;
     P.reward_fn = h->cfg.reward_fn;
+    if (h->cfg.reward_fn != D2D_REWARD_SYSTEM_CAPACITY) {
+        // the hard SINR threshold of the per-agent reward functions: links this close to it are decided in fp64
+        P.thr_dB = (float)h->cfg.reward_param; P.thr_d = h->cfg.reward_param;
+        P.thr_band = (h->ple2 && !shadowing) ? 2e-3f : 1.6e-2f;
+    }
     P.ple_d = h->ple;
     P.linkA = h->dA; P.linkB = h->dB; P.linkD = h->dD; P.link_meta = h->dMeta; P.pwr_lin = h->dPwr; P.pwr_lin_d = h->dPwrD;
     P.pos = h->pos; P.pos64 = h->pos64; P.step_count = h->step_count; P.stats = h->stats;
+    P.rng_step_dev = h->dRngStep;
+    P.cell_radius = (float)h->cfg.cell_radius_m; P.d2d_radius = (float)h->cfg.d2d_radius_m;
+    P.pos_out = h->pos;
+    P.obs_dyn = reinterpret_cast<float2 *>(io->obs_dyn); P.actions_out = io->actions_out;
     P.actions = io->actions; P.obs = io->obs; P.cap = io->capacity_mbps; P.reward = io->reward;
     P.done = io->done; P.rate = io->rate_bps; P.rb_out = io->rb; P.pwr_out = io->tx_pwr_dBm;
     return P;
-}
-
-// Launch a step kernel with programmatic stream serialisation (PDL): it may begin launching while the previous
-// kernel in the stream drains; the kernel itself orders its memory accesses with griddepcontrol.wait.
-template <typename K>
-cudaError_t launch_step(K kernel, int grid, int block, size_t smem, cudaStream_t st, const D2DParams &P, bool pdl) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3((unsigned)block);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kernel, P);
-}
-
-template <typename K>
-int allow_smem(K kernel, size_t smem) {
-    if (smem > 48 * 1024) D2D_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    return D2D_OK;
-}
-
-// every (EXACT, FULL) instantiation d2d_step may launch for this handle needs the dynamic shared-memory opt-in
-template <bool PLE2, int WPB, bool SPEC>
-int allow_smem_warp(size_t smem) {
-    int rc = allow_smem(d2d_step_warp_kernel<PLE2, false, WPB, false, SPEC, false>, smem);
-    if (!rc) rc = allow_smem(d2d_step_warp_kernel<PLE2, false, WPB, true, SPEC, false>, smem);
-    if (!rc) rc = allow_smem(d2d_step_warp_kernel<PLE2, true, WPB, false, SPEC, false>, smem);
-    if (!rc) rc = allow_smem(d2d_step_warp_kernel<PLE2, true, WPB, true, SPEC, false>, smem);
-    if (!rc) rc = allow_smem(d2d_step_warp_kernel<PLE2, false, WPB, false, SPEC, true>, smem);
-    if (!rc) rc = allow_smem(d2d_step_warp_kernel<PLE2, true, WPB, false, SPEC, true>, smem);
-    return rc;
-}
-
-template <typename K>
-int plan_geometry(d2d_handle *h, K kernel, int block, size_t smem, int envs_per_block) {
-    int rc = allow_smem(kernel, smem);
-    if (rc) return rc;
-    int occ = 0;
-    D2D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem));
-    if (occ < 1) return fail(D2D_ERR_UNSUPPORTED, "step kernel does not fit on an SM for this configuration");
-    const int64_t need = (h->cfg.num_envs + envs_per_block - 1) / envs_per_block;
-    const int64_t resident = (int64_t)h->num_sms * occ;
-    h->grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, resident));
-    h->block = block;
-    h->smem = (int)smem;
-    h->envs_per_block = envs_per_block;
-    return D2D_OK;
-}
-
-// every (FULL, EXACT) instantiation d2d_step may launch for this handle needs the dynamic shared-memory opt-in
-template <bool PLE2, int LPT, int BT>
-int plan_dense(d2d_handle *h, size_t smem) {
-    int rc = allow_smem(d2d_step_dense_kernel<PLE2, LPT, BT, false, false>, smem);
-    if (!rc) rc = allow_smem(d2d_step_dense_kernel<PLE2, LPT, BT, false, true>, smem);
-    if (!rc) rc = allow_smem(d2d_step_dense_kernel<PLE2, LPT, BT, true, true>, smem);
-    if (!rc) rc = plan_geometry(h, d2d_step_dense_kernel<PLE2, LPT, BT, true, false>, BT, smem, 1);
-    return rc;
-}
-
-template <int WPB>
-int plan_warp(d2d_handle *h, size_t smem) {
-    int rc;
-    if (h->spec) {          // the reference's default EnvConfig shape: counts and division magics are immediates
-        rc = allow_smem_warp<true, WPB, true>(smem);
-        if (!rc) rc = plan_geometry(h, d2d_step_warp_kernel<true, false, WPB, true, true, false>, WPB * 32, smem, WPB);
-    } else if (h->ple2) {
-        rc = allow_smem_warp<true, WPB, false>(smem);
-        if (!rc) rc = plan_geometry(h, d2d_step_warp_kernel<true, false, WPB, true, false, false>, WPB * 32, smem, WPB);
-    } else {
-        rc = allow_smem_warp<false, WPB, false>(smem);
-        if (!rc) rc = plan_geometry(h, d2d_step_warp_kernel<false, false, WPB, true, false, false>, WPB * 32, smem, WPB);
-    }
-    return rc;
 }
 
 }  // namespace
@@ -265,10 +130,10 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
     h->K_dB = 10.0 * ple * std::log10(cfg->carrier_freq_GHz * 1e9) + 10.0 * ple * std::log10((4.0 * M_PI) / kSpeedOfLight);
 
     auto bail = [&](int code) { d2d_destroy(h); return code; };
-    cudaError_t e = cudaSetDevice(cfg->cuda_device);
-    if (e != cudaSuccess) return bail(fail(D2D_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e)));
+    D2DDeviceGuard guard(cfg->cuda_device);        // restores the caller's current device on every return path
+    if (guard.err != cudaSuccess) return bail(fail(D2D_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(guard.err)));
     cudaDeviceProp prop{};
-    e = cudaGetDeviceProperties(&prop, cfg->cuda_device);
+    cudaError_t e = cudaGetDeviceProperties(&prop, cfg->cuda_device);
     if (e != cudaSuccess) return bail(fail(D2D_ERR_CUDA, std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e)));
     if (prop.major != 10)
         return bail(fail(D2D_ERR_UNSUPPORTED, "libd2d_b200 is built for sm_100a (Blackwell B200) only; device is sm_" +
@@ -327,10 +192,6 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
         pwr_d[p] = std::pow(10.0, p / 10.0);
         pwr[p] = (float)pwr_d[p];
     }
-    {   // the warp kernel's fp64 pass reads the fp64 table from the constant bank (per device: set at every create)
-        cudaError_t err__ = cudaMemcpyToSymbol(d2d_pwr_lin_c, pwr_d, sizeof(pwr_d));
-        if (err__ != cudaSuccess) return bail(fail(D2D_ERR_CUDA, std::string("cudaMemcpyToSymbol(d2d_pwr_lin_c): ") + cudaGetErrorString(err__)));
-    }
 
 #define D2D_CUDA_BAIL(call)                                                                              \
     do {                                                                                                 \
@@ -350,6 +211,10 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
     D2D_CUDA_BAIL(cudaMemcpy(h->dB, B.data(), sizeof(D2DLinkB) * h->N, cudaMemcpyHostToDevice));
     D2D_CUDA_BAIL(cudaMemcpy(h->dD, Dv.data(), sizeof(D2DLinkD) * h->N, cudaMemcpyHostToDevice));
     D2D_CUDA_BAIL(cudaMemcpy(h->dPwr, pwr, sizeof(pwr), cudaMemcpyHostToDevice));
+    if (cfg->path_loss_model == D2D_PL_SHADOWING) {
+        D2D_CUDA_BAIL(cudaMalloc(&h->dRngStep, sizeof(uint64_t)));
+        D2D_CUDA_BAIL(cudaMemset(h->dRngStep, 0, sizeof(uint64_t)));
+    }
 #undef D2D_CUDA_BAIL
 
     // warp kernel: one lane slot per CUE and per DUE pair, one shared-memory bin per RB
@@ -362,21 +227,25 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
     int rc;
     if (h->use_warp) {
         // launch shape by batch size (d2d_step_warp.cuh): about one wave of envs -> 4-warp blocks, many waves -> 8-warp blocks
-        h->wpb = cfg->num_envs >= 65536 ? 8 : cfg->num_envs <= D2D_LATENCY_ENVS ? 2 : D2D_WPB_MID;
-        if (const char *w = std::getenv("D2D_B200_WPB")) { const int v = std::atoi(w); h->wpb = v == 8 ? 8 : v == 2 ? 2 : D2D_WPB_MID; }
+        h->wpb = cfg->num_envs >= 65536 ? 8 : cfg->num_envs <= D2D_LATENCY_ENVS ? 2 : 4;
+        if (const char *w = std::getenv("D2D_B200_WPB")) { const int v = std::atoi(w); h->wpb = v == 8 ? 8 : v == 2 ? 2 : 4; }
         h->spec = h->ple2 && h->uniform && cfg->path_loss_model != D2D_PL_COST_HATA && cfg->num_rbs == 25 && cfg->num_cues == 25 && cfg->num_due_pairs == 25 && cfg->n_pwr_cue == 24 &&
                   cfg->n_pwr_due == 21;
         if (const char *sp = std::getenv("D2D_B200_SPEC")) h->spec = h->spec && std::atoi(sp) != 0;   // tests: force the generic shape
-        const size_t smem = d2d_warp_smem_bytes(cfg->num_rbs, h->wpb);
-        rc = h->wpb == 8 ? plan_warp<8>(h, smem) : h->wpb == 2 ? plan_warp<2>(h, smem) : plan_warp<D2D_WPB_MID>(h, smem);
+        // the fp64 pass reads 10^(p/10) from the constant bank of the translation unit that holds this shape's kernels
+        // (per device: set at every create)
+        cudaError_t et = h->wpb == 8 ? d2d_warp_tables_8(pwr_d) : h->wpb == 2 ? d2d_warp_tables_2(pwr_d) : d2d_warp_tables_4(pwr_d);
+        if (et != cudaSuccess) return bail(fail(D2D_ERR_CUDA, std::string("cudaMemcpyToSymbol(d2d_pwr_lin_c): ") + cudaGetErrorString(et)));
+        const size_t smem = h->wpb == 8 ? d2d_warp_smem_8(cfg->num_rbs) : h->wpb == 2 ? d2d_warp_smem_2(cfg->num_rbs) : d2d_warp_smem_4(cfg->num_rbs);
+        rc = h->wpb == 8 ? d2d_warp_plan_8(h, smem) : h->wpb == 2 ? d2d_warp_plan_2(h, smem) : d2d_warp_plan_4(h, smem);
     } else {
         // <= 1024 links: the binned one-barrier kernel (d2d_step_dense.cuh), LPT links per thread; when its double-buffered
         // bins do not fit (many RBs) the sorting block kernel; beyond 1024 links / other topologies: everything staged in shared memory
         h->lpt = (h->N <= D2D_BLOCK_THREADS * D2D_BLOCK_MAX_LPT && !general)
                      ? (h->N + D2D_BLOCK_THREADS - 1) / D2D_BLOCK_THREADS : 0;      // downlinks: the general-topology kernel
-        h->bin_cap = d2d_dense_bin_cap(h->N, cfg->num_rbs);
+        h->bin_cap = d2d_dense_bin_cap_host(h->N, cfg->num_rbs);
         const char *dn = std::getenv("D2D_B200_DENSE");
-        bool dense = h->lpt > 0 && d2d_dense_layout(h->N, cfg->num_rbs, h->bin_cap).total <= 72 * 1024 && !(dn && std::atoi(dn) == 0);
+        const bool dense = h->lpt > 0 && d2d_dense_smem(h->N, cfg->num_rbs, h->bin_cap) <= 72 * 1024 && !(dn && std::atoi(dn) == 0);
         if (dense) {
             // threads per block / links per thread: the shape with the fewest (warp, slot) bodies per env - every warp runs the
             // straight-line code of each of its slots whether or not all 32 lanes hold a link (N = 600: 10 warps x 2 slots,
@@ -386,44 +255,47 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
             h->dense_bt = bt;
             h->lpt = (h->N + bt - 1) / bt;
         }
-        const size_t smem = dense ? d2d_dense_layout(h->N, cfg->num_rbs, h->bin_cap).total
-                          : h->lpt ? d2d_block2_smem_bytes(h->N, cfg->num_rbs) : d2d_block_smem_bytes(h->N, cfg->num_rbs);
+        const size_t smem = dense ? d2d_dense_smem(h->N, cfg->num_rbs, h->bin_cap) : d2d_block_smem(h->N, cfg->num_rbs, h->lpt);
         if (smem > 227 * 1024) return bail(fail(D2D_ERR_UNSUPPORTED, "d2d_create: too many links / RBs for one SM's shared memory"));
-#define D2D_PLAN_BLOCK(LPT_) (h->ple2 ? plan_geometry(h, d2d_step_block_kernel<true, LPT_>, D2D_BLOCK_THREADS, smem, 1) \
-                                      : plan_geometry(h, d2d_step_block_kernel<false, LPT_>, D2D_BLOCK_THREADS, smem, 1))
-#define D2D_PLAN_DENSE(LPT_, BT_) (h->ple2 ? plan_dense<true, LPT_, BT_>(h, smem) \
-                                           : plan_dense<false, LPT_, BT_>(h, smem))
-        if (dense) {
-            rc = fail(D2D_ERR_UNSUPPORTED, "d2d_create: no dense kernel instantiation for this shape");
-            D2D_DENSE_SHAPES(D2D_DENSE_PLAN_CASE)
-        } else switch (h->lpt) {
-            case 1: rc = D2D_PLAN_BLOCK(1); break;
-            case 2: rc = D2D_PLAN_BLOCK(2); break;
-            case 3: rc = D2D_PLAN_BLOCK(3); break;
-            case 4: rc = D2D_PLAN_BLOCK(4); break;
-            default:
-                rc = h->ple2 ? plan_geometry(h, d2d_step_block_generic_kernel<true>, D2D_BLOCK_THREADS, smem, 1)
-                             : plan_geometry(h, d2d_step_block_generic_kernel<false>, D2D_BLOCK_THREADS, smem, 1);
-        }
-#undef D2D_PLAN_DENSE
-#undef D2D_PLAN_BLOCK
+        rc = dense ? d2d_dense_plan(h, smem) : d2d_block_plan(h, smem);
     }
     if (rc != D2D_OK) return bail(rc);
+    // CueSinrShannonRewardFunction's post-pass keeps one weak-link counter per RB and team in shared memory
+    if (cfg->reward_fn == D2D_REWARD_CUE_SINR_SHANNON) {
+        const size_t smem = (size_t)(h->N <= 64 ? 8 : 1) * cfg->num_rbs * sizeof(uint32_t);
+        if (smem > 200 * 1024) return bail(fail(D2D_ERR_UNSUPPORTED, "d2d_create: CueSinrShannonRewardFunction supports at most " +
+                                                                         std::to_string(200 * 1024 / 4 / (h->N <= 64 ? 8 : 1)) + " RBs for this link count"));
+        rc = h->N <= 64 ? d2d_allow_smem(d2d_agent_reward_kernel<32>, smem) : d2d_allow_smem(d2d_agent_reward_kernel<256>, smem);
+        if (rc != D2D_OK) return bail(rc);
+    }
     if (const char *gs = std::getenv("D2D_B200_GRID"))      // tests: few blocks, so every block steps many envs
         if (std::atoi(gs) > 0) h->grid = std::min(h->grid, std::atoi(gs));
     *out = h;
     return D2D_OK;
 }
 
+namespace {
+void free_slot(d2d_host_slot &s) {
+    cudaFree(s.dev);
+    if (s.host) cudaFreeHost(s.host);
+    s.dev = s.host = nullptr;
+    s.bytes = s.out_offset = s.out_bytes = 0;
+    s.mask = 0;
+}
+}  // namespace
+
 D2D_API int d2d_destroy(d2d_handle_t *h) {
     if (!h) return D2D_OK;
+    D2DDeviceGuard guard(h->cfg.cuda_device);
     cudaFree(h->dA); cudaFree(h->dB); cudaFree(h->dD); cudaFree(h->dMeta); cudaFree(h->dPwr); cudaFree(h->dPwrD); cudaFree(h->stage_pos);
-    for (auto &slot : h->stage2)
-        for (void *p : slot) cudaFree(p);
-    if (h->pipe_ready) {
-        cudaStreamDestroy(h->s_in); cudaStreamDestroy(h->s_out);
-        for (int s = 0; s < 2; ++s) { cudaEventDestroy(h->ev_in[s]); cudaEventDestroy(h->ev_kernel[s]); cudaEventDestroy(h->ev_out[s]); }
+    cudaFree(h->dRngStep); cudaFree(h->act_scratch);
+    for (auto &s : h->slot) {
+        if (s.used && s.ev_out) cudaEventSynchronize(s.ev_out);
+        free_slot(s);
+        for (void *p : s.stage) cudaFree(p);
+        if (h->pipe_ready) { cudaEventDestroy(s.ev_in); cudaEventDestroy(s.ev_kernel); cudaEventDestroy(s.ev_out); }
     }
+    if (h->pipe_ready) { cudaStreamDestroy(h->s_in); cudaStreamDestroy(h->s_out); }
     delete h;
     return D2D_OK;
 }
@@ -439,6 +311,7 @@ D2D_API int d2d_state_bytes(const d2d_handle_t *h, size_t *pos_bytes, size_t *st
 D2D_API int d2d_bind_state(d2d_handle_t *h, float *positions, uint8_t *step_count, double *stats) {
     if (!h || !positions) return fail(D2D_ERR_INVALID_ARG, "d2d_bind_state: positions buffer is required");
     if ((uintptr_t)positions % 16) return fail(D2D_ERR_INVALID_ARG, "d2d_bind_state: positions must be 16-byte aligned");
+    if (positions != h->pos) h->last_kind = D2D_LAST_OTHER;      // new positions: nothing is known about who wrote them
     h->pos = positions;
     h->step_count = step_count;
     h->stats = stats;
@@ -450,6 +323,7 @@ D2D_API int d2d_bind_positions_f64(d2d_handle_t *h, double *positions_f64) {
     if (positions_f64 && ((uintptr_t)positions_f64 % 16))
         return fail(D2D_ERR_INVALID_ARG, "d2d_bind_positions_f64: buffer must be 16-byte aligned");
     h->pos64 = positions_f64;
+    h->last_kind = D2D_LAST_OTHER;
     return D2D_OK;
 }
 
@@ -460,8 +334,7 @@ D2D_API int d2d_set_positions(d2d_handle_t *h, const double *src, int src_on_dev
     if (first_env < 0 || count < 0 || first_env + count > h->cfg.num_envs)
         return fail(D2D_ERR_INVALID_ARG, "d2d_set_positions: env range out of bounds");
     if (count == 0) return D2D_OK;
-    int rc = ensure_device(h);
-    if (rc) return rc;
+    D2D_GUARD(h);
     cudaStream_t st = (cudaStream_t)stream;
     const double *dsrc = src;
     if (!src_on_device) {
@@ -480,128 +353,57 @@ D2D_API int d2d_set_positions(d2d_handle_t *h, const double *src, int src_on_dev
                                                     h->pos64 ? h->pos64 + first_env * h->V * 2 : nullptr, count, h->V);
     D2D_CUDA(cudaGetLastError());
     ++h->launches;
+    h->last_kind = D2D_LAST_OTHER; h->last_stream = stream;
     if (!src_on_device) D2D_CUDA(cudaStreamSynchronize(st));
     return D2D_OK;
 }
 
-D2D_API int d2d_reset(d2d_handle_t *h, uint64_t seed, uint64_t first_global_env, const uint8_t *env_mask, void *stream) {
-    if (!h) return fail(D2D_ERR_INVALID_ARG, "d2d_reset: null handle");
-    if (!h->pos) return fail(D2D_ERR_STATE, "d2d_reset: call d2d_bind_state first");
-    int rc = ensure_device(h);
-    if (rc) return rc;
-    const int64_t total = h->cfg.num_envs * h->N;
-    const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->num_sms * 16);
-    d2d_reset_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->pos, h->pos64, h->step_count, env_mask, h->cfg.num_envs, h->cfg.num_cues,
-                                                             h->cfg.num_due_pairs, (float)h->cfg.cell_radius_m,
-                                                             (float)h->cfg.d2d_radius_m, seed, first_global_env);
-    D2D_CUDA(cudaGetLastError());
-    ++h->launches;
+D2D_API int d2d_get_positions(d2d_handle_t *h, float *dst, int dst_on_device, int64_t first_env, int64_t count, void *stream) {
+    if (!h || !dst) return fail(D2D_ERR_INVALID_ARG, "d2d_get_positions: null argument");
+    if (!h->pos) return fail(D2D_ERR_STATE, "d2d_get_positions: call d2d_bind_state first");
+    if (first_env < 0 || count < 0 || first_env + count > h->cfg.num_envs)
+        return fail(D2D_ERR_INVALID_ARG, "d2d_get_positions: env range out of bounds");
+    if (count == 0) return D2D_OK;
+    D2D_GUARD(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t row = sizeof(float) * 2 * h->V;
+    D2D_CUDA(cudaMemcpyAsync(dst, h->pos + first_env * h->V * 2, row * count, dst_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    if (!dst_on_device) D2D_CUDA(cudaStreamSynchronize(st));
     return D2D_OK;
 }
 
 namespace {
 
-// One launch (per chunk of envs) that makes T consecutive steps: T == 1 is d2d_step; T > 1 needs the warp kernel.
-int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, void *stream) {
-    D2DParams P = make_params(h, io);
-    P.T = T;
-    P.t_stride = h->cfg.num_envs;
-    cudaStream_t st = (cudaStream_t)stream;
-    const bool many = T > 1;
-    h->rng_calls += (uint64_t)T;
-    // the kernels index with 32 bits: batches beyond 2^31 / (T max(6N, 2V)) envs (> 7 million default envs) go in chunks
-    int64_t chunk = std::max<int64_t>(1, (int64_t)0x7fffffff / std::max(6 * h->N, 2 * h->V));
-    if (many) chunk = h->cfg.num_envs;        // d2d_step_many checked that T slices fit 32-bit indices
-    if (h->chunk_override > 0 && !many) chunk = std::min(chunk, h->chunk_override);
+// Simulator.reset for every env in the mask; `total` units per launch stay below 2^32
+int reset_launch(d2d_handle *h, uint64_t seed, uint64_t first_global_env, const uint8_t *env_mask, cudaStream_t st) {
+    const int C = h->cfg.num_cues, D = h->cfg.num_due_pairs;
+    const int64_t units = (C + 1) / 2 + D;
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)0x7fffffff / std::max<int64_t>(units, 2 * h->V));
     for (int64_t e0 = 0; e0 < h->cfg.num_envs; e0 += chunk) {
         const int64_t n = std::min<int64_t>(chunk, h->cfg.num_envs - e0);
-        if (e0 > 0) {
-            const int64_t dl = chunk * h->N;
-            P.first_global_env += (uint64_t)chunk;
-            P.actions += dl; P.pos += chunk * h->V * 2;
-            if (P.pos64) P.pos64 += chunk * h->V * 2;
-            if (P.step_count) P.step_count += chunk;
-            if (P.obs) P.obs += dl * 6;
-            if (P.cap) P.cap += dl;
-            if (P.reward) P.reward += chunk;
-            if (P.done) P.done += chunk;
-            if (P.rate) P.rate += dl;
-            if (P.rb_out) P.rb_out += dl;
-            if (P.pwr_out) P.pwr_out += dl;
-        }
-        P.num_envs = n;
-#ifdef D2D_TIMELINE
-        P.tl_slot = (int32_t)(h->launches % D2D_TL_SLOTS);
-#endif
-        const int grid = (int)std::min<int64_t>(h->grid, (n + h->envs_per_block - 1) / h->envs_per_block);
-        if (h->use_warp) { const int64_t warps = (int64_t)grid * h->wpb; P.envs_per_warp = (uint32_t)((n + warps - 1) / warps); }
-        const bool exact = h->pos64 != nullptr;
-        cudaError_t err;
-        // FULL: exactly the core outputs were passed, so the kernel tests no output pointer on its hot path
-        const bool full = io->obs && io->capacity_mbps && io->reward && io->done && !io->rate_bps && !io->rb && !io->tx_pwr_dBm &&
-                          h->step_count;
-#define D2D_LAUNCH_WARP(PLE2_, EXACT_, WPB_, FULL_, SPEC_, MANY_) \
-    launch_step(d2d_step_warp_kernel<PLE2_, EXACT_, WPB_, FULL_, SPEC_, MANY_>, grid, WPB_ * 32, h->smem, st, P, h->pdl)
-#define D2D_PICK_FULL(PLE2_, EXACT_, WPB_, SPEC_)                                               \
-    (many ? D2D_LAUNCH_WARP(PLE2_, EXACT_, WPB_, false, SPEC_, true)                             \
-          : full ? D2D_LAUNCH_WARP(PLE2_, EXACT_, WPB_, true, SPEC_, false) : D2D_LAUNCH_WARP(PLE2_, EXACT_, WPB_, false, SPEC_, false))
-#define D2D_PICK_EXACT(PLE2_, WPB_, SPEC_) (exact ? D2D_PICK_FULL(PLE2_, true, WPB_, SPEC_) : D2D_PICK_FULL(PLE2_, false, WPB_, SPEC_))
-#define D2D_PICK_SHAPE(WPB_) \
-    (h->spec ? D2D_PICK_EXACT(true, WPB_, true) : h->ple2 ? D2D_PICK_EXACT(true, WPB_, false) : D2D_PICK_EXACT(false, WPB_, false))
-        if (h->use_warp && h->wpb == 8) {
-            err = D2D_PICK_SHAPE(8);
-        } else if (h->use_warp && h->wpb == 2) {
-            err = D2D_PICK_SHAPE(2);
-        } else if (h->use_warp) {
-            err = D2D_PICK_SHAPE(D2D_WPB_MID);
-        } else {
-#define D2D_LAUNCH_BLOCK(LPT_) (h->ple2 ? launch_step(d2d_step_block_kernel<true, LPT_>, grid, h->block, h->smem, st, P, h->pdl) \
-                                        : launch_step(d2d_step_block_kernel<false, LPT_>, grid, h->block, h->smem, st, P, h->pdl))
-#define D2D_LAUNCH_DENSE4(PLE2_, LPT_, BT_, FULL_, EXACT_) \
-    launch_step(d2d_step_dense_kernel<PLE2_, LPT_, BT_, FULL_, EXACT_>, grid, h->block, h->smem, st, P, h->pdl)
-#define D2D_LAUNCH_DENSE3(PLE2_, LPT_, BT_)                                                                                    \
-    (full && h->uniform ? (exact ? D2D_LAUNCH_DENSE4(PLE2_, LPT_, BT_, true, true) : D2D_LAUNCH_DENSE4(PLE2_, LPT_, BT_, true, false)) \
-                        : (exact ? D2D_LAUNCH_DENSE4(PLE2_, LPT_, BT_, false, true) : D2D_LAUNCH_DENSE4(PLE2_, LPT_, BT_, false, false)))
-#define D2D_LAUNCH_DENSE(LPT_, BT_) (h->ple2 ? D2D_LAUNCH_DENSE3(true, LPT_, BT_) : D2D_LAUNCH_DENSE3(false, LPT_, BT_))
-            if (h->dense_bt) {
-                err = cudaErrorInvalidValue;
-                D2D_DENSE_SHAPES(D2D_DENSE_LAUNCH_CASE)
-            } else
-            switch (h->lpt) {
-                case 1: err = D2D_LAUNCH_BLOCK(1); break;
-                case 2: err = D2D_LAUNCH_BLOCK(2); break;
-                case 3: err = D2D_LAUNCH_BLOCK(3); break;
-                case 4: err = D2D_LAUNCH_BLOCK(4); break;
-                default:
-                    err = h->ple2 ? launch_step(d2d_step_block_generic_kernel<true>, grid, h->block, h->smem, st, P, h->pdl)
-                                  : launch_step(d2d_step_block_generic_kernel<false>, grid, h->block, h->smem, st, P, h->pdl);
-            }
-#undef D2D_LAUNCH_BLOCK
-#undef D2D_LAUNCH_DENSE
-#undef D2D_LAUNCH_DENSE3
-#undef D2D_LAUNCH_DENSE4
-        }
-        if (err != cudaSuccess) return fail(D2D_ERR_CUDA, std::string("step kernel launch: ") + cudaGetErrorString(err));
+        const int64_t total = n * units;
+        const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->num_sms * 16);
+        d2d_reset_kernel<<<grid, 256, 0, st>>>(h->pos + e0 * h->V * 2, h->pos64 ? h->pos64 + e0 * h->V * 2 : nullptr,
+                                               h->step_count ? h->step_count + e0 : nullptr, env_mask ? env_mask + e0 : nullptr,
+                                               (uint32_t)total, (uint32_t)C, (uint32_t)D, (float)h->cfg.cell_radius_m,
+                                               (float)h->cfg.d2d_radius_m, seed, first_global_env + (uint64_t)e0);
+        D2D_CUDA(cudaGetLastError());
         ++h->launches;
     }
-    D2D_CUDA(cudaGetLastError());
-    // per-agent rewards (SHANNON / CUE_SINR_SHANNON always; SYSTEM_CAPACITY when the caller asked for the broadcast): one more
-    // small kernel over the T x E env-steps just written
-    if (h->cfg.reward_fn != D2D_REWARD_SYSTEM_CAPACITY || io->agent_reward) {
-        if (!io->obs || !io->reward)
-            return fail(D2D_ERR_INVALID_ARG, "per-agent rewards need the obs and reward outputs");
-        const int64_t total = (int64_t)T * h->cfg.num_envs;
-        const bool warp_team = h->N <= 64;
-        const int teams = warp_team ? 8 : 1;
-        const int grid = (int)std::min<int64_t>((total + teams - 1) / teams, (int64_t)h->num_sms * 8);
-        const size_t smem = (size_t)teams * h->cfg.num_rbs * sizeof(uint32_t);
-        double *stats = h->cfg.reward_fn != D2D_REWARD_SYSTEM_CAPACITY ? h->stats : nullptr;
-        if (warp_team)
-            d2d_agent_reward_kernel<32><<<grid, 256, smem, st>>>(io->actions, io->obs, io->agent_reward, io->reward, stats, total, h->N,
-                                                                h->dMeta, h->cfg.num_rbs, h->cfg.reward_fn, (float)h->cfg.reward_param);
-        else
-            d2d_agent_reward_kernel<256><<<grid, 256, smem, st>>>(io->actions, io->obs, io->agent_reward, io->reward, stats, total, h->N,
-                                                                 h->dMeta, h->cfg.num_rbs, h->cfg.reward_fn, (float)h->cfg.reward_param);
+    return D2D_OK;
+}
+
+int sample_launch(d2d_handle *h, int32_t *actions, uint64_t seed, uint32_t t, cudaStream_t st) {
+    const int C = h->cfg.num_cues, D = h->cfg.num_due_pairs;
+    const int64_t L = std::max(C, D);
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)0x7fffffff / std::max<int64_t>(L, h->N));
+    for (int64_t e0 = 0; e0 < h->cfg.num_envs; e0 += chunk) {
+        const int64_t n = std::min<int64_t>(chunk, h->cfg.num_envs - e0);
+        const int64_t total = n * L;
+        const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)h->num_sms * 16);
+        d2d_sample_actions_kernel<<<grid, 256, 0, st>>>(actions + e0 * h->N, (uint32_t)total, (uint32_t)C, (uint32_t)D, (uint32_t)h->N,
+                                                        (uint32_t)(h->cfg.num_rbs * h->cfg.n_pwr_cue), (uint32_t)(h->cfg.num_rbs * h->cfg.n_pwr_due),
+                                                        seed, h->cfg.first_global_env + (uint64_t)e0, t);
         D2D_CUDA(cudaGetLastError());
         ++h->launches;
     }
@@ -610,18 +412,157 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, void *stream) {
 
 }  // namespace
 
+D2D_API int d2d_reset(d2d_handle_t *h, uint64_t seed, uint64_t first_global_env, const uint8_t *env_mask, void *stream) {
+    if (!h) return fail(D2D_ERR_INVALID_ARG, "d2d_reset: null handle");
+    if (!h->pos) return fail(D2D_ERR_STATE, "d2d_reset: call d2d_bind_state first");
+    D2D_GUARD(h);
+    h->last_kind = D2D_LAST_OTHER; h->last_stream = stream;
+    return reset_launch(h, seed, first_global_env, env_mask, (cudaStream_t)stream);
+}
+
+D2D_API int d2d_sample_actions(d2d_handle_t *h, int32_t *actions, uint64_t seed, uint32_t step_index, void *stream) {
+    if (!h || !actions) return fail(D2D_ERR_INVALID_ARG, "d2d_sample_actions: null argument");
+    D2D_GUARD(h);
+    h->last_kind = D2D_LAST_OTHER; h->last_stream = stream;      // it writes actions: the next step orders itself the default way
+    return sample_launch(h, actions, seed, step_index, (cudaStream_t)stream);
+}
+
+namespace {
+
+enum { MODE_STEP = 0, MODE_MANY = 1, MODE_EPISODE = 2 };
+
+// per-agent rewards (SHANNON / CUE_SINR_SHANNON always; SYSTEM_CAPACITY when the caller asked for the broadcast): one more
+// small kernel over `total` env-steps of io; `with_stats`: the reward statistics of the per-agent functions
+int agent_reward_launch(d2d_handle *h, const d2d_step_io_t *io, int64_t total, bool with_stats, cudaStream_t st) {
+    if (!io->obs || !io->reward || !io->actions) return fail(D2D_ERR_INVALID_ARG, "per-agent rewards need the actions, obs and reward buffers");
+    const bool warp_team = h->N <= 64;
+    const int teams = warp_team ? 8 : 1;
+    const int grid = (int)std::min<int64_t>((total + teams - 1) / teams, (int64_t)h->num_sms * 8);
+    // only CueSinrShannon keeps per-RB counters in shared memory (opt-in done by d2d_create)
+    const size_t smem = h->cfg.reward_fn == D2D_REWARD_CUE_SINR_SHANNON ? (size_t)teams * h->cfg.num_rbs * sizeof(uint32_t) : 0;
+    double *stats = with_stats && h->cfg.reward_fn != D2D_REWARD_SYSTEM_CAPACITY ? h->stats : nullptr;
+    if (warp_team)
+        d2d_agent_reward_kernel<32><<<grid, 256, smem, st>>>(io->actions, io->obs, io->agent_reward, io->reward, stats, total, h->N,
+                                                            h->dMeta, h->cfg.num_rbs, h->cfg.reward_fn, (float)h->cfg.reward_param);
+    else
+        d2d_agent_reward_kernel<256><<<grid, 256, smem, st>>>(io->actions, io->obs, io->agent_reward, io->reward, stats, total, h->N,
+                                                             h->dMeta, h->cfg.num_rbs, h->cfg.reward_fn, (float)h->cfg.reward_param);
+    D2D_CUDA(cudaGetLastError());
+    ++h->launches;
+    return D2D_OK;
+}
+
+// One launch (per chunk of envs) that makes T consecutive steps: MODE_STEP (T = 1) is d2d_step; MODE_MANY / MODE_EPISODE need
+// the warp kernel (T slices per env; the episode's slice 0 is the uncounted reset step).
+int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, int mode, void *stream, uint64_t ep_seed = 0, uint64_t act_seed = 0,
+                bool draw_actions = false) {
+    D2DParams P = make_params(h, io);
+    P.T = T;
+    P.t_stride = h->cfg.num_envs;
+    P.ep_seed = ep_seed; P.act_seed = act_seed;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool many = mode != MODE_STEP;
+    // "Ordering rule" of include/d2d_b200.h: inputs may be read ahead of griddepcontrol.wait only on the caller's promise AND when
+    // the kernel before this one (for this handle, in this stream) was a step kernel, which writes neither actions nor positions.
+    // An episode that draws its own actions reads no input at all.
+    bool stable = h->pdl && h->last_stream == stream;
+    if (mode == MODE_EPISODE && draw_actions) stable = h->pdl;
+    else if (mode == MODE_EPISODE) stable = stable && (io->flags & D2D_STEP_INPUTS_STABLE) && h->last_kind != D2D_LAST_OTHER;
+    else stable = stable && (io->flags & D2D_STEP_INPUTS_STABLE) && h->last_kind == D2D_LAST_STEP;
+    P.flags = (stable ? 0u : D2D_PF_INPUTS_FRESH) | (draw_actions ? D2D_PF_DRAW_ACTIONS : 0u);
+    // the kernels index with 32 bits: batches beyond 2^31 / (T max(6N, 2V)) envs (> 7 million default envs) go in chunks
+    int64_t chunk = std::max<int64_t>(1, (int64_t)0x7fffffff / std::max(6 * h->N, 2 * h->V));
+    if (many) chunk = h->cfg.num_envs;        // the callers checked that T slices fit 32-bit indices
+    if (h->chunk_override > 0 && !many) chunk = std::min(chunk, h->chunk_override);
+    for (int64_t e0 = 0; e0 < h->cfg.num_envs; e0 += chunk) {
+        const int64_t n = std::min<int64_t>(chunk, h->cfg.num_envs - e0);
+        if (e0 > 0) {
+            const int64_t dl = chunk * h->N;
+            P.first_global_env += (uint64_t)chunk;
+            P.actions += dl; P.pos += chunk * h->V * 2; P.pos_out += chunk * h->V * 2;
+            if (P.pos64) P.pos64 += chunk * h->V * 2;
+            if (P.step_count) P.step_count += chunk;
+            if (P.obs) P.obs += dl * 6;
+            if (P.obs_dyn) P.obs_dyn += dl;
+            if (P.cap) P.cap += dl;
+            if (P.reward) P.reward += chunk;
+            if (P.done) P.done += chunk;
+            if (P.rate) P.rate += dl;
+            if (P.rb_out) P.rb_out += dl;
+            if (P.pwr_out) P.pwr_out += dl;
+            // a later chunk of the same step follows a kernel that passed its wait (or was itself entitled to skip it)
+            if (h->pdl) P.flags &= ~D2D_PF_INPUTS_FRESH;
+        }
+        P.num_envs = n;
+#ifdef D2D_TIMELINE
+        P.tl_slot = (int32_t)(h->launches % D2D_TL_SLOTS);
+#endif
+        const int grid = (int)std::min<int64_t>(h->grid, (n + h->envs_per_block - 1) / h->envs_per_block);
+        if (h->use_warp) { const int64_t warps = (int64_t)grid * h->wpb; P.envs_per_warp = (uint32_t)((n + warps - 1) / warps); }
+        D2DLaunchSel sel;
+        sel.many = mode == MODE_MANY; sel.episode = mode == MODE_EPISODE;
+        sel.exact = h->pos64 != nullptr;
+        // FULL: exactly the core outputs were passed, so the kernel tests no output pointer on its hot path
+        sel.full = io->obs && io->capacity_mbps && io->reward && io->done && !io->rate_bps && !io->rb && !io->tx_pwr_dBm && !io->obs_dyn &&
+                   h->step_count && h->cfg.reward_fn == D2D_REWARD_SYSTEM_CAPACITY;
+        cudaError_t err;
+        if (h->use_warp) err = h->wpb == 8 ? d2d_warp_launch_8(h, P, grid, sel, st, h->pdl) : h->wpb == 2 ? d2d_warp_launch_2(h, P, grid, sel, st, h->pdl)
+                                                                                                       : d2d_warp_launch_4(h, P, grid, sel, st, h->pdl);
+        else if (h->dense_bt) err = d2d_dense_launch(h, P, grid, sel, st, h->pdl);
+        else err = d2d_block_launch(h, P, grid, st, h->pdl);
+        if (err != cudaSuccess) return fail(D2D_ERR_CUDA, std::string("step kernel launch: ") + cudaGetErrorString(err));
+        ++h->launches;
+    }
+    D2D_CUDA(cudaGetLastError());
+    h->last_stream = stream;
+    h->last_kind = mode == MODE_EPISODE ? D2D_LAST_EPISODE : D2D_LAST_STEP;
+    if (h->dRngStep) {      // ShadowingPathLoss: the next call draws fresh values, also when this one is replayed from a CUDA graph
+        d2d_advance_counter_kernel<<<1, 1, 0, st>>>(h->dRngStep, (uint64_t)T);
+        D2D_CUDA(cudaGetLastError());
+    }
+    if (mode != MODE_EPISODE && (h->cfg.reward_fn != D2D_REWARD_SYSTEM_CAPACITY || io->agent_reward))
+        return agent_reward_launch(h, io, (int64_t)T * h->cfg.num_envs, true, st);
+    return D2D_OK;
+}
+
+int check_step_args(const d2d_handle_t *h, const d2d_step_io_t *io, const char *who, bool need_actions = true) {
+    if (!h || !io || (need_actions && !io->actions)) return fail(D2D_ERR_INVALID_ARG, std::string(who) + ": handle, io and io->actions are required");
+    if (!h->pos) return fail(D2D_ERR_STATE, std::string(who) + ": call d2d_bind_state first");
+    if (io->obs && ((uintptr_t)io->obs % 8)) return fail(D2D_ERR_INVALID_ARG, std::string(who) + ": obs must be 8-byte aligned");
+    if (io->obs_dyn && ((uintptr_t)io->obs_dyn % 8)) return fail(D2D_ERR_INVALID_ARG, std::string(who) + ": obs_dyn must be 8-byte aligned");
+    return D2D_OK;
+}
+
+// io advanced by `steps` slices of E envs
+void advance_io(d2d_step_io_t &cur, int64_t steps, int64_t E, int N) {
+    const int64_t dl = steps * E * N, de = steps * E;
+    if (cur.actions) cur.actions += dl;
+    if (cur.obs) cur.obs += dl * 6;
+    if (cur.obs_dyn) cur.obs_dyn += dl * 2;
+    if (cur.capacity_mbps) cur.capacity_mbps += dl;
+    if (cur.reward) cur.reward += de;
+    if (cur.done) cur.done += de;
+    if (cur.rate_bps) cur.rate_bps += dl;
+    if (cur.rb) cur.rb += dl;
+    if (cur.tx_pwr_dBm) cur.tx_pwr_dBm += dl;
+    if (cur.agent_reward) cur.agent_reward += dl;
+    if (cur.actions_out) cur.actions_out += dl;
+}
+
+}  // namespace
+
 D2D_API int d2d_step(d2d_handle_t *h, const d2d_step_io_t *io, void *stream) {
-    if (!h || !io || !io->actions) return fail(D2D_ERR_INVALID_ARG, "d2d_step: handle, io and io->actions are required");
-    if (!h->pos) return fail(D2D_ERR_STATE, "d2d_step: call d2d_bind_state first");
-    if (io->obs && ((uintptr_t)io->obs % 8)) return fail(D2D_ERR_INVALID_ARG, "d2d_step: obs must be 8-byte aligned");
-    return step_launch(h, io, 1, stream);
+    int rc = check_step_args(h, io, "d2d_step");
+    if (rc) return rc;
+    D2D_GUARD(h);
+    return step_launch(h, io, 1, MODE_STEP, stream);
 }
 
 D2D_API int d2d_step_many(d2d_handle_t *h, const d2d_step_io_t *io, int32_t num_steps, void *stream) {
-    if (!h || !io || !io->actions) return fail(D2D_ERR_INVALID_ARG, "d2d_step_many: handle, io and io->actions are required");
-    if (!h->pos) return fail(D2D_ERR_STATE, "d2d_step_many: call d2d_bind_state first");
+    int rc = check_step_args(h, io, "d2d_step_many");
+    if (rc) return rc;
     if (num_steps < 1) return fail(D2D_ERR_INVALID_ARG, "d2d_step_many: num_steps must be >= 1");
-    if (io->obs && ((uintptr_t)io->obs % 8)) return fail(D2D_ERR_INVALID_ARG, "d2d_step_many: obs must be 8-byte aligned");
+    D2D_GUARD(h);
     const int64_t E = h->cfg.num_envs, per_env = std::max(6 * h->N, 2 * h->V);
     // fused launches of as many steps as 32-bit indices allow (all of them unless T E N is astronomically large);
     // configurations served by the block kernel take one launch per step
@@ -630,18 +571,72 @@ D2D_API int d2d_step_many(d2d_handle_t *h, const d2d_step_io_t *io, int32_t num_
     d2d_step_io_t cur = *io;
     for (int64_t t0 = 0; t0 < num_steps; t0 += fuse) {
         const int T = (int)std::min<int64_t>(fuse, num_steps - t0);
-        int rc = step_launch(h, &cur, T, stream);
+        rc = step_launch(h, &cur, T, T > 1 ? MODE_MANY : MODE_STEP, stream);
         if (rc) return rc;
-        const int64_t dl = (int64_t)T * E * h->N, de = (int64_t)T * E;
-        cur.actions += dl;
-        if (cur.obs) cur.obs += dl * 6;
-        if (cur.capacity_mbps) cur.capacity_mbps += dl;
-        if (cur.reward) cur.reward += de;
-        if (cur.done) cur.done += de;
-        if (cur.rate_bps) cur.rate_bps += dl;
-        if (cur.rb) cur.rb += dl;
-        if (cur.tx_pwr_dBm) cur.tx_pwr_dBm += dl;
-        if (cur.agent_reward) cur.agent_reward += dl;
+        advance_io(cur, T, E, h->N);
+    }
+    return D2D_OK;
+}
+
+D2D_API int d2d_episode(d2d_handle_t *h, const d2d_step_io_t *io, int32_t num_steps, uint64_t reset_seed, uint64_t action_seed,
+                        uint32_t episode_flags, void *stream) {
+    const bool draw = (episode_flags & D2D_EPISODE_DRAW_ACTIONS) != 0u;
+    int rc = check_step_args(h, io, "d2d_episode", !draw);
+    if (rc) return rc;
+    if (num_steps < 0 || num_steps > 254) return fail(D2D_ERR_INVALID_ARG, "d2d_episode: num_steps must be in [0, 254]");
+    if (!h->step_count) return fail(D2D_ERR_STATE, "d2d_episode: a step-counter buffer must be bound");
+    D2D_GUARD(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t E = h->cfg.num_envs, per_env = std::max(6 * h->N, 2 * h->V);
+    const int T1 = num_steps + 1;
+    const bool agent_pass = h->cfg.reward_fn != D2D_REWARD_SYSTEM_CAPACITY || io->agent_reward;
+    d2d_step_io_t cur = *io;
+    const bool fused = h->use_warp && (int64_t)T1 * E * per_env <= (int64_t)0x7fffffff;
+    // the per-agent reward pass and the composed path read the actions back: record drawn ones in handle-owned scratch
+    if (draw && !cur.actions_out && (agent_pass || !fused)) {
+        const size_t need = (size_t)(fused ? T1 : 1) * E * h->N;
+        if (h->act_scratch_elems < need) {
+            D2D_CUDA(cudaStreamSynchronize(st));
+            cudaFree(h->act_scratch);
+            h->act_scratch = nullptr; h->act_scratch_elems = 0;
+            D2D_CUDA(cudaMalloc(&h->act_scratch, need * sizeof(int32_t)));
+            h->act_scratch_elems = need;
+        }
+    }
+    if (fused) {
+        if (draw && !cur.actions_out && agent_pass) cur.actions_out = h->act_scratch;
+        rc = step_launch(h, &cur, T1, MODE_EPISODE, stream, reset_seed, action_seed, draw);
+        if (rc) return rc;
+        if (agent_pass) {
+            if (draw) cur.actions = cur.actions_out;
+            rc = agent_reward_launch(h, &cur, E, false, st);                    // slice 0: the reset step enters no statistic
+            if (rc || num_steps == 0) return rc;
+            advance_io(cur, 1, E, h->N);
+            return agent_reward_launch(h, &cur, (int64_t)num_steps * E, true, st);
+        }
+        return D2D_OK;
+    }
+    // composed: d2d_reset, then per slice d2d_sample_actions (when drawing) + d2d_step; the reset step is not counted
+    h->last_kind = D2D_LAST_OTHER; h->last_stream = stream;
+    rc = reset_launch(h, reset_seed, h->cfg.first_global_env, nullptr, st);
+    if (rc) return rc;
+    uint8_t *counters = h->step_count;
+    double *stats = h->stats;
+    for (int t = 0; t < T1; ++t) {
+        d2d_step_io_t one = cur;
+        one.actions_out = nullptr;
+        if (draw) {
+            int32_t *dst = cur.actions_out ? cur.actions_out : h->act_scratch;
+            rc = sample_launch(h, dst, action_seed, (uint32_t)t, st);
+            if (rc) return rc;
+            one.actions = dst;
+            h->last_kind = D2D_LAST_OTHER;
+        }
+        if (t == 0) { h->step_count = nullptr; h->stats = nullptr; }          // envs/d2d_env.py:50: simulator.step, no num_steps += 1
+        rc = step_launch(h, &one, 1, MODE_STEP, stream);
+        h->step_count = counters; h->stats = stats;
+        if (rc) return rc;
+        advance_io(cur, 1, E, h->N);
     }
     return D2D_OK;
 }
@@ -653,67 +648,132 @@ int host_pipeline_init(d2d_handle *h) {
     if (h->pipe_ready) return D2D_OK;
     D2D_CUDA(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     D2D_CUDA(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
-    for (int s = 0; s < 2; ++s) {
-        D2D_CUDA(cudaEventCreateWithFlags(&h->ev_in[s], cudaEventDisableTiming));
-        D2D_CUDA(cudaEventCreateWithFlags(&h->ev_kernel[s], cudaEventDisableTiming));
-        D2D_CUDA(cudaEventCreateWithFlags(&h->ev_out[s], cudaEventDisableTiming));
+    for (auto &s : h->slot) {
+        D2D_CUDA(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
+        D2D_CUDA(cudaEventCreateWithFlags(&s.ev_kernel, cudaEventDisableTiming));
+        D2D_CUDA(cudaEventCreateWithFlags(&s.ev_out, cudaEventDisableTiming));
     }
     h->pipe_ready = true;
     return D2D_OK;
 }
 
+// the buffers of a d2d_step_io_t in a fixed order: actions, then the outputs
+struct IoField { void *d2d_step_io_t::*dummy; };
+void io_pointers(const d2d_step_io_t *io, void *out[D2D_NUM_IO_BUFFERS]) {
+    out[0] = (void *)io->actions; out[1] = io->obs; out[2] = io->obs_dyn; out[3] = io->capacity_mbps; out[4] = io->reward;
+    out[5] = io->done; out[6] = io->rate_bps; out[7] = io->rb; out[8] = io->tx_pwr_dBm; out[9] = io->agent_reward;
+}
+void io_from_pointers(void *const p[D2D_NUM_IO_BUFFERS], d2d_step_io_t *io) {
+    io->actions = (const int32_t *)p[0]; io->obs = (float *)p[1]; io->obs_dyn = (float *)p[2]; io->capacity_mbps = (float *)p[3];
+    io->reward = (float *)p[4]; io->done = (uint8_t *)p[5]; io->rate_bps = (float *)p[6]; io->rb = (int16_t *)p[7];
+    io->tx_pwr_dBm = (int16_t *)p[8]; io->agent_reward = (float *)p[9];
+}
+void io_sizes(const d2d_handle *h, size_t bytes[D2D_NUM_IO_BUFFERS]) {
+    const size_t E = (size_t)h->cfg.num_envs, EN = E * h->N;
+    const size_t b[D2D_NUM_IO_BUFFERS] = {EN * 4, EN * 24, EN * 8, EN * 4, E * 4, E, EN * 4, EN * 2, EN * 2, EN * 4};
+    std::memcpy(bytes, b, sizeof(b));
+}
+const uint32_t kIoMask[D2D_NUM_IO_BUFFERS] = {0u, D2D_OUT_OBS, D2D_OUT_OBS_DYN, D2D_OUT_CAPACITY, D2D_OUT_REWARD, D2D_OUT_DONE,
+                                              D2D_OUT_RATE, D2D_OUT_RB, D2D_OUT_TX_PWR, D2D_OUT_AGENT_REWARD};
+
 }  // namespace
+
+D2D_API int d2d_host_slot_buffers(d2d_handle_t *h, int slot, uint32_t outputs, d2d_step_io_t *host_io) {
+    if (!h || !host_io || slot < 0 || slot > 1) return fail(D2D_ERR_INVALID_ARG, "d2d_host_slot_buffers: bad handle, slot or io");
+    if (!(outputs & (D2D_OUT_OBS | D2D_OUT_OBS_DYN | D2D_OUT_CAPACITY | D2D_OUT_REWARD | D2D_OUT_DONE | D2D_OUT_RATE | D2D_OUT_RB |
+                     D2D_OUT_TX_PWR | D2D_OUT_AGENT_REWARD)))
+        return fail(D2D_ERR_INVALID_ARG, "d2d_host_slot_buffers: empty output mask");
+    D2D_GUARD(h);
+    int rc = host_pipeline_init(h);
+    if (rc) return rc;
+    d2d_host_slot &s = h->slot[slot];
+    if (s.host && s.mask == outputs) { *host_io = s.host_io; return D2D_OK; }
+    if (s.used) D2D_CUDA(cudaEventSynchronize(s.ev_out));
+    free_slot(s);
+    size_t bytes[D2D_NUM_IO_BUFFERS], off[D2D_NUM_IO_BUFFERS] = {}, total = 0;
+    io_sizes(h, bytes);
+    auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    total = align(bytes[0]);
+    s.out_offset = total;
+    for (int i = 1; i < D2D_NUM_IO_BUFFERS; ++i)
+        if (outputs & kIoMask[i]) { off[i] = total; total = align(total + bytes[i]); }
+    s.out_bytes = total - s.out_offset;
+    D2D_CUDA(cudaMalloc(&s.dev, total));
+    D2D_CUDA(cudaHostAlloc(&s.host, total, cudaHostAllocDefault));
+    std::memset(s.host, 0, total);
+    s.bytes = total; s.mask = outputs;
+    void *hp[D2D_NUM_IO_BUFFERS] = {}, *dp[D2D_NUM_IO_BUFFERS] = {};
+    hp[0] = s.host; dp[0] = s.dev;
+    for (int i = 1; i < D2D_NUM_IO_BUFFERS; ++i)
+        if (outputs & kIoMask[i]) { hp[i] = (char *)s.host + off[i]; dp[i] = (char *)s.dev + off[i]; }
+    s.host_io = d2d_step_io_t{}; s.dev_io = d2d_step_io_t{};
+    io_from_pointers(hp, &s.host_io);
+    io_from_pointers(dp, &s.dev_io);
+    *host_io = s.host_io;
+    return D2D_OK;
+}
 
 D2D_API int d2d_step_host_async(d2d_handle_t *h, const d2d_step_io_t *hio, int slot, void *stream) {
     if (!h || !hio || !hio->actions) return fail(D2D_ERR_INVALID_ARG, "d2d_step_host_async: handle, io and io->actions are required");
     if (slot < 0 || slot > 1) return fail(D2D_ERR_INVALID_ARG, "d2d_step_host_async: slot must be 0 or 1");
     if (!h->pos) return fail(D2D_ERR_STATE, "d2d_step_host_async: call d2d_bind_state first");
-    int rc = ensure_device(h);
+    D2D_GUARD(h);
+    int rc = host_pipeline_init(h);
     if (rc) return rc;
-    rc = host_pipeline_init(h);
-    if (rc) return rc;
-    const size_t E = (size_t)h->cfg.num_envs, EN = E * h->N;
-    const size_t bytes[9] = {EN * 4, EN * 24, EN * 4, E * 4, E, EN * 4, EN * 2, EN * 2, EN * 4};
-    void *host[9] = {(void *)hio->actions, hio->obs, hio->capacity_mbps, hio->reward, hio->done, hio->rate_bps, hio->rb, hio->tx_pwr_dBm,
-                     hio->agent_reward};
-    void **stage = h->stage2[slot];
-    for (int i = 0; i < 9; ++i)
-        if (host[i] && !stage[i]) D2D_CUDA(cudaMalloc(&stage[i], bytes[i]));
+    d2d_host_slot &s = h->slot[slot];
     cudaStream_t st = (cudaStream_t)stream;
+    size_t bytes[D2D_NUM_IO_BUFFERS];
+    io_sizes(h, bytes);
+    void *host[D2D_NUM_IO_BUFFERS], *mine[D2D_NUM_IO_BUFFERS];
+    io_pointers(hio, host);
+    io_pointers(&s.host_io, mine);
+    // the slot's own pinned output buffers (d2d_host_slot_buffers): ONE copy back for all of them; the actions may come from
+    // the slot's pinned action buffer or from any other host buffer of the caller's (a ring of pre-filled ones, say)
+    const bool packed = s.host && std::memcmp(host + 1, mine + 1, sizeof(host) - sizeof(host[0])) == 0;
+    d2d_step_io_t dio{};
+    if (packed) dio = s.dev_io;
+    else {
+        void *dp[D2D_NUM_IO_BUFFERS] = {};
+        for (int i = 0; i < D2D_NUM_IO_BUFFERS; ++i) {
+            if (host[i] && !s.stage[i]) D2D_CUDA(cudaMalloc(&s.stage[i], bytes[i]));
+            dp[i] = host[i] ? s.stage[i] : nullptr;
+        }
+        io_from_pointers(dp, &dio);
+    }
+    // the actions arrive by a copy on another stream: never D2D_STEP_INPUTS_STABLE
+    dio.flags = 0;
     // copy-in: this slot's action staging is free once the kernel that last read it has run
-    if (h->slot_used[slot]) D2D_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_kernel[slot], 0));
-    D2D_CUDA(cudaMemcpyAsync(stage[0], host[0], bytes[0], cudaMemcpyHostToDevice, h->s_in));
-    D2D_CUDA(cudaEventRecord(h->ev_in[slot], h->s_in));
+    if (s.used) D2D_CUDA(cudaStreamWaitEvent(h->s_in, s.ev_kernel, 0));
+    D2D_CUDA(cudaMemcpyAsync((void *)dio.actions, host[0], bytes[0], cudaMemcpyHostToDevice, h->s_in));
+    D2D_CUDA(cudaEventRecord(s.ev_in, h->s_in));
     // kernel on the caller's stream (steps stay ordered there): needs the actions in, and this slot's previous
     // outputs copied out
-    D2D_CUDA(cudaStreamWaitEvent(st, h->ev_in[slot], 0));
-    if (h->slot_used[slot]) D2D_CUDA(cudaStreamWaitEvent(st, h->ev_out[slot], 0));
-    d2d_step_io_t dio{};
-    dio.actions = (const int32_t *)stage[0];
-    dio.obs = hio->obs ? (float *)stage[1] : nullptr;
-    dio.capacity_mbps = hio->capacity_mbps ? (float *)stage[2] : nullptr;
-    dio.reward = hio->reward ? (float *)stage[3] : nullptr;
-    dio.done = hio->done ? (uint8_t *)stage[4] : nullptr;
-    dio.rate_bps = hio->rate_bps ? (float *)stage[5] : nullptr;
-    dio.rb = hio->rb ? (int16_t *)stage[6] : nullptr;
-    dio.tx_pwr_dBm = hio->tx_pwr_dBm ? (int16_t *)stage[7] : nullptr;
-    dio.agent_reward = hio->agent_reward ? (float *)stage[8] : nullptr;
-    rc = d2d_step(h, &dio, stream);
+    D2D_CUDA(cudaStreamWaitEvent(st, s.ev_in, 0));
+    if (s.used) D2D_CUDA(cudaStreamWaitEvent(st, s.ev_out, 0));
+    rc = check_step_args(h, &dio, "d2d_step_host_async");
+    if (!rc) rc = step_launch(h, &dio, 1, MODE_STEP, stream);
     if (rc) return rc;
-    D2D_CUDA(cudaEventRecord(h->ev_kernel[slot], st));
+    D2D_CUDA(cudaEventRecord(s.ev_kernel, st));
     // copy-out
-    D2D_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_kernel[slot], 0));
-    for (int i = 1; i < 9; ++i)
-        if (host[i]) D2D_CUDA(cudaMemcpyAsync(host[i], stage[i], bytes[i], cudaMemcpyDeviceToHost, h->s_out));
-    D2D_CUDA(cudaEventRecord(h->ev_out[slot], h->s_out));
-    h->slot_used[slot] = true;
+    D2D_CUDA(cudaStreamWaitEvent(h->s_out, s.ev_kernel, 0));
+    if (packed) {
+        D2D_CUDA(cudaMemcpyAsync((char *)s.host + s.out_offset, (char *)s.dev + s.out_offset, s.out_bytes, cudaMemcpyDeviceToHost, h->s_out));
+    } else {
+        void *dp[D2D_NUM_IO_BUFFERS];
+        io_pointers(&dio, dp);
+        for (int i = 1; i < D2D_NUM_IO_BUFFERS; ++i)
+            if (host[i]) D2D_CUDA(cudaMemcpyAsync(host[i], dp[i], bytes[i], cudaMemcpyDeviceToHost, h->s_out));
+    }
+    D2D_CUDA(cudaEventRecord(s.ev_out, h->s_out));
+    s.used = true;
     return D2D_OK;
 }
 
 D2D_API int d2d_step_host_wait(d2d_handle_t *h, int slot) {
     if (!h || slot < 0 || slot > 1) return fail(D2D_ERR_INVALID_ARG, "d2d_step_host_wait: bad handle or slot");
-    if (!h->slot_used[slot]) return D2D_OK;
-    D2D_CUDA(cudaEventSynchronize(h->ev_out[slot]));
+    if (!h->slot[slot].used) return D2D_OK;
+    D2D_GUARD(h);
+    D2D_CUDA(cudaEventSynchronize(h->slot[slot].ev_out));
     return D2D_OK;
 }
 
@@ -728,6 +788,7 @@ D2D_API int d2d_per_agent_obs(d2d_handle_t *h, const float *table, float *out, i
     if (num_envs < 0 || num_envs > h->cfg.num_envs) return fail(D2D_ERR_INVALID_ARG, "d2d_per_agent_obs: bad num_envs");
     if (num_envs == 0) return D2D_OK;
     if (num_envs * h->N > 0x7fffffffLL) return fail(D2D_ERR_UNSUPPORTED, "d2d_per_agent_obs: num_envs * N exceeds the grid limit");
+    D2D_GUARD(h);
     d2d_per_agent_obs_kernel<<<(unsigned)(num_envs * h->N), 128, 0, (cudaStream_t)stream>>>(table, out, h->N);
     D2D_CUDA(cudaGetLastError());
     ++h->launches;
@@ -737,6 +798,7 @@ D2D_API int d2d_per_agent_obs(d2d_handle_t *h, const float *table, float *out, i
 D2D_API int d2d_stats_reset(d2d_handle_t *h, void *stream) {
     if (!h) return fail(D2D_ERR_INVALID_ARG, "d2d_stats_reset: null handle");
     if (!h->stats) return fail(D2D_ERR_STATE, "d2d_stats_reset: no stats buffer bound");
+    D2D_GUARD(h);
     D2D_CUDA(cudaMemsetAsync(h->stats, 0, (size_t)D2D_STATS_REPLICAS * 8 * sizeof(double), (cudaStream_t)stream));
     return D2D_OK;
 }
@@ -760,4 +822,3 @@ D2D_API int d2d_step_geometry(const d2d_handle_t *h, int32_t *grid, int32_t *blo
     if (envs_per_block) *envs_per_block = h->envs_per_block;
     return D2D_OK;
 }
-

@@ -18,56 +18,64 @@ __global__ void d2d_set_positions_kernel(const double *__restrict__ src, float *
     }
 }
 
-// uniform-in-disc draw (position.py:24-28): theta = 2 pi u1, r = radius sqrt(u2)
-__device__ __forceinline__ float2 d2d_disc_draw(uint64_t seed, uint64_t genv, uint32_t dev, uint32_t attempt, float radius) {
-    const uint4 o = d2d_philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32), dev, attempt),
-                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-    // 24-bit uniforms centred in their cell, so u is never 0 (r = 0 would put a receiver on its transmitter)
-    const float u1 = ((float)(o.x >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = ((float)(o.y >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    float s, c;
-    sincospif(2.0f * u1, &s, &c);
-    const float r = radius * sqrtf(u2);
-    return make_float2(r * c, r * s);
-}
-
-// Simulator.reset (simulator.py:61-75): one thread per (env, link slot); a DUE thread draws its tx in
-// the cell and re-draws its rx around the tx until it falls inside the cell (position.py:31-45).
+// Simulator.reset (simulator.py:61-75): one thread per (env, draw unit) - a pair of CUEs or one DUE pair, one Philox block each
+// (d2d_common.cuh) - writing 16 bytes; a DUE unit re-draws its receiver around the transmitter until it falls inside the cell
+// (position.py:31-45).  units = ceil(C / 2) + D per env; `total` = num_envs * units < 2^32 per launch (the host chunks).
 __global__ void d2d_reset_kernel(float *__restrict__ pos, double *__restrict__ pos64, uint8_t *__restrict__ step_count,
-                                 const uint8_t *__restrict__ env_mask, int64_t num_envs, int C, int D, float cell_radius,
+                                 const uint8_t *__restrict__ env_mask, uint32_t total, uint32_t C, uint32_t D, float cell_radius,
                                  float d2d_radius, uint64_t seed, uint64_t first_global_env) {
-    const int N = C + D, V = 1 + C + 2 * D;
-    const int64_t total = num_envs * N;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t e = i / N;
-        const int j = (int)(i - e * N);
+    const uint32_t CU = (C + 1u) >> 1, U = CU + D, V = 1u + C + 2u * D;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t e = i / U, u = i - e * U;
         if (env_mask && !env_mask[e]) continue;
-        float2 *pe = reinterpret_cast<float2 *>(pos) + e * V;
+        float2 *pe = reinterpret_cast<float2 *>(pos) + (uint64_t)e * V;
+        double2 *pe64 = pos64 ? reinterpret_cast<double2 *>(pos64) + (uint64_t)e * V : nullptr;
         const uint64_t g = first_global_env + (uint64_t)e;
-        double2 *pe64 = pos64 ? reinterpret_cast<double2 *>(pos64) + e * V : nullptr;
-        if (j == 0) {
+        if (u == 0u) {
             pe[0] = make_float2(0.f, 0.f);                       // simulator.py:63-64
             if (pe64) pe64[0] = make_double2(0.0, 0.0);
             if (step_count) step_count[e] = 0;                   // envs/d2d_env.py:46
         }
-        if (j < C) {
-            const float2 c = d2d_disc_draw(seed, g, (uint32_t)(1 + j), 0, cell_radius);
-            pe[1 + j] = c;
-            if (pe64) pe64[1 + j] = make_double2((double)c.x, (double)c.y);
-        } else {
-            const int t = 1 + C + 2 * (j - C);
-            const float2 tx = d2d_disc_draw(seed, g, (uint32_t)t, 0, cell_radius);
-            float2 rx = tx;
-            for (uint32_t a = 0; a < 64; ++a) {
-                const float2 o = d2d_disc_draw(seed, g, (uint32_t)(t + 1), a, d2d_radius);
-                rx = make_float2(tx.x + o.x, tx.y + o.y);
-                if (fmaf(rx.x, rx.x, rx.y * rx.y) <= cell_radius * cell_radius) break;
+        if (u < CU) {
+            const uint4 b = d2d_reset_block(seed, g, u, 0u);
+            const uint32_t j = 2u * u;
+            const float2 c0 = d2d_disc_from_words(b.x, b.y, cell_radius);
+            pe[1u + j] = c0;
+            if (pe64) pe64[1u + j] = make_double2((double)c0.x, (double)c0.y);
+            if (j + 1u < C) {
+                const float2 c1 = d2d_disc_from_words(b.z, b.w, cell_radius);
+                pe[2u + j] = c1;
+                if (pe64) pe64[2u + j] = make_double2((double)c1.x, (double)c1.y);
             }
-            pe[t] = tx;
-            pe[t + 1] = rx;
-            if (pe64) { pe64[t] = make_double2((double)tx.x, (double)tx.y); pe64[t + 1] = make_double2((double)rx.x, (double)rx.y); }
+        } else {
+            const uint32_t d = u - CU, t = 1u + C + 2u * d;
+            const float4 p = d2d_draw_due(seed, g, CU, d, cell_radius, d2d_radius);
+            if ((((uintptr_t)(pe + t)) & 15u) == 0u) *reinterpret_cast<float4 *>(pe + t) = p;
+            else { pe[t] = make_float2(p.x, p.y); pe[t + 1u] = make_float2(p.z, p.w); }
+            if (pe64) { pe64[t] = make_double2((double)p.x, (double)p.y); pe64[t + 1u] = make_double2((double)p.z, (double)p.w); }
         }
     }
 }
+
+// Discrete(n).sample() for every agent of every env (envs/d2d_env.py:54-60), step index t of the episode (0 = the reset step):
+// the same draws the EPISODE instantiation of the warp kernel makes in registers (d2d_common.cuh).  One thread per (env, pair
+// index l): CUE l and DUE pair l share a Philox block.  Links beyond the uplinks and sidelinks (DOWNLINK 'mbs:cueXX', never
+// sampled by the reference's reset) are marked absent (-1).
+__global__ void d2d_sample_actions_kernel(int32_t *__restrict__ actions, uint32_t total, uint32_t C, uint32_t D, uint32_t N,
+                                          uint32_t n_cue, uint32_t n_due, uint64_t act_seed, uint64_t first_global_env, uint32_t t) {
+    const uint32_t L = max(C, D), X = N - C - D;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t e = i / L, l = i - e * L;
+        const uint4 b = d2d_action_block(act_seed, first_global_env + (uint64_t)e, l, t);
+        int32_t *a = actions + (uint64_t)e * N;
+        if (l < C) a[l] = (int32_t)__umulhi(d2d_action_word(b, t, false), n_cue);
+        if (l < D) a[C + l] = (int32_t)__umulhi(d2d_action_word(b, t, true), n_due);
+        if (l < X) a[C + D + l] = -1;
+    }
+}
+
+// ShadowingPathLoss: the step-call counter lives in device memory and advances on the stream (so does a replayed CUDA graph's)
+__global__ void d2d_advance_counter_kernel(uint64_t *counter, uint64_t by) { *counter += by; }
 
 // LinearObsFunction.get_state (envs/obs_fn.py:43-53): agent i's vector = its own row, then every other
 // row in link order.  One block per (env, agent); float2 granularity (3 per row).
@@ -98,7 +106,7 @@ __global__ void d2d_agent_reward_kernel(const int32_t *__restrict__ actions, con
                                         int64_t num_envs, int N, const int32_t *__restrict__ link_meta, int R, int mode, float param) {
     extern __shared__ uint32_t d2d_weak_smem[];
     const int teams = blockDim.x / TEAM, team = threadIdx.x / TEAM, tl = threadIdx.x % TEAM;
-    uint32_t *weak = d2d_weak_smem + (size_t)team * R;
+    uint32_t *weak = d2d_weak_smem + (size_t)team * R;         // mode 2 only (the launch requests no shared memory otherwise)
     auto team_sync = [&]() { if (TEAM == 32) __syncwarp(); else __syncthreads(); };
     float st_r = 0.f, st_r2 = 0.f;
     const int64_t rounds = (num_envs + (int64_t)gridDim.x * teams - 1) / ((int64_t)gridDim.x * teams);

@@ -70,6 +70,10 @@ struct D2DParams {
     float rescue_band_dB;        // |SINR_dB| or |SNR_dB| below rescue_band_dB + rescue_c / d_min is recomputed in fp64
     float rescue_c;              // 0 unless an fp64 position shadow is bound (covers the fp32 rounding of positions)
     float rescue_dmin2;          // with a shadow: links with a distance^2 below this are always recomputed
+    // per-agent reward functions (envs/reward_fn.py:47-78) compare a link's SINR_dB with a threshold: links within thr_band of it
+    // take the fp64 pass, whose stored fp32 value falls on the float64 value's side of the threshold (d2d_sinr_store)
+    float thr_dB, thr_band;      // thr_band = 0: no threshold (SystemCapacityRewardFunction)
+    double thr_d;
     float4 u_cue, u_due;         // default-shape kernel: the one D2DLinkA of every CUE link / every DUE link (constant bank)
     float2 us_cue, us_due;       // ... and the (sens_dBm, bw_MHz) of D2DLinkB
     D2DLinkD ud_cue, ud_due;     // ... and their fp64 twins for the fp64 pass (valid when `uniform`)
@@ -78,6 +82,15 @@ struct D2DParams {
     float shadow_chi_dB;         // 0 = no shadowing
     float shadow_d0sq;           // d0^2
     uint64_t rng_seed, first_global_env, rng_step;
+    const uint64_t *rng_step_dev; // ShadowingPathLoss: the step-call counter in device memory (added to rng_step), advanced on the stream
+                                 // after every step so that a replayed CUDA graph draws fresh values each time
+    uint32_t flags;              // D2D_PF_*
+    // d2d_episode (warp kernel, EPISODE instantiation): Simulator.reset + the uncounted reset step + T counted steps in one launch
+    uint64_t ep_seed;            // Philox key of this episode's position draws (d2d_reset's `seed`)
+    uint64_t act_seed;           // Philox key of the on-device action draws
+    float cell_radius, d2d_radius;
+    int32_t *actions_out;        // [T + 1][E][N] optional record of the drawn actions
+    float *pos_out;              // = pos (the episode's positions become the bound state)
     double shadow_chi_d, shadow_d0sq_d;   // unrounded copies for the fp64 rescue path
     double ple_d;                // fp64 copy for the rescue path
     const D2DLinkA *linkA;       // [N]
@@ -94,6 +107,7 @@ struct D2DParams {
     // step io
     const int32_t *actions;      // [E][N]
     float *obs;                  // [E][N][6]
+    float2 *obs_dyn;             // [E][N] (sinr_dB, snr_dB): the per-step part of the observation table alone
     float *cap;                  // [E][N]
     float *reward;               // [E]
     uint8_t *done;               // [E]
@@ -133,12 +147,28 @@ __device__ __forceinline__ float d2d_rcp(float x) {
     return y;
 }
 
-// Programmatic dependent launch (PDL).  Every step kernel lets its successor start launching right away
-// (launch_dependents) and itself waits for its predecessor's memory to be complete and visible (wait) only after
-// its own prologue - constant tables, shared-memory setup - so back-to-back steps hide launch latency.  Everything
-// a previous kernel may have written (actions, positions, counters, output buffers) is touched after the wait.
+// Programmatic dependent launch (PDL; the ordering rule is spelled out in include/d2d_b200.h).  A step kernel is launched
+// with programmatic stream serialisation, so it may start while the previous kernel in its stream is still running.
+// What it may touch before griddepcontrol.wait depends on D2D_PF_INPUTS_FRESH:
+//   set (the default):  something other than this handle's own step kernels may have written this step's actions or the
+//       positions (a policy kernel, a copy, d2d_reset ...).  The kernel waits FIRST - every earlier kernel's memory is
+//       then complete and visible - and only then releases its own dependents and loads anything.  PDL still hides the
+//       launch latency and the block scheduling, nothing else.
+//   clear (the caller's D2D_STEP_INPUTS_STABLE promise, honoured only when the previous kernel this handle enqueued on
+//       the stream was one of its own step kernels):  a step kernel never writes actions or positions, so the inputs are
+//       loaded and the whole env-step computed right away; the wait comes only before the first access to memory a
+//       previous STEP wrote - the step counters and the output buffers.  By induction every such kernel starts after
+//       the last "fresh" kernel passed its wait (that one releases its dependents only afterwards), so whatever wrote
+//       the inputs before that point is complete and visible.
+#define D2D_PF_INPUTS_FRESH 1u
+#define D2D_PF_DRAW_ACTIONS 2u     // d2d_episode: actions drawn on the device instead of read from P.actions
 __device__ __forceinline__ void d2d_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void d2d_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// kernel entry: see above
+__device__ __forceinline__ void d2d_pdl_entry(uint32_t flags) {
+    if (flags & D2D_PF_INPUTS_FRESH) d2d_pdl_wait();
+    d2d_pdl_launch_dependents();
+}
 
 // envs/d2d_env.py:95: rb = a // n_pwr for a >= 0.  n_pwr is a runtime value, so divide by multiplying
 // with magic = ceil(2^32 / n) (exact for a < 2^32 / n; n = 1 has no 32-bit magic and is passed through).
@@ -162,10 +192,67 @@ __device__ __forceinline__ uint4 d2d_philox4x32_10(uint4 c, uint2 k) {
     return c;
 }
 
+// ---- counter-based draws of the device-side reset and of the on-device action sampling -------------------------------------
+// (restated value for value by oracle/d2d_oracle.c: d2d_oracle_reset_positions / d2d_oracle_sample_actions; the reference
+// draws from Python's global Mersenne Twister - position.py:18-45, envs/d2d_env.py:54-60 - so only distributions can match.)
+//
+// Reset.  An env's devices are drawn in UNITS of one Philox block (four 32-bit words = two uniform-in-disc draws):
+//   unit u < CU = ceil(C / 2):  CUE 2u from words (x, y), CUE 2u + 1 from words (z, w)
+//   unit CU + d:                DUE pair d - attempt 0: transmitter from (x, y), first receiver offset from (z, w);
+//                               attempt a >= 1: receiver offsets 2a - 1 from (x, y) and 2a from (z, w)
+//   block(u, a) = Philox4x32-10(counter = (global env lo, hi, u, a), key = seed)
+// position.py:24-28: theta = 2 pi u1, r = radius sqrt(u2); 24-bit uniforms centred in their cell, so u is never 0 (r = 0 would
+// put a receiver on its transmitter).  The products are rounded separately (no FMA contraction) so that every kernel that
+// inlines these helpers draws bit-identical positions.
+#define D2D_RESET_MAX_OFFSETS 64u
+__device__ __forceinline__ uint4 d2d_reset_block(uint64_t seed, uint64_t genv, uint32_t unit, uint32_t attempt) {
+    return d2d_philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32), unit, attempt),
+                             make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+__device__ __forceinline__ float2 d2d_disc_from_words(uint32_t w0, uint32_t w1, float radius) {
+    const float u1 = __fmul_rn((float)(w0 >> 8) + 0.5f, 1.0f / 16777216.0f), u2 = __fmul_rn((float)(w1 >> 8) + 0.5f, 1.0f / 16777216.0f);
+    float s, c;
+    __sincosf(__fmul_rn(6.283185307179586f, u1), &s, &c);
+    const float r = __fmul_rn(radius, __fsqrt_rn(u2));
+    return make_float2(__fmul_rn(r, c), __fmul_rn(r, s));
+}
+// CUE j of global env genv
+__device__ __forceinline__ float2 d2d_draw_cue(uint64_t seed, uint64_t genv, uint32_t j, float cell_radius) {
+    const uint4 b = d2d_reset_block(seed, genv, j >> 1, 0u);
+    return (j & 1u) ? d2d_disc_from_words(b.z, b.w, cell_radius) : d2d_disc_from_words(b.x, b.y, cell_radius);
+}
+// DUE pair d: (tx_x, tx_y, rx_x, rx_y); the receiver is re-drawn around the transmitter until it falls inside the cell
+// (position.py:38-44; bounded to D2D_RESET_MAX_OFFSETS candidates)
+__device__ __forceinline__ float4 d2d_draw_due(uint64_t seed, uint64_t genv, uint32_t cu, uint32_t d, float cell_radius, float d2d_radius) {
+    uint4 b = d2d_reset_block(seed, genv, cu + d, 0u);
+    const float2 tx = d2d_disc_from_words(b.x, b.y, cell_radius);
+    const float r2max = __fmul_rn(cell_radius, cell_radius);
+    float2 rx = tx;
+    for (uint32_t k = 0; k < D2D_RESET_MAX_OFFSETS; ++k) {
+        if (k && (k & 1u)) b = d2d_reset_block(seed, genv, cu + d, (k + 1u) >> 1);
+        const float2 o = (k & 1u) ? d2d_disc_from_words(b.x, b.y, d2d_radius) : d2d_disc_from_words(b.z, b.w, d2d_radius);
+        rx = make_float2(__fadd_rn(tx.x, o.x), __fadd_rn(tx.y, o.y));
+        if (__fadd_rn(__fmul_rn(rx.x, rx.x), __fmul_rn(rx.y, rx.y)) <= r2max) break;
+    }
+    return make_float4(tx.x, tx.y, rx.x, rx.y);
+}
+// Actions (envs/d2d_env.py:54-60: Discrete(n).sample(), uniform over 0 .. n - 1).  One Philox block serves the CUE and the DUE
+// link of pair index l (CUE l / DUE pair l) for two consecutive steps:
+//   block(l, t) = Philox4x32-10(counter = (global env lo, hi, l, t >> 1), key = action seed ^ D2D_ACTION_KEY)
+//   word        = 2 (t & 1) + (1 if the link is a DUE pair);   a = floor(word * n / 2^32)
+#define D2D_ACTION_KEY 0xA511E9B3u
+__device__ __forceinline__ uint4 d2d_action_block(uint64_t act_seed, uint64_t genv, uint32_t l, uint32_t t) {
+    return d2d_philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32), l, t >> 1),
+                             make_uint2((uint32_t)act_seed ^ D2D_ACTION_KEY, (uint32_t)(act_seed >> 32)));
+}
+__device__ __forceinline__ uint32_t d2d_action_word(const uint4 &b, uint32_t t, bool due) {
+    return (t & 1u) ? (due ? b.w : b.z) : (due ? b.y : b.x);
+}
+
 // The N(0,1) draw of one ShadowingPathLoss evaluation (kind 0: the terms of the SINR, 1: the SNR's own-link evaluation): Box-Muller
 // on two 24-bit uniforms of one Philox block.  Restated value for value by the oracle (d2d_oracle_shadow_normal).
 __device__ __forceinline__ uint2 d2d_shadow_bits(const D2DParams &P, uint64_t genv, uint32_t victim, uint32_t source, uint32_t kind) {
-    const uint64_t step = P.rng_step;
+    const uint64_t step = P.rng_step + (P.rng_step_dev ? *P.rng_step_dev : 0ull);
     const uint4 o = d2d_philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32) ^ (kind << 31) ^ ((uint32_t)(step >> 32) << 8),
                                                  victim | (source << 16), (uint32_t)step),
                                       make_uint2((uint32_t)P.rng_seed ^ 0x5bd1e995u, (uint32_t)(P.rng_seed >> 32)));
@@ -215,6 +302,18 @@ __device__ __forceinline__ float d2d_log2_1p(float r) {
 struct D2DLinkOut {
     float sinr_dB, snr_dB, rate, cap;
 };
+
+// The fp32 image of a float64 SINR_dB.  ShannonRewardFunction / CueSinrShannonRewardFunction (envs/reward_fn.py:55,72) compare
+// the float64 value with a threshold; the post-pass kernel compares the stored fp32 value with the fp32 threshold, so the
+// stored value is moved by at most one ulp onto the float64 value's side of it when plain rounding would cross.
+__device__ __forceinline__ float d2d_sinr_store(double sinr, const D2DParams &P) {
+    float v = (float)sinr;
+    if (P.thr_band > 0.f) {
+        const bool ge = sinr >= P.thr_d;
+        if ((v >= P.thr_dB) != ge) v = ge ? P.thr_dB : nextafterf(P.thr_dB, -3.0e38f);
+    }
+    return v;
+}
 
 // Per-link epilogue in fp32 (Appendix A).  p_lin = 10^(p/10); lg_d2 = log2(d^2) and g = d^-ple of the own link;
 // I = interference [mW]; cA = (tx_lin0, a_lin, inv_noise, snr0_dB); sb = (sens_dBm, bw_MHz).
@@ -316,20 +415,21 @@ __device__ __forceinline__ D2DLinkOut d2d_link_f64(int j, double2 tx, double2 rx
     const double rate = 1.4426950408889634074 * d2d_ln_f64(1.0 + r);
     const bool ok = sinr > (double)sens_dBm;
     D2DLinkOut o;
-    o.sinr_dB = (float)sinr;
+    o.sinr_dB = d2d_sinr_store(sinr, P);
     o.snr_dB = (float)(4.3429448190325182765 * d2d_ln_f64(S));
     o.rate = ok ? (float)rate : 0.0f;
     o.cap = ok ? (float)(Lj.bw_MHz * rate) : 0.0f;
     return o;
 }
-// does this link need the fp64 pass?  dmin2 = smallest squared distance that entered its sums (EXACT only)
-template <bool EXACT>
+// does this link need the fp64 pass?  dmin2 = smallest squared distance that entered its sums (EXACT only).  THR: the
+// instantiation also serves per-agent reward functions, whose hard SINR threshold is a second ill-conditioned point.
+template <bool EXACT, bool THR = true>
 __device__ __forceinline__ bool d2d_needs_rescue(const D2DLinkOut &o, float dmin2, const D2DParams &P) {
     const float lo = fminf(fabsf(o.sinr_dB), fabsf(o.snr_dB));
-    if (!EXACT) return lo < P.rescue_band_dB;
-    return lo < fmaf(P.rescue_c, rsqrtf(dmin2), P.rescue_band_dB) || dmin2 < P.rescue_dmin2;
+    const bool thr = THR && fabsf(o.sinr_dB - P.thr_dB) < P.thr_band;
+    if (!EXACT) return lo < P.rescue_band_dB || thr;
+    return lo < fmaf(P.rescue_c, rsqrtf(dmin2), P.rescue_band_dB) || dmin2 < P.rescue_dmin2 || thr;
 }
-
 // ---- cheap fp64 building blocks of the rescue passes (no division or libm subroutines) ------------------------------------
 // 1 / x in fp64 from the fp32 reciprocal and three Newton steps (x normal, > 0): no division subroutine
 __device__ __forceinline__ double d2d_rcp_f64(double x) {

@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_generic_kern
     const int N = P.N, V = P.V, nbins = P.nbins;
     D2DBlockSmemView S = d2d_block_carve(d2d_smem_raw, N, nbins);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    d2d_pdl_launch_dependents();
+    d2d_pdl_entry(P.flags);
 
     for (int i = tid; i < N; i += D2D_BLOCK_THREADS) {
         S.linkA[i] = reinterpret_cast<const float4 *>(P.linkA)[i];
@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_generic_kern
                 ob[1] = make_float2(xj.x, xj.y);
                 ob[2] = make_float2(o.sinr_dB, o.snr_dB);
             }
+            if (P.obs_dyn) P.obs_dyn[g] = make_float2(o.sinr_dB, o.snr_dB);
             if (P.cap) P.cap[g] = o.cap;
             if (P.rate) P.rate[g] = o.rate;
             if (P.rb_out) P.rb_out[g] = active ? (int16_t)(key & 0x1fffffffu) : (int16_t)0;
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS, LPT <= 2 ? 4 : 3) d2d_step_
     uint32_t *resq = reinterpret_cast<uint32_t *>(red) - 2 * (D2D_BLOCK_RESQ * 8 + 4);      // [2][4 + 32 * 8]: word 0 = count
     uint32_t *who = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(resq) - (((size_t)N * sizeof(uint32_t) + 15) & ~(size_t)15));
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    d2d_pdl_launch_dependents();
+    d2d_pdl_entry(P.flags);
 
     for (uint32_t i = tid; i < D2D_MAX_PWR_LEVELS; i += D2D_BLOCK_THREADS) pwr[i] = P.pwr_lin[i];
     for (uint32_t i = tid; i <= nbins; i += D2D_BLOCK_THREADS) cnt[i] = 0u;
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS, LPT <= 2 ? 4 : 3) d2d_step_
                     const double r = Sg * d2d_rcp_f64(fma(I64, Lj.inv_noise, 1.0));
                     const bool r1 = fabs(r - 1.0) < 0.0625, s1 = fabs(Sg - 1.0) < 0.0625;
                     double sinr = (double)o.sinr_dB;
-                    if (exact || r1) { sinr = r1 ? d2d_db_near1(r) : 4.3429448190325182765 * d2d_ln_f64(r); o.sinr_dB = (float)sinr; }
+                    if (exact || r1 || P.thr_band > 0.f) { sinr = r1 ? d2d_db_near1(r) : 4.3429448190325182765 * d2d_ln_f64(r); o.sinr_dB = d2d_sinr_store(sinr, P); }
                     if (exact || s1) o.snr_dB = (float)(s1 ? d2d_db_near1(Sg) : 4.3429448190325182765 * d2d_ln_f64(Sg));
                     if (exact || (r1 && fabsf(sBk.x) < 0.5f)) {
                         const double rate = sinr > (double)sBk.x ? 1.4426950408889634074 * d2d_ln_f64(1.0 + r) : 0.0;
@@ -436,6 +437,7 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS, LPT <= 2 ? 4 : 3) d2d_step_
                     ob[1] = rx[k];
                     ob[2] = make_float2(o.sinr_dB, o.snr_dB);
                 }
+                if (P.obs_dyn) P.obs_dyn[gi] = make_float2(o.sinr_dB, o.snr_dB);
                 if (P.cap) P.cap[gi] = o.cap;
                 if (P.rate) P.rate[gi] = o.rate;
                 if (P.rb_out) P.rb_out[gi] = live[k] ? (int16_t)rb[k] : (int16_t)0;
@@ -485,11 +487,17 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS, LPT <= 2 ? 4 : 3) d2d_step_
                     const bool r1 = fabs(r - 1.0) < 0.0625, s1 = fabs(Sg - 1.0) < 0.0625;
                     const uint64_t gi = (uint64_t)e * N + j;
                     double sinr = 0.0;
-                    if (exact || r1) {
+                    if (exact || r1 || P.thr_band > 0.f) {
                         sinr = r1 ? d2d_db_near1(r) : 4.3429448190325182765 * d2d_ln_f64(r);
-                        if (P.obs) P.obs[gi * 6u + 4u] = (float)sinr;
+                        const float sv = d2d_sinr_store(sinr, P);
+                        if (P.obs) P.obs[gi * 6u + 4u] = sv;
+                        if (P.obs_dyn) P.obs_dyn[gi].x = sv;
                     }
-                    if ((exact || s1) && P.obs) P.obs[gi * 6u + 5u] = (float)(s1 ? d2d_db_near1(Sg) : 4.3429448190325182765 * d2d_ln_f64(Sg));
+                    if (exact || s1) {
+                        const float snr = (float)(s1 ? d2d_db_near1(Sg) : 4.3429448190325182765 * d2d_ln_f64(Sg));
+                        if (P.obs) P.obs[gi * 6u + 5u] = snr;
+                        if (P.obs_dyn) P.obs_dyn[gi].y = snr;
+                    }
                     if (exact || (r1 && fabsf(sens) < 0.5f)) {
                         const double rate = sinr > (double)sens ? 1.4426950408889634074 * d2d_ln_f64(1.0 + r) : 0.0;
                         if (P.cap) P.cap[gi] = (float)(Lj.bw_MHz * rate);

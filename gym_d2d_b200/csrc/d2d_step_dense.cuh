@@ -80,7 +80,7 @@ struct D2DDenseFix {
 // Warp-cooperative fp64 recomputation of link vj of env e (rb, slot in its bin and Tx power given): the lanes split the RB's
 // peer records, a butterfly sums their terms, every lane returns the same result.  Kept out of line: rare, and its fp64
 // registers must not count against the hot loop's allocation.
-template <bool PLE2>
+template <bool PLE2, bool THR>
 __device__ __noinline__ D2DDenseFix d2d_dense_rescue(const D2DParams &P, uint32_t e, uint32_t vj, uint32_t vrb, uint32_t vself, uint32_t vpw,
                                                      const float4 *bp, const uint32_t *cn, const float4 *ovrec,
                                                      const uint16_t *ovrb, const double *pwd, uint32_t ovn, uint32_t lane) {
@@ -116,7 +116,7 @@ __device__ __noinline__ D2DDenseFix d2d_dense_rescue(const D2DParams &P, uint32_
     const bool r1 = fabs(r - 1.0) < 0.0625, s1 = fabs(Sg - 1.0) < 0.0625;
     D2DDenseFix f = {0.f, 0.f, 0.f, 0.f, 0u};
     double sinr = 0.0;
-    if (exact || r1) { sinr = r1 ? d2d_db_near1(r) : 4.3429448190325182765 * d2d_ln_f64(r); f.sinr_dB = (float)sinr; f.flags |= 1u; }
+    if (exact || r1 || (THR && P.thr_band > 0.f)) { sinr = r1 ? d2d_db_near1(r) : 4.3429448190325182765 * d2d_ln_f64(r); f.sinr_dB = THR ? d2d_sinr_store(sinr, P) : (float)sinr; f.flags |= 1u; }
     if (exact || s1) { f.snr_dB = (float)(s1 ? d2d_db_near1(Sg) : 4.3429448190325182765 * d2d_ln_f64(Sg)); f.flags |= 2u; }
     if (exact || (r1 && fabsf(sens) < 0.5f)) {
         const double rate = sinr > (double)sens ? 1.4426950408889634074 * d2d_ln_f64(1.0 + r) : 0.0;
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
     float *red = reinterpret_cast<float *>(d2d_dense_smem + L.red);
     uint16_t *ovrb = reinterpret_cast<uint16_t *>(d2d_dense_smem + L.ovrb);
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    d2d_pdl_launch_dependents();
+    d2d_pdl_entry(P.flags);
 
     for (uint32_t i = tid; i < D2D_MAX_PWR_LEVELS; i += BT) { pwr[i] = P.pwr_lin[i]; pwd[i] = P.pwr_lin_d[i]; }
     for (uint32_t i = tid; i < 3u * L.cnt_words; i += BT) cnt[i] = 0u;
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
                 const float gown = PLE2 ? d2d_rcp(d2own) : d2d_ex2(P.neg_half_ple * lg);
                 sBk = link_sB(j, cue[k]);
                 o = d2d_link_epilogue<PLE2>((int)pw[k], pl[k], lg, gown, I, link_cA(j, cue[k]), sBk, P);
-                need = D2D_RESCUE_ENABLED && d2d_needs_rescue<EXACT>(o, fminf(dmin2, d2own), P);
+                need = D2D_RESCUE_ENABLED && d2d_needs_rescue<EXACT, !FULL>(o, fminf(dmin2, d2own), P);
             }
             if (live[k]) {
                 cap_part += o.cap;
@@ -331,6 +331,7 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
                 }
                 if (FULL || P.cap) P.cap[gi] = o.cap;
                 if (!FULL) {
+                    if (P.obs_dyn) P.obs_dyn[gi] = make_float2(o.sinr_dB, o.snr_dB);
                     if (P.rate) P.rate[gi] = o.rate;
                     if (P.rb_out) P.rb_out[gi] = live[k] ? (int16_t)rb[k] : (int16_t)0;
                     if (P.pwr_out) P.pwr_out[gi] = live[k] ? (int16_t)pw[k] : (int16_t)0;
@@ -351,12 +352,16 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
                     mask &= mask - 1u;
                     ++resc;
                     const uint32_t vj = (tid - lane) + (uint32_t)src + k * BT;
-                    const D2DDenseFix f = d2d_dense_rescue<PLE2>(P, e, vj, __shfl_sync(0xffffffffu, rb[k], src), __shfl_sync(0xffffffffu, selfq[k], src),
+                    const D2DDenseFix f = d2d_dense_rescue<PLE2, !FULL>(P, e, vj, __shfl_sync(0xffffffffu, rb[k], src), __shfl_sync(0xffffffffu, selfq[k], src),
                                                                  __shfl_sync(0xffffffffu, pw[k], src), bp, cn, ovrec, ovrb, pwd, ovn, lane);
                     if ((int)lane == src) {
                         const uint64_t gi = (uint64_t)e * N + vj;
                         if ((f.flags & 1u) && (FULL || P.obs)) P.obs[gi * 6u + 4u] = f.sinr_dB;
                         if ((f.flags & 2u) && (FULL || P.obs)) P.obs[gi * 6u + 5u] = f.snr_dB;
+                        if (!FULL && P.obs_dyn) {
+                            if (f.flags & 1u) P.obs_dyn[gi].x = f.sinr_dB;
+                            if (f.flags & 2u) P.obs_dyn[gi].y = f.snr_dB;
+                        }
                         if (f.flags & 4u) {
                             if (FULL || P.cap) P.cap[gi] = f.cap;
                             if (!FULL && P.rate) P.rate[gi] = f.rate;

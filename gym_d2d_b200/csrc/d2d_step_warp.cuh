@@ -379,9 +379,9 @@ __device__ __forceinline__ double d2d_shfl_xor_f64(double v, int m) {
 // gate (simulator.py:123,149) could sit inside that band.  With a shadow every output of the link is rewritten.
 // Returns the number of links recomputed.
 // 10^(p/10) in fp64 for the warp kernel's fp64 pass: the constant bank instead of a global table (filled by d2d_create)
-__constant__ double d2d_pwr_lin_c[D2D_MAX_PWR_LEVELS];
+static __constant__ double d2d_pwr_lin_c[D2D_MAX_PWR_LEVELS];    // one copy per translation unit (d2d_tu_warp.cu)
 
-template <bool PLE2, bool EXACT, bool SPEC, bool STORE>
+template <bool PLE2, bool EXACT, bool SPEC, bool STORE, bool THR>
 __device__ __forceinline__ int d2d_rescue_warp(const D2DParams &P, const D2DShape<SPEC> &S, uint32_t e, uint32_t lane, uint32_t jA,
                                                uint32_t keyA, uint32_t keyB, bool needA, bool needB, uint32_t pA, uint32_t pB_,
                                                const float2 &tA, const float4 &pB, D2DLinkOut &oA, D2DLinkOut &oB) {
@@ -434,14 +434,16 @@ __device__ __forceinline__ int d2d_rescue_warp(const D2DParams &P, const D2DShap
                 D2DLinkOut o;
                 if (!STORE) o = s ? oB : oA;
                 double sinr = 0.0;
-                if (EXACT || r1) {
+                if (EXACT || r1 || (THR && P.thr_band > 0.f)) {
                     sinr = r1 ? d2d_db_near1(r) : 4.3429448190325182765 * d2d_ln_f64(r);
-                    o.sinr_dB = (float)sinr;
+                    o.sinr_dB = THR ? d2d_sinr_store(sinr, P) : (float)sinr;
                     if (STORE && P.obs) P.obs[(uint64_t)row * 6u + 4u] = o.sinr_dB;
+                    if (STORE && P.obs_dyn) P.obs_dyn[row].x = o.sinr_dB;
                 }
                 if (EXACT || s1) {
                     o.snr_dB = (float)(s1 ? d2d_db_near1(Sg) : 4.3429448190325182765 * d2d_ln_f64(Sg));
                     if (STORE && P.obs) P.obs[(uint64_t)row * 6u + 5u] = o.snr_dB;
+                    if (STORE && P.obs_dyn) P.obs_dyn[row].y = o.snr_dB;
                 }
                 if (EXACT || (r1 && fabsf(sens) < 0.5f)) {
                     const double rate = sinr > (double)sens ? 1.4426950408889634074 * d2d_ln_f64(1.0 + r) : 0.0;
@@ -459,12 +461,12 @@ __device__ __forceinline__ int d2d_rescue_warp(const D2DParams &P, const D2DShap
 }
 
 // the throughput shapes' call of the pass (after the stores): one place to take it out of line
-template <bool PLE2, bool EXACT, bool SPEC>
+template <bool PLE2, bool EXACT, bool SPEC, bool THR>
 __device__ D2D_RARE_ATTR int d2d_rescue_warp_late(const D2DParams &P, const D2DShape<SPEC> &S, uint32_t e, uint32_t lane, uint32_t jA,
                                                   uint32_t keyA, uint32_t keyB, bool needA, bool needB, uint32_t pA, uint32_t pB_,
                                                   float2 tA, float4 pB) {
     D2DLinkOut oA, oB;       // unused by the storing variant
-    return d2d_rescue_warp<PLE2, EXACT, SPEC, true>(P, S, e, lane, jA, keyA, keyB, needA, needB, pA, pB_, tA, pB, oA, oB);
+    return d2d_rescue_warp<PLE2, EXACT, SPEC, true, THR>(P, S, e, lane, jA, keyA, keyB, needA, needB, pA, pB_, tA, pB, oA, oB);
 }
 
 // FULL: the caller passed exactly the core outputs (obs, capacity, reward, done) and a step counter is bound - the
@@ -472,10 +474,17 @@ __device__ D2D_RARE_ATTR int d2d_rescue_warp_late(const D2DParams &P, const D2DS
 // MANY: d2d_step_many - P.T consecutive steps per env in ONE launch (the agent loop of examples/simple_env.py:20-33
 // with the actions of all T steps given up front).  An env's positions are read once and stay in registers for its T
 // steps; step t reads actions[t][e] and writes the [t][e] slice of every output (slices P.t_stride envs apart).
-template <bool PLE2, bool EXACT, int WPB, bool FULL, bool SPEC, bool MANY>
+// MODE 0: d2d_step.  MODE 1 (MANY): d2d_step_many.  MODE 2 (EPISODE): d2d_episode - D2DEnv.reset (envs/d2d_env.py:45-52) and the
+// agent loop after it in ONE launch: slice 0 of every output is the uncounted reset step on freshly drawn positions
+// (Simulator.reset, simulator.py:61-75; the draws of d2d_reset, d2d_common.cuh), slices 1 .. P.T - 1 are the counted steps.  The
+// positions are drawn in registers and written to the bound state once; the actions of every step are either read from
+// actions [P.T][E][N] or (D2D_PF_DRAW_ACTIONS) drawn on the device like envs/d2d_env.py:54-60 - the kernel then reads nothing
+// but its constant tables.
+template <bool PLE2, bool EXACT, int WPB, bool FULL, bool SPEC, int MODE>
 __global__ void __launch_bounds__(WPB * 32, D2D_WARP_MIN_BLOCKS(WPB))
 d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
     extern __shared__ __align__(16) unsigned char d2d_warp_smem[];
+    constexpr bool MANY = MODE != 0, EPI = MODE == 2;
     const D2DShape<SPEC> S(P);
     // latency shape: the fp64 pass runs before griddepcontrol.wait
     constexpr bool RESCUE_EARLY = WPB == 2;
@@ -488,7 +497,7 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
     const unsigned long long tl_g0 = d2d_tl_gtime(), tl_c0 = d2d_tl_clock();
     unsigned long long tl_c1 = 0, tl_c2 = 0;
 #endif
-    d2d_pdl_launch_dependents();
+    d2d_pdl_entry(P.flags);
     uint32_t blk = (uint32_t)__cvta_generic_to_shared(d2d_warp_smem);
     asm volatile("mov.u32 %0, %0;" : "+r"(blk));      // opaque: keep the base in a register instead of re-deriving it
     const uint32_t bins = blk + D2D_BLK_BYTES + warp * d2d_warp_smem_per_warp((int)R);
@@ -505,7 +514,11 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
     // the first env's inputs go out before anything else: their latency overlaps the table loads of the prologue instead of
     // following them (a warp of a one-wave batch steps a single env: two serial memory round trips were a tenth of its life)
     D2DLaneIn nxt;
-    if (e < e_end) nxt = d2d_load_inputs<SPEC>(P, S, iA, qN, lane, hasA, hasB);
+    const bool draw_actions = EPI && (P.flags & D2D_PF_DRAW_ACTIONS) != 0u;
+    if (EPI) {
+        nxt.aA = nxt.aB = 0xffffffffu; nxt.tA = make_float2(1.f, 0.f); nxt.pB = make_float4(1.f, 0.f, 0.f, 0.f);
+        if (e < e_end && !draw_actions) d2d_load_actions<SPEC>(P, S, iA, hasA, hasB, nxt);
+    } else if (e < e_end) nxt = d2d_load_inputs<SPEC>(P, S, iA, qN, lane, hasA, hasB);
 
     // ---- prologue (constant tables only: nothing a previous kernel in the stream may have written) ------------------
     // block tables: 10^(p/10) for integer dBm, and the per-link constants by lane slot (zeros where there is no link)
@@ -555,6 +568,7 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
     const uint32_t T = MANY ? (uint32_t)P.T : 1u, strideE = MANY ? (uint32_t)P.t_stride : 0u, strideN = strideE * N;
     float2 tA_keep = make_float2(1.f, 0.f);
     float4 pB_keep = make_float4(1.f, 0.f, 0.f, 0.f);
+    uint4 ablk = make_uint4(0u, 0u, 0u, 0u);                       // EPISODE: the lane's action block of steps t & ~1, t | 1
     // Programmatic dependent launch: the kernel BEFORE this one in the stream may still be running.  If it is one of this
     // library's step kernels it never writes actions or positions (and anything else - a policy kernel, a reset, a copy -
     // does not release its dependents early), so this env-step's inputs are read and its whole chain computed right away;
@@ -563,13 +577,30 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
     while (e < e_end) {
         // ---- one coalesced pass over the env's inputs, software-pipelined: the NEXT env's (or step's) loads are in
         // flight while this one computes, so a warp hides its own HBM latency -------------------------------------------
-        const uint32_t aA = nxt.aA, aB = nxt.aB;
-        if (!MANY || t == 0u) { tA_keep = nxt.tA; pB_keep = nxt.pB; }
+        uint32_t aA = nxt.aA, aB = nxt.aB;
+        if (EPI) {
+            const uint64_t genv = P.first_global_env + (uint64_t)e;
+            if (t == 0u) {                                          // Simulator.reset (simulator.py:61-75): this env's new positions
+                tA_keep = make_float2(1.f, 0.f); pB_keep = make_float4(1.f, 0.f, 0.f, 0.f);
+                if (hasA) tA_keep = d2d_draw_cue(P.ep_seed, genv, lane, P.cell_radius);
+                if (hasB) pB_keep = d2d_draw_due(P.ep_seed, genv, (C + 1u) >> 1, lane, P.cell_radius, P.d2d_radius);
+            }
+            if (draw_actions) {                                     // envs/d2d_env.py:54-60: Discrete(R n_pwr).sample() per agent
+                if ((t & 1u) == 0u) ablk = d2d_action_block(P.act_seed, genv, lane, t);
+                aA = hasA ? __umulhi(d2d_action_word(ablk, t, false), limA) : 0xffffffffu;
+                aB = hasB ? __umulhi(d2d_action_word(ablk, t, true), limB) : 0xffffffffu;
+            }
+        } else if (!MANY || t == 0u) { tA_keep = nxt.tA; pB_keep = nxt.pB; }
         const float2 tA = tA_keep;
         const float4 pB = pB_keep;
         const uint32_t jA = iA + tN, jB = jA + C;                   // this env-step's link indices (outputs)
         const bool last_t = !MANY || t + 1u == T;
-        if (last_t) {
+        if (EPI) {
+            if (!draw_actions) {
+                if (!last_t) d2d_load_actions<SPEC>(P, S, jA + strideN, hasA, hasB, nxt);
+                else if (e + 1u < e_end) d2d_load_actions<SPEC>(P, S, iA + N, hasA, hasB, nxt);
+            }
+        } else if (last_t) {
             qN += V;
             if (e + 1u < e_end) nxt = d2d_load_inputs<SPEC>(P, S, iA + N, qN, lane, hasA, hasB);
         } else {
@@ -629,8 +660,8 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         const float slope = PLE2 ? 3.0102999566398120f : P.snr_slope;
         const D2DLinkOut oA32 = d2d_link_epilogue_warp(liveA, (int)pA, plA, lgA, gA, IA, cA, sA, slope);
         const D2DLinkOut oB32 = d2d_link_epilogue_warp(liveB, (int)pB_, plB, lgB, gB, IB, cB, sB, slope);
-        const bool needA = liveA && d2d_needs_rescue<EXACT>(oA32, fminf(dminA, d2A), P);
-        const bool needB = liveB && d2d_needs_rescue<EXACT>(oB32, fminf(dminB, d2B), P);
+        const bool needA = liveA && d2d_needs_rescue<EXACT, !FULL>(oA32, fminf(dminA, d2A), P);
+        const bool needB = liveB && d2d_needs_rescue<EXACT, !FULL>(oB32, fminf(dminB, d2B), P);
 
         // ---- envs/reward_fn.py:27-44 -----------------------------------------------------------------------------------
         const bool bad = __any_sync(0xffffffffu, liveA && ctA.y != 0u && oA32.cap <= P.min_cap);
@@ -649,19 +680,21 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         D2DLinkOut oA = oA32, oB = oB32;
         if (D2D_RESCUE_ENABLED && RESCUE_EARLY && __any_sync(0xffffffffu, needA || needB)) {
             const uint32_t keyA = liveA ? rbA : (D2D_INACTIVE_KEY | lane), keyB = liveB ? rbB : (D2D_INACTIVE_KEY | 32u | lane);
-            st_resc += (uint32_t)d2d_rescue_warp<PLE2, EXACT, SPEC, false>(P, S, e, lane, jA, keyA, keyB, needA, needB, pA, pB_, tA, pB, oA, oB);
+            st_resc += (uint32_t)d2d_rescue_warp<PLE2, EXACT, SPEC, false, !FULL>(P, S, e, lane, jA, keyA, keyB, needA, needB, pA, pB_, tA, pB, oA, oB);
         }
 
         // ---- per-warp statistics; flushed with the warp's LAST env, ahead of the wait and of that env's stores: the reductions
         // commute with every other launch's, and a warp (hence its block's slot) is not retired before its outstanding atomics
         // are acknowledged - issued at the very end they cost 0.3 us per launch of a one-wave batch (profiles/README.md) --------
-        if (P.reward_fn == 0) { st_reward += reward; st_reward2 = fmaf(reward, reward, st_reward2); }
-        st_cap += cap_sum;
-        st_pen += bad ? 1u : 0u;
+        if (!EPI || t != 0u) {                                      // the reset step (envs/d2d_env.py:50) earns no reward
+            if (P.reward_fn == 0) { st_reward += reward; st_reward2 = fmaf(reward, reward, st_reward2); }
+            st_cap += cap_sum;
+            st_pen += bad ? 1u : 0u;
+        }
         if (FLUSH_EARLY && P.stats && last_t && e + 1u == e_end && lane < (RESCUE_EARLY ? 6u : 5u)) {
             // one fire-and-forget fp64 reduction per statistic and warp, spread over the replicas
             const float vf = lane == 0 ? st_reward : lane == 1 ? st_cap : st_reward2;
-            const uint32_t vi = lane == 3 ? (e_end - e0) * T                   // env-steps this warp made
+            const uint32_t vi = lane == 3 ? (e_end - e0) * (EPI ? T - 1u : T)  // env-steps this warp made
                               : lane == 4 ? st_pen : st_resc;
             const double v = lane < 3u ? (double)vf : (double)vi;              // (two conversions instead of six)
 #ifndef D2D_EXPERIMENT_NOSTATS      // A/B only: what the statistics flush costs
@@ -680,11 +713,27 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
 #ifdef D2D_EXPERIMENT_NOCOUNT     // A/B only: how much of the post-wait tail is the step-counter load
         ns_keep = 0;
 #else
-        if (g == 0u && t == 0u && (FULL || P.step_count)) ns_keep = e + lane < e_end ? (int)P.step_count[e + lane] : 0;   // consumed at the group's end
+        if (!EPI && g == 0u && t == 0u && (FULL || P.step_count)) ns_keep = e + lane < e_end ? (int)P.step_count[e + lane] : 0;   // consumed at the group's end
 #endif
         // ---- outputs: compact observation table (envs/obs_fn.py:55-61), capacity, optional info.  Rows of absent
         // agents carry their positions and zeros (the reference has no row for them). ---------------------------------
         // (one divergent branch per slot: cheaper than predicating every store, and the two merge when C == D)
+        if (EPI && t == 0u) {
+            // the drawn positions become the bound state (after the wait: an earlier step kernel may still be reading it)
+            float2 *pe = reinterpret_cast<float2 *>(P.pos_out) + (uint64_t)e * V;
+            double2 *pe64 = P.pos64 ? reinterpret_cast<double2 *>(const_cast<double *>(P.pos64)) + (uint64_t)e * V : nullptr;
+            if (lane == 0u) { pe[0] = make_float2(0.f, 0.f); if (pe64) pe64[0] = make_double2(0.0, 0.0); }     // simulator.py:63-64
+            if (hasA) { pe[1u + lane] = tA; if (pe64) pe64[1u + lane] = make_double2((double)tA.x, (double)tA.y); }
+            if (hasB) {
+                const uint32_t q = 1u + C + 2u * lane;
+                pe[q] = make_float2(pB.x, pB.y); pe[q + 1u] = make_float2(pB.z, pB.w);
+                if (pe64) { pe64[q] = make_double2((double)pB.x, (double)pB.y); pe64[q + 1u] = make_double2((double)pB.z, (double)pB.w); }
+            }
+        }
+        if (EPI && P.actions_out) {
+            if (hasA) P.actions_out[jA] = (int32_t)aA;
+            if (hasB) P.actions_out[jB] = (int32_t)aB;
+        }
         if (hasA) {
             if (FULL || P.obs) {
                 float2 *oa = reinterpret_cast<float2 *>(reinterpret_cast<char *>(P.obs) + (uint64_t)jA * 24u);
@@ -692,6 +741,7 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
             }
             if (FULL || P.cap) P.cap[jA] = oA.cap;
             if (!FULL) {
+                if (P.obs_dyn) P.obs_dyn[jA] = make_float2(oA.sinr_dB, oA.snr_dB);
                 if (P.rate) P.rate[jA] = oA.rate;
                 if (P.rb_out) P.rb_out[jA] = (int16_t)(liveA ? rbA : 0u);
                 if (P.pwr_out) P.pwr_out[jA] = (int16_t)(liveA ? pA : 0u);
@@ -704,6 +754,7 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
             }
             if (FULL || P.cap) P.cap[jB] = oB.cap;
             if (!FULL) {
+                if (P.obs_dyn) P.obs_dyn[jB] = make_float2(oB.sinr_dB, oB.snr_dB);
                 if (P.rate) P.rate[jB] = oB.rate;
                 if (P.rb_out) P.rb_out[jB] = (int16_t)(liveB ? rbB : 0u);
                 if (P.pwr_out) P.pwr_out[jB] = (int16_t)(liveB ? pB_ : 0u);
@@ -713,7 +764,8 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
             // per-step scalars straight to slice t (write-only, so partial sectors merge in L2); the step counter stays
             // in the group's registers until the env's last step
             if (lane == g) {
-                const int ns = min(ns_keep + (int)t + 1, 255);
+                // EPISODE: num_steps = 0 at reset (envs/d2d_env.py:46) and slice 0 is the uncounted reset step
+                const int ns = EPI ? (int)min(t, 255u) : min(ns_keep + (int)t + 1, 255);
                 if (P.reward) P.reward[tE + e] = reward;
                 if (P.done) P.done[tE + e] = ns >= P.episode_length ? 1 : 0;
                 if (last_t) ns_keep = ns;
@@ -735,7 +787,7 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         // ---- throughput shape: the rare fp64 pass after the env's outputs are stored (it overwrites them) -------------------
         if (D2D_RESCUE_ENABLED && !RESCUE_EARLY && __any_sync(0xffffffffu, needA || needB)) {
             const uint32_t keyA = liveA ? rbA : (D2D_INACTIVE_KEY | lane), keyB = liveB ? rbB : (D2D_INACTIVE_KEY | 32u | lane);
-            st_resc += (uint32_t)d2d_rescue_warp_late<PLE2, EXACT, SPEC>(P, S, e, lane, jA, keyA, keyB, needA, needB, pA, pB_, tA, pB);
+            st_resc += (uint32_t)d2d_rescue_warp_late<PLE2, EXACT, SPEC, !FULL>(P, S, e, lane, jA, keyA, keyB, needA, needB, pA, pB_, tA, pB);
         }
         if (last_t) {
             g = (g + 1u) & 31u;
@@ -757,7 +809,7 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
     if (!FLUSH_EARLY) {
         if (P.stats && lane < 6u) {
             const float vf = lane == 0 ? st_reward : lane == 1 ? st_cap : st_reward2;
-            const uint32_t vi = lane == 3 ? (e_end - e0) * T : lane == 4 ? st_pen : st_resc;
+            const uint32_t vi = lane == 3 ? (e_end - e0) * (EPI ? T - 1u : T) : lane == 4 ? st_pen : st_resc;
             const double v = lane < 3u ? (double)vf : (double)vi;
             if (v != 0.0) atomicAdd(P.stats + ((blockIdx.x * WPB + warp) % D2D_STATS_REPLICAS) * 8 + lane, v);
         }

@@ -38,6 +38,8 @@ class D2DEnv:
         self.state: Optional[dict] = None
         self.num_steps = 0
         self._present: List[int] = []
+        import random
+        self._host_rng = random.Random(seed)             # receivers re-drawn around file-placed transmitters (reset)
 
     def _bind_vec(self) -> None:
         cfg = self.vec.config
@@ -122,6 +124,18 @@ class D2DEnv:
             'capacity_mbps': {i: float(h['capacity_mbps'][0, r]) for i, r in zip(ids, rows)},
         }
 
+    def _position_nearby(self, anchor) -> Tuple[float, float]:
+        """get_random_position_nearby (position.py:31-45) for one receiver, on the host (E = 1 adapter only)."""
+        import math
+        cfg = self.config
+        rng = self._host_rng
+        while True:
+            theta = 2 * math.pi * rng.random()
+            r = cfg.d2d_radius_m * math.sqrt(rng.random())
+            x, y = float(anchor[0]) + r * math.cos(theta), float(anchor[1]) + r * math.sin(theta)
+            if x * x + y * y <= cfg.cell_radius_m ** 2:
+                return x, y
+
     # ---- gym surface ----------------------------------------------------------------------------
     def reset(self) -> Dict[str, np.ndarray]:
         """envs/d2d_env.py:45-52: new positions, then one uncounted step with random actions."""
@@ -130,9 +144,18 @@ class D2DEnv:
         file_devices = self.config.devices
         if file_devices:                                               # simulator.py:65-66
             pos = self.vec.positions_f64[0].cpu().numpy()
+            placed = set()
             for idx, id_ in enumerate(self.device_ids):
                 if idx and id_ in file_devices and 'position' in file_devices[id_]:
                     pos[idx] = file_devices[id_]['position']
+                    placed.add(id_)
+            # simulator.py:70-73: a DUE receiver that is NOT in the file is drawn around its transmitter's FINAL position - which
+            # may have come from the file - so re-draw those receivers (position.py:31-45) instead of leaving them next to the
+            # transmitter position the device-side reset had drawn
+            index = {id_: i for i, id_ in enumerate(self.device_ids)}
+            for tx_id, rx_id in self.config.link_ids()[self.config.num_cues:self.config.num_cues + self.config.num_due_pairs]:
+                if tx_id in placed and rx_id not in placed:
+                    pos[index[rx_id]] = self._position_nearby(pos[index[tx_id]])
             self.vec.set_positions(pos[None])
         raw = {k: self.action_space['cue' if k.startswith('cue') else 'due'].sample() for k in self.link_keys
                if not k.startswith(BASE_STATION_ID + ':')}             # envs/d2d_env.py:54-60: uplinks and sidelinks only

@@ -55,3 +55,96 @@ def make_sharded_env(total_envs: int, env_config: Optional[dict] = None, seed: i
     local = int(os.environ.get('LOCAL_RANK', rank % max(torch.cuda.device_count(), 1)))
     return VecD2DEnv(count, env_config, device=torch.device('cuda', local), seed=seed, global_env_offset=first,
                      **kwargs)
+
+
+def bind_to_gpu_numa_node(device_index: int) -> Dict[str, object]:
+    """Pin the calling process to the CPUs of the NUMA node the GPU hangs off and prefer that node for new pages, so that the
+    pinned host buffers of the end-to-end path (d2d_host_slot_buffers, torch pin_memory) are allocated next to the GPU's
+    PCIe root instead of wherever rank 0's first touch put them.  Call BEFORE allocating pinned memory.  Best effort: returns
+    what it found / did ({'node': -1, ...} when the platform exposes no topology - containers with one visible node)."""
+    import ctypes
+    import os
+    info: Dict[str, object] = {'node': -1, 'cpus': None, 'mempolicy': False}
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = f'{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0'
+        info['pci'] = bdf
+        with open(f'/sys/bus/pci/devices/{bdf}/numa_node') as f:
+            node = int(f.read().strip())
+        info['node'] = node
+        if node < 0:
+            return info
+        with open(f'/sys/devices/system/node/node{node}/cpulist') as f:
+            cpus = set()
+            for part in f.read().strip().split(','):
+                lo, _, hi = part.partition('-')
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info['cpus'] = len(allowed)
+        # set_mempolicy(MPOL_PREFERRED, nodemask): syscall 238 on x86-64, 237 on aarch64
+        import platform
+        nr = {'x86_64': 238, 'aarch64': 237}.get(platform.machine())
+        if nr is not None and node < 1024:
+            mask = (ctypes.c_ulong * 16)()
+            mask[node // 64] = 1 << (node % 64)
+            rc = ctypes.CDLL(None, use_errno=True).syscall(nr, 1, ctypes.byref(mask), 1024)
+            info['mempolicy'] = rc == 0
+    except Exception as exc:  # noqa: BLE001 - topology files are absent in many containers
+        info['error'] = f'{type(exc).__name__}: {exc}'
+    return info
+
+
+class EpisodeStatsReducer:
+    """Per-episode all-reduce of the statistics vector, off the step stream (BASELINE config #5).
+
+    Two statistics buffers alternate: while episode k + 1 accumulates into one, a side stream sums episode k's replicas and
+    all-reduces the [NUM_STATS] vector over the ranks (NCCL over NVLink on GPUs).  Usage per episode:
+
+        red.begin_episode()          # binds + zeroes this episode's buffer on the step stream
+        env.episode(...) / steps
+        red.end_episode()            # side stream: wait for the episode, reduce, all-reduce; returns at once
+
+    `results` holds one reduced float64 [NUM_STATS] device tensor per finished episode (read them after `finish()`)."""
+
+    def __init__(self, env, group: Optional[dist.ProcessGroup] = None, keep: int = 64) -> None:
+        self.env = env
+        self.group = group
+        self.bufs = [torch.zeros_like(env._stats), torch.zeros_like(env._stats)]
+        self.free_events = [None, None]              # side stream done with buffer i
+        self.side = torch.cuda.Stream(device=env.device)
+        self.k = 0
+        self.keep = keep
+        self.results = []
+        self.all_reduces = 0
+
+    def begin_episode(self) -> None:
+        i = self.k & 1
+        cur = torch.cuda.current_stream(self.env.device)
+        if self.free_events[i] is not None:
+            cur.wait_event(self.free_events[i])      # the reduction of episode k - 2 has read this buffer
+        self.env.bind_stats(self.bufs[i])
+        self.env.reset_stats()
+
+    def end_episode(self) -> None:
+        i = self.k & 1
+        cur = torch.cuda.current_stream(self.env.device)
+        done = torch.cuda.Event()
+        done.record(cur)
+        self.side.wait_event(done)
+        with torch.cuda.stream(self.side):
+            v = self.bufs[i].sum(dim=0)
+            all_reduce_stats(v, self.group)
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+                self.all_reduces += 1
+            free = torch.cuda.Event()
+            free.record(self.side)
+        self.free_events[i] = free
+        self.results.append(v)
+        if len(self.results) > self.keep:
+            self.results.pop(0)
+        self.k += 1
+
+    def finish(self) -> None:
+        torch.cuda.current_stream(self.env.device).wait_stream(self.side)

@@ -162,6 +162,39 @@ class VecD2DEnv:
             raise ValueError(f'positions must be [count][{self.num_devices}][2], got {tuple(src.shape)}')
         _lib.check(self._lib.d2d_set_positions(self._h, ptr, on_dev, int(first_env), int(src.shape[0]), self._stream()))
 
+    def get_positions(self, host: bool = True):
+        """The bound float32 positions [E][V][2] (d2d_get_positions): a fresh device tensor, or a host ndarray.  With the
+        `obs_dyn` output this is the once-per-reset half of the observation table (see obs_static / assemble_obs)."""
+        E, V = self.num_envs, self.num_devices
+        if host:
+            dst = np.empty((E, V, 2), np.float32)
+            _lib.check(self._lib.d2d_get_positions(self._h, dst.ctypes.data, 0, 0, E, self._stream()))
+            return dst
+        dst = torch.empty((E, V, 2), dtype=torch.float32, device=self.device)
+        _lib.check(self._lib.d2d_get_positions(self._h, dst.data_ptr(), 1, 0, E, self._stream()))
+        return dst
+
+    def obs_static(self, positions=None) -> np.ndarray:
+        """Columns 0-3 of the observation table, float32 [E][N][4] = (tx_x, tx_y, rx_x, rx_y) per link (envs/obs_fn.py:55-61),
+        from a host copy of the positions: they change only on reset() / set_positions()."""
+        pos = self.get_positions() if positions is None else np.asarray(positions, np.float32)
+        C_, D = self.config.num_cues, self.config.num_due_pairs
+        tx = np.concatenate([1 + np.arange(C_), 1 + C_ + 2 * np.arange(D)] + ([np.zeros(C_, np.int64)] if self.config.downlinks else []))
+        rx = np.concatenate([np.zeros(C_, np.int64), 2 + C_ + 2 * np.arange(D)] + ([1 + np.arange(C_)] if self.config.downlinks else []))
+        return np.concatenate([pos[:, tx], pos[:, rx]], axis=-1)
+
+    @staticmethod
+    def assemble_obs(obs_static: np.ndarray, obs_dyn: np.ndarray) -> np.ndarray:
+        """The full [E][N][6] table from its once-per-reset and per-step halves (bit-identical to the `obs` output)."""
+        return np.concatenate([obs_static, obs_dyn], axis=-1)
+
+    def sample_actions_philox(self, seed: int, step_index: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Discrete(n).sample() for every agent on the device (d2d_sample_actions): counter-based, a function of
+        (seed, global env, link, step_index) only - the draws d2d_episode makes internally for that step."""
+        a = out if out is not None else torch.empty((self.num_envs, self.num_links), dtype=torch.int32, device=self.device)
+        _lib.check(self._lib.d2d_sample_actions(self._h, a.data_ptr(), int(seed) & 0xFFFFFFFFFFFFFFFF, int(step_index), self._stream()))
+        return a
+
     def sample_actions(self, generator: Optional[torch.Generator] = None) -> torch.Tensor:
         """Uniform draw from the reference's Discrete action spaces (envs/d2d_env.py:36-40, :54-60)."""
         u = torch.rand((self.num_envs, self.num_links), device=self.device, generator=generator)
@@ -199,7 +232,7 @@ class VecD2DEnv:
         return self.obs
 
     # ---- the hot path --------------------------------------------------------------------------
-    def _launch(self, actions: torch.Tensor, out: Optional[StepBuffers] = None) -> None:
+    def _launch(self, actions: torch.Tensor, out: Optional[StepBuffers] = None, inputs_stable: bool = False) -> None:
         if actions.dtype != torch.int32 or not actions.is_cuda or not actions.is_contiguous():
             raise ValueError('actions must be a contiguous int32 CUDA tensor [num_envs][num_links]')
         if tuple(actions.shape) != (self.num_envs, self.num_links):
@@ -215,11 +248,17 @@ class VecD2DEnv:
         io.rb = _ptr(o.rb)
         io.tx_pwr_dBm = _ptr(o.tx_pwr_dbm)
         io.agent_reward = _ptr(o.agent_reward)
+        io.flags = _lib.STEP_INPUTS_STABLE if inputs_stable else 0
         _lib.check(self._lib.d2d_step(self._h, C.byref(io), self._stream()))
 
-    def step(self, actions: torch.Tensor, validate: bool = False, out: Optional[StepBuffers] = None
-             ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, Dict[str, torch.Tensor]]:
+    def step(self, actions: torch.Tensor, validate: bool = False, out: Optional[StepBuffers] = None,
+             inputs_stable: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, Dict[str, torch.Tensor]]:
         """One env.step for all E envs: a single fused kernel launch on the current stream, no host sync.
+
+        inputs_stable=True is the D2D_STEP_INPUTS_STABLE promise of include/d2d_b200.h ("Ordering rule"): `actions` (and the
+        positions) were written before the PREVIOUS step call on this stream - pre-generated action buffers - so the kernel may
+        read them while its predecessor is still running.  The default orders the step after everything earlier in the stream,
+        which is what a loop whose policy writes the actions between steps needs.
 
         actions: int32 [E][N]; < 0 marks an agent absent this step (Appendix B.8).  Returns the preallocated
         (obs [E][N][6], reward [E], done [E] uint8, info) tensors, overwritten by the next call.
@@ -227,7 +266,7 @@ class VecD2DEnv:
         are otherwise the caller's responsibility (the reference accepts them silently, Appendix B.9)."""
         if validate and bool((actions >= self._nvec_dev.to(actions.dtype)).any()):
             raise ValueError('action out of range for its Discrete space')
-        self._launch(actions, out)
+        self._launch(actions, out, inputs_stable)
         o = out if out is not None else self._out
         info = {'capacity_mbps': o.capacity_mbps}
         if o.agent_reward is not None:
@@ -237,7 +276,8 @@ class VecD2DEnv:
                         sinr_db=o.obs[..., 4], snr_db=o.obs[..., 5])
         return o.obs, o.reward, o.done, info
 
-    def step_many(self, actions: torch.Tensor, out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+    def step_many(self, actions: torch.Tensor, out: Optional[Dict[str, torch.Tensor]] = None,
+                  inputs_stable: bool = False) -> Dict[str, torch.Tensor]:
         """T consecutive env.step calls in ONE kernel launch (d2d_step_many): the reference's agent loop
         (examples/simple_env.py:20-33) when the actions of every step are known up front.
 
@@ -254,9 +294,54 @@ class VecD2DEnv:
             raise ValueError('out was allocated for a different number of steps')
         io = _lib.D2DStepIO(actions=actions.data_ptr(), obs=o['obs'].data_ptr(), capacity_mbps=o['capacity_mbps'].data_ptr(),
                             reward=o['reward'].data_ptr(), done=o['done'].data_ptr(), rate_bps=_ptr(o.get('rate_bps')),
-                            rb=_ptr(o.get('rb')), tx_pwr_dBm=_ptr(o.get('tx_pwr_dbm')), agent_reward=_ptr(o.get('agent_reward')))
+                            rb=_ptr(o.get('rb')), tx_pwr_dBm=_ptr(o.get('tx_pwr_dbm')), agent_reward=_ptr(o.get('agent_reward')),
+                            flags=_lib.STEP_INPUTS_STABLE if inputs_stable else 0)
         _lib.check(self._lib.d2d_step_many(self._h, C.byref(io), T, self._stream()))
         return o
+
+    def episode(self, num_steps: int = EPISODE_LENGTH, actions: Optional[torch.Tensor] = None,
+                out: Optional[Dict[str, torch.Tensor]] = None, reset_seed: Optional[int] = None,
+                action_seed: Optional[int] = None, record_actions: bool = False) -> Dict[str, torch.Tensor]:
+        """One whole episode in ONE launch (d2d_episode): D2DEnv.reset (envs/d2d_env.py:45-52: new positions, num_steps = 0,
+        one uncounted step with sampled actions) and `num_steps` counted steps.  Every output has a leading
+        [num_steps + 1] dimension; slice 0 is the reset step's observation, slice t the t-th counted step.
+
+        actions=None samples every step's actions on the device (Discrete.sample, envs/d2d_env.py:54-60; keyed by
+        action_seed - default: this episode's reset key) - the kernel then reads no global memory but its constants;
+        otherwise actions is int32 [num_steps + 1][E][N].  reset_seed=None continues the env's own episode key sequence,
+        exactly like reset().  record_actions adds 'actions' (what was drawn) to the result."""
+        T1 = int(num_steps) + 1
+        if reset_seed is None:
+            reset_seed = (self.seed + 0x9E3779B97F4A7C15 * self._episode) & 0xFFFFFFFFFFFFFFFF
+            self._episode += 1
+        if action_seed is None:
+            action_seed = reset_seed
+        draw = actions is None
+        if not draw:
+            if actions.dtype != torch.int32 or not actions.is_cuda or not actions.is_contiguous() or \
+                    tuple(actions.shape) != (T1, self.num_envs, self.num_links):
+                raise ValueError(f'actions must be a contiguous int32 CUDA tensor of shape {(T1, self.num_envs, self.num_links)}')
+        o = out if out is not None else self.alloc_many_outputs(T1)
+        if int(o['obs'].shape[0]) != T1:
+            raise ValueError('out was allocated for a different number of steps')
+        if record_actions and 'actions' not in o:
+            o['actions'] = torch.empty((T1, self.num_envs, self.num_links), dtype=torch.int32, device=self.device)
+        io = _lib.D2DStepIO(actions=_ptr(actions), obs=o['obs'].data_ptr(), capacity_mbps=o['capacity_mbps'].data_ptr(),
+                            reward=o['reward'].data_ptr(), done=o['done'].data_ptr(), rate_bps=_ptr(o.get('rate_bps')),
+                            rb=_ptr(o.get('rb')), tx_pwr_dBm=_ptr(o.get('tx_pwr_dbm')), agent_reward=_ptr(o.get('agent_reward')),
+                            actions_out=_ptr(o.get('actions')) if draw else None)
+        _lib.check(self._lib.d2d_episode(self._h, C.byref(io), int(num_steps), int(reset_seed) & 0xFFFFFFFFFFFFFFFF,
+                                         int(action_seed) & 0xFFFFFFFFFFFFFFFF, _lib.EPISODE_DRAW_ACTIONS if draw else 0,
+                                         self._stream()))
+        return o
+
+    def bind_stats(self, stats: torch.Tensor) -> None:
+        """Accumulate the episode statistics into another float64 [STATS_REPLICAS][NUM_STATS] device tensor from now on (e.g.
+        one of two buffers alternated per episode, so that a side stream can reduce the finished episode's sums)."""
+        if stats.dtype != torch.float64 or tuple(stats.shape) != (_lib.STATS_REPLICAS, _lib.NUM_STATS) or not stats.is_cuda:
+            raise ValueError('stats must be a float64 CUDA tensor [STATS_REPLICAS][NUM_STATS]')
+        self._stats = stats
+        self._bind(True)
 
     def alloc_many_outputs(self, T: int) -> Dict[str, torch.Tensor]:
         E, N, dev = self.num_envs, self.num_links, self.device
@@ -272,9 +357,12 @@ class VecD2DEnv:
                      tx_pwr_dbm=torch.empty((T, E, N), dtype=torch.int16, device=dev))
         return o
 
-    def capture_steps(self, actions_seq, outs_seq=None) -> 'torch.cuda.CUDAGraph':
+    def capture_steps(self, actions_seq, outs_seq=None, inputs_stable: bool = False) -> 'torch.cuda.CUDAGraph':
         """Capture len(actions_seq) consecutive steps (step i reads actions_seq[i], writes outs_seq[i] or the
-        default buffers) into one CUDA graph: replay() then costs one launch for the whole sequence."""
+        default buffers) into one CUDA graph: replay() then costs one launch for the whole sequence.
+        inputs_stable: the action buffers are filled before every replay() and not rewritten during it (see step()); the
+        first step of the graph is always ordered after whatever precedes the replay.  With ShadowingPathLoss the step-call
+        counter lives on the device, so every replay draws fresh shadowing values like the reference (path_loss.py:75-81)."""
         outs_seq = outs_seq if outs_seq is not None else [None] * len(actions_seq)
         graph = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream(device=self.device)
@@ -282,20 +370,22 @@ class VecD2DEnv:
         with torch.cuda.stream(side):
             with torch.cuda.graph(graph, stream=side):
                 for a, o in zip(actions_seq, outs_seq):
-                    self._launch(a, o)
+                    self._launch(a, o, inputs_stable)
         torch.cuda.current_stream(self.device).wait_stream(side)
         return graph
 
     def _host_io(self, actions: np.ndarray, out: Dict[str, np.ndarray]) -> '_lib.D2DStepIO':
         if actions.dtype != np.int32 or not actions.flags['C_CONTIGUOUS'] or actions.shape != (self.num_envs, self.num_links):
             raise ValueError(f'actions must be a C-contiguous int32 array of shape {(self.num_envs, self.num_links)}')
-        return _lib.D2DStepIO(actions=actions.ctypes.data, obs=out['obs'].ctypes.data,
-                              capacity_mbps=out['capacity_mbps'].ctypes.data, reward=out['reward'].ctypes.data,
-                              done=out['done'].ctypes.data,
+        return _lib.D2DStepIO(actions=actions.ctypes.data, obs=out['obs'].ctypes.data if 'obs' in out else None,
+                              capacity_mbps=out['capacity_mbps'].ctypes.data if 'capacity_mbps' in out else None,
+                              reward=out['reward'].ctypes.data if 'reward' in out else None,
+                              done=out['done'].ctypes.data if 'done' in out else None,
                               rate_bps=out['rate_bps'].ctypes.data if 'rate_bps' in out else None,
                               rb=out['rb'].ctypes.data if 'rb' in out else None,
                               tx_pwr_dBm=out['tx_pwr_dbm'].ctypes.data if 'tx_pwr_dbm' in out else None,
-                              agent_reward=out['agent_reward'].ctypes.data if 'agent_reward' in out else None)
+                              agent_reward=out['agent_reward'].ctypes.data if 'agent_reward' in out else None,
+                              obs_dyn=out['obs_dyn'].ctypes.data if 'obs_dyn' in out else None)
 
     def step_host(self, actions: np.ndarray, out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
         """End-to-end host call (d2d_step_host): host int32 actions in, host arrays out, copies included.
@@ -316,10 +406,46 @@ class VecD2DEnv:
     def step_host_wait(self, slot: int) -> None:
         _lib.check(self._lib.d2d_step_host_wait(self._h, int(slot)))
 
-    def alloc_host_outputs(self, pinned: bool = False, info: bool = True) -> Dict[str, np.ndarray]:
+    _HOST_FIELDS = (('obs', _lib.OUT_OBS, 6, np.float32), ('obs_dyn', _lib.OUT_OBS_DYN, 2, np.float32),
+                    ('capacity_mbps', _lib.OUT_CAPACITY, 1, np.float32), ('reward', _lib.OUT_REWARD, 0, np.float32),
+                    ('done', _lib.OUT_DONE, 0, np.uint8), ('rate_bps', _lib.OUT_RATE, 1, np.float32), ('rb', _lib.OUT_RB, 1, np.int16),
+                    ('tx_pwr_dbm', _lib.OUT_TX_PWR, 1, np.int16), ('agent_reward', _lib.OUT_AGENT_REWARD, 1, np.float32))
+
+    def host_slot_buffers(self, slot: int, outputs=('obs_dyn', 'capacity_mbps', 'reward', 'done')) -> Dict[str, np.ndarray]:
+        """Library-owned PINNED host buffers of pipeline slot 0 / 1 (d2d_host_slot_buffers) as numpy views: 'actions' (write
+        the step's int32 [E][N] actions here) plus the requested outputs.  Passing the returned dict to
+        step_host_async(out['actions'], out, slot) moves each direction with ONE copy.  The default outputs are the per-step
+        part of a step's results - 12 N + 5 bytes per env-step instead of 28 N + 5 with the full observation table, whose
+        position columns only change on reset (get_positions / obs_static / assemble_obs)."""
         E, N = self.num_envs, self.num_links
-        spec = {'obs': ((E, N, 6), torch.float32), 'capacity_mbps': ((E, N), torch.float32),
+        mask = 0
+        for name, bit, _w, _dt in self._HOST_FIELDS:
+            if name in outputs:
+                mask |= bit
+        unknown = set(outputs) - {f[0] for f in self._HOST_FIELDS}
+        if unknown:
+            raise ValueError(f'unknown outputs {sorted(unknown)}')
+        io = _lib.D2DStepIO()
+        _lib.check(self._lib.d2d_host_slot_buffers(self._h, int(slot), mask, C.byref(io)))
+
+        def view(ptr, shape, dtype):
+            n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+            return np.frombuffer((C.c_char * n).from_address(ptr), dtype=dtype).reshape(shape)
+
+        out = {'actions': view(io.actions, (E, N), np.int32)}
+        ptrs = {'obs': io.obs, 'obs_dyn': io.obs_dyn, 'capacity_mbps': io.capacity_mbps, 'reward': io.reward, 'done': io.done,
+                'rate_bps': io.rate_bps, 'rb': io.rb, 'tx_pwr_dbm': io.tx_pwr_dBm, 'agent_reward': io.agent_reward}
+        for name, _bit, width, dt in self._HOST_FIELDS:
+            if name in outputs:
+                out[name] = view(ptrs[name], (E, N, width) if width > 1 else (E, N) if width == 1 else (E,), dt)
+        return out
+
+    def alloc_host_outputs(self, pinned: bool = False, info: bool = True, dyn: bool = False) -> Dict[str, np.ndarray]:
+        """Caller-owned host arrays for step_host*: the full observation table, or with dyn=True its per-step columns only."""
+        E, N = self.num_envs, self.num_links
+        spec = {'capacity_mbps': ((E, N), torch.float32),
                 'reward': ((E,), torch.float32), 'done': ((E,), torch.uint8)}
+        spec['obs_dyn' if dyn else 'obs'] = ((E, N, 2), torch.float32) if dyn else ((E, N, 6), torch.float32)
         if self.per_agent_reward:
             spec['agent_reward'] = ((E, N), torch.float32)
         if info:

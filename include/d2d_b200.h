@@ -15,7 +15,23 @@
  *    stream-ordered and asynchronous unless stated; d2d_step performs no allocation and no host
  *    synchronisation, so it can be captured into a CUDA graph.
  *  - a handle is bound to one CUDA device and is not thread-safe.  Multi-GPU = one process (one
- *    handle) per GPU, each owning a contiguous slice of the global environment batch.
+ *    handle) per GPU, each owning a contiguous slice of the global environment batch.  Every entry point
+ *    selects the handle's device for the duration of the call and restores the caller's current device.
+ *
+ * Ordering rule (programmatic dependent launch).  Step kernels are launched with programmatic stream
+ * serialisation: a launch may begin while the previous kernel in `stream` is still running and orders itself
+ * with griddepcontrol.wait.  By DEFAULT a step kernel executes that wait before it reads anything the caller
+ * or another kernel may have written - this step's `actions`, the bound positions - so any producer earlier
+ * in `stream` (a policy / sampling kernel, a copy, d2d_reset, d2d_set_positions, d2d_episode) is complete
+ * and visible, exactly as with an ordinary launch.  Setting D2D_STEP_INPUTS_STABLE in d2d_step_io.flags is
+ * the caller's promise that every write to this step's `actions` and to the positions was enqueued on
+ * `stream` BEFORE the previous d2d_step / d2d_step_many call on this handle (or had completed by then): the
+ * kernel then loads its inputs and computes the whole step while its predecessor drains, and waits only
+ * before touching the step counters and the output buffers.  The library honours the flag only when the
+ * previous kernel it enqueued for this handle was a step kernel on the same `stream`; after d2d_reset,
+ * d2d_set_positions, d2d_episode, or on a different stream, the next step is ordered the default way
+ * whatever the flag says.  Pre-generated action buffers (replay, evaluation, benchmarks, CUDA graphs of
+ * scripted steps) may set it; a loop whose policy writes the actions between steps must not.
  *
  * Index conventions (devices.py:20-25, simulator.py:34-48, envs/d2d_env.py:55-60):
  *   C = num_cues, D = num_due_pairs, N = C + D links, V = 1 + C + 2D devices.
@@ -34,7 +50,7 @@
 #define D2D_API __attribute__((visibility("default")))
 #endif
 
-#define D2D_ABI_VERSION 4
+#define D2D_ABI_VERSION 5
 
 typedef struct d2d_handle d2d_handle_t;
 
@@ -111,6 +127,9 @@ typedef struct d2d_link {
     double path_loss_const_dB;  /* D2D_PL_COST_HATA only: the path-loss constant toward this link's receiver */
 } d2d_link_t;
 
+/* d2d_step_io.flags */
+#define D2D_STEP_INPUTS_STABLE 1u   /* see "Ordering rule" above; 0 is always safe */
+
 /* Buffers of one step.  All pointers are device pointers for d2d_step and host pointers for
  * d2d_step_host.  `actions` is required; any output may be NULL to skip it. */
 typedef struct d2d_step_io {
@@ -127,7 +146,18 @@ typedef struct d2d_step_io {
     int16_t *tx_pwr_dBm;        /* [E][N]  decoded Tx power (envs/d2d_env.py:96) */
     float *agent_reward;        /* [E][N]  per-agent reward of SHANNON / CUE_SINR_SHANNON (0 for absent agents); with
                                    SYSTEM_CAPACITY the env's scalar broadcast to its acting agents (envs/reward_fn.py:44) */
+    float *obs_dyn;             /* [E][N][2] (sinr_dB, snr_dB): the columns of `obs` that change between resets
+                                   (envs/obs_fn.py:55-61: the other four are device positions, which only reset() /
+                                   set_position move - fetch those once per reset with d2d_get_positions).  A host loop that
+                                   asks for obs_dyn instead of obs moves 8N instead of 24N bytes per env-step. */
+    int32_t *actions_out;       /* d2d_episode only: [T + 1][E][N] record of the actions taken (NULL to skip) */
+    uint32_t flags;             /* D2D_STEP_* */
+    uint32_t reserved0;
 } d2d_step_io_t;
+
+/* bits of an output mask (d2d_host_slot_buffers) */
+enum { D2D_OUT_OBS = 1, D2D_OUT_CAPACITY = 2, D2D_OUT_REWARD = 4, D2D_OUT_DONE = 8, D2D_OUT_RATE = 16, D2D_OUT_RB = 32,
+       D2D_OUT_TX_PWR = 64, D2D_OUT_AGENT_REWARD = 128, D2D_OUT_OBS_DYN = 256 };
 
 /* Episode statistics accumulated on the device by d2d_step when a stats buffer is bound;
  * this is the vector the multi-GPU shell all-reduces over NCCL (never inside the step). */
@@ -170,6 +200,18 @@ D2D_API int d2d_set_positions(d2d_handle_t *h, const double *src, int src_on_dev
 D2D_API int d2d_reset(d2d_handle_t *h, uint64_t seed, uint64_t first_global_env, const uint8_t *env_mask,
                       void *stream);
 
+/* Copies the bound float32 positions of envs [first_env, first_env + count) to dst, float32 [count][V][2] (host memory
+ * unless dst_on_device; a host copy synchronises the stream).  With d2d_step_io.obs_dyn this is the once-per-reset half
+ * of the observation table: row j of obs is (pos[tx_j], pos[rx_j], obs_dyn[j]) with the device indices of the header
+ * comment (CUE j: tx = 1 + j, rx = 0; DUE pair d: tx = 1 + C + 2d, rx = tx + 1). */
+D2D_API int d2d_get_positions(d2d_handle_t *h, float *dst, int dst_on_device, int64_t first_env, int64_t count, void *stream);
+
+/* Discrete(n).sample() for every agent of every env (envs/d2d_env.py:54-60; gym.spaces.Discrete.sample is uniform over
+ * 0 .. n - 1): int32 [E][N] device buffer, counter-based Philox4x32-10 draws keyed by (seed, first_global_env + env, link,
+ * step_index), the same values d2d_episode draws internally for that step (step_index 0 = the reset step).  DOWNLINK
+ * links, which the reference's reset never samples, are marked absent (-1). */
+D2D_API int d2d_sample_actions(d2d_handle_t *h, int32_t *actions, uint64_t seed, uint32_t step_index, void *stream);
+
 /* Replaces D2DEnv.step (envs/d2d_env.py:62-71): _decode_action (:93-101), Simulator.step
  * (simulator.py:77-154), LinearObsFunction (envs/obs_fn.py:43-61), SystemCapacityRewardFunction
  * (envs/reward_fn.py:27-44), the done flag (:68) and the info fields (:106-116), for all E envs. */
@@ -181,6 +223,20 @@ D2D_API int d2d_step(d2d_handle_t *h, const d2d_step_io_t *io, void *stream);
  * leading [num_steps] dimension: actions [T][E][N], obs [T][E][N][6], reward [T][E], ...; slice t holds exactly what the
  * t-th d2d_step call would have written.  An env's positions are read once for its T steps. */
 D2D_API int d2d_step_many(d2d_handle_t *h, const d2d_step_io_t *io, int32_t num_steps, void *stream);
+
+/* One whole episode in ONE launch: D2DEnv.reset (envs/d2d_env.py:45-52: Simulator.reset draws new
+ * positions - the values d2d_reset(reset_seed) draws - num_steps = 0, one UNCOUNTED step with sampled actions produces the
+ * initial observation) followed by num_steps counted steps, the agent loop of examples/simple_env.py:20-33.  Every io
+ * buffer has a leading [num_steps + 1] dimension: slice 0 is the reset step (done = 0; it enters no statistic), slice t
+ * the t-th counted step, exactly what d2d_reset + d2d_step x (num_steps + 1) would have produced on the same actions.
+ * With D2D_EPISODE_DRAW_ACTIONS the actions are sampled on the device (d2d_sample_actions(action_seed, t) for slice t;
+ * io->actions may be NULL, io->actions_out records them); otherwise io->actions is [num_steps + 1][E][N].  The drawn
+ * positions are left in the bound state and the step counters at num_steps, so d2d_step can continue the episode.
+ * Default-topology configurations run it as one launch of the warp kernel that reads no global memory but its
+ * constants; others compose it from d2d_reset, d2d_sample_actions and d2d_step launches. */
+#define D2D_EPISODE_DRAW_ACTIONS 1u
+D2D_API int d2d_episode(d2d_handle_t *h, const d2d_step_io_t *io, int32_t num_steps, uint64_t reset_seed, uint64_t action_seed,
+                        uint32_t episode_flags, void *stream);
 
 /* Same call with HOST buffers: copies the actions to the device, steps, copies every non-NULL output
  * back and synchronises the stream.  This is the end-to-end path a CPU-side caller (the reference's
@@ -194,6 +250,14 @@ D2D_API int d2d_step_host(d2d_handle_t *h, const d2d_step_io_t *host_io, void *s
  * pinned.  d2d_step_host(...) == d2d_step_host_async(..., 0, ...) + d2d_step_host_wait(0). */
 D2D_API int d2d_step_host_async(d2d_handle_t *h, const d2d_step_io_t *host_io, int slot, void *stream);
 D2D_API int d2d_step_host_wait(d2d_handle_t *h, int slot);
+
+/* Library-owned PINNED host buffers of pipeline slot `slot` for the outputs in `outputs` (a D2D_OUT_* mask): fills
+ * host_io with pointers into one contiguous pinned allocation (actions first, then the requested outputs, each 256-byte
+ * aligned) that has a device twin of the same layout.  Passing this host_io to d2d_step_host_async(slot) brings all
+ * outputs back with ONE copy (the caller-owned-buffer form issues one per output); `actions` may be replaced by any
+ * other host buffer of the caller's.  The buffers live until the handle
+ * is destroyed or the slot is re-laid-out with another mask. */
+D2D_API int d2d_host_slot_buffers(d2d_handle_t *h, int slot, uint32_t outputs, d2d_step_io_t *host_io);
 
 /* Materialises the reference's per-agent observation layout (envs/obs_fn.py:43-53) from the compact
  * table: out[e][i] = concat(table[e][i], table[e][k] for k != i), float32 [E][N][6N].  O(N^2) bytes:

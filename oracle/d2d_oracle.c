@@ -270,36 +270,71 @@ void d2d_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* uniform-in-disc draw: theta = 2*pi*u1, r = radius*sqrt(u2)  (position.py:24-28, 41-44) */
-static void disc_draw(uint64_t seed, uint64_t genv, uint32_t dev, uint32_t attempt, double radius,
-                      double *x, double *y) {
-    uint32_t ctr[4] = {(uint32_t)genv, (uint32_t)(genv >> 32), dev, attempt};
-    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, o[4];
-    d2d_oracle_philox4x32_10(ctr, key, o);
-    double u1 = ((double)(o[0] >> 8) + 0.5) * (1.0 / 16777216.0), u2 = ((double)(o[1] >> 8) + 0.5) * (1.0 / 16777216.0);
+/* uniform-in-disc draw from two 32-bit words: theta = 2*pi*u1, r = radius*sqrt(u2)  (position.py:24-28, 41-44); 24-bit
+ * uniforms centred in their cell */
+static void disc_from_words(uint32_t w0, uint32_t w1, double radius, double *x, double *y) {
+    double u1 = ((double)(w0 >> 8) + 0.5) * (1.0 / 16777216.0), u2 = ((double)(w1 >> 8) + 0.5) * (1.0 / 16777216.0);
     double r = radius * sqrt(u2);
     *x = r * cos(2.0 * M_PI * u1);
     *y = r * sin(2.0 * M_PI * u1);
 }
+static void reset_block(uint64_t seed, uint64_t genv, uint32_t unit, uint32_t attempt, uint32_t o[4]) {
+    uint32_t ctr[4] = {(uint32_t)genv, (uint32_t)(genv >> 32), unit, attempt};
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    d2d_oracle_philox4x32_10(ctr, key, o);
+}
 
+/* The product's draw scheme (gym_d2d_b200/csrc/d2d_common.cuh): an env's devices are drawn in UNITS of one Philox block -
+ * unit u < CU = ceil(C/2): CUE 2u from words (0,1), CUE 2u+1 from words (2,3); unit CU + d: DUE pair d, attempt 0 = transmitter
+ * from words (0,1) and the first receiver offset from (2,3), attempt a >= 1 = offsets 2a-1 from (0,1) and 2a from (2,3). */
 void d2d_oracle_reset_positions(const d2d_oracle_cfg *cfg, double cell_radius_m, double d2d_radius_m,
                                 uint64_t seed, uint64_t first_global_env, int64_t E, double *positions) {
-    const int C = cfg->num_cues, D = cfg->num_due_pairs, V = 1 + C + 2 * D;
+    const int C = cfg->num_cues, D = cfg->num_due_pairs, V = 1 + C + 2 * D, CU = (C + 1) / 2;
     for (int64_t e = 0; e < E; ++e) {
         double *p = positions + (size_t)e * V * 2;
         uint64_t g = first_global_env + (uint64_t)e;
+        uint32_t o[4];
         p[0] = 0.0; p[1] = 0.0;                                    /* simulator.py:63-64 */
-        for (int v = 1; v <= C; ++v) disc_draw(seed, g, (uint32_t)v, 0, cell_radius_m, &p[2 * v], &p[2 * v + 1]);
+        for (int j = 0; j < C; ++j) {
+            int v = 1 + j;
+            reset_block(seed, g, (uint32_t)(j >> 1), 0, o);
+            if (j & 1) disc_from_words(o[2], o[3], cell_radius_m, &p[2 * v], &p[2 * v + 1]);
+            else disc_from_words(o[0], o[1], cell_radius_m, &p[2 * v], &p[2 * v + 1]);
+        }
         for (int d = 0; d < D; ++d) {
             int t = 1 + C + 2 * d, r = t + 1;
-            disc_draw(seed, g, (uint32_t)t, 0, cell_radius_m, &p[2 * t], &p[2 * t + 1]);
-            /* position.py:38-44: redraw until inside the cell (bounded to 64 attempts here) */
-            for (uint32_t a = 0; a < 64; ++a) {
+            reset_block(seed, g, (uint32_t)(CU + d), 0, o);
+            disc_from_words(o[0], o[1], cell_radius_m, &p[2 * t], &p[2 * t + 1]);
+            /* position.py:38-44: redraw until inside the cell (bounded to 64 candidates here) */
+            for (uint32_t k = 0; k < 64; ++k) {
                 double ox, oy;
-                disc_draw(seed, g, (uint32_t)r, a, d2d_radius_m, &ox, &oy);
+                if (k && (k & 1)) reset_block(seed, g, (uint32_t)(CU + d), (k + 1) >> 1, o);
+                if (k & 1) disc_from_words(o[0], o[1], d2d_radius_m, &ox, &oy);
+                else disc_from_words(o[2], o[3], d2d_radius_m, &ox, &oy);
                 p[2 * r] = p[2 * t] + ox; p[2 * r + 1] = p[2 * t + 1] + oy;
                 if (p[2 * r] * p[2 * r] + p[2 * r + 1] * p[2 * r + 1] <= cell_radius_m * cell_radius_m) break;
             }
+        }
+    }
+}
+
+/* The product's on-device Discrete(n).sample() (envs/d2d_env.py:54-60; uniform over 0 .. n-1): CUE l and DUE pair l share the
+ * block Philox(counter = (global env, l, t >> 1), key = seed ^ 0xA511E9B3); word = 2 (t & 1) + (1 for the DUE link);
+ * a = floor(word * n / 2^32).  Links beyond C + D (DOWNLINK) are absent (-1).  actions int32 [E][N]. */
+void d2d_oracle_sample_actions(const d2d_oracle_cfg *cfg, int32_t num_links, uint64_t seed, uint64_t first_global_env, uint32_t t,
+                               int64_t E, int32_t *actions) {
+    const int C = cfg->num_cues, D = cfg->num_due_pairs, L = C > D ? C : D;
+    const uint32_t n_cue = (uint32_t)(cfg->num_rbs * cfg->n_pwr_cue), n_due = (uint32_t)(cfg->num_rbs * cfg->n_pwr_due);
+    for (int64_t e = 0; e < E; ++e) {
+        uint64_t g = first_global_env + (uint64_t)e;
+        int32_t *a = actions + (size_t)e * num_links;
+        for (int j = C + D; j < num_links; ++j) a[j] = -1;
+        for (int l = 0; l < L; ++l) {
+            uint32_t ctr[4] = {(uint32_t)g, (uint32_t)(g >> 32), (uint32_t)l, t >> 1};
+            uint32_t key[2] = {(uint32_t)seed ^ 0xA511E9B3u, (uint32_t)(seed >> 32)}, o[4];
+            d2d_oracle_philox4x32_10(ctr, key, o);
+            if (l < C) a[l] = (int32_t)(((uint64_t)o[2 * (t & 1)] * n_cue) >> 32);
+            if (l < D) a[C + l] = (int32_t)(((uint64_t)o[2 * (t & 1) + 1] * n_due) >> 32);
         }
     }
 }

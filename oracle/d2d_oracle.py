@@ -144,6 +144,8 @@ def lib():
         L.d2d_oracle_philox4x32_10.restype = None
         L.d2d_oracle_reset_positions.argtypes = [C.POINTER(_Cfg), d, d, C.c_uint64, C.c_uint64, C.c_int64, vp]
         L.d2d_oracle_reset_positions.restype = None
+        L.d2d_oracle_sample_actions.argtypes = [C.POINTER(_Cfg), C.c_int32, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int64, vp]
+        L.d2d_oracle_sample_actions.restype = None
         _lib = L
     return _lib
 
@@ -253,6 +255,15 @@ def reset_positions(cfg: OracleConfig, seed: int, first_global_env: int, num_env
     ccfg = _c_cfg(cfg)
     lib().d2d_oracle_reset_positions(C.byref(ccfg), cfg.cell_radius_m, cfg.d2d_radius_m, seed, first_global_env,
                                      num_envs, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def sample_actions(cfg: OracleConfig, seed: int, first_global_env: int, step_index: int, num_envs: int) -> np.ndarray:
+    """The product's counter-based Discrete(n).sample() (d2d_sample_actions / d2d_episode), restated: int32 [E][N]."""
+    out = np.empty((num_envs, cfg.num_links), np.int32)
+    ccfg = _c_cfg(cfg)
+    lib().d2d_oracle_sample_actions(C.byref(ccfg), cfg.num_links, seed & 0xFFFFFFFFFFFFFFFF, first_global_env, step_index, num_envs,
+                                    out.ctypes.data_as(C.c_void_p))
     return out
 
 

@@ -44,3 +44,44 @@ def check_against_oracle(out, ref, rtol=RTOL, pos_rtol=RTOL):
     worst['rate'] = assert_rel(out['rate_bps'], ref['rate_bps'], rtol, 'rate_bps')
     worst['reward'] = assert_rel(out['reward'], ref['reward'], rtol, 'reward')
     return worst
+
+
+def ks_against_quantiles(sample, levels, quantiles):
+    """Two-sample Kolmogorov-Smirnov distance between `sample` and the sample a quantile table (levels, quantiles) was
+    made from: max |F_sample(q_i) - level_i| over the table's points."""
+    x = np.sort(np.asarray(sample, np.float64))
+    f = np.searchsorted(x, quantiles, side='right') / x.size
+    return float(np.max(np.abs(f - levels)))
+
+
+def check_reset_distribution(positions, num_cues, fixture, alpha_c=1.95):
+    """positions [E][V][2] drawn by the product's reset scheme against tests/golden/reset_distribution.npz (quantile tables of
+    the UNMODIFIED reference's get_random_position / get_random_position_nearby, position.py:18-45).  alpha_c = 1.95 is the
+    two-sample KS coefficient for alpha = 0.001: D < c sqrt((n + m) / (n m))."""
+    pos = np.asarray(positions, np.float64)
+    Rc, d, m = float(fixture['cell_radius_m']), float(fixture['d2d_radius_m']), int(fixture['samples'])
+    lv = fixture['levels']
+    cue = pos[:, 1:1 + num_cues].reshape(-1, 2)
+    tx = pos[:, 1 + num_cues::2].reshape(-1, 2)
+    rx = pos[:, 2 + num_cues::2].reshape(-1, 2)
+    off = rx - tx
+    band = np.sqrt((tx ** 2).sum(-1)) > Rc - d
+    stats = {
+        'cue_r2': (cue ** 2).sum(-1) / Rc ** 2,
+        'cue_theta': np.mod(np.arctan2(cue[:, 1], cue[:, 0]) / (2 * np.pi), 1.0),
+        'off_r2': (off[~band] ** 2).sum(-1) / d ** 2,
+        'off_theta': np.mod(np.arctan2(off[~band, 1], off[~band, 0]) / (2 * np.pi), 1.0),
+        'edge_dr': np.sqrt((rx[band] ** 2).sum(-1)) - np.sqrt((tx[band] ** 2).sum(-1)),
+        'edge_off_r2': (off[band] ** 2).sum(-1) / d ** 2,
+    }
+    out = {}
+    for name, sample in stats.items():
+        n = sample.size
+        assert n > 1000, f'{name}: only {n} samples'
+        dist = ks_against_quantiles(sample, lv, fixture[name])
+        bound = alpha_c * np.sqrt((n + m) / (n * m)) + 0.5 / lv.size      # + the table's own resolution
+        assert dist < bound, f'{name}: KS distance {dist:.4f} >= {bound:.4f} (n = {n})'
+        out[name] = (dist, bound)
+    # the share of transmitters in the edge band is itself a property of the uniform-in-disc draw
+    assert abs(band.mean() - float(fixture['edge_fraction'])) < 4 * np.sqrt(0.0784 * 0.9216 / band.size)
+    return out

@@ -1,0 +1,416 @@
+"""GPU tier (-m gpu), second batch: the episode path (device-side reset, on-device action sampling, d2d_episode), the
+per-step observation columns (obs_dyn) and packed host slots, the programmatic-dependent-launch ordering rule, and the
+device guard.  Same conventions as test_gpu_parity.py: everything goes through the C ABI; the oracle is the checker.
+"""
+import numpy as np
+import pytest
+
+from oracle import d2d_oracle as O
+from tests._util import check_reset_distribution
+from tests.test_gpu_parity import CONFIGS, make_vec
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+
+# ---- reset: the distribution of the reference's own sampler (position.py:18-45) -------------------------------------------
+def test_reset_distribution_matches_reference_sampler(golden_dir):
+    fx = np.load(golden_dir / 'reset_distribution.npz')
+    env = make_vec(8192, seed=99)
+    env.reset()
+    torch.cuda.synchronize()
+    check_reset_distribution(env.positions.cpu().numpy(), 25, fx)
+    out = env.episode(2)                                   # the fused kernel draws the same way
+    torch.cuda.synchronize()
+    check_reset_distribution(env.positions.cpu().numpy(), 25, fx)
+    assert out['obs'].shape == (3, 8192, 50, 6)
+    env.close()
+
+
+def test_sample_actions_match_oracle_and_are_uniform():
+    for name in ('default', 'small', 'block_min'):
+        kw = CONFIGS[name]
+        cfg = O.OracleConfig(**kw)
+        E = 3000
+        env = make_vec(E, kw, global_env_offset=77)
+        for t in (0, 1, 2, 7):
+            got = env.sample_actions_philox(seed=1234, step_index=t).cpu().numpy()
+            want = O.sample_actions(cfg, 1234, 77, t, E)
+            np.testing.assert_array_equal(got, want)
+        a = np.concatenate([env.sample_actions_philox(5, t).cpu().numpy() for t in range(8)])
+        nvec = env.action_nvec
+        assert (a >= 0).all() and (a < nvec).all()
+        # uniform over 0 .. n - 1 (gym.spaces.Discrete.sample): mean (n - 1) / 2, every value's share 1 / n
+        assert np.abs(a.mean(0) / ((nvec - 1) / 2) - 1).max() < 0.03
+        j = 0
+        counts = np.bincount(a[:, j], minlength=int(nvec[j]))
+        expect = a.shape[0] / nvec[j]
+        assert np.abs(counts - expect).max() < 6 * np.sqrt(expect) + 1
+        env.close()
+
+
+# ---- d2d_episode == d2d_reset + d2d_sample_actions + d2d_step x (T + 1) --------------------------------------------------------
+@pytest.mark.parametrize('name', ['default', 'small', 'one_rb_crowded', 'block_min', 'dense_small'])
+@pytest.mark.parametrize('given_actions', [False, True])
+def test_episode_equals_reset_plus_single_steps(name, given_actions):
+    kw = CONFIGS[name]
+    E, T = 257, 10
+    fused = make_vec(E, kw, seed=31, global_env_offset=5)
+    single = make_vec(E, kw, seed=31, global_env_offset=5)
+    for ep in range(2):                                     # two consecutive episodes: the key sequence advances alike
+        key = (31 + 0x9E3779B97F4A7C15 * ep) & 0xFFFFFFFFFFFFFFFF
+        fused.reset_stats(); single.reset_stats()
+        acts = None
+        if given_actions:
+            acts = torch.stack([single.sample_actions() for _ in range(T + 1)]).contiguous()
+        out = fused.episode(T, actions=acts, record_actions=True)
+        torch.cuda.synchronize()
+        # positions: exactly what reset() draws for the same episode key
+        single.reset(mask=torch.ones(E, dtype=torch.uint8, device='cuda'))
+        assert torch.equal(fused.positions, single.positions)
+        assert (fused.step_count == T).all()
+        for t in range(T + 1):
+            a = acts[t] if given_actions else single.sample_actions_philox(key, t)
+            if not given_actions:
+                assert torch.equal(out['actions'][t], a)
+            if t == 0:                                      # envs/d2d_env.py:50: the reset step is not counted
+                single._bind(False)
+            obs, reward, done, info = single.step(a)
+            single._bind(True)
+            torch.cuda.synchronize()
+            assert torch.equal(out['obs'][t], obs), (name, t)
+            assert torch.equal(out['capacity_mbps'][t], info['capacity_mbps'])
+            assert torch.equal(out['rate_bps'][t], info['rate_bps'])
+            assert torch.equal(out['rb'][t], info['rb']) and torch.equal(out['tx_pwr_dbm'][t], info['tx_pwr_dbm'])
+            assert torch.equal(out['reward'][t], reward)
+            assert (out['done'][t] == (1 if t >= 10 else 0)).all()
+        assert (single.step_count == T).all()
+        sf, ss = fused.stats(), single.stats()
+        assert sf['env_steps'] == ss['env_steps'] == T * E
+        assert sf['penalties'] == ss['penalties'] and sf['rescues'] == ss['rescues']
+        for k in ('sum_reward', 'sum_capacity_mbps', 'sum_reward_sq'):
+            assert sf[k] == pytest.approx(ss[k], rel=1e-6)
+    # the episode leaves a state d2d_step continues from
+    a = single.sample_actions()
+    o1 = fused.step(a)[0].clone()
+    o2 = single.step(a)[0]
+    assert torch.equal(o1, o2) and (fused.step_count == T + 1).all()
+    fused.close(); single.close()
+
+
+def test_episode_first_step_matches_oracle():
+    cfg = O.OracleConfig()
+    E = 512
+    env = make_vec(E, seed=3)
+    out = env.episode(3, record_actions=True)
+    torch.cuda.synchronize()
+    pos = env.positions.double().cpu().numpy()
+    for t in range(4):
+        ref = O.step_batch(cfg, pos, out['actions'][t].cpu().numpy(), nthreads=4)
+        from tests._util import RTOL, assert_rel
+        assert_rel(out['obs'][t, :, :, 4].cpu().numpy(), ref['sinr_db'], RTOL, f'sinr slice {t}')
+        assert_rel(out['capacity_mbps'][t].cpu().numpy(), ref['capacity_mbps'], RTOL, f'capacity slice {t}')
+        assert_rel(out['reward'][t].cpu().numpy(), ref['reward'], RTOL, f'reward slice {t}')
+        np.testing.assert_array_equal(out['rb'][t].cpu().numpy(), ref['rb'])
+    env.close()
+
+
+def test_episode_with_per_agent_rewards():
+    import gym_d2d_b200 as G
+    E, T = 300, 4
+    kw = dict(reward_fn=G.ShannonRewardFunction)
+    fused = make_vec(E, dict(kw), seed=8)
+    single = make_vec(E, dict(kw), seed=8)
+    out = fused.episode(T, record_actions=True)
+    single.reset(mask=torch.ones(E, dtype=torch.uint8, device='cuda'))
+    single.reset_stats()
+    for t in range(T + 1):
+        if t == 0:
+            single._bind(False)
+        obs, reward, done, info = single.step(out['actions'][t].contiguous())
+        single._bind(True)
+        assert torch.equal(out['agent_reward'][t], info['agent_reward']) and torch.equal(out['reward'][t], reward)
+    # the reset step's rewards enter no statistic
+    assert fused.stats()['sum_reward'] == pytest.approx(out['reward'][1:].double().sum().item(), rel=1e-5)
+    fused.close(); single.close()
+
+
+# ---- obs_dyn / packed host slots --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['default', 'small', 'block_min', 'dense_small'])
+def test_obs_dyn_reassembles_the_full_table_bit_for_bit(name):
+    kw = CONFIGS[name]
+    E = 300
+    env = make_vec(E, kw, seed=4)
+    env.reset()
+    static = env.obs_static()
+    full = env.alloc_host_outputs(info=True)
+    slots = [env.host_slot_buffers(s) for s in (0, 1)]
+    assert set(slots[0]) == {'actions', 'obs_dyn', 'capacity_mbps', 'reward', 'done'}
+    for i in range(6):
+        a = env.sample_actions().cpu().numpy()
+        if i % 2:
+            a[::3, ::2] = -1                                 # absent agents keep their position columns
+        env.step_count.zero_()
+        env.step_host(a, full)
+        env.step_count.zero_()
+        s = slots[i & 1]
+        s['actions'][...] = a
+        env.step_host_async(s['actions'], s, i & 1)
+        env.step_host_wait(i & 1)
+        np.testing.assert_array_equal(env.assemble_obs(static, s['obs_dyn']), full['obs'])
+        for k in ('capacity_mbps', 'reward', 'done'):
+            np.testing.assert_array_equal(s[k], full[k])
+    # caller-owned buffers with the per-step columns only
+    dyn = env.alloc_host_outputs(info=False, dyn=True)
+    a = env.sample_actions().cpu().numpy()
+    env.step_count.zero_(); env.step_host(a, full)
+    env.step_count.zero_(); env.step_host(a, dyn)
+    np.testing.assert_array_equal(env.assemble_obs(static, dyn['obs_dyn']), full['obs'])
+    # a positions change shows up in get_positions
+    env.reset()
+    assert not np.array_equal(env.obs_static(), static)
+    env.close()
+
+
+# ---- the ordering rule of include/d2d_b200.h ----------------------------------------------------------------------------------------
+def _policy(env, obs, out):
+    """A stand-in policy kernel: the next actions are a function of the current observation (a real data dependency)."""
+    x = (obs[..., 4].abs() * 977.0 + obs[..., 5].abs() * 131.0).to(torch.int64)
+    out.copy_((x % env._nvec_dev).to(torch.int32))
+
+
+@pytest.mark.parametrize('E', [256, 4096])
+def test_pdl_policy_writes_actions_between_steps(monkeypatch, E):
+    """10 000 iterations of {torch kernels write the actions -> step}: the default ordering must give exactly what a library
+    without programmatic dependent launch gives, eagerly and from a replayed CUDA graph."""
+    iters = 10000
+    monkeypatch.setenv('D2D_B200_PDL', '0')
+    plain = make_vec(E, seed=21)
+    monkeypatch.delenv('D2D_B200_PDL')
+    pdl = make_vec(E, seed=21)
+    graphed = make_vec(E, seed=21)
+    for env in (plain, pdl, graphed):
+        env.reset(initial_actions=torch.zeros((E, 50), dtype=torch.int32, device='cuda'))
+    acts = {env: torch.zeros((E, 50), dtype=torch.int32, device='cuda') for env in (plain, pdl, graphed)}
+    diff = torch.zeros((), dtype=torch.int64, device='cuda')
+
+    def one(env):
+        _policy(env, env.obs, acts[env])
+        env.step(acts[env])                                   # default: ordered after the policy's writes
+
+    # the graph holds 8 policy + step pairs
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(8):
+                one(graphed)
+    torch.cuda.current_stream().wait_stream(s)
+    for env in (plain, pdl):                                  # the capture did not execute: start all three from one state
+        env.step_count.zero_()
+    graphed.step_count.zero_()
+    for it in range(iters // 8):
+        for _ in range(8):
+            one(plain); one(pdl)
+        g.replay()
+        if it % 50 == 0:
+            diff += (plain.obs != pdl.obs).sum() + (plain.obs != graphed.obs).sum() + (plain.reward != pdl.reward).sum()
+    diff += (plain.obs != pdl.obs).sum() + (plain.obs != graphed.obs).sum() + (acts[plain] != acts[pdl]).sum() + (acts[plain] != acts[graphed]).sum()
+    torch.cuda.synchronize()
+    assert int(diff.item()) == 0
+    assert torch.equal(plain.step_count, pdl.step_count) and torch.equal(plain.step_count, graphed.step_count)
+    for env in (plain, pdl, graphed):
+        env.close()
+
+
+def test_pdl_reset_then_step_and_stable_flag(monkeypatch):
+    """{reset -> step} x 10 000 and a run of inputs_stable steps: bit-identical to a library without PDL."""
+    E = 1024
+    monkeypatch.setenv('D2D_B200_PDL', '0')
+    plain = make_vec(E, seed=5)
+    monkeypatch.delenv('D2D_B200_PDL')
+    pdl = make_vec(E, seed=5)
+    ring = [pdl.sample_actions() for _ in range(4)]
+    all_envs = torch.ones(E, dtype=torch.uint8, device='cuda')
+    diff = torch.zeros((), dtype=torch.int64, device='cuda')
+    for it in range(10000):
+        a = ring[it & 3]
+        for env in (plain, pdl):
+            env.reset(mask=all_envs)                          # new positions every iteration (same key sequence in both)
+            env.step(a, inputs_stable=True)                   # the library must ignore the flag right after a reset
+            env.step(ring[(it + 1) & 3], inputs_stable=True)  # honoured here: follows a step, actions long written
+        if it % 100 == 0:
+            diff += (plain.obs != pdl.obs).sum() + (plain.positions != pdl.positions).sum()
+    diff += (plain.obs != pdl.obs).sum() + (plain.reward != pdl.reward).sum()
+    torch.cuda.synchronize()
+    assert int(diff.item()) == 0
+    plain.close(); pdl.close()
+
+
+def test_episode_then_step_orders_after_the_position_writes(monkeypatch):
+    E = 2048
+    monkeypatch.setenv('D2D_B200_PDL', '0')
+    plain = make_vec(E, seed=6)
+    monkeypatch.delenv('D2D_B200_PDL')
+    pdl = make_vec(E, seed=6)
+    a = pdl.sample_actions()
+    diff = torch.zeros((), dtype=torch.int64, device='cuda')
+    outs = {env: env.alloc_many_outputs(3) for env in (plain, pdl)}
+    for it in range(2000):
+        for env in (plain, pdl):
+            env.episode(2, out=outs[env])
+            env.step(a, inputs_stable=True)                   # reads the positions the episode kernel just wrote
+        if it % 50 == 0:
+            diff += (plain.obs != pdl.obs).sum() + (outs[plain]['obs'] != outs[pdl]['obs']).sum()
+    diff += (plain.obs != pdl.obs).sum()
+    torch.cuda.synchronize()
+    assert int(diff.item()) == 0
+    plain.close(); pdl.close()
+
+
+# ---- device guard: a handle on a device other than the caller's current one -------------------------------------------------
+def test_env_on_another_device_than_the_current_one():
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two GPUs')
+    import gym_d2d_b200 as G
+    torch.cuda.set_device(0)
+    cfg = O.OracleConfig()
+    env1 = G.VecD2DEnv(300, {}, device='cuda:1', info=True, seed=1)
+    env0 = G.VecD2DEnv(300, {}, device='cuda:0', info=True, seed=1)
+    assert torch.cuda.current_device() == 0
+    env1.reset(); env0.reset()
+    assert torch.cuda.current_device() == 0
+    assert torch.equal(env1.positions.cpu(), env0.positions.cpu())
+    a = env0.sample_actions()
+    o1 = env1.step(a.to('cuda:1'))[0]
+    o0 = env0.step(a)[0]
+    assert torch.cuda.current_device() == 0 and o1.device.index == 1
+    torch.cuda.synchronize(0); torch.cuda.synchronize(1)
+    assert torch.equal(o1.cpu(), o0.cpu())
+    ref = O.step_batch(cfg, env1.positions.double().cpu().numpy(), a.cpu().numpy(), nthreads=2)
+    from tests._util import RTOL, assert_rel
+    assert_rel(o1[..., 4].cpu().numpy(), ref['sinr_db'], RTOL, 'sinr on cuda:1')
+    out = env1.episode(3)
+    env1.step_host(a.cpu().numpy())
+    assert torch.cuda.current_device() == 0
+    env1.close(); env0.close()
+
+
+# ---- ShadowingPathLoss under CUDA graphs: every replay draws fresh values (path_loss.py:75-81) ----------------------------------------------
+def test_shadowing_graph_replays_draw_fresh_values():
+    import gym_d2d_b200 as G
+    E = 64
+    kw = dict(num_rbs=3, num_cues=4, num_due_pairs=5, path_loss_model=G.ShadowingPathLoss)
+    eager = make_vec(E, dict(kw), seed=9)
+    graphed = make_vec(E, dict(kw), seed=9)
+    pos = O.random_positions(O.OracleConfig(num_rbs=3, num_cues=4, num_due_pairs=5), E, np.random.default_rng(0))
+    eager.set_positions(pos); graphed.set_positions(pos)
+    a = eager.sample_actions()
+    g = graphed.capture_steps([a])
+    seen = []
+    for i in range(3):
+        want = eager.step(a)[0].clone()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(graphed.obs, want), i              # replay i == the i-th eager call: same counter, same draws
+        seen.append(want)
+    assert not torch.equal(seen[0], seen[1]) and not torch.equal(seen[1], seen[2])
+    eager.close(); graphed.close()
+
+
+# ---- per-agent rewards with many resource blocks (the post-pass asked for 32 B of shared memory per RB) ----------------------------
+@pytest.mark.parametrize('kind', ['shannon', 'cue_sinr_shannon'])
+def test_per_agent_rewards_with_many_rbs(kind):
+    import gym_d2d_b200 as G
+    fn, param = (G.ShannonRewardFunction, -70.0) if kind == 'shannon' else (G.CueSinrShannonRewardFunction, 0.0)
+    kw = dict(num_rbs=3000, num_cues=6, num_due_pairs=10)
+    cfg = O.OracleConfig(**kw)
+    E = 40
+    env = make_vec(E, dict(kw, reward_fn=fn), seed=2)
+    rng = np.random.default_rng(5)
+    pos = O.random_positions(cfg, E, rng)
+    act = O.random_actions(cfg, E, rng)
+    act[:, :] = act[:, :] % (7 * 21)                          # crowd a few RBs so that the CUE-SINR rule has something to do
+    env.set_positions(pos)
+    obs, reward, done, info = env.step(torch.as_tensor(act, dtype=torch.int32, device='cuda'))
+    torch.cuda.synchronize()
+    ref = O.step_batch(cfg, pos, act, nthreads=2)
+    want = O.agent_rewards(cfg, ref, kind, param)
+    from tests.test_gpu_parity import _agent_reward_check
+    _agent_reward_check(info['agent_reward'].cpu().numpy(), want, ref['sinr_db'], param)
+    env.close()
+
+
+# ---- per-agent reward thresholds decided in fp64 (the threshold neighbourhood used to be exempt) -------------------------
+@pytest.mark.parametrize('name', ['default', 'block_min', 'dense_small', 'one_rb_crowded'])
+@pytest.mark.parametrize('kind', ['shannon', 'cue_sinr_shannon'])
+def test_reward_threshold_a_hair_from_a_link_sinr(name, kind):
+    """The threshold is placed 1e-9 dB above / below the float64 SINR of actual links - far inside fp32's resolution of a dB
+    value (4e-6 dB at best) - so only the fp64 pass with threshold-consistent rounding can decide those links like the
+    reference (envs/reward_fn.py:55,72).  Every agent is checked, none exempt."""
+    import gym_d2d_b200 as G
+    from tests._util import RTOL, rel_err
+    kw = CONFIGS[name]
+    cfg = O.OracleConfig(**kw)
+    rng = np.random.default_rng(77)
+    E = 96
+    pos, act = O.random_positions(cfg, E, rng), O.random_actions(cfg, E, rng)
+    ref = O.step_batch(cfg, pos, act, nthreads=4)
+    C_ = cfg.num_cues
+    cls = G.ShannonRewardFunction if kind == 'shannon' else G.CueSinrShannonRewardFunction
+    a = torch.as_tensor(act, dtype=torch.int32, device='cuda')
+    flips = 0
+    for pick in range(6):
+        # a link that matters for the rule: any link for Shannon, a CUE that shares its RB for CueSinrShannon
+        e = int(rng.integers(E))
+        if kind == 'shannon' or C_ == 0:
+            j = int(rng.integers(cfg.num_links))
+        else:
+            shared = [j for j in range(C_) if (ref['rb'][e] == ref['rb'][e, j]).sum() > 1]
+            if not shared:
+                continue
+            j = int(rng.choice(shared))
+        s_star = float(ref['sinr_db'][e, j])
+        for eps in (+1e-9, -1e-9):
+            thr = s_star + eps
+            env = make_vec(E, dict(kw, reward_fn=_with_param(cls, thr)))
+            env.set_positions(pos)
+            obs, reward, done, info = env.step(a)
+            torch.cuda.synchronize()
+            want = O.agent_rewards(cfg, ref, kind, thr)
+            got = info['agent_reward'].cpu().numpy()
+            err = rel_err(got, want)
+            assert (err <= RTOL).all(), (name, kind, pick, eps, float(err.max()), np.argwhere(err > RTOL)[:4])
+            flips += int((want[e] == -1).sum())
+            env.close()
+    assert flips > 0                                                   # the -1 branch was exercised at the hair's breadth
+
+
+def _with_param(cls, value):
+    """The plugin surface takes CLASSES (envs/d2d_env.py:27-28 instantiates them without arguments); a threshold other than
+    the default is passed the way the reference's users do it: functools.partial over the class."""
+    import functools
+    import gym_d2d_b200 as G
+    return functools.partial(cls, **{'min_sinr' if cls is G.ShannonRewardFunction else 'sinr_threshold_dB': value})
+
+
+# ---- a device_config_file that places a DUE transmitter but not its receiver ------------------------------------------
+def test_partial_device_file_redraws_receivers_around_file_transmitters(tmp_path):
+    import json
+    import gym_d2d_b200 as G
+    # transmitters of pairs 0 and 1 pinned near the cell edge / centre; their receivers and everything else left to reset()
+    doc = {'due00': {'position': [480.0, 0.0]}, 'due02': {'position': [-3.0, 4.0]}, 'cue00': {'position': [100.0, -50.0]}}
+    f = tmp_path / 'partial.json'
+    f.write_text(json.dumps(doc))
+    env = G.D2DEnv({'device_config_file': f}, seed=3)
+    for _ in range(5):
+        env.reset()
+        pos = env.device_positions()
+        assert pos['due00'] == (480.0, 0.0) and pos['due02'] == (-3.0, 4.0) and pos['cue00'] == (100.0, -50.0)
+        for tx, rx in (('due00', 'due01'), ('due02', 'due03')):
+            d = np.hypot(pos[rx][0] - pos[tx][0], pos[rx][1] - pos[tx][1])
+            assert d <= 20.0 and np.hypot(*pos[rx]) <= 500.0, (tx, rx, d)      # simulator.py:70-73, position.py:31-45
+        d = np.hypot(pos['due05'][0] - pos['due04'][0], pos['due05'][1] - pos['due04'][1])
+        assert d <= 20.0 + 1e-3                                                # untouched pairs keep the device-side draw
+    env.close()

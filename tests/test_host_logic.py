@@ -33,10 +33,29 @@ def test_library_exports_every_declared_symbol():
     assert _lib.load().d2d_abi_version() == _lib.ABI_VERSION
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof / offsetof of every ABI struct as a C compiler sees include/d2d_b200.h against the ctypes mirrors."""
+    import subprocess
     assert C.sizeof(_lib.D2DConfig) == 2 * 4 + 8 + 12 * 4 + 10 * 8
     assert C.sizeof(_lib.D2DLink) == 5 * 8 + 2 * 4 + 8
-    assert C.sizeof(_lib.D2DStepIO) == 9 * C.sizeof(C.c_void_p)
+    assert C.sizeof(_lib.D2DStepIO) == 11 * C.sizeof(C.c_void_p) + 8
+    structs = {'d2d_config_t': _lib.D2DConfig, 'd2d_link_t': _lib.D2DLink, 'd2d_step_io_t': _lib.D2DStepIO}
+    lines = ['#include <stddef.h>', '#include <stdio.h>', f'#include "{ROOT / "include" / "d2d_b200.h"}"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  printf("abi %d\\n", D2D_ABI_VERSION);', '  return 0;', '}']
+    src = tmp_path / 'layout.c'
+    src.write_text('\n'.join(lines))
+    subprocess.run(['gcc', '-std=c99', '-o', str(tmp_path / 'layout'), str(src)], check=True)
+    got = dict(l.rsplit(' ', 1) for l in subprocess.run([str(tmp_path / 'layout')], check=True, capture_output=True,
+                                                        text=True).stdout.strip().splitlines())
+    assert int(got['abi']) == _lib.ABI_VERSION
+    for cname, cls in structs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f'{cname}.{fname}']) == getattr(cls, fname).offset, f'{cname}.{fname}'
 
 
 def test_error_paths_without_gpu():

@@ -289,3 +289,62 @@ def test_shadowing_distribution_matches_reference(golden_dir):
     np.testing.assert_allclose(snr.std(0)[far], 2.7, rtol=0.08)
     corr = np.array([np.corrcoef(sinr[:, j], snr[:, j])[0, 1] for j in np.nonzero(far)[0]])
     assert (np.abs(corr - g['corr_sinr_snr'][far]) < 0.1).all()          # separate evaluations: (nearly) uncorrelated
+
+
+# ---- the product's counter-based draw schemes, restated by the oracle, against the reference's own sampler ---------------------
+def test_reset_scheme_matches_reference_sampler_distribution(golden_dir):
+    """tests/golden/reset_distribution.npz holds quantile tables of the UNMODIFIED reference's get_random_position /
+    get_random_position_nearby (position.py:18-45; generated by tests/golden/gen_reset_distribution.py): radial and angular
+    laws of a CUE, of a DUE receiver's offset, and the inward skew the in-cell rejection loop gives receivers of transmitters
+    near the cell edge.  The oracle's restatement of the device-side reset must follow the same laws (two-sample KS)."""
+    from tests._util import check_reset_distribution
+    fx = np.load(golden_dir / 'reset_distribution.npz')
+    cfg = O.OracleConfig()
+    pos = O.reset_positions(cfg, seed=2026, first_global_env=123, num_envs=8192)
+    res = check_reset_distribution(pos, cfg.num_cues, fx)
+    assert set(res) == {'cue_r2', 'cue_theta', 'off_r2', 'off_theta', 'edge_dr', 'edge_off_r2'}
+    assert (pos[:, 0] == 0).all()                                                  # simulator.py:63-64
+    # a wrong law is caught: receivers drawn WITHOUT the rejection loop's inward skew
+    bad = pos.copy()
+    tx = bad[:, 1 + cfg.num_cues::2]
+    rng = np.random.default_rng(0)
+    th, r = 2 * np.pi * rng.random(tx.shape[:2]), 20.0 * np.sqrt(rng.random(tx.shape[:2]))
+    bad[:, 2 + cfg.num_cues::2] = tx + np.stack([r * np.cos(th), r * np.sin(th)], -1)
+    with pytest.raises(AssertionError):
+        check_reset_distribution(bad, cfg.num_cues, fx)
+
+
+def test_live_reference_sampler_matches_fixture(golden_dir):
+    """The fixture itself against a fresh run of the reference's sampler, when a copy of the reference is importable."""
+    from oracle import ref_runner as R
+    if R.import_reference() is None:
+        pytest.skip('reference not available')
+    import random
+    from gym_d2d.position import get_random_position
+    from tests._util import ks_against_quantiles
+    fx = np.load(golden_dir / 'reset_distribution.npz')
+    random.seed(1)
+    p = np.array([get_random_position(500.0).as_tuple() for _ in range(50000)])
+    assert ks_against_quantiles((p ** 2).sum(-1) / 500.0 ** 2, fx['levels'], fx['cue_r2']) < 0.01
+
+
+def test_action_scheme_is_uniform_like_discrete_sample():
+    """envs/d2d_env.py:54-60 samples gym.spaces.Discrete(n): uniform over 0 .. n - 1.  The product's counter-based draw
+    (restated by d2d_oracle_sample_actions) must be uniform, differ between steps / envs / links, and not depend on sharding."""
+    cfg = O.OracleConfig()
+    E = 20000
+    a = np.stack([O.sample_actions(cfg, 42, 0, t, E) for t in range(4)])
+    n_cue, n_due = 25 * 24, 25 * 21
+    assert a[..., :25].min() == 0 and a[..., :25].max() == n_cue - 1
+    assert a[..., 25:].min() == 0 and a[..., 25:].max() == n_due - 1
+    for block, n in ((a[..., :25], n_cue), (a[..., 25:], n_due)):
+        counts = np.bincount(block.ravel(), minlength=n)
+        expect = block.size / n
+        assert np.abs(counts - expect).max() < 6 * np.sqrt(expect)               # every value equally likely
+    assert not np.array_equal(a[0], a[1]) and not np.array_equal(a[2], a[3])     # the two halves of one Philox block differ too
+    # successive steps of one link are uncorrelated
+    x = a[:, :, 3].astype(np.float64)
+    assert abs(np.corrcoef(x[0], x[1])[0, 1]) < 0.03 and abs(np.corrcoef(x[1], x[2])[0, 1]) < 0.03
+    # sharding invariance: global env g draws the same action whatever the shard offset
+    b = O.sample_actions(cfg, 42, 5000, 1, 100)
+    np.testing.assert_array_equal(b, a[1, 5000:5100])
