@@ -392,39 +392,40 @@ def run_cuda_arm(args) -> None:
     # fetched once (d2d_get_positions).  Outputs land in the library's packed pinned slot buffers: one copy per direction.
     e2e = None
     if not args.skip_e2e:
-        slots = [env.host_slot_buffers(0), env.host_slot_buffers(1)]
+        DEPTH = 4                                  # steps in flight (D2D_HOST_SLOTS)
+        slots = [env.host_slot_buffers(k) for k in range(DEPTH)]
         obs_static = env.obs_static()              # once per reset, outside the per-step loop (E x N x 16 B)
         host_acts = [torch.empty((E, N), dtype=torch.int32, pin_memory=True) for _ in range(4)]
         for h, a in zip(host_acts, acts):
             h.copy_(a)
         host_np = [h.numpy() for h in host_acts]
         h2d, d2h = E * N * 4, E * N * 8 + E * N * 4 + E * 4 + E
-        e2e_steps = max(20, min(args.steps, 400))
-        for i in range(4):                 # warm-up through BOTH pipeline slots
-            env.step_host_async(host_np[i % 4], slots[i & 1], i & 1)
-            env.step_host_wait(i & 1)
+        e2e_steps = max(200, min(args.steps, 400))
+        for i in range(2 * DEPTH):         # warm-up through every pipeline slot
+            env.step_host_async(host_np[i % 4], slots[i % DEPTH], i % DEPTH)
+            env.step_host_wait(i % DEPTH)
         # parity of the transport: the reassembled table equals the full-table device output of the same step
         env.step_count.zero_()
         env.step(acts[3], out=outs[0])
         torch.cuda.synchronize()
         import numpy as np
-        assert np.array_equal(env.assemble_obs(obs_static, slots[1]['obs_dyn']), outs[0].obs.cpu().numpy()), 'obs_dyn transport mismatch'
+        assert np.array_equal(env.assemble_obs(obs_static, slots[DEPTH - 1]['obs_dyn']), outs[0].obs.cpu().numpy()), 'obs_dyn transport mismatch'
         link = host_link_peak(torch, env.device, h2d, d2h, pg)
         torch.cuda.synchronize()
         if pg is not None:
             pg.barrier()
-        # two steps in flight: upload(i+1) and download(i-1) overlap kernel(i); every step's results reach the host.
+        # DEPTH steps in flight: uploads and downloads overlap the kernels; every step's results reach the host.
         # The window is short and sees the host's other activity, so it is repeated three times and the MEDIAN window is
         # reported (all three are listed in `window_ms`).
         dts = []
         for rep in range(3):
             t0 = time.perf_counter()
             for i in range(e2e_steps):
-                if i >= 2:
-                    env.step_host_wait(i & 1)
-                env.step_host_async(host_np[i % 4], slots[i & 1], i & 1)
-            env.step_host_wait(0)
-            env.step_host_wait(1)
+                if i >= DEPTH:
+                    env.step_host_wait(i % DEPTH)
+                env.step_host_async(host_np[i % 4], slots[i % DEPTH], i % DEPTH)
+            for k in range(DEPTH):
+                env.step_host_wait(k)
             t1 = time.perf_counter()
             windows.append((t0, t1))
             dt = t1 - t0
@@ -439,28 +440,27 @@ def run_cuda_arm(args) -> None:
                'host_link_gbs_per_gpu': (h2d + d2h) * e2e_steps / dt / 1e9,   # copies in both directions: the PCIe link bounds this number
                'd2h_gbs_per_gpu': d2h * e2e_steps / dt / 1e9, 'host_link_peak': link, 'numa': numa,
                'once_per_reset_bytes': int(obs_static.nbytes),
-               'api': 'd2d_step_host_async/_wait via VecD2DEnv.step_host_async (pinned host buffers, two steps in flight; actions '
+               'api': 'd2d_step_host_async/_wait via VecD2DEnv.step_host_async (pinned host buffers, four steps in flight; actions '
                       'copied in; obs_dyn (sinr, snr) + capacity + reward + done copied back every step as ONE packed copy; the '
                       'position columns of the observation table are fetched once per reset with d2d_get_positions)'}
-    # ---- fused rollouts: d2d_step_many, T steps of every env per launch -----------------------------------
+    # ---- fused rollouts: d2d_rollout, T counted steps of every env per launch with the actions sampled on the
+    # device (Discrete.sample, envs/d2d_env.py:54-60) - no [T][E][N] action input at all; positions read once per launch ----
     fused = None
     if args.fused_steps > 1:
         T = args.fused_steps
-        nbuf = max(2, min(8, (192 << 20) // (E * T * (B - 8 * V)) + 1))      # > L2 worth of outputs in flight
-        many_acts = [torch.stack([env.sample_actions(gen_many) for _ in range(T)]).contiguous()
-                     for gen_many in [torch.Generator(device=env.device).manual_seed(7 + rank)] for _ in range(nbuf)]
+        nbuf = max(2, min(8, (192 << 20) // (E * T * (B - 8 * V - 4 * N)) + 1))      # > L2 worth of outputs in flight
         many_outs = [env.alloc_many_outputs(T) for _ in range(nbuf)]
-        for a_, o_ in zip(many_acts, many_outs):
-            env.step_many(a_, o_)
+        for k, o_ in enumerate(many_outs):
+            env.rollout(T, action_seed=7 + rank, first_step_index=1 + k * T, out=o_)
         torch.cuda.synchronize()
         if pg is not None:
             pg.barrier()
-        reps = max(4, min(64, args.steps // T))
+        reps = max(32, min(128, args.steps // T))
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         ev0.record()
         for i in range(reps):
-            env.step_many(many_acts[i % nbuf], many_outs[i % nbuf])
+            env.rollout(T, action_seed=7 + rank, first_step_index=1 + i * T, out=many_outs[i % nbuf], inputs_stable=True)
         ev1.record()
         torch.cuda.synchronize()
         windows.append((t0, time.perf_counter()))
@@ -469,9 +469,12 @@ def run_cuda_arm(args) -> None:
             tt = torch.tensor([secs_f], dtype=torch.float64, device=env.device)
             pg.all_reduce(tt, op=pg.ReduceOp.MAX)
             secs_f = float(tt.item())
-        fused = {'workload': f'd2d_step_many: {T} consecutive steps of the same {E} envs per launch (positions read once), {reps} launches',
-                 'value': world * E * T * reps / secs_f, 'unit': UNIT, 'steps_per_launch': T, 'us_per_step': 1e6 * secs_f / (reps * T)}
-        del many_acts, many_outs
+        BF = 28 * N + 5 + (8 * V + 1) / T                 # per env-step: outputs only; positions + counter once per launch
+        fused = {'workload': f'd2d_rollout: {T} consecutive counted steps of the same {E} envs per launch, actions sampled on the device '
+                             f'(no action input), positions read once; {reps} eager launches',
+                 'value': world * E * T * reps / secs_f, 'unit': UNIT, 'steps_per_launch': T, 'us_per_step': 1e6 * secs_f / (reps * T),
+                 'algorithmic_bytes_per_env_step': BF}
+        del many_outs
     env.close()
     del env, acts, outs
 

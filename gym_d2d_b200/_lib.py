@@ -77,6 +77,7 @@ SIGNATURES = {
     'd2d_sample_actions': (C.c_int, [_vp, _vp, _u64, C.c_uint32, _vp]),
     'd2d_step': (C.c_int, [_vp, C.POINTER(D2DStepIO), _vp]),
     'd2d_episode': (C.c_int, [_vp, C.POINTER(D2DStepIO), _i32, _u64, _u64, C.c_uint32, _vp]),
+    'd2d_rollout': (C.c_int, [_vp, C.POINTER(D2DStepIO), _i32, _u64, C.c_uint32, _vp]),
     'd2d_host_slot_buffers': (C.c_int, [_vp, C.c_int, C.c_uint32, C.POINTER(D2DStepIO)]),
     'd2d_step_many': (C.c_int, [_vp, C.POINTER(D2DStepIO), _i32, _vp]),
     'd2d_step_host': (C.c_int, [_vp, C.POINTER(D2DStepIO), _vp]),

@@ -454,22 +454,31 @@ int agent_reward_launch(d2d_handle *h, const d2d_step_io_t *io, int64_t total, b
 
 // One launch (per chunk of envs) that makes T consecutive steps: MODE_STEP (T = 1) is d2d_step; MODE_MANY / MODE_EPISODE need
 // the warp kernel (T slices per env; the episode's slice 0 is the uncounted reset step).
-int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, int mode, void *stream, uint64_t ep_seed = 0, uint64_t act_seed = 0,
-                bool draw_actions = false) {
+struct EpisodeArgs {
+    uint64_t ep_seed = 0, act_seed = 0;
+    uint32_t act_t0 = 0;         // step index of slice 0 in the action draws
+    bool draw_actions = false;
+    bool no_reset = false;       // d2d_rollout: continue from the bound state, every slice counted
+};
+
+int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, int mode, void *stream, const EpisodeArgs &ea = EpisodeArgs()) {
     D2DParams P = make_params(h, io);
     P.T = T;
     P.t_stride = h->cfg.num_envs;
-    P.ep_seed = ep_seed; P.act_seed = act_seed;
+    P.ep_seed = ea.ep_seed; P.act_seed = ea.act_seed; P.act_t0 = ea.act_t0;
+    const bool draw_actions = ea.draw_actions;
     cudaStream_t st = (cudaStream_t)stream;
     const bool many = mode != MODE_STEP;
     // "Ordering rule" of include/d2d_b200.h: inputs may be read ahead of griddepcontrol.wait only on the caller's promise AND when
     // the kernel before this one (for this handle, in this stream) was a step kernel, which writes neither actions nor positions.
     // An episode that draws its own actions reads no input at all.
+    // An episode that draws its own actions reads no input at all; a rollout reads the positions like a step does.
     bool stable = h->pdl && h->last_stream == stream;
-    if (mode == MODE_EPISODE && draw_actions) stable = h->pdl;
-    else if (mode == MODE_EPISODE) stable = stable && (io->flags & D2D_STEP_INPUTS_STABLE) && h->last_kind != D2D_LAST_OTHER;
+    const bool reads_positions = mode != MODE_EPISODE || ea.no_reset;
+    if (!reads_positions && draw_actions) stable = h->pdl;
+    else if (!reads_positions) stable = stable && (io->flags & D2D_STEP_INPUTS_STABLE) && h->last_kind != D2D_LAST_OTHER;
     else stable = stable && (io->flags & D2D_STEP_INPUTS_STABLE) && h->last_kind == D2D_LAST_STEP;
-    P.flags = (stable ? 0u : D2D_PF_INPUTS_FRESH) | (draw_actions ? D2D_PF_DRAW_ACTIONS : 0u);
+    P.flags = (stable ? 0u : D2D_PF_INPUTS_FRESH) | (draw_actions ? D2D_PF_DRAW_ACTIONS : 0u) | (ea.no_reset ? D2D_PF_NO_RESET : 0u);
     // the kernels index with 32 bits: batches beyond 2^31 / (T max(6N, 2V)) envs (> 7 million default envs) go in chunks
     int64_t chunk = std::max<int64_t>(1, (int64_t)0x7fffffff / std::max(6 * h->N, 2 * h->V));
     if (many) chunk = h->cfg.num_envs;        // the callers checked that T slices fit 32-bit indices
@@ -479,7 +488,8 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, int mode, void *s
         if (e0 > 0) {
             const int64_t dl = chunk * h->N;
             P.first_global_env += (uint64_t)chunk;
-            P.actions += dl; P.pos += chunk * h->V * 2; P.pos_out += chunk * h->V * 2;
+            if (P.actions) P.actions += dl;
+            P.pos += chunk * h->V * 2; P.pos_out += chunk * h->V * 2;
             if (P.pos64) P.pos64 += chunk * h->V * 2;
             if (P.step_count) P.step_count += chunk;
             if (P.obs) P.obs += dl * 6;
@@ -501,6 +511,8 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, int mode, void *s
         if (h->use_warp) { const int64_t warps = (int64_t)grid * h->wpb; P.envs_per_warp = (uint32_t)((n + warps - 1) / warps); }
         D2DLaunchSel sel;
         sel.many = mode == MODE_MANY; sel.episode = mode == MODE_EPISODE;
+        sel.no_reset = ea.no_reset;
+        sel.fast = mode == MODE_EPISODE && draw_actions && !io->actions_out;
         sel.exact = h->pos64 != nullptr;
         // FULL: exactly the core outputs were passed, so the kernel tests no output pointer on its hot path
         sel.full = io->obs && io->capacity_mbps && io->reward && io->done && !io->rate_bps && !io->rb && !io->tx_pwr_dBm && !io->obs_dyn &&
@@ -515,7 +527,7 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, int mode, void *s
     }
     D2D_CUDA(cudaGetLastError());
     h->last_stream = stream;
-    h->last_kind = mode == MODE_EPISODE ? D2D_LAST_EPISODE : D2D_LAST_STEP;
+    h->last_kind = mode == MODE_EPISODE && !ea.no_reset ? D2D_LAST_EPISODE : D2D_LAST_STEP;
     if (h->dRngStep) {      // ShadowingPathLoss: the next call draws fresh values, also when this one is replayed from a CUDA graph
         d2d_advance_counter_kernel<<<1, 1, 0, st>>>(h->dRngStep, (uint64_t)T);
         D2D_CUDA(cudaGetLastError());
@@ -605,7 +617,9 @@ D2D_API int d2d_episode(d2d_handle_t *h, const d2d_step_io_t *io, int32_t num_st
     }
     if (fused) {
         if (draw && !cur.actions_out && agent_pass) cur.actions_out = h->act_scratch;
-        rc = step_launch(h, &cur, T1, MODE_EPISODE, stream, reset_seed, action_seed, draw);
+        EpisodeArgs ea;
+        ea.ep_seed = reset_seed; ea.act_seed = action_seed; ea.draw_actions = draw;
+        rc = step_launch(h, &cur, T1, MODE_EPISODE, stream, ea);
         if (rc) return rc;
         if (agent_pass) {
             if (draw) cur.actions = cur.actions_out;
@@ -635,6 +649,53 @@ D2D_API int d2d_episode(d2d_handle_t *h, const d2d_step_io_t *io, int32_t num_st
         if (t == 0) { h->step_count = nullptr; h->stats = nullptr; }          // envs/d2d_env.py:50: simulator.step, no num_steps += 1
         rc = step_launch(h, &one, 1, MODE_STEP, stream);
         h->step_count = counters; h->stats = stats;
+        if (rc) return rc;
+        advance_io(cur, 1, E, h->N);
+    }
+    return D2D_OK;
+}
+
+D2D_API int d2d_rollout(d2d_handle_t *h, const d2d_step_io_t *io, int32_t num_steps, uint64_t action_seed, uint32_t first_step_index,
+                        void *stream) {
+    int rc = check_step_args(h, io, "d2d_rollout", false);
+    if (rc) return rc;
+    if (num_steps < 1) return fail(D2D_ERR_INVALID_ARG, "d2d_rollout: num_steps must be >= 1");
+    D2D_GUARD(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t E = h->cfg.num_envs, per_env = std::max(6 * h->N, 2 * h->V);
+    const bool agent_pass = h->cfg.reward_fn != D2D_REWARD_SYSTEM_CAPACITY || io->agent_reward;
+    d2d_step_io_t cur = *io;
+    cur.actions = nullptr;
+    // (with an fp64 position shadow bound the steps must run the shadow-aware instantiation: composed path)
+    const bool fused = h->use_warp && !h->pos64 && (int64_t)num_steps * E * per_env <= (int64_t)0x7fffffff;
+    if (!cur.actions_out && (agent_pass || !fused)) {
+        const size_t need = (size_t)(fused ? num_steps : 1) * E * h->N;
+        if (h->act_scratch_elems < need) {
+            D2D_CUDA(cudaStreamSynchronize(st));
+            cudaFree(h->act_scratch);
+            h->act_scratch = nullptr; h->act_scratch_elems = 0;
+            D2D_CUDA(cudaMalloc(&h->act_scratch, need * sizeof(int32_t)));
+            h->act_scratch_elems = need;
+        }
+    }
+    if (fused) {
+        if (!cur.actions_out && agent_pass) cur.actions_out = h->act_scratch;
+        EpisodeArgs ea;
+        ea.act_seed = action_seed; ea.act_t0 = first_step_index; ea.draw_actions = true; ea.no_reset = true;
+        rc = step_launch(h, &cur, num_steps, MODE_EPISODE, stream, ea);
+        if (rc || !agent_pass) return rc;
+        cur.actions = cur.actions_out;
+        return agent_reward_launch(h, &cur, (int64_t)num_steps * E, true, st);
+    }
+    for (int t = 0; t < num_steps; ++t) {
+        d2d_step_io_t one = cur;
+        one.actions_out = nullptr;
+        int32_t *dst = cur.actions_out ? cur.actions_out : h->act_scratch;
+        rc = sample_launch(h, dst, action_seed, first_step_index + (uint32_t)t, st);
+        if (rc) return rc;
+        one.actions = dst;
+        h->last_kind = D2D_LAST_OTHER;
+        rc = step_launch(h, &one, 1, MODE_STEP, stream);
         if (rc) return rc;
         advance_io(cur, 1, E, h->N);
     }
@@ -679,7 +740,7 @@ const uint32_t kIoMask[D2D_NUM_IO_BUFFERS] = {0u, D2D_OUT_OBS, D2D_OUT_OBS_DYN, 
 }  // namespace
 
 D2D_API int d2d_host_slot_buffers(d2d_handle_t *h, int slot, uint32_t outputs, d2d_step_io_t *host_io) {
-    if (!h || !host_io || slot < 0 || slot > 1) return fail(D2D_ERR_INVALID_ARG, "d2d_host_slot_buffers: bad handle, slot or io");
+    if (!h || !host_io || slot < 0 || slot >= D2D_HOST_SLOTS) return fail(D2D_ERR_INVALID_ARG, "d2d_host_slot_buffers: bad handle, slot or io");
     if (!(outputs & (D2D_OUT_OBS | D2D_OUT_OBS_DYN | D2D_OUT_CAPACITY | D2D_OUT_REWARD | D2D_OUT_DONE | D2D_OUT_RATE | D2D_OUT_RB |
                      D2D_OUT_TX_PWR | D2D_OUT_AGENT_REWARD)))
         return fail(D2D_ERR_INVALID_ARG, "d2d_host_slot_buffers: empty output mask");
@@ -715,7 +776,7 @@ D2D_API int d2d_host_slot_buffers(d2d_handle_t *h, int slot, uint32_t outputs, d
 
 D2D_API int d2d_step_host_async(d2d_handle_t *h, const d2d_step_io_t *hio, int slot, void *stream) {
     if (!h || !hio || !hio->actions) return fail(D2D_ERR_INVALID_ARG, "d2d_step_host_async: handle, io and io->actions are required");
-    if (slot < 0 || slot > 1) return fail(D2D_ERR_INVALID_ARG, "d2d_step_host_async: slot must be 0 or 1");
+    if (slot < 0 || slot >= D2D_HOST_SLOTS) return fail(D2D_ERR_INVALID_ARG, "d2d_step_host_async: slot must be in [0, D2D_HOST_SLOTS)");
     if (!h->pos) return fail(D2D_ERR_STATE, "d2d_step_host_async: call d2d_bind_state first");
     D2D_GUARD(h);
     int rc = host_pipeline_init(h);
@@ -770,7 +831,7 @@ D2D_API int d2d_step_host_async(d2d_handle_t *h, const d2d_step_io_t *hio, int s
 }
 
 D2D_API int d2d_step_host_wait(d2d_handle_t *h, int slot) {
-    if (!h || slot < 0 || slot > 1) return fail(D2D_ERR_INVALID_ARG, "d2d_step_host_wait: bad handle or slot");
+    if (!h || slot < 0 || slot >= D2D_HOST_SLOTS) return fail(D2D_ERR_INVALID_ARG, "d2d_step_host_wait: bad handle or slot");
     if (!h->slot[slot].used) return D2D_OK;
     D2D_GUARD(h);
     D2D_CUDA(cudaEventSynchronize(h->slot[slot].ev_out));

@@ -88,6 +88,7 @@ struct D2DParams {
     // d2d_episode (warp kernel, EPISODE instantiation): Simulator.reset + the uncounted reset step + T counted steps in one launch
     uint64_t ep_seed;            // Philox key of this episode's position draws (d2d_reset's `seed`)
     uint64_t act_seed;           // Philox key of the on-device action draws
+    uint32_t act_t0;             // step index of slice 0 in the action draws (d2d_rollout continues an episode's sequence)
     float cell_radius, d2d_radius;
     int32_t *actions_out;        // [T + 1][E][N] optional record of the drawn actions
     float *pos_out;              // = pos (the episode's positions become the bound state)
@@ -161,7 +162,8 @@ __device__ __forceinline__ float d2d_rcp(float x) {
 //       the last "fresh" kernel passed its wait (that one releases its dependents only afterwards), so whatever wrote
 //       the inputs before that point is complete and visible.
 #define D2D_PF_INPUTS_FRESH 1u
-#define D2D_PF_DRAW_ACTIONS 2u     // d2d_episode: actions drawn on the device instead of read from P.actions
+#define D2D_PF_DRAW_ACTIONS 2u     // d2d_episode / d2d_rollout: actions drawn on the device instead of read from P.actions
+#define D2D_PF_NO_RESET 4u         // d2d_rollout: the EPISODE instantiation continues from the bound state (no position draw, every slice counted)
 __device__ __forceinline__ void d2d_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void d2d_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // kernel entry: see above

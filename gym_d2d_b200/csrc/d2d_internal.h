@@ -68,8 +68,8 @@ struct d2d_handle {
     double *pos64 = nullptr;
     uint8_t *step_count = nullptr;
     double *stats = nullptr;
-    // host-buffer steps (d2d_step_host*): two pipeline slots
-    d2d_host_slot slot[2];
+    // host-buffer steps (d2d_step_host*): the pipeline slots
+    d2d_host_slot slot[D2D_HOST_SLOTS];
     cudaStream_t s_in = nullptr, s_out = nullptr;
     bool pipe_ready = false;
     double *stage_pos = nullptr;
@@ -154,7 +154,9 @@ struct D2DLaunchSel {
     bool many = false;       // d2d_step_many: P.T steps per env in this launch
     bool full = false;       // exactly the core outputs (obs, capacity, reward, done) + a bound step counter
     bool exact = false;      // an fp64 position shadow is bound
-    bool episode = false;    // d2d_episode: P.T slices per env; positions and (optionally) actions are drawn inside the kernel
+    bool episode = false;    // d2d_episode / d2d_rollout: P.T slices per env; positions and / or actions are drawn inside the kernel
+    bool fast = false;       // ... with drawn actions, no action record and no fp64 shadow: the compiled-in variants
+    bool no_reset = false;   // ... d2d_rollout
 };
 
 // warp kernel (d2d_step_warp.cuh), one TU per warps-per-block shape

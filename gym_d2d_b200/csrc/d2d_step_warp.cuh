@@ -479,12 +479,15 @@ __device__ D2D_RARE_ATTR int d2d_rescue_warp_late(const D2DParams &P, const D2DS
 // (Simulator.reset, simulator.py:61-75; the draws of d2d_reset, d2d_common.cuh), slices 1 .. P.T - 1 are the counted steps.  The
 // positions are drawn in registers and written to the bound state once; the actions of every step are either read from
 // actions [P.T][E][N] or (D2D_PF_DRAW_ACTIONS) drawn on the device like envs/d2d_env.py:54-60 - the kernel then reads nothing
-// but its constant tables.
+// but its constant tables.  MODE 2 reads its variant from P.flags (given or drawn actions, d2d_episode or d2d_rollout, any
+// set of outputs); MODE 3 (episode) and MODE 4 (rollout) are the instantiations of the common case - drawn actions, exactly
+// the core outputs (FULL) - with those choices compiled in: 490 instead of 590 warp-instructions per env-step.
 template <bool PLE2, bool EXACT, int WPB, bool FULL, bool SPEC, int MODE>
 __global__ void __launch_bounds__(WPB * 32, D2D_WARP_MIN_BLOCKS(WPB))
 d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
     extern __shared__ __align__(16) unsigned char d2d_warp_smem[];
-    constexpr bool MANY = MODE != 0, EPI = MODE == 2;
+    constexpr bool MANY = MODE != 0, EPI = MODE >= 2, EPI_FAST = MODE >= 3;
+    static_assert(!EPI_FAST || FULL, "the fast episode / rollout instantiations write exactly the core outputs");
     const D2DShape<SPEC> S(P);
     // latency shape: the fp64 pass runs before griddepcontrol.wait
     constexpr bool RESCUE_EARLY = WPB == 2;
@@ -514,7 +517,8 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
     // the first env's inputs go out before anything else: their latency overlaps the table loads of the prologue instead of
     // following them (a warp of a one-wave batch steps a single env: two serial memory round trips were a tenth of its life)
     D2DLaneIn nxt;
-    const bool draw_actions = EPI && (P.flags & D2D_PF_DRAW_ACTIONS) != 0u;
+    const bool draw_actions = EPI_FAST || (EPI && (P.flags & D2D_PF_DRAW_ACTIONS) != 0u);
+    const bool ep_reset = MODE == 3 || (MODE == 2 && (P.flags & D2D_PF_NO_RESET) == 0u);     // d2d_episode (true) or d2d_rollout (false)
     if (EPI) {
         nxt.aA = nxt.aB = 0xffffffffu; nxt.tA = make_float2(1.f, 0.f); nxt.pB = make_float4(1.f, 0.f, 0.f, 0.f);
         if (e < e_end && !draw_actions) d2d_load_actions<SPEC>(P, S, iA, hasA, hasB, nxt);
@@ -580,15 +584,25 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         uint32_t aA = nxt.aA, aB = nxt.aB;
         if (EPI) {
             const uint64_t genv = P.first_global_env + (uint64_t)e;
-            if (t == 0u) {                                          // Simulator.reset (simulator.py:61-75): this env's new positions
+            if (t == 0u) {
                 tA_keep = make_float2(1.f, 0.f); pB_keep = make_float4(1.f, 0.f, 0.f, 0.f);
-                if (hasA) tA_keep = d2d_draw_cue(P.ep_seed, genv, lane, P.cell_radius);
-                if (hasB) pB_keep = d2d_draw_due(P.ep_seed, genv, (C + 1u) >> 1, lane, P.cell_radius, P.d2d_radius);
+                if (ep_reset) {                                     // Simulator.reset (simulator.py:61-75): this env's new positions
+                    if (hasA) tA_keep = d2d_draw_cue(P.ep_seed, genv, lane, P.cell_radius);
+                    if (hasB) pB_keep = d2d_draw_due(P.ep_seed, genv, (C + 1u) >> 1, lane, P.cell_radius, P.d2d_radius);
+                } else {                                            // d2d_rollout: the bound positions, read once for the T steps
+                    const float2 *pe = reinterpret_cast<const float2 *>(P.pos) + (uint64_t)e * V;
+                    if (hasA) tA_keep = __ldg(pe + 1u + lane);
+                    if (hasB) {
+                        const float2 tx = __ldg(pe + 1u + C + 2u * lane), rx = __ldg(pe + 2u + C + 2u * lane);
+                        pB_keep = make_float4(tx.x, tx.y, rx.x, rx.y);
+                    }
+                }
             }
             if (draw_actions) {                                     // envs/d2d_env.py:54-60: Discrete(R n_pwr).sample() per agent
-                if ((t & 1u) == 0u) ablk = d2d_action_block(P.act_seed, genv, lane, t);
-                aA = hasA ? __umulhi(d2d_action_word(ablk, t, false), limA) : 0xffffffffu;
-                aB = hasB ? __umulhi(d2d_action_word(ablk, t, true), limB) : 0xffffffffu;
+                const uint32_t ts = t + P.act_t0;
+                if ((ts & 1u) == 0u || t == 0u) ablk = d2d_action_block(P.act_seed, genv, lane, ts);
+                aA = hasA ? __umulhi(d2d_action_word(ablk, ts, false), limA) : 0xffffffffu;
+                aB = hasB ? __umulhi(d2d_action_word(ablk, ts, true), limB) : 0xffffffffu;
             }
         } else if (!MANY || t == 0u) { tA_keep = nxt.tA; pB_keep = nxt.pB; }
         const float2 tA = tA_keep;
@@ -680,13 +694,14 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         D2DLinkOut oA = oA32, oB = oB32;
         if (D2D_RESCUE_ENABLED && RESCUE_EARLY && __any_sync(0xffffffffu, needA || needB)) {
             const uint32_t keyA = liveA ? rbA : (D2D_INACTIVE_KEY | lane), keyB = liveB ? rbB : (D2D_INACTIVE_KEY | 32u | lane);
-            st_resc += (uint32_t)d2d_rescue_warp<PLE2, EXACT, SPEC, false, !FULL>(P, S, e, lane, jA, keyA, keyB, needA, needB, pA, pB_, tA, pB, oA, oB);
+            const uint32_t nr = (uint32_t)d2d_rescue_warp<PLE2, EXACT, SPEC, false, !FULL>(P, S, e, lane, jA, keyA, keyB, needA, needB, pA, pB_, tA, pB, oA, oB);
+            st_resc += (ep_reset && t == 0u) ? 0u : nr;            // the reset step enters no statistic
         }
 
         // ---- per-warp statistics; flushed with the warp's LAST env, ahead of the wait and of that env's stores: the reductions
         // commute with every other launch's, and a warp (hence its block's slot) is not retired before its outstanding atomics
         // are acknowledged - issued at the very end they cost 0.3 us per launch of a one-wave batch (profiles/README.md) --------
-        if (!EPI || t != 0u) {                                      // the reset step (envs/d2d_env.py:50) earns no reward
+        if (!ep_reset || t != 0u) {                                 // the reset step (envs/d2d_env.py:50) earns no reward
             if (P.reward_fn == 0) { st_reward += reward; st_reward2 = fmaf(reward, reward, st_reward2); }
             st_cap += cap_sum;
             st_pen += bad ? 1u : 0u;
@@ -694,7 +709,7 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         if (FLUSH_EARLY && P.stats && last_t && e + 1u == e_end && lane < (RESCUE_EARLY ? 6u : 5u)) {
             // one fire-and-forget fp64 reduction per statistic and warp, spread over the replicas
             const float vf = lane == 0 ? st_reward : lane == 1 ? st_cap : st_reward2;
-            const uint32_t vi = lane == 3 ? (e_end - e0) * (EPI ? T - 1u : T)  // env-steps this warp made
+            const uint32_t vi = lane == 3 ? (e_end - e0) * (ep_reset ? T - 1u : T)  // env-steps this warp made
                               : lane == 4 ? st_pen : st_resc;
             const double v = lane < 3u ? (double)vf : (double)vi;              // (two conversions instead of six)
 #ifndef D2D_EXPERIMENT_NOSTATS      // A/B only: what the statistics flush costs
@@ -713,12 +728,12 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
 #ifdef D2D_EXPERIMENT_NOCOUNT     // A/B only: how much of the post-wait tail is the step-counter load
         ns_keep = 0;
 #else
-        if (!EPI && g == 0u && t == 0u && (FULL || P.step_count)) ns_keep = e + lane < e_end ? (int)P.step_count[e + lane] : 0;   // consumed at the group's end
+        if (!ep_reset && g == 0u && t == 0u && (FULL || P.step_count)) ns_keep = e + lane < e_end ? (int)P.step_count[e + lane] : 0;   // consumed at the group's end
 #endif
         // ---- outputs: compact observation table (envs/obs_fn.py:55-61), capacity, optional info.  Rows of absent
         // agents carry their positions and zeros (the reference has no row for them). ---------------------------------
         // (one divergent branch per slot: cheaper than predicating every store, and the two merge when C == D)
-        if (EPI && t == 0u) {
+        if (ep_reset && t == 0u) {
             // the drawn positions become the bound state (after the wait: an earlier step kernel may still be reading it)
             float2 *pe = reinterpret_cast<float2 *>(P.pos_out) + (uint64_t)e * V;
             double2 *pe64 = P.pos64 ? reinterpret_cast<double2 *>(const_cast<double *>(P.pos64)) + (uint64_t)e * V : nullptr;
@@ -730,7 +745,7 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
                 if (pe64) { pe64[q] = make_double2((double)pB.x, (double)pB.y); pe64[q + 1u] = make_double2((double)pB.z, (double)pB.w); }
             }
         }
-        if (EPI && P.actions_out) {
+        if (EPI && !EPI_FAST && P.actions_out) {
             if (hasA) P.actions_out[jA] = (int32_t)aA;
             if (hasB) P.actions_out[jB] = (int32_t)aB;
         }
@@ -765,9 +780,9 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
             // in the group's registers until the env's last step
             if (lane == g) {
                 // EPISODE: num_steps = 0 at reset (envs/d2d_env.py:46) and slice 0 is the uncounted reset step
-                const int ns = EPI ? (int)min(t, 255u) : min(ns_keep + (int)t + 1, 255);
-                if (P.reward) P.reward[tE + e] = reward;
-                if (P.done) P.done[tE + e] = ns >= P.episode_length ? 1 : 0;
+                const int ns = ep_reset ? (int)min(t, 255u) : min(ns_keep + (int)t + 1, 255);
+                if (FULL || P.reward) P.reward[tE + e] = reward;
+                if (FULL || P.done) P.done[tE + e] = ns >= P.episode_length ? 1 : 0;
                 if (last_t) ns_keep = ns;
             }
         } else {
@@ -787,7 +802,8 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         // ---- throughput shape: the rare fp64 pass after the env's outputs are stored (it overwrites them) -------------------
         if (D2D_RESCUE_ENABLED && !RESCUE_EARLY && __any_sync(0xffffffffu, needA || needB)) {
             const uint32_t keyA = liveA ? rbA : (D2D_INACTIVE_KEY | lane), keyB = liveB ? rbB : (D2D_INACTIVE_KEY | 32u | lane);
-            st_resc += (uint32_t)d2d_rescue_warp_late<PLE2, EXACT, SPEC, !FULL>(P, S, e, lane, jA, keyA, keyB, needA, needB, pA, pB_, tA, pB);
+            const uint32_t nr = (uint32_t)d2d_rescue_warp_late<PLE2, EXACT, SPEC, !FULL>(P, S, e, lane, jA, keyA, keyB, needA, needB, pA, pB_, tA, pB);
+            st_resc += (ep_reset && t == 0u) ? 0u : nr;
         }
         if (last_t) {
             g = (g + 1u) & 31u;
@@ -809,7 +825,7 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
     if (!FLUSH_EARLY) {
         if (P.stats && lane < 6u) {
             const float vf = lane == 0 ? st_reward : lane == 1 ? st_cap : st_reward2;
-            const uint32_t vi = lane == 3 ? (e_end - e0) * (EPI ? T - 1u : T) : lane == 4 ? st_pen : st_resc;
+            const uint32_t vi = lane == 3 ? (e_end - e0) * (ep_reset ? T - 1u : T) : lane == 4 ? st_pen : st_resc;
             const double v = lane < 3u ? (double)vf : (double)vi;
             if (v != 0.0) atomicAdd(P.stats + ((blockIdx.x * WPB + warp) % D2D_STATS_REPLICAS) * 8 + lane, v);
         }

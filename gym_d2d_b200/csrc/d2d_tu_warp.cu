@@ -23,13 +23,17 @@ int allow_all(size_t smem) {
     if (!rc) rc = d2d_allow_smem(d2d_step_warp_kernel<PLE2, false, WPB, false, SPEC, 1>, smem);
     if (!rc) rc = d2d_allow_smem(d2d_step_warp_kernel<PLE2, true, WPB, false, SPEC, 1>, smem);
     if (!rc) rc = d2d_allow_smem(d2d_step_warp_kernel<PLE2, false, WPB, false, SPEC, 2>, smem);
+    if (!rc) rc = d2d_allow_smem(d2d_step_warp_kernel<PLE2, false, WPB, true, SPEC, 3>, smem);
+    if (!rc) rc = d2d_allow_smem(d2d_step_warp_kernel<PLE2, false, WPB, true, SPEC, 4>, smem);
     return rc;
 }
 
 template <bool PLE2, bool SPEC>
 cudaError_t launch(const D2DParams &P, int grid, size_t smem, const D2DLaunchSel &sel, cudaStream_t st, bool pdl) {
 #define D2D_GO(EXACT_, FULL_, MODE_) d2d_launch_step(d2d_step_warp_kernel<PLE2, EXACT_, WPB, FULL_, SPEC, MODE_>, grid, WPB * 32, smem, st, P, pdl)
-    if (sel.episode) return D2D_GO(false, false, 2);      // drawn positions are exact in fp32: no fp64 shadow path needed
+    // (an episode's drawn positions are exact in fp32, so it never needs the fp64 shadow path)
+    if (sel.episode && sel.fast && sel.full) return sel.no_reset ? D2D_GO(false, true, 4) : D2D_GO(false, true, 3);
+    if (sel.episode) return D2D_GO(false, false, 2);
     if (sel.many) return sel.exact ? D2D_GO(true, false, 1) : D2D_GO(false, false, 1);
     if (sel.full) return sel.exact ? D2D_GO(true, true, 0) : D2D_GO(false, true, 0);
     return sel.exact ? D2D_GO(true, false, 0) : D2D_GO(false, false, 0);

@@ -335,6 +335,26 @@ class VecD2DEnv:
                                          self._stream()))
         return o
 
+    def rollout(self, num_steps: int, action_seed: int, first_step_index: int = 1,
+                out: Optional[Dict[str, torch.Tensor]] = None, record_actions: bool = False,
+                inputs_stable: bool = False) -> Dict[str, torch.Tensor]:
+        """`num_steps` counted steps from the current state in ONE launch with actions sampled on the device (d2d_rollout): the
+        random-policy agent loop without any action buffer.  Slice t equals sample_actions_philox(action_seed,
+        first_step_index + t) + step()."""
+        T = int(num_steps)
+        o = out if out is not None else self.alloc_many_outputs(T)
+        if int(o['obs'].shape[0]) != T:
+            raise ValueError('out was allocated for a different number of steps')
+        if record_actions and 'actions' not in o:
+            o['actions'] = torch.empty((T, self.num_envs, self.num_links), dtype=torch.int32, device=self.device)
+        io = _lib.D2DStepIO(obs=o['obs'].data_ptr(), capacity_mbps=o['capacity_mbps'].data_ptr(),
+                            reward=o['reward'].data_ptr(), done=o['done'].data_ptr(), rate_bps=_ptr(o.get('rate_bps')),
+                            rb=_ptr(o.get('rb')), tx_pwr_dBm=_ptr(o.get('tx_pwr_dbm')), agent_reward=_ptr(o.get('agent_reward')),
+                            actions_out=_ptr(o.get('actions')), flags=_lib.STEP_INPUTS_STABLE if inputs_stable else 0)
+        _lib.check(self._lib.d2d_rollout(self._h, C.byref(io), T, int(action_seed) & 0xFFFFFFFFFFFFFFFF, int(first_step_index),
+                                         self._stream()))
+        return o
+
     def bind_stats(self, stats: torch.Tensor) -> None:
         """Accumulate the episode statistics into another float64 [STATS_REPLICAS][NUM_STATS] device tensor from now on (e.g.
         one of two buffers alternated per episode, so that a side stream can reduce the finished episode's sums)."""

@@ -238,16 +238,24 @@ D2D_API int d2d_step_many(d2d_handle_t *h, const d2d_step_io_t *io, int32_t num_
 D2D_API int d2d_episode(d2d_handle_t *h, const d2d_step_io_t *io, int32_t num_steps, uint64_t reset_seed, uint64_t action_seed,
                         uint32_t episode_flags, void *stream);
 
+/* num_steps COUNTED steps from the current state with actions sampled on the device - a random-policy rollout (the loop of
+ * examples/simple_env.py:20-33 with Discrete.sample() as the policy) that reads no action buffer: slice t of every io buffer
+ * ([num_steps][E]...) is what d2d_sample_actions(action_seed, first_step_index + t) + d2d_step would have produced.
+ * io->actions is ignored; io->actions_out records the draws.  One launch on default-topology configurations. */
+D2D_API int d2d_rollout(d2d_handle_t *h, const d2d_step_io_t *io, int32_t num_steps, uint64_t action_seed, uint32_t first_step_index,
+                        void *stream);
+
 /* Same call with HOST buffers: copies the actions to the device, steps, copies every non-NULL output
  * back and synchronises the stream.  This is the end-to-end path a CPU-side caller (the reference's
  * own env.step loop) would bind. */
 D2D_API int d2d_step_host(d2d_handle_t *h, const d2d_step_io_t *host_io, void *stream);
 
-/* Pipelined form of d2d_step_host for a CPU-side loop that keeps two steps in flight: slot 0 / 1 select one of two
- * device staging sets; the action upload runs on the library's copy-in stream, the kernel on `stream` (so steps stay
+/* Pipelined form of d2d_step_host for a CPU-side loop that keeps several steps in flight: slot 0 .. D2D_HOST_SLOTS - 1 selects
+ * one of the device staging sets; the action upload runs on the library's copy-in stream, the kernel on `stream` (so steps stay
  * ordered), the result download on its copy-out stream.  d2d_step_host_wait(slot) blocks until that slot's results
  * are in the host buffers; a slot may be re-submitted only after it has been waited for.  Host buffers should be
  * pinned.  d2d_step_host(...) == d2d_step_host_async(..., 0, ...) + d2d_step_host_wait(0). */
+#define D2D_HOST_SLOTS 4
 D2D_API int d2d_step_host_async(d2d_handle_t *h, const d2d_step_io_t *host_io, int slot, void *stream);
 D2D_API int d2d_step_host_wait(d2d_handle_t *h, int slot);
 

@@ -1,4 +1,4 @@
-"""Tiny driver for ncu captures: `python profiles/prof_step.py E [steps] [dense]` runs a few fused steps."""
+"""Tiny driver for ncu captures: `python profiles/prof_step.py E [steps] [dense] [episode]` runs a few fused steps / episodes."""
 import sys
 from pathlib import Path
 
@@ -15,7 +15,12 @@ env.reset()
 acts = [env.sample_actions() for _ in range(4)]
 outs = [env.alloc_outputs() for _ in range(4)]
 torch.cuda.synchronize()
-for i in range(steps):
-    env.step(acts[i % 4], out=outs[i % 4])
+if 'episode' in sys.argv:          # d2d_episode: reset + uncounted step + 10 counted steps with on-device sampled actions per launch
+    o = env.alloc_many_outputs(11)
+    for i in range(steps):
+        env.episode(10, out=o)
+else:
+    for i in range(steps):
+        env.step(acts[i % 4], out=outs[i % 4], inputs_stable=True)
 torch.cuda.synchronize()
 print('done', E, steps, env.step_geometry(), env.stats())

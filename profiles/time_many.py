@@ -15,15 +15,29 @@ env.reset()
 ring = max(2, min(16, (256 << 20) // (E * T * 1405) + 1))      # > 126 MB of outputs in flight: per-step I/O never sits in L2
 acts = [torch.stack([env.sample_actions() for _ in range(T)]).contiguous() for _ in range(ring)]
 outs = [env.alloc_many_outputs(T) for _ in range(ring)]
-for a, o in zip(acts, outs):
-    env.step_many(a, o)
+mode = 'episode' if 'episode' in sys.argv else 'rollout' if 'rollout' in sys.argv else 'many'
+if mode == 'episode':          # T counted steps + reset + the uncounted reset step per launch: T + 1 slices
+    outs = [env.alloc_many_outputs(T + 1) for _ in range(ring)]
+
+
+def launch(i):
+    if mode == 'episode':
+        env.episode(T, out=outs[i % ring])
+    elif mode == 'rollout':
+        env.rollout(T, action_seed=3, first_step_index=1 + i * T, out=outs[i % ring], inputs_stable=True)
+    else:
+        env.step_many(acts[i % ring], outs[i % ring], inputs_stable=True)
+
+
+for i in range(ring):
+    launch(i)
 torch.cuda.synchronize()
 s, t = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 s.record()
 for i in range(iters):
-    env.step_many(acts[i % ring], outs[i % ring])
+    launch(i)
 t.record()
 torch.cuda.synchronize()
 us = s.elapsed_time(t) * 1e3 / (iters * T)
 B = 32 * env.num_links + 5 + 8 * env.num_devices / T
-print(f'E={E} T={T} ring={ring} {us:.2f} us/step  {E / us * 1e6:.3e} env-steps/s  frac={B * E / us / 1e3 / 6546.2:.3f} (bytes/env-step {B:.0f})')
+print(f'{mode} E={E} T={T} ring={ring} {us:.2f} us/step  {E / us * 1e6:.3e} env-steps/s  frac={B * E / us / 1e3 / 6546.2:.3f} (bytes/env-step {B:.0f})')

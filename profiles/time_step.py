@@ -1,4 +1,4 @@
-"""Quick device-time probe: `python profiles/time_step.py E [iters]` -> us per fused step (CUDA events, graph of 32)."""
+"""Quick device-time probe: `python profiles/time_step.py E [iters] [dense] [fresh]` -> us per fused step (CUDA events, graph of 32)."""
 import sys
 from pathlib import Path
 
@@ -19,7 +19,7 @@ acts = [env.sample_actions() for _ in range(ring)]
 outs = [env.alloc_outputs() for _ in range(ring)]
 for a, o in zip(acts, outs):
     env.step(a, out=o)
-g = env.capture_steps(acts, outs)
+g = env.capture_steps(acts, outs, inputs_stable='fresh' not in sys.argv)      # 'fresh': every step orders itself the default way
 for _ in range(3):
     g.replay()
 torch.cuda.synchronize()
