@@ -57,6 +57,8 @@ struct D2DParams {
     int32_t align4;              // warp kernel: every env's DUE (tx, rx) pair is a 16-byte aligned float4
     int32_t reward_fn;           // d2d_reward_fn: per-agent reward functions take their reward statistics from the post-pass kernel
     int32_t uniform;             // every CUE link shares one set of constants, and every DUE link (u_cue / u_due below)
+    int32_t rescue_defer;        // dense kernel: an fp64 pass can only change the two dB values (no receiver sensitivity within 0.5 dB
+                                 // of 0, where the rate / capacity gate could flip), so it may run after the env's reward is reduced
     int32_t T;                   // d2d_step_many: steps per env in this launch (1 for d2d_step)
     uint32_t envs_per_warp;      // warp kernel: ceil(num_envs / (grid * warps per block)), divided on the host (a 20-instruction
                                  // sequence ahead of every warp's first load otherwise)
@@ -181,10 +183,13 @@ __device__ __forceinline__ int d2d_div(int a, uint32_t magic) {
     return magic ? (int)__umulhi((uint32_t)a, magic) : a;
 }
 
-// Philox4x32-10 (Salmon et al. 2011); same constants as the oracle's restatement.
-__device__ __forceinline__ uint4 d2d_philox4x32_10(uint4 c, uint2 k) {
+// Philox4x32-R (Salmon et al. 2011); same constants as the oracle's restatement.  R = 10 is the standard strength (positions,
+// shadowing); R = 7 is the smallest round count the paper reports as passing BigCrush and is used for the per-step action draws,
+// which are made inside the step kernel's hot loop.
+template <int ROUNDS>
+__device__ __forceinline__ uint4 d2d_philox4x32(uint4 c, uint2 k) {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < ROUNDS; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
         c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
@@ -193,6 +198,7 @@ __device__ __forceinline__ uint4 d2d_philox4x32_10(uint4 c, uint2 k) {
     }
     return c;
 }
+__device__ __forceinline__ uint4 d2d_philox4x32_10(uint4 c, uint2 k) { return d2d_philox4x32<10>(c, k); }
 
 // ---- counter-based draws of the device-side reset and of the on-device action sampling -------------------------------------
 // (restated value for value by oracle/d2d_oracle.c: d2d_oracle_reset_positions / d2d_oracle_sample_actions; the reference
@@ -240,11 +246,11 @@ __device__ __forceinline__ float4 d2d_draw_due(uint64_t seed, uint64_t genv, uin
 }
 // Actions (envs/d2d_env.py:54-60: Discrete(n).sample(), uniform over 0 .. n - 1).  One Philox block serves the CUE and the DUE
 // link of pair index l (CUE l / DUE pair l) for two consecutive steps:
-//   block(l, t) = Philox4x32-10(counter = (global env lo, hi, l, t >> 1), key = action seed ^ D2D_ACTION_KEY)
+//   block(l, t) = Philox4x32-7(counter = (global env lo, hi, l, t >> 1), key = action seed ^ D2D_ACTION_KEY)
 //   word        = 2 (t & 1) + (1 if the link is a DUE pair);   a = floor(word * n / 2^32)
 #define D2D_ACTION_KEY 0xA511E9B3u
 __device__ __forceinline__ uint4 d2d_action_block(uint64_t act_seed, uint64_t genv, uint32_t l, uint32_t t) {
-    return d2d_philox4x32_10(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32), l, t >> 1),
+    return d2d_philox4x32<7>(make_uint4((uint32_t)genv, (uint32_t)(genv >> 32), l, t >> 1),
                              make_uint2((uint32_t)act_seed ^ D2D_ACTION_KEY, (uint32_t)(act_seed >> 32)));
 }
 __device__ __forceinline__ uint32_t d2d_action_word(const uint4 &b, uint32_t t, bool due) {
@@ -317,15 +323,19 @@ __device__ __forceinline__ float d2d_sinr_store(double sinr, const D2DParams &P)
     return v;
 }
 
-// Per-link epilogue in fp32 (Appendix A).  p_lin = 10^(p/10); lg_d2 = log2(d^2) and g = d^-ple of the own link;
+// Per-link epilogue in fp32 (Appendix A).  p_lin = 10^(p/10); g = d^-ple of the own link as the SINR sees it, g_snr as the SNR
+// sees it (the same value unless ShadowingPathLoss draws the two evaluations separately);
 // I = interference [mW]; cA = (tx_lin0, a_lin, inv_noise, snr0_dB); sb = (sens_dBm, bw_MHz).
+// SNR_dB is taken from the LINEAR ratio like SINR_dB: its absolute error is then ~1e-6 dB near 0 dB, where the pure relative
+// 1e-4 bound bites.  (The dB-domain form p + snr0 - 5 ple log10 d^2 subtracts two ~60 dB numbers: 1e-5 dB of rounding,
+// 1.5e-4 relative at 0.064 dB - found by tests/test_gpu_round2.py::test_band_edge_sweep_of_sinr_and_snr.)
 template <bool PLE2>
-__device__ __forceinline__ D2DLinkOut d2d_link_epilogue(int p, float p_lin, float lg_d2, float g, float I, const float4 &cA,
+__device__ __forceinline__ D2DLinkOut d2d_link_epilogue(int p, float p_lin, float g_snr, float g, float I, const float4 &cA,
                                                         const float2 &sb, const D2DParams &P) {
     D2DLinkOut o;
     const float snr_lin = p_lin * cA.y * g;
     const float r = snr_lin * d2d_rcp(fmaf(I, cA.z, 1.0f));
-    o.snr_dB = ((float)p + cA.w) - P.snr_slope * lg_d2;
+    o.snr_dB = 3.0102999566398120f * d2d_lg2(p_lin * cA.y * g_snr);
     o.sinr_dB = 3.0102999566398120f * d2d_lg2(r);
     const bool ok = o.sinr_dB > sb.x;
     const float rate = d2d_log2_1p(r);

@@ -148,9 +148,8 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS) d2d_step_block_generic_kern
                 const float2 sb = make_float2(Bv.x, Bv.y);
                 const float dx = rj.x - xj.x, dy = rj.y - xj.y;
                 const float d2own = fmaf(dx, dx, dy * dy);
-                const float lg = d2d_lg2(d2own);
-                const float gown = PLE2 ? d2d_rcp(d2own) : d2d_ex2(P.neg_half_ple * lg);
-                o = d2d_link_epilogue<PLE2>(p, xj.z, lg, gown * d2d_shadow_factor(P, d2own, genv, (uint32_t)j, (uint32_t)j, 0), I, Av, sb, P);
+                const float gown = d2d_gain<PLE2>(d2own, P.neg_half_ple);
+                o = d2d_link_epilogue<PLE2>(p, xj.z, gown, gown * d2d_shadow_factor(P, d2own, genv, (uint32_t)j, (uint32_t)j, 0), I, Av, sb, P);
                 if (P.shadow_chi_dB > 0.f && d2own > P.shadow_d0sq)      // the SNR's own evaluation of the path loss (simulator.py:113)
                     o.snr_dB -= P.shadow_chi_dB * d2d_shadow_normal(P, genv, (uint32_t)j, (uint32_t)j, 1);
                 if (D2D_RESCUE_ENABLED && d2d_needs_rescue<true>(o, fminf(dmin2, d2own), P)) {   // rare: fp64 pass (d2d_common.cuh)
@@ -334,14 +333,13 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS, LPT <= 2 ? 4 : 3) d2d_step_
         // ---- phase 3: peer records, grouped by RB -------------------------------------------------------------------------
         uint32_t beg[LPT], end[LPT], self[LPT];
         bool side[LPT];
-        float lg[LPT], gown[LPT];
+        float gown[LPT];
 #pragma unroll
         for (int k = 0; k < LPT; ++k) {
             beg[k] = 0u; end[k] = 0u; self[k] = 0u; side[k] = false;
             const float dxo = tx[k].x - rx[k].x, dyo = tx[k].y - rx[k].y;       // own link (a CUE's receiver is the MBS at the origin)
             const float d2own = fmaf(dxo, dxo, dyo * dyo);
-            lg[k] = d2d_lg2(d2own);
-            gown[k] = PLE2 ? d2d_rcp(d2own) : d2d_ex2(P.neg_half_ple * lg[k]);
+            gown[k] = d2d_gain<PLE2>(d2own, P.neg_half_ple);
             if (live[k]) {
                 const uint32_t o = off[rb[k]];
                 beg[k] = o & 0xffffu; end[k] = off[rb[k] + 1u] & 0xffffu; side[k] = (o >> 16) != 0u;
@@ -382,7 +380,7 @@ __global__ void __launch_bounds__(D2D_BLOCK_THREADS, LPT <= 2 ? 4 : 3) d2d_step_
                 }
                 const float dxo = tx[k].x - rx[k].x, dyo = tx[k].y - rx[k].y;
                 const float2 sBk = link_sB(j, cue[k]);
-                o = d2d_link_epilogue<PLE2>((int)pw[k], pl[k], lg[k], gown[k], I, link_cA(j, cue[k]), sBk, P);
+                o = d2d_link_epilogue<PLE2>((int)pw[k], pl[k], gown[k], gown[k], I, link_cA(j, cue[k]), sBk, P);
                 uint32_t qslot = D2D_BLOCK_RESQ;
                 const bool need = D2D_RESCUE_ENABLED && d2d_needs_rescue<true>(o, fminf(dmin2, fmaf(dxo, dxo, dyo * dyo)), P);
                 if (need) {

@@ -308,12 +308,12 @@ __device__ __forceinline__ float d2d_log2_1p_sel(float r) {
     return r < 0.25f ? small : big;
 }
 // Per-link epilogue in fp32 (Appendix A), dead lanes zeroed.  Same arithmetic as d2d_link_epilogue (d2d_common.cuh).
-__device__ __forceinline__ D2DLinkOut d2d_link_epilogue_warp(bool live, int p, float p_lin, float lg_d2, float g, float I,
-                                                              const float4 &cA, const float2 &sb, float snr_slope) {
+// SNR_dB comes from the linear ratio, like SINR_dB (see d2d_link_epilogue).
+__device__ __forceinline__ D2DLinkOut d2d_link_epilogue_warp(bool live, float p_lin, float g, float I, const float4 &cA, const float2 &sb) {
     D2DLinkOut o;
     const float snr_lin = p_lin * cA.y * g;
     const float r = snr_lin * d2d_rcp(fmaf(I, cA.z, 1.0f));
-    const float snr = fmaf(-snr_slope, lg_d2, (float)p + cA.w);
+    const float snr = 3.0102999566398120f * d2d_lg2(snr_lin);
     const float sinr = 3.0102999566398120f * d2d_lg2(r);
     const bool ok = live && sinr > sb.x;
     const float rate = d2d_log2_1p_sel(r);
@@ -638,16 +638,14 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
 
         // ---- peer records: position, radiated weight w, and its value u at the MBS -------------------------------
         const float d2A = fmaf(tA.x, tA.x, tA.y * tA.y);                       // CUE -> MBS distance^2 (own link)
-        const float lgA = d2d_lg2(d2A);
-        const float gA = PLE2 ? d2d_rcp(d2A) : d2d_ex2(P.neg_half_ple * lgA);
+        const float gA = d2d_gain<PLE2>(d2A, P.neg_half_ple);
         const float wA = plA * cA.x;
         const float d2Bm = fmaf(pB.x, pB.x, pB.y * pB.y);                      // DUE tx -> MBS distance^2 (as interferer)
         const float wB = plB * cB.x;
         const float uA = wA * gA, uB = wB * d2d_gain<PLE2>(d2Bm, P.neg_half_ple);
         const float dxB = pB.x - pB.z, dyB = pB.y - pB.w;                      // DUE own link
         const float d2B = fmaf(dxB, dxB, dyB * dyB);
-        const float lgB = d2d_lg2(d2B);
-        const float gB = PLE2 ? d2d_rcp(d2B) : d2d_ex2(P.neg_half_ple * lgB);
+        const float gB = d2d_gain<PLE2>(d2B, P.neg_half_ple);
         d2d_sts128_if(liveA && rankA < D2D_BIN_CAP, binA + (rankA << 4), tA.x, tA.y, wA, uA);
         d2d_sts128_if(liveB && rankB < D2D_BIN_CAP, binB + (rankB << 4), pB.x, pB.y, wB, uB);
         __syncwarp();
@@ -671,9 +669,8 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
 
         // ---- per-link epilogue (simulator.py:93,106-107,110-127,144-154); dead lanes are zeroed ------------------------
         const float2 sA = SPEC ? P.us_cue : d2d_lds64(lkS), sB = SPEC ? P.us_due : d2d_lds64(lkS + 256u);   // (sensitivity, RB bandwidth in MHz)
-        const float slope = PLE2 ? 3.0102999566398120f : P.snr_slope;
-        const D2DLinkOut oA32 = d2d_link_epilogue_warp(liveA, (int)pA, plA, lgA, gA, IA, cA, sA, slope);
-        const D2DLinkOut oB32 = d2d_link_epilogue_warp(liveB, (int)pB_, plB, lgB, gB, IB, cB, sB, slope);
+        const D2DLinkOut oA32 = d2d_link_epilogue_warp(liveA, plA, gA, IA, cA, sA);
+        const D2DLinkOut oB32 = d2d_link_epilogue_warp(liveB, plB, gB, IB, cB, sB);
         const bool needA = liveA && d2d_needs_rescue<EXACT, !FULL>(oA32, fminf(dminA, d2A), P);
         const bool needB = liveB && d2d_needs_rescue<EXACT, !FULL>(oB32, fminf(dminB, d2B), P);
 
@@ -775,9 +772,22 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
                 if (P.pwr_out) P.pwr_out[jB] = (int16_t)(liveB ? pB_ : 0u);
             }
         }
-        if (MANY) {
-            // per-step scalars straight to slice t (write-only, so partial sectors merge in L2); the step counter stays
-            // in the group's registers until the env's last step
+        if (MANY && T <= 32u) {
+            // per-step scalars: lane t keeps slice t's reward until the env's last step, then T lanes store their slices at once
+            // (two strided stores per env instead of two single-lane stores per step)
+            rew_keep = lane == t ? reward : rew_keep;
+            if (last_t) {
+                // num_steps before this launch: lane g of the group holds it (episode: num_steps = 0 at reset, slice 0 uncounted)
+                const int ns0 = ep_reset ? -1 : __shfl_sync(0xffffffffu, ns_keep, (int)g);
+                if (lane < T) {
+                    if (FULL || P.reward) P.reward[lane * strideE + e] = rew_keep;
+                    if (FULL || P.done) P.done[lane * strideE + e] = min(ns0 + (int)lane + 1, 255) >= P.episode_length ? 1 : 0;
+                }
+                if (lane == g) ns_keep = min(ns0 + (int)T, 255);
+            }
+        } else if (MANY) {
+            // (more than 32 steps per launch) per-step scalars straight to slice t (write-only, so partial sectors merge in L2);
+            // the step counter stays in the group's registers until the env's last step
             if (lane == g) {
                 // EPISODE: num_steps = 0 at reset (envs/d2d_env.py:46) and slice 0 is the uncounted reset step
                 const int ns = ep_reset ? (int)min(t, 255u) : min(ns_keep + (int)t + 1, 255);

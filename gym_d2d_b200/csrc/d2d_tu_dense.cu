@@ -1,41 +1,26 @@
 // d2d_tu_dense.cu - the instantiations of d2d_step_dense_kernel (d2d_step_dense.cuh): one block per env, 65 <= N <= 1024 links.
-#include <cstdlib>
-
 #include "d2d_internal.h"
 #include "d2d_step_dense.cuh"
 
 // (links per thread, threads per block) instantiations
-#define D2D_DENSE_SHAPES(X) X(1, 256) X(2, 256) X(3, 256) X(4, 256) X(1, 320) X(2, 320) X(3, 320) X(1, 640)
+#define D2D_DENSE_SHAPES(X) X(1, 256) X(2, 256) X(3, 256) X(4, 256) X(1, 320) X(2, 320) X(3, 320)
 
 size_t d2d_dense_smem(int N, int R, int bin_cap) { return d2d_dense_layout(N, R, bin_cap).total; }
 int d2d_dense_bin_cap_host(int N, int R) { return d2d_dense_bin_cap(N, R); }
 
 namespace {
-// the SPEC instantiation exists for the launch shapes BASELINE config #3 may run in (320 x 2 links by default; 640 x 1 on request)
-template <bool PLE2, int LPT, int BT>
-struct DenseSpecOk { static constexpr bool value = PLE2 && ((LPT == 2 && BT == 320) || (LPT == 1 && BT == 640)); };
-template <bool PLE2, int LPT, int BT>
-bool dense_spec(const d2d_handle *h) {
-    const char *sp = std::getenv("D2D_B200_SPEC");      // tests: force the generic instantiation
-    return DenseSpecOk<PLE2, LPT, BT>::value && h->N == D2D_DENSE_SPEC_N && h->cfg.num_cues == D2D_DENSE_SPEC_C &&
-           h->cfg.num_rbs == D2D_DENSE_SPEC_R && h->bin_cap == D2D_DENSE_SPEC_CAP && h->cfg.n_pwr_cue == 24 && h->cfg.n_pwr_due == 21 &&
-           h->cfg.num_downlinks == 0 && !(sp && std::atoi(sp) == 0);
-}
 // every (FULL, EXACT) instantiation d2d_step may launch for this handle needs the dynamic shared-memory opt-in
 template <bool PLE2, int LPT, int BT>
 int plan(d2d_handle *h, size_t smem) {
     int rc = d2d_allow_smem(d2d_step_dense_kernel<PLE2, LPT, BT, false, false>, smem);
     if (!rc) rc = d2d_allow_smem(d2d_step_dense_kernel<PLE2, LPT, BT, false, true>, smem);
     if (!rc) rc = d2d_allow_smem(d2d_step_dense_kernel<PLE2, LPT, BT, true, true>, smem);
-    if (!rc && dense_spec<PLE2, LPT, BT>(h)) rc = d2d_allow_smem(d2d_step_dense_kernel<PLE2, LPT, BT, true, false, DenseSpecOk<PLE2, LPT, BT>::value>, smem);
     if (!rc) rc = d2d_plan_geometry(h, d2d_step_dense_kernel<PLE2, LPT, BT, true, false>, BT, smem, 1);
     return rc;
 }
 template <bool PLE2, int LPT, int BT>
 cudaError_t launch(const d2d_handle *h, const D2DParams &P, int grid, const D2DLaunchSel &sel, cudaStream_t st, bool pdl) {
 #define D2D_GO(FULL_, EXACT_) d2d_launch_step(d2d_step_dense_kernel<PLE2, LPT, BT, FULL_, EXACT_>, grid, h->block, (size_t)h->smem, st, P, pdl)
-    if (sel.full && h->uniform && !sel.exact && dense_spec<PLE2, LPT, BT>(h))
-        return d2d_launch_step(d2d_step_dense_kernel<PLE2, LPT, BT, true, false, DenseSpecOk<PLE2, LPT, BT>::value>, grid, h->block, (size_t)h->smem, st, P, pdl);
     if (sel.full && h->uniform) return sel.exact ? D2D_GO(true, true) : D2D_GO(true, false);
     return sel.exact ? D2D_GO(false, true) : D2D_GO(false, false);
 #undef D2D_GO

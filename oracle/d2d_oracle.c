@@ -258,9 +258,9 @@ void d2d_oracle_per_agent_obs(const double *table, const int32_t *present, int32
 }
 
 /* ---- Philox4x32-10 (Salmon et al., SC'11): the product's counter-based reset sampler ---- */
-void d2d_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+static void philox4x32(const uint32_t ctr[4], const uint32_t key[2], int rounds, uint32_t out[4]) {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < rounds; ++r) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
         uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
@@ -269,6 +269,7 @@ void d2d_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+void d2d_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { philox4x32(ctr, key, 10, out); }
 
 /* uniform-in-disc draw from two 32-bit words: theta = 2*pi*u1, r = radius*sqrt(u2)  (position.py:24-28, 41-44); 24-bit
  * uniforms centred in their cell */
@@ -319,7 +320,7 @@ void d2d_oracle_reset_positions(const d2d_oracle_cfg *cfg, double cell_radius_m,
 }
 
 /* The product's on-device Discrete(n).sample() (envs/d2d_env.py:54-60; uniform over 0 .. n-1): CUE l and DUE pair l share the
- * block Philox(counter = (global env, l, t >> 1), key = seed ^ 0xA511E9B3); word = 2 (t & 1) + (1 for the DUE link);
+ * block Philox4x32-7 (seven rounds: the draws sit in the step kernel's hot loop) (counter = (global env, l, t >> 1), key = seed ^ 0xA511E9B3); word = 2 (t & 1) + (1 for the DUE link);
  * a = floor(word * n / 2^32).  Links beyond C + D (DOWNLINK) are absent (-1).  actions int32 [E][N]. */
 void d2d_oracle_sample_actions(const d2d_oracle_cfg *cfg, int32_t num_links, uint64_t seed, uint64_t first_global_env, uint32_t t,
                                int64_t E, int32_t *actions) {
@@ -332,7 +333,7 @@ void d2d_oracle_sample_actions(const d2d_oracle_cfg *cfg, int32_t num_links, uin
         for (int l = 0; l < L; ++l) {
             uint32_t ctr[4] = {(uint32_t)g, (uint32_t)(g >> 32), (uint32_t)l, t >> 1};
             uint32_t key[2] = {(uint32_t)seed ^ 0xA511E9B3u, (uint32_t)(seed >> 32)}, o[4];
-            d2d_oracle_philox4x32_10(ctr, key, o);
+            philox4x32(ctr, key, 7, o);
             if (l < C) a[l] = (int32_t)(((uint64_t)o[2 * (t & 1)] * n_cue) >> 32);
             if (l < D) a[C + l] = (int32_t)(((uint64_t)o[2 * (t & 1) + 1] * n_due) >> 32);
         }
