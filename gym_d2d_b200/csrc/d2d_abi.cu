@@ -64,7 +64,6 @@ D2DParams make_params(const d2d_handle *h, const d2d_step_io_t *io) {
     P.us_cue = make_float2(h->us_cue[0], h->us_cue[1]);
     P.us_due = make_float2(h->us_due[0], h->us_due[1]);
     P.uniform = h->uniform ? 1 : 0;
-    P.rescue_defer = h->rescue_defer ? 1 : 0;
     P.ud_cue = h->ud_cue; P.ud_due = h->ud_due;
     P.reward_fn = h->cfg.reward_fn;
     if (h->cfg.reward_fn != D2D_REWARD_SYSTEM_CAPACITY) {
@@ -181,10 +180,6 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
             B[j].sens_dBm != B[j0].sens_dBm || B[j].bw_MHz != B[j0].bw_MHz)
             h->uniform = false;
     }
-    h->rescue_defer = true;
-    for (int j = 0; j < h->N; ++j)
-        if (std::fabs(B[j].sens_dBm) < 0.5f) h->rescue_defer = false;
-    if (const char *rd = std::getenv("D2D_B200_DEFER")) h->rescue_defer = h->rescue_defer && std::atoi(rd) != 0;      // tests / A-B: inline passes
     if (cfg->num_cues > 0) h->ud_cue = Dv[0];
     if (cfg->num_due_pairs > 0) h->ud_due = Dv[cfg->num_cues];
     if (cfg->num_cues > 0) { h->u_cue = A[0]; h->us_cue[0] = B[0].sens_dBm; h->us_cue[1] = B[0].bw_MHz; }
@@ -250,7 +245,7 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
                      ? (h->N + D2D_BLOCK_THREADS - 1) / D2D_BLOCK_THREADS : 0;      // downlinks: the general-topology kernel
         h->bin_cap = d2d_dense_bin_cap_host(h->N, cfg->num_rbs);
         const char *dn = std::getenv("D2D_B200_DENSE");
-        const bool dense = h->lpt > 0 && d2d_dense_smem(h->N, cfg->num_rbs, h->bin_cap) <= 74 * 1024 && !(dn && std::atoi(dn) == 0);
+        const bool dense = h->lpt > 0 && d2d_dense_smem(h->N, cfg->num_rbs, h->bin_cap) <= 72 * 1024 && !(dn && std::atoi(dn) == 0);
         if (dense) {
             // threads per block / links per thread: the shape with the fewest (warp, slot) bodies per env - every warp runs the
             // straight-line code of each of its slots whether or not all 32 lanes hold a link (N = 600: 10 warps x 2 slots,

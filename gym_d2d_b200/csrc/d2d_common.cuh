@@ -57,8 +57,6 @@ struct D2DParams {
     int32_t align4;              // warp kernel: every env's DUE (tx, rx) pair is a 16-byte aligned float4
     int32_t reward_fn;           // d2d_reward_fn: per-agent reward functions take their reward statistics from the post-pass kernel
     int32_t uniform;             // every CUE link shares one set of constants, and every DUE link (u_cue / u_due below)
-    int32_t rescue_defer;        // dense kernel: an fp64 pass can only change the two dB values (no receiver sensitivity within 0.5 dB
-                                 // of 0, where the rate / capacity gate could flip), so it may run after the env's reward is reduced
     int32_t T;                   // d2d_step_many: steps per env in this launch (1 for d2d_step)
     uint32_t envs_per_warp;      // warp kernel: ceil(num_envs / (grid * warps per block)), divided on the host (a 20-instruction
                                  // sequence ahead of every warp's first load otherwise)

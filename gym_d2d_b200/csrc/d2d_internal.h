@@ -44,7 +44,6 @@ struct d2d_handle {
     bool use_warp = true;
     bool spec = false;         // warp kernel instantiated for the reference's default EnvConfig shape
     bool uniform = false;      // every CUE link has the same constants, and every DUE link (no per-device overrides)
-    bool rescue_defer = false; // no receiver sensitivity within 0.5 dB of 0: an fp64 pass never changes a rate / capacity
     D2DLinkA u_cue{}, u_due{};
     D2DLinkD ud_cue{}, ud_due{};
     float us_cue[2] = {0, 0}, us_due[2] = {0, 0};

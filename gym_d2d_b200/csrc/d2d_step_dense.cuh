@@ -32,9 +32,8 @@
 // blocks per SM the register allocation has to allow (80 registers at 256 threads)
 #define D2D_DENSE_MINB(BT) ((BT) <= 128 ? 6 : (BT) <= 160 ? 5 : (BT) <= 192 ? 4 : 3)
 
-#define D2D_DENSE_QCAP 8u     // deferred fp64 passes per env (more are taken inline)
 struct D2DDenseLayout {
-    uint32_t bins, ovrec, pwr, pwr_d, cnt, red, ovrb, total, cnt_words, qcnt, qdesc, qrec;
+    uint32_t bins, ovrec, pwr, pwr_d, cnt, red, ovrb, total, cnt_words;
 };
 
 __host__ __device__ inline D2DDenseLayout d2d_dense_layout(int N, int R, int cap) {
@@ -45,9 +44,6 @@ __host__ __device__ inline D2DDenseLayout d2d_dense_layout(int N, int R, int cap
     L.red = b;   b += 2u * 4u * D2D_DENSE_MAX_WARPS * 4u;                 // [2][4][warps]: capacity, acting agents, rescues, penalty
     L.cnt_words = ((uint32_t)R + 2u + 3u) & ~3u;                          // per buffer: R counters (links | SIDELINKs << 16), overflow count
     L.cnt = b;   b += 3u * L.cnt_words * 4u;
-    L.qcnt = b;  b += 16u;                                                // [2] deferred fp64 passes queued for env parity 0 / 1
-    L.qdesc = b; b += 2u * D2D_DENSE_QCAP * 32u;                          // [2][QCAP][8 words] victim descriptors
-    L.qrec = b;  b += 2u * D2D_DENSE_QCAP * (uint32_t)cap * 16u;          // [2][QCAP][cap] copies of the victim's RB bin
     L.bins = b;  b += 2u * (uint32_t)R * (uint32_t)cap * 16u;            // [2][R][cap] float4 peer records
     L.ovrec = b; b += (uint32_t)N * 16u;                                  // [N] overflow records
     L.ovrb = b;  b += ((uint32_t)N * 2u + 15u) & ~15u;                    // [N] RB of each overflow record
@@ -129,52 +125,6 @@ __device__ __noinline__ D2DDenseFix d2d_dense_rescue(const D2DParams &P, uint32_
     return f;
 }
 
-// The DEFERRED form of the pass.  One link per env and a bit needs it; taken inline it stretches its warp's phase 2 by ~2 000
-// cycles while the block's other warps wait at the next barrier (18 % of the kernel at BASELINE config #3: a build without the
-// pass runs at 673 instead of 817 us).  When the block's LAST warp has an empty link slot (N = 600 on 10 warps x 2 slots: warp 9
-// steps 32 links where the others step 64) the pass moves there: the victim's warp only queues a descriptor and a copy of its RB
-// bin (two dozen instructions), and the last warp works the queue of env e off during phase 2 of env e + 1 - after the barrier
-// that makes every queued entry visible, and before the next barrier, after which the queue buffer (one per env parity) is
-// refilled.  It rewrites only the two dB values (callers make sure rate / capacity cannot change: no fp64 shadow, no receiver
-// sensitivity within the band), so the reward reduction never waits for it.
-template <bool PLE2, bool THR>
-__device__ __noinline__ void d2d_dense_drain(const D2DParams &P, uint32_t e, const uint32_t *desc, const float4 *qrec, uint32_t n, const double *pwd,
-                                             uint32_t lane) {
-    const uint32_t C = (uint32_t)P.C, N = (uint32_t)P.N, CAP = (uint32_t)P.bin_cap;
-    for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t *d = desc + i * 8u;
-        const uint32_t vj = d[0], vself = d[1], vpw = d[2] & 0xffffu, vn = d[2] >> 16;
-        const double2 rxd = make_double2((double)__uint_as_float(d[3]), (double)__uint_as_float(d[4]));
-        const float4 *recs = qrec + i * CAP;
-        const float4 own = recs[vself];
-        double I64 = 0.0;
-        for (uint32_t q = lane; q < vn; q += 32u)
-            if (q != vself) I64 += d2d_dense_term_f64<PLE2>(recs[q], rxd, nullptr, C, pwd, P);
-#pragma unroll
-        for (int sh = 16; sh > 0; sh >>= 1)
-            I64 += __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(I64), sh), __shfl_xor_sync(0xffffffffu, __double2loint(I64), sh));
-        if (lane == 0u) {
-            const D2DLinkD Lj = P.uniform ? (vj < C ? P.ud_cue : P.ud_due) : P.linkD[vj];
-            const double ex = (double)own.x - rxd.x, ey = (double)own.y - rxd.y;
-            const double Sg = pwd[vpw] * Lj.a_lin * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, P.ple_d);
-            const double r = Sg * d2d_rcp_f64(fma(I64, Lj.inv_noise, 1.0));
-            const bool r1 = fabs(r - 1.0) < 0.0625, s1 = fabs(Sg - 1.0) < 0.0625;
-            const uint64_t gi = (uint64_t)e * N + vj;
-            if (r1 || (THR && P.thr_band > 0.f)) {
-                const double sinr = r1 ? d2d_db_near1(r) : 4.3429448190325182765 * d2d_ln_f64(r);
-                const float sv = THR ? d2d_sinr_store(sinr, P) : (float)sinr;
-                if (P.obs) P.obs[gi * 6u + 4u] = sv;
-                if (P.obs_dyn) P.obs_dyn[gi].x = sv;
-            }
-            if (s1) {
-                const float sv = (float)d2d_db_near1(Sg);
-                if (P.obs) P.obs[gi * 6u + 5u] = sv;
-                if (P.obs_dyn) P.obs_dyn[gi].y = sv;
-            }
-        }
-    }
-}
-
 // FULL: exactly the core outputs (obs, capacity, reward, done) and the step counters are bound and every link of a type shares
 // one set of constants (no per-device overrides) - the VecD2DEnv default - so the hot path tests no pointer and selects its
 // constants from the constant bank.  EXACT: an fp64 shadow of the positions is bound (the fp64 pass then needs d_min).
@@ -193,18 +143,11 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
     uint32_t *cnt = reinterpret_cast<uint32_t *>(d2d_dense_smem + L.cnt);
     float *red = reinterpret_cast<float *>(d2d_dense_smem + L.red);
     uint16_t *ovrb = reinterpret_cast<uint16_t *>(d2d_dense_smem + L.ovrb);
-    uint32_t *qcnt = reinterpret_cast<uint32_t *>(d2d_dense_smem + L.qcnt);
-    uint32_t *qdesc = reinterpret_cast<uint32_t *>(d2d_dense_smem + L.qdesc);
-    float4 *qrec = reinterpret_cast<float4 *>(d2d_dense_smem + L.qrec);
-    // deferred fp64 passes: only when they cannot change a rate / capacity (host flag), and only when the last warp has an empty
-    // link slot to spend on them
-    const bool defer = !EXACT && P.rescue_defer != 0 && N + 32u <= NW * 32u * (uint32_t)LPT;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     d2d_pdl_entry(P.flags);
 
     for (uint32_t i = tid; i < D2D_MAX_PWR_LEVELS; i += BT) { pwr[i] = P.pwr_lin[i]; pwd[i] = P.pwr_lin_d[i]; }
     for (uint32_t i = tid; i < 3u * L.cnt_words; i += BT) cnt[i] = 0u;
-    if (tid < 2u) qcnt[tid] = 0u;
     bool has[LPT], cue[LPT];
 #pragma unroll
     for (int k = 0; k < LPT; ++k) {
@@ -344,7 +287,11 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
                 // one induction variable - the record's shared-window address; the victim's own record is skipped by address
                 const uint32_t pb = (uint32_t)__cvta_generic_to_shared(bp + rb[k] * CAP), pend = pb + nb * 16u, pself = pb + selfq[k] * 16u;
                 float I = 0.0f, dmin2 = 3.0e38f;
-#pragma unroll 2
+#ifndef D2D_DENSE_UNROLL
+#define D2D_DENSE_UNROLL 2
+#endif
+                constexpr int WALK_UNROLL = D2D_DENSE_UNROLL;
+#pragma unroll WALK_UNROLL
                 for (uint32_t pa = pb; pa < pend; pa += 16u) {
                     float4 rk;
                     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(rk.x), "=f"(rk.y), "=f"(rk.z), "=f"(rk.w) : "r"(pa));
@@ -410,26 +357,6 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
                     mask &= mask - 1u;
                     ++resc;
                     const uint32_t vj = (tid - lane) + (uint32_t)src + k * BT;
-                    if (defer) {
-                        // queue it for the last warp (see d2d_dense_drain) unless its RB spilled into the overflow list or the queue is full
-                        const uint32_t vrb = __shfl_sync(0xffffffffu, rb[k], src), vself = __shfl_sync(0xffffffffu, selfq[k], src);
-                        const uint32_t vn = cn[vrb] & 0xffffu;
-                        uint32_t slot = D2D_DENSE_QCAP;
-                        if (vn <= CAP) {
-                            if (lane == 0u) slot = atomicAdd(&qcnt[e & 1u], 1u);
-                            slot = __shfl_sync(0xffffffffu, slot, 0);
-                        }
-                        if (slot < D2D_DENSE_QCAP) {
-                            const uint32_t qi = (e & 1u) * D2D_DENSE_QCAP + slot;
-                            if ((int)lane == src) {
-                                uint32_t *d = qdesc + qi * 8u;
-                                d[0] = vj; d[1] = vself; d[2] = pw[k] | (vn << 16);
-                                d[3] = __float_as_uint(rx[k].x); d[4] = __float_as_uint(rx[k].y);
-                            }
-                            if (lane < vn) qrec[qi * CAP + lane] = bp[vrb * CAP + lane];
-                            continue;
-                        }
-                    }
                     const D2DDenseFix f = d2d_dense_rescue<PLE2, !FULL>(P, e, vj, __shfl_sync(0xffffffffu, rb[k], src), __shfl_sync(0xffffffffu, selfq[k], src),
                                                                  __shfl_sync(0xffffffffu, pw[k], src), bp, cn, ovrec, ovrb, pwd, ovn, lane);
                     if ((int)lane == src) {
@@ -463,26 +390,12 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
             rd[warp] = cap_part; rd[D2D_DENSE_MAX_WARPS + warp] = (float)n_act_w;
             rd[2 * D2D_DENSE_MAX_WARPS + warp] = (float)resc; rd[3 * D2D_DENSE_MAX_WARPS + warp] = bad_w ? 1.f : 0.f;     // resc is warp-uniform
         }
-        // the last warp works off the fp64 passes queued during the previous env (every entry is visible since this env's barrier;
-        // its buffer is refilled only after the next one)
-        if (defer && warp == NW - 1u && e > e0) {
-            const uint32_t qb = (e - 1u) & 1u, qn = min(qcnt[qb], D2D_DENSE_QCAP);
-            if (qn) {
-                d2d_dense_drain<PLE2, !FULL>(P, e - 1u, qdesc + qb * D2D_DENSE_QCAP * 8u, qrec + qb * D2D_DENSE_QCAP * CAP, qn, pwd, lane);
-                __syncwarp();
-            }
-            if (lane == 0u) qcnt[qb] = 0u;
-        }
         if (ovn != 0u) __syncthreads();      // the overflow list has one buffer: everybody is done with it before the next env fills it
         g = g + 1u == BT ? 0u : g + 1u;
         c3 = c3 == 2u ? 0u : c3 + 1u;
     }
     __syncthreads();
     if (e_end > e0) finalise(e_end - 1u, g == 0u ? BT - 1u : g - 1u, true);
-    if (defer && warp == NW - 1u && e_end > e0) {                      // the last env's queue
-        const uint32_t qb = (e_end - 1u) & 1u, qn = min(qcnt[qb], D2D_DENSE_QCAP);
-        if (qn) d2d_dense_drain<PLE2, !FULL>(P, e_end - 1u, qdesc + qb * D2D_DENSE_QCAP * 8u, qrec + qb * D2D_DENSE_QCAP * CAP, qn, pwd, lane);
-    }
 
     if (P.stats) {
         // block totals of the six statistics -> one fp64 atomic each

@@ -523,39 +523,3 @@ def test_band_edge_sweep_of_sinr_and_snr(ple):
           f'snr {e_snr.max():.3e} at {rn[:half][e_snr.argmax()]:+.4f} dB); inside the band {e_sinr[np.abs(rs) < band].max():.2e}')
     assert worst < 0.5e-4, worst                                           # a 2x margin to the 1e-4 bound
     env.close()
-
-
-# ---- dense kernel: fp64 passes deferred to the block's last warp == fp64 passes taken inline -------------------------------------------
-def test_dense_deferred_fp64_pass_equals_inline(monkeypatch):
-    """BASELINE config #3's shape (N = 600 on 10 warps x 2 link slots: the last warp has an empty slot and works the queued passes
-    off one env later) against the same launch with every pass taken inline (D2D_B200_DEFER=0), against the oracle, and on a
-    shape whose last warp has no spare slot (the queue must stay unused there)."""
-    from tests._util import RTOL, assert_rel
-    kw = CONFIGS['dense']
-    cfg = O.OracleConfig(**kw)
-    E = 600                                                   # > one env per block: 444 blocks at most, most step two envs
-    rng = np.random.default_rng(11)
-    pos, act = O.random_positions(cfg, E, rng), O.random_actions(cfg, E, rng)
-    a = torch.as_tensor(act, dtype=torch.int32, device='cuda')
-    monkeypatch.setenv('D2D_B200_GRID', '40')                 # 15 envs per block: queues are filled and drained many times
-    deferred = make_vec(E, kw)
-    monkeypatch.setenv('D2D_B200_DEFER', '0')
-    inline = make_vec(E, kw)
-    monkeypatch.delenv('D2D_B200_DEFER')
-    outs = []
-    for env in (deferred, inline):
-        env.set_positions(pos)
-        env.reset_stats()
-        obs, reward, done, info = env.step(a)
-        torch.cuda.synchronize()
-        outs.append((obs.cpu().numpy(), reward.cpu().numpy(), info['capacity_mbps'].cpu().numpy(), env.stats()))
-    assert outs[0][3]['rescues'] == outs[1][3]['rescues'] > E / 2          # about 1.3 passes per env
-    np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=1e-5, atol=1e-5)
-    np.testing.assert_allclose(outs[0][2], outs[1][2], rtol=1e-5, atol=1e-6)
-    ref = O.step_batch(cfg, pos, act, nthreads=4)
-    for got in outs:
-        assert_rel(got[0][..., 4], ref['sinr_db'], RTOL, 'sinr_db')
-        assert_rel(got[0][..., 5], ref['snr_db'], RTOL, 'snr_db')
-        assert_rel(got[2], ref['capacity_mbps'], RTOL, 'capacity')
-        assert_rel(got[1], ref['reward'], RTOL, 'reward')
-    deferred.close(); inline.close()
