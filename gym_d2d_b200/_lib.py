@@ -13,7 +13,7 @@ from .build import LIB
 ABI_VERSION = 5
 STATS_REPLICAS = 1024
 NUM_STATS = 8
-STAT_NAMES = ('sum_reward', 'sum_capacity_mbps', 'sum_reward_sq', 'env_steps', 'penalties', 'rescues')
+STAT_NAMES = ('sum_reward', 'sum_capacity_mbps', 'sum_reward_sq', 'env_steps', 'penalties', 'rescues', 'ticket_timeouts')
 
 PL_LOG_DISTANCE, PL_FREE_SPACE, PL_COST_HATA, PL_SHADOWING = 0, 1, 2, 3
 OBS_LINEAR = 0

@@ -222,6 +222,7 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
     const bool general = cfg->num_downlinks != 0 || cfg->path_loss_model == D2D_PL_SHADOWING;
     h->use_warp = cfg->num_cues <= 32 && cfg->num_due_pairs <= 32 && cfg->num_rbs <= 64 && !general;
     if (const char *c = std::getenv("D2D_B200_CHUNK")) h->chunk_override = std::atoll(c);
+    if (const char *c = std::getenv("D2D_B200_TICKET")) h->tickets_on = std::atoi(c) != 0;
     const char *pdl = std::getenv("D2D_B200_PDL");
     h->pdl = !(pdl && std::strcmp(pdl, "0") == 0);
     int rc;
@@ -270,6 +271,12 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
     }
     if (const char *gs = std::getenv("D2D_B200_GRID"))      // tests: few blocks, so every block steps many envs
         if (std::atoi(gs) > 0) h->grid = std::min(h->grid, std::atoi(gs));
+    if (h->use_warp) {      // one ticket word per warp slot of the step geometry
+        const size_t words = (size_t)h->grid * h->wpb;
+        cudaError_t et = cudaMalloc(&h->dTickets, words * sizeof(uint64_t));
+        if (et == cudaSuccess) et = cudaMemset(h->dTickets, 0, words * sizeof(uint64_t));
+        if (et != cudaSuccess) return bail(fail(D2D_ERR_CUDA, std::string("ticket buffer: ") + cudaGetErrorString(et)));
+    }
     *out = h;
     return D2D_OK;
 }
@@ -288,7 +295,7 @@ D2D_API int d2d_destroy(d2d_handle_t *h) {
     if (!h) return D2D_OK;
     D2DDeviceGuard guard(h->cfg.cuda_device);
     cudaFree(h->dA); cudaFree(h->dB); cudaFree(h->dD); cudaFree(h->dMeta); cudaFree(h->dPwr); cudaFree(h->dPwrD); cudaFree(h->stage_pos);
-    cudaFree(h->dRngStep); cudaFree(h->act_scratch);
+    cudaFree(h->dRngStep); cudaFree(h->act_scratch); cudaFree(h->dTickets);
     for (auto &s : h->slot) {
         if (s.used && s.ev_out) cudaEventSynchronize(s.ev_out);
         free_slot(s);
@@ -479,6 +486,24 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, int mode, void *s
     else if (!reads_positions) stable = stable && (io->flags & D2D_STEP_INPUTS_STABLE) && h->last_kind != D2D_LAST_OTHER;
     else stable = stable && (io->flags & D2D_STEP_INPUTS_STABLE) && h->last_kind == D2D_LAST_STEP;
     P.flags = (stable ? 0u : D2D_PF_INPUTS_FRESH) | (draw_actions ? D2D_PF_DRAW_ACTIONS : 0u) | (ea.no_reset ? D2D_PF_NO_RESET : 0u);
+    // Per-warp tickets (d2d_common.cuh): a single-launch d2d_step publishes a token per warp; the next one - same stream, same
+    // geometry, inputs declared stable - waits per warp for that token instead of for the whole grid.
+    // (not when a post-pass kernel follows the step kernel: the next step's predecessor in the stream is then that kernel)
+    const bool single_launch = h->use_warp && mode == MODE_STEP && h->dTickets && h->pdl && h->tickets_on &&
+                               h->cfg.reward_fn == D2D_REWARD_SYSTEM_CAPACITY && !io->agent_reward && !h->dRngStep &&
+                               h->cfg.num_envs <= std::max<int64_t>(1, (int64_t)0x7fffffff / std::max(6 * h->N, 2 * h->V)) &&
+                               !(h->chunk_override > 0 && h->chunk_override < h->cfg.num_envs);
+    if (single_launch) {
+        const int grid1 = (int)std::min<int64_t>(h->grid, (h->cfg.num_envs + h->envs_per_block - 1) / h->envs_per_block);
+        const bool follow = stable && h->chain_seq > 0 && h->chain_seq < 0xffffu && h->chain_grid == grid1 && h->last_stream == stream;
+        if (!follow) { ++h->chain_id; h->chain_seq = 0; h->chain_grid = grid1; }
+        P.tickets = h->dTickets;
+        P.tok_wait = follow ? ((h->chain_id << 16) | h->chain_seq) : 0ull;
+        P.tok_sign = (h->chain_id << 16) | (h->chain_seq + 1u);
+        ++h->chain_seq;
+    } else {
+        h->chain_seq = 0;
+    }
     // the kernels index with 32 bits: batches beyond 2^31 / (T max(6N, 2V)) envs (> 7 million default envs) go in chunks
     int64_t chunk = std::max<int64_t>(1, (int64_t)0x7fffffff / std::max(6 * h->N, 2 * h->V));
     if (many) chunk = h->cfg.num_envs;        // the callers checked that T slices fit 32-bit indices

@@ -85,6 +85,10 @@ struct D2DParams {
     const uint64_t *rng_step_dev; // ShadowingPathLoss: the step-call counter in device memory (added to rng_step), advanced on the stream
                                  // after every step so that a replayed CUDA graph draws fresh values each time
     uint32_t flags;              // D2D_PF_*
+    // Per-warp tickets (warp kernel, single-launch d2d_step): see d2d_ticket_wait below
+    uint64_t *tickets;           // [grid * warps per block] one word per warp slot of the launch geometry, or nullptr
+    uint64_t tok_wait;           // != 0: wait for this token in the warp's ticket word instead of executing griddepcontrol.wait
+    uint64_t tok_sign;           // != 0: the token this launch's warps publish when their stores are done
     // d2d_episode (warp kernel, EPISODE instantiation): Simulator.reset + the uncounted reset step + T counted steps in one launch
     uint64_t ep_seed;            // Philox key of this episode's position draws (d2d_reset's `seed`)
     uint64_t act_seed;           // Philox key of the on-device action draws
@@ -170,6 +174,32 @@ __device__ __forceinline__ void d2d_pdl_wait() { asm volatile("griddepcontrol.wa
 __device__ __forceinline__ void d2d_pdl_entry(uint32_t flags) {
     if (flags & D2D_PF_INPUTS_FRESH) d2d_pdl_wait();
     d2d_pdl_launch_dependents();
+}
+// Per-warp tickets.  griddepcontrol.wait orders a launch after ALL of its predecessor, although env e of step k + 1 depends only on
+// env e of step k (its step counter, its output rows), which the SAME warp slot of the same launch geometry stepped.  When the
+// host knows that the previous kernel in the stream was this handle's single-launch d2d_step with the same geometry (and the
+// caller made the D2D_STEP_INPUTS_STABLE promise), launch k + 1 carries tok_wait = the token launch k's warps publish with a
+// gpu-scope RELEASE store after their last store; warp w of launch k + 1 ACQUIRE-spins on its own ticket word in place of the
+// grid-wide wait.  A token is (chain id, position in the chain) - unique per launch of a chain, baked into the launch parameters,
+// so it survives CUDA-graph replays (the word holds the chain's LAST token between replays, never a waited-for one: a chain
+// with a waiter has at least two launches).  Every warp of launch k is resident or finished before a block of launch k + 1 can
+// start (a dependent launches only after every block of its predecessor has executed launch_dependents), so the spin cannot
+// deadlock; and launch k + 1 cannot complete before every warp of launch k has published, so a later consumer ordered after
+// launch k + 1 - by stream order or by its own griddepcontrol.wait - sees launch k's stores as well.
+// The spin is bounded (~10 ms): should a token ever fail to arrive - a host-side bookkeeping bug, not a legal state - the warp falls
+// back to griddepcontrol.wait, which is always sufficient, and counts the event in statistic D2D_STAT_TICKET_TIMEOUTS (tests assert 0).
+__device__ __forceinline__ bool d2d_ticket_wait(const uint64_t *word, uint64_t token) {
+    uint64_t v;
+    for (uint32_t spin = 0; spin < 200000u; ++spin) {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(word) : "memory");
+        if (v == token) return true;
+        __nanosleep(40);
+    }
+    d2d_pdl_wait();
+    return false;
+}
+__device__ __forceinline__ void d2d_ticket_sign(uint64_t *word, uint64_t token) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(word), "l"(token) : "memory");
 }
 
 // envs/d2d_env.py:95: rb = a // n_pwr for a >= 0.  n_pwr is a runtime value, so divide by multiplying

@@ -80,6 +80,12 @@ struct d2d_handle {
     // wrote state a step kernel reads ahead of griddepcontrol.wait)
     void *last_stream = nullptr;
     int last_kind = 0;             // D2D_LAST_*
+    // per-warp tickets (d2d_common.cuh: d2d_ticket_wait): one word per warp slot of the step geometry, and the chain bookkeeping
+    uint64_t *dTickets = nullptr;
+    uint64_t chain_id = 0;         // id of the current chain of single-launch steps
+    uint32_t chain_seq = 0;        // tokens published so far in this chain (0: the previous launch was not a signing step)
+    int chain_grid = 0;            // grid of the chain's launches
+    bool tickets_on = true;        // D2D_B200_TICKET=0 disables (A/B, tests)
     // d2d_episode: handle-owned scratch for drawn actions when the caller does not ask for them but a later pass needs them
     int32_t *act_scratch = nullptr;
     size_t act_scratch_elems = 0;

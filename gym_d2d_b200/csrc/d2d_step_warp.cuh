@@ -717,10 +717,21 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         // griddepcontrol.wait: everything above read only inputs (no step kernel writes actions or positions); from here on every
         // earlier kernel's memory is complete.  What is left after it is the step-counter load, the stores and the exit - the part
         // of a launch that cannot overlap its predecessor (profiles/timeline.py).
+        // (single-launch d2d_step after a d2d_step of the same geometry: this warp waits for ITS predecessor only - d2d_ticket_wait)
 #ifdef D2D_TIMELINE
-        if (e == e0 && t == 0u) { tl_c1 = d2d_tl_clock(); d2d_pdl_wait(); tl_c2 = d2d_tl_clock(); }
-#else
-        if (e == e0 && t == 0u) d2d_pdl_wait();
+        if (e == e0 && t == 0u) tl_c1 = d2d_tl_clock();
+#endif
+        if (e == e0 && t == 0u) {
+            if (!MANY && P.tok_wait != 0ull) {
+                if (lane == 0u && !d2d_ticket_wait(P.tickets + (blockIdx.x * WPB + warp), P.tok_wait) && P.stats)
+                    atomicAdd(P.stats + 6, 1.0);                           // D2D_STAT_TICKET_TIMEOUTS
+                __syncwarp();
+            } else {
+                d2d_pdl_wait();
+            }
+        }
+#ifdef D2D_TIMELINE
+        if (e == e0 && t == 0u) tl_c2 = d2d_tl_clock();
 #endif
 #ifdef D2D_EXPERIMENT_NOCOUNT     // A/B only: how much of the post-wait tail is the step-counter load
         ns_keep = 0;
@@ -826,6 +837,16 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         __syncwarp();     // every lane is done with this env's records and counters before the next env's are written
     }
 
+    // this warp's stores are done: publish the launch's token for the same warp slot of the next launch (d2d_ticket_wait).  A warp
+    // without envs still has to wait for its predecessor first, or its token could overtake an unfinished one's.
+    if (!MANY && P.tok_sign != 0ull) {
+        __syncwarp();
+        if (lane == 0u) {
+            uint64_t *word = P.tickets + (blockIdx.x * WPB + warp);
+            if (e0 >= e_end && P.tok_wait != 0ull && !d2d_ticket_wait(word, P.tok_wait) && P.stats) atomicAdd(P.stats + 6, 1.0);
+            d2d_ticket_sign(word, P.tok_sign);
+        }
+    }
 #ifdef D2D_TIMELINE
     if (lane == 0u && blockIdx.x * WPB + warp < D2D_TL_WARPS) {
         D2DTlRec r; r.g0 = tl_g0; r.c0 = tl_c0; r.c1 = tl_c1; r.c2 = tl_c2; r.c3 = d2d_tl_clock(); r.smid = d2d_tl_smid();

@@ -32,6 +32,12 @@
  * d2d_set_positions, d2d_episode, or on a different stream, the next step is ordered the default way
  * whatever the flag says.  Pre-generated action buffers (replay, evaluation, benchmarks, CUDA graphs of
  * scripted steps) may set it; a loop whose policy writes the actions between steps must not.
+ * Between two consecutive flagged steps the caller may enqueue work that READS the step's outputs, but nothing
+ * that WRITES a buffer either step reads or writes (actions, outputs, the bound positions and step counters):
+ * consecutive flagged single-launch steps of the same geometry do not wait for each other as whole grids -
+ * each warp waits only for the warp that stepped the same environments one launch earlier (a per-warp
+ * release / acquire ticket; gym_d2d_b200/csrc/d2d_common.cuh), which is what removes the grid-wide
+ * completion-and-release latency from a chain of small steps.
  *
  * Index conventions (devices.py:20-25, simulator.py:34-48, envs/d2d_env.py:55-60):
  *   C = num_cues, D = num_due_pairs, N = C + D links, V = 1 + C + 2D devices.
@@ -163,7 +169,9 @@ enum { D2D_OUT_OBS = 1, D2D_OUT_CAPACITY = 2, D2D_OUT_REWARD = 4, D2D_OUT_DONE =
  * this is the vector the multi-GPU shell all-reduces over NCCL (never inside the step). */
 #define D2D_STATS_REPLICAS 1024   /* the stats buffer is [D2D_STATS_REPLICAS][D2D_NUM_STATS]; readers sum over replicas */
 enum { D2D_STAT_SUM_REWARD = 0, D2D_STAT_SUM_CAPACITY = 1, D2D_STAT_SUM_REWARD_SQ = 2,
-       D2D_STAT_ENV_STEPS = 3, D2D_STAT_PENALTIES = 4, D2D_STAT_RESCUES = 5, D2D_NUM_STATS = 8 };
+       D2D_STAT_ENV_STEPS = 3, D2D_STAT_PENALTIES = 4, D2D_STAT_RESCUES = 5,
+       D2D_STAT_TICKET_TIMEOUTS = 6,   /* diagnostic: per-warp ticket waits that fell back to the grid-wide wait (always 0) */
+       D2D_NUM_STATS = 8 };
 
 D2D_API int d2d_abi_version(void);
 D2D_API const char *d2d_last_error(void);

@@ -523,3 +523,68 @@ def test_band_edge_sweep_of_sinr_and_snr(ple):
           f'snr {e_snr.max():.3e} at {rn[:half][e_snr.argmax()]:+.4f} dB); inside the band {e_sinr[np.abs(rs) < band].max():.2e}')
     assert worst < 0.5e-4, worst                                           # a 2x margin to the 1e-4 bound
     env.close()
+
+
+# ---- per-warp tickets: chains of flagged single-launch steps ---------------------------------------------------------------------------------
+@pytest.mark.parametrize('E,grid', [(4096, None), (1000, None), (70000, None), (3000, '7'), (130, '3')])
+def test_ticket_chains_bit_identical_to_serialised_launches(monkeypatch, E, grid):
+    """Consecutive D2D_STEP_INPUTS_STABLE steps wait per warp for the warp that stepped the same envs one launch earlier
+    (d2d_ticket_wait) instead of for the whole previous grid.  Thousands of replays of a 16-step graph that reuses ONE output
+    buffer set (so every step overwrites its predecessor's rows and reads its counters), eager chains, chains broken by a reset
+    and by a change of stream: all bit-identical to a library without programmatic dependent launch; no ticket ever timed out."""
+    if grid:
+        monkeypatch.setenv('D2D_B200_GRID', grid)            # few blocks: warps step many envs, some none
+    monkeypatch.setenv('D2D_B200_PDL', '0')
+    plain = make_vec(E, seed=9)
+    monkeypatch.delenv('D2D_B200_PDL')
+    chain = make_vec(E, seed=9)
+    monkeypatch.setenv('D2D_B200_TICKET', '0')
+    noticket = make_vec(E, seed=9)
+    monkeypatch.delenv('D2D_B200_TICKET')
+    envs = (plain, chain, noticket)
+    for env in envs:
+        env.reset()
+        env.reset_stats()
+    ring = [chain.sample_actions() for _ in range(4)]
+    seq = [ring[i % 4] for i in range(16)]
+    graphs = {env: env.capture_steps(seq, inputs_stable=True) for env in (chain, noticket)}
+    diff = torch.zeros((), dtype=torch.int64, device='cuda')
+    replays = 400 if E <= 4096 else 60
+
+    def check():
+        return ((plain.obs != chain.obs).sum() + (plain.obs != noticket.obs).sum() + (plain.reward != chain.reward).sum() +
+                (plain.step_count != chain.step_count).sum() + (plain.capacity_mbps != chain.capacity_mbps).sum())
+
+    for it in range(replays):
+        for a in seq:
+            plain.step(a)
+        graphs[chain].replay(); graphs[noticket].replay()
+        if it % 20 == 0:
+            diff += check()
+    # eager chains, broken in the middle by a masked reset (new positions: the next step must order itself the default way)
+    mask = torch.ones(E, dtype=torch.uint8, device='cuda')
+    for it in range(40):
+        for env in envs:
+            for k in range(8):
+                env.step(ring[(it + k) % 4], inputs_stable=True)
+            env.reset(mask=mask)
+            env.step(ring[it % 4], inputs_stable=True)
+            env.step(ring[(it + 1) % 4], inputs_stable=True)
+        diff += check() + (plain.positions != chain.positions).sum()
+    # a chain continued on another stream starts over
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for env in envs:
+            for k in range(6):
+                env.step(ring[k % 4], inputs_stable=True)
+    torch.cuda.current_stream().wait_stream(side)
+    diff += check()
+    torch.cuda.synchronize()
+    assert int(diff.item()) == 0
+    sp, sc = plain.stats(), chain.stats()
+    assert sc['ticket_timeouts'] == 0 and noticket.stats()['ticket_timeouts'] == 0
+    assert sp['env_steps'] == sc['env_steps'] and sp['rescues'] == sc['rescues'] and sp['penalties'] == sc['penalties']
+    assert sc['sum_reward'] == pytest.approx(sp['sum_reward'], rel=1e-9)
+    for env in envs:
+        env.close()
