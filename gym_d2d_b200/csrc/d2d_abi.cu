@@ -223,12 +223,15 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
     h->use_warp = cfg->num_cues <= 32 && cfg->num_due_pairs <= 32 && cfg->num_rbs <= 64 && !general;
     if (const char *c = std::getenv("D2D_B200_CHUNK")) h->chunk_override = std::atoll(c);
     if (const char *c = std::getenv("D2D_B200_TICKET")) h->tickets_on = std::atoi(c) != 0;
+    if (const char *c = std::getenv("D2D_B200_TICKET_MIN")) h->ticket_min_quarters = std::max(1, std::atoi(c));
     const char *pdl = std::getenv("D2D_B200_PDL");
     h->pdl = !(pdl && std::strcmp(pdl, "0") == 0);
     int rc;
     if (h->use_warp) {
-        // launch shape by batch size (d2d_step_warp.cuh): about one wave of envs -> 4-warp blocks, many waves -> 8-warp blocks
-        h->wpb = cfg->num_envs >= 65536 ? 8 : cfg->num_envs <= D2D_LATENCY_ENVS ? 2 : 4;
+        // launch shape by batch size (d2d_step_warp.cuh): well under one wave of envs -> 2-warp blocks, everything else 4-warp blocks
+        // (8-warp blocks were the large-batch shape until chains of steps stopped waiting for whole grids: with per-warp tickets
+        // the 4-warp shape's 28 resident warps per SM win at every size - E = 131 072: 63.5 vs 65.9 us; D2D_B200_WPB=8 still selects it)
+        h->wpb = cfg->num_envs <= D2D_LATENCY_ENVS ? 2 : 4;
         if (const char *w = std::getenv("D2D_B200_WPB")) { const int v = std::atoi(w); h->wpb = v == 8 ? 8 : v == 2 ? 2 : 4; }
         h->spec = h->ple2 && h->uniform && cfg->path_loss_model != D2D_PL_COST_HATA && cfg->num_rbs == 25 && cfg->num_cues == 25 && cfg->num_due_pairs == 25 && cfg->n_pwr_cue == 24 &&
                   cfg->n_pwr_due == 21;
@@ -493,8 +496,13 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, int mode, void *s
                                h->cfg.reward_fn == D2D_REWARD_SYSTEM_CAPACITY && !io->agent_reward && !h->dRngStep &&
                                h->cfg.num_envs <= std::max<int64_t>(1, (int64_t)0x7fffffff / std::max(6 * h->N, 2 * h->V)) &&
                                !(h->chunk_override > 0 && h->chunk_override < h->cfg.num_envs);
-    if (single_launch) {
-        const int grid1 = (int)std::min<int64_t>(h->grid, (h->cfg.num_envs + h->envs_per_block - 1) / h->envs_per_block);
+    const int grid1 = (int)std::min<int64_t>(h->grid, (h->cfg.num_envs + h->envs_per_block - 1) / h->envs_per_block);
+    // measured (profiles/README.md): the per-warp hand-off wins as soon as warps step more than one env per launch (E = 6 144,
+    // 1.5 envs per warp: 7.6 -> 5.3 us; E = 16 384: 12.4 -> 9.4 us; E = 131 072: 69.5 -> 65.9 us) and loses at exactly one
+    // (E = 4 096: 5.4 -> 6.8 us; E = 1 024: 2.7 -> 9.5 us), where the hardware's grid-wide wait stays - and where the launches do
+    // not publish tokens either (the release store holds a warp's block slot for an L2 round trip: 5.4 -> 10 us at E = 4 096)
+    const bool worth = 4 * h->cfg.num_envs >= (int64_t)h->ticket_min_quarters * grid1 * h->wpb;
+    if (single_launch && worth) {
         const bool follow = stable && h->chain_seq > 0 && h->chain_seq < 0xffffu && h->chain_grid == grid1 && h->last_stream == stream;
         if (!follow) { ++h->chain_id; h->chain_seq = 0; h->chain_grid = grid1; }
         P.tickets = h->dTickets;

@@ -86,6 +86,8 @@ struct d2d_handle {
     uint32_t chain_seq = 0;        // tokens published so far in this chain (0: the previous launch was not a signing step)
     int chain_grid = 0;            // grid of the chain's launches
     bool tickets_on = true;        // D2D_B200_TICKET=0 disables (A/B, tests)
+    int ticket_min_quarters = 5;   // D2D_B200_TICKET_MIN: tickets from this many QUARTER envs per warp (5 = 1.25 envs): with one env per
+                                   // warp the hardware's grid-wide wait is cheaper than the release / acquire hand-off (two L2 round trips)
     // d2d_episode: handle-owned scratch for drawn actions when the caller does not ask for them but a later pass needs them
     int32_t *act_scratch = nullptr;
     size_t act_scratch_elems = 0;
