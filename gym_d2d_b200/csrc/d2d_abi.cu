@@ -241,6 +241,13 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
         cudaError_t et = h->wpb == 8 ? d2d_warp_tables_8(pwr_d) : h->wpb == 2 ? d2d_warp_tables_2(pwr_d) : d2d_warp_tables_4(pwr_d);
         if (et != cudaSuccess) return bail(fail(D2D_ERR_CUDA, std::string("cudaMemcpyToSymbol(d2d_pwr_lin_c): ") + cudaGetErrorString(et)));
         const size_t smem = h->wpb == 8 ? d2d_warp_smem_8(cfg->num_rbs) : h->wpb == 2 ? d2d_warp_smem_2(cfg->num_rbs) : d2d_warp_smem_4(cfg->num_rbs);
+        if (h->wpb == 4 && cfg->num_envs >= 65536 && !std::getenv("D2D_B200_WPB")) {      // the fused launches' own shape
+            et = d2d_warp_tables_8(pwr_d);
+            if (et != cudaSuccess) return bail(fail(D2D_ERR_CUDA, std::string("cudaMemcpyToSymbol(d2d_pwr_lin_c): ") + cudaGetErrorString(et)));
+            rc = d2d_warp_plan_8(h, d2d_warp_smem_8(cfg->num_rbs));
+            if (rc != D2D_OK) return bail(rc);
+            h->many.wpb = 8; h->many.grid = h->grid; h->many.smem = h->smem; h->many.envs_per_block = h->envs_per_block;
+        }
         rc = h->wpb == 8 ? d2d_warp_plan_8(h, smem) : h->wpb == 2 ? d2d_warp_plan_2(h, smem) : d2d_warp_plan_4(h, smem);
     } else {
         // <= 1024 links: the binned one-barrier kernel (d2d_step_dense.cuh), LPT links per thread; when its double-buffered
@@ -273,7 +280,7 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
         if (rc != D2D_OK) return bail(rc);
     }
     if (const char *gs = std::getenv("D2D_B200_GRID"))      // tests: few blocks, so every block steps many envs
-        if (std::atoi(gs) > 0) h->grid = std::min(h->grid, std::atoi(gs));
+        if (std::atoi(gs) > 0) { h->grid = std::min(h->grid, std::atoi(gs)); h->many.grid = std::min(h->many.grid, std::atoi(gs)); }
     if (h->use_warp) {      // one ticket word per warp slot of the step geometry
         const size_t words = (size_t)h->grid * h->wpb;
         cudaError_t et = cudaMalloc(&h->dTickets, words * sizeof(uint64_t));
@@ -540,18 +547,21 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, int mode, void *s
 #ifdef D2D_TIMELINE
         P.tl_slot = (int32_t)(h->launches % D2D_TL_SLOTS);
 #endif
-        const int grid = (int)std::min<int64_t>(h->grid, (n + h->envs_per_block - 1) / h->envs_per_block);
-        if (h->use_warp) { const int64_t warps = (int64_t)grid * h->wpb; P.envs_per_warp = (uint32_t)((n + warps - 1) / warps); }
+        const bool alt = many && h->many.wpb != 0;               // fused multi-step launches of large batches: their own shape
+        const int wpb = alt ? h->many.wpb : h->wpb, epb = alt ? h->many.envs_per_block : h->envs_per_block;
+        const int grid = (int)std::min<int64_t>(alt ? h->many.grid : h->grid, (n + epb - 1) / epb);
+        if (h->use_warp) { const int64_t warps = (int64_t)grid * wpb; P.envs_per_warp = (uint32_t)((n + warps - 1) / warps); }
         D2DLaunchSel sel;
         sel.many = mode == MODE_MANY; sel.episode = mode == MODE_EPISODE;
         sel.no_reset = ea.no_reset;
         sel.fast = mode == MODE_EPISODE && draw_actions && !io->actions_out;
         sel.exact = h->pos64 != nullptr;
+        sel.smem = alt ? h->many.smem : h->smem;
         // FULL: exactly the core outputs were passed, so the kernel tests no output pointer on its hot path
         sel.full = io->obs && io->capacity_mbps && io->reward && io->done && !io->rate_bps && !io->rb && !io->tx_pwr_dBm && !io->obs_dyn &&
                    h->step_count && h->cfg.reward_fn == D2D_REWARD_SYSTEM_CAPACITY;
         cudaError_t err;
-        if (h->use_warp) err = h->wpb == 8 ? d2d_warp_launch_8(h, P, grid, sel, st, h->pdl) : h->wpb == 2 ? d2d_warp_launch_2(h, P, grid, sel, st, h->pdl)
+        if (h->use_warp) err = wpb == 8 ? d2d_warp_launch_8(h, P, grid, sel, st, h->pdl) : wpb == 2 ? d2d_warp_launch_2(h, P, grid, sel, st, h->pdl)
                                                                                                        : d2d_warp_launch_4(h, P, grid, sel, st, h->pdl);
         else if (h->dense_bt) err = d2d_dense_launch(h, P, grid, sel, st, h->pdl);
         else err = d2d_block_launch(h, P, grid, st, h->pdl);

@@ -54,6 +54,10 @@ struct d2d_handle {
     int64_t chunk_override = 0;  // D2D_B200_CHUNK: force small launch chunks (tests of the > 2^31-element path)
     bool pdl = true;           // programmatic dependent launch (D2D_B200_PDL=0 disables)
     int grid = 0, block = 0, smem = 0, envs_per_block = 0;
+    // second geometry of the warp kernel for the fused multi-step launches (d2d_step_many / d2d_episode / d2d_rollout) of large
+    // batches: their warps run for hundreds of microseconds and never hand over per step, and there 8-warp blocks measured
+    // better than the 4-warp shape the single steps use (episode at E = 131 072: 785 vs 830 us); wpb = 0: same geometry as the steps
+    struct { int wpb = 0, grid = 0, smem = 0, envs_per_block = 0; } many;
     double K_dB = 0.0, ple = 2.0;
     D2DLinkA *dA = nullptr;
     D2DLinkB *dB = nullptr;
@@ -165,6 +169,7 @@ struct D2DLaunchSel {
     bool episode = false;    // d2d_episode / d2d_rollout: P.T slices per env; positions and / or actions are drawn inside the kernel
     bool fast = false;       // ... with drawn actions, no action record and no fp64 shadow: the compiled-in variants
     bool no_reset = false;   // ... d2d_rollout
+    int smem = 0;            // dynamic shared memory of the geometry this launch uses
 };
 
 // warp kernel (d2d_step_warp.cuh), one TU per warps-per-block shape

@@ -60,9 +60,9 @@ int D2D_CAT(d2d_warp_plan_, D2D_TU_WPB)(d2d_handle *h, size_t smem) {
 
 cudaError_t D2D_CAT(d2d_warp_launch_, D2D_TU_WPB)(const d2d_handle *h, const D2DParams &P, int grid, const D2DLaunchSel &sel, cudaStream_t st,
                                                   bool pdl) {
-    if (h->spec) return launch<true, true>(P, grid, (size_t)h->smem, sel, st, pdl);
-    if (h->ple2) return launch<true, false>(P, grid, (size_t)h->smem, sel, st, pdl);
-    return launch<false, false>(P, grid, (size_t)h->smem, sel, st, pdl);
+    if (h->spec) return launch<true, true>(P, grid, (size_t)sel.smem, sel, st, pdl);
+    if (h->ple2) return launch<true, false>(P, grid, (size_t)sel.smem, sel, st, pdl);
+    return launch<false, false>(P, grid, (size_t)sel.smem, sel, st, pdl);
 }
 
 // the fp64 pass reads 10^(p/10) from this translation unit's constant bank (per device: set at every d2d_create)

@@ -588,3 +588,26 @@ def test_ticket_chains_bit_identical_to_serialised_launches(monkeypatch, E, grid
     assert sc['sum_reward'] == pytest.approx(sp['sum_reward'], rel=1e-9)
     for env in envs:
         env.close()
+
+
+def test_large_batch_fused_launches_use_their_own_shape_and_agree():
+    """From 65 536 envs the fused launches (d2d_step_many / d2d_episode / d2d_rollout) run in 8-warp blocks while single steps run
+    in 4-warp blocks with per-warp tickets: same results."""
+    E, T = 70000, 2
+    fused = make_vec(E, seed=41)
+    single = make_vec(E, seed=41)
+    out = fused.episode(T, record_actions=True)
+    single.reset(mask=torch.ones(E, dtype=torch.uint8, device='cuda'))
+    assert torch.equal(fused.positions, single.positions)
+    for t in range(T + 1):
+        if t == 0:
+            single._bind(False)
+        obs, reward, done, info = single.step(out['actions'][t], inputs_stable=(t > 0))
+        single._bind(True)
+        assert torch.equal(out['obs'][t], obs) and torch.equal(out['reward'][t], reward) and torch.equal(out['capacity_mbps'][t], info['capacity_mbps'])
+    ro = fused.rollout(3, action_seed=5, first_step_index=7, record_actions=True)
+    many = single.step_many(ro['actions'].contiguous())
+    for k in ('obs', 'reward', 'done', 'capacity_mbps'):
+        assert torch.equal(ro[k], many[k]), k
+    assert fused.stats()['ticket_timeouts'] == 0 and single.stats()['ticket_timeouts'] == 0
+    fused.close(); single.close()
