@@ -379,7 +379,7 @@ def run_cuda_arm(args) -> None:
     ring_bytes = RING * (acts[0].numel() * 4 + outs[0].nbytes())
 
     traffic = None
-    prof = ROOT / 'profiles' / 'roofline_r01.json'
+    prof = ROOT / 'profiles' / 'roofline_r02.json'
     if prof.exists():
         try:
             traffic = json.loads(prof.read_text()).get(f'dram_bytes_per_launch_E{E}')
@@ -542,7 +542,12 @@ def run_cuda_arm(args) -> None:
                        'last_episode_stats': {k: last[k] for k in ('env_steps', 'mean_reward', 'mean_capacity_mbps', 'penalties')},
                        'roofline': {'bound': 'hbm', 'algorithmic_bytes_per_env_episode': BE,
                                     'achieved': BE * EL * args.episodes / secsE / 1e9, 'peak': peak, 'unit': 'GB/s',
-                                    'frac': BE * EL * args.episodes / secsE / 1e9 / peak}}
+                                    'frac': BE * EL * args.episodes / secsE / 1e9 / peak, 'traffic': None}}
+            if prof.exists():
+                try:
+                    episode['roofline']['traffic'] = json.loads(prof.read_text()).get(f'dram_bytes_per_launch_episode_E{EL}')
+                except Exception:  # noqa: BLE001
+                    pass
             del ep_outs
         envL.close()
         del envL

@@ -403,7 +403,8 @@ int reset_launch(d2d_handle *h, uint64_t seed, uint64_t first_global_env, const 
         d2d_reset_kernel<<<grid, 256, 0, st>>>(h->pos + e0 * h->V * 2, h->pos64 ? h->pos64 + e0 * h->V * 2 : nullptr,
                                                h->step_count ? h->step_count + e0 : nullptr, env_mask ? env_mask + e0 : nullptr,
                                                (uint32_t)total, (uint32_t)C, (uint32_t)D, (float)h->cfg.cell_radius_m,
-                                               (float)h->cfg.d2d_radius_m, seed, first_global_env + (uint64_t)e0);
+                                               (float)h->cfg.d2d_radius_m, seed, first_global_env + (uint64_t)e0,
+                                               (uint32_t)((0x100000000ull + (uint64_t)units - 1) / (uint64_t)units));
         D2D_CUDA(cudaGetLastError());
         ++h->launches;
     }

@@ -19,14 +19,20 @@ __global__ void d2d_set_positions_kernel(const double *__restrict__ src, float *
 }
 
 // Simulator.reset (simulator.py:61-75): one thread per (env, draw unit) - a pair of CUEs or one DUE pair, one Philox block each
-// (d2d_common.cuh) - writing 16 bytes; a DUE unit re-draws its receiver around the transmitter until it falls inside the cell
-// (position.py:31-45).  units = ceil(C / 2) + D per env; `total` = num_envs * units < 2^32 per launch (the host chunks).
+// (d2d_common.cuh) - writing 16 bytes.  Both kinds of unit run the SAME instruction stream - two uniform-in-disc draws from the
+// block's four words, the second one with the cell radius (a CUE) or as an offset of d2d radius from the first (a DUE receiver) -
+// so a warp that holds both kinds does not execute two divergent halves; only the in-cell re-draw of a receiver
+// (position.py:31-45, a few per cent of the pairs) diverges.  units = ceil(C / 2) + D per env; `total` = num_envs * units
+// < 2^32 per launch (the host chunks); `magic` = ceil(2^32 / units) turns the env index into one multiply.
 __global__ void d2d_reset_kernel(float *__restrict__ pos, double *__restrict__ pos64, uint8_t *__restrict__ step_count,
                                  const uint8_t *__restrict__ env_mask, uint32_t total, uint32_t C, uint32_t D, float cell_radius,
-                                 float d2d_radius, uint64_t seed, uint64_t first_global_env) {
+                                 float d2d_radius, uint64_t seed, uint64_t first_global_env, uint32_t magic) {
     const uint32_t CU = (C + 1u) >> 1, U = CU + D, V = 1u + C + 2u * D;
+    const float r2max = __fmul_rn(cell_radius, cell_radius);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const uint32_t e = i / U, u = i - e * U;
+        uint32_t e = __umulhi(i, magic);
+        e -= (e * U > i) ? 1u : 0u;                              // (the magic may overshoot by one for large i)
+        const uint32_t u = i - e * U;
         if (env_mask && !env_mask[e]) continue;
         float2 *pe = reinterpret_cast<float2 *>(pos) + (uint64_t)e * V;
         double2 *pe64 = pos64 ? reinterpret_cast<double2 *>(pos64) + (uint64_t)e * V : nullptr;
@@ -36,24 +42,25 @@ __global__ void d2d_reset_kernel(float *__restrict__ pos, double *__restrict__ p
             if (pe64) pe64[0] = make_double2(0.0, 0.0);
             if (step_count) step_count[e] = 0;                   // envs/d2d_env.py:46
         }
-        if (u < CU) {
-            const uint4 b = d2d_reset_block(seed, g, u, 0u);
-            const uint32_t j = 2u * u;
-            const float2 c0 = d2d_disc_from_words(b.x, b.y, cell_radius);
-            pe[1u + j] = c0;
-            if (pe64) pe64[1u + j] = make_double2((double)c0.x, (double)c0.y);
-            if (j + 1u < C) {
-                const float2 c1 = d2d_disc_from_words(b.z, b.w, cell_radius);
-                pe[2u + j] = c1;
-                if (pe64) pe64[2u + j] = make_double2((double)c1.x, (double)c1.y);
+        const bool due = u >= CU;
+        uint4 b = d2d_reset_block(seed, g, u, 0u);
+        const float2 p0 = d2d_disc_from_words(b.x, b.y, cell_radius);
+        float2 p1 = d2d_disc_from_words(b.z, b.w, due ? d2d_radius : cell_radius);
+        if (due) {
+            p1 = make_float2(__fadd_rn(p0.x, p1.x), __fadd_rn(p0.y, p1.y));
+            // position.py:38-44: re-draw the receiver until it falls inside the cell (the same candidates as d2d_draw_due)
+            for (uint32_t k = 1; k < D2D_RESET_MAX_OFFSETS && __fadd_rn(__fmul_rn(p1.x, p1.x), __fmul_rn(p1.y, p1.y)) > r2max; ++k) {
+                if (k & 1u) b = d2d_reset_block(seed, g, u, (k + 1u) >> 1);
+                const float2 o = (k & 1u) ? d2d_disc_from_words(b.x, b.y, d2d_radius) : d2d_disc_from_words(b.z, b.w, d2d_radius);
+                p1 = make_float2(__fadd_rn(p0.x, o.x), __fadd_rn(p0.y, o.y));
             }
-        } else {
-            const uint32_t d = u - CU, t = 1u + C + 2u * d;
-            const float4 p = d2d_draw_due(seed, g, CU, d, cell_radius, d2d_radius);
-            if ((((uintptr_t)(pe + t)) & 15u) == 0u) *reinterpret_cast<float4 *>(pe + t) = p;
-            else { pe[t] = make_float2(p.x, p.y); pe[t + 1u] = make_float2(p.z, p.w); }
-            if (pe64) { pe64[t] = make_double2((double)p.x, (double)p.y); pe64[t + 1u] = make_double2((double)p.z, (double)p.w); }
         }
+        // devices 1 + 2u, 2 + 2u (CUEs; the second one may not exist) or 1 + C + 2d, 2 + C + 2d (a DUE pair)
+        const uint32_t t = due ? 1u + C + 2u * (u - CU) : 1u + 2u * u;
+        const bool two = due || 2u * u + 1u < C;
+        if (two && (((uintptr_t)(pe + t)) & 15u) == 0u) *reinterpret_cast<float4 *>(pe + t) = make_float4(p0.x, p0.y, p1.x, p1.y);
+        else { pe[t] = p0; if (two) pe[t + 1u] = p1; }
+        if (pe64) { pe64[t] = make_double2((double)p0.x, (double)p0.y); if (two) pe64[t + 1u] = make_double2((double)p1.x, (double)p1.y); }
     }
 }
 
