@@ -268,6 +268,9 @@ def timed_steps(env, torch, actions, outs, steps, warmup, dist, use_graph=True):
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = env.launch_count
     t0 = time.perf_counter()
+    # keep the device busy for ~0.3 ms while the host enqueues the timed region, so that the window between the two events holds
+    # the K steps back to back and not the host's launch latency after an idle device (it varied 5-20 us between ranks and boxes)
+    torch.cuda._sleep(600_000)
     start.record()
     done = 0
     if graph is not None:
