@@ -256,7 +256,8 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
                      ? (h->N + D2D_BLOCK_THREADS - 1) / D2D_BLOCK_THREADS : 0;      // downlinks: the general-topology kernel
         h->bin_cap = d2d_dense_bin_cap_host(h->N, cfg->num_rbs);
         const char *dn = std::getenv("D2D_B200_DENSE");
-        const bool dense = h->lpt > 0 && d2d_dense_smem(h->N, cfg->num_rbs, h->bin_cap) <= 72 * 1024 && !(dn && std::atoi(dn) == 0);
+        const bool dense = h->lpt > 0 && cfg->num_rbs <= 512 /* 9 bits of the packed link state */ && d2d_dense_smem(h->N, cfg->num_rbs, h->bin_cap) <= 72 * 1024 &&
+                           !(dn && std::atoi(dn) == 0);
         if (dense) {
             // threads per block / links per thread: the shape with the fewest (warp, slot) bodies per env - every warp runs the
             // straight-line code of each of its slots whether or not all 32 lanes hold a link (N = 600: 10 warps x 2 slots,

@@ -29,11 +29,12 @@
 
 #define D2D_DENSE_MAX_LPT 5
 #define D2D_DENSE_MAX_WARPS 16
+#define D2D_DENSE_MAX_BT 320u          // the largest block of D2D_DENSE_SHAPES (d2d_tu_dense.cu)
 // blocks per SM the register allocation has to allow (80 registers at 256 threads)
 #define D2D_DENSE_MINB(BT) ((BT) <= 128 ? 6 : (BT) <= 160 ? 5 : (BT) <= 192 ? 4 : 3)
 
 struct D2DDenseLayout {
-    uint32_t bins, ovrec, pwr, pwr_d, cnt, red, ovrb, total, cnt_words;
+    uint32_t bins, ovrec, pwr, pwr_d, cnt, red, sst, act, grp, ovrb, total, cnt_words;
 };
 
 __host__ __device__ inline D2DDenseLayout d2d_dense_layout(int N, int R, int cap) {
@@ -42,22 +43,27 @@ __host__ __device__ inline D2DDenseLayout d2d_dense_layout(int N, int R, int cap
     L.pwr_d = b; b += D2D_MAX_PWR_LEVELS * 8u;                            // 10^(p/10) in fp64 (the fp64 pass)  (fixed offsets first)
     L.pwr = b;   b += D2D_MAX_PWR_LEVELS * 4u;                            // 10^(p/10)
     L.red = b;   b += 2u * 4u * D2D_DENSE_MAX_WARPS * 4u;                 // [2][4][warps]: capacity, acting agents, rescues, penalty
+    L.sst = b;   b += 8u * 8u;                                            // the block's statistics (one thread adds to them per env)
+    L.act = b;   b += (((uint32_t)N + D2D_DENSE_MAX_BT - 1u) / D2D_DENSE_MAX_BT + 1u) * D2D_DENSE_MAX_BT * 4u;   // [LPT][BT] staged actions of the next env (LPT * BT < N + 2 BT)
+    L.grp = b;   b += 2u * D2D_DENSE_MAX_BT * 4u;                        // [2][BT]: reward and step counter of the envs of the current group of BT
     L.cnt_words = ((uint32_t)R + 2u + 3u) & ~3u;                          // per buffer: R counters (links | SIDELINKs << 16), overflow count
     L.cnt = b;   b += 3u * L.cnt_words * 4u;
-    L.bins = b;  b += 2u * (uint32_t)R * (uint32_t)cap * 16u;            // [2][R][cap] float4 peer records
+    b = (b + 127u) & ~127u;
+    L.bins = b;  b += 2u * (uint32_t)R * (uint32_t)cap * 16u;            // [2][R][cap] float4 peer records; 128-byte aligned, cap % 8 == 0
     L.ovrec = b; b += (uint32_t)N * 16u;                                  // [N] overflow records
     L.ovrb = b;  b += ((uint32_t)N * 2u + 15u) & ~15u;                    // [N] RB of each overflow record
-    L.total = b;
+    L.total = b + 112u;                                                   // the kernel rounds the dynamic window's base up to 128 bytes
     return L;
 }
 
-// bin capacity for an expected per-RB load of N / R links: mean + 4 sigma, at least 8, odd
+// bin capacity for an expected per-RB load of N / R links: mean + 3.5 sigma rounded up to a multiple of 8 (the walk's conflict-free
+// rotation works on 128-byte groups of 8 records)
 __host__ inline int d2d_dense_bin_cap(int N, int R) {
     const double m = (double)N / (double)(R > 0 ? R : 1);
-    int cap = (int)(m + 4.0 * sqrt(m) + 2.0);
-    if (cap < 8) cap = 8;
+    int cap = (int)(m + 3.5 * sqrt(m) + 1.0);
     if (cap > N) cap = N;
-    return cap | 1;
+    if (cap < 8) cap = 8;
+    return (cap + 7) & ~7;
 }
 
 // interferer record rk's fp64 term at receiver rxd (the cooperative fp64 pass); pwd = the fp64 power table in shared memory
@@ -83,20 +89,17 @@ struct D2DDenseFix {
 template <bool PLE2, bool THR>
 __device__ __noinline__ D2DDenseFix d2d_dense_rescue(const D2DParams &P, uint32_t e, uint32_t vj, uint32_t vrb, uint32_t vself, uint32_t vpw,
                                                      const float4 *bp, const uint32_t *cn, const float4 *ovrec,
-                                                     const uint16_t *ovrb, const double *pwd, uint32_t ovn, uint32_t lane) {
-    // (without an fp64 shadow of the positions and with uniform link constants the only global access is the victim's receiver
-    // position: the transmitters come from the peer records, the tables from shared memory and the constant bank - the pass
-    // sits between two block barriers, so its latency is what the other warps wait for)
+                                                     const uint16_t *ovrb, const double *pwd, uint32_t ovn, uint32_t lane, float vrx_x, float vrx_y) {
+    // (without an fp64 shadow of the positions and with uniform link constants the pass reads no global memory: the victim's
+    // receiver comes from its lane's registers, the transmitters from the peer records, the tables from shared memory and the
+    // constant bank - the pass sits between two block barriers, so its latency is what the other warps wait for)
     const uint32_t C = (uint32_t)P.C, V = (uint32_t)P.V, CAP = (uint32_t)P.bin_cap;
     const bool exact = P.pos64 != nullptr;
     const double2 *pe64 = exact ? reinterpret_cast<const double2 *>(P.pos64) + (int64_t)e * V : nullptr;
     const float4 own = vself < CAP ? bp[vrb * CAP + vself] : ovrec[vself - CAP];                 // the victim's own record: (tx_x, tx_y, ..)
     const double2 txd = exact ? pe64[d2d_tx_dev((int)vj, (int)C)] : make_double2((double)own.x, (double)own.y);
     double2 rxd = make_double2(0.0, 0.0);                                                          // a CUE's receiver: the MBS at the origin
-    if (vj >= C) {
-        if (exact) rxd = pe64[d2d_rx_dev((int)vj, (int)C)];
-        else { const float2 r = (reinterpret_cast<const float2 *>(P.pos) + (uint64_t)e * V)[d2d_rx_dev((int)vj, (int)C)]; rxd = make_double2((double)r.x, (double)r.y); }
-    }
+    if (vj >= C) rxd = exact ? pe64[d2d_rx_dev((int)vj, (int)C)] : make_double2((double)vrx_x, (double)vrx_y);
     const uint32_t vn = cn[vrb] & 0xffffu, vnb = min(vn, CAP);
     const float4 *vbase = bp + vrb * CAP;
     double I64 = 0.0;
@@ -136,18 +139,27 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
     const uint32_t npc = (uint32_t)P.n_pwr_cue, npd = (uint32_t)P.n_pwr_due;
     const uint32_t mgc = P.magic_cue, mgd = P.magic_due, n1c = P.npw1_cue, n1d = P.npw1_due;
     const D2DDenseLayout L = d2d_dense_layout((int)N, (int)R, (int)CAP);
-    float4 *bins = reinterpret_cast<float4 *>(d2d_dense_smem + L.bins);
-    float4 *ovrec = reinterpret_cast<float4 *>(d2d_dense_smem + L.ovrec);
-    float *pwr = reinterpret_cast<float *>(d2d_dense_smem + L.pwr);
-    double *pwd = reinterpret_cast<double *>(d2d_dense_smem + L.pwr_d);
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(d2d_dense_smem + L.cnt);
-    float *red = reinterpret_cast<float *>(d2d_dense_smem + L.red);
-    uint16_t *ovrb = reinterpret_cast<uint16_t *>(d2d_dense_smem + L.ovrb);
+    // the bins sit on 128-byte boundaries of the shared window (see the walk): round the dynamic region's base up
+    unsigned char *const sm = d2d_dense_smem + ((0u - (uint32_t)__cvta_generic_to_shared(d2d_dense_smem)) & 127u);
+    float4 *bins = reinterpret_cast<float4 *>(sm + L.bins);
+    float4 *ovrec = reinterpret_cast<float4 *>(sm + L.ovrec);
+    float *pwr = reinterpret_cast<float *>(sm + L.pwr);
+    double *pwd = reinterpret_cast<double *>(sm + L.pwr_d);
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(sm + L.cnt);
+    float *red = reinterpret_cast<float *>(sm + L.red);
+    uint16_t *ovrb = reinterpret_cast<uint16_t *>(sm + L.ovrb);
+    // block-level scalars in shared memory rather than in registers that would live across the whole env loop (and spill):
+    // the statistics of the envs this block stepped, and the reward / step counter of every env of the current group
+    double *sst = reinterpret_cast<double *>(sm + L.sst);
+    float *grew = reinterpret_cast<float *>(sm + L.grp);
+    int32_t *gns = reinterpret_cast<int32_t *>(sm + L.grp) + D2D_DENSE_MAX_BT;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t act_sa = (uint32_t)__cvta_generic_to_shared(sm + L.act) + tid * 4u;      // this thread's staged actions: [k][tid]
     d2d_pdl_entry(P.flags);
 
     for (uint32_t i = tid; i < D2D_MAX_PWR_LEVELS; i += BT) { pwr[i] = P.pwr_lin[i]; pwd[i] = P.pwr_lin_d[i]; }
     for (uint32_t i = tid; i < 3u * L.cnt_words; i += BT) cnt[i] = 0u;
+    if (tid < 8u) sst[tid] = 0.0;
     bool has[LPT], cue[LPT];
 #pragma unroll
     for (int k = 0; k < LPT; ++k) {
@@ -162,30 +174,33 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
     auto link_sB = [&](uint32_t j, bool is_cue) -> float2 {
         return (FULL || P.uniform) ? (is_cue ? P.us_cue : P.us_due) : __ldg(reinterpret_cast<const float2 *>(P.linkB + j));
     };
-    // one coalesced pass over an env's inputs: action, transmitter and (DUE) receiver position of each of this thread's links
-    auto load_inputs = [&](uint32_t e, uint32_t (&a)[LPT], float2 (&tx)[LPT], float2 (&rx)[LPT]) {
+    // one coalesced pass over an env's inputs: action, transmitter and (DUE) receiver position of each of this thread's links.
+    // Branch-free: a thread without a link in slot k re-reads the env's last link and never uses the values (a conditional load
+    // made the compiler keep the prefetched actions in local memory - and wait for each load right behind its issue).
+    auto load_inputs = [&](uint32_t e, float2 (&tx)[LPT], float2 (&rx)[LPT]) {
         const int32_t *act = P.actions + e * N;
         const float2 *pe = reinterpret_cast<const float2 *>(P.pos) + e * V;
 #pragma unroll
         for (int k = 0; k < LPT; ++k) {
-            const uint32_t j = tid + k * BT;
-            a[k] = 0xffffffffu; tx[k] = make_float2(1.f, 0.f); rx[k] = make_float2(0.f, 0.f);
-            if (has[k]) {
-                a[k] = (uint32_t)__ldg(act + j);
-                const uint32_t txd = cue[k] ? 1u + j : 1u + C + 2u * (j - C);
-                tx[k] = __ldg(pe + txd);
-                if (!cue[k]) rx[k] = __ldg(pe + txd + 1u);
-            }
+            const uint32_t j = min(tid + k * BT, N - 1u);
+            const uint32_t txd = cue[k] ? 1u + j : 1u + C + 2u * (j - C);
+            // the action goes to this thread's own staging word without passing through a register (cp.async; read back by the
+            // same thread after cp.async.wait_all): held in a register over the walk it was the value the compiler spilled -
+            // with the spill store waiting for the load right behind its issue
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(act_sa + (uint32_t)k * BT * 4u), "l"(act + j) : "memory");
+            tx[k] = __ldg(pe + txd);                              // (has[k] is applied where the values are used)
+            rx[k] = __ldg(pe + (cue[k] ? 0u : txd + 1u));         // a CUE's receiver: the MBS (device 0)
         }
     };
-    float st_reward = 0.f, st_cap = 0.f, st_reward2 = 0.f, st_pen = 0.f, st_resc = 0.f, st_n = 0.f;   // of the envs this thread owns
-
+    auto staged_action = [&](int k) -> uint32_t {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(act_sa + (uint32_t)k * BT * 4u) : "memory");
+        return v;
+    };
     const uint32_t num_envs = (uint32_t)P.num_envs;
     const uint32_t per_block = (num_envs + gridDim.x - 1u) / gridDim.x;
     const uint32_t e0 = min(blockIdx.x * per_block, num_envs), e_end = min(e0 + per_block, num_envs);
     uint32_t g = 0;                  // position of the env in its group of BT
-    int ns_keep = 0;                 // thread i: step counter of the group's env i
-    float rew_keep = 0.f;            // thread i: reward of the group's env i
 
     // reward / statistics of env `ep` (buffer pb of red), by the thread that owns it; the group's scalars when it is complete
     auto finalise = [&](uint32_t ep, uint32_t gp, bool flush) {
@@ -198,24 +213,27 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
             }
             const bool any_bad = bd != 0.f;
             const float reward = any_bad ? -1.0f : cs / na;
-            rew_keep = reward;
-            if (P.reward_fn == 0) { st_reward += reward; st_reward2 = fmaf(reward, reward, st_reward2); }
-            st_cap += cs;
-            st_pen += any_bad ? 1.f : 0.f; st_resc += rs; st_n += 1.f;
+            grew[gp] = reward;
+            // (one thread per env, and consecutive envs' threads are a barrier apart: plain read-modify-writes)
+            if (P.reward_fn == 0) { sst[0] += (double)reward; sst[2] += (double)reward * (double)reward; }
+            sst[1] += (double)cs;
+            sst[3] += 1.0; sst[4] += any_bad ? 1.0 : 0.0; sst[5] += (double)rs;
         }
-        if (flush && tid <= gp) {
-            // envs/d2d_env.py:65,68 for the whole group: num_steps += 1; done = num_steps >= EPISODE_LENGTH
-            const uint32_t eg = ep - gp + tid;
-            const int ns = min(ns_keep + 1, 255);
-            if (FULL || P.step_count) P.step_count[eg] = (uint8_t)ns;
-            if (FULL || P.reward) P.reward[eg] = rew_keep;
-            if (FULL || P.done) P.done[eg] = ns >= P.episode_length ? 1 : 0;
+        if (flush) {
+            __syncthreads();                                     // (block-uniform) the last env's reward is in grew
+            if (tid <= gp) {
+                // envs/d2d_env.py:65,68 for the whole group: num_steps += 1; done = num_steps >= EPISODE_LENGTH
+                const uint32_t eg = ep - gp + tid;
+                const int ns = min(gns[tid] + 1, 255);
+                if (FULL || P.step_count) P.step_count[eg] = (uint8_t)ns;
+                if (FULL || P.reward) P.reward[eg] = grew[tid];
+                if (FULL || P.done) P.done[eg] = ns >= P.episode_length ? 1 : 0;
+            }
         }
     };
 
-    uint32_t an[LPT];
     float2 txn[LPT], rxn[LPT];
-    if (e0 < e_end) load_inputs(e0, an, txn, rxn);
+    if (e0 < e_end) load_inputs(e0, txn, rxn);
     __syncthreads();
     // (griddepcontrol.wait comes before the first access to memory an earlier step wrote - see d2d_step_warp.cuh)
 
@@ -227,41 +245,55 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
         // ---- phase 1: inputs (the next env's loads go out first), decode, rank inside the RB, peer record --------------------
         uint32_t a[LPT];
         float2 tx[LPT], rx[LPT];
+        asm volatile("cp.async.wait_all;" ::: "memory");
 #pragma unroll
-        for (int k = 0; k < LPT; ++k) { a[k] = an[k]; tx[k] = txn[k]; rx[k] = rxn[k]; }
-        float pl[LPT];
-        uint32_t rb[LPT], pw[LPT], selfq[LPT];
-        bool live[LPT];
+        for (int k = 0; k < LPT; ++k) { a[k] = staged_action(k); tx[k] = txn[k]; rx[k] = rxn[k]; }
+        // what phase 2 needs of a link besides its positions, in ONE register (the kernel runs at its 64-register cap):
+        // rb | Tx power << 9 | slot in the bin (or bin_cap + place in the overflow list) << 16 | valid action << 31
+        float d2own[LPT];
+        uint32_t st[LPT];
+        // (griddepcontrol.wait comes before the first access to memory an earlier step wrote or read: this phase already stores
+        // the position columns of the env's observation rows, which do not depend on the step)
+        if (e == e0) d2d_pdl_wait();
 #pragma unroll
         for (int k = 0; k < LPT; ++k) {
             const uint32_t j = tid + k * BT;
             const uint32_t npw = cue[k] ? npc : npd;
-            live[k] = has[k] && a[k] < R * npw;                   // valid actions: 0 <= a < R n_pwr (envs/d2d_env.py:36-40)
-            const uint32_t as = live[k] ? a[k] : 0u;
-            rb[k] = __umulhi(as, cue[k] ? mgc : mgd) + (as & (cue[k] ? n1c : n1d));
-            pw[k] = as - rb[k] * npw;
-            pl[k] = live[k] ? pwr[pw[k]] : 0.0f;
-            selfq[k] = 0u;
-            if (live[k]) {
-                const uint32_t rank = atomicAdd(&cn[rb[k]], cue[k] ? 1u : 0x10001u) & 0xffffu;      // high half counts the SIDELINKs
-                const float4 rec = make_float4(tx[k].x, tx[k].y, pl[k] * link_cA(j, cue[k]).x, __uint_as_float(j | (pw[k] << 16)));
+            {
+                const float dxo = tx[k].x - rx[k].x, dyo = tx[k].y - rx[k].y;       // own link (a CUE's receiver is the MBS at the origin)
+                d2own[k] = fmaf(dxo, dxo, dyo * dyo);
+            }
+            if (has[k] && (FULL || P.obs)) {
+                float2 *ob = reinterpret_cast<float2 *>(reinterpret_cast<char *>(P.obs) + (uint64_t)(e * N + j) * 24u);
+                ob[0] = tx[k];                                       // an absent agent's row keeps its positions (sinr = snr = 0)
+                ob[1] = rx[k];
+            }
+            const bool lv = has[k] && a[k] < R * npw;             // valid actions: 0 <= a < R n_pwr (envs/d2d_env.py:36-40)
+            const uint32_t as = lv ? a[k] : 0u;
+            const uint32_t rbk = __umulhi(as, cue[k] ? mgc : mgd) + (as & (cue[k] ? n1c : n1d));
+            const uint32_t pwk = as - rbk * npw;
+            const float plk = lv ? pwr[pwk] : 0.0f;
+            uint32_t sq = 0u;
+            if (lv) {
+                const uint32_t rank = atomicAdd(&cn[rbk], cue[k] ? 1u : 0x10001u) & 0xffffu;      // high half counts the SIDELINKs
+                const float4 rec = make_float4(tx[k].x, tx[k].y, plk * link_cA(j, cue[k]).x, __uint_as_float(j | (pwk << 16)));
                 if (rank < CAP) {
-                    selfq[k] = rank;
-                    bp[rb[k] * CAP + rank] = rec;
+                    sq = rank;
+                    bp[rbk * CAP + rank] = rec;
                 } else {                                                                         // crowded RB: the env's overflow list
                     const uint32_t s = atomicAdd(&cn[R], 1u);
-                    selfq[k] = CAP + s;
+                    sq = CAP + s;
                     ovrec[s] = rec;
-                    ovrb[s] = (uint16_t)rb[k];
+                    ovrb[s] = (uint16_t)rbk;
                 }
             }
+            st[k] = rbk | (pwk << 9) | (sq << 16) | (lv ? 0x80000000u : 0u);
         }
         __syncthreads();
 
         // ---- deferred: env e - 1 is complete (every warp's partial sums are in), its counters can go ------------------------
-        if (e == e0) d2d_pdl_wait();
         if (e > e0) finalise(e - 1u, g == 0u ? BT - 1u : g - 1u, g == 0u);
-        if (g == 0u && (FULL || P.step_count)) ns_keep = e + tid < e_end ? (int)P.step_count[e + tid] : 0;      // consumed at the group's flush
+        if (g == 0u) gns[tid] = ((FULL || P.step_count) && e + tid < e_end) ? (int)P.step_count[e + tid] : 0;   // consumed at the group's flush
         {
             uint32_t *cprev = cnt + (c3 == 0u ? 2u : c3 - 1u) * L.cnt_words;
             for (uint32_t i = tid; i <= R; i += BT) cprev[i] = 0u;
@@ -269,7 +301,7 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
         const uint32_t ovn = cn[R];                               // block-uniform: the env spilled into the overflow list
         // the next env's inputs: in flight during this env's walk (issued here rather than before phase 1: the previous env's
         // stores, which read the registers these loads reuse, have drained by now)
-        if (e + 1u < e_end) load_inputs(e + 1u, an, txn, rxn);
+        if (e + 1u < e_end) load_inputs(e + 1u, txn, rxn);
 
         // ---- phase 2: interference walk (simulator.py:95-101), epilogue, outputs --------------------------------------------------
         float cap_part = 0.0f;
@@ -278,32 +310,57 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
 #pragma unroll
         for (int k = 0; k < LPT; ++k) {
             const uint32_t j = tid + k * BT;
+            const bool lv = (int32_t)st[k] < 0;
+            const uint32_t rbk = st[k] & 0x1ffu, pwk = (st[k] >> 9) & 0x7fu, sq = (st[k] >> 16) & 0x7fffu;
             D2DLinkOut o = {0.f, 0.f, 0.f, 0.f};
             bool need = false, side = false;
             float2 sBk = make_float2(0.f, 0.f);
-            if (live[k]) {
-                const uint32_t cw = cn[rb[k]], n = cw & 0xffffu, nb = min(n, CAP);
+            // The walk (simulator.py:95-101).  A record's 16-byte bank group is its slot modulo 8 (bins start on 128-byte boundaries),
+            // whatever the RB.  Lane l therefore visits the 8 slots of a group in the order (l & 7) ^ i: in every iteration the
+            // eight lanes of a quarter-warp - the unit LDS.128 is served in - read eight different bank groups, so the random
+            // RBs of a warp's 32 victims cost no bank conflicts (in slot order they cost 6.2 wavefronts per load where 2.6
+            // would do).  Slots 8.. are taken four at a time, and only while some lane of the warp still has records there.
+            uint32_t pb = 0u, pend = 0u, pself = 0u, n = 0u;
+            if (lv) {
+                const uint32_t cw = cn[rbk];
+                n = cw & 0xffffu;
                 side = (cw >> 16) != 0u;
-                // one induction variable - the record's shared-window address; the victim's own record is skipped by address
-                const uint32_t pb = (uint32_t)__cvta_generic_to_shared(bp + rb[k] * CAP), pend = pb + nb * 16u, pself = pb + selfq[k] * 16u;
-                float I = 0.0f, dmin2 = 3.0e38f;
-#ifndef D2D_DENSE_UNROLL
-#define D2D_DENSE_UNROLL 2
-#endif
-                constexpr int WALK_UNROLL = D2D_DENSE_UNROLL;
-#pragma unroll WALK_UNROLL
-                for (uint32_t pa = pb; pa < pend; pa += 16u) {
-                    float4 rk;
-                    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(rk.x), "=f"(rk.y), "=f"(rk.z), "=f"(rk.w) : "r"(pa));
-                    const float dx = rk.x - rx[k].x, dy = rk.y - rx[k].y;
-                    const float d2 = fmaf(dx, dx, dy * dy);
-                    const float gq = d2d_gain<PLE2>(d2, P.neg_half_ple);
-                    I = fmaf(rk.z, pa == pself ? 0.0f : gq, I);
-                    if (EXACT) dmin2 = fminf(dmin2, d2);
+                pb = (uint32_t)__cvta_generic_to_shared(bp + rbk * CAP);
+                pend = pb + min(n, CAP) * 16u; pself = pb + sq * 16u;
+            }
+            float I = 0.0f, dmin2 = 3.0e38f;
+            {
+                uint64_t nrx;                                                   // (-rx.x, -rx.y) for the packed subtract
+                asm("mov.b64 %0, {%1, %2};" : "=l"(nrx) : "f"(-rx[k].x), "f"(-rx[k].y));
+                auto term = [&](uint32_t pa) {
+                    if (pa < pend) {
+                        float4 rk;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(rk.x), "=f"(rk.y), "=f"(rk.z), "=f"(rk.w) : "r"(pa));
+                        uint64_t t, dd;
+                        float qx, qy;
+                        asm("mov.b64 %0, {%1, %2};" : "=l"(t) : "f"(rk.x), "f"(rk.y));
+                        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(dd) : "l"(t), "l"(nrx));
+                        asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(dd) : "l"(dd));
+                        asm("mov.b64 {%0, %1}, %2;" : "=f"(qx), "=f"(qy) : "l"(dd));
+                        const float d2 = qx + qy;
+                        const float gq = d2d_gain<PLE2>(d2, P.neg_half_ple);
+                        I = fmaf(rk.z, pa == pself ? 0.0f : gq, I);
+                        if (EXACT) dmin2 = fminf(dmin2, d2);
+                    }
+                };
+                const uint32_t rot8 = (lane & 7u) << 4, rot4 = (lane & 3u) << 4;
+#pragma unroll
+                for (uint32_t i = 0; i < 8u; ++i) term(pb | (rot8 ^ (i << 4)));
+                for (uint32_t base = 128u; base < CAP * 16u; base += 64u) {
+                    if (!__any_sync(0xffffffffu, pb + base < pend)) break;
+#pragma unroll
+                    for (uint32_t i = 0; i < 4u; ++i) term((pb + base) | (rot4 ^ (i << 4)));
                 }
+            }
+            if (lv) {
                 if (n > CAP) {
                     for (uint32_t q = 0; q < ovn; ++q) {
-                        if (ovrb[q] != (uint16_t)rb[k] || CAP + q == selfq[k]) continue;
+                        if (ovrb[q] != (uint16_t)rbk || CAP + q == sq) continue;
                         const float4 rk = ovrec[q];
                         const float dx = rk.x - rx[k].x, dy = rk.y - rx[k].y;
                         const float d2 = fmaf(dx, dx, dy * dy);
@@ -311,14 +368,12 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
                         dmin2 = fminf(dmin2, d2);
                     }
                 }
-                const float dxo = tx[k].x - rx[k].x, dyo = tx[k].y - rx[k].y;       // own link (a CUE's receiver is the MBS at the origin)
-                const float d2own = fmaf(dxo, dxo, dyo * dyo);
-                const float gown = d2d_gain<PLE2>(d2own, P.neg_half_ple);
+                const float gown = d2d_gain<PLE2>(d2own[k], P.neg_half_ple);
                 sBk = link_sB(j, cue[k]);
-                o = d2d_link_epilogue<PLE2>((int)pw[k], pl[k], gown, gown, I, link_cA(j, cue[k]), sBk, P);
-                need = D2D_RESCUE_ENABLED && d2d_needs_rescue<EXACT, !FULL>(o, fminf(dmin2, d2own), P);
+                o = d2d_link_epilogue<PLE2>((int)pwk, pwr[pwk] /* 10^(p/10) again: a table read costs less than a register held across the barrier */, gown, gown, I, link_cA(j, cue[k]), sBk, P);
+                need = D2D_RESCUE_ENABLED && d2d_needs_rescue<EXACT, !FULL>(o, fminf(dmin2, d2own[k]), P);
             }
-            if (live[k]) {
+            if (lv) {
                 cap_part += o.cap;
                 ++n_act;
                 if (cue[k] && side && o.cap <= P.min_cap) badbits |= 1u << k;      // envs/reward_fn.py:30-39
@@ -330,16 +385,14 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
                 const uint32_t gi = e * N + j;
                 if (FULL || P.obs) {
                     float2 *ob = reinterpret_cast<float2 *>(reinterpret_cast<char *>(P.obs) + (uint64_t)gi * 24u);
-                    ob[0] = tx[k];                                   // an absent agent's row keeps its positions (sinr = snr = 0)
-                    ob[1] = rx[k];
                     ob[2] = make_float2(o.sinr_dB, o.snr_dB);
                 }
                 if (FULL || P.cap) P.cap[gi] = o.cap;
                 if (!FULL) {
                     if (P.obs_dyn) P.obs_dyn[gi] = make_float2(o.sinr_dB, o.snr_dB);
                     if (P.rate) P.rate[gi] = o.rate;
-                    if (P.rb_out) P.rb_out[gi] = live[k] ? (int16_t)rb[k] : (int16_t)0;
-                    if (P.pwr_out) P.pwr_out[gi] = live[k] ? (int16_t)pw[k] : (int16_t)0;
+                    if (P.rb_out) P.rb_out[gi] = lv ? (int16_t)rbk : (int16_t)0;
+                    if (P.pwr_out) P.pwr_out[gi] = lv ? (int16_t)pwk : (int16_t)0;
                 }
             }
         }
@@ -357,8 +410,9 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
                     mask &= mask - 1u;
                     ++resc;
                     const uint32_t vj = (tid - lane) + (uint32_t)src + k * BT;
-                    const D2DDenseFix f = d2d_dense_rescue<PLE2, !FULL>(P, e, vj, __shfl_sync(0xffffffffu, rb[k], src), __shfl_sync(0xffffffffu, selfq[k], src),
-                                                                 __shfl_sync(0xffffffffu, pw[k], src), bp, cn, ovrec, ovrb, pwd, ovn, lane);
+                    const uint32_t vst = __shfl_sync(0xffffffffu, st[k], src);
+                    const D2DDenseFix f = d2d_dense_rescue<PLE2, !FULL>(P, e, vj, vst & 0x1ffu, (vst >> 16) & 0x7fffu, (vst >> 9) & 0x7fu, bp, cn, ovrec, ovrb, pwd, ovn, lane,
+                                                                 __shfl_sync(0xffffffffu, rx[k].x, src), __shfl_sync(0xffffffffu, rx[k].y, src));
                     if ((int)lane == src) {
                         const uint64_t gi = (uint64_t)e * N + vj;
                         if ((f.flags & 1u) && (FULL || P.obs)) P.obs[gi * 6u + 4u] = f.sinr_dB;
@@ -399,19 +453,7 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
 
     if (P.stats) {
         // block totals of the six statistics -> one fp64 atomic each
-        float v[6] = {st_reward, st_cap, st_reward2, st_n, st_pen, st_resc};
         __syncthreads();
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-#pragma unroll
-            for (int s = 16; s > 0; s >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], s);
-            if (lane == 0) red[i * D2D_DENSE_MAX_WARPS + warp] = v[i];
-        }
-        __syncthreads();
-        if (tid < 6) {
-            double t = 0.0;
-            for (uint32_t w2 = 0; w2 < NW; ++w2) t += (double)red[tid * D2D_DENSE_MAX_WARPS + w2];
-            if (t != 0.0) atomicAdd(P.stats + (blockIdx.x % D2D_STATS_REPLICAS) * 8 + tid, t);
-        }
+        if (tid < 6 && sst[tid] != 0.0) atomicAdd(P.stats + (blockIdx.x % D2D_STATS_REPLICAS) * 8 + tid, sst[tid]);
     }
 }
