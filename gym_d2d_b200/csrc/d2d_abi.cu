@@ -64,6 +64,8 @@ D2DParams make_params(const d2d_handle *h, const d2d_step_io_t *io) {
     P.us_cue = make_float2(h->us_cue[0], h->us_cue[1]);
     P.us_due = make_float2(h->us_due[0], h->us_due[1]);
     P.uniform = h->uniform ? 1 : 0;
+    P.rescue_defer = h->defer_ok ? 1 : 0;
+    P.dense_ovf = h->dDenseOvf;
     P.ud_cue = h->ud_cue; P.ud_due = h->ud_due;
     P.reward_fn = h->cfg.reward_fn;
     if (h->cfg.reward_fn != D2D_REWARD_SYSTEM_CAPACITY) {
@@ -180,6 +182,10 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
             B[j].sens_dBm != B[j0].sens_dBm || B[j].bw_MHz != B[j0].bw_MHz)
             h->uniform = false;
     }
+    h->defer_ok = true;
+    for (int j = 0; j < h->N; ++j)
+        if (std::fabs(B[j].sens_dBm) < 0.5f) h->defer_ok = false;
+    if (const char *rd = std::getenv("D2D_B200_DEFER")) h->defer_ok = h->defer_ok && std::atoi(rd) != 0;      // tests / A-B: every pass inline
     if (cfg->num_cues > 0) h->ud_cue = Dv[0];
     if (cfg->num_due_pairs > 0) h->ud_due = Dv[cfg->num_cues];
     if (cfg->num_cues > 0) { h->u_cue = A[0]; h->us_cue[0] = B[0].sens_dBm; h->us_cue[1] = B[0].bw_MHz; }
@@ -256,22 +262,26 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
                      ? (h->N + D2D_BLOCK_THREADS - 1) / D2D_BLOCK_THREADS : 0;      // downlinks: the general-topology kernel
         h->bin_cap = d2d_dense_bin_cap_host(h->N, cfg->num_rbs);
         const char *dn = std::getenv("D2D_B200_DENSE");
-        const bool dense = h->lpt > 0 && cfg->num_rbs <= 512 /* 9 bits of the packed link state */ && d2d_dense_smem(h->N, cfg->num_rbs, h->bin_cap) <= 72 * 1024 &&
-                           !(dn && std::atoi(dn) == 0);
+        // threads per block / links per thread: the shape with the fewest (warp, slot) bodies per env - every warp runs the
+        // straight-line code of each of its slots whether or not all 32 lanes hold a link (N = 600: 10 warps x 2 slots,
+        // all but one full, instead of 8 warps x 3 with the third slot three-quarters empty)
+        int bt = ((h->N + 319) / 320) * 10 < ((h->N + 255) / 256) * 8 && (h->N + 319) / 320 <= 3 ? 320 : 256;
+        if (dn && std::atoi(dn) >= 64) bt = std::atoi(dn);
+        const bool dense = h->lpt > 0 && cfg->num_rbs <= 512 /* 9 bits of the packed link state */ &&
+                           d2d_dense_smem(h->N, cfg->num_rbs, h->bin_cap, bt, h->V) <= 75 * 1024 /* three blocks per SM */ && !(dn && std::atoi(dn) == 0);
         if (dense) {
-            // threads per block / links per thread: the shape with the fewest (warp, slot) bodies per env - every warp runs the
-            // straight-line code of each of its slots whether or not all 32 lanes hold a link (N = 600: 10 warps x 2 slots,
-            // all but one full, instead of 8 warps x 3 with the third slot three-quarters empty)
-            int bt = ((h->N + 319) / 320) * 10 < ((h->N + 255) / 256) * 8 && (h->N + 319) / 320 <= 3 ? 320 : 256;
-            if (dn && std::atoi(dn) >= 64) bt = std::atoi(dn);
             h->dense_bt = bt;
             h->lpt = (h->N + bt - 1) / bt;
         }
-        const size_t smem = dense ? d2d_dense_smem(h->N, cfg->num_rbs, h->bin_cap) : d2d_block_smem(h->N, cfg->num_rbs, h->lpt);
+        const size_t smem = dense ? d2d_dense_smem(h->N, cfg->num_rbs, h->bin_cap, bt, h->V) : d2d_block_smem(h->N, cfg->num_rbs, h->lpt);
         if (smem > 227 * 1024) return bail(fail(D2D_ERR_UNSUPPORTED, "d2d_create: too many links / RBs for one SM's shared memory"));
         rc = dense ? d2d_dense_plan(h, smem) : d2d_block_plan(h, smem);
     }
     if (rc != D2D_OK) return bail(rc);
+    if (h->dense_bt) {      // the blocks' overflow lists: [grid][N] records + [grid][N] RBs
+        cudaError_t eo = cudaMalloc(&h->dDenseOvf, (size_t)h->grid * h->N * (sizeof(float4) + sizeof(uint16_t)) + 16);
+        if (eo != cudaSuccess) return bail(fail(D2D_ERR_CUDA, std::string("dense overflow scratch: ") + cudaGetErrorString(eo)));
+    }
     // CueSinrShannonRewardFunction's post-pass keeps one weak-link counter per RB and team in shared memory
     if (cfg->reward_fn == D2D_REWARD_CUE_SINR_SHANNON) {
         const size_t smem = (size_t)(h->N <= 64 ? 8 : 1) * cfg->num_rbs * sizeof(uint32_t);
@@ -306,7 +316,7 @@ D2D_API int d2d_destroy(d2d_handle_t *h) {
     if (!h) return D2D_OK;
     D2DDeviceGuard guard(h->cfg.cuda_device);
     cudaFree(h->dA); cudaFree(h->dB); cudaFree(h->dD); cudaFree(h->dMeta); cudaFree(h->dPwr); cudaFree(h->dPwrD); cudaFree(h->stage_pos);
-    cudaFree(h->dRngStep); cudaFree(h->act_scratch); cudaFree(h->dTickets);
+    cudaFree(h->dRngStep); cudaFree(h->act_scratch); cudaFree(h->dTickets); cudaFree(h->dDenseOvf);
     for (auto &s : h->slot) {
         if (s.used && s.ev_out) cudaEventSynchronize(s.ev_out);
         free_slot(s);

@@ -84,6 +84,8 @@ struct d2d_handle {
     // wrote state a step kernel reads ahead of griddepcontrol.wait)
     void *last_stream = nullptr;
     int last_kind = 0;             // D2D_LAST_*
+    void *dDenseOvf = nullptr;     // dense kernel: the blocks' overflow lists (d2d_step_dense.cuh)
+    bool defer_ok = false;         // no receiver sensitivity within 0.5 dB of 0: an fp64 pass never changes a rate / capacity (d2d_step_dense.cuh)
     // per-warp tickets (d2d_common.cuh: d2d_ticket_wait): one word per warp slot of the step geometry, and the chain bookkeeping
     uint64_t *dTickets = nullptr;
     uint64_t chain_id = 0;         // id of the current chain of single-launch steps
@@ -186,7 +188,7 @@ D2D_DECLARE_WARP_TU(4)
 D2D_DECLARE_WARP_TU(8)
 
 // dense kernel (d2d_step_dense.cuh)
-size_t d2d_dense_smem(int N, int R, int bin_cap);
+size_t d2d_dense_smem(int N, int R, int bin_cap, int bt, int V);
 int d2d_dense_bin_cap_host(int N, int R);
 int d2d_dense_plan(d2d_handle *h, size_t smem);
 cudaError_t d2d_dense_launch(const d2d_handle *h, const D2DParams &P, int grid, const D2DLaunchSel &sel, cudaStream_t st, bool pdl);

@@ -29,29 +29,27 @@
 
 #define D2D_DENSE_MAX_LPT 5
 #define D2D_DENSE_MAX_WARPS 16
-#define D2D_DENSE_MAX_BT 320u          // the largest block of D2D_DENSE_SHAPES (d2d_tu_dense.cu)
 // blocks per SM the register allocation has to allow (80 registers at 256 threads)
 #define D2D_DENSE_MINB(BT) ((BT) <= 128 ? 6 : (BT) <= 160 ? 5 : (BT) <= 192 ? 4 : 3)
 
 struct D2DDenseLayout {
-    uint32_t bins, ovrec, pwr, pwr_d, cnt, red, sst, act, grp, ovrb, total, cnt_words;
+    uint32_t bins, pwr, pwr_d, cnt, red, sst, act, grp, total, cnt_words;
 };
 
-__host__ __device__ inline D2DDenseLayout d2d_dense_layout(int N, int R, int cap) {
+__host__ __device__ inline D2DDenseLayout d2d_dense_layout(int N, int R, int cap, int bt, int V) {
     D2DDenseLayout L;
     uint32_t b = 0;
     L.pwr_d = b; b += D2D_MAX_PWR_LEVELS * 8u;                            // 10^(p/10) in fp64 (the fp64 pass)  (fixed offsets first)
     L.pwr = b;   b += D2D_MAX_PWR_LEVELS * 4u;                            // 10^(p/10)
     L.red = b;   b += 2u * 4u * D2D_DENSE_MAX_WARPS * 4u;                 // [2][4][warps]: capacity, acting agents, rescues, penalty
     L.sst = b;   b += 8u * 8u;                                            // the block's statistics (one thread adds to them per env)
-    L.act = b;   b += (((uint32_t)N + D2D_DENSE_MAX_BT - 1u) / D2D_DENSE_MAX_BT + 1u) * D2D_DENSE_MAX_BT * 4u;   // [LPT][BT] staged actions of the next env (LPT * BT < N + 2 BT)
-    L.grp = b;   b += 2u * D2D_DENSE_MAX_BT * 4u;                        // [2][BT]: reward and step counter of the envs of the current group of BT
+    L.act = b;   b += (((uint32_t)N + (uint32_t)bt - 1u) / (uint32_t)bt) * (uint32_t)bt * 4u;   // [LPT][BT] the next env's actions, staged by cp.async
+    L.grp = b;   b += 2u * (uint32_t)bt * 4u;                        // [2][BT]: reward and step counter of the envs of the current group of BT
     L.cnt_words = ((uint32_t)R + 2u + 3u) & ~3u;                          // per buffer: R counters (links | SIDELINKs << 16), overflow count
     L.cnt = b;   b += 3u * L.cnt_words * 4u;
     b = (b + 127u) & ~127u;
     L.bins = b;  b += 2u * (uint32_t)R * (uint32_t)cap * 16u;            // [2][R][cap] float4 peer records; 128-byte aligned, cap % 8 == 0
-    L.ovrec = b; b += (uint32_t)N * 16u;                                  // [N] overflow records
-    L.ovrb = b;  b += ((uint32_t)N * 2u + 15u) & ~15u;                    // [N] RB of each overflow record
+    (void)V;
     L.total = b + 112u;                                                   // the kernel rounds the dynamic window's base up to 128 bytes
     return L;
 }
@@ -106,6 +104,7 @@ __device__ __noinline__ D2DDenseFix d2d_dense_rescue(const D2DParams &P, uint32_
     for (uint32_t q = lane; q < vnb; q += 32u)
         if (q != vself) I64 += d2d_dense_term_f64<PLE2>(vbase[q], rxd, pe64, C, pwd, P);
     if (vn > CAP)
+#pragma unroll 1
         for (uint32_t q = lane; q < ovn; q += 32u)
             if (ovrb[q] == (uint16_t)vrb && CAP + q != vself) I64 += d2d_dense_term_f64<PLE2>(ovrec[q], rxd, pe64, C, pwd, P);
 #pragma unroll
@@ -138,21 +137,23 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
     const uint32_t N = (uint32_t)P.N, C = (uint32_t)P.C, V = (uint32_t)P.V, R = (uint32_t)P.R, CAP = (uint32_t)P.bin_cap;
     const uint32_t npc = (uint32_t)P.n_pwr_cue, npd = (uint32_t)P.n_pwr_due;
     const uint32_t mgc = P.magic_cue, mgd = P.magic_due, n1c = P.npw1_cue, n1d = P.npw1_due;
-    const D2DDenseLayout L = d2d_dense_layout((int)N, (int)R, (int)CAP);
+    const D2DDenseLayout L = d2d_dense_layout((int)N, (int)R, (int)CAP, BT, (int)V);
     // the bins sit on 128-byte boundaries of the shared window (see the walk): round the dynamic region's base up
     unsigned char *const sm = d2d_dense_smem + ((0u - (uint32_t)__cvta_generic_to_shared(d2d_dense_smem)) & 127u);
     float4 *bins = reinterpret_cast<float4 *>(sm + L.bins);
-    float4 *ovrec = reinterpret_cast<float4 *>(sm + L.ovrec);
+    // the overflow list of a crowded RB's links lives in a handle-owned global scratch (N records per block; L2-resident and
+    // touched by 2-3 % of the envs): in shared memory it cost 11 KB
+    float4 *ovrec = reinterpret_cast<float4 *>(P.dense_ovf) + (uint64_t)blockIdx.x * N;
+    uint16_t *ovrb = reinterpret_cast<uint16_t *>(reinterpret_cast<float4 *>(P.dense_ovf) + (uint64_t)gridDim.x * N) + (uint64_t)blockIdx.x * N;
     float *pwr = reinterpret_cast<float *>(sm + L.pwr);
     double *pwd = reinterpret_cast<double *>(sm + L.pwr_d);
     uint32_t *cnt = reinterpret_cast<uint32_t *>(sm + L.cnt);
     float *red = reinterpret_cast<float *>(sm + L.red);
-    uint16_t *ovrb = reinterpret_cast<uint16_t *>(sm + L.ovrb);
     // block-level scalars in shared memory rather than in registers that would live across the whole env loop (and spill):
     // the statistics of the envs this block stepped, and the reward / step counter of every env of the current group
     double *sst = reinterpret_cast<double *>(sm + L.sst);
     float *grew = reinterpret_cast<float *>(sm + L.grp);
-    int32_t *gns = reinterpret_cast<int32_t *>(sm + L.grp) + D2D_DENSE_MAX_BT;
+    int32_t *gns = reinterpret_cast<int32_t *>(sm + L.grp) + BT;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t act_sa = (uint32_t)__cvta_generic_to_shared(sm + L.act) + tid * 4u;      // this thread's staged actions: [k][tid]
     d2d_pdl_entry(P.flags);
@@ -359,6 +360,7 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
             }
             if (lv) {
                 if (n > CAP) {
+#pragma unroll 1
                     for (uint32_t q = 0; q < ovn; ++q) {
                         if (ovrb[q] != (uint16_t)rbk || CAP + q == sq) continue;
                         const float4 rk = ovrec[q];

@@ -5,7 +5,7 @@
 // (links per thread, threads per block) instantiations
 #define D2D_DENSE_SHAPES(X) X(1, 256) X(2, 256) X(3, 256) X(4, 256) X(1, 320) X(2, 320) X(3, 320)
 
-size_t d2d_dense_smem(int N, int R, int bin_cap) { return d2d_dense_layout(N, R, bin_cap).total; }
+size_t d2d_dense_smem(int N, int R, int bin_cap, int bt, int V) { return d2d_dense_layout(N, R, bin_cap, bt, V).total; }
 int d2d_dense_bin_cap_host(int N, int R) { return d2d_dense_bin_cap(N, R); }
 
 namespace {
