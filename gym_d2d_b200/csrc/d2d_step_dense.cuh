@@ -33,7 +33,7 @@
 #define D2D_DENSE_MINB(BT) ((BT) <= 128 ? 6 : (BT) <= 160 ? 5 : (BT) <= 192 ? 4 : 3)
 
 struct D2DDenseLayout {
-    uint32_t bins, pwr, pwr_d, cnt, red, sst, act, grp, total, cnt_words;
+    uint32_t bins, pwr, pwr_d, cnt, red, sst, mbar, sact, spos, grp, total, cnt_words;
 };
 
 __host__ __device__ inline D2DDenseLayout d2d_dense_layout(int N, int R, int cap, int bt, int V) {
@@ -43,13 +43,14 @@ __host__ __device__ inline D2DDenseLayout d2d_dense_layout(int N, int R, int cap
     L.pwr = b;   b += D2D_MAX_PWR_LEVELS * 4u;                            // 10^(p/10)
     L.red = b;   b += 2u * 4u * D2D_DENSE_MAX_WARPS * 4u;                 // [2][4][warps]: capacity, acting agents, rescues, penalty
     L.sst = b;   b += 8u * 8u;                                            // the block's statistics (one thread adds to them per env)
-    L.act = b;   b += (((uint32_t)N + (uint32_t)bt - 1u) / (uint32_t)bt) * (uint32_t)bt * 4u;   // [LPT][BT] the next env's actions, staged by cp.async
+    L.mbar = b;  b += 16u;                                                // the staging buffer's mbarrier
+    L.sact = b;  b += (((uint32_t)N * 4u + 15u) & ~15u) + 16u;            // the next env's actions: its 16-byte aligned window of the global array
+    L.spos = b;  b += (((uint32_t)V * 8u + 15u) & ~15u) + 16u;            // and its V positions
     L.grp = b;   b += 2u * (uint32_t)bt * 4u;                        // [2][BT]: reward and step counter of the envs of the current group of BT
     L.cnt_words = ((uint32_t)R + 2u + 3u) & ~3u;                          // per buffer: R counters (links | SIDELINKs << 16), overflow count
     L.cnt = b;   b += 3u * L.cnt_words * 4u;
     b = (b + 127u) & ~127u;
     L.bins = b;  b += 2u * (uint32_t)R * (uint32_t)cap * 16u;            // [2][R][cap] float4 peer records; 128-byte aligned, cap % 8 == 0
-    (void)V;
     L.total = b + 112u;                                                   // the kernel rounds the dynamic window's base up to 128 bytes
     return L;
 }
@@ -155,7 +156,8 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
     float *grew = reinterpret_cast<float *>(sm + L.grp);
     int32_t *gns = reinterpret_cast<int32_t *>(sm + L.grp) + BT;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint32_t act_sa = (uint32_t)__cvta_generic_to_shared(sm + L.act) + tid * 4u;      // this thread's staged actions: [k][tid]
+    const uint32_t sact_sa = (uint32_t)__cvta_generic_to_shared(sm + L.sact), spos_sa = (uint32_t)__cvta_generic_to_shared(sm + L.spos);
+    const uint32_t mbar_sa = (uint32_t)__cvta_generic_to_shared(sm + L.mbar);
     d2d_pdl_entry(P.flags);
 
     for (uint32_t i = tid; i < D2D_MAX_PWR_LEVELS; i += BT) { pwr[i] = P.pwr_lin[i]; pwd[i] = P.pwr_lin_d[i]; }
@@ -175,28 +177,47 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
     auto link_sB = [&](uint32_t j, bool is_cue) -> float2 {
         return (FULL || P.uniform) ? (is_cue ? P.us_cue : P.us_due) : __ldg(reinterpret_cast<const float2 *>(P.linkB + j));
     };
-    // one coalesced pass over an env's inputs: action, transmitter and (DUE) receiver position of each of this thread's links.
-    // Branch-free: a thread without a link in slot k re-reads the env's last link and never uses the values (a conditional load
-    // made the compiler keep the prefetched actions in local memory - and wait for each load right behind its issue).
-    auto load_inputs = [&](uint32_t e, float2 (&tx)[LPT], float2 (&rx)[LPT]) {
-        const int32_t *act = P.actions + e * N;
-        const float2 *pe = reinterpret_cast<const float2 *>(P.pos) + e * V;
-#pragma unroll
-        for (int k = 0; k < LPT; ++k) {
-            const uint32_t j = min(tid + k * BT, N - 1u);
-            const uint32_t txd = cue[k] ? 1u + j : 1u + C + 2u * (j - C);
-            // the action goes to this thread's own staging word without passing through a register (cp.async; read back by the
-            // same thread after cp.async.wait_all): held in a register over the walk it was the value the compiler spilled -
-            // with the spill store waiting for the load right behind its issue
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(act_sa + (uint32_t)k * BT * 4u), "l"(act + j) : "memory");
-            tx[k] = __ldg(pe + txd);                              // (has[k] is applied where the values are used)
-            rx[k] = __ldg(pe + (cue[k] ? 0u : txd + 1u));         // a CUE's receiver: the MBS (device 0)
+    // The next env's inputs - N actions, V positions: two contiguous rows of the global arrays - are STAGED in shared memory one
+    // env ahead by the bulk-copy engine: thread 0 issues one cp.async.bulk per row for the row's 16-byte aligned interior and
+    // 4-byte cp.asyncs for the (at most three) words on either side of it, and every thread waits for both on an mbarrier at the
+    // top of phase 1.  Nothing is prefetched into registers: held there across the walk the values were what the compiler spilled at
+    // the kernel's 64-register cap - with the spill store waiting for the load right behind its issue (20 % of all stall
+    // samples) - and 60 LDG with their 64-bit address arithmetic per env are gone.  A row keeps its alignment modulo 16 in the
+    // staging buffer (element i of the row at buffer + (row address & 15) + i * size).
+    auto stage_row = [&](const char *row, uint32_t bytes, uint32_t dst_sa) -> uint32_t {      // thread 0; returns the bulk copy's bytes
+        const uint64_t a0 = (uint64_t)row, a1 = a0 + bytes;
+        const uint64_t w0 = (a0 + 15ull) & ~15ull, w1 = a1 & ~15ull;
+        const uint32_t d0 = dst_sa + ((uint32_t)a0 & 15u);
+        for (uint64_t x = a0; x < (w0 < a1 ? w0 : a1); x += 4ull)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + (uint32_t)(x - a0)), "l"(x) : "memory");
+        for (uint64_t x = (w1 > w0 ? w1 : w0); x < a1; x += 4ull)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d0 + (uint32_t)(x - a0)), "l"(x) : "memory");
+        return w1 > w0 ? (uint32_t)(w1 - w0) : 0u;
+    };
+    auto stage_inputs = [&](uint32_t e) {
+        if (tid == 0u) {
+            const char *arow = reinterpret_cast<const char *>(P.actions + (uint64_t)e * N), *prow = reinterpret_cast<const char *>(P.pos) + (uint64_t)e * V * 8ull;
+            const uint32_t ba = stage_row(arow, N * 4u, sact_sa), bpz = stage_row(prow, V * 8u, spos_sa);
+            // two arrivals complete a phase: this thread's word copies (cp.async; fires at once when there were none) and the
+            // expect_tx one, which the bulk copies' bytes then complete
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(mbar_sa) : "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar_sa), "r"(ba + bpz) : "memory");
+            if (ba) {
+                const uint64_t w0 = ((uint64_t)arow + 15ull) & ~15ull;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(sact_sa + ((uint32_t)(uint64_t)arow & 15u) + (uint32_t)(w0 - (uint64_t)arow)), "l"(w0), "r"(ba), "r"(mbar_sa) : "memory");
+            }
+            if (bpz) {
+                const uint64_t w0 = ((uint64_t)prow + 15ull) & ~15ull;
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(spos_sa + ((uint32_t)(uint64_t)prow & 15u) + (uint32_t)(w0 - (uint64_t)prow)), "l"(w0), "r"(bpz), "r"(mbar_sa) : "memory");
+            }
         }
     };
-    auto staged_action = [&](int k) -> uint32_t {
-        uint32_t v;
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(act_sa + (uint32_t)k * BT * 4u) : "memory");
-        return v;
+    auto staged_wait = [&](uint32_t parity) {
+        uint32_t done = 0u;
+        while (!done)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(mbar_sa), "r"(parity) : "memory");
     };
     const uint32_t num_envs = (uint32_t)P.num_envs;
     const uint32_t per_block = (num_envs + gridDim.x - 1u) / gridDim.x;
@@ -233,8 +254,12 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
         }
     };
 
-    float2 txn[LPT], rxn[LPT];
-    if (e0 < e_end) load_inputs(e0, txn, rxn);
+    if (tid == 0u) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 2;" ::"r"(mbar_sa) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (e0 < e_end) stage_inputs(e0);
     __syncthreads();
     // (griddepcontrol.wait comes before the first access to memory an earlier step wrote - see d2d_step_warp.cuh)
 
@@ -246,9 +271,19 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
         // ---- phase 1: inputs (the next env's loads go out first), decode, rank inside the RB, peer record --------------------
         uint32_t a[LPT];
         float2 tx[LPT], rx[LPT];
-        asm volatile("cp.async.wait_all;" ::: "memory");
+        staged_wait((e - e0) & 1u);
+        {
+            const uint32_t sa = sact_sa + ((uint32_t)(uint64_t)(P.actions + (uint64_t)e * N) & 15u);
+            const uint32_t sp = spos_sa + ((uint32_t)((uint64_t)P.pos + (uint64_t)e * V * 8ull) & 15u);
 #pragma unroll
-        for (int k = 0; k < LPT; ++k) { a[k] = staged_action(k); tx[k] = txn[k]; rx[k] = rxn[k]; }
+            for (int k = 0; k < LPT; ++k) {
+                const uint32_t j = min(tid + k * BT, N - 1u);         // (a thread without a link in slot k re-reads the last link and never uses it)
+                const uint32_t txd = cue[k] ? 1u + j : 1u + C + 2u * (j - C);
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(a[k]) : "r"(sa + j * 4u) : "memory");
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(tx[k].x), "=f"(tx[k].y) : "r"(sp + txd * 8u) : "memory");
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(rx[k].x), "=f"(rx[k].y) : "r"(sp + (cue[k] ? 0u : txd + 1u) * 8u) : "memory");      // a CUE's receiver: the MBS (device 0)
+            }
+        }
         // what phase 2 needs of a link besides its positions, in ONE register (the kernel runs at its 64-register cap):
         // rb | Tx power << 9 | slot in the bin (or bin_cap + place in the overflow list) << 16 | valid action << 31
         float d2own[LPT];
@@ -302,7 +337,7 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
         const uint32_t ovn = cn[R];                               // block-uniform: the env spilled into the overflow list
         // the next env's inputs: in flight during this env's walk (issued here rather than before phase 1: the previous env's
         // stores, which read the registers these loads reuse, have drained by now)
-        if (e + 1u < e_end) load_inputs(e + 1u, txn, rxn);
+        if (e + 1u < e_end) stage_inputs(e + 1u);
 
         // ---- phase 2: interference walk (simulator.py:95-101), epilogue, outputs --------------------------------------------------
         float cap_part = 0.0f;
