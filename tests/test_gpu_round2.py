@@ -611,3 +611,36 @@ def test_large_batch_fused_launches_use_their_own_shape_and_agree():
         assert torch.equal(ro[k], many[k]), k
     assert fused.stats()['ticket_timeouts'] == 0 and single.stats()['ticket_timeouts'] == 0
     fused.close(); single.close()
+
+
+# ---- dense kernel: bulk-copy staging of rows that do not start on 16-byte boundaries -------------------------------------------------------
+@pytest.mark.parametrize('kw', [dict(num_rbs=5, num_cues=41, num_due_pairs=60),      # N = 101: action rows rotate through all four alignments, V = 162
+                                dict(num_rbs=5, num_cues=40, num_due_pairs=61)])     # N = 101, V = 163: position rows alternate between 0 and 8
+def test_dense_staging_of_unaligned_rows(monkeypatch, kw):
+    """d2d_step_dense_kernel stages each env's action and position rows with one cp.async.bulk per row for the 16-byte aligned
+    interior plus 4-byte cp.asyncs for the words on either side.  Rows of 101 actions / 163 positions start at every possible
+    alignment; the action tensor is additionally a view that starts 4 bytes into its allocation and ends exactly at its end
+    (nothing beyond the last row may be read: run under compute-sanitizer this is the out-of-bounds check).  Two blocks step
+    all envs, so consecutive rows alternate inside one block."""
+    from tests._util import RTOL, assert_rel
+    monkeypatch.setenv('D2D_B200_GRID', '2')
+    cfg = O.OracleConfig(**kw)
+    E = 37
+    rng = np.random.default_rng(2718)
+    pos, act = O.random_positions(cfg, E, rng, fp32_exact=True), O.random_actions(cfg, E, rng)
+    env = make_vec(E, kw)
+    assert env.step_geometry()['block'] in (256, 320) and env.step_geometry()['smem_bytes'] > 20000      # the dense kernel
+    env.set_positions(pos)
+    flat = torch.empty(E * cfg.num_links + 1, dtype=torch.int32, device='cuda')
+    a = flat[1:].view(E, cfg.num_links)
+    a.copy_(torch.as_tensor(act, dtype=torch.int32))
+    assert a.data_ptr() % 16 == 4 and a.is_contiguous()
+    obs, reward, done, info = env.step(a)
+    torch.cuda.synchronize()
+    ref = O.step_batch(cfg, pos, act, nthreads=4)
+    assert_rel(obs[..., 4].cpu().numpy(), ref['sinr_db'], RTOL, 'sinr_db')
+    assert_rel(obs[..., 5].cpu().numpy(), ref['snr_db'], RTOL, 'snr_db')
+    assert_rel(info['capacity_mbps'].cpu().numpy(), ref['capacity_mbps'], RTOL, 'capacity')
+    assert_rel(reward.cpu().numpy(), ref['reward'], RTOL, 'reward')
+    np.testing.assert_array_equal(obs[..., :2].cpu().numpy().reshape(E, -1)[:, :2 * cfg.num_cues], pos[:, 1:1 + cfg.num_cues].astype(np.float32).reshape(E, -1))
+    env.close()
