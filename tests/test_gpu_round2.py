@@ -645,3 +645,4 @@ def test_dense_staging_of_unaligned_rows(monkeypatch, kw):
     np.testing.assert_array_equal(obs[..., :2].cpu().numpy().reshape(E, -1)[:, :2 * cfg.num_cues], pos[:, 1:1 + cfg.num_cues].astype(np.float32).reshape(E, -1))
     env.close()
 
+
