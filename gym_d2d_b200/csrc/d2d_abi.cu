@@ -64,7 +64,6 @@ D2DParams make_params(const d2d_handle *h, const d2d_step_io_t *io) {
     P.us_cue = make_float2(h->us_cue[0], h->us_cue[1]);
     P.us_due = make_float2(h->us_due[0], h->us_due[1]);
     P.uniform = h->uniform ? 1 : 0;
-    P.rescue_defer = h->defer_ok ? 1 : 0;
     P.dense_ovf = h->dDenseOvf;
     P.ud_cue = h->ud_cue; P.ud_due = h->ud_due;
     P.reward_fn = h->cfg.reward_fn;
@@ -182,10 +181,6 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
             B[j].sens_dBm != B[j0].sens_dBm || B[j].bw_MHz != B[j0].bw_MHz)
             h->uniform = false;
     }
-    h->defer_ok = true;
-    for (int j = 0; j < h->N; ++j)
-        if (std::fabs(B[j].sens_dBm) < 0.5f) h->defer_ok = false;
-    if (const char *rd = std::getenv("D2D_B200_DEFER")) h->defer_ok = h->defer_ok && std::atoi(rd) != 0;      // tests / A-B: every pass inline
     if (cfg->num_cues > 0) h->ud_cue = Dv[0];
     if (cfg->num_due_pairs > 0) h->ud_due = Dv[cfg->num_cues];
     if (cfg->num_cues > 0) { h->u_cue = A[0]; h->us_cue[0] = B[0].sens_dBm; h->us_cue[1] = B[0].bw_MHz; }

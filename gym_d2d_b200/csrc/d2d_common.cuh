@@ -58,8 +58,6 @@ struct D2DParams {
     int32_t reward_fn;           // d2d_reward_fn: per-agent reward functions take their reward statistics from the post-pass kernel
     int32_t uniform;             // every CUE link shares one set of constants, and every DUE link (u_cue / u_due below)
     void *dense_ovf;             // dense kernel: [grid][N] float4 overflow records, then [grid][N] u16 RBs (handle-owned scratch)
-    int32_t rescue_defer;        // dense kernel: an fp64 pass can only change the two dB values (no fp64 position shadow, no receiver
-                                 // sensitivity within 0.5 dB of 0, where the rate / capacity gate could flip), so it may be queued
     int32_t T;                   // d2d_step_many: steps per env in this launch (1 for d2d_step)
     uint32_t envs_per_warp;      // warp kernel: ceil(num_envs / (grid * warps per block)), divided on the host (a 20-instruction
                                  // sequence ahead of every warp's first load otherwise)

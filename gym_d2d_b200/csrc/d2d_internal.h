@@ -85,7 +85,6 @@ struct d2d_handle {
     void *last_stream = nullptr;
     int last_kind = 0;             // D2D_LAST_*
     void *dDenseOvf = nullptr;     // dense kernel: the blocks' overflow lists (d2d_step_dense.cuh)
-    bool defer_ok = false;         // no receiver sensitivity within 0.5 dB of 0: an fp64 pass never changes a rate / capacity (d2d_step_dense.cuh)
     // per-warp tickets (d2d_common.cuh: d2d_ticket_wait): one word per warp slot of the step geometry, and the chain bookkeeping
     uint64_t *dTickets = nullptr;
     uint64_t chain_id = 0;         // id of the current chain of single-launch steps
