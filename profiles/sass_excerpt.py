@@ -4,7 +4,8 @@ For the instantiation each bench leg launches it lists the static instruction mi
 on the SFU pipe), shared-memory atomics and 128-bit shared loads / stores (the binned per-RB tables), global loads / stores, fp64
 (the rare recomputation pass), local-memory spills - the programmatic-dependent-launch instructions (PREEXIT =
 griddepcontrol.launch_dependents, ACQBULK = griddepcontrol.wait) with the instructions around them, and confirms what is NOT there:
-no tensor-core (HMMA / UTCMMA / UTMA) or cp.async (LDGSTS) instructions - north_star says so, DESIGN.md explains why.
+no tensor-core instructions (HMMA / UTCMMA) - north_star says so, DESIGN.md explains why; the bulk-copy engine (UBLKCP, tracked by
+SYNCS mbarrier instructions) and cp.async (LDGSTS) appear in the dense kernel only, which stages each env's input rows with them.
 """
 import collections
 import re
@@ -28,7 +29,10 @@ GROUPS = collections.OrderedDict([
     ('SHFL / VOTE / REDUX / MATCH', r'^(SHFL|VOTE|REDUX|MATCH)'), ('fp64 (DFMA / DADD / DMUL)', r'^(DFMA|DADD|DMUL)'),
     ('IMAD (incl. Philox)', r'^IMAD'), ('BAR / barrier', r'^(BAR|WARPSYNC)'), ('STL / LDL (spills)', r'^(STL|LDL)'),
     ('PREEXIT (griddepcontrol.launch_dependents)', r'^PREEXIT'), ('ACQBULK (griddepcontrol.wait)', r'^ACQBULK'),
-    ('tensor core / TMA / cp.async (HMMA, UTCMMA, UTMA*, LDGSTS)', r'^(HMMA|UTC|UTMA|LDGSTS|UBLKCP)'),
+    ('tensor core (HMMA, UTCMMA)', r'^(HMMA|UTC)'),
+    ('bulk copy / TMA (UBLKCP, UTMA*)', r'^(UTMA|UBLKCP)'),
+    ('cp.async (LDGSTS)', r'^LDGSTS'),
+    ('mbarrier (SYNCS.*)', r'^SYNCS'),
 ])
 
 
