@@ -290,7 +290,8 @@ def timed_steps(env, torch, actions, outs, steps, warmup, dist, use_graph=True):
         dist.barrier()
     how = (f'{steps // G} replay(s) of a CUDA graph of {G} step kernels' + (f' + {steps - done} eager launches' if steps - done else '')
            if graph is not None else f'{steps} eager launches')
-    return secs, (t0, t1), launches, how + '; pre-generated actions (D2D_STEP_INPUTS_STABLE)'
+    return secs, (t0, t1), launches, how + ('; pre-generated actions (D2D_STEP_INPUTS_STABLE); consecutive steps write different output sets of the ring, '
+                                            'so their per-link outputs are stored ahead of griddepcontrol.wait (late wait)')
 
 
 def host_link_peak(torch, device, nbytes_in, nbytes_out, dist, iters=30):

@@ -225,6 +225,7 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
     if (const char *c = std::getenv("D2D_B200_CHUNK")) h->chunk_override = std::atoll(c);
     if (const char *c = std::getenv("D2D_B200_TICKET")) h->tickets_on = std::atoi(c) != 0;
     if (const char *c = std::getenv("D2D_B200_TICKET_MIN")) h->ticket_min_quarters = std::max(1, std::atoi(c));
+    if (const char *c = std::getenv("D2D_B200_LATE_WAIT")) h->late_wait_on = std::atoi(c) != 0;      // tests / A-B
     const char *pdl = std::getenv("D2D_B200_PDL");
     h->pdl = !(pdl && std::strcmp(pdl, "0") == 0);
     int rc;
@@ -503,10 +504,35 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, int mode, void *s
     else if (!reads_positions) stable = stable && (io->flags & D2D_STEP_INPUTS_STABLE) && h->last_kind != D2D_LAST_OTHER;
     else stable = stable && (io->flags & D2D_STEP_INPUTS_STABLE) && h->last_kind == D2D_LAST_STEP;
     P.flags = (stable ? 0u : D2D_PF_INPUTS_FRESH) | (draw_actions ? D2D_PF_DRAW_ACTIONS : 0u) | (ea.no_reset ? D2D_PF_NO_RESET : 0u);
+    // Late wait (d2d_step_warp.cuh): a flagged single-launch d2d_step right behind another one of this handle, whose per-link output
+    // buffers alias none of the previous step's, stores them ahead of griddepcontrol.wait - nothing the predecessor does can
+    // collide with them, and whatever was enqueued before the predecessor is complete (a kernel that is not a step kernel never
+    // lets its successor start early).  The step counters and per-env scalars stay behind the wait.  Not when a post-pass kernel
+    // follows the step kernel.
+    // (measured, profiles/ab_r02_25 .. 28.log: a win at every batch size - E = 1 024: 2.55 -> 1.94 us, 4 096: 5.42 -> 4.94 us,
+    // 4 608: 7.76 -> 4.75 us, and level with or ahead of the per-warp tickets beyond one wave (E = 32 768: 17.8 -> 17.3 us) - except
+    // where two launches of 2-warp blocks fill the SM's warp slots exactly: E = 2 048 3.46 -> 4.22 us)
+    bool late = false;
+    {
+        const size_t EN = (size_t)h->cfg.num_envs * h->N;
+        const uintptr_t cur[6][2] = {{(uintptr_t)io->obs, EN * 24}, {(uintptr_t)io->obs_dyn, EN * 8}, {(uintptr_t)io->capacity_mbps, EN * 4},
+                                     {(uintptr_t)io->rate_bps, EN * 4}, {(uintptr_t)io->rb, EN * 2}, {(uintptr_t)io->tx_pwr_dBm, EN * 2}};
+        const bool plain = h->use_warp && mode == MODE_STEP && h->cfg.reward_fn == D2D_REWARD_SYSTEM_CAPACITY && !io->agent_reward && !h->dRngStep &&
+                           h->cfg.num_envs <= std::max<int64_t>(1, (int64_t)0x7fffffff / std::max(6 * h->N, 2 * h->V)) &&
+                           !(h->chunk_override > 0 && h->chunk_override < h->cfg.num_envs);
+        late = plain && stable && h->late_wait_on && h->prev_out_valid && h->last_kind == D2D_LAST_STEP && !(h->wpb == 2 && h->cfg.num_envs > 1792);
+        for (int a = 0; late && a < 6; ++a)
+            for (int b = 0; b < 6; ++b)
+                if (cur[a][0] && h->prev_out[b][0] && cur[a][0] < h->prev_out[b][1] && h->prev_out[b][0] < cur[a][0] + cur[a][1]) late = false;
+        if (late) P.flags |= D2D_PF_LATE_WAIT;
+        h->prev_out_valid = plain;
+        for (int a = 0; a < 6; ++a) { h->prev_out[a][0] = cur[a][0]; h->prev_out[a][1] = cur[a][0] ? cur[a][0] + cur[a][1] : 0; }
+    }
     // Per-warp tickets (d2d_common.cuh): a single-launch d2d_step publishes a token per warp; the next one - same stream, same
     // geometry, inputs declared stable - waits per warp for that token instead of for the whole grid.
-    // (not when a post-pass kernel follows the step kernel: the next step's predecessor in the stream is then that kernel)
-    const bool single_launch = h->use_warp && mode == MODE_STEP && h->dTickets && h->pdl && h->tickets_on &&
+    // (not when a post-pass kernel follows the step kernel: the next step's predecessor in the stream is then that kernel; and only
+    // for steps that write buffers their predecessor wrote - the late wait above serves the others)
+    const bool single_launch = !late && h->use_warp && mode == MODE_STEP && h->dTickets && h->pdl && h->tickets_on &&
                                h->cfg.reward_fn == D2D_REWARD_SYSTEM_CAPACITY && !io->agent_reward && !h->dRngStep &&
                                h->cfg.num_envs <= std::max<int64_t>(1, (int64_t)0x7fffffff / std::max(6 * h->N, 2 * h->V)) &&
                                !(h->chunk_override > 0 && h->chunk_override < h->cfg.num_envs);

@@ -168,6 +168,8 @@ __device__ __forceinline__ float d2d_rcp(float x) {
 //       the inputs before that point is complete and visible.
 #define D2D_PF_INPUTS_FRESH 1u
 #define D2D_PF_DRAW_ACTIONS 2u     // d2d_episode / d2d_rollout: actions drawn on the device instead of read from P.actions
+#define D2D_PF_LATE_WAIT 8u        // d2d_step after a d2d_step whose output buffers this one does not touch: the per-link outputs are stored
+                                   // AHEAD of griddepcontrol.wait; only the step counters and the per-env scalars come after it (d2d_abi.cu)
 #define D2D_PF_NO_RESET 4u         // d2d_rollout: the EPISODE instantiation continues from the bound state (no position draw, every slice counted)
 __device__ __forceinline__ void d2d_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void d2d_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

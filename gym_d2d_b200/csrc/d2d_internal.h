@@ -84,6 +84,11 @@ struct d2d_handle {
     // wrote state a step kernel reads ahead of griddepcontrol.wait)
     void *last_stream = nullptr;
     int last_kind = 0;             // D2D_LAST_*
+    // the per-link output buffers of the last single-launch d2d_step ([begin, end) byte ranges; obs, obs_dyn, capacity, rate, rb,
+    // Tx power): a d2d_step right behind it that touches none of them stores its own ahead of griddepcontrol.wait (D2D_PF_LATE_WAIT)
+    uintptr_t prev_out[6][2] = {};
+    bool prev_out_valid = false;
+    bool late_wait_on = true;      // D2D_B200_LATE_WAIT=0 switches the late wait off (tests, A/B)
     void *dDenseOvf = nullptr;     // dense kernel: the blocks' overflow lists (d2d_step_dense.cuh)
     // per-warp tickets (d2d_common.cuh: d2d_ticket_wait): one word per warp slot of the step geometry, and the chain bookkeeping
     uint64_t *dTickets = nullptr;

@@ -721,7 +721,12 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
 #ifdef D2D_TIMELINE
         if (e == e0 && t == 0u) tl_c1 = d2d_tl_clock();
 #endif
-        if (e == e0 && t == 0u) {
+        // LATE: the host found that this launch's per-link outputs (observation table, capacities, info) alias nothing its predecessor
+        // - another d2d_step of this handle - writes: they go out right away, and the wait moves in front of the only accesses that
+        // do depend on the predecessor, the step counters and the per-env scalars of the warp's first group (see below).  At one wave
+        // of envs every warp's stores used to queue up behind the grid-wide release.
+        const bool LATE = !MANY && (P.flags & D2D_PF_LATE_WAIT) != 0u;
+        if (e == e0 && t == 0u && !LATE) {
             if (!MANY && P.tok_wait != 0ull) {
                 if (lane == 0u && !d2d_ticket_wait(P.tickets + (blockIdx.x * WPB + warp), P.tok_wait) && P.stats)
                     atomicAdd(P.stats + 6, 1.0);                           // D2D_STAT_TICKET_TIMEOUTS
@@ -736,7 +741,7 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
 #ifdef D2D_EXPERIMENT_NOCOUNT     // A/B only: how much of the post-wait tail is the step-counter load
         ns_keep = 0;
 #else
-        if (!ep_reset && g == 0u && t == 0u && (FULL || P.step_count)) ns_keep = e + lane < e_end ? (int)P.step_count[e + lane] : 0;   // consumed at the group's end
+        if (!LATE && !ep_reset && g == 0u && t == 0u && (FULL || P.step_count)) ns_keep = e + lane < e_end ? (int)P.step_count[e + lane] : 0;   // consumed at the group's end
 #endif
         // ---- outputs: compact observation table (envs/obs_fn.py:55-61), capacity, optional info.  Rows of absent
         // agents carry their positions and zeros (the reference has no row for them). ---------------------------------
@@ -810,6 +815,10 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
             rew_keep = lane == g ? reward : rew_keep;
         }
         if (last_t && (g == 31u || e + 1u == e_end)) {
+            if (LATE) {
+                if (e - g == e0) d2d_pdl_wait();                       // (the warp's first group: once per warp)
+                ns_keep = ((FULL || P.step_count) && lane <= g) ? (int)P.step_count[e - g + lane] : 0;
+            }
             // envs/d2d_env.py:65,68 for the whole group: num_steps += 1; done = num_steps >= EPISODE_LENGTH
             if (lane <= g) {
                 const uint32_t eg = e - g + lane;

@@ -37,7 +37,12 @@
  * consecutive flagged single-launch steps of the same geometry do not wait for each other as whole grids -
  * each warp waits only for the warp that stepped the same environments one launch earlier (a per-warp
  * release / acquire ticket; gym_d2d_b200/csrc/d2d_common.cuh), which is what removes the grid-wide
- * completion-and-release latency from a chain of small steps.
+ * completion-and-release latency from a chain of small steps.  And when the per-link output buffers of a flagged
+ * step (obs, obs_dyn, capacity_mbps, rate_bps, rb, tx_pwr_dBm) overlap none of the previous step's - the library
+ * compares the pointers itself - the kernel stores them BEFORE it waits: its predecessor cannot touch them, and
+ * anything enqueued ahead of the predecessor is complete.  Only the step counters and the per-env scalars (reward,
+ * done) are written after the wait.  A caller that rotates two or more output sets gets this without asking; nothing
+ * changes for one that reuses a single set.
  *
  * Index conventions (devices.py:20-25, simulator.py:34-48, envs/d2d_env.py:55-60):
  *   C = num_cues, D = num_due_pairs, N = C + D links, V = 1 + C + 2D devices.

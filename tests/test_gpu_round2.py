@@ -646,3 +646,65 @@ def test_dense_staging_of_unaligned_rows(monkeypatch, kw):
     env.close()
 
 
+
+
+# ---- late wait: a flagged step whose output buffers its predecessor does not touch stores them ahead of griddepcontrol.wait -----------------
+@pytest.mark.parametrize('E,grid', [(4096, None), (1000, None), (148, None), (3000, '7')])
+def test_late_wait_bit_identical_to_serialised_launches(monkeypatch, E, grid):
+    """d2d_step right behind a d2d_step of the same handle, D2D_STEP_INPUTS_STABLE, output buffers disjoint from the predecessor's:
+    the per-link outputs go out before the wait, the step counters / reward / done after it (D2D_PF_LATE_WAIT).  Graph replays and
+    eager chains over a ring of four output sets - also with the SAME set twice in a row, where the library must fall back to the
+    early wait - broken by resets; every buffer of the ring, the counters and the done flags bit-identical to a library without
+    programmatic dependent launch and to one with the late wait switched off."""
+    if grid:
+        monkeypatch.setenv('D2D_B200_GRID', grid)
+    monkeypatch.setenv('D2D_B200_PDL', '0')
+    plain = make_vec(E, seed=13)
+    monkeypatch.delenv('D2D_B200_PDL')
+    late = make_vec(E, seed=13)
+    monkeypatch.setenv('D2D_B200_LATE_WAIT', '0')
+    early = make_vec(E, seed=13)
+    monkeypatch.delenv('D2D_B200_LATE_WAIT')
+    envs = (plain, late, early)
+    for env in envs:
+        env.reset()
+        env.reset_stats()
+    acts = [late.sample_actions() for _ in range(4)]
+    outs = {env: [env.alloc_outputs() for _ in range(4)] for env in envs}
+    order = [0, 1, 2, 3, 3, 0, 1, 1, 2, 0, 3, 2]               # consecutive steps mostly on different sets, twice on the same one
+    graphs = {env: env.capture_steps([acts[i] for i in order], [outs[env][i] for i in order], inputs_stable=True) for env in (late, early)}
+    diff = torch.zeros((), dtype=torch.int64, device='cuda')
+
+    def check():
+        d = (plain.step_count != late.step_count).sum() + (plain.step_count != early.step_count).sum()
+        for i in range(4):
+            for name in ('obs', 'capacity_mbps', 'reward', 'done'):
+                ref = getattr(outs[plain][i], name)
+                d = d + (ref != getattr(outs[late][i], name)).sum() + (ref != getattr(outs[early][i], name)).sum()
+        return d
+
+    for it in range(300 if E <= 4096 else 50):
+        for i in order:
+            plain.step(acts[i], out=outs[plain][i])
+        graphs[late].replay(); graphs[early].replay()
+        if it % 15 == 0:
+            diff += check()
+        if it % 40 == 7:                                        # new episodes in between (counters back to 0, new positions)
+            for env in envs:
+                env.reset()
+    mask = torch.ones(E, dtype=torch.uint8, device='cuda')
+    for it in range(30):                                        # eager chains
+        for env in envs:
+            for k in range(9):
+                env.step(acts[(it + k) % 4], out=outs[env][(it + k) % 4], inputs_stable=True)
+            env.reset(mask=mask)
+            env.step(acts[it % 4], out=outs[env][it % 4], inputs_stable=True)
+            env.step(acts[(it + 1) % 4], out=outs[env][(it + 1) % 4], inputs_stable=True)
+        diff += check() + (plain.positions != late.positions).sum()
+    torch.cuda.synchronize()
+    assert int(diff.item()) == 0
+    sp, sl = plain.stats(), late.stats()
+    assert sp['env_steps'] == sl['env_steps'] and sp['rescues'] == sl['rescues'] and sp['penalties'] == sl['penalties']
+    assert sl['sum_reward'] == pytest.approx(sp['sum_reward'], rel=1e-9)
+    for env in envs:
+        env.close()
