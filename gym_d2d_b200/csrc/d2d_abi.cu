@@ -268,6 +268,10 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
         if (dense) {
             h->dense_bt = bt;
             h->lpt = (h->N + bt - 1) / bt;
+            // BASELINE config #3's shape has its own instantiation (d2d_step_dense.cuh: SPEC)
+            h->spec = h->ple2 && bt == 320 && h->N == 600 && cfg->num_cues == 100 && cfg->num_rbs == 100 && h->bin_cap == 16 && cfg->n_pwr_cue == 24 &&
+                      cfg->n_pwr_due == 21;
+            if (const char *sp = std::getenv("D2D_B200_SPEC")) h->spec = h->spec && std::atoi(sp) != 0;   // tests: force the generic shape
         }
         const size_t smem = dense ? d2d_dense_smem(h->N, cfg->num_rbs, h->bin_cap, bt, h->V) : d2d_block_smem(h->N, cfg->num_rbs, h->lpt);
         if (smem > 227 * 1024) return bail(fail(D2D_ERR_UNSUPPORTED, "d2d_create: too many links / RBs for one SM's shared memory"));

@@ -131,13 +131,23 @@ __device__ __noinline__ D2DDenseFix d2d_dense_rescue(const D2DParams &P, uint32_
 // FULL: exactly the core outputs (obs, capacity, reward, done) and the step counters are bound and every link of a type shares
 // one set of constants (no per-device overrides) - the VecD2DEnv default - so the hot path tests no pointer and selects its
 // constants from the constant bank.  EXACT: an fp64 shadow of the positions is bound (the fp64 pass then needs d_min).
-template <bool PLE2, int LPT, int BT, bool FULL, bool EXACT>
+#define D2D_DENSE_SPEC_N 600u
+#define D2D_DENSE_SPEC_C 100u
+#define D2D_DENSE_SPEC_R 100u
+#define D2D_DENSE_SPEC_CAP 16u
+template <bool PLE2, int LPT, int BT, bool FULL, bool EXACT, bool SPEC = false>
 __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(const __grid_constant__ D2DParams P) {
     extern __shared__ __align__(16) unsigned char d2d_dense_smem[];
     constexpr uint32_t NW = BT / 32;
-    const uint32_t N = (uint32_t)P.N, C = (uint32_t)P.C, V = (uint32_t)P.V, R = (uint32_t)P.R, CAP = (uint32_t)P.bin_cap;
-    const uint32_t npc = (uint32_t)P.n_pwr_cue, npd = (uint32_t)P.n_pwr_due;
-    const uint32_t mgc = P.magic_cue, mgd = P.magic_due, n1c = P.npw1_cue, n1d = P.npw1_due;
+    // SPEC: BASELINE config #3 itself (100 RBs / 100 CUEs / 500 DUE pairs, the reference's default power levels: envs/env_config.py:12-27,
+    // envs/d2d_env.py:31-35) with every count, stride, shared-memory offset and division magic an immediate - and, because no link of
+    // a thread's second slot can be a CUE, that slot's code without the link-type selects: 738 -> 666 us
+    const uint32_t N = SPEC ? D2D_DENSE_SPEC_N : (uint32_t)P.N, C = SPEC ? D2D_DENSE_SPEC_C : (uint32_t)P.C,
+                   V = SPEC ? 1u + D2D_DENSE_SPEC_C + 2u * (D2D_DENSE_SPEC_N - D2D_DENSE_SPEC_C) : (uint32_t)P.V,
+                   R = SPEC ? D2D_DENSE_SPEC_R : (uint32_t)P.R, CAP = SPEC ? D2D_DENSE_SPEC_CAP : (uint32_t)P.bin_cap;
+    const uint32_t npc = SPEC ? 24u : (uint32_t)P.n_pwr_cue, npd = SPEC ? 21u : (uint32_t)P.n_pwr_due;
+    const uint32_t mgc = SPEC ? 178956971u : P.magic_cue, mgd = SPEC ? 204522253u : P.magic_due;      // ceil(2^32 / 24), ceil(2^32 / 21)
+    const uint32_t n1c = SPEC ? 0u : P.npw1_cue, n1d = SPEC ? 0u : P.npw1_due;
     const D2DDenseLayout L = d2d_dense_layout((int)N, (int)R, (int)CAP, BT, (int)V);
     // the bins sit on 128-byte boundaries of the shared window (see the walk): round the dynamic region's base up
     unsigned char *const sm = d2d_dense_smem + ((0u - (uint32_t)__cvta_generic_to_shared(d2d_dense_smem)) & 127u);
@@ -167,7 +177,7 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
 #pragma unroll
     for (int k = 0; k < LPT; ++k) {
         const uint32_t j = tid + k * BT;
-        has[k] = j < N; cue[k] = j < C;
+        has[k] = j < N; cue[k] = j < C && !(SPEC && k * BT >= (int)D2D_DENSE_SPEC_C);
     }
     // link constants (tx_lin0, a_lin, inv_noise, snr0_dB) and (sens, bw): one set per link type from the constant bank unless
     // a device-config file overrode single devices (then the per-link tables, through L1)

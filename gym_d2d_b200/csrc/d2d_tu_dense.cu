@@ -18,9 +18,23 @@ int plan(d2d_handle *h, size_t smem) {
     if (!rc) rc = d2d_plan_geometry(h, d2d_step_dense_kernel<PLE2, LPT, BT, true, false>, BT, smem, 1);
     return rc;
 }
+// the instantiations for BASELINE config #3's shape (d2d_step_dense.cuh: SPEC)
+int plan_spec(size_t smem) {
+    int rc = d2d_allow_smem(d2d_step_dense_kernel<true, 2, 320, false, false, true>, smem);
+    if (!rc) rc = d2d_allow_smem(d2d_step_dense_kernel<true, 2, 320, false, true, true>, smem);
+    if (!rc) rc = d2d_allow_smem(d2d_step_dense_kernel<true, 2, 320, true, true, true>, smem);
+    if (!rc) rc = d2d_allow_smem(d2d_step_dense_kernel<true, 2, 320, true, false, true>, smem);
+    return rc;
+}
 template <bool PLE2, int LPT, int BT>
 cudaError_t launch(const d2d_handle *h, const D2DParams &P, int grid, const D2DLaunchSel &sel, cudaStream_t st, bool pdl) {
 #define D2D_GO(FULL_, EXACT_) d2d_launch_step(d2d_step_dense_kernel<PLE2, LPT, BT, FULL_, EXACT_>, grid, h->block, (size_t)h->smem, st, P, pdl)
+    if (sel.full && h->uniform) return sel.exact ? D2D_GO(true, true) : D2D_GO(true, false);
+    return sel.exact ? D2D_GO(false, true) : D2D_GO(false, false);
+#undef D2D_GO
+}
+cudaError_t launch_spec(const d2d_handle *h, const D2DParams &P, int grid, const D2DLaunchSel &sel, cudaStream_t st, bool pdl) {
+#define D2D_GO(FULL_, EXACT_) d2d_launch_step(d2d_step_dense_kernel<true, 2, 320, FULL_, EXACT_, true>, grid, h->block, (size_t)h->smem, st, P, pdl)
     if (sel.full && h->uniform) return sel.exact ? D2D_GO(true, true) : D2D_GO(true, false);
     return sel.exact ? D2D_GO(false, true) : D2D_GO(false, false);
 #undef D2D_GO
@@ -33,10 +47,12 @@ int d2d_dense_plan(d2d_handle *h, size_t smem) {
     if (h->lpt == LPT_ && h->dense_bt == BT_) rc = h->ple2 ? plan<true, LPT_, BT_>(h, smem) : plan<false, LPT_, BT_>(h, smem);
     D2D_DENSE_SHAPES(D2D_CASE)
 #undef D2D_CASE
+    if (!rc && h->spec) rc = plan_spec(smem);
     return rc;
 }
 
 cudaError_t d2d_dense_launch(const d2d_handle *h, const D2DParams &P, int grid, const D2DLaunchSel &sel, cudaStream_t st, bool pdl) {
+    if (h->spec) return launch_spec(h, P, grid, sel, st, pdl);
     cudaError_t err = cudaErrorInvalidValue;
 #define D2D_CASE(LPT_, BT_)                                                                                      \
     if (h->lpt == LPT_ && h->dense_bt == BT_)                                                                    \

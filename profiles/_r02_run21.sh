@@ -1,4 +1,4 @@
-# round 2, GPU call 21+: dense kernel experiments, one change at a time
+# round 2, GPU calls 21+: dense kernel experiments, one change at a time
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q -x -k "dense or config3 or block or overflow or crowded or golden or fixture" 2>&1 | tail -12

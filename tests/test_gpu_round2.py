@@ -708,3 +708,45 @@ def test_late_wait_bit_identical_to_serialised_launches(monkeypatch, E, grid):
     assert sl['sum_reward'] == pytest.approx(sp['sum_reward'], rel=1e-9)
     for env in envs:
         env.close()
+
+
+# ---- dense kernel: the instantiation for BASELINE config #3's shape == the generic one ----------------------------------------------------------
+@pytest.mark.parametrize('info', [True, False])
+def test_dense_spec_instantiation_equals_generic(monkeypatch, info):
+    """100 RBs / 100 CUEs / 500 DUE pairs runs on d2d_step_dense_kernel<.., SPEC> (counts, strides and division magics as
+    immediates); D2D_B200_SPEC=0 forces the generic instantiation.  Same results (to the last-ulp freedom of two block-kernel
+    launches), both within tolerance of the oracle; crowded RBs, absent agents, several envs per block, two steps."""
+    import gym_d2d_b200 as G
+    from tests._util import RTOL, assert_rel
+    kw = CONFIGS['dense']
+    cfg = O.OracleConfig(**kw)
+    E = 500
+    rng = np.random.default_rng(99)
+    pos, act = O.random_positions(cfg, E, rng), O.random_actions(cfg, E, rng)
+    act[::7, ::3] = -1
+    crowd = np.arange(E) % 40 == 3
+    act[crowd] = act[crowd] % 21                                       # everybody on RB 0: the overflow list
+    a = torch.as_tensor(act, dtype=torch.int32, device='cuda')
+    monkeypatch.setenv('D2D_B200_GRID', '30')
+    spec = G.VecD2DEnv(E, dict(kw), device='cuda', info=info)
+    monkeypatch.setenv('D2D_B200_SPEC', '0')
+    generic = G.VecD2DEnv(E, dict(kw), device='cuda', info=info)
+    monkeypatch.delenv('D2D_B200_SPEC')
+    outs = []
+    for env in (spec, generic):
+        env.set_positions(pos)
+        for _ in range(2):
+            obs, reward, done, inf = env.step(a)
+        torch.cuda.synchronize()
+        outs.append((obs.cpu().numpy(), reward.cpu().numpy(), inf['capacity_mbps'].cpu().numpy(), env.step_count.cpu().numpy()))
+    np.testing.assert_allclose(outs[0][0], outs[1][0], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(outs[0][2], outs[1][2], rtol=1e-5, atol=1e-6)
+    np.testing.assert_array_equal(outs[0][3], outs[1][3])
+    on = act >= 0
+    ref = O.step_batch(cfg, pos, np.where(on, act, 0), active=on.astype(np.uint8), nthreads=4)
+    for got in outs:
+        assert_rel(got[0][..., 4][on], ref['sinr_db'][on], RTOL, 'sinr_db')
+        assert_rel(got[0][..., 5][on], ref['snr_db'][on], RTOL, 'snr_db')
+        assert_rel(got[2][on], ref['capacity_mbps'][on], RTOL, 'capacity')
+        assert_rel(got[1], ref['reward'], RTOL, 'reward')
+    spec.close(); generic.close()
