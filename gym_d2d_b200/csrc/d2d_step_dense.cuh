@@ -32,8 +32,21 @@
 // blocks per SM the register allocation has to allow (80 registers at 256 threads)
 #define D2D_DENSE_MINB(BT) ((BT) <= 128 ? 6 : (BT) <= 160 ? 5 : (BT) <= 192 ? 4 : 3)
 
+// What the out-of-line fp64 pass needs of the launch parameters, copied to shared memory once per block: read through the
+// reference to the __grid_constant__ parameter struct every field was a generic-address global load - a quarter of the pass's
+// cycles were long-scoreboard stalls on them (profiles/README.md), and the block's other warps wait for the pass at the barrier.
+struct D2DDenseRC {
+    D2DLinkD ud_cue, ud_due;     // the two link types' fp64 constants (uniform)
+    double ple_d, thr_d;
+    const double *pos64;         // fp64 position shadow or nullptr
+    const D2DLinkD *linkD;       // per-link tables (per-device overrides)
+    const D2DLinkB *linkB;
+    float sens_cue, sens_due, thr_dB, thr_band;
+    uint32_t C, V, CAP, uniform;
+};
+
 struct D2DDenseLayout {
-    uint32_t bins, pwr, pwr_d, cnt, red, sst, mbar, sact, spos, grp, total, cnt_words;
+    uint32_t bins, pwr, pwr_d, cnt, red, sst, rc, mbar, sact, spos, grp, total, cnt_words;
 };
 
 __host__ __device__ inline D2DDenseLayout d2d_dense_layout(int N, int R, int cap, int bt, int V) {
@@ -43,6 +56,7 @@ __host__ __device__ inline D2DDenseLayout d2d_dense_layout(int N, int R, int cap
     L.pwr = b;   b += D2D_MAX_PWR_LEVELS * 4u;                            // 10^(p/10)
     L.red = b;   b += 2u * 4u * D2D_DENSE_MAX_WARPS * 4u;                 // [2][4][warps]: capacity, acting agents, rescues, penalty
     L.sst = b;   b += 8u * 8u;                                            // the block's statistics (one thread adds to them per env)
+    L.rc = b;    b += (uint32_t)((sizeof(D2DDenseRC) + 15u) & ~15u);      // the fp64 pass's constants
     L.mbar = b;  b += 16u;                                                // the staging buffer's mbarrier
     L.sact = b;  b += (((uint32_t)N * 4u + 15u) & ~15u) + 16u;            // the next env's actions: its 16-byte aligned window of the global array
     L.spos = b;  b += (((uint32_t)V * 8u + 15u) & ~15u) + 16u;            // and its V positions
@@ -67,13 +81,12 @@ __host__ inline int d2d_dense_bin_cap(int N, int R) {
 
 // interferer record rk's fp64 term at receiver rxd (the cooperative fp64 pass); pwd = the fp64 power table in shared memory
 template <bool PLE2>
-__device__ __forceinline__ double d2d_dense_term_f64(const float4 rk, const double2 rxd, const double2 *pe64, uint32_t C, const double *pwd,
-                                                     const D2DParams &P) {
+__device__ __forceinline__ double d2d_dense_term_f64(const float4 rk, const double2 rxd, const double2 *pe64, const double *pwd, const D2DDenseRC &rc) {
     const uint32_t wk = __float_as_uint(rk.w), kk = wk & 0xffffu;
-    const double2 tk = pe64 ? pe64[d2d_tx_dev((int)kk, (int)C)] : make_double2((double)rk.x, (double)rk.y);
+    const double2 tk = pe64 ? pe64[d2d_tx_dev((int)kk, (int)rc.C)] : make_double2((double)rk.x, (double)rk.y);
     const double ex = tk.x - rxd.x, ey = tk.y - rxd.y;
-    const double t_lin = P.uniform ? (kk < C ? P.ud_cue.t_lin : P.ud_due.t_lin) : P.linkD[kk].t_lin;
-    return pwd[wk >> 16] * t_lin * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, P.ple_d);
+    const double t_lin = rc.uniform ? (kk < rc.C ? rc.ud_cue.t_lin : rc.ud_due.t_lin) : rc.linkD[kk].t_lin;
+    return pwd[wk >> 16] * t_lin * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, rc.ple_d);
 }
 
 // What the fp64 pass changes of a link's outputs: flag 1 = sinr_dB, 2 = snr_dB, 4 = rate and capacity
@@ -86,15 +99,15 @@ struct D2DDenseFix {
 // peer records, a butterfly sums their terms, every lane returns the same result.  Kept out of line: rare, and its fp64
 // registers must not count against the hot loop's allocation.
 template <bool PLE2, bool THR>
-__device__ __noinline__ D2DDenseFix d2d_dense_rescue(const D2DParams &P, uint32_t e, uint32_t vj, uint32_t vrb, uint32_t vself, uint32_t vpw,
+__device__ __noinline__ D2DDenseFix d2d_dense_rescue(const D2DDenseRC &rc, uint32_t e, uint32_t vj, uint32_t vrb, uint32_t vself, uint32_t vpw,
                                                      const float4 *bp, const uint32_t *cn, const float4 *ovrec,
                                                      const uint16_t *ovrb, const double *pwd, uint32_t ovn, uint32_t lane, float vrx_x, float vrx_y) {
     // (without an fp64 shadow of the positions and with uniform link constants the pass reads no global memory: the victim's
-    // receiver comes from its lane's registers, the transmitters from the peer records, the tables from shared memory and the
-    // constant bank - the pass sits between two block barriers, so its latency is what the other warps wait for)
-    const uint32_t C = (uint32_t)P.C, V = (uint32_t)P.V, CAP = (uint32_t)P.bin_cap;
-    const bool exact = P.pos64 != nullptr;
-    const double2 *pe64 = exact ? reinterpret_cast<const double2 *>(P.pos64) + (int64_t)e * V : nullptr;
+    // receiver comes from its lane's registers, the transmitters from the peer records, the tables and constants from shared
+    // memory - the pass sits between two block barriers, so its latency is what the other warps wait for)
+    const uint32_t C = rc.C, V = rc.V, CAP = rc.CAP;
+    const bool exact = rc.pos64 != nullptr;
+    const double2 *pe64 = exact ? reinterpret_cast<const double2 *>(rc.pos64) + (int64_t)e * V : nullptr;
     const float4 own = vself < CAP ? bp[vrb * CAP + vself] : ovrec[vself - CAP];                 // the victim's own record: (tx_x, tx_y, ..)
     const double2 txd = exact ? pe64[d2d_tx_dev((int)vj, (int)C)] : make_double2((double)own.x, (double)own.y);
     double2 rxd = make_double2(0.0, 0.0);                                                          // a CUE's receiver: the MBS at the origin
@@ -103,23 +116,31 @@ __device__ __noinline__ D2DDenseFix d2d_dense_rescue(const D2DParams &P, uint32_
     const float4 *vbase = bp + vrb * CAP;
     double I64 = 0.0;
     for (uint32_t q = lane; q < vnb; q += 32u)
-        if (q != vself) I64 += d2d_dense_term_f64<PLE2>(vbase[q], rxd, pe64, C, pwd, P);
+        if (q != vself) I64 += d2d_dense_term_f64<PLE2>(vbase[q], rxd, pe64, pwd, rc);
     if (vn > CAP)
 #pragma unroll 1
         for (uint32_t q = lane; q < ovn; q += 32u)
-            if (ovrb[q] == (uint16_t)vrb && CAP + q != vself) I64 += d2d_dense_term_f64<PLE2>(ovrec[q], rxd, pe64, C, pwd, P);
+            if (ovrb[q] == (uint16_t)vrb && CAP + q != vself) I64 += d2d_dense_term_f64<PLE2>(ovrec[q], rxd, pe64, pwd, rc);
 #pragma unroll
     for (int sh = 16; sh > 0; sh >>= 1)
         I64 += __hiloint2double(__shfl_xor_sync(0xffffffffu, __double2hiint(I64), sh), __shfl_xor_sync(0xffffffffu, __double2loint(I64), sh));
-    const D2DLinkD Lj = P.uniform ? (vj < C ? P.ud_cue : P.ud_due) : P.linkD[vj];
-    const float sens = P.uniform ? (vj < C ? P.us_cue.x : P.us_due.x) : P.linkB[vj].sens_dBm;
+    const D2DLinkD Lj = rc.uniform ? (vj < C ? rc.ud_cue : rc.ud_due) : rc.linkD[vj];
+    const float sens = rc.uniform ? (vj < C ? rc.sens_cue : rc.sens_due) : rc.linkB[vj].sens_dBm;
     const double ex = txd.x - rxd.x, ey = txd.y - rxd.y;
-    const double Sg = pwd[vpw] * Lj.a_lin * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, P.ple_d);
+    const double Sg = pwd[vpw] * Lj.a_lin * d2d_gain_f64_fast<PLE2>(ex * ex + ey * ey, rc.ple_d);
     const double r = Sg * d2d_rcp_f64(fma(I64, Lj.inv_noise, 1.0));
     const bool r1 = fabs(r - 1.0) < 0.0625, s1 = fabs(Sg - 1.0) < 0.0625;
     D2DDenseFix f = {0.f, 0.f, 0.f, 0.f, 0u};
     double sinr = 0.0;
-    if (exact || r1 || (THR && P.thr_band > 0.f)) { sinr = r1 ? d2d_db_near1(r) : 4.3429448190325182765 * d2d_ln_f64(r); f.sinr_dB = THR ? d2d_sinr_store(sinr, P) : (float)sinr; f.flags |= 1u; }
+    if (exact || r1 || (THR && rc.thr_band > 0.f)) {
+        sinr = r1 ? d2d_db_near1(r) : 4.3429448190325182765 * d2d_ln_f64(r);
+        float sv = (float)sinr;
+        if (THR && rc.thr_band > 0.f) {             // d2d_sinr_store: the fp32 image stays on the float64 value's side of the reward threshold
+            const bool ge = sinr >= rc.thr_d;
+            if ((sv >= rc.thr_dB) != ge) sv = ge ? rc.thr_dB : nextafterf(rc.thr_dB, -3.0e38f);
+        }
+        f.sinr_dB = sv; f.flags |= 1u;
+    }
     if (exact || s1) { f.snr_dB = (float)(s1 ? d2d_db_near1(Sg) : 4.3429448190325182765 * d2d_ln_f64(Sg)); f.flags |= 2u; }
     if (exact || (r1 && fabsf(sens) < 0.5f)) {
         const double rate = sinr > (double)sens ? 1.4426950408889634074 * d2d_ln_f64(1.0 + r) : 0.0;
@@ -173,6 +194,12 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
     for (uint32_t i = tid; i < D2D_MAX_PWR_LEVELS; i += BT) { pwr[i] = P.pwr_lin[i]; pwd[i] = P.pwr_lin_d[i]; }
     for (uint32_t i = tid; i < 3u * L.cnt_words; i += BT) cnt[i] = 0u;
     if (tid < 8u) sst[tid] = 0.0;
+    D2DDenseRC *rcs = reinterpret_cast<D2DDenseRC *>(sm + L.rc);
+    if (tid == 32u) {
+        rcs->ud_cue = P.ud_cue; rcs->ud_due = P.ud_due; rcs->ple_d = P.ple_d; rcs->thr_d = P.thr_d; rcs->pos64 = P.pos64;
+        rcs->linkD = P.linkD; rcs->linkB = P.linkB; rcs->sens_cue = P.us_cue.x; rcs->sens_due = P.us_due.x; rcs->thr_dB = P.thr_dB;
+        rcs->thr_band = P.thr_band; rcs->C = C; rcs->V = V; rcs->CAP = CAP; rcs->uniform = (uint32_t)P.uniform;
+    }
     bool has[LPT], cue[LPT];
 #pragma unroll
     for (int k = 0; k < LPT; ++k) {
@@ -458,7 +485,7 @@ __global__ void __launch_bounds__(BT, D2D_DENSE_MINB(BT)) d2d_step_dense_kernel(
                     ++resc;
                     const uint32_t vj = (tid - lane) + (uint32_t)src + k * BT;
                     const uint32_t vst = __shfl_sync(0xffffffffu, st[k], src);
-                    const D2DDenseFix f = d2d_dense_rescue<PLE2, !FULL>(P, e, vj, vst & 0x1ffu, (vst >> 16) & 0x7fffu, (vst >> 9) & 0x7fu, bp, cn, ovrec, ovrb, pwd, ovn, lane,
+                    const D2DDenseFix f = d2d_dense_rescue<PLE2, !FULL>(*rcs, e, vj, vst & 0x1ffu, (vst >> 16) & 0x7fffu, (vst >> 9) & 0x7fu, bp, cn, ovrec, ovrb, pwd, ovn, lane,
                                                                  __shfl_sync(0xffffffffu, rx[k].x, src), __shfl_sync(0xffffffffu, rx[k].y, src));
                     if ((int)lane == src) {
                         const uint64_t gi = (uint64_t)e * N + vj;
