@@ -290,6 +290,15 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
         rc = h->N <= 64 ? d2d_allow_smem(d2d_agent_reward_kernel<32>, smem) : d2d_allow_smem(d2d_agent_reward_kernel<256>, smem);
         if (rc != D2D_OK) return bail(rc);
     }
+    // Late-wait steps of small and medium batches run on a FRACTION of the block slots: a launch that fills the machine
+    // keeps its successor's blocks out until its own retire, so consecutive steps overlap only in their tails (E = 4096, one env per
+    // warp on 1024 of 1036 slots: 4.95 us per step); on one block per SM - every warp a software-pipelined loop over ~7 envs - several
+    // launches are resident at once and a step costs the launch floor plus its share of the machine's throughput (3.8 us; E = 8192:
+    // 6.3 -> 5.1 us).  Large batches need every warp slot for their own latency hiding (E = 32 768: 17.1 us on the full grid, 18.0 on 296
+    // blocks).  Sweep: profiles/ab_r02_41.log
+    if (h->use_warp && h->wpb == 4)
+        h->grid_late = cfg->num_envs <= 56 * (int64_t)h->num_sms ? h->num_sms : cfg->num_envs <= 166 * (int64_t)h->num_sms ? 3 * h->num_sms : 0;
+    if (const char *gl = std::getenv("D2D_B200_LATE_GRID")) h->grid_late = std::max(0, std::atoi(gl));      // A/B
     if (const char *gs = std::getenv("D2D_B200_GRID"))      // tests: few blocks, so every block steps many envs
         if (std::atoi(gs) > 0) { h->grid = std::min(h->grid, std::atoi(gs)); h->many.grid = std::min(h->many.grid, std::atoi(gs)); }
     if (h->use_warp) {      // one ticket word per warp slot of the step geometry
@@ -540,7 +549,8 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, int mode, void *s
                                h->cfg.reward_fn == D2D_REWARD_SYSTEM_CAPACITY && !io->agent_reward && !h->dRngStep &&
                                h->cfg.num_envs <= std::max<int64_t>(1, (int64_t)0x7fffffff / std::max(6 * h->N, 2 * h->V)) &&
                                !(h->chunk_override > 0 && h->chunk_override < h->cfg.num_envs);
-    const int grid1 = (int)std::min<int64_t>(h->grid, (h->cfg.num_envs + h->envs_per_block - 1) / h->envs_per_block);
+    const int step_grid = late && h->grid_late > 0 ? std::min(h->grid, h->grid_late) : h->grid;     // (late: one chunk, never a fused launch)
+    const int grid1 = (int)std::min<int64_t>(step_grid, (h->cfg.num_envs + h->envs_per_block - 1) / h->envs_per_block);
     // measured (profiles/README.md): the per-warp hand-off wins as soon as warps step more than one env per launch (E = 6 144,
     // 1.5 envs per warp: 7.6 -> 5.3 us; E = 16 384: 12.4 -> 9.4 us; E = 131 072: 69.5 -> 65.9 us) and loses at exactly one
     // (E = 4 096: 5.4 -> 6.8 us; E = 1 024: 2.7 -> 9.5 us), where the hardware's grid-wide wait stays - and where the launches do
@@ -586,8 +596,8 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, int mode, void *s
 #endif
         const bool alt = many && h->many.wpb != 0;               // fused multi-step launches of large batches: their own shape
         const int wpb = alt ? h->many.wpb : h->wpb, epb = alt ? h->many.envs_per_block : h->envs_per_block;
-        const int grid = (int)std::min<int64_t>(alt ? h->many.grid : h->grid, (n + epb - 1) / epb);
-        if (h->use_warp) { const int64_t warps = (int64_t)grid * wpb; P.envs_per_warp = (uint32_t)((n + warps - 1) / warps); }
+        const int grid = (int)std::min<int64_t>(alt ? h->many.grid : step_grid, (n + epb - 1) / epb);
+        if (h->use_warp) { const int64_t warps = (int64_t)grid * wpb; P.envs_per_warp = (uint32_t)(n / warps); P.envs_extra = (uint32_t)(n % warps); }
         D2DLaunchSel sel;
         sel.many = mode == MODE_MANY; sel.episode = mode == MODE_EPISODE;
         sel.no_reset = ea.no_reset;

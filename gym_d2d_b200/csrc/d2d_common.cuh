@@ -59,8 +59,9 @@ struct D2DParams {
     int32_t uniform;             // every CUE link shares one set of constants, and every DUE link (u_cue / u_due below)
     void *dense_ovf;             // dense kernel: [grid][N] float4 overflow records, then [grid][N] u16 RBs (handle-owned scratch)
     int32_t T;                   // d2d_step_many: steps per env in this launch (1 for d2d_step)
-    uint32_t envs_per_warp;      // warp kernel: ceil(num_envs / (grid * warps per block)), divided on the host (a 20-instruction
-                                 // sequence ahead of every warp's first load otherwise)
+    uint32_t envs_per_warp;      // warp kernel: floor(num_envs / (grid * warps per block)), divided on the host (a 20-instruction
+                                 // sequence ahead of every warp's first load otherwise) ...
+    uint32_t envs_extra;         // ... and the remainder: warps [0, envs_extra) step one env more (contiguous ranges, balanced to +-1)
     int64_t t_stride;            // d2d_step_many: envs between consecutive step slices of the io buffers
     uint32_t magic_cue, magic_due;  // d2d_div_magic(n_pwr_cue / n_pwr_due): rb = umulhi(a, magic) + (a & npw1)
     uint32_t npw1_cue, npw1_due;    // 0xffffffff when n_pwr == 1 (then magic = 0 and rb = a), else 0

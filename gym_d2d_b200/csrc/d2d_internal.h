@@ -89,6 +89,9 @@ struct d2d_handle {
     uintptr_t prev_out[6][2] = {};
     bool prev_out_valid = false;
     bool late_wait_on = true;      // D2D_B200_LATE_WAIT=0 switches the late wait off (tests, A/B)
+    int grid_late = 0;             // warp kernel: blocks of a late-wait step (0 = the full grid).  Under the late wait consecutive steps overlap
+                                   // for as long as the SMs have room for both: a launch that leaves the larger part of the block slots free
+                                   // lets its successor's blocks start while its own are still running (d2d_abi.cu)
     void *dDenseOvf = nullptr;     // dense kernel: the blocks' overflow lists (d2d_step_dense.cuh)
     // per-warp tickets (d2d_common.cuh: d2d_ticket_wait): one word per warp slot of the step geometry, and the chain bookkeeping
     uint64_t *dTickets = nullptr;

@@ -509,8 +509,9 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
     const bool hasA = lane < C, hasB = lane < S.D();
 
     const uint32_t num_envs = (uint32_t)P.num_envs;
-    const uint32_t per_warp = P.envs_per_warp;
-    const uint32_t e0 = min((blockIdx.x * WPB + warp) * per_warp, num_envs), e_end = min(e0 + per_warp, num_envs);
+    const uint32_t gw = blockIdx.x * WPB + warp;
+    const uint32_t e0 = min(gw * P.envs_per_warp + min(gw, P.envs_extra), num_envs),
+                   e_end = min(e0 + P.envs_per_warp + (gw < P.envs_extra ? 1u : 0u), num_envs);
     uint32_t e = e0;
     uint32_t iA = e * N + lane;                                    // slot-A link index of the env being computed
     uint32_t qN = e * V + 1u + lane;                               // slot-A device index of the env being prefetched
@@ -816,8 +817,18 @@ d2d_step_warp_kernel(const __grid_constant__ D2DParams P) {
         }
         if (last_t && (g == 31u || e + 1u == e_end)) {
             if (LATE) {
+#ifdef D2D_TIMELINE
+                if (e - g == e0) tl_c1 = d2d_tl_clock();
+#endif
                 if (e - g == e0) d2d_pdl_wait();                       // (the warp's first group: once per warp)
+#ifdef D2D_TIMELINE
+                if (e - g == e0) tl_c2 = d2d_tl_clock();
+#endif
+#ifdef D2D_EXPERIMENT_NOCOUNT
+                ns_keep = 0;
+#else
                 ns_keep = ((FULL || P.step_count) && lane <= g) ? (int)P.step_count[e - g + lane] : 0;
+#endif
             }
             // envs/d2d_env.py:65,68 for the whole group: num_steps += 1; done = num_steps >= EPISODE_LENGTH
             if (lane <= g) {

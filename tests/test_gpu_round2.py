@@ -649,7 +649,7 @@ def test_dense_staging_of_unaligned_rows(monkeypatch, kw):
 
 
 # ---- late wait: a flagged step whose output buffers its predecessor does not touch stores them ahead of griddepcontrol.wait -----------------
-@pytest.mark.parametrize('E,grid', [(4096, None), (1000, None), (148, None), (3000, '7')])
+@pytest.mark.parametrize('E,grid', [(4096, None), (1000, None), (148, None), (3000, '7'), (20000, None)])      # (late-wait steps run on 1 / 3 blocks per SM up to 8 288 / 24 568 envs)
 def test_late_wait_bit_identical_to_serialised_launches(monkeypatch, E, grid):
     """d2d_step right behind a d2d_step of the same handle, D2D_STEP_INPUTS_STABLE, output buffers disjoint from the predecessor's:
     the per-link outputs go out before the wait, the step counters / reward / done after it (D2D_PF_LATE_WAIT).  Graph replays and
@@ -705,7 +705,9 @@ def test_late_wait_bit_identical_to_serialised_launches(monkeypatch, E, grid):
     assert int(diff.item()) == 0
     sp, sl = plain.stats(), late.stats()
     assert sp['env_steps'] == sl['env_steps'] and sp['rescues'] == sl['rescues'] and sp['penalties'] == sl['penalties']
-    assert sl['sum_reward'] == pytest.approx(sp['sum_reward'], rel=1e-9)
+    # (per-warp fp32 partial sums over the envs a warp steps, then fp64 atomics: a late-wait step runs on fewer, fuller warps than the
+    # serialised launch, so the partial sums group differently)
+    assert sl['sum_reward'] == pytest.approx(sp['sum_reward'], rel=1e-7)
     for env in envs:
         env.close()
 
