@@ -292,12 +292,15 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
     }
     // Late-wait steps of small and medium batches run on a FRACTION of the block slots: a launch that fills the machine
     // keeps its successor's blocks out until its own retire, so consecutive steps overlap only in their tails (E = 4096, one env per
-    // warp on 1024 of 1036 slots: 4.95 us per step); on one block per SM - every warp a software-pipelined loop over ~7 envs - several
-    // launches are resident at once and a step costs the launch floor plus its share of the machine's throughput (3.8 us; E = 8192:
-    // 6.3 -> 5.1 us).  Large batches need every warp slot for their own latency hiding (E = 32 768: 17.1 us on the full grid, 18.0 on 296
-    // blocks).  Sweep: profiles/ab_r02_41.log
-    if (h->use_warp && h->wpb == 4)
-        h->grid_late = cfg->num_envs <= 56 * (int64_t)h->num_sms ? h->num_sms : cfg->num_envs <= 166 * (int64_t)h->num_sms ? 3 * h->num_sms : 0;
+    // warp on 1024 of 1036 slots: 4.95 us per step in a long chain).  On three of an SM's seven slots - every warp a software-pipelined
+    // loop over 2-3 envs - two launches are resident at once: 3.86 us (E = 8192: 6.3 -> 5.4 us, E = 16 384: 9.3 -> 8.7 us).  One block
+    // per SM is faster still in a long chain (3.75 us: up to seven launches in flight) but a launch then takes 14 us from its first
+    // warp to its last, which a chain of 10-20 steps pays for (20 steps: 4.2-4.4 us per step on three blocks, 4.4 on one, 5.3 on the
+    // full grid; 10 steps: 4.7 / 5.3 / 5.5).  Large batches need every warp slot for their own latency hiding (E = 32 768: 17.1 us on
+    // the full grid, 17.8 on three blocks per SM).  The latency shape (2-warp blocks): two blocks per SM - E = 1024 1.87 -> 1.76 us,
+    // E = 2048 3.38 -> 2.32 us.  Sweeps: profiles/ab_r02_40.log .. ab_r02_46.log
+    if (h->use_warp && h->wpb == 2) h->grid_late = 2 * h->num_sms;
+    if (h->use_warp && h->wpb == 4) h->grid_late = cfg->num_envs <= 166 * (int64_t)h->num_sms ? 3 * h->num_sms : 0;
     if (const char *gl = std::getenv("D2D_B200_LATE_GRID")) h->grid_late = std::max(0, std::atoi(gl));      // A/B
     if (const char *gs = std::getenv("D2D_B200_GRID"))      // tests: few blocks, so every block steps many envs
         if (std::atoi(gs) > 0) { h->grid = std::min(h->grid, std::atoi(gs)); h->many.grid = std::min(h->many.grid, std::atoi(gs)); }
@@ -533,7 +536,7 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, int mode, void *s
         const bool plain = h->use_warp && mode == MODE_STEP && h->cfg.reward_fn == D2D_REWARD_SYSTEM_CAPACITY && !io->agent_reward && !h->dRngStep &&
                            h->cfg.num_envs <= std::max<int64_t>(1, (int64_t)0x7fffffff / std::max(6 * h->N, 2 * h->V)) &&
                            !(h->chunk_override > 0 && h->chunk_override < h->cfg.num_envs);
-        late = plain && stable && h->late_wait_on && h->prev_out_valid && h->last_kind == D2D_LAST_STEP && !(h->wpb == 2 && h->cfg.num_envs > 1792);
+        late = plain && stable && h->late_wait_on && h->prev_out_valid && h->last_kind == D2D_LAST_STEP && !(h->wpb == 2 && h->cfg.num_envs > 1792 && h->grid_late == 0);
         for (int a = 0; late && a < 6; ++a)
             for (int b = 0; b < 6; ++b)
                 if (cur[a][0] && h->prev_out[b][0] && cur[a][0] < h->prev_out[b][1] && h->prev_out[b][0] < cur[a][0] + cur[a][1]) late = false;
