@@ -58,6 +58,8 @@ class D2DEnv:
         self._cues = set(self.device_ids[1:1 + cfg.num_cues])
         self._due_tx = {t for (t, _r) in cfg.link_ids()[cfg.num_cues:]}
         self._host = self.vec.alloc_host_outputs(pinned=False, info=True)
+        self._nvec = [int(n) for n in self.vec.action_nvec]
+        self._views: Dict[tuple, tuple] = {}                  # per set of present agents: (rows, per-agent row order, id pairs)
 
     def _enable_downlink(self) -> None:
         """envs/d2d_env.py:87-89: a key whose transmitter is neither a DUE nor a CUE is a DOWNLINK action of the MBS.  The
@@ -77,14 +79,14 @@ class D2DEnv:
         """Type rule of envs/d2d_env.py:93-101; the integer itself is decoded on the GPU."""
         if not isinstance(action, (int, np.integer)) or isinstance(action, bool):
             raise ValueError(f'Unable to decode action type "{type(action)}"')
-        tx_id, _, rx_id = key.partition(':')
-        for id_ in (tx_id, rx_id):
-            if id_ not in self._device_set:
-                raise KeyError(id_)                                   # devices.py:28
-        if key not in self._link_index:
+        j = self._link_index.get(key)
+        if j is None:
+            tx_id, _, rx_id = key.partition(':')
+            for id_ in (tx_id, rx_id):
+                if id_ not in self._device_set:
+                    raise KeyError(id_)                               # devices.py:28
             raise KeyError(key)
-        j = self._link_index[key]
-        n = int(self.vec.action_nvec[j])
+        n = self._nvec[j]
         a = int(action)
         if not 0 <= a < n:
             raise ValueError(f'action {a} for "{key}" is outside Discrete({n})')
@@ -94,34 +96,52 @@ class D2DEnv:
         if not self.vec.config.downlinks and any(isinstance(k, str) and k.startswith(BASE_STATION_ID + ':') and
                                                  k.partition(':')[2] in self._cues for k in raw_actions):
             self._enable_downlink()                                    # envs/d2d_env.py:87-89: DOWNLINK actions of the MBS
-        acts = np.full((1, self.config.num_links), -1, np.int32)      # -1: agent absent (Appendix B.8)
+        acts = [-1] * self.config.num_links                            # -1: agent absent (Appendix B.8)
         keys = []
+        index = self._link_index
         for key, action in raw_actions.items():                       # caller's insertion order (envs/d2d_env.py:75)
-            a = self._decode_action(key, action)
-            acts[0, self._link_index[key]] = a
+            a = self._decode_action(key, action)                      # (raises for keys that are no link of this env)
+            acts[index[key]] = a
             keys.append(key)
-        self.vec.step_host(acts, self._host)
+        self.vec.step_host(np.asarray([acts], dtype=np.int32), self._host)
         return keys
+
+    def _view(self, keys: List[str]) -> tuple:
+        """Index tables of one set of present agents, built once per distinct key order: the agents' link rows, the row order of
+        every agent's observation (envs/obs_fn.py:43-53: own 6-tuple first, then the others in the action dict's order) and the
+        (tx, rx) id pairs the reference keys its state by."""
+        tk = tuple(keys)
+        v = self._views.get(tk)
+        if v is None:
+            rows = np.asarray([self._link_index[k] for k in keys], dtype=np.intp)
+            n = len(keys)
+            order = np.empty((n, n), dtype=np.intp)
+            for i in range(n):
+                order[i, 0] = rows[i]
+                order[i, 1:i + 1] = rows[:i]
+                order[i, i + 1:] = rows[i + 1:]
+            ids = [tuple(k.split(':')) for k in keys]
+            if len(self._views) >= 64:
+                self._views.clear()
+            v = self._views[tk] = (rows, order, ids)
+        return v
 
     def _obs_dict(self, keys: List[str]) -> Dict[str, np.ndarray]:
         """envs/obs_fn.py:43-53: own 6-tuple then every other present link's, in the action dict's order."""
         table = self._host['obs'][0].astype(np.float64)
-        rows = [self._link_index[k] for k in keys]
-        out = {}
-        for i, k in enumerate(keys):
-            order = [rows[i]] + rows[:i] + rows[i + 1:]
-            out[k] = table[order].reshape(-1)
-        return out
+        _rows, order, _ids = self._view(keys)
+        flat = table[order].reshape(len(keys), -1)                     # one gather for all agents; each agent's obs is its row
+        return dict(zip(keys, flat))
 
     def _state(self, keys: List[str]) -> dict:
         h = self._host
-        ids = [tuple(k.split(':')) for k in keys]
-        rows = [self._link_index[k] for k in keys]
+        rows, _order, ids = self._view(keys)
+        dyn = h['obs'][0, rows, 4:6].astype(np.float64)
         return {
-            'sinrs_db': {i: float(h['obs'][0, r, 4]) for i, r in zip(ids, rows)},
-            'snrs_db': {i: float(h['obs'][0, r, 5]) for i, r in zip(ids, rows)},
-            'rate_bps': {i: float(h['rate_bps'][0, r]) for i, r in zip(ids, rows)},
-            'capacity_mbps': {i: float(h['capacity_mbps'][0, r]) for i, r in zip(ids, rows)},
+            'sinrs_db': dict(zip(ids, dyn[:, 0].tolist())),
+            'snrs_db': dict(zip(ids, dyn[:, 1].tolist())),
+            'rate_bps': dict(zip(ids, h['rate_bps'][0, rows].astype(np.float64).tolist())),
+            'capacity_mbps': dict(zip(ids, h['capacity_mbps'][0, rows].astype(np.float64).tolist())),
         }
 
     def _position_nearby(self, anchor) -> Tuple[float, float]:
@@ -176,24 +196,22 @@ class D2DEnv:
         self.state = self._state(keys)
         obs = self._obs_dict(keys)
         if self.vec.per_agent_reward:                                  # envs/reward_fn.py:47-78: one reward per agent
-            rewards = {k: float(self._host['agent_reward'][0, self._link_index[k]]) for k in keys}
+            rewards = dict(zip(keys, self._host['agent_reward'][0, self._view(keys)[0]].astype(np.float64).tolist()))
         else:
             reward = float(self._host['reward'][0])
             rewards = {k: reward for k in keys}                        # envs/reward_fn.py:44
         game_over = {'__all__': self.num_steps >= EPISODE_LENGTH}      # envs/d2d_env.py:68
-        info = {k: self._info(k) for k in keys}
+        # envs/d2d_env.py:106-116
+        st = self.state
+        info = {k: {'rb': a[0], 'tx_pwr_dbm': a[1], 'snr_db': snr, 'sinr_db': sinr, 'rate_bps': rate, 'capacity_mbps': cap}
+                for k, a, snr, sinr, rate, cap in zip(keys, self.actions.values(), st['snrs_db'].values(), st['sinrs_db'].values(),
+                                                      st['rate_bps'].values(), st['capacity_mbps'].values())}
         return obs, rewards, game_over, info
 
     def _actions_view(self, keys: List[str]) -> Dict[str, Tuple[int, int]]:
         h = self._host
-        return {k: (int(h['rb'][0, self._link_index[k]]), int(h['tx_pwr_dbm'][0, self._link_index[k]])) for k in keys}
-
-    def _info(self, key: str) -> Dict[str, Any]:
-        """envs/d2d_env.py:106-116."""
-        j, h = self._link_index[key], self._host
-        return {'rb': int(h['rb'][0, j]), 'tx_pwr_dbm': int(h['tx_pwr_dbm'][0, j]),
-                'snr_db': float(h['obs'][0, j, 5]), 'sinr_db': float(h['obs'][0, j, 4]),
-                'rate_bps': float(h['rate_bps'][0, j]), 'capacity_mbps': float(h['capacity_mbps'][0, j])}
+        rows = self._view(keys)[0]
+        return dict(zip(keys, zip(h['rb'][0, rows].tolist(), h['tx_pwr_dbm'][0, rows].tolist())))
 
     def render(self, mode: str = 'human') -> None:
         assert self.state is not None and self.actions is not None, \
