@@ -57,7 +57,10 @@ class D2DEnv:
         self._device_set = set(self.device_ids)
         self._cues = set(self.device_ids[1:1 + cfg.num_cues])
         self._due_tx = {t for (t, _r) in cfg.link_ids()[cfg.num_cues:]}
-        self._host = self.vec.alloc_host_outputs(pinned=False, info=True)
+        # the library's pinned slot buffers (d2d_host_slot_buffers): the step's actions go up and all of its results come back
+        # with ONE copy each way instead of one pageable copy per output array
+        outputs = ('obs', 'capacity_mbps', 'reward', 'done', 'rate_bps', 'rb', 'tx_pwr_dbm') + (('agent_reward',) if self.vec.per_agent_reward else ())
+        self._host = self.vec.host_slot_buffers(0, outputs=outputs)
         self._nvec = [int(n) for n in self.vec.action_nvec]
         self._views: Dict[tuple, tuple] = {}                  # per set of present agents: (rows, per-agent row order, id pairs)
 
@@ -103,7 +106,9 @@ class D2DEnv:
             a = self._decode_action(key, action)                      # (raises for keys that are no link of this env)
             acts[index[key]] = a
             keys.append(key)
-        self.vec.step_host(np.asarray([acts], dtype=np.int32), self._host)
+        self._host['actions'][0] = acts
+        self.vec.step_host_async(self._host['actions'], self._host, 0)
+        self.vec.step_host_wait(0)
         return keys
 
     def _view(self, keys: List[str]) -> tuple:
