@@ -752,3 +752,45 @@ def test_dense_spec_instantiation_equals_generic(monkeypatch, info):
         assert_rel(got[2][on], ref['capacity_mbps'][on], RTOL, 'capacity')
         assert_rel(got[1], ref['reward'], RTOL, 'reward')
     spec.close(); generic.close()
+
+
+# ---- dict API: cached index tables per set of present agents ----------------------------------------------------------------
+def test_dict_api_changing_agent_sets_match_tensor_api():
+    """D2DEnv caches its index tables (rows, per-agent observation order, id pairs) per ORDERED set of present agents and builds all
+    observations with one gather (envs/obs_fn.py:43-53, envs/d2d_env.py:62-71, 103-116).  Steps with all agents, a shuffled subset, a
+    different subset and all agents again (reversed) must each equal the tensor API's step on the same positions and actions -
+    row for row, in the caller's key order - and `state` / `actions` must follow the last step only."""
+    import gym_d2d_b200 as G
+    rng = np.random.default_rng(5)
+    vec = make_vec(1, seed=0, exact_positions=True)
+    env = G.D2DEnv({}, seed=11)
+    env.reset()
+    vec.set_positions(env.vec.positions_f64)
+    keys_all = list(env.link_keys)
+    N = len(keys_all)
+    index = {k: i for i, k in enumerate(keys_all)}
+    orders = [list(range(N)), list(rng.permutation(N)[:17]), list(rng.permutation(N)[:30]), list(range(N))[::-1], list(rng.permutation(N)[:17])]
+    orders.append(orders[1])                                   # a set seen before: served from the cache
+    for order in orders:
+        keys = [keys_all[i] for i in order]
+        acts_row = np.full((1, N), -1, np.int32)
+        raw = {}
+        for k in keys:
+            a = int(rng.integers(0, env.vec.action_nvec[index[k]]))
+            raw[k] = a
+            acts_row[0, index[k]] = a
+        obs, rewards, done, info = env.step(raw)
+        t_obs, t_rew, _t_done, t_info = vec.step(torch.as_tensor(acts_row, device='cuda'))
+        table = t_obs[0].cpu().numpy().astype(np.float64)
+        assert list(obs) == keys and list(info) == keys and list(rewards) == keys
+        for pos, k in enumerate(keys):
+            rows = [order[pos]] + [j for q, j in enumerate(order) if q != pos]
+            np.testing.assert_array_equal(obs[k], table[rows].reshape(-1))
+            j = index[k]
+            assert info[k]['sinr_db'] == float(table[j, 4]) and info[k]['snr_db'] == float(table[j, 5])
+            assert info[k]['capacity_mbps'] == float(t_info['capacity_mbps'][0, j]) and info[k]['rate_bps'] == float(t_info['rate_bps'][0, j])
+            assert info[k]['rb'] == int(t_info['rb'][0, j]) and info[k]['tx_pwr_dbm'] == int(t_info['tx_pwr_dbm'][0, j])
+            assert rewards[k] == float(t_rew[0])
+            assert env.actions[k] == (info[k]['rb'], info[k]['tx_pwr_dbm'])
+        assert list(env.state['sinrs_db']) == [tuple(k.split(':')) for k in keys]
+    env.close(); vec.close()
