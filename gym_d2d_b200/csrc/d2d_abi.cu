@@ -335,7 +335,7 @@ D2D_API int d2d_destroy(d2d_handle_t *h) {
         for (void *p : s.stage) cudaFree(p);
         if (h->pipe_ready) { cudaEventDestroy(s.ev_in); cudaEventDestroy(s.ev_kernel); cudaEventDestroy(s.ev_out); }
     }
-    if (h->pipe_ready) { cudaStreamDestroy(h->s_in); cudaStreamDestroy(h->s_out); }
+    if (h->pipe_ready) { cudaStreamDestroy(h->s_in); cudaStreamDestroy(h->s_out); if (h->s_out2) cudaStreamDestroy(h->s_out2); }
     delete h;
     return D2D_OK;
 }
@@ -802,6 +802,7 @@ int host_pipeline_init(d2d_handle *h) {
     if (h->pipe_ready) return D2D_OK;
     D2D_CUDA(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     D2D_CUDA(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    if (const char *c = std::getenv("D2D_B200_OUT_STREAMS")) if (std::atoi(c) == 2) D2D_CUDA(cudaStreamCreateWithFlags(&h->s_out2, cudaStreamNonBlocking));
     for (auto &s : h->slot) {
         D2D_CUDA(cudaEventCreateWithFlags(&s.ev_in, cudaEventDisableTiming));
         D2D_CUDA(cudaEventCreateWithFlags(&s.ev_kernel, cudaEventDisableTiming));
@@ -909,16 +910,17 @@ D2D_API int d2d_step_host_async(d2d_handle_t *h, const d2d_step_io_t *hio, int s
     if (rc) return rc;
     D2D_CUDA(cudaEventRecord(s.ev_kernel, st));
     // copy-out
-    D2D_CUDA(cudaStreamWaitEvent(h->s_out, s.ev_kernel, 0));
+    cudaStream_t so = (h->s_out2 && (slot & 1)) ? h->s_out2 : h->s_out;
+    D2D_CUDA(cudaStreamWaitEvent(so, s.ev_kernel, 0));
     if (packed) {
-        D2D_CUDA(cudaMemcpyAsync((char *)s.host + s.out_offset, (char *)s.dev + s.out_offset, s.out_bytes, cudaMemcpyDeviceToHost, h->s_out));
+        D2D_CUDA(cudaMemcpyAsync((char *)s.host + s.out_offset, (char *)s.dev + s.out_offset, s.out_bytes, cudaMemcpyDeviceToHost, so));
     } else {
         void *dp[D2D_NUM_IO_BUFFERS];
         io_pointers(&dio, dp);
         for (int i = 1; i < D2D_NUM_IO_BUFFERS; ++i)
-            if (host[i]) D2D_CUDA(cudaMemcpyAsync(host[i], dp[i], bytes[i], cudaMemcpyDeviceToHost, h->s_out));
+            if (host[i]) D2D_CUDA(cudaMemcpyAsync(host[i], dp[i], bytes[i], cudaMemcpyDeviceToHost, so));
     }
-    D2D_CUDA(cudaEventRecord(s.ev_out, h->s_out));
+    D2D_CUDA(cudaEventRecord(s.ev_out, so));
     s.used = true;
     return D2D_OK;
 }

@@ -74,7 +74,7 @@ struct d2d_handle {
     double *stats = nullptr;
     // host-buffer steps (d2d_step_host*): the pipeline slots
     d2d_host_slot slot[D2D_HOST_SLOTS];
-    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_out2 = nullptr;      // s_out2: odd slots' copy-out (D2D_B200_OUT_STREAMS=2, A/B)
     bool pipe_ready = false;
     double *stage_pos = nullptr;
     int64_t stage_pos_envs = 0;

@@ -117,6 +117,7 @@ class VecD2DEnv:
                                                                 self._out.reward, self._out.done)
         self.rate_bps, self.rb, self.tx_pwr_dbm = self._out.rate_bps, self._out.rb, self._out.tx_pwr_dbm
         self._io = _lib.D2DStepIO()
+        self._host_io_cache: Dict[tuple, tuple] = {}
         self._nvec_dev = torch.as_tensor(self.action_nvec, device=dev)
         self._nvec_f = self._nvec_dev.to(torch.float32)
         self._nvec_m1 = (self._nvec_dev - 1).to(torch.int32)
@@ -138,6 +139,7 @@ class VecD2DEnv:
         if getattr(self, '_h', None):
             self._lib.d2d_destroy(self._h)
             self._h = None
+            self._host_io_cache.clear()
 
     def __del__(self) -> None:
         try:
@@ -395,6 +397,20 @@ class VecD2DEnv:
         return graph
 
     def _host_io(self, actions: np.ndarray, out: Dict[str, np.ndarray]) -> '_lib.D2DStepIO':
+        # a pipelined host loop passes the same few (actions, outputs) pairs over and over: their descriptor is built once
+        # (ten `.ctypes.data` lookups cost more host time than the call they feed).  The cache holds the arrays, so an id
+        # cannot be recycled for another object while its entry lives; a dict whose set of outputs changed misses by length.
+        key = (id(actions), id(out), len(out))
+        hit = self._host_io_cache.get(key)
+        if hit is not None and hit[1] is actions and hit[2] is out and all(a is b for a, b in zip(out.values(), hit[3])):
+            return hit[0]
+        io = self._build_host_io(actions, out)
+        if len(self._host_io_cache) >= 64:
+            self._host_io_cache.clear()
+        self._host_io_cache[key] = (io, actions, out, tuple(out.values()))
+        return io
+
+    def _build_host_io(self, actions: np.ndarray, out: Dict[str, np.ndarray]) -> '_lib.D2DStepIO':
         if actions.dtype != np.int32 or not actions.flags['C_CONTIGUOUS'] or actions.shape != (self.num_envs, self.num_links):
             raise ValueError(f'actions must be a C-contiguous int32 array of shape {(self.num_envs, self.num_links)}')
         return _lib.D2DStepIO(actions=actions.ctypes.data, obs=out['obs'].ctypes.data if 'obs' in out else None,
