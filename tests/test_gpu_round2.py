@@ -683,7 +683,7 @@ def test_late_wait_bit_identical_to_serialised_launches(monkeypatch, E, grid):
                 d = d + (ref != getattr(outs[late][i], name)).sum() + (ref != getattr(outs[early][i], name)).sum()
         return d
 
-    for it in range(300 if E <= 4096 else 50):
+    for it in range(2000 if E <= 4096 else 100):              # E = 4096: 24 000 late-wait steps in 2 000 graph replays
         for i in order:
             plain.step(acts[i], out=outs[plain][i])
         graphs[late].replay(); graphs[early].replay()
