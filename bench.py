@@ -399,11 +399,13 @@ def run_cuda_arm(args) -> None:
         DEPTH = 4                                  # steps in flight (D2D_HOST_SLOTS)
         slots = [env.host_slot_buffers(k) for k in range(DEPTH)]
         obs_static = env.obs_static()              # once per reset, outside the per-step loop (E x N x 16 B)
-        host_acts = [torch.empty((E, N), dtype=torch.int32, pin_memory=True) for _ in range(4)]
+        # the actions go up as int16 (D2D_STEP_ACTIONS_I16: every Discrete space of the reference fits 15 bits; the library widens
+        # them on the device): on a host link shared by several GPUs the download gets what the upload leaves
+        host_acts = [torch.empty((E, N), dtype=torch.int16, pin_memory=True) for _ in range(4)]
         for h, a in zip(host_acts, acts):
-            h.copy_(a)
+            h.copy_(a.to(torch.int16))
         host_np = [h.numpy() for h in host_acts]
-        h2d, d2h = E * N * 4, E * N * 8 + E * N * 4 + E * 4 + E
+        h2d, d2h = E * N * 2, E * N * 8 + E * N * 4 + E * 4 + E
         e2e_steps = max(200, min(args.steps, 400))
         for i in range(2 * DEPTH):         # warm-up through every pipeline slot
             env.step_host_async(host_np[i % 4], slots[i % DEPTH], i % DEPTH)
@@ -444,8 +446,8 @@ def run_cuda_arm(args) -> None:
                'host_link_gbs_per_gpu': (h2d + d2h) * e2e_steps / dt / 1e9,   # copies in both directions: the PCIe link bounds this number
                'd2h_gbs_per_gpu': d2h * e2e_steps / dt / 1e9, 'host_link_peak': link, 'numa': numa,
                'once_per_reset_bytes': int(obs_static.nbytes),
-               'api': 'd2d_step_host_async/_wait via VecD2DEnv.step_host_async (pinned host buffers, four steps in flight; actions '
-                      'copied in; obs_dyn (sinr, snr) + capacity + reward + done copied back every step as ONE packed copy; the '
+               'api': 'd2d_step_host_async/_wait via VecD2DEnv.step_host_async (pinned host buffers, four steps in flight; int16 actions '
+                      'copied in (D2D_STEP_ACTIONS_I16); obs_dyn (sinr, snr) + capacity + reward + done copied back every step as ONE packed copy; the '
                       'position columns of the observation table are fetched once per reset with d2d_get_positions)'}
     # ---- fused rollouts: d2d_rollout, T counted steps of every env per launch with the actions sampled on the
     # device (Discrete.sample, envs/d2d_env.py:54-60) - no [T][E][N] action input at all; positions read once per launch ----

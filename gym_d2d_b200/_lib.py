@@ -48,6 +48,7 @@ class D2DStepIO(C.Structure):
 
 
 STEP_INPUTS_STABLE = 1          # d2d_step_io.flags (include/d2d_b200.h, "Ordering rule")
+STEP_ACTIONS_I16 = 2            # d2d_step_host*: `actions` is int16 [E][N]
 EPISODE_DRAW_ACTIONS = 1        # d2d_episode flags
 OUT_OBS, OUT_CAPACITY, OUT_REWARD, OUT_DONE, OUT_RATE, OUT_RB, OUT_TX_PWR, OUT_AGENT_REWARD, OUT_OBS_DYN = (
     1, 2, 4, 8, 16, 32, 64, 128, 256)

@@ -317,6 +317,8 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
 namespace {
 void free_slot(d2d_host_slot &s) {
     cudaFree(s.dev);
+    cudaFree(s.stage16);
+    s.stage16 = nullptr;
     if (s.host) cudaFreeHost(s.host);
     s.dev = s.host = nullptr;
     s.bytes = s.out_offset = s.out_bytes = 0;
@@ -899,7 +901,17 @@ D2D_API int d2d_step_host_async(d2d_handle_t *h, const d2d_step_io_t *hio, int s
     dio.flags = 0;
     // copy-in: this slot's action staging is free once the kernel that last read it has run
     if (s.used) D2D_CUDA(cudaStreamWaitEvent(h->s_in, s.ev_kernel, 0));
-    D2D_CUDA(cudaMemcpyAsync((void *)dio.actions, host[0], bytes[0], cudaMemcpyHostToDevice, h->s_in));
+    if (hio->flags & D2D_STEP_ACTIONS_I16) {
+        // half the upload: int16 actions, widened on the copy-in stream (so ev_in covers the widening too)
+        if (!s.stage16) D2D_CUDA(cudaMalloc(&s.stage16, bytes[0] / 2));
+        D2D_CUDA(cudaMemcpyAsync(s.stage16, host[0], bytes[0] / 2, cudaMemcpyHostToDevice, h->s_in));
+        const int64_t count = (int64_t)(bytes[0] / 4);
+        d2d_widen_actions_kernel<<<(unsigned)std::min<int64_t>(4 * h->num_sms, (count / 2 + 255) / 256 + 1), 256, 0, h->s_in>>>(
+            (const int16_t *)s.stage16, (int32_t *)dio.actions, count);
+        D2D_CUDA(cudaGetLastError());
+    } else {
+        D2D_CUDA(cudaMemcpyAsync((void *)dio.actions, host[0], bytes[0], cudaMemcpyHostToDevice, h->s_in));
+    }
     D2D_CUDA(cudaEventRecord(s.ev_in, h->s_in));
     // kernel on the caller's stream (steps stay ordered there): needs the actions in, and this slot's previous
     // outputs copied out

@@ -81,6 +81,16 @@ __global__ void d2d_sample_actions_kernel(int32_t *__restrict__ actions, uint32_
     }
 }
 
+// D2D_STEP_ACTIONS_I16: the host uploaded int16 actions; the step kernels read int32 (sign-extended: < 0 stays "absent")
+__global__ void d2d_widen_actions_kernel(const int16_t *__restrict__ src, int32_t *__restrict__ dst, int64_t count) {
+    const int64_t pairs = count >> 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pairs; i += (int64_t)gridDim.x * blockDim.x) {
+        const short2 v = reinterpret_cast<const short2 *>(src)[i];
+        reinterpret_cast<int2 *>(dst)[i] = make_int2((int)v.x, (int)v.y);
+    }
+    if ((count & 1) && blockIdx.x == 0 && threadIdx.x == 0) dst[count - 1] = (int32_t)src[count - 1];
+}
+
 // ShadowingPathLoss: the step-call counter lives in device memory and advances on the stream (so does a replayed CUDA graph's)
 __global__ void d2d_advance_counter_kernel(uint64_t *counter, uint64_t by) { *counter += by; }
 

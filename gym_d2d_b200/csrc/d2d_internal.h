@@ -32,6 +32,7 @@ struct d2d_host_slot {
     d2d_step_io_t host_io{}, dev_io{};
     // caller-owned host buffers: per-buffer device staging, allocated on first use
     void *stage[D2D_NUM_IO_BUFFERS] = {};
+    void *stage16 = nullptr;       // D2D_STEP_ACTIONS_I16: the int16 actions as uploaded, widened into the int32 action staging
     cudaEvent_t ev_in = nullptr, ev_kernel = nullptr, ev_out = nullptr;
     bool used = false;
 };

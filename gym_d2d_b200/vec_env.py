@@ -411,9 +411,10 @@ class VecD2DEnv:
         return io
 
     def _build_host_io(self, actions: np.ndarray, out: Dict[str, np.ndarray]) -> '_lib.D2DStepIO':
-        if actions.dtype != np.int32 or not actions.flags['C_CONTIGUOUS'] or actions.shape != (self.num_envs, self.num_links):
-            raise ValueError(f'actions must be a C-contiguous int32 array of shape {(self.num_envs, self.num_links)}')
-        return _lib.D2DStepIO(actions=actions.ctypes.data, obs=out['obs'].ctypes.data if 'obs' in out else None,
+        if actions.dtype not in (np.int32, np.int16) or not actions.flags['C_CONTIGUOUS'] or actions.shape != (self.num_envs, self.num_links):
+            raise ValueError(f'actions must be a C-contiguous int32 (or int16) array of shape {(self.num_envs, self.num_links)}')
+        return _lib.D2DStepIO(flags=_lib.STEP_ACTIONS_I16 if actions.dtype == np.int16 else 0,   # int16: half the upload (D2D_STEP_ACTIONS_I16)
+                              actions=actions.ctypes.data, obs=out['obs'].ctypes.data if 'obs' in out else None,
                               capacity_mbps=out['capacity_mbps'].ctypes.data if 'capacity_mbps' in out else None,
                               reward=out['reward'].ctypes.data if 'reward' in out else None,
                               done=out['done'].ctypes.data if 'done' in out else None,
@@ -468,7 +469,7 @@ class VecD2DEnv:
             n = int(np.prod(shape)) * np.dtype(dtype).itemsize
             return np.frombuffer((C.c_char * n).from_address(ptr), dtype=dtype).reshape(shape)
 
-        out = {'actions': view(io.actions, (E, N), np.int32)}
+        out = {'actions': view(io.actions, (E, N), np.int32), 'actions16': view(io.actions, (E, N), np.int16)}    # (the same pinned bytes)
         ptrs = {'obs': io.obs, 'obs_dyn': io.obs_dyn, 'capacity_mbps': io.capacity_mbps, 'reward': io.reward, 'done': io.done,
                 'rate_bps': io.rate_bps, 'rb': io.rb, 'tx_pwr_dbm': io.tx_pwr_dBm, 'agent_reward': io.agent_reward}
         for name, _bit, width, dt in self._HOST_FIELDS:

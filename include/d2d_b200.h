@@ -140,6 +140,10 @@ typedef struct d2d_link {
 
 /* d2d_step_io.flags */
 #define D2D_STEP_INPUTS_STABLE 1u   /* see "Ordering rule" above; 0 is always safe */
+#define D2D_STEP_ACTIONS_I16 2u     /* d2d_step_host / d2d_step_host_async only: `actions` points to int16_t [E][N] (every Discrete space of
+                                       the reference fits: R n_pwr <= 32767; < 0 = agent absent) - half the upload per step; the library widens
+                                       them on the device.  A host link shared by several GPUs gives the download what the upload leaves:
+                                       profiles/README.md, "host link" */
 
 /* Buffers of one step.  All pointers are device pointers for d2d_step and host pointers for
  * d2d_step_host.  `actions` is required; any output may be NULL to skip it. */

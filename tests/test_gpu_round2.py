@@ -794,3 +794,50 @@ def test_dict_api_changing_agent_sets_match_tensor_api():
             assert env.actions[k] == (info[k]['rb'], info[k]['tx_pwr_dbm'])
         assert list(env.state['sinrs_db']) == [tuple(k.split(':')) for k in keys]
     env.close(); vec.close()
+
+
+# ---- host steps with int16 actions (D2D_STEP_ACTIONS_I16): half the upload, same results --------------------------------------
+@pytest.mark.parametrize('E', [1, 333, 4096])
+def test_host_steps_with_int16_actions_match_int32(E):
+    """d2d_step_host_async with D2D_STEP_ACTIONS_I16: the int16 [E][N] actions are widened on the device (sign-extended: < 0 stays
+    'agent absent', envs/d2d_env.py:36-40 spaces fit 15 bits) - every output bit-identical to the int32 upload, through the packed
+    pinned slot buffers and through caller-owned arrays, with several steps in flight."""
+    rng = np.random.default_rng(E)
+    env = make_vec(E, seed=5)
+    env.reset()
+    N = env.num_links
+    acts = [rng.integers(0, 500, size=(E, N), dtype=np.int32) for _ in range(6)]
+    for a in acts:
+        a[rng.random(a.shape) < 0.1] = -1                      # absent agents
+    names = ('obs_dyn', 'capacity_mbps', 'reward', 'done')
+    ref = []
+    slots = [env.host_slot_buffers(k) for k in range(4)]
+    env.step_count.zero_()
+    for i, a in enumerate(acts):                                # int32, one step at a time
+        slots[0]['actions'][:] = a
+        env.step_host_async(slots[0]['actions'], slots[0], 0)
+        env.step_host_wait(0)
+        ref.append({k: slots[0][k].copy() for k in names})
+    env.step_count.zero_()
+    got = [None] * len(acts)
+    for i, a in enumerate(acts):                                # int16 through the slots' own pinned bytes, four steps in flight
+        k = i % 4
+        if i >= 4:
+            env.step_host_wait(k)
+            got[i - 4] = {n: slots[k][n].copy() for n in names}
+        slots[k]['actions16'][:] = a.astype(np.int16)
+        env.step_host_async(slots[k]['actions16'], slots[k], k)
+    for i in range(max(0, len(acts) - 4), len(acts)):
+        env.step_host_wait(i % 4)
+        got[i] = {n: slots[i % 4][n].copy() for n in names}
+    for r, g in zip(ref, got):
+        for n in names:
+            np.testing.assert_array_equal(r[n], g[n])
+    env.step_count.zero_()
+    out = env.alloc_host_outputs(pinned=True, info=False, dyn=True)      # caller-owned arrays (per-buffer staging)
+    a16 = np.ascontiguousarray(acts[0].astype(np.int16))
+    env.step_host_async(a16, out, 1)
+    env.step_host_wait(1)
+    for n in names:
+        np.testing.assert_array_equal(ref[0][n], out[n])
+    env.close()
