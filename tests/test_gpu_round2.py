@@ -171,7 +171,7 @@ def test_obs_dyn_reassembles_the_full_table_bit_for_bit(name):
     # the default slot layout against a full-table host step on caller-owned buffers (two launches: see WARP_CONFIGS)
     full = env.alloc_host_outputs(info=True)
     slots = [env.host_slot_buffers(s) for s in (2, 3)]
-    assert set(slots[0]) == {'actions', 'obs_dyn', 'capacity_mbps', 'reward', 'done'}
+    assert set(slots[0]) == {'actions', 'actions16', 'obs_dyn', 'capacity_mbps', 'reward', 'done'}      # ('actions16': the same pinned bytes as int16)
     dyn = env.alloc_host_outputs(info=False, dyn=True)
     for i in range(4):
         a = env.sample_actions().cpu().numpy()
