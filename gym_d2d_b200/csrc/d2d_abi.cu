@@ -635,6 +635,8 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, int mode, void *s
 int check_step_args(const d2d_handle_t *h, const d2d_step_io_t *io, const char *who, bool need_actions = true) {
     if (!h || !io || (need_actions && !io->actions)) return fail(D2D_ERR_INVALID_ARG, std::string(who) + ": handle, io and io->actions are required");
     if (!h->pos) return fail(D2D_ERR_STATE, std::string(who) + ": call d2d_bind_state first");
+    if (io->flags & D2D_STEP_ACTIONS_I16)      // (d2d_step_host_async clears the flag on the device-side io it passes down)
+        return fail(D2D_ERR_INVALID_ARG, std::string(who) + ": D2D_STEP_ACTIONS_I16 applies to d2d_step_host / d2d_step_host_async only");
     if (io->obs && ((uintptr_t)io->obs % 8)) return fail(D2D_ERR_INVALID_ARG, std::string(who) + ": obs must be 8-byte aligned");
     if (io->obs_dyn && ((uintptr_t)io->obs_dyn % 8)) return fail(D2D_ERR_INVALID_ARG, std::string(who) + ": obs_dyn must be 8-byte aligned");
     return D2D_OK;

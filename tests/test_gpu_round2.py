@@ -840,4 +840,10 @@ def test_host_steps_with_int16_actions_match_int32(E):
     env.step_host_wait(1)
     for n in names:
         np.testing.assert_array_equal(ref[0][n], out[n])
+    # the flag belongs to the host entry points: d2d_step (device pointers) refuses it
+    import ctypes as C
+    from gym_d2d_b200 import _lib
+    dev_a = env.sample_actions()
+    io = _lib.D2DStepIO(actions=dev_a.data_ptr(), obs=env.alloc_outputs().obs.data_ptr(), flags=_lib.STEP_ACTIONS_I16)
+    assert env._lib.d2d_step(env._h, C.byref(io), None) == _lib.ERR_INVALID_ARG
     env.close()
