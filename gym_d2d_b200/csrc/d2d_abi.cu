@@ -301,6 +301,10 @@ D2D_API int d2d_create(const d2d_config_t *cfg, const d2d_link_t *links, d2d_han
     // E = 2048 3.38 -> 2.32 us.  Sweeps: profiles/ab_r02_40.log .. ab_r02_46.log
     if (h->use_warp && h->wpb == 2) h->grid_late = 2 * h->num_sms;
     if (h->use_warp && h->wpb == 4) h->grid_late = cfg->num_envs <= 166 * (int64_t)h->num_sms ? 3 * h->num_sms : 0;
+    // (default-ordering steps keep the full grid: two envs per warp on half the blocks - D2D_B200_FRESH_GRID = ceil(E / 8) - speeds up
+    // back-to-back chains of them, E = 4096 10.6 -> 8.3 us, E = 6144 14.4 -> 9.7 us, but costs an isolated step behind a policy
+    // kernel 0.7 - 1 us, E = 2560 9.9 -> 10.9 us per pair: profiles/ab_r02_60.log)
+    if (const char *gf = std::getenv("D2D_B200_FRESH_GRID")) h->grid_fresh = std::max(0, std::atoi(gf));    // A/B
     if (const char *gl = std::getenv("D2D_B200_LATE_GRID")) h->grid_late = std::max(0, std::atoi(gl));      // A/B
     if (const char *gs = std::getenv("D2D_B200_GRID"))      // tests: few blocks, so every block steps many envs
         if (std::atoi(gs) > 0) { h->grid = std::min(h->grid, std::atoi(gs)); h->many.grid = std::min(h->many.grid, std::atoi(gs)); }
@@ -554,7 +558,9 @@ int step_launch(d2d_handle *h, const d2d_step_io_t *io, int T, int mode, void *s
                                h->cfg.reward_fn == D2D_REWARD_SYSTEM_CAPACITY && !io->agent_reward && !h->dRngStep &&
                                h->cfg.num_envs <= std::max<int64_t>(1, (int64_t)0x7fffffff / std::max(6 * h->N, 2 * h->V)) &&
                                !(h->chunk_override > 0 && h->chunk_override < h->cfg.num_envs);
-    const int step_grid = late && h->grid_late > 0 ? std::min(h->grid, h->grid_late) : h->grid;     // (late: one chunk, never a fused launch)
+    // (late: one chunk, never a fused launch; grid_fresh: an A/B knob, 0 by default - see d2d_create)
+    const int step_grid = late && h->grid_late > 0 ? std::min(h->grid, h->grid_late)
+                          : (!stable && mode == MODE_STEP && h->grid_fresh > 0) ? std::min(h->grid, h->grid_fresh) : h->grid;
     const int grid1 = (int)std::min<int64_t>(step_grid, (h->cfg.num_envs + h->envs_per_block - 1) / h->envs_per_block);
     // measured (profiles/README.md): the per-warp hand-off wins as soon as warps step more than one env per launch (E = 6 144,
     // 1.5 envs per warp: 7.6 -> 5.3 us; E = 16 384: 12.4 -> 9.4 us; E = 131 072: 69.5 -> 65.9 us) and loses at exactly one

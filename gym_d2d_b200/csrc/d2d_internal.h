@@ -90,6 +90,7 @@ struct d2d_handle {
     uintptr_t prev_out[6][2] = {};
     bool prev_out_valid = false;
     bool late_wait_on = true;      // D2D_B200_LATE_WAIT=0 switches the late wait off (tests, A/B)
+    int grid_fresh = 0;            // warp kernel: blocks of a default-ordering step (0 = the full grid; D2D_B200_FRESH_GRID, A/B only)
     int grid_late = 0;             // warp kernel: blocks of a late-wait step (0 = the full grid).  Under the late wait consecutive steps overlap
                                    // for as long as the SMs have room for both: a launch that leaves the larger part of the block slots free
                                    // lets its successor's blocks start while its own are still running (d2d_abi.cu)
