@@ -45,6 +45,12 @@ def test_struct_layouts_match_header(tmp_path):
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
         for fname, _ in cls._fields_:
             lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    consts = {'D2D_STEP_INPUTS_STABLE': _lib.STEP_INPUTS_STABLE, 'D2D_STEP_ACTIONS_I16': _lib.STEP_ACTIONS_I16,
+              'D2D_OUT_OBS': _lib.OUT_OBS, 'D2D_OUT_CAPACITY': _lib.OUT_CAPACITY, 'D2D_OUT_REWARD': _lib.OUT_REWARD, 'D2D_OUT_DONE': _lib.OUT_DONE,
+              'D2D_OUT_RATE': _lib.OUT_RATE, 'D2D_OUT_RB': _lib.OUT_RB, 'D2D_OUT_TX_PWR': _lib.OUT_TX_PWR,
+              'D2D_OUT_AGENT_REWARD': _lib.OUT_AGENT_REWARD, 'D2D_OUT_OBS_DYN': _lib.OUT_OBS_DYN}
+    for cname in consts:                                      # flag / mask constants of the binding against the header's
+        lines.append(f'  printf("{cname} %d\\n", (int){cname});')
     lines += ['  printf("abi %d\\n", D2D_ABI_VERSION);', '  return 0;', '}']
     src = tmp_path / 'layout.c'
     src.write_text('\n'.join(lines))
@@ -52,6 +58,8 @@ def test_struct_layouts_match_header(tmp_path):
     got = dict(l.rsplit(' ', 1) for l in subprocess.run([str(tmp_path / 'layout')], check=True, capture_output=True,
                                                         text=True).stdout.strip().splitlines())
     assert int(got['abi']) == _lib.ABI_VERSION
+    for cname, value in consts.items():
+        assert int(got[cname]) == value, cname
     for cname, cls in structs.items():
         assert int(got[cname]) == C.sizeof(cls), cname
         for fname, _ in cls._fields_:
