@@ -981,10 +981,9 @@ D2D_API int d2d_stats_reset(d2d_handle_t *h, void *stream) {
 
 #ifdef D2D_TIMELINE
 // instrumented build only (profiles/timeline.py): copies the stamp table to the host
-D2D_API int d2d_debug_timeline(void *host_out, size_t bytes) {
-    if (bytes > sizeof(d2d_tl_buf)) bytes = sizeof(d2d_tl_buf);
+D2D_API int d2d_debug_timeline(void *host_out, size_t bytes, int wpb) {
     D2D_CUDA(cudaDeviceSynchronize());
-    D2D_CUDA(cudaMemcpyFromSymbol(host_out, d2d_tl_buf, bytes));
+    D2D_CUDA(wpb == 8 ? d2d_warp_timeline_8(host_out, bytes) : wpb == 2 ? d2d_warp_timeline_2(host_out, bytes) : d2d_warp_timeline_4(host_out, bytes));
     return D2D_OK;
 }
 #endif

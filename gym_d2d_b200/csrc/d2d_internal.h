@@ -191,7 +191,8 @@ struct D2DLaunchSel {
     size_t d2d_warp_smem_##WPB(int R);                                                                                  \
     int d2d_warp_plan_##WPB(d2d_handle *h, size_t smem);                                                                \
     cudaError_t d2d_warp_launch_##WPB(const d2d_handle *h, const D2DParams &P, int grid, const D2DLaunchSel &sel, cudaStream_t st, bool pdl); \
-    cudaError_t d2d_warp_tables_##WPB(const double *pwr_lin_d);
+    cudaError_t d2d_warp_tables_##WPB(const double *pwr_lin_d);                                                         \
+    cudaError_t d2d_warp_timeline_##WPB(void *host_out, size_t bytes);      /* instrumented builds only (-DD2D_TIMELINE) */
 D2D_DECLARE_WARP_TU(2)
 D2D_DECLARE_WARP_TU(4)
 D2D_DECLARE_WARP_TU(8)

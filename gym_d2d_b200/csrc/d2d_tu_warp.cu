@@ -69,3 +69,11 @@ cudaError_t D2D_CAT(d2d_warp_launch_, D2D_TU_WPB)(const d2d_handle *h, const D2D
 cudaError_t D2D_CAT(d2d_warp_tables_, D2D_TU_WPB)(const double *pwr_lin_d) {
     return cudaMemcpyToSymbol(d2d_pwr_lin_c, pwr_lin_d, sizeof(double) * D2D_MAX_PWR_LEVELS);
 }
+
+#ifdef D2D_TIMELINE
+// instrumented build (profiles/timeline.py): the stamp table is a __device__ variable of d2d_common.cuh, so every translation unit
+// has its own copy - the one this shape's kernels write is read here
+cudaError_t D2D_CAT(d2d_warp_timeline_, D2D_TU_WPB)(void *host_out, size_t bytes) {
+    return cudaMemcpyFromSymbol(host_out, d2d_tl_buf, bytes < sizeof(d2d_tl_buf) ? bytes : sizeof(d2d_tl_buf));
+}
+#endif

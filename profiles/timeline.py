@@ -27,11 +27,11 @@ outs = [env.alloc_outputs() for _ in range(RING)]
 lib = _lib.load()
 if not hasattr(lib, 'd2d_debug_timeline'):
     raise SystemExit('not an instrumented build: set D2D_B200_LIB to a -DD2D_TIMELINE build of libd2d_b200')
-lib.d2d_debug_timeline.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+lib.d2d_debug_timeline.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
 for a, o in zip(acts, outs):
-    env.step(a, out=o)
+    env.step(a, out=o, inputs_stable=True)
 first_slot = env.launch_count % SLOTS          # the graph's nodes keep the slots they were captured with
-g = env.capture_steps(acts, outs)
+g = env.capture_steps(acts, outs, inputs_stable=True)      # the bench's launch mode: flagged steps over a ring of output sets
 for _ in range(5):
     g.replay()
 torch.cuda.synchronize()
@@ -44,11 +44,15 @@ torch.cuda.synchronize()
 print(f'E={E}: {s.elapsed_time(t) * 1e3 / (20 * RING):.2f} us/step (instrumented build)  geom={env.step_geometry()}')
 
 buf = np.zeros((SLOTS, WARPS, 6), dtype=np.uint64)
-rc = lib.d2d_debug_timeline(buf.ctypes.data_as(ctypes.c_void_p), buf.nbytes)
-assert rc == 0
 geom = env.step_geometry()
+rc = lib.d2d_debug_timeline(buf.ctypes.data_as(ctypes.c_void_p), buf.nbytes, geom['block'] // 32)      # (one stamp table per warps-per-block shape)
+assert rc == 0
 nw = min(WARPS, geom['grid'] * geom['block'] // 32)
 order = [(first_slot + k) % SLOTS for k in range(RING)]
+# a late-wait step runs on fewer blocks than step_geometry reports, and the table keeps older launches' stamps: count the warps of the
+# last launch that stamped during the last replay (within 1 ms of the replay's first stamp)
+t_cut = int(buf[order[0], 0, 0]) - 1_000_000
+nw = int((buf[order[-1], :nw, 0].astype(np.int64) >= t_cut).sum()) or nw
 rec = buf[order, :nw].astype(np.int64)              # [launch][warp][g0, c0, c1, c2, c3, smid]
 g0, c0, c1, c2, c3, smid = (rec[..., i] for i in range(6))
 # clock64 is per SM: bring every SM onto the globaltimer axis with one offset per SM (SM clock = 1.965 GHz under load)
