@@ -259,3 +259,37 @@ def test_shard_range_partitions_the_batch():
         for (f0, c0), (f1, _c1) in zip(spans, spans[1:]):
             assert f0 + c0 == f1
         assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+def test_dict_views_follow_the_reference_layout():
+    """D2DEnv's dict building (cached index tables, one gather) against a per-key restatement of envs/obs_fn.py:43-53 (own 6-tuple, then
+    every other present link's in the action dict's order), envs/d2d_env.py:103-116 (info) and simulator.py:77-87 (state keys) - on
+    synthetic host arrays, no GPU: a full agent set, a shuffled subset, and the first set again (served from the cache)."""
+    from gym_d2d_b200.d2d_env import D2DEnv
+    rng = np.random.default_rng(3)
+    N = 12
+    env = object.__new__(D2DEnv)
+    keys_all = [f'cue{i:02d}:mbs' for i in range(5)] + [f'due{2 * i:02d}:due{2 * i + 1:02d}' for i in range(7)]
+    env._link_index = {k: i for i, k in enumerate(keys_all)}
+    env._views = {}
+    env._host = {'obs': rng.normal(size=(1, N, 6)).astype(np.float32), 'rate_bps': rng.random((1, N)).astype(np.float32),
+                 'capacity_mbps': rng.random((1, N)).astype(np.float32), 'rb': rng.integers(0, 25, (1, N)).astype(np.int16),
+                 'tx_pwr_dbm': rng.integers(0, 24, (1, N)).astype(np.int16)}
+    table = env._host['obs'][0].astype(np.float64)
+    for keys in (keys_all, [keys_all[i] for i in rng.permutation(N)[:7]], keys_all):
+        obs, state, acts = env._obs_dict(keys), env._state(keys), env._actions_view(keys)
+        assert list(obs) == keys and list(acts) == keys
+        rows = [env._link_index[k] for k in keys]
+        for pos, k in enumerate(keys):
+            expect = np.concatenate([table[rows[pos]]] + [table[r] for q, r in enumerate(rows) if q != pos])
+            np.testing.assert_array_equal(obs[k], expect)
+            assert obs[k].dtype == np.float64 and obs[k].shape == (6 * len(keys),)
+            pair = tuple(k.split(':'))
+            assert state['sinrs_db'][pair] == float(env._host['obs'][0, rows[pos], 4]) and isinstance(state['sinrs_db'][pair], float)
+            assert state['snrs_db'][pair] == float(env._host['obs'][0, rows[pos], 5])
+            assert state['rate_bps'][pair] == float(env._host['rate_bps'][0, rows[pos]])
+            assert state['capacity_mbps'][pair] == float(env._host['capacity_mbps'][0, rows[pos]])
+            assert acts[k] == (int(env._host['rb'][0, rows[pos]]), int(env._host['tx_pwr_dbm'][0, rows[pos]]))
+            assert all(isinstance(v, int) for v in acts[k])
+        assert list(state['sinrs_db']) == [tuple(k.split(':')) for k in keys]
+    assert len(env._views) == 2
